@@ -1,0 +1,197 @@
+/*
+ * seekr_b200.h -- C ABI of libseekr_b200.so, the B200 (sm_100a) implementation of SEEKR's hot path.
+ *
+ * The reference (CalabreseLab/seekr 2.0.2) is pure Python and has no FFI of its own; its
+ * boundary for this path is the Python API.  Each entry point below names the reference
+ * lines it replaces; the modules under seekr_b200/ bind them with ctypes and re-create that Python API
+ * on top (INTEGRATION.md shows the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - every function returns an int status (SKR_OK == 0); skr_last_error() gives the text of
+ *     the last failure on the calling thread;
+ *   - plain pointers and sizes only; "d_" pointers are device memory owned by the caller
+ *     (the Python layer allocates them with torch), host pointers are plain host memory;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); all device entry
+ *     points are asynchronous on it and never synchronise;
+ *   - the current CUDA device must be the one that owns the buffers;
+ *   - matrices are row-major; `ld` is the row pitch in elements.
+ */
+#ifndef SEEKR_B200_H
+#define SEEKR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SKR_ABI_VERSION 1
+
+enum {
+    SKR_OK = 0,
+    SKR_ERR_ARG = 1,           /* bad argument (unsupported k, misaligned pointer, ...) */
+    SKR_ERR_CUDA = 2,          /* a CUDA call failed; skr_last_error() has the CUDA message */
+    SKR_ERR_IO = 3,            /* cannot open / read the FASTA file */
+    SKR_ERR_NOMEM = 4,
+    SKR_ERR_FASTA_BLANK = 5,   /* blank line: the reference raises IndexError (fasta_reader.py:53) */
+    SKR_ERR_FASTA_HEADER = 6,  /* header without a sequence: AssertionError (fasta_reader.py:58) */
+};
+
+const char* skr_last_error(void);
+int skr_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Host ingest: FASTA text -> 2-bit codes + invalid mask   (replaces seekr/fasta_reader.py:41-78)
+ *
+ * Packed layout ("blocks" of 64 bases; every record starts on a block boundary):
+ *   codes : 4 x uint32 per block, base p of a record in word p/16 at bits [30-2*(p%16), +2),
+ *           i.e. earlier bases in higher bits, so a k-mer read as an integer has its first
+ *           letter most significant like the reference's column order (kmer_counts.py:121-122)
+ *   mask  : 2 x uint32 per block, base p in word p/32 at bit 31-(p%32); 1 = letter outside the
+ *           alphabet, or padding past the end of the record (its code is 0)
+ *   block_offsets[m+1] : first block of each record; lengths[m] : bases per record
+ * One extra all-invalid block follows the last record so kernels may read one word ahead.
+ * `lut[256]` maps a byte of the *upper-cased* sequence to its digit 0..3 or 255 (not in the
+ * alphabet); the packer upper-cases ASCII letters itself, as Reader does (fasta_reader.py:55,62).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct SkrPacked SkrPacked;
+
+/* Parse FASTA text held in memory.  Line breaks are \n, \r\n or \r (text-mode open); lines are
+ * stripped of leading/trailing ASCII whitespace; a line whose first character is '>' starts a
+ * record.  nthreads <= 0 picks hardware_concurrency.  pinned != 0 allocates the packed arrays
+ * with cudaHostAlloc (from a reusable pool) so they can be streamed to the GPU asynchronously. */
+int skr_pack_fasta_buffer(const void* text, size_t nbytes, const uint8_t* lut, int nthreads, int pinned,
+                          SkrPacked** out);
+int skr_pack_fasta_file(const char* path, const uint8_t* lut, int nthreads, int pinned, SkrPacked** out);
+/* Already-joined sequences (BasicCounter.seqs assigned by hand, occurrences(row, seq)):
+ * letters = concatenated bytes, offs[m+1]. */
+int skr_pack_sequences(const void* letters, const int64_t* offs, int64_t m, const uint8_t* lut, int nthreads,
+                       int pinned, SkrPacked** out);
+void skr_packed_free(SkrPacked* p);
+
+int64_t skr_packed_num_records(const SkrPacked* p);
+int64_t skr_packed_num_blocks(const SkrPacked* p);  /* including the trailing pad block */
+int64_t skr_packed_total_bases(const SkrPacked* p);
+const uint32_t* skr_packed_codes(const SkrPacked* p);          /* 4 * num_blocks words */
+const uint32_t* skr_packed_mask(const SkrPacked* p);           /* 2 * num_blocks words */
+const uint64_t* skr_packed_block_offsets(const SkrPacked* p);  /* m + 1 */
+const uint32_t* skr_packed_lengths(const SkrPacked* p);        /* m */
+/* byte spans into the source text, 2 per record: (offset, length) of the stripped header line
+ * (Reader.get_headers, fasta_reader.py:75-78) and of the record body (first to last sequence line) */
+const uint64_t* skr_packed_header_spans(const SkrPacked* p);
+const uint64_t* skr_packed_body_spans(const SkrPacked* p);
+/* the four arrays live in one contiguous host slab (codes first), so one copy moves them all */
+const void* skr_packed_slab(const SkrPacked* p);
+size_t skr_packed_slab_bytes(const SkrPacked* p);
+/* 1-based line number of the offending line after SKR_ERR_FASTA_BLANK / _HEADER (0 otherwise) */
+int64_t skr_pack_error_line(void);
+
+/* ------------------------------------------------------------------------------------------
+ * k-mer counting with fused normalisation   (replaces seekr/kmer_counts.py:140-151, 189-209)
+ * ------------------------------------------------------------------------------------------ */
+
+/* Device cell for the matrix-wide minimum Log2.post needs (kmer_counts.py:208). */
+typedef struct {
+    uint32_t min_ordered; /* order-preserving encoding of the smallest non-NaN value seen */
+    uint32_t nan_seen;    /* non-zero once any NaN was seen: np.min propagates NaN */
+} SkrMinCell;
+
+int skr_min_reset(SkrMinCell* d_cell, void* stream);
+
+/* One row per record: overlapping k-mer histogram, scaled to counts per kb exactly as the
+ * reference does (c-fold binary64 sum of 1000/(L-k+1), rounded once), then optionally
+ * log2(x+1) [log2_pre], -mean, /std.  d_mean/d_std may be NULL (step skipped); vec_is_f64
+ * says whether they hold doubles (numpy then computes in binary64 and rounds) or floats.
+ * out_is_f64 != 0 writes doubles (raw counts only: occurrences() on a float64 row).
+ * d_min, when given, receives the running minimum / NaN flag of everything written.
+ * Records with L < k give a zero-count row; the caller must reject L == k-1 beforehand
+ * (ZeroDivisionError in the reference).  1 <= k <= 8. */
+int skr_count(const uint32_t* d_codes, const uint32_t* d_mask, const uint64_t* d_block_offsets,
+              const uint32_t* d_lengths, int64_t m, int k, int log2_pre, const void* d_mean, const void* d_std,
+              int vec_is_f64, void* d_out, int out_is_f64, int64_t ld_out, SkrMinCell* d_min, void* stream);
+
+/* a = log2(a + 1)                                   (BasicCounter.log2_norm, kmer_counts.py:189-192) */
+int skr_log2_norm(float* d_a, int64_t m, int64_t cols, int64_t ld, void* stream);
+/* a = log2((a + |min|) + 1), min read from the device cell; NaN min -> all NaN   (kmer_counts.py:207-209) */
+int skr_post_log2(float* d_a, int64_t m, int64_t cols, int64_t ld, const SkrMinCell* d_min, void* stream);
+/* a -= vec (center with a supplied vector, kmer_counts.py:169);  a /= vec (standardize, :175).
+ * Both update d_min (optional) with what they write. */
+int skr_sub_vec(float* d_a, int64_t m, int64_t cols, int64_t ld, const void* d_vec, int vec_is_f64,
+                SkrMinCell* d_min, void* stream);
+int skr_div_vec(float* d_a, int64_t m, int64_t cols, int64_t ld, const void* d_vec, int vec_is_f64,
+                SkrMinCell* d_min, void* stream);
+/* running minimum / NaN flag of an existing matrix */
+int skr_min_scan(const float* d_a, int64_t m, int64_t cols, int64_t ld, SkrMinCell* d_min, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Column statistics for mean=True / std=True and seekr_norm_vectors
+ * (replaces np.mean / np.std(axis=0) at seekr/kmer_counts.py:168,174)
+ *
+ * Order-exact passes: numpy reduces axis 0 row after row in fp32, so each column is summed
+ * sequentially in row order with plain fp32 adds; d_acc[cols] carries the running sums in and
+ * out, which lets row shards on several GPUs be chained (rank r continues from rank r-1).
+ * ------------------------------------------------------------------------------------------ */
+enum {
+    SKR_COLPASS_SUM = 0,    /* acc += a[i][j] */
+    SKR_COLPASS_CENTER = 1, /* a[i][j] -= vec[j] (in place), then acc += a[i][j] */
+    SKR_COLPASS_SQDEV = 2,  /* acc += (a[i][j] - vec[j])^2 */
+};
+int skr_col_pass(int kind, float* d_a, int64_t m, int64_t cols, int64_t ld, const void* d_vec, int vec_is_f64,
+                 float* d_acc, void* stream);
+/* mean[j] = (float)((double)acc[j] / rows);  std[j] = sqrtf((float)((double)acc[j] / rows)) */
+int skr_col_finish(const float* d_acc, int64_t cols, int64_t total_rows, int take_sqrt, float* d_out, void* stream);
+
+/* Scalable passes for sharded runs: per-column binary64 partial sums computed row-parallel
+ * (to be summed across ranks with one all-reduce), kinds as above except CENTER does not
+ * write.  More accurate than the reference, not bit-identical to it. */
+int skr_col_partial_f64(int kind, const float* d_a, int64_t m, int64_t cols, int64_t ld, const void* d_vec,
+                        int vec_is_f64, double* d_acc, void* stream);
+int skr_col_finish_f64(const double* d_acc, int64_t cols, int64_t total_rows, int take_sqrt, float* d_out,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Pearson   (replaces seekr/pearson.py:32-44)
+ *
+ * skr_pearson_prepare row-standardises (mean, std ddof=0; pearson.py:35-38) and splits every
+ * value into two fp16 planes hi + lo (22 significant bits) after scaling the row by a power of
+ * two; skr_pearson_gemm forms hi*hi' + hi*lo' + lo*hi' with tcgen05 MMAs (fp32 accumulation in
+ * TMEM), un-scales and multiplies by alpha (= 1/K, pearson.py:41).
+ * Planes are [rows_padded][k_padded] fp16, rows_padded % 128 == 0, k_padded % 64 == 0, zero filled.
+ * ------------------------------------------------------------------------------------------ */
+int64_t skr_pearson_rows_padded(int64_t rows);
+int64_t skr_pearson_k_padded(int64_t K);
+int skr_pearson_prepare(const void* d_a, int a_is_f64, int64_t rows, int64_t K, int64_t ld, int row_standardize,
+                        uint16_t* d_hi, uint16_t* d_lo, float* d_row_scale, void* stream);
+int skr_pearson_gemm(const uint16_t* d_a_hi, const uint16_t* d_a_lo, const float* d_a_scale, int64_t m,
+                     const uint16_t* d_b_hi, const uint16_t* d_b_lo, const float* d_b_scale, int64_t n, int64_t K,
+                     double alpha, void* d_c, int c_is_f64, int64_t ldc, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Host <-> device plumbing used by the Python layer (thin wrappers; no reference counterpart)
+ * ------------------------------------------------------------------------------------------ */
+int skr_host_alloc(size_t bytes, void** out); /* pinned host memory from the library's pool */
+void skr_host_free(void* p);                  /* returns it to the pool */
+void skr_host_pool_trim(void);                /* releases every pooled slab */
+int skr_copy_h2d(void* d_dst, const void* h_src, size_t bytes, void* stream);
+int skr_copy_d2h(void* h_dst, const void* d_src, size_t bytes, void* stream);
+/* rows x row_bytes with different pitches on either side */
+int skr_copy_d2h_2d(void* h_dst, size_t h_pitch, const void* d_src, size_t d_pitch, size_t row_bytes, size_t rows,
+                    void* stream);
+int skr_copy_h2d_2d(void* d_dst, size_t d_pitch, const void* h_src, size_t h_pitch, size_t row_bytes, size_t rows,
+                    void* stream);
+int skr_stream_sync(void* stream);
+int skr_device_count(int* out);
+
+/* number of kernels launched by this library on the calling thread since the last reset
+ * (bench.py reports it as gpu_launches) */
+int64_t skr_launch_count(int reset);
+
+/* Host-side evaluation of the same binade-jumping routine the count kernel uses for the
+ * c-fold binary64 sum (unit-tested against the literal loop on the CPU). */
+double skr_chain_sum_host(double increment, uint32_t count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEEKR_B200_H */

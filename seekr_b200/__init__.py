@@ -8,3 +8,21 @@ device is missing.
 """
 
 from .__version__ import __version__  # noqa: F401
+
+
+def install_as_seekr():
+    """Make ``import seekr.kmer_counts`` / ``seekr.pearson`` / ... resolve to this package, so code
+    written against the reference (its L3 consumers, its tests) runs on the GPU path unchanged."""
+    import importlib
+    import sys
+    import types
+
+    pkg = types.ModuleType("seekr")
+    pkg.__path__ = []
+    pkg.__version__ = __version__
+    sys.modules["seekr"] = pkg
+    for name in ("kmer_counts", "pearson", "fasta_reader", "console_scripts", "my_tqdm"):
+        mod = importlib.import_module("seekr_b200." + name)
+        sys.modules["seekr." + name] = mod
+        setattr(pkg, name, mod)
+    return pkg

@@ -1,0 +1,125 @@
+"""ctypes binding of libseekr_b200.so (the C ABI declared in include/seekr_b200.h).
+
+The library is built in-tree by ``seekr_b200/csrc/Makefile`` (``python -m seekr_b200.build`` or
+``__graft_entry__.build()``).  There is no fallback: if the shared object is missing, or a numeric
+entry point is used without a CUDA device, an exception is raised.
+"""
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libseekr_b200.so")
+
+SKR_OK = 0
+SKR_ERR_ARG = 1
+SKR_ERR_CUDA = 2
+SKR_ERR_IO = 3
+SKR_ERR_NOMEM = 4
+SKR_ERR_FASTA_BLANK = 5
+SKR_ERR_FASTA_HEADER = 6
+
+COLPASS_SUM = 0
+COLPASS_CENTER = 1
+COLPASS_SQDEV = 2
+
+_vp = ctypes.c_void_p
+_i64 = ctypes.c_int64
+_int = ctypes.c_int
+_sz = ctypes.c_size_t
+_dbl = ctypes.c_double
+
+# name -> (restype, argtypes); kept in one table so tests can check it against the header
+SIGNATURES = {
+    "skr_last_error": (ctypes.c_char_p, []),
+    "skr_abi_version": (_int, []),
+    "skr_pack_fasta_buffer": (_int, [_vp, _sz, _vp, _int, _int, ctypes.POINTER(_vp)]),
+    "skr_pack_fasta_file": (_int, [ctypes.c_char_p, _vp, _int, _int, ctypes.POINTER(_vp)]),
+    "skr_pack_sequences": (_int, [_vp, _vp, _i64, _vp, _int, _int, ctypes.POINTER(_vp)]),
+    "skr_packed_free": (None, [_vp]),
+    "skr_packed_num_records": (_i64, [_vp]),
+    "skr_packed_num_blocks": (_i64, [_vp]),
+    "skr_packed_total_bases": (_i64, [_vp]),
+    "skr_packed_codes": (_vp, [_vp]),
+    "skr_packed_mask": (_vp, [_vp]),
+    "skr_packed_block_offsets": (_vp, [_vp]),
+    "skr_packed_lengths": (_vp, [_vp]),
+    "skr_packed_header_spans": (_vp, [_vp]),
+    "skr_packed_body_spans": (_vp, [_vp]),
+    "skr_packed_slab": (_vp, [_vp]),
+    "skr_packed_slab_bytes": (_sz, [_vp]),
+    "skr_pack_error_line": (_i64, []),
+    "skr_min_reset": (_int, [_vp, _vp]),
+    "skr_count": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _int, _vp, _vp, _int, _vp, _int, _i64, _vp, _vp]),
+    "skr_log2_norm": (_int, [_vp, _i64, _i64, _i64, _vp]),
+    "skr_post_log2": (_int, [_vp, _i64, _i64, _i64, _vp, _vp]),
+    "skr_sub_vec": (_int, [_vp, _i64, _i64, _i64, _vp, _int, _vp, _vp]),
+    "skr_div_vec": (_int, [_vp, _i64, _i64, _i64, _vp, _int, _vp, _vp]),
+    "skr_min_scan": (_int, [_vp, _i64, _i64, _i64, _vp, _vp]),
+    "skr_col_pass": (_int, [_int, _vp, _i64, _i64, _i64, _vp, _int, _vp, _vp]),
+    "skr_col_finish": (_int, [_vp, _i64, _i64, _int, _vp, _vp]),
+    "skr_col_partial_f64": (_int, [_int, _vp, _i64, _i64, _i64, _vp, _int, _vp, _vp]),
+    "skr_col_finish_f64": (_int, [_vp, _i64, _i64, _int, _vp, _vp]),
+    "skr_pearson_rows_padded": (_i64, [_i64]),
+    "skr_pearson_k_padded": (_i64, [_i64]),
+    "skr_pearson_prepare": (_int, [_vp, _int, _i64, _i64, _i64, _int, _vp, _vp, _vp, _vp]),
+    "skr_pearson_gemm": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _dbl, _vp, _int, _i64, _vp]),
+    "skr_host_alloc": (_int, [_sz, ctypes.POINTER(_vp)]),
+    "skr_host_free": (None, [_vp]),
+    "skr_host_pool_trim": (None, []),
+    "skr_copy_h2d": (_int, [_vp, _vp, _sz, _vp]),
+    "skr_copy_d2h": (_int, [_vp, _vp, _sz, _vp]),
+    "skr_copy_d2h_2d": (_int, [_vp, _sz, _vp, _sz, _sz, _sz, _vp]),
+    "skr_copy_h2d_2d": (_int, [_vp, _sz, _vp, _sz, _sz, _sz, _vp]),
+    "skr_stream_sync": (_int, [_vp]),
+    "skr_device_count": (_int, [ctypes.POINTER(_int)]),
+    "skr_launch_count": (_i64, [_int]),
+    "skr_chain_sum_host": (_dbl, [_dbl, ctypes.c_uint32]),
+}
+
+_lib = None
+
+
+class SeekrB200Error(RuntimeError):
+    """A C-ABI call failed; the message is skr_last_error()."""
+
+
+def load():
+    """Load libseekr_b200.so (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "seekr_b200: %s is missing. Build it with `python -m seekr_b200.build` "
+                "(nvcc, sm_100a); there is no CPU fallback." % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        if lib.skr_abi_version() != 1:
+            raise RuntimeError("seekr_b200: ABI version mismatch, rebuild the library")
+        _lib = lib
+    return _lib
+
+
+def last_error():
+    return load().skr_last_error().decode("utf-8", "replace")
+
+
+def check(rc):
+    """Map a non-zero status to the exception the reference would raise for the same condition."""
+    if rc == SKR_OK:
+        return
+    msg = last_error()
+    if rc == SKR_ERR_FASTA_BLANK:
+        raise IndexError("string index out of range")            # fasta_reader.py:53 on a blank line
+    if rc == SKR_ERR_FASTA_HEADER:
+        raise AssertionError(msg)                                 # fasta_reader.py:58
+    if rc == SKR_ERR_IO:
+        raise FileNotFoundError(msg)
+    if rc == SKR_ERR_NOMEM:
+        raise MemoryError(msg)
+    if rc == SKR_ERR_ARG:
+        raise ValueError(msg)
+    raise SeekrB200Error(msg)

@@ -1,0 +1,448 @@
+// K1: sliding-window k-mer counting with a fused normalisation epilogue, plus the element-wise
+// kernels of the get_counts() tail.  Replaces seekr/kmer_counts.py:140-151 and :189-209.
+//
+// One CTA owns one record at a time (records are handed out through a device counter, so a
+// long transcript does not stall a fixed partner set).  The record's overlapping k-mers are
+// counted into a shared-memory histogram of 16-bit sub-counters (two bins per 32-bit word, one
+// shared atomicAdd per window, consecutive equal k-mers merged per thread).  A record with more
+// than 65 520 windows is processed in segments whose partial histograms are spilled into a
+// per-CTA 32-bit row in global memory, so no sub-counter can overflow.  The epilogue turns the
+// integer count c of every bin into the reference's float32 value: the c-fold binary64 sum of
+// 1000/(L-k+1) (kmer_counts.py:144-150 adds the increment once per window in Python floats),
+// rounded once, then log2(x+1) / -mean / /std as requested, and writes the dense output row
+// with 128-bit stores.  HBM traffic per record is its packed codes + mask + one output row.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <mutex>
+#include <unordered_map>
+
+#include "skr_common.h"
+#include "skr_device.cuh"
+
+namespace {
+
+constexpr int kSegChunks = 4095;  // 4095 chunks x 16 windows = 65 520 < 65 536 increments per segment
+
+template <int K>
+struct CountCfg {
+    static constexpr int kBins = 1 << (2 * K);
+    static constexpr int kWords = kBins / 2;  // 16-bit sub-counters, two per word
+    static constexpr int kThreads = K <= 4 ? 64 : (K == 5 ? 128 : (K <= 7 ? 256 : 1024));
+    static constexpr size_t kSmem = (size_t)kWords * 4;
+};
+
+struct CountParams {
+    const uint32_t* codes;
+    const uint32_t* mask;
+    const uint64_t* blk_off;
+    const uint32_t* len;
+    long long m;
+    int log2_pre;
+    const void* mean;
+    const void* std_;
+    void* out;
+    long long ld_out;
+    SkrMinCell* min_cell;
+    unsigned int* work_counter;
+    uint32_t* spill;  // [gridDim.x][kBins] 32-bit counts for records longer than one segment
+};
+
+template <int K, bool kVecF64, typename OutT>
+__global__ void __launch_bounds__(CountCfg<K>::kThreads) count_kernel(const CountParams p) {
+    using Cfg = CountCfg<K>;
+    constexpr int T = Cfg::kThreads;
+    extern __shared__ __align__(16) uint32_t hist[];
+    __shared__ long long s_rec;
+    __shared__ float s_wmin[T / 32];
+    __shared__ int s_wnan[T / 32];
+
+    const int tid = threadIdx.x;
+    float tmin = INFINITY;
+    int tnan = 0;
+    uint32_t* spill = p.spill + (size_t)blockIdx.x * Cfg::kBins;
+
+    for (;;) {
+        if (tid == 0) s_rec = (long long)atomicAdd(p.work_counter, 1u);
+        __syncthreads();  // also orders the previous record's histogram reads before the zeroing below
+        const long long rec = s_rec;
+        if (rec >= p.m) break;
+
+        if constexpr (Cfg::kWords % 4 == 0) {
+            for (int i = tid; i < Cfg::kWords / 4; i += T) reinterpret_cast<uint4*>(hist)[i] = make_uint4(0, 0, 0, 0);
+        } else {
+            for (int i = tid; i < Cfg::kWords; i += T) hist[i] = 0;
+        }
+        __syncthreads();
+
+        const uint32_t L = p.len[rec];
+        const long long nwin = (long long)L - K + 1;  // > 0 or the row is all zero counts (L == k-1 is rejected on the host)
+        const uint64_t b0 = p.blk_off[rec];
+        const uint32_t* __restrict__ cw = p.codes + b0 * 4;
+        const uint32_t* __restrict__ mw = p.mask + b0 * 2;
+        const long long nchunks = nwin > 0 ? (nwin + 15) / 16 : 0;
+        const int nseg = (int)((nchunks + kSegChunks - 1) / kSegChunks);
+
+        for (int seg = 0; seg < (nseg > 0 ? nseg : 1); ++seg) {
+            const long long c_begin = (long long)seg * kSegChunks;
+            const long long c_end = min(nchunks, c_begin + kSegChunks);
+            for (long long c = c_begin + tid; c < c_end; c += T) {
+                const uint64_t x = ((uint64_t)__ldg(cw + c) << 32) | __ldg(cw + c + 1);
+                const uint64_t m64 = ((uint64_t)__ldg(mw + (c >> 1)) << 32) | __ldg(mw + (c >> 1) + 1);
+                // the 16 + K - 1 mask bits of this chunk, first base in the top bit
+                const uint32_t mb = (uint32_t)((m64 << (16 * (int)(c & 1))) >> (64 - (16 + K - 1)));
+                const long long left = nwin - c * 16;
+                const int nv = left < 16 ? (int)left : 16;
+                uint32_t prev = 0xFFFFFFFFu, run = 0;
+                if (mb == 0 && nv == 16) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const uint32_t kmer = (uint32_t)(x >> (64 - 2 * (j + K))) & (Cfg::kBins - 1);
+                        if (kmer == prev) {
+                            ++run;
+                        } else {
+                            if (run) atomicAdd(&hist[prev >> 1], run << ((prev & 1) * 16));
+                            prev = kmer;
+                            run = 1;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const uint32_t kmer = (uint32_t)(x >> (64 - 2 * (j + K))) & (Cfg::kBins - 1);
+                        const uint32_t bad = (mb >> (16 - 1 - j)) & ((1u << K) - 1);
+                        if (j < nv && bad == 0) {
+                            if (kmer == prev) {
+                                ++run;
+                            } else {
+                                if (run) atomicAdd(&hist[prev >> 1], run << ((prev & 1) * 16));
+                                prev = kmer;
+                                run = 1;
+                            }
+                        }
+                    }
+                }
+                if (run) atomicAdd(&hist[prev >> 1], run << ((prev & 1) * 16));
+            }
+            __syncthreads();
+            if (nseg > 1) {
+                // spill this segment's 16-bit partial counts into the CTA's 32-bit row and start over
+                for (int w = tid; w < Cfg::kWords; w += T) {
+                    const uint32_t v = hist[w];
+                    uint32_t lo = v & 0xFFFFu, hi = v >> 16;
+                    if (seg > 0) {
+                        lo += spill[2 * w];
+                        hi += spill[2 * w + 1];
+                    }
+                    spill[2 * w] = lo;
+                    spill[2 * w + 1] = hi;
+                    hist[w] = 0;
+                }
+                __syncthreads();
+            }
+        }
+
+        // ---- epilogue: 4 bins per thread per step ----------------------------------------------
+        const double inc = nwin > 0 ? 1000.0 / (double)nwin : 0.0;
+        OutT* __restrict__ orow = reinterpret_cast<OutT*>(p.out) + (size_t)rec * (size_t)p.ld_out;
+        for (int q = tid; q < Cfg::kBins / 4; q += T) {
+            uint32_t c4[4];
+            if (nseg > 1) {
+                const uint4 v = reinterpret_cast<const uint4*>(spill)[q];
+                c4[0] = v.x; c4[1] = v.y; c4[2] = v.z; c4[3] = v.w;
+            } else {
+                const uint2 v = reinterpret_cast<const uint2*>(hist)[q];
+                c4[0] = v.x & 0xFFFFu; c4[1] = v.x >> 16; c4[2] = v.y & 0xFFFFu; c4[3] = v.y >> 16;
+            }
+            if constexpr (sizeof(OutT) == 8) {
+                double r[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) r[e] = skr::chain_sum(inc, c4[e]);
+                reinterpret_cast<double2*>(orow)[2 * q] = make_double2(r[0], r[1]);
+                reinterpret_cast<double2*>(orow)[2 * q + 1] = make_double2(r[2], r[3]);
+            } else {
+                float r[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float v = __double2float_rn(skr::chain_sum(inc, c4[e]));
+                    if (p.log2_pre) v = log2f(__fadd_rn(v, 1.0f));
+                    r[e] = v;
+                }
+                if (p.mean) {
+                    if constexpr (kVecF64) {
+                        const double* mv = reinterpret_cast<const double*>(p.mean) + 4 * q;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) r[e] = __double2float_rn(__dsub_rn((double)r[e], __ldg(mv + e)));
+                    } else {
+                        const float4 mv = __ldg(reinterpret_cast<const float4*>(p.mean) + q);
+                        r[0] = __fsub_rn(r[0], mv.x); r[1] = __fsub_rn(r[1], mv.y);
+                        r[2] = __fsub_rn(r[2], mv.z); r[3] = __fsub_rn(r[3], mv.w);
+                    }
+                }
+                if (p.std_) {
+                    if constexpr (kVecF64) {
+                        const double* sv = reinterpret_cast<const double*>(p.std_) + 4 * q;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) r[e] = __double2float_rn(__ddiv_rn((double)r[e], __ldg(sv + e)));
+                    } else {
+                        const float4 sv = __ldg(reinterpret_cast<const float4*>(p.std_) + q);
+                        r[0] = __fdiv_rn(r[0], sv.x); r[1] = __fdiv_rn(r[1], sv.y);
+                        r[2] = __fdiv_rn(r[2], sv.z); r[3] = __fdiv_rn(r[3], sv.w);
+                    }
+                }
+                if (p.min_cell) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) skr::min_update(r[e], tmin, tnan);
+                }
+                reinterpret_cast<float4*>(orow)[q] = make_float4(r[0], r[1], r[2], r[3]);
+            }
+        }
+        // the __syncthreads at the top of the loop separates these reads from the next zeroing
+    }
+
+    if (p.min_cell) skr::min_commit<T>(tmin, tnan, s_wmin, s_wnan, p.min_cell);
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-device scratch: work counters (a ring, so launches on different streams do not share one)
+// and the per-CTA spill rows
+// ---------------------------------------------------------------------------------------------
+struct DeviceScratch {
+    unsigned int* counters = nullptr;
+    int next_counter = 0;
+    uint32_t* spill = nullptr;
+    size_t spill_bytes = 0;
+    int num_sms = 0;
+};
+constexpr int kCounterRing = 256;
+std::mutex g_scratch_mu;
+std::unordered_map<int, DeviceScratch> g_scratch;
+
+int get_scratch(int dev, size_t spill_bytes, DeviceScratch** out) {
+    std::lock_guard<std::mutex> lock(g_scratch_mu);
+    DeviceScratch& s = g_scratch[dev];
+    if (!s.counters) {
+        SKR_CUDA_CHECK(cudaMalloc(&s.counters, kCounterRing * sizeof(unsigned int)));
+        SKR_CUDA_CHECK(cudaDeviceGetAttribute(&s.num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    if (s.spill_bytes < spill_bytes) {
+        if (s.spill) SKR_CUDA_CHECK(cudaFree(s.spill));  // synchronises: older launches are done with it
+        s.spill = nullptr;
+        s.spill_bytes = 0;
+        SKR_CUDA_CHECK(cudaMalloc(&s.spill, spill_bytes));
+        s.spill_bytes = spill_bytes;
+    }
+    *out = &s;
+    return SKR_OK;
+}
+
+template <int K, bool kVecF64, typename OutT>
+int launch_count(CountParams p, cudaStream_t stream) {
+    using Cfg = CountCfg<K>;
+    auto kern = count_kernel<K, kVecF64, OutT>;
+    int dev = 0;
+    SKR_CUDA_CHECK(cudaGetDevice(&dev));
+    static thread_local int configured_dev[16] = {0};
+    (void)configured_dev;
+    SKR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem));
+    int per_sm = 0;
+    SKR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Cfg::kThreads, Cfg::kSmem));
+    if (per_sm < 1) return skr::fail(SKR_ERR_CUDA, "count kernel for k=%d does not fit on this device", K);
+    DeviceScratch* sc = nullptr;
+    int sms = 0;
+    SKR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    long long grid = (long long)sms * per_sm;
+    if (grid > p.m) grid = p.m;
+    int rc = get_scratch(dev, (size_t)sms * per_sm * Cfg::kBins * 4, &sc);
+    if (rc != SKR_OK) return rc;
+    {
+        std::lock_guard<std::mutex> lock(g_scratch_mu);
+        p.work_counter = sc->counters + sc->next_counter;
+        sc->next_counter = (sc->next_counter + 1) % kCounterRing;
+    }
+    p.spill = sc->spill;
+    SKR_CUDA_CHECK(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned int), stream));
+    kern<<<(unsigned)grid, Cfg::kThreads, Cfg::kSmem, stream>>>(p);
+    SKR_LAUNCH_CHECK();
+    return SKR_OK;
+}
+
+template <int K>
+int dispatch_count(const CountParams& p, int vec_is_f64, int out_is_f64, cudaStream_t stream) {
+    if (out_is_f64) return launch_count<K, false, double>(p, stream);
+    if (vec_is_f64) return launch_count<K, true, float>(p, stream);
+    return launch_count<K, false, float>(p, stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// element-wise kernels of the get_counts() tail
+// ---------------------------------------------------------------------------------------------
+enum { OP_LOG2 = 0, OP_POST = 1, OP_SUB = 2, OP_DIV = 3, OP_SCAN = 4 };
+
+template <int OP, bool kVecF64>
+__device__ __forceinline__ float ew_apply(float v, const void* vec, long long col, float shift) {
+    if constexpr (OP == OP_LOG2) return log2f(__fadd_rn(v, 1.0f));
+    if constexpr (OP == OP_POST) return log2f(__fadd_rn(__fadd_rn(v, shift), 1.0f));
+    if constexpr (OP == OP_SUB) {
+        if constexpr (kVecF64) return __double2float_rn(__dsub_rn((double)v, __ldg((const double*)vec + col)));
+        else return __fsub_rn(v, __ldg((const float*)vec + col));
+    }
+    if constexpr (OP == OP_DIV) {
+        if constexpr (kVecF64) return __double2float_rn(__ddiv_rn((double)v, __ldg((const double*)vec + col)));
+        else return __fdiv_rn(v, __ldg((const float*)vec + col));
+    }
+    return v;
+}
+
+// Rows are contiguous when ld == cols; the vector path needs cols % 4 == 0 and 16-byte aligned rows.
+template <int OP, bool kVecF64, bool kVec4>
+__global__ void __launch_bounds__(256) ew_kernel(float* a, long long m, long long cols, long long ld, const void* vec,
+                                                 const SkrMinCell* min_in, SkrMinCell* min_out) {
+    __shared__ float s_wmin[8];
+    __shared__ int s_wnan[8];
+    float shift = 0.0f;
+    if constexpr (OP == OP_POST) {
+        // np.abs(np.min(counts)): NaN anywhere makes the shift NaN, hence the whole matrix (kmer_counts.py:208)
+        shift = min_in->nan_seen ? __int_as_float(0x7FC00000) : fabsf(skr::ordered_decode(min_in->min_ordered));
+    }
+    float tmin = INFINITY;
+    int tnan = 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    if constexpr (kVec4) {
+        const long long c4 = cols / 4;
+        const long long total = m * c4;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+            const long long r = i / c4, q = i - r * c4;
+            float4* ptr = reinterpret_cast<float4*>(a + r * ld) + q;
+            float4 v = *ptr;
+            v.x = ew_apply<OP, kVecF64>(v.x, vec, 4 * q + 0, shift);
+            v.y = ew_apply<OP, kVecF64>(v.y, vec, 4 * q + 1, shift);
+            v.z = ew_apply<OP, kVecF64>(v.z, vec, 4 * q + 2, shift);
+            v.w = ew_apply<OP, kVecF64>(v.w, vec, 4 * q + 3, shift);
+            if (min_out) {
+                skr::min_update(v.x, tmin, tnan); skr::min_update(v.y, tmin, tnan);
+                skr::min_update(v.z, tmin, tnan); skr::min_update(v.w, tmin, tnan);
+            }
+            if constexpr (OP != OP_SCAN) *ptr = v;
+        }
+    } else {
+        const long long total = m * cols;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+            const long long r = i / cols, c = i - r * cols;
+            float v = ew_apply<OP, kVecF64>(a[r * ld + c], vec, c, shift);
+            if (min_out) skr::min_update(v, tmin, tnan);
+            if constexpr (OP != OP_SCAN) a[r * ld + c] = v;
+        }
+    }
+    if (min_out) skr::min_commit<256>(tmin, tnan, s_wmin, s_wnan, min_out);
+}
+
+template <int OP>
+int launch_ew(float* a, long long m, long long cols, long long ld, const void* vec, int vec_is_f64,
+              const SkrMinCell* min_in, SkrMinCell* min_out, cudaStream_t stream) {
+    if (m <= 0 || cols <= 0) return SKR_OK;
+    if (!a) return skr::fail(SKR_ERR_ARG, "null matrix");
+    if (ld < cols) return skr::fail(SKR_ERR_ARG, "ld < cols");
+    const bool vec4 = (cols % 4 == 0) && (ld % 4 == 0) && (((uintptr_t)a & 15) == 0);
+    int dev = 0, sms = 0;
+    SKR_CUDA_CHECK(cudaGetDevice(&dev));
+    SKR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const long long work = vec4 ? m * (cols / 4) : m * cols;
+    long long grid = (work + 255) / 256;
+    const long long cap = (long long)sms * 8;  // 8 resident CTAs of 256 threads per SM, grid-stride beyond that
+    if (grid > cap) grid = cap;
+    auto go = [&](auto kern) {
+        kern<<<(unsigned)grid, 256, 0, stream>>>(a, m, cols, ld, vec, min_in, min_out);
+    };
+    if (vec_is_f64) {
+        if (vec4) go(ew_kernel<OP, true, true>); else go(ew_kernel<OP, true, false>);
+    } else {
+        if (vec4) go(ew_kernel<OP, false, true>); else go(ew_kernel<OP, false, false>);
+    }
+    SKR_LAUNCH_CHECK();
+    return SKR_OK;
+}
+
+__global__ void min_reset_kernel(SkrMinCell* cell) {
+    cell->min_ordered = skr::ordered_encode(INFINITY);
+    cell->nan_seen = 0;
+}
+
+}  // namespace
+
+extern "C" int skr_min_reset(SkrMinCell* d_cell, void* stream) {
+    if (!d_cell) return skr::fail(SKR_ERR_ARG, "skr_min_reset: null cell");
+    min_reset_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(d_cell);
+    SKR_LAUNCH_CHECK();
+    return SKR_OK;
+}
+
+extern "C" int skr_count(const uint32_t* d_codes, const uint32_t* d_mask, const uint64_t* d_block_offsets,
+                         const uint32_t* d_lengths, int64_t m, int k, int log2_pre, const void* d_mean,
+                         const void* d_std, int vec_is_f64, void* d_out, int out_is_f64, int64_t ld_out,
+                         SkrMinCell* d_min, void* stream) {
+    if (m == 0) return SKR_OK;
+    if (!d_codes || !d_mask || !d_block_offsets || !d_lengths || !d_out || m < 0)
+        return skr::fail(SKR_ERR_ARG, "skr_count: null or negative argument");
+    if (k < 1 || k > 8) return skr::fail(SKR_ERR_ARG, "skr_count: k=%d not supported (1 <= k <= 8)", k);
+    const int64_t bins = (int64_t)1 << (2 * k);
+    if (ld_out < bins) return skr::fail(SKR_ERR_ARG, "skr_count: ld_out < 4^k");
+    if (out_is_f64 && (log2_pre || d_mean || d_std || d_min))
+        return skr::fail(SKR_ERR_ARG, "skr_count: float64 output carries raw counts only");
+    const size_t esz = out_is_f64 ? 8 : 4;
+    if (((uintptr_t)d_out & 15) || ((size_t)ld_out * esz) % 16)
+        return skr::fail(SKR_ERR_ARG, "skr_count: output rows must be 16-byte aligned");
+    if ((d_mean && ((uintptr_t)d_mean & 15)) || (d_std && ((uintptr_t)d_std & 15)))
+        return skr::fail(SKR_ERR_ARG, "skr_count: mean/std vectors must be 16-byte aligned");
+    CountParams p{};
+    p.codes = d_codes;
+    p.mask = d_mask;
+    p.blk_off = d_block_offsets;
+    p.len = d_lengths;
+    p.m = m;
+    p.log2_pre = log2_pre;
+    p.mean = d_mean;
+    p.std_ = d_std;
+    p.out = d_out;
+    p.ld_out = ld_out;
+    p.min_cell = d_min;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (k) {
+        case 1: return dispatch_count<1>(p, vec_is_f64, out_is_f64, s);
+        case 2: return dispatch_count<2>(p, vec_is_f64, out_is_f64, s);
+        case 3: return dispatch_count<3>(p, vec_is_f64, out_is_f64, s);
+        case 4: return dispatch_count<4>(p, vec_is_f64, out_is_f64, s);
+        case 5: return dispatch_count<5>(p, vec_is_f64, out_is_f64, s);
+        case 6: return dispatch_count<6>(p, vec_is_f64, out_is_f64, s);
+        case 7: return dispatch_count<7>(p, vec_is_f64, out_is_f64, s);
+        default: return dispatch_count<8>(p, vec_is_f64, out_is_f64, s);
+    }
+}
+
+extern "C" int skr_log2_norm(float* d_a, int64_t m, int64_t cols, int64_t ld, void* stream) {
+    return launch_ew<OP_LOG2>(d_a, m, cols, ld, nullptr, 0, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int skr_post_log2(float* d_a, int64_t m, int64_t cols, int64_t ld, const SkrMinCell* d_min, void* stream) {
+    if (!d_min) return skr::fail(SKR_ERR_ARG, "skr_post_log2: null min cell");
+    return launch_ew<OP_POST>(d_a, m, cols, ld, nullptr, 0, d_min, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int skr_sub_vec(float* d_a, int64_t m, int64_t cols, int64_t ld, const void* d_vec, int vec_is_f64,
+                           SkrMinCell* d_min, void* stream) {
+    if (!d_vec) return skr::fail(SKR_ERR_ARG, "skr_sub_vec: null vector");
+    return launch_ew<OP_SUB>(d_a, m, cols, ld, d_vec, vec_is_f64, nullptr, d_min, (cudaStream_t)stream);
+}
+
+extern "C" int skr_div_vec(float* d_a, int64_t m, int64_t cols, int64_t ld, const void* d_vec, int vec_is_f64,
+                           SkrMinCell* d_min, void* stream) {
+    if (!d_vec) return skr::fail(SKR_ERR_ARG, "skr_div_vec: null vector");
+    return launch_ew<OP_DIV>(d_a, m, cols, ld, d_vec, vec_is_f64, nullptr, d_min, (cudaStream_t)stream);
+}
+
+extern "C" int skr_min_scan(const float* d_a, int64_t m, int64_t cols, int64_t ld, SkrMinCell* d_min, void* stream) {
+    if (!d_min) return skr::fail(SKR_ERR_ARG, "skr_min_scan: null min cell");
+    return launch_ew<OP_SCAN>(const_cast<float*>(d_a), m, cols, ld, nullptr, 0, nullptr, d_min, (cudaStream_t)stream);
+}
+
+extern "C" double skr_chain_sum_host(double increment, uint32_t count) { return skr::chain_sum(increment, count); }

@@ -1,0 +1,565 @@
+// Host FASTA ingest: text -> 2-bit codes + invalid mask in (pinned) host memory.
+//
+// Replaces seekr/fasta_reader.py:41-78 (Reader._read_data, _upper_seq_per_line, get_seqs,
+// get_headers) for the counting path.  Semantics kept from the reference:
+//   * text-mode line splitting: "\n", "\r\n" and a lone "\r" all end a line;
+//   * every line is stripped of leading/trailing whitespace (str.strip: 0x09-0x0D, 0x1C-0x20);
+//   * a stripped line starting with '>' is a header, everything else is sequence, joined per record
+//     and upper-cased; every remaining byte counts as one base (inner blanks included);
+//   * a blank line raises IndexError there (line[0] on an empty string)   -> SKR_ERR_FASTA_BLANK;
+//   * a header directly after a header (except at line 0) trips the assert -> SKR_ERR_FASTA_HEADER;
+//   * the last record may be empty.
+// The packed layout is described in include/seekr_b200.h.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include "skr_common.h"
+
+namespace skr {
+
+std::string& last_error() {
+    thread_local std::string s;
+    return s;
+}
+int64_t& launch_counter() {
+    thread_local int64_t n = 0;
+    return n;
+}
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    last_error() = buf;
+    return code;
+}
+
+}  // namespace skr
+
+extern "C" const char* skr_last_error(void) { return skr::last_error().c_str(); }
+extern "C" int skr_abi_version(void) { return SKR_ABI_VERSION; }
+extern "C" int64_t skr_launch_count(int reset) {
+    int64_t v = skr::launch_counter();
+    if (reset) skr::launch_counter() = 0;
+    return v;
+}
+
+namespace {
+
+thread_local int64_t g_error_line = 0;
+
+// ---------------------------------------------------------------------------------------------
+// slab allocation (pinned slabs are pooled: cudaHostAlloc costs milliseconds per call)
+// ---------------------------------------------------------------------------------------------
+struct Slab {
+    void* ptr = nullptr;
+    size_t cap = 0;
+    bool pinned = false;
+};
+
+std::mutex g_pool_mu;
+std::vector<Slab> g_pool;
+constexpr size_t kPoolMaxSlabs = 8;
+
+int slab_alloc(size_t bytes, bool pinned, Slab* out) {
+    bytes = std::max<size_t>(bytes, 4096);
+    if (pinned) {
+        std::lock_guard<std::mutex> lock(g_pool_mu);
+        int best = -1;
+        for (size_t i = 0; i < g_pool.size(); ++i)
+            if (g_pool[i].cap >= bytes && (best < 0 || g_pool[i].cap < g_pool[best].cap)) best = (int)i;
+        if (best >= 0) {
+            *out = g_pool[best];
+            g_pool.erase(g_pool.begin() + best);
+            return SKR_OK;
+        }
+    }
+    out->pinned = pinned;
+    if (pinned) {
+        size_t cap = bytes + bytes / 8;  // head-room so a slightly larger next input reuses the slab
+        cudaError_t e = cudaHostAlloc(&out->ptr, cap, cudaHostAllocDefault);
+        if (e != cudaSuccess)
+            return skr::fail(SKR_ERR_CUDA, "cudaHostAlloc(%zu) failed: %s", cap, cudaGetErrorString(e));
+        out->cap = cap;
+    } else {
+        if (posix_memalign(&out->ptr, 4096, bytes) != 0) return skr::fail(SKR_ERR_NOMEM, "out of host memory");
+        out->cap = bytes;
+    }
+    return SKR_OK;
+}
+
+void slab_free(Slab& s) {
+    if (!s.ptr) return;
+    if (s.pinned) {
+        std::lock_guard<std::mutex> lock(g_pool_mu);
+        if (g_pool.size() < kPoolMaxSlabs) {
+            g_pool.push_back(s);
+        } else {
+            // drop the smallest pooled slab in favour of this one if it is larger
+            size_t small = 0;
+            for (size_t i = 1; i < g_pool.size(); ++i)
+                if (g_pool[i].cap < g_pool[small].cap) small = i;
+            if (g_pool[small].cap < s.cap) {
+                cudaFreeHost(g_pool[small].ptr);
+                g_pool[small] = s;
+            } else {
+                cudaFreeHost(s.ptr);
+            }
+        }
+    } else {
+        free(s.ptr);
+    }
+    s.ptr = nullptr;
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+std::mutex g_live_mu;
+std::unordered_map<void*, Slab> g_live;  // slabs handed out through skr_host_alloc
+
+}  // namespace
+
+extern "C" int skr_host_alloc(size_t bytes, void** out) {
+    if (!out) return skr::fail(SKR_ERR_ARG, "skr_host_alloc: null out");
+    Slab s;
+    int rc = slab_alloc(bytes, true, &s);
+    if (rc != SKR_OK) return rc;
+    {
+        std::lock_guard<std::mutex> lock(g_live_mu);
+        g_live[s.ptr] = s;
+    }
+    *out = s.ptr;
+    return SKR_OK;
+}
+
+extern "C" void skr_host_free(void* p) {
+    if (!p) return;
+    Slab s;
+    {
+        std::lock_guard<std::mutex> lock(g_live_mu);
+        auto it = g_live.find(p);
+        if (it == g_live.end()) return;
+        s = it->second;
+        g_live.erase(it);
+    }
+    slab_free(s);
+}
+
+extern "C" void skr_host_pool_trim(void) {
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    for (auto& s : g_pool) cudaFreeHost(s.ptr);
+    g_pool.clear();
+}
+
+extern "C" int skr_copy_h2d(void* d_dst, const void* h_src, size_t bytes, void* stream) {
+    if (!bytes) return SKR_OK;
+    SKR_CUDA_CHECK(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return SKR_OK;
+}
+extern "C" int skr_copy_d2h(void* h_dst, const void* d_src, size_t bytes, void* stream) {
+    if (!bytes) return SKR_OK;
+    SKR_CUDA_CHECK(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return SKR_OK;
+}
+extern "C" int skr_copy_d2h_2d(void* h_dst, size_t h_pitch, const void* d_src, size_t d_pitch, size_t row_bytes,
+                               size_t rows, void* stream) {
+    if (!rows || !row_bytes) return SKR_OK;
+    SKR_CUDA_CHECK(cudaMemcpy2DAsync(h_dst, h_pitch, d_src, d_pitch, row_bytes, rows, cudaMemcpyDeviceToHost,
+                                     (cudaStream_t)stream));
+    return SKR_OK;
+}
+extern "C" int skr_copy_h2d_2d(void* d_dst, size_t d_pitch, const void* h_src, size_t h_pitch, size_t row_bytes,
+                               size_t rows, void* stream) {
+    if (!rows || !row_bytes) return SKR_OK;
+    SKR_CUDA_CHECK(cudaMemcpy2DAsync(d_dst, d_pitch, h_src, h_pitch, row_bytes, rows, cudaMemcpyHostToDevice,
+                                     (cudaStream_t)stream));
+    return SKR_OK;
+}
+extern "C" int skr_stream_sync(void* stream) {
+    SKR_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+    return SKR_OK;
+}
+extern "C" int skr_device_count(int* out) {
+    if (!out) return skr::fail(SKR_ERR_ARG, "null out");
+    SKR_CUDA_CHECK(cudaGetDeviceCount(out));
+    return SKR_OK;
+}
+
+struct SkrPacked {
+    int64_t m = 0;
+    int64_t nblocks = 0;  // including the trailing pad block
+    int64_t total_bases = 0;
+    Slab slab;
+    size_t slab_bytes = 0;
+    uint32_t* codes = nullptr;
+    uint32_t* mask = nullptr;
+    uint64_t* blk_off = nullptr;
+    uint32_t* len = nullptr;
+    std::vector<uint64_t> header_spans;
+    std::vector<uint64_t> body_spans;
+};
+
+namespace {
+
+inline bool is_space(unsigned char c) { return (c >= 0x09 && c <= 0x0D) || (c >= 0x1C && c <= 0x20); }
+
+// Calls fn(line_begin, line_end) for every line that STARTS in [from, to); a line may extend past
+// `to` (never past `end`).  Line breaks: \n, \r\n, \r (text-mode "universal newlines").  fn returns
+// false to stop.  Returns the start of the first line not visited, or nullptr when stopped.
+template <class Fn>
+const char* for_each_line(const char* base, const char* from, const char* to, const char* end, Fn&& fn) {
+    const char* s = from;
+    if (s > base) {  // move to the first line start at or after `from`
+        while (s < end) {
+            char prev = s[-1];
+            if (prev == '\n' || (prev == '\r' && *s != '\n')) break;
+            ++s;
+        }
+    }
+    const char* nl = nullptr;  // cached position of the next '\n' at or after s (end if none)
+    while (s < to && s < end) {
+        if (!nl || nl < s) {
+            nl = (const char*)memchr(s, '\n', (size_t)(end - s));
+            if (!nl) nl = end;
+        }
+        const char* e = nl;
+        const char* nxt = nl < end ? nl + 1 : end;
+        const char* cr = (const char*)memchr(s, '\r', (size_t)(nl - s));
+        if (cr && !(cr + 1 == nl && nl < end)) {  // a lone \r ends the line (a \r\n pair is left to strip())
+            e = cr;
+            nxt = cr + 1;
+        }
+        if (!fn(s, e)) return nullptr;
+        s = nxt;
+    }
+    return s;
+}
+
+inline void strip(const char*& a, const char*& b) {
+    while (a < b && is_space((unsigned char)*a)) ++a;
+    while (b > a && is_space((unsigned char)b[-1])) --b;
+}
+
+struct Rec {
+    uint64_t hdr_off, hdr_len;
+    uint64_t body_off, body_len;  // first sequence line start .. last sequence line end (unstripped span)
+    uint64_t bases;
+};
+
+struct ChunkResult {
+    std::vector<Rec> recs;
+    uint64_t err_off = UINT64_MAX;
+    int err_code = 0;
+    bool first_line_not_header = false;
+};
+
+void build_lut2(const uint8_t* lut, uint8_t* lut2) {
+    for (int c = 0; c < 256; ++c) {
+        int u = (c >= 'a' && c <= 'z') ? c - 32 : c;
+        lut2[c] = lut[u];
+    }
+}
+
+// Packs stripped line segments of one record.
+struct BitWriter {
+    uint32_t* cw;
+    uint32_t* mw;
+    uint32_t cacc = 0, macc = 0;
+    int cn = 0, mn = 0;
+    inline void put(uint8_t d) {
+        uint32_t inv = d > 3;
+        cacc = (cacc << 2) | (inv ? 0u : d);
+        macc = (macc << 1) | inv;
+        if (++cn == 16) { *cw++ = cacc; cacc = 0; cn = 0; }
+        if (++mn == 32) { *mw++ = macc; macc = 0; mn = 0; }
+    }
+    // pad to the end of the record's last block: codes 0, mask 1
+    void finish(uint32_t* cend, uint32_t* mend) {
+        if (cn) { *cw++ = cacc << (2 * (16 - cn)); cn = 0; }
+        if (mn) { *mw++ = (macc << (32 - mn)) | (mn == 32 ? 0u : (0xFFFFFFFFu >> mn)); mn = 0; }
+        while (cw < cend) *cw++ = 0;
+        while (mw < mend) *mw++ = 0xFFFFFFFFu;
+    }
+};
+
+int run_threads(int nthreads, const std::function<void(int)>& fn) {
+    if (nthreads <= 1) {
+        fn(0);
+        return 0;
+    }
+    std::vector<std::thread> th;
+    th.reserve(nthreads - 1);
+    for (int t = 1; t < nthreads; ++t) th.emplace_back(fn, t);
+    fn(0);
+    for (auto& t : th) t.join();
+    return 0;
+}
+
+int pick_threads(int nthreads, size_t work_bytes) {
+    if (nthreads > 0) return std::min(nthreads, 256);  // explicit request: honoured as is
+    nthreads = (int)std::thread::hardware_concurrency();
+    if (nthreads <= 0) nthreads = 1;
+    nthreads = std::min(nthreads, 64);
+    size_t by_work = std::max<size_t>(1, work_bytes / (256 * 1024));
+    return (int)std::min<size_t>((size_t)nthreads, by_work);
+}
+
+int alloc_packed(SkrPacked* P, int64_t m, const std::vector<uint64_t>& bases, bool pinned) {
+    P->m = m;
+    uint64_t blocks = 0;
+    for (int64_t i = 0; i < m; ++i) blocks += (bases[i] + 63) / 64;
+    P->nblocks = (int64_t)blocks + 1;
+    size_t off_codes = 0;
+    size_t off_mask = align_up(off_codes + (size_t)P->nblocks * 16, 256);
+    size_t off_blk = align_up(off_mask + (size_t)P->nblocks * 8, 256);
+    size_t off_len = align_up(off_blk + (size_t)(m + 1) * 8, 256);
+    size_t total = align_up(off_len + (size_t)std::max<int64_t>(m, 1) * 4, 256);
+    int rc = slab_alloc(total, pinned, &P->slab);
+    if (rc != SKR_OK) return rc;
+    P->slab_bytes = total;
+    char* base = (char*)P->slab.ptr;
+    P->codes = (uint32_t*)(base + off_codes);
+    P->mask = (uint32_t*)(base + off_mask);
+    P->blk_off = (uint64_t*)(base + off_blk);
+    P->len = (uint32_t*)(base + off_len);
+    uint64_t b = 0;
+    uint64_t tot = 0;
+    for (int64_t i = 0; i < m; ++i) {
+        P->blk_off[i] = b;
+        P->len[i] = (uint32_t)bases[i];
+        b += (bases[i] + 63) / 64;
+        tot += bases[i];
+    }
+    P->blk_off[m] = b;
+    P->total_bases = (int64_t)tot;
+    // trailing pad block: codes 0, mask all ones
+    memset(P->codes + b * 4, 0, 16);
+    memset(P->mask + b * 2, 0xFF, 8);
+    return SKR_OK;
+}
+
+}  // namespace
+
+extern "C" int64_t skr_pack_error_line(void) { return g_error_line; }
+
+extern "C" int skr_pack_fasta_buffer(const void* text_v, size_t nbytes, const uint8_t* lut, int nthreads, int pinned,
+                                     SkrPacked** out) {
+    g_error_line = 0;
+    if (!out || !lut || (!text_v && nbytes)) return skr::fail(SKR_ERR_ARG, "skr_pack_fasta_buffer: null argument");
+    *out = nullptr;
+    const char* text = (const char*)text_v;
+    const char* end = text + nbytes;
+    uint8_t lut2[256];
+    build_lut2(lut, lut2);
+    int T = pick_threads(nthreads, nbytes);
+
+    // ---- pass 1: records and their lengths, chunked by byte range ----------------------------
+    std::vector<ChunkResult> res(T);
+    run_threads(T, [&](int t) {
+        ChunkResult& R = res[t];
+        const char* from = text + nbytes * (size_t)t / (size_t)T;
+        const char* to = text + nbytes * (size_t)(t + 1) / (size_t)T;
+        bool in_record = false;  // a header that started in this chunk is open
+        bool beyond = false;     // phase 2: lines that start past `to` (they finish our last record)
+        auto on_line = [&](const char* a, const char* b) -> bool {
+            const char* la = a;
+            const char* lb = b;
+            strip(la, lb);
+            if (la == lb) {
+                if (beyond) return false;  // the chunk that owns this line reports it
+                uint64_t off = (uint64_t)(a - text);
+                if (off < R.err_off) { R.err_off = off; R.err_code = SKR_ERR_FASTA_BLANK; }
+                return false;
+            }
+            if (*la == '>') {
+                if (beyond) return false;  // next chunk's record: our last record is complete
+                Rec r;
+                r.hdr_off = (uint64_t)(la - text);
+                r.hdr_len = (uint64_t)(lb - la);
+                r.body_off = (uint64_t)(b - text);
+                r.body_len = 0;
+                r.bases = 0;
+                R.recs.push_back(r);
+                in_record = true;
+                return true;
+            }
+            if (!in_record) {  // sequence line of a record opened in an earlier chunk
+                if (t == 0) { R.first_line_not_header = true; return false; }
+                return true;
+            }
+            Rec& r = R.recs.back();
+            if (r.body_len == 0) r.body_off = (uint64_t)(a - text);
+            r.body_len = (uint64_t)(b - text) - r.body_off;
+            r.bases += (uint64_t)(lb - la);
+            return true;
+        };
+        const char* next = for_each_line(text, from, to, end, on_line);
+        if (next && in_record && next < end) {
+            beyond = true;
+            for_each_line(text, next, end, end, on_line);
+        }
+    });
+
+    // the earliest error wins: the reference stops at the first offending line
+    uint64_t err_off = UINT64_MAX;
+    int err_code = 0;
+    for (int t = 0; t < T; ++t)
+        if (res[t].err_off < err_off) { err_off = res[t].err_off; err_code = res[t].err_code; }
+    if (res[0].first_line_not_header)
+        return skr::fail(SKR_ERR_ARG, "FASTA text does not start with a '>' header line");
+
+    std::vector<Rec> recs;
+    size_t nrec = 0;
+    for (auto& r : res) nrec += r.recs.size();
+    recs.reserve(nrec);
+    for (auto& r : res) recs.insert(recs.end(), r.recs.begin(), r.recs.end());
+    // empty record anywhere but last -> the reference's assert (only i == 0 is exempt, which is the
+    // first header itself, never an empty record followed by a header)
+    for (size_t i = 0; i + 1 < recs.size(); ++i) {
+        if (recs[i].bases == 0) {
+            uint64_t off = recs[i + 1].hdr_off;
+            if (off < err_off) { err_off = off; err_code = SKR_ERR_FASTA_HEADER; }
+            break;
+        }
+    }
+    if (err_code) {
+        int64_t line = 1;
+        for (const char* p = text; p < text + err_off; ++p) {
+            if (*p == '\n' || (*p == '\r' && p[1] != '\n')) ++line;
+        }
+        g_error_line = line;
+        if (err_code == SKR_ERR_FASTA_BLANK)
+            return skr::fail(err_code, "string index out of range (blank line %lld in FASTA)", (long long)line);
+        return skr::fail(err_code, "There may be a header without a sequence at line %lld.", (long long)(line - 1));
+    }
+
+    // ---- pass 2: allocate + pack ---------------------------------------------------------------
+    SkrPacked* P = new SkrPacked();
+    int64_t m = (int64_t)recs.size();
+    std::vector<uint64_t> bases((size_t)m);
+    for (int64_t i = 0; i < m; ++i) {
+        bases[i] = recs[i].bases;
+        if (bases[i] > 0xFFFFFFFFull) {
+            delete P;
+            return skr::fail(SKR_ERR_ARG, "record %lld longer than 2^32-1 bases", (long long)i);
+        }
+    }
+    int rc = alloc_packed(P, m, bases, pinned != 0);
+    if (rc != SKR_OK) { delete P; return rc; }
+    P->header_spans.resize((size_t)m * 2);
+    P->body_spans.resize((size_t)m * 2);
+    std::atomic<int64_t> next_rec{0};
+    run_threads(T, [&](int) {
+        for (;;) {
+            int64_t i0 = next_rec.fetch_add(64);
+            if (i0 >= m) break;
+            int64_t i1 = std::min(m, i0 + 64);
+            for (int64_t i = i0; i < i1; ++i) {
+                const Rec& r = recs[i];
+                P->header_spans[2 * i] = r.hdr_off;
+                P->header_spans[2 * i + 1] = r.hdr_len;
+                P->body_spans[2 * i] = r.body_off;
+                P->body_spans[2 * i + 1] = r.body_len;
+                uint64_t b0 = P->blk_off[i], b1 = P->blk_off[i + 1];
+                BitWriter w{P->codes + b0 * 4, P->mask + b0 * 2};
+                const char* bs = text + r.body_off;
+                const char* be = bs + r.body_len;
+                if (r.body_len)
+                    for_each_line(bs, bs, be, be, [&](const char* a, const char* b) -> bool {
+                        strip(a, b);
+                        for (const char* p = a; p < b; ++p) w.put(lut2[(unsigned char)*p]);
+                        return true;
+                    });
+                w.finish(P->codes + b1 * 4, P->mask + b1 * 2);
+            }
+        }
+    });
+    *out = P;
+    return SKR_OK;
+}
+
+extern "C" int skr_pack_fasta_file(const char* path, const uint8_t* lut, int nthreads, int pinned, SkrPacked** out) {
+    if (!path) return skr::fail(SKR_ERR_ARG, "skr_pack_fasta_file: null path");
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return skr::fail(SKR_ERR_IO, "cannot open %s", path);
+    struct stat st;
+    if (fstat(fd, &st) != 0) { close(fd); return skr::fail(SKR_ERR_IO, "cannot stat %s", path); }
+    size_t n = (size_t)st.st_size;
+    if (n == 0) { close(fd); return skr_pack_fasta_buffer("", 0, lut, nthreads, pinned, out); }
+    void* map = mmap(nullptr, n, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+    close(fd);
+    if (map == MAP_FAILED) return skr::fail(SKR_ERR_IO, "cannot mmap %s", path);
+    madvise(map, n, MADV_SEQUENTIAL);
+    int rc = skr_pack_fasta_buffer(map, n, lut, nthreads, pinned, out);
+    munmap(map, n);
+    return rc;
+}
+
+extern "C" int skr_pack_sequences(const void* letters_v, const int64_t* offs, int64_t m, const uint8_t* lut,
+                                  int nthreads, int pinned, SkrPacked** out) {
+    g_error_line = 0;
+    if (!out || !lut || !offs || m < 0) return skr::fail(SKR_ERR_ARG, "skr_pack_sequences: bad argument");
+    *out = nullptr;
+    const unsigned char* letters = (const unsigned char*)letters_v;
+    uint8_t lut2[256];
+    build_lut2(lut, lut2);
+    std::vector<uint64_t> bases((size_t)m);
+    for (int64_t i = 0; i < m; ++i) {
+        if (offs[i + 1] < offs[i]) return skr::fail(SKR_ERR_ARG, "offsets must be non-decreasing");
+        bases[i] = (uint64_t)(offs[i + 1] - offs[i]);
+        if (bases[i] > 0xFFFFFFFFull) return skr::fail(SKR_ERR_ARG, "record %lld too long", (long long)i);
+    }
+    SkrPacked* P = new SkrPacked();
+    int rc = alloc_packed(P, m, bases, pinned != 0);
+    if (rc != SKR_OK) { delete P; return rc; }
+    int T = pick_threads(nthreads, m ? (size_t)(offs[m] - offs[0]) : 0);
+    std::atomic<int64_t> next_rec{0};
+    run_threads(T, [&](int) {
+        for (;;) {
+            int64_t i0 = next_rec.fetch_add(64);
+            if (i0 >= m) break;
+            int64_t i1 = std::min(m, i0 + 64);
+            for (int64_t i = i0; i < i1; ++i) {
+                uint64_t b0 = P->blk_off[i], b1 = P->blk_off[i + 1];
+                BitWriter w{P->codes + b0 * 4, P->mask + b0 * 2};
+                for (int64_t p = offs[i]; p < offs[i + 1]; ++p) w.put(lut2[letters[p]]);
+                w.finish(P->codes + b1 * 4, P->mask + b1 * 2);
+            }
+        }
+    });
+    *out = P;
+    return SKR_OK;
+}
+
+extern "C" void skr_packed_free(SkrPacked* p) {
+    if (!p) return;
+    slab_free(p->slab);
+    delete p;
+}
+
+extern "C" int64_t skr_packed_num_records(const SkrPacked* p) { return p->m; }
+extern "C" int64_t skr_packed_num_blocks(const SkrPacked* p) { return p->nblocks; }
+extern "C" int64_t skr_packed_total_bases(const SkrPacked* p) { return p->total_bases; }
+extern "C" const uint32_t* skr_packed_codes(const SkrPacked* p) { return p->codes; }
+extern "C" const uint32_t* skr_packed_mask(const SkrPacked* p) { return p->mask; }
+extern "C" const uint64_t* skr_packed_block_offsets(const SkrPacked* p) { return p->blk_off; }
+extern "C" const uint32_t* skr_packed_lengths(const SkrPacked* p) { return p->len; }
+extern "C" const uint64_t* skr_packed_header_spans(const SkrPacked* p) { return p->header_spans.data(); }
+extern "C" const uint64_t* skr_packed_body_spans(const SkrPacked* p) { return p->body_spans.data(); }
+extern "C" const void* skr_packed_slab(const SkrPacked* p) { return p->slab.ptr; }
+extern "C" size_t skr_packed_slab_bytes(const SkrPacked* p) { return p->slab_bytes; }

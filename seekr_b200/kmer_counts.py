@@ -1,0 +1,512 @@
+"""k-mer count matrices on the GPU behind the reference's ``BasicCounter`` API.
+
+Drop-in for ``seekr.kmer_counts.BasicCounter`` (seekr/kmer_counts.py:48-262): same constructor
+signature (positional order included), attributes (``seqs``, ``counts``, ``mean``, ``std``, ``kmers``,
+``map``, ``alpha_len`` ...), methods and exceptions.  The numeric work is done by libseekr_b200:
+
+    get_counts()   -> skr_count (count kernel with fused per-kb scaling / log2 / -mean / /std),
+                      skr_col_pass (order-exact column mean/std when mean/std is True),
+                      skr_sub_vec / skr_div_vec, skr_post_log2            (kmer_counts.py:194-209)
+    occurrences()  -> skr_count on one record                             (kmer_counts.py:140-151)
+    center() / standardize() / log2_norm() on a hand-assigned ``counts``  (kmer_counts.py:165-192)
+
+There is no CPU path: without the library or a CUDA device these methods raise.
+"""
+
+import ctypes
+from itertools import product
+
+import numpy as np
+
+from . import _lib, device
+from .fasta_reader import LazySeqs, PackedFasta, Reader
+from .my_tqdm import my_tqdm
+
+
+class Log2:
+    """Compatibility names for code written against the pre-2.0 enum (``Log2.post`` etc.);
+    the reference now uses the plain strings (kmer_counts.py:36,134)."""
+
+    pre = "Log2.pre"
+    post = "Log2.post"
+    none = "Log2.none"
+
+
+_LOG2_MODES = ["Log2.pre", "Log2.post", "Log2.none"]
+
+_NAN_WARNING = (
+    "\nWARNING: You have `np.nan` values in your counts "
+    "after standardization. This is likely due to "
+    "a kmer not appearing in any of your sequences. "
+    "Try: \n1) using a smaller kmer size, \n2) beginning "
+    "with a larger set of sequences, \n3) passing "
+    "precomputed normalization vectors from a larger "
+    "data set (e.g. GENCODE)."
+)
+
+
+def _vector_for(value, cols):
+    """Normalise a user-supplied mean/std vector the way numpy's in-place ufunc would see it.
+
+    Returns (contiguous array of length cols, is_f64).  ``counts -= vec`` on a float32 matrix is an
+    fp32 operation when result_type(float32, vec.dtype) is float32 and otherwise runs in binary64
+    and is rounded back to float32 (kmer_counts.py:169,175 with ndarray / int vectors).
+    """
+    vec = np.asarray(value)
+    if vec.dtype == object or vec.dtype.kind not in "fiub":
+        raise TypeError("mean/std vector must be numeric, got dtype %s" % vec.dtype)
+    if vec.ndim == 2 and vec.shape[0] == 1:
+        vec = vec[0]
+    if vec.ndim > 1:
+        raise NotImplementedError("mean/std must be a scalar or a vector of length 4^k")
+    vec = np.broadcast_to(vec, (cols,))  # ValueError on a length mismatch, like the reference's `counts -= mean`
+    if np.result_type(np.float32, vec.dtype) == np.float32:
+        return np.ascontiguousarray(vec, dtype=np.float32), False
+    return np.ascontiguousarray(vec, dtype=np.float64), True
+
+
+class DeviceVector:
+    """A mean/std vector resident on the device, fp32 or fp64."""
+
+    def __init__(self, tensor, is_f64):
+        self.t = tensor
+        self.is_f64 = is_f64
+
+    @classmethod
+    def from_host(cls, value, cols):
+        vec, is_f64 = _vector_for(value, cols)
+        return cls(device.to_device(vec), is_f64)
+
+    def as_f64(self):
+        import torch
+
+        return self if self.is_f64 else DeviceVector(self.t.to(torch.float64), True)
+
+
+class CountEngine:
+    """The get_counts() pipeline on device tensors.  Shared by BasicCounter, the sharded driver
+    (seekr_b200.parallel) and bench.py, so the timed path and the API path are the same code."""
+
+    def __init__(self, k, log2="Log2.post", stream=None):
+        if log2 not in _LOG2_MODES:
+            raise ValueError("log2 must be one of ['Log2.pre', 'Log2.post', 'Log2.none']")
+        self.lib = _lib.load()
+        self.torch = device.require_cuda()
+        self.k = int(k)
+        self.cols = 4 ** self.k
+        self.log2 = log2
+        self.stream = stream
+        self.min_cell = device.MinCell()
+        self.nan_cell = device.MinCell()
+
+    # -- building blocks ------------------------------------------------------------------------
+    def upload(self, packed):
+        """PackedFasta -> one device slab (a single async copy; pinned when the packer was asked to)."""
+        torch = self.torch
+        slab = torch.empty(max(packed.slab_bytes, 16), dtype=torch.uint8, device=device.current_device())
+        _lib.check(self.lib.skr_copy_h2d(device.ptr(slab), ctypes.c_void_p(packed.slab_ptr), packed.slab_bytes,
+                                         device.stream_ptr(self.stream)))
+        return DevicePacked(slab, packed)
+
+    def count(self, dpk, out, mean=None, std=None, track_min=False, out_is_f64=False):
+        """skr_count into ``out`` (m x cols).  mean/std: DeviceVector or None."""
+        vec_is_f64 = False
+        if mean is not None and std is not None and mean.is_f64 != std.is_f64:
+            # (double)x op (double)v rounded to fp32 equals the fp32 operation (24-bit operands,
+            # 53 >= 2*24+2), so the fp32 vector can ride the binary64 path unchanged
+            mean, std = mean.as_f64(), std.as_f64()
+        for v in (mean, std):
+            if v is not None:
+                vec_is_f64 = v.is_f64
+        log2_pre = 1 if self.log2 == "Log2.pre" else 0
+        if track_min:
+            self.min_cell.reset(self.stream)
+        rc = self.lib.skr_count(
+            dpk.codes, dpk.mask, dpk.blk_off, dpk.lengths, dpk.m, self.k, 0 if out_is_f64 else log2_pre,
+            device.ptr(mean.t if mean else None), device.ptr(std.t if std else None), int(vec_is_f64),
+            device.ptr(out), int(out_is_f64), out.stride(0), device.ptr(self.min_cell.t if track_min else None),
+            device.stream_ptr(self.stream))
+        _lib.check(rc)
+        self._keep = (mean, std)  # converted vectors must outlive the launch
+
+    def col_sum(self, kind, a, vec=None):
+        """One order-exact column pass over ``a`` (all rows on this device); returns the fp32 sums."""
+        acc = device.zeros(a.shape[1], self.torch.float32)
+        self.col_pass(kind, a, acc, vec)
+        return acc
+
+    def col_pass(self, kind, a, acc, vec=None):
+        m, cols = a.shape
+        rc = self.lib.skr_col_pass(kind, device.ptr(a), m, cols, a.stride(0), device.ptr(vec.t if vec else None),
+                                   int(vec.is_f64) if vec else 0, device.ptr(acc), device.stream_ptr(self.stream))
+        _lib.check(rc)
+
+    def col_finish(self, acc, rows, take_sqrt):
+        out = device.empty(acc.shape[0], self.torch.float32)
+        _lib.check(self.lib.skr_col_finish(device.ptr(acc), acc.shape[0], rows, int(take_sqrt), device.ptr(out),
+                                           device.stream_ptr(self.stream)))
+        return out
+
+    def sub_vec(self, a, vec, track_min=False):
+        if track_min:
+            self.min_cell.reset(self.stream)
+        m, cols = a.shape
+        _lib.check(self.lib.skr_sub_vec(device.ptr(a), m, cols, a.stride(0), device.ptr(vec.t), int(vec.is_f64),
+                                        device.ptr(self.min_cell.t if track_min else None),
+                                        device.stream_ptr(self.stream)))
+
+    def div_vec(self, a, vec, track_min=True):
+        if track_min:
+            self.min_cell.reset(self.stream)
+        m, cols = a.shape
+        _lib.check(self.lib.skr_div_vec(device.ptr(a), m, cols, a.stride(0), device.ptr(vec.t), int(vec.is_f64),
+                                        device.ptr(self.min_cell.t if track_min else None),
+                                        device.stream_ptr(self.stream)))
+
+    def min_scan(self, a):
+        self.min_cell.reset(self.stream)
+        m, cols = a.shape
+        _lib.check(self.lib.skr_min_scan(device.ptr(a), m, cols, a.stride(0), device.ptr(self.min_cell.t),
+                                         device.stream_ptr(self.stream)))
+
+    def post_log2(self, a):
+        m, cols = a.shape
+        _lib.check(self.lib.skr_post_log2(device.ptr(a), m, cols, a.stride(0), device.ptr(self.min_cell.t),
+                                          device.stream_ptr(self.stream)))
+
+    def log2_norm(self, a):
+        m, cols = a.shape
+        _lib.check(self.lib.skr_log2_norm(device.ptr(a), m, cols, a.stride(0), device.stream_ptr(self.stream)))
+
+    # -- the whole tail of get_counts() (kmer_counts.py:199-209) ----------------------------------
+    def run(self, dpk, mean, std, out=None, reducer=None):
+        """mean/std: False, True, or DeviceVector.  Returns (out, mean_vec, std_vec, nan_checked).
+
+        ``reducer`` (optional) supplies the cross-rank pieces of a sharded run: an object with
+        ``col_stat(engine, kind, a, vec, rows_local)`` -> (fp32 vector of the finished statistic)
+        and ``min_allreduce(engine)``; None means all rows live on this device.
+        """
+        torch = self.torch
+        m = dpk.m
+        if out is None:
+            out = device.empty((m, self.cols), torch.float32)
+        need_min = self.log2 == "Log2.post"
+        min_valid = False
+        self.std_applied = std is not False
+        mean_vec = mean if isinstance(mean, DeviceVector) else None
+        std_vec = std if isinstance(std, DeviceVector) else None
+
+        if mean is not True and std is not True:
+            # every vector is known up front: one fused launch (+ the Log2.post pass)
+            track = need_min or std is not False
+            self.count(dpk, out, mean_vec, std_vec, track_min=track)
+            min_valid = track
+        else:
+            self.count(dpk, out)  # raw counts per kb (log2'd first for Log2.pre)
+            stat = reducer.col_stat if reducer else self._local_col_stat
+            centred_sum = None
+            if mean is True:
+                mean_t = stat(self, _lib.COLPASS_SUM, out, None, finish="mean")
+                mean_vec = DeviceVector(mean_t, False)
+            if mean is not False:
+                if std is True:
+                    # centre in place and get the column sums of the centred matrix in the same pass:
+                    # np.std starts by averaging what center() left behind (kmer_counts.py:169,174)
+                    centred_sum = stat(self, _lib.COLPASS_CENTER, out, mean_vec, finish="mean")
+                else:
+                    self.sub_vec(out, mean_vec, track_min=need_min and std is False)
+                    min_valid = need_min and std is False
+            if std is True:
+                arrmean = centred_sum if centred_sum is not None else \
+                    stat(self, _lib.COLPASS_SUM, out, None, finish="mean")
+                std_t = stat(self, _lib.COLPASS_SQDEV, out, DeviceVector(arrmean, False), finish="std")
+                std_vec = DeviceVector(std_t, False)
+            if std is not False:
+                self.div_vec(out, std_vec, track_min=True)
+                min_valid = True
+        if need_min:
+            if not min_valid:
+                self.min_scan(out)
+            if reducer:
+                reducer.min_allreduce(self)
+            self.post_log2(out)
+        return out, mean_vec, std_vec
+
+    def _local_col_stat(self, engine, kind, a, vec, finish):
+        acc = self.col_sum(kind, a, vec)
+        return self.col_finish(acc, a.shape[0], take_sqrt=(finish == "std"))
+
+    def nan_after_standardize(self):
+        """True when the standardised matrix held a NaN (the reference's warning, kmer_counts.py:176)."""
+        if not getattr(self, "std_applied", False):
+            return False
+        _, nan_seen = self.min_cell.read(self.stream)
+        return nan_seen
+
+
+class DevicePacked:
+    """Device copy of a PackedFasta slab with typed pointers into it."""
+
+    def __init__(self, slab, packed):
+        self.slab = slab
+        base = slab.data_ptr()
+        self.m = packed.m
+        self.total_bases = packed.total_bases
+        self.codes = ctypes.c_void_p(base + packed.off_codes)
+        self.mask = ctypes.c_void_p(base + packed.off_mask)
+        self.blk_off = ctypes.c_void_p(base + packed.off_blk)
+        self.lengths = ctypes.c_void_p(base + packed.off_len)
+        self.nbytes = packed.slab_bytes
+
+
+class BasicCounter:
+    """Generates overlapping kmer counts for a fasta file (same parameters and attributes as the
+    reference class, seekr/kmer_counts.py:48-135)."""
+
+    def __init__(
+        self,
+        infasta=None,
+        outfile=None,
+        k=6,
+        binary=True,
+        mean=True,
+        std=True,
+        log2="Log2.post",
+        leave=True,
+        silent=False,
+        label=False,
+        alphabet="AGTC",
+    ):
+        self.infasta = infasta
+        self._packed = None
+        self._seqs = None
+        self.alphabet = alphabet
+        if infasta is not None:
+            self._packed = PackedFasta.from_file(infasta, alphabet=alphabet, pinned=_pinned_ok())
+            self._seqs = LazySeqs(self._packed)
+        self.outfile = outfile
+        self.k = k
+        self.binary = binary
+        self.mean = mean
+        if isinstance(mean, str):
+            self.mean = np.load(mean)
+        self.std = std
+        if isinstance(std, str):
+            self.std = np.load(std)
+        self.log2 = log2
+        self.leave = leave
+        self.silent = silent
+        self.label = label
+        self.counts = None
+        self.counts_device = None
+        self.alpha_len = len(alphabet)
+        self._kmers = None
+        self._map = None
+
+        if self.seqs is not None:
+            if len(self.seqs) == 1 and self.std is True:
+                err = (
+                    "You cannot standardize a single sequence. "
+                    "Please pass the path to an std. dev. array, "
+                    "or use raw counts by setting std=False."
+                )
+                raise ValueError(err)
+
+        if self.log2 not in _LOG2_MODES:
+            raise ValueError("log2 must be one of ['Log2.pre', 'Log2.post', 'Log2.none']")
+
+    # -- attributes the reference builds eagerly (kmer_counts.py:121-122); 4^k strings are only
+    #    materialised when somebody looks at them --------------------------------------------------
+    @property
+    def kmers(self):
+        if self._kmers is None:
+            self._kmers = ["".join(i) for i in product(self.alphabet, repeat=self.k)]
+        return self._kmers
+
+    @property
+    def map(self):
+        if self._map is None:
+            self._map = {kmer: i for kmer, i in zip(self.kmers, range(self.alpha_len ** self.k))}
+        return self._map
+
+    @property
+    def seqs(self):
+        return self._seqs
+
+    @seqs.setter
+    def seqs(self, value):
+        self._seqs = value
+        self._packed = None  # re-packed on demand from the new list
+
+    def _get_packed(self):
+        if self._packed is None:
+            self._packed = PackedFasta.from_sequences([s for s in self._seqs], alphabet=self.alphabet,
+                                                      pinned=_pinned_ok())
+        return self._packed
+
+    # -- reference methods ------------------------------------------------------------------------
+    def occurrences(self, row, seq):
+        """Counts kmers on a per kilobase scale (kmer_counts.py:140-151): only the k-mers present in
+        ``seq`` are assigned into ``row``; the values are the reference's binary64 sums."""
+        torch = device.require_cuda()
+        if len(seq) - self.k + 1 == 0:
+            raise ZeroDivisionError("division by zero")
+        packed = PackedFasta.from_sequences([seq], alphabet=self.alphabet)
+        engine = CountEngine(self.k, "Log2.none")
+        dpk = engine.upload(packed)
+        out = device.empty((1, 4 ** self.k), torch.float64)
+        engine.count(dpk, out, out_is_f64=True)
+        vals = device.to_host(out, pinned=False)[0]
+        hit = vals != 0
+        row[hit] = vals[hit]
+        return row
+
+    def _progress(self):
+        """Determine which iterator to loop over for counting (kmer_counts.py:153-163)."""
+        if self.silent:
+            return self.seqs
+        if not self.leave:
+            return my_tqdm()(self.seqs, desc="Kmers", leave=False)
+        return my_tqdm()(self.seqs)
+
+    def _counts_f32(self):
+        counts = self.counts
+        if not isinstance(counts, np.ndarray) or counts.dtype != np.float32 or counts.ndim != 2:
+            raise NotImplementedError("seekr_b200 normalises 2-D float32 count matrices on the GPU; got %r"
+                                      % (getattr(counts, "dtype", type(counts)),))
+        return counts
+
+    def _roundtrip(self, fn):
+        """Run ``fn(engine, device_matrix)`` on a device copy of self.counts and write the result back
+        into the same host array (the reference's methods work in place)."""
+        torch = device.require_cuda()
+        counts = self._counts_f32()
+        m, cols = counts.shape
+        ld = (cols + 3) // 4 * 4  # TMA / 128-bit paths want 16-byte rows
+        buf = device.zeros((m, ld), torch.float32)
+        lib = _lib.load()
+        src = np.ascontiguousarray(counts)
+        _lib.check(lib.skr_copy_h2d_2d(device.ptr(buf), ld * 4, device.host_ptr(src), cols * 4, cols * 4, m,
+                                       device.stream_ptr()))
+        engine = CountEngine(1, "Log2.none")
+        view = buf[:, :cols]
+        result = fn(engine, view)
+        _lib.check(lib.skr_copy_d2h_2d(device.host_ptr(src), cols * 4, device.ptr(buf), ld * 4, cols * 4, m,
+                                       device.stream_ptr()))
+        device.sync()
+        if src is not counts:
+            counts[...] = src
+        return engine, result
+
+    def center(self):
+        """Mean center counts by column (kmer_counts.py:165-169)."""
+        cols = self._counts_f32().shape[1]
+
+        def fn(engine, a):
+            if self.mean is True:
+                acc = engine.col_sum(_lib.COLPASS_SUM, a)
+                vec = DeviceVector(engine.col_finish(acc, a.shape[0], False), False)
+                self.mean = device.to_host(vec.t, pinned=False)
+            else:
+                vec = DeviceVector.from_host(self.mean, cols)
+            engine.sub_vec(a, vec)
+
+        self._roundtrip(fn)
+
+    def standardize(self):
+        """Divide out the standard deviations from columns of the count matrix (kmer_counts.py:171-187)."""
+        cols = self._counts_f32().shape[1]
+
+        def fn(engine, a):
+            if self.std is True:
+                acc = engine.col_sum(_lib.COLPASS_SUM, a)
+                arrmean = DeviceVector(engine.col_finish(acc, a.shape[0], False), False)
+                acc = engine.col_sum(_lib.COLPASS_SQDEV, a, arrmean)
+                vec = DeviceVector(engine.col_finish(acc, a.shape[0], True), False)
+                self.std = device.to_host(vec.t, pinned=False)
+            else:
+                vec = DeviceVector.from_host(self.std, cols)
+            engine.div_vec(a, vec, track_min=True)
+            engine.std_applied = True
+
+        engine, _ = self._roundtrip(fn)
+        if engine.nan_after_standardize():
+            print(_NAN_WARNING)
+
+    def log2_norm(self):
+        """Apply a log2 transform to the count matrix (kmer_counts.py:189-192)."""
+        src = self._counts_f32()
+        self.counts = np.array(src, copy=True)  # the reference rebinds counts to np.log2's result
+        self._roundtrip(lambda engine, a: engine.log2_norm(a))
+
+    def get_counts(self):
+        """Generates kmer counts for a fasta file (kmer_counts.py:194-209)."""
+        torch = device.require_cuda()
+        packed = self._get_packed()
+        cols = self.alpha_len ** self.k
+        lengths = packed.lengths
+        if lengths.size and np.any(lengths.astype(np.int64) - self.k + 1 == 0):
+            raise ZeroDivisionError("division by zero")  # 1000 / (length - k + 1), kmer_counts.py:144
+        if not 1 <= self.k <= 8:
+            raise NotImplementedError("seekr_b200 counts k-mers for 1 <= k <= 8, got k=%r" % (self.k,))
+        bar = None if self.silent else my_tqdm()(total=packed.m, **({} if self.leave else
+                                                                    {"desc": "Kmers", "leave": False}))
+        engine = CountEngine(self.k, self.log2)
+        mean = self.mean if isinstance(self.mean, bool) else DeviceVector.from_host(self.mean, cols)
+        std = self.std if isinstance(self.std, bool) else DeviceVector.from_host(self.std, cols)
+        if packed.m == 0:
+            self.counts = np.zeros([0, cols], dtype=np.float32)
+            return
+        dpk = engine.upload(packed)
+        out, mean_vec, std_vec = engine.run(dpk, mean, std)
+        self.counts = device.to_host(out)
+        self.counts_device = out
+        if self.mean is True:
+            self.mean = device.to_host(mean_vec.t, pinned=False)
+        if self.std is True:
+            self.std = device.to_host(std_vec.t, pinned=False)
+        if engine.nan_after_standardize():
+            print(_NAN_WARNING)
+        if bar is not None:
+            bar.update(packed.m)
+            bar.close()
+
+    def save(self, names=None):
+        """Saves the counts appropriately based on current settings (kmer_counts.py:211-241):
+        binary .npy, labelled csv (fasta headers or ``names`` as the index), or bare csv."""
+        err_msg = (
+            "You cannot label a binary file. "
+            'Set only one of "binary" or "label" as True. '
+            "If you used `-b` from the command line, "
+            "try also using `-rl`."
+        )
+        assert not (self.binary and self.label), err_msg
+        assert self.outfile is not None, "Please provide an outfile location."
+        if self.binary:
+            np.save(self.outfile, self.counts)
+        elif self.label:
+            from pandas import DataFrame
+
+            if names is None:
+                names = Reader(self.infasta).get_headers()
+            df = DataFrame(data=self.counts, index=names, columns=self.kmers)
+            df.to_csv(self.outfile)
+        else:
+            np.savetxt(self.outfile, self.counts, delimiter=",", fmt="%1.6f")
+
+    def make_count_file(self, names=None):
+        """get_counts() then save() when an outfile was given (kmer_counts.py:243-262)."""
+        self.get_counts()
+        if self.outfile is not None:
+            self.save(names)
+        return self.counts
+
+
+def _pinned_ok():
+    """Pack into pinned memory when a CUDA device is there to stream it to."""
+    try:
+        import torch
+
+        return bool(torch.cuda.is_available())
+    except Exception:
+        return False

@@ -1,0 +1,381 @@
+"""Parity of the CUDA counting / normalisation path with the oracle and the reference's goldens.
+
+Everything here goes through the C ABI (via seekr_b200.kmer_counts) on cuda:0.
+Bars: raw counts bit-exact; every stage before a log2 bit-exact; after a log2 within 1e-5 absolute.
+"""
+
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import golden
+from oracle import c_oracle, seekr_oracle as po
+from seekr_b200 import _lib, device, synth
+from seekr_b200.console_scripts import _run_kmer_counts, _run_norm_vectors
+from seekr_b200.fasta_reader import PackedFasta
+from seekr_b200.kmer_counts import BasicCounter, CountEngine, DeviceVector, Log2
+
+pytestmark = pytest.mark.gpu
+
+EX = golden("ref_fixtures", "example.fa")
+TOL = 1e-5
+
+
+def make(**kwargs):
+    kwargs.setdefault("silent", True)
+    return BasicCounter(infasta=EX, **kwargs)
+
+
+# ---- the reference's own unit tests, ported (seekr/tests/test_kmer_counts.py) ----------------------
+
+def test_counter_init():
+    counter = make(log2=Log2.post)
+    assert len(counter.seqs) == 5
+    assert counter.seqs[0] == "AAAAAA"
+
+
+def test_occurrences_k1():
+    counter = make(k=1)
+    row = counter.occurrences(np.zeros(4), counter.seqs[0])
+    assert np.allclose(row, [1000, 0, 0, 0])
+    row = counter.occurrences(np.zeros(4), counter.seqs[1])
+    assert np.allclose(row, [0, 500, 500, 0])
+
+
+def test_occurrences_k2():
+    counter = make(k=2)
+    expected = np.zeros(16)
+    expected[5], expected[9], expected[10] = 454.545, 90.909, 454.545
+    row = counter.occurrences(np.zeros(16), counter.seqs[1])
+    assert np.allclose(row, expected)
+    # float64 rows keep the reference's binary64 sums exactly
+    assert np.array_equal(row, po.occurrences(counter.seqs[1], 2))
+
+
+def test_center_true():
+    counter = make(k=1)
+    counter.counts = np.array([[1, 2, 3, 4], [1, -2, 5, 10]], dtype=np.float32)
+    counter.center()
+    assert np.allclose(counter.counts, np.array([[0, 2, -1, -3], [0, -2, 1, 3]], dtype=np.float32))
+
+
+def test_center_vector():
+    counter = make(k=1)
+    counter.counts = np.array([[1, 2, 3, 4], [1, -2, 5, 10]], dtype=np.float32)
+    mean = np.ones(4)
+    mean[3] = -1
+    counter.mean = mean
+    counter.center()
+    assert np.allclose(counter.counts, np.array([[0, 1, 2, 5], [0, -3, 4, 11]], dtype=np.float32))
+
+
+def test_standardize_true():
+    counter = make(k=1)
+    counter.counts = np.array([[1, 2, 3, 4], [0, -2, 5, 10]], dtype=np.float32)
+    counter.standardize()
+    assert np.allclose(counter.counts, np.array([[2, 1, 3, 4 / 3], [0, -1, 5, 10 / 3]], dtype=np.float32))
+
+
+def test_standardize_vector():
+    counter = make(k=1)
+    counter.counts = np.array([[1, 2, 3, 4], [0, -2, 5, 10]], dtype=np.float32)
+    counter.std = np.arange(1, 5)
+    counter.standardize()
+    assert np.allclose(counter.counts, np.array([[1, 1, 1, 1], [0, -1, 5 / 3, 2.5]], dtype=np.float32))
+
+
+def test_log2_norm():
+    counter = make(k=1)
+    counts = np.array([[1, 2, 3, 4], [0, -2, 5, 10]], dtype=np.float32)
+    counts += np.abs(np.min(counts))
+    counter.counts = counts.copy()
+    counter.log2_norm()
+    assert np.allclose(counter.counts, np.log2(counts + 1))
+
+
+def test_get_counts():
+    counter = make(k=1)
+    counter.get_counts()
+    expected = np.array([[2.1798673, 0.27807194, 0.0, 0.5133058],
+                         [0.6370419, 2.1100981, 2.048016, 0.5133058],
+                         [1.2010899, 1.4672222, 1.3604679, 1.8107259],
+                         [1.2073011, 1.3895708, 1.3721647, 1.8666755],
+                         [1.318994, 1.1856667, 1.5349197, 1.6688585]], dtype=np.float32)
+    assert counter.counts.dtype == np.float32
+    assert np.allclose(counter.counts, expected, rtol=0.0001, atol=0.00001)
+
+
+def test_get_counts_raw():
+    counter = make(k=2, mean=False, std=False)
+    counter.get_counts()
+    expected = np.zeros((5, 16))
+    for i in range(5):
+        expected[i] = counter.occurrences(np.zeros(16), counter.seqs[i])
+    assert np.allclose(counter.counts, expected)
+    assert np.array_equal(counter.counts, expected.astype(np.float32))
+
+
+# ---- the reference's console tests, ported (seekr/tests/test_console_scripts.py:34-124) -----------
+
+def test_run_kmer_counts(tmp_path):
+    out = str(tmp_path / "2mers.npy")
+    _run_kmer_counts(EX, out, 2, True, True, True, Log2.post, True, None, None, "AGTC")
+    assert np.allclose(np.load(out), np.load(golden("ref_fixtures", "example_2mers_counts.npy")))
+
+
+def test_run_kmer_counts_raw_csv(tmp_path):
+    out = str(tmp_path / "3mers.csv")
+    _run_kmer_counts(EX, out, 3, False, False, False, Log2.none, True, None, None, "AGTC")
+    got = pd.read_csv(out, header=None).values
+    exp = pd.read_csv(golden("ref_fixtures", "example_3mers_raw.csv"), header=None).values
+    assert np.allclose(got, exp)
+
+
+def test_run_kmer_counts_vectors(tmp_path):
+    out = str(tmp_path / "2mers_vectors.npy")
+    _run_kmer_counts(EX, out, 2, True, False, False, Log2.post, True, golden("ref_fixtures", "example_mean.npy"),
+                     golden("ref_fixtures", "example_std.npy"), "AGTC")
+    assert np.allclose(np.load(out), np.load(golden("ref_fixtures", "example_2mers_count.npy")))
+
+
+def test_run_norm_vectors(tmp_path):
+    mean, std = str(tmp_path / "mean.npy"), str(tmp_path / "std.npy")
+    _run_norm_vectors(EX, mean, std, Log2.none, 2)
+    assert np.array_equal(np.load(mean), np.load(golden("ref_fixtures", "example_mean.npy")))
+    assert np.array_equal(np.load(std), np.load(golden("ref_fixtures", "example_std.npy")))
+
+
+def test_labelled_csv_and_alphabet(tmp_path):
+    out = str(tmp_path / "lab.csv")
+    _run_kmer_counts(EX, out, 2, False, True, True, Log2.post, False, None, None, "AGTC")
+    got = pd.read_csv(out, index_col=0)
+    exp = pd.read_csv(golden("console", "ex_k2_labelled.csv"), index_col=0)
+    assert list(got.index) == list(exp.index) and list(got.columns) == list(exp.columns)
+    assert np.allclose(got.values, exp.values, rtol=0, atol=TOL)
+    out = str(tmp_path / "acgt.npy")
+    _run_kmer_counts(EX, out, 2, True, True, True, Log2.post, True, None, None, "ACGT")
+    assert np.allclose(np.load(out), np.load(golden("console", "ex_k2_acgt.npy")), rtol=0, atol=TOL)
+
+
+def test_console_vectors_pre(tmp_path):
+    mean, std = str(tmp_path / "m.npy"), str(tmp_path / "s.npy")
+    _run_norm_vectors(golden("medium.fa"), mean, std, Log2.pre, 5)
+    assert np.allclose(np.load(mean), np.load(golden("console", "medium_mean_k5.npy")), rtol=1e-6, atol=0)
+    assert np.allclose(np.load(std), np.load(golden("console", "medium_std_k5.npy")), rtol=1e-5, atol=0)
+    out = str(tmp_path / "v.npy")
+    _run_kmer_counts(golden("small.fa"), out, 5, True, False, False, Log2.pre, True,
+                     golden("console", "medium_mean_k5.npy"), golden("console", "medium_std_k5.npy"), "AGTC")
+    assert np.allclose(np.load(out), np.load(golden("console", "small_k5_vec.npy")), rtol=0, atol=TOL)
+
+
+# ---- fixtures generated from the unmodified reference -------------------------------------------------
+
+@pytest.fixture(scope="module")
+def small():
+    return np.load(golden("counts_small.npz")), po.read_fasta(golden("small.fa"))[1]
+
+
+@pytest.mark.parametrize("k", range(1, 9))
+def test_raw_counts_bit_exact_small(small, k):
+    g, seqs = small
+    sub = [seqs[i] for i in g[f"raw_k{k}_keep"]]
+    exp = np.zeros((len(sub), 4 ** k), dtype=np.float32)
+    exp[g[f"raw_k{k}_rows"], g[f"raw_k{k}_cols"]] = g[f"raw_k{k}_vals"]
+    counter = BasicCounter(k=k, mean=False, std=False, log2="Log2.none", silent=True)
+    counter.seqs = sub
+    counter.get_counts()
+    assert counter.counts.dtype == np.float32 and counter.counts.shape == exp.shape
+    assert np.array_equal(counter.counts, exp)
+
+
+@pytest.mark.parametrize("k", [2, 4, 6])
+@pytest.mark.parametrize("mode", ["pre", "post", "none"])
+def test_self_normalised_small(small, k, mode, capsys):
+    g, seqs = small
+    sub = [s for s in seqs if len(s) != k - 1]
+    tag = f"norm_k{k}_{mode}"
+    counter = BasicCounter(k=k, log2="Log2." + mode, silent=True)
+    counter.seqs = sub
+    counter.get_counts()
+    if mode == "pre":
+        assert np.allclose(counter.mean, g[tag + "_mean"], rtol=1e-6, atol=0)
+        assert np.allclose(counter.std, g[tag + "_std"], rtol=1e-5, atol=0, equal_nan=True)
+    else:
+        assert np.array_equal(counter.mean, g[tag + "_mean"])
+        assert np.array_equal(counter.std, g[tag + "_std"], equal_nan=True)
+    if k <= 4:
+        exp, got = g[tag], counter.counts
+    else:
+        exp, got = g[tag + "_vals"], counter.counts[g[tag + "_ri"], g[tag + "_ci"]]
+    assert np.allclose(got, exp, rtol=0, atol=TOL, equal_nan=True)
+    warned = "WARNING: You have `np.nan` values" in capsys.readouterr().out
+    assert warned == bool(np.isnan(exp).any())
+
+
+@pytest.mark.parametrize("k", [3, 6])
+def test_norm_matrix_medium(k):
+    g = np.load(golden("norm_medium.npz"))
+    vm, vs = g[f"k{k}_vec_mean"], g[f"k{k}_vec_std"]
+    combos = {"TT": (True, True), "FF": (False, False), "TF": (True, False), "FT": (False, True),
+              "VV": (vm, vs), "V64": (vm.astype(np.float64), vs.astype(np.float64))}
+    for cname, (mean, std) in combos.items():
+        for mode in ("pre", "post", "none"):
+            tag = f"k{k}_{cname}_{mode}"
+            counter = BasicCounter(golden("medium.fa"), k=k, mean=mean, std=std, log2="Log2." + mode, silent=True)
+            counter.get_counts()
+            if k == 3:
+                exp, got = g[tag], counter.counts
+            else:
+                exp, got = g[tag + "_vals"], counter.counts[g[f"k{k}_ri"], g[f"k{k}_ci"]]
+            assert np.allclose(got, exp, rtol=0, atol=TOL, equal_nan=True), tag
+            if mode == "none":
+                assert np.array_equal(got, exp, equal_nan=True), tag     # no log2 anywhere: IEEE exact
+                if mean is True:
+                    assert np.array_equal(counter.mean, g[tag + "_mean"]), tag
+                if std is True:
+                    assert np.array_equal(counter.std, g[tag + "_std"], equal_nan=True), tag
+
+
+def kmerlike_matrix(m, cols, seed):
+    rng = np.random.default_rng(seed)
+    lens = np.clip(rng.lognormal(np.log(2200), 0.9, size=m), 500, 20000)
+    lam = lens[:, None] / cols * rng.gamma(2.0, 0.5, size=cols)[None, :]
+    c = rng.poisson(lam).astype(np.float64)
+    return (c * (1000.0 / lens[:, None])).astype(np.float32)
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_column_stats_order_exact(tag):
+    """numpy's sequential fp32 column mean/std reproduced bit for bit at 30000 x 64 ... 2500 x 4096."""
+    g = np.load(golden("colstats.npz"))
+    m, cols, seed = (int(v) for v in g[f"{tag}_shape_seed"])
+    a = kmerlike_matrix(m, cols, seed)
+    counter = BasicCounter(k=1, silent=True)
+    counter.counts = a.copy()
+    counter.center()
+    assert np.array_equal(counter.mean, g[f"{tag}_mean"])
+    assert np.array_equal(counter.counts, a - g[f"{tag}_mean"])
+    counter.standardize()
+    assert np.array_equal(counter.std, g[f"{tag}_std"])
+    assert np.array_equal(counter.counts, (a - g[f"{tag}_mean"]) / g[f"{tag}_std"], equal_nan=True)
+
+
+# ---- oracle parity on synthetic sets, edge cases ---------------------------------------------------------
+
+@pytest.mark.parametrize("k", [1, 4, 5, 6, 7, 8])
+def test_stress_set_bit_exact(k, tmp_path):
+    """N, lower case, odd letters, homopolymer / dinucleotide records, records shorter than k and a
+    70 kb record with a 66 000-long run (16-bit sub-counter spill)."""
+    path = str(tmp_path / "stress.fa")
+    synth.write_fasta(path, 96, seed=77, stress=True, lo=40, hi=6000)
+    seqs = po.read_fasta(path)[1]
+    assert max(len(s) for s in seqs) == 70000
+    keep = [s for s in seqs if len(s) != k - 1]
+    exp = c_oracle.raw_counts(keep, k)
+    counter = BasicCounter(k=k, mean=False, std=False, log2="Log2.none", silent=True)
+    counter.seqs = keep
+    counter.get_counts()
+    assert np.array_equal(counter.counts, exp)
+    assert exp.max() > 1000 * 65536 / 70000  # the spill path really was exercised
+    if k == 6:
+        full = BasicCounter(path, k=k, mean=False, std=False, log2="Log2.none", silent=True)
+        full.get_counts()
+        assert np.array_equal(full.counts, c_oracle.raw_counts(seqs, k))
+
+
+def test_zero_division_and_short_records():
+    counter = BasicCounter(k=4, mean=False, std=False, log2="Log2.none", silent=True)
+    counter.seqs = ["ACGTAC", "ACG"]
+    with pytest.raises(ZeroDivisionError):
+        counter.get_counts()
+    counter.seqs = ["ACGTAC", "AC", ""]
+    counter.get_counts()
+    assert counter.counts[0].sum() > 0 and not counter.counts[1:].any()
+    with pytest.raises(ZeroDivisionError):
+        counter.occurrences(np.zeros(256), "ACG")
+    with pytest.raises(ValueError):
+        BasicCounter(EX, log2="log2")
+
+
+def test_single_sequence_cannot_be_standardised(tmp_path):
+    path = str(tmp_path / "one.fa")
+    with open(path, "w") as handle:
+        handle.write(">only\nACGTACGTAC\n")
+    with pytest.raises(ValueError, match="cannot standardize a single sequence"):
+        BasicCounter(path, k=2, silent=True)                       # kmer_counts.py:124-131
+    counter = BasicCounter(path, k=2, std=False, mean=False, log2="Log2.none", silent=True)
+    counter.get_counts()
+    assert np.array_equal(counter.counts, c_oracle.raw_counts(["ACGTACGTAC"], 2))
+
+
+def test_vector_length_mismatch_raises():
+    with pytest.raises(ValueError):
+        c = BasicCounter(EX, k=2, mean=np.zeros(5, dtype=np.float32), std=False, silent=True)
+        c.get_counts()
+
+
+def test_engine_fused_equals_staged():
+    """The fused count+normalise launch and the staged kernels give identical bits."""
+    import torch
+
+    seqs = synth.seq_strings(300, seed=5, lo=300, hi=5000)
+    k = 6
+    raw = c_oracle.raw_counts(seqs, k)
+    mean = raw.mean(axis=0).astype(np.float32)
+    std = (raw.std(axis=0) + 0.25).astype(np.float32)
+    packed = PackedFasta.from_sequences(seqs, pinned=True)
+    for mode in ("Log2.none", "Log2.pre", "Log2.post"):
+        eng = CountEngine(k, mode)
+        dpk = eng.upload(packed)
+        fused, _, _ = eng.run(dpk, DeviceVector.from_host(mean, 4 ** k), DeviceVector.from_host(std, 4 ** k))
+        exp, _, _ = c_oracle.normalise(raw, mean, std, mode)
+        got = fused.cpu().numpy()
+        if mode == "Log2.none":
+            assert np.array_equal(got, exp)
+        else:
+            assert np.allclose(got, exp, rtol=0, atol=TOL)
+        torch.cuda.synchronize()
+
+
+def test_full_size_properties():
+    """BASELINE config 2 shape (50k transcripts, k=6): size-independent checks on the raw matrix.
+
+    For pure ACGT input every window is counted, so row i holds integers c with
+    sum(c) = L_i - 5 and value = chain(1000 / (L_i - 5), c); recover c and compare checksums with
+    the packed input, and check 200 random rows against the oracle bit for bit."""
+    m = 50000
+    letters, offs = synth.sequences_bytes(m, seed=50000)
+    lens = np.diff(offs)
+    lut = np.full(256, 255, dtype=np.uint8)
+    for i, ch in enumerate("AGTC"):
+        lut[ord(ch)] = i
+    import ctypes
+    lib = _lib.load()
+    out = ctypes.c_void_p()
+    _lib.check(lib.skr_pack_sequences(ctypes.c_void_p(letters.ctypes.data), ctypes.c_void_p(offs.ctypes.data), m,
+                                      ctypes.c_void_p(lut.ctypes.data), 0, 1, ctypes.byref(out)))
+    packed = PackedFasta(out, None)
+    eng = CountEngine(6, "Log2.none")
+    dpk = eng.upload(packed)
+    dev, _, _ = eng.run(dpk, False, False)
+    import torch
+    nwin = torch.from_numpy((lens - 5).astype(np.float64)).cuda()
+    ints = torch.round(dev.double() * nwin[:, None] / 1000.0)
+    assert torch.equal(ints.sum(dim=1), nwin)                       # every window landed in exactly one bin
+    col_total = ints.sum(dim=0).cpu().numpy()
+    # column totals against a direct numpy count of all 6-mers over the concatenated letters
+    digits = lut[letters].astype(np.int64)
+    idx = np.zeros(len(digits) - 5, dtype=np.int64)
+    for j in range(6):
+        idx = idx * 4 + digits[j:len(digits) - 5 + j]
+    valid = np.ones(len(digits) - 5, dtype=bool)
+    for b in offs[1:-1]:
+        valid[max(0, b - 5):b] = False                              # windows straddling two records
+    exp_total = np.bincount(idx[valid], minlength=4096)
+    assert np.array_equal(col_total.astype(np.int64), exp_total)
+    rows = np.random.default_rng(1).choice(m, size=200, replace=False)
+    text = letters.tobytes().decode("ascii")
+    sub = [text[offs[i]:offs[i + 1]] for i in rows]
+    assert np.array_equal(dev[torch.from_numpy(rows).cuda()].cpu().numpy(), c_oracle.raw_counts(sub, 6))

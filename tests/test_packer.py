@@ -1,0 +1,135 @@
+"""Host FASTA packer (skr_pack_*) against the oracle's restatement of Reader (fasta_reader.py:41-78)."""
+
+import os
+
+import numpy as np
+import pytest
+
+from conftest import golden
+from oracle import seekr_oracle as po
+from seekr_b200 import synth
+from seekr_b200.fasta_reader import LazySeqs, PackedFasta, Reader, alphabet_lut
+
+
+def unpack(packed):
+    """(digits uint8 with 255 = invalid, per record) decoded from the packed arrays."""
+    codes, mask = packed.codes, packed.mask
+    offs, lens = packed.block_offsets, packed.lengths
+    out = []
+    for i in range(packed.m):
+        L = int(lens[i])
+        b0, b1 = int(offs[i]), int(offs[i + 1])
+        assert b1 - b0 == (L + 63) // 64
+        cw = codes[b0 * 4:b1 * 4].astype(np.uint64)
+        mw = mask[b0 * 2:b1 * 2].astype(np.uint64)
+        p = np.arange((b1 - b0) * 64, dtype=np.int64)
+        d = ((cw[p // 16] >> (30 - 2 * (p % 16)).astype(np.uint64)) & np.uint64(3)).astype(np.uint8)
+        inv = ((mw[p // 32] >> (31 - (p % 32)).astype(np.uint64)) & np.uint64(1)).astype(bool)
+        assert inv[L:].all(), "padding must be masked"
+        assert not d[inv].any(), "invalid positions carry code 0"
+        d = d.copy()
+        d[inv] = 255
+        out.append(d[:L])
+    return out
+
+
+def expected_digits(seq, alphabet="AGTC"):
+    lut = alphabet_lut(alphabet)
+    return lut[np.frombuffer(seq.encode("latin-1", "replace"), dtype=np.uint8)] if seq else np.zeros(0, np.uint8)
+
+
+@pytest.mark.parametrize("name", ["small.fa", "small_crlf.fa", "medium.fa", os.path.join("ref_fixtures", "example.fa")])
+@pytest.mark.parametrize("threads", [1, 3, 16])
+def test_pack_matches_reader(name, threads):
+    path = golden(name)
+    headers, seqs = po.read_fasta(path)
+    packed = PackedFasta.from_file(path, nthreads=threads)
+    assert packed.m == len(seqs)
+    assert list(packed.lengths) == [len(s) for s in seqs]
+    assert packed.headers() == headers
+    assert list(LazySeqs(packed)) == seqs
+    for got, s in zip(unpack(packed), seqs):
+        assert np.array_equal(got, expected_digits(s))
+    # trailing pad block
+    assert packed.nblocks == int(packed.block_offsets[-1]) + 1
+    assert (packed.mask[-2:] == 0xFFFFFFFF).all() and not packed.codes[-4:].any()
+
+
+def test_alphabet_permutation_and_case():
+    text = b">a\nacgtNNacgu\n>b\nTTTT\n"
+    p = PackedFasta.from_buffer(text, alphabet="ACGT")
+    d = unpack(p)
+    assert list(d[0]) == [0, 1, 2, 3, 255, 255, 0, 1, 2, 255]   # lower case is upper-cased; U is not T
+    assert list(d[1]) == [3, 3, 3, 3]
+    p = PackedFasta.from_buffer(text, alphabet="AGTC")
+    assert list(unpack(p)[0]) == [0, 3, 1, 2, 255, 255, 0, 3, 1, 255]
+    with pytest.raises(NotImplementedError):
+        PackedFasta.from_buffer(text, alphabet="ACG")
+
+
+@pytest.mark.parametrize("threads", [1, 4])
+def test_line_endings_and_whitespace(threads, tmp_path):
+    cases = {
+        "unix": b">h1\nACGT\nAC\n>h2\nGG\n",
+        "no_final_newline": b">h1\nACGT\nAC\n>h2\nGG",
+        "crlf": b">h1\r\nACGT\r\nAC\r\n>h2\r\nGG\r\n",
+        "old_mac": b">h1\rACGT\rAC\r>h2\rGG\r",
+        "padded": b"  >h1 \n  ACGT\t\n AC \n>h2\nG G\n",        # inner blank is a base, outer ones are stripped
+        "empty_last_record": b">h1\nACGT\n>h2\n",
+        "only_header": b">h1\n",
+    }
+    for name, text in cases.items():
+        path = os.path.join(tmp_path, name + ".fa")
+        with open(path, "wb") as handle:
+            handle.write(text)
+        headers, seqs = po.read_fasta(path)
+        packed = PackedFasta.from_file(path, nthreads=threads)
+        assert list(LazySeqs(packed)) == seqs, name
+        assert packed.headers() == headers, name
+        assert list(packed.lengths) == [len(s) for s in seqs], name
+        for got, s in zip(unpack(packed), seqs):
+            assert np.array_equal(got, expected_digits(s)), name
+        assert Reader(path).get_seqs() == seqs and Reader(path).get_headers() == headers
+
+
+@pytest.mark.parametrize("threads", [1, 5])
+def test_errors_match_the_reference(threads, tmp_path):
+    bad = {
+        "blank_middle": (b">h1\nACGT\n\nAC\n>h2\nGG\n", IndexError),
+        "blank_end": (b">h1\nACGT\n\n", IndexError),
+        "spaces_only_line": (b">h1\nACGT\n   \n>h2\nAA\n", IndexError),
+        "header_header": (b">h1\nACGT\n>h2\n>h3\nAA\n", AssertionError),
+        "first_record_empty": (b">h1\n>h2\nAA\n", AssertionError),
+    }
+    for name, (text, exc) in bad.items():
+        path = os.path.join(tmp_path, name + ".fa")
+        with open(path, "wb") as handle:
+            handle.write(text)
+        with pytest.raises(exc):
+            po.read_fasta(path)          # what the reference does
+        with pytest.raises(exc):
+            PackedFasta.from_file(path, nthreads=threads)
+    assert PackedFasta.from_buffer(b"").m == 0
+    with pytest.raises(FileNotFoundError):
+        PackedFasta.from_file(os.path.join(tmp_path, "missing.fa"))
+
+
+def test_many_threads_on_a_larger_set(tmp_path):
+    path = os.path.join(tmp_path, "s.fa")
+    synth.write_fasta(path, 700, seed=9, stress=True, lo=30, hi=3000)
+    seqs = synth.seq_strings(700, seed=9, stress=True, lo=30, hi=3000)
+    ref = unpack(PackedFasta.from_file(path, nthreads=1))
+    for threads in (2, 7, 32):
+        packed = PackedFasta.from_file(path, nthreads=threads)
+        assert list(packed.lengths) == [len(s) for s in seqs]
+        got = unpack(packed)
+        assert all(np.array_equal(a, b) for a, b in zip(got, ref))
+    for a, s in zip(ref, seqs):
+        assert np.array_equal(a, expected_digits(s))
+
+
+def test_pack_sequences_matches_pack_file():
+    seqs = po.read_fasta(golden("small.fa"))[1]
+    a = unpack(PackedFasta.from_file(golden("small.fa")))
+    b = unpack(PackedFasta.from_sequences(seqs))
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
