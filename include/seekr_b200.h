@@ -121,6 +121,9 @@ int skr_sub_vec(float* d_a, int64_t m, int64_t cols, int64_t ld, const void* d_v
                 SkrMinCell* d_min, void* stream);
 int skr_div_vec(float* d_a, int64_t m, int64_t cols, int64_t ld, const void* d_vec, int vec_is_f64,
                 SkrMinCell* d_min, void* stream);
+/* a = fl(fl(a - mean) / std) in one pass, either vector optional (both share vec_is_f64) */
+int skr_normalize(float* d_a, int64_t m, int64_t cols, int64_t ld, const void* d_mean, const void* d_std,
+                  int vec_is_f64, SkrMinCell* d_min, void* stream);
 /* running minimum / NaN flag of an existing matrix */
 int skr_min_scan(const float* d_a, int64_t m, int64_t cols, int64_t ld, SkrMinCell* d_min, void* stream);
 
@@ -133,20 +136,23 @@ int skr_min_scan(const float* d_a, int64_t m, int64_t cols, int64_t ld, SkrMinCe
  * out, which lets row shards on several GPUs be chained (rank r continues from rank r-1).
  * ------------------------------------------------------------------------------------------ */
 enum {
-    SKR_COLPASS_SUM = 0,    /* acc += a[i][j] */
-    SKR_COLPASS_CENTER = 1, /* a[i][j] -= vec[j] (in place), then acc += a[i][j] */
-    SKR_COLPASS_SQDEV = 2,  /* acc += (a[i][j] - vec[j])^2 */
+    SKR_COLPASS_SUM = 0,      /* acc += a[i][j] */
+    SKR_COLPASS_CENTERED = 1, /* acc += fl(a[i][j] - vec[j])                     (sum of the centred matrix) */
+    SKR_COLPASS_SQDEV = 2,    /* acc += fl(y - vec2[j])^2, y = vec ? fl(a[i][j] - vec[j]) : a[i][j] */
 };
-int skr_col_pass(int kind, float* d_a, int64_t m, int64_t cols, int64_t ld, const void* d_vec, int vec_is_f64,
-                 float* d_acc, void* stream);
+/* None of the passes writes the matrix: the centred values are recomputed where they are needed
+ * (each with the same single fp32 rounding the reference's in-place `counts -= mean` applies), and
+ * skr_normalize writes the final matrix once.  d_vec: mean vector (fp32 or fp64), d_vec2: fp32. */
+int skr_col_pass(int kind, const float* d_a, int64_t m, int64_t cols, int64_t ld, const void* d_vec, int vec_is_f64,
+                 const float* d_vec2, float* d_acc, void* stream);
 /* mean[j] = (float)((double)acc[j] / rows);  std[j] = sqrtf((float)((double)acc[j] / rows)) */
 int skr_col_finish(const float* d_acc, int64_t cols, int64_t total_rows, int take_sqrt, float* d_out, void* stream);
 
 /* Scalable passes for sharded runs: per-column binary64 partial sums computed row-parallel
- * (to be summed across ranks with one all-reduce), kinds as above except CENTER does not
- * write.  More accurate than the reference, not bit-identical to it. */
+ * (to be summed across ranks with one all-reduce), kinds as above.  More accurate than the
+ * reference, not bit-identical to it. */
 int skr_col_partial_f64(int kind, const float* d_a, int64_t m, int64_t cols, int64_t ld, const void* d_vec,
-                        int vec_is_f64, double* d_acc, void* stream);
+                        int vec_is_f64, const float* d_vec2, double* d_acc, void* stream);
 int skr_col_finish_f64(const double* d_acc, int64_t cols, int64_t total_rows, int take_sqrt, float* d_out,
                        void* stream);
 

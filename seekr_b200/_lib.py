@@ -20,7 +20,7 @@ SKR_ERR_FASTA_BLANK = 5
 SKR_ERR_FASTA_HEADER = 6
 
 COLPASS_SUM = 0
-COLPASS_CENTER = 1
+COLPASS_CENTERED = 1
 COLPASS_SQDEV = 2
 
 _vp = ctypes.c_void_p
@@ -55,10 +55,11 @@ SIGNATURES = {
     "skr_post_log2": (_int, [_vp, _i64, _i64, _i64, _vp, _vp]),
     "skr_sub_vec": (_int, [_vp, _i64, _i64, _i64, _vp, _int, _vp, _vp]),
     "skr_div_vec": (_int, [_vp, _i64, _i64, _i64, _vp, _int, _vp, _vp]),
+    "skr_normalize": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _int, _vp, _vp]),
     "skr_min_scan": (_int, [_vp, _i64, _i64, _i64, _vp, _vp]),
-    "skr_col_pass": (_int, [_int, _vp, _i64, _i64, _i64, _vp, _int, _vp, _vp]),
+    "skr_col_pass": (_int, [_int, _vp, _i64, _i64, _i64, _vp, _int, _vp, _vp, _vp]),
     "skr_col_finish": (_int, [_vp, _i64, _i64, _int, _vp, _vp]),
-    "skr_col_partial_f64": (_int, [_int, _vp, _i64, _i64, _i64, _vp, _int, _vp, _vp]),
+    "skr_col_partial_f64": (_int, [_int, _vp, _i64, _i64, _i64, _vp, _int, _vp, _vp, _vp]),
     "skr_col_finish_f64": (_int, [_vp, _i64, _i64, _int, _vp, _vp]),
     "skr_pearson_rows_padded": (_i64, [_i64]),
     "skr_pearson_k_padded": (_i64, [_i64]),

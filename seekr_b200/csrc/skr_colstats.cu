@@ -6,7 +6,8 @@
 // history (at 250k rows its std is ~1e-3 relative away from the binary64 value).  To reproduce
 // them bit for bit each column is summed sequentially in row order with plain fp32 adds.  The
 // dependent add chain is 4 cycles per row, about the time HBM needs to deliver the row anyway,
-// provided the loads never stall it: a CTA owns a strip of 32 columns; one producer thread
+// provided the loads never stall it (no pass writes the matrix: the centred values are recomputed
+// where needed, with the same single rounding): a CTA owns a strip of 32 columns; one producer thread
 // streams [128 rows x 32 columns] boxes of the strip through a 4-deep shared-memory ring with
 // TMA (cp.async.bulk.tensor + mbarrier), and one consumer warp (lane = column) walks the rows.
 // The running sums enter and leave through d_acc, so row shards on several GPUs can be chained.
@@ -27,9 +28,9 @@ constexpr int kStages = 4;
 constexpr int kTileBytes = kTileRows * kStripCols * 4;  // 16 KB
 
 template <int KIND, bool kVecF64>
-__global__ void __launch_bounds__(64) col_pass_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ a,
+__global__ void __launch_bounds__(64) col_pass_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ a,
                                                       long long m, long long cols, long long ld, const void* vec,
-                                                      float* acc_io) {
+                                                      const float* vec2, float* acc_io) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t full_bar[kStages];
     __shared__ uint64_t empty_bar[kStages];
@@ -66,21 +67,24 @@ __global__ void __launch_bounds__(64) col_pass_kernel(const __grid_constant__ CU
     const long long col = col0 + lane;
     const bool active = col < cols;
     float acc = active ? acc_io[col] : 0.0f;
-    float vf = 0.0f;
+    float vf = 0.0f, v2 = 0.0f;
     double vd = 0.0;
-    if (KIND != SKR_COLPASS_SUM && active) {
-        if (kVecF64) vd = reinterpret_cast<const double*>(vec)[col];
-        else vf = reinterpret_cast<const float*>(vec)[col];
+    const bool has_vec = vec != nullptr;
+    if (active) {
+        if (has_vec) {
+            if (kVecF64) vd = reinterpret_cast<const double*>(vec)[col];
+            else vf = reinterpret_cast<const float*>(vec)[col];
+        }
+        if (KIND == SKR_COLPASS_SQDEV) v2 = vec2[col];
     }
-    auto step = [&](float x, long long row) {
-        float y;
-        if (KIND == SKR_COLPASS_SUM) {
-            y = x;
-        } else if (KIND == SKR_COLPASS_CENTER) {
+    // one IEEE operation per step, exactly the reference's sequence: counts -= mean (one rounding),
+    // np.std: x - arrmean, square, sequential fp32 sum (kmer_counts.py:169,174; numpy _methods.py:_var)
+    auto step = [&](float x) {
+        float y = x;
+        if (KIND != SKR_COLPASS_SUM && has_vec)
             y = kVecF64 ? __double2float_rn(__dsub_rn((double)x, vd)) : __fsub_rn(x, vf);
-            if (active) a[row * ld + col] = y;
-        } else {
-            const float d = __fsub_rn(x, vf);
+        if (KIND == SKR_COLPASS_SQDEV) {
+            const float d = __fsub_rn(y, v2);
             y = __fmul_rn(d, d);
         }
         acc = __fadd_rn(acc, y);
@@ -89,17 +93,16 @@ __global__ void __launch_bounds__(64) col_pass_kernel(const __grid_constant__ CU
         const int s = (int)(t % kStages);
         const uint32_t ph = (uint32_t)((t / kStages) & 1);
         skr::mbar_wait(&full_bar[s], ph);
-        const long long row0 = t * kTileRows;
-        const int rows = (int)min((long long)kTileRows, m - row0);
+        const int rows = (int)min((long long)kTileRows, m - t * kTileRows);
         int r = 0;
         for (; r + 8 <= rows; r += 8) {
             float x[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) x[u] = tiles[s][r + u][lane];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) step(x[u], row0 + r + u);
+            for (int u = 0; u < 8; ++u) step(x[u]);
         }
-        for (; r < rows; ++r) step(tiles[s][r][lane], row0 + r);
+        for (; r < rows; ++r) step(tiles[s][r][lane]);
         __syncwarp();
         if (lane == 0) skr::mbar_arrive(&empty_bar[s]);
     }
@@ -126,20 +129,22 @@ __global__ void col_finish_f64_kernel(const double* acc, long long cols, long lo
 // Row-parallel binary64 partial sums: a CTA covers 128 columns x a slab of rows; thread = column.
 template <int KIND, bool kVecF64>
 __global__ void __launch_bounds__(128) col_partial_kernel(const float* __restrict__ a, long long m, long long cols,
-                                                          long long ld, const void* vec, long long rows_per_cta,
-                                                          double* acc) {
+                                                          long long ld, const void* vec, const float* vec2,
+                                                          long long rows_per_cta, double* acc) {
     const long long col = (long long)blockIdx.x * 128 + threadIdx.x;
     if (col >= cols) return;
     const long long r0 = (long long)blockIdx.y * rows_per_cta;
     const long long r1 = min(m, r0 + rows_per_cta);
-    double v = 0.0;
-    if (KIND != SKR_COLPASS_SUM) v = kVecF64 ? ((const double*)vec)[col] : (double)((const float*)vec)[col];
+    double v = 0.0, v2 = 0.0;
+    if (KIND != SKR_COLPASS_SUM && vec) v = kVecF64 ? ((const double*)vec)[col] : (double)((const float*)vec)[col];
+    if (KIND == SKR_COLPASS_SQDEV) v2 = (double)vec2[col];
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     long long r = r0;
     auto term = [&](float x) -> double {
         if (KIND == SKR_COLPASS_SUM) return (double)x;
         const double d = (double)x - v;
-        return KIND == SKR_COLPASS_CENTER ? d : d * d;
+        if (KIND == SKR_COLPASS_CENTERED) return d;
+        return (d - v2) * (d - v2);
     };
     for (; r + 4 <= r1; r += 4) {
         const float x0 = a[(r + 0) * ld + col], x1 = a[(r + 1) * ld + col];
@@ -152,12 +157,12 @@ __global__ void __launch_bounds__(128) col_partial_kernel(const float* __restric
 
 }  // namespace
 
-extern "C" int skr_col_pass(int kind, float* d_a, int64_t m, int64_t cols, int64_t ld, const void* d_vec,
-                            int vec_is_f64, float* d_acc, void* stream) {
+extern "C" int skr_col_pass(int kind, const float* d_a, int64_t m, int64_t cols, int64_t ld, const void* d_vec,
+                            int vec_is_f64, const float* d_vec2, float* d_acc, void* stream) {
     if (m <= 0 || cols <= 0) return SKR_OK;
     if (!d_a || !d_acc) return skr::fail(SKR_ERR_ARG, "skr_col_pass: null argument");
-    if (kind != SKR_COLPASS_SUM && !d_vec) return skr::fail(SKR_ERR_ARG, "skr_col_pass: this pass needs a vector");
-    if (kind == SKR_COLPASS_SQDEV && vec_is_f64) return skr::fail(SKR_ERR_ARG, "skr_col_pass: SQDEV takes an fp32 vector");
+    if (kind == SKR_COLPASS_CENTERED && !d_vec) return skr::fail(SKR_ERR_ARG, "skr_col_pass: CENTERED needs the mean vector");
+    if (kind == SKR_COLPASS_SQDEV && !d_vec2) return skr::fail(SKR_ERR_ARG, "skr_col_pass: SQDEV needs vec2");
     if (ld < cols || (ld % 4) != 0) return skr::fail(SKR_ERR_ARG, "skr_col_pass: ld must be >= cols and a multiple of 4");
     if (m > 0x7FFFFFFFll || cols > 0x7FFFFFFFll) return skr::fail(SKR_ERR_ARG, "skr_col_pass: matrix too large");
     CUtensorMap tmap;
@@ -167,19 +172,21 @@ extern "C" int skr_col_pass(int kind, float* d_a, int64_t m, int64_t cols, int64
     const unsigned grid = (unsigned)((cols + kStripCols - 1) / kStripCols);
     const size_t smem = (size_t)kStages * kTileBytes;
     cudaStream_t s = (cudaStream_t)stream;
+    const bool f64 = d_vec && vec_is_f64;
 #define SKR_COL_LAUNCH(KIND, F64)                                                                              \
     do {                                                                                                       \
         auto kern = col_pass_kernel<KIND, F64>;                                                                \
         SKR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-        kern<<<grid, 64, smem, s>>>(tmap, d_a, m, cols, ld, d_vec, d_acc);                                     \
+        kern<<<grid, 64, smem, s>>>(tmap, d_a, m, cols, ld, d_vec, d_vec2, d_acc);                             \
     } while (0)
     switch (kind) {
         case SKR_COLPASS_SUM: SKR_COL_LAUNCH(SKR_COLPASS_SUM, false); break;
-        case SKR_COLPASS_CENTER:
-            if (vec_is_f64) SKR_COL_LAUNCH(SKR_COLPASS_CENTER, true);
-            else SKR_COL_LAUNCH(SKR_COLPASS_CENTER, false);
+        case SKR_COLPASS_CENTERED:
+            if (f64) SKR_COL_LAUNCH(SKR_COLPASS_CENTERED, true); else SKR_COL_LAUNCH(SKR_COLPASS_CENTERED, false);
             break;
-        case SKR_COLPASS_SQDEV: SKR_COL_LAUNCH(SKR_COLPASS_SQDEV, false); break;
+        case SKR_COLPASS_SQDEV:
+            if (f64) SKR_COL_LAUNCH(SKR_COLPASS_SQDEV, true); else SKR_COL_LAUNCH(SKR_COLPASS_SQDEV, false);
+            break;
         default: return skr::fail(SKR_ERR_ARG, "skr_col_pass: unknown pass kind %d", kind);
     }
 #undef SKR_COL_LAUNCH
@@ -198,10 +205,11 @@ extern "C" int skr_col_finish(const float* d_acc, int64_t cols, int64_t total_ro
 }
 
 extern "C" int skr_col_partial_f64(int kind, const float* d_a, int64_t m, int64_t cols, int64_t ld, const void* d_vec,
-                                   int vec_is_f64, double* d_acc, void* stream) {
+                                   int vec_is_f64, const float* d_vec2, double* d_acc, void* stream) {
     if (m <= 0 || cols <= 0) return SKR_OK;
     if (!d_a || !d_acc) return skr::fail(SKR_ERR_ARG, "skr_col_partial_f64: null argument");
-    if (kind != SKR_COLPASS_SUM && !d_vec) return skr::fail(SKR_ERR_ARG, "skr_col_partial_f64: this pass needs a vector");
+    if (kind == SKR_COLPASS_CENTERED && !d_vec) return skr::fail(SKR_ERR_ARG, "skr_col_partial_f64: CENTERED needs the mean");
+    if (kind == SKR_COLPASS_SQDEV && !d_vec2) return skr::fail(SKR_ERR_ARG, "skr_col_partial_f64: SQDEV needs vec2");
     int dev = 0, sms = 0;
     SKR_CUDA_CHECK(cudaGetDevice(&dev));
     SKR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -213,14 +221,15 @@ extern "C" int skr_col_partial_f64(int kind, const float* d_a, int64_t m, int64_
     gy = (m + rows_per_cta - 1) / rows_per_cta;
     dim3 grid((unsigned)gx, (unsigned)gy);
     cudaStream_t s = (cudaStream_t)stream;
-#define SKR_PART_LAUNCH(KIND)                                                                                   \
-    do {                                                                                                        \
-        if (vec_is_f64) col_partial_kernel<KIND, true><<<grid, 128, 0, s>>>(d_a, m, cols, ld, d_vec, rows_per_cta, d_acc); \
-        else col_partial_kernel<KIND, false><<<grid, 128, 0, s>>>(d_a, m, cols, ld, d_vec, rows_per_cta, d_acc);           \
+    const bool f64 = d_vec && vec_is_f64;
+#define SKR_PART_LAUNCH(KIND)                                                                                         \
+    do {                                                                                                              \
+        if (f64) col_partial_kernel<KIND, true><<<grid, 128, 0, s>>>(d_a, m, cols, ld, d_vec, d_vec2, rows_per_cta, d_acc);  \
+        else col_partial_kernel<KIND, false><<<grid, 128, 0, s>>>(d_a, m, cols, ld, d_vec, d_vec2, rows_per_cta, d_acc);     \
     } while (0)
     switch (kind) {
         case SKR_COLPASS_SUM: SKR_PART_LAUNCH(SKR_COLPASS_SUM); break;
-        case SKR_COLPASS_CENTER: SKR_PART_LAUNCH(SKR_COLPASS_CENTER); break;
+        case SKR_COLPASS_CENTERED: SKR_PART_LAUNCH(SKR_COLPASS_CENTERED); break;
         case SKR_COLPASS_SQDEV: SKR_PART_LAUNCH(SKR_COLPASS_SQDEV); break;
         default: return skr::fail(SKR_ERR_ARG, "skr_col_partial_f64: unknown pass kind %d", kind);
     }

@@ -23,6 +23,7 @@
 namespace {
 
 constexpr int kSegChunks = 4095;  // 4095 chunks x 16 windows = 65 520 < 65 536 increments per segment
+constexpr int kTab = 64;          // counts below this are looked up, larger ones take the generic chain_sum
 
 template <int K>
 struct CountCfg {
@@ -56,6 +57,10 @@ __global__ void __launch_bounds__(CountCfg<K>::kThreads) count_kernel(const Coun
     __shared__ long long s_rec;
     __shared__ float s_wmin[T / 32];
     __shared__ int s_wnan[T / 32];
+    // per-record value table: s_tab[c] = float32 value of a bin seen c times (c < kTab), so the
+    // epilogue does one shared load per bin instead of a binary64 add chain
+    __shared__ float s_tab[kTab];
+    __shared__ double s_tab64[sizeof(OutT) == 8 ? kTab : 1];
 
     const int tid = threadIdx.x;
     float tmin = INFINITY;
@@ -73,10 +78,22 @@ __global__ void __launch_bounds__(CountCfg<K>::kThreads) count_kernel(const Coun
         } else {
             for (int i = tid; i < Cfg::kWords; i += T) hist[i] = 0;
         }
-        __syncthreads();
-
         const uint32_t L = p.len[rec];
         const long long nwin = (long long)L - K + 1;  // > 0 or the row is all zero counts (L == k-1 is rejected on the host)
+        const double inc = nwin > 0 ? 1000.0 / (double)nwin : 0.0;
+        if (tid >= T - kTab) {  // the last kTab threads fill the table while the others start counting
+            const int c = tid - (T - kTab);
+            const double v64 = skr::chain_sum(inc, (uint32_t)c);
+            if constexpr (sizeof(OutT) == 8) {
+                s_tab64[c] = v64;
+            } else {
+                float v = __double2float_rn(v64);
+                if (p.log2_pre) v = log2f(__fadd_rn(v, 1.0f));
+                s_tab[c] = v;
+            }
+        }
+        __syncthreads();
+
         const uint64_t b0 = p.blk_off[rec];
         const uint32_t* __restrict__ cw = p.codes + b0 * 4;
         const uint32_t* __restrict__ mw = p.mask + b0 * 2;
@@ -143,7 +160,6 @@ __global__ void __launch_bounds__(CountCfg<K>::kThreads) count_kernel(const Coun
         }
 
         // ---- epilogue: 4 bins per thread per step ----------------------------------------------
-        const double inc = nwin > 0 ? 1000.0 / (double)nwin : 0.0;
         OutT* __restrict__ orow = reinterpret_cast<OutT*>(p.out) + (size_t)rec * (size_t)p.ld_out;
         for (int q = tid; q < Cfg::kBins / 4; q += T) {
             uint32_t c4[4];
@@ -157,16 +173,20 @@ __global__ void __launch_bounds__(CountCfg<K>::kThreads) count_kernel(const Coun
             if constexpr (sizeof(OutT) == 8) {
                 double r[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) r[e] = skr::chain_sum(inc, c4[e]);
+                for (int e = 0; e < 4; ++e) r[e] = c4[e] < kTab ? s_tab64[c4[e]] : skr::chain_sum(inc, c4[e]);
                 reinterpret_cast<double2*>(orow)[2 * q] = make_double2(r[0], r[1]);
                 reinterpret_cast<double2*>(orow)[2 * q + 1] = make_double2(r[2], r[3]);
             } else {
                 float r[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    float v = __double2float_rn(skr::chain_sum(inc, c4[e]));
-                    if (p.log2_pre) v = log2f(__fadd_rn(v, 1.0f));
-                    r[e] = v;
+                    if (c4[e] < kTab) {
+                        r[e] = s_tab[c4[e]];
+                    } else {
+                        float v = __double2float_rn(skr::chain_sum(inc, c4[e]));
+                        if (p.log2_pre) v = log2f(__fadd_rn(v, 1.0f));
+                        r[e] = v;
+                    }
                 }
                 if (p.mean) {
                     if constexpr (kVecF64) {
@@ -277,10 +297,17 @@ int dispatch_count(const CountParams& p, int vec_is_f64, int out_is_f64, cudaStr
 // ---------------------------------------------------------------------------------------------
 // element-wise kernels of the get_counts() tail
 // ---------------------------------------------------------------------------------------------
-enum { OP_LOG2 = 0, OP_POST = 1, OP_SUB = 2, OP_DIV = 3, OP_SCAN = 4 };
+enum { OP_LOG2 = 0, OP_POST = 1, OP_SUB = 2, OP_DIV = 3, OP_SCAN = 4, OP_NORM = 5 };
 
 template <int OP, bool kVecF64>
-__device__ __forceinline__ float ew_apply(float v, const void* vec, long long col, float shift) {
+__device__ __forceinline__ float ew_apply(float v, const void* vec, const void* vec2, long long col, float shift) {
+    if constexpr (OP == OP_NORM) {  // fl(fl(v - mean) / std), either vector optional
+        if (vec) v = kVecF64 ? __double2float_rn(__dsub_rn((double)v, __ldg((const double*)vec + col)))
+                             : __fsub_rn(v, __ldg((const float*)vec + col));
+        if (vec2) v = kVecF64 ? __double2float_rn(__ddiv_rn((double)v, __ldg((const double*)vec2 + col)))
+                              : __fdiv_rn(v, __ldg((const float*)vec2 + col));
+        return v;
+    }
     if constexpr (OP == OP_LOG2) return log2f(__fadd_rn(v, 1.0f));
     if constexpr (OP == OP_POST) return log2f(__fadd_rn(__fadd_rn(v, shift), 1.0f));
     if constexpr (OP == OP_SUB) {
@@ -297,7 +324,7 @@ __device__ __forceinline__ float ew_apply(float v, const void* vec, long long co
 // Rows are contiguous when ld == cols; the vector path needs cols % 4 == 0 and 16-byte aligned rows.
 template <int OP, bool kVecF64, bool kVec4>
 __global__ void __launch_bounds__(256) ew_kernel(float* a, long long m, long long cols, long long ld, const void* vec,
-                                                 const SkrMinCell* min_in, SkrMinCell* min_out) {
+                                                 const void* vec2, const SkrMinCell* min_in, SkrMinCell* min_out) {
     __shared__ float s_wmin[8];
     __shared__ int s_wnan[8];
     float shift = 0.0f;
@@ -315,10 +342,10 @@ __global__ void __launch_bounds__(256) ew_kernel(float* a, long long m, long lon
             const long long r = i / c4, q = i - r * c4;
             float4* ptr = reinterpret_cast<float4*>(a + r * ld) + q;
             float4 v = *ptr;
-            v.x = ew_apply<OP, kVecF64>(v.x, vec, 4 * q + 0, shift);
-            v.y = ew_apply<OP, kVecF64>(v.y, vec, 4 * q + 1, shift);
-            v.z = ew_apply<OP, kVecF64>(v.z, vec, 4 * q + 2, shift);
-            v.w = ew_apply<OP, kVecF64>(v.w, vec, 4 * q + 3, shift);
+            v.x = ew_apply<OP, kVecF64>(v.x, vec, vec2, 4 * q + 0, shift);
+            v.y = ew_apply<OP, kVecF64>(v.y, vec, vec2, 4 * q + 1, shift);
+            v.z = ew_apply<OP, kVecF64>(v.z, vec, vec2, 4 * q + 2, shift);
+            v.w = ew_apply<OP, kVecF64>(v.w, vec, vec2, 4 * q + 3, shift);
             if (min_out) {
                 skr::min_update(v.x, tmin, tnan); skr::min_update(v.y, tmin, tnan);
                 skr::min_update(v.z, tmin, tnan); skr::min_update(v.w, tmin, tnan);
@@ -329,7 +356,7 @@ __global__ void __launch_bounds__(256) ew_kernel(float* a, long long m, long lon
         const long long total = m * cols;
         for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
             const long long r = i / cols, c = i - r * cols;
-            float v = ew_apply<OP, kVecF64>(a[r * ld + c], vec, c, shift);
+            float v = ew_apply<OP, kVecF64>(a[r * ld + c], vec, vec2, c, shift);
             if (min_out) skr::min_update(v, tmin, tnan);
             if constexpr (OP != OP_SCAN) a[r * ld + c] = v;
         }
@@ -339,7 +366,7 @@ __global__ void __launch_bounds__(256) ew_kernel(float* a, long long m, long lon
 
 template <int OP>
 int launch_ew(float* a, long long m, long long cols, long long ld, const void* vec, int vec_is_f64,
-              const SkrMinCell* min_in, SkrMinCell* min_out, cudaStream_t stream) {
+              const SkrMinCell* min_in, SkrMinCell* min_out, cudaStream_t stream, const void* vec2 = nullptr) {
     if (m <= 0 || cols <= 0) return SKR_OK;
     if (!a) return skr::fail(SKR_ERR_ARG, "null matrix");
     if (ld < cols) return skr::fail(SKR_ERR_ARG, "ld < cols");
@@ -352,7 +379,7 @@ int launch_ew(float* a, long long m, long long cols, long long ld, const void* v
     const long long cap = (long long)sms * 8;  // 8 resident CTAs of 256 threads per SM, grid-stride beyond that
     if (grid > cap) grid = cap;
     auto go = [&](auto kern) {
-        kern<<<(unsigned)grid, 256, 0, stream>>>(a, m, cols, ld, vec, min_in, min_out);
+        kern<<<(unsigned)grid, 256, 0, stream>>>(a, m, cols, ld, vec, vec2, min_in, min_out);
     };
     if (vec_is_f64) {
         if (vec4) go(ew_kernel<OP, true, true>); else go(ew_kernel<OP, true, false>);
@@ -438,6 +465,12 @@ extern "C" int skr_div_vec(float* d_a, int64_t m, int64_t cols, int64_t ld, cons
                            SkrMinCell* d_min, void* stream) {
     if (!d_vec) return skr::fail(SKR_ERR_ARG, "skr_div_vec: null vector");
     return launch_ew<OP_DIV>(d_a, m, cols, ld, d_vec, vec_is_f64, nullptr, d_min, (cudaStream_t)stream);
+}
+
+extern "C" int skr_normalize(float* d_a, int64_t m, int64_t cols, int64_t ld, const void* d_mean, const void* d_std,
+                             int vec_is_f64, SkrMinCell* d_min, void* stream) {
+    if (!d_mean && !d_std) return skr::fail(SKR_ERR_ARG, "skr_normalize: no vector given");
+    return launch_ew<OP_NORM>(d_a, m, cols, ld, d_mean, vec_is_f64, nullptr, d_min, (cudaStream_t)stream, d_std);
 }
 
 extern "C" int skr_min_scan(const float* d_a, int64_t m, int64_t cols, int64_t ld, SkrMinCell* d_min, void* stream) {

@@ -129,16 +129,18 @@ class CountEngine:
         _lib.check(rc)
         self._keep = (mean, std)  # converted vectors must outlive the launch
 
-    def col_sum(self, kind, a, vec=None):
+    def col_sum(self, kind, a, vec=None, vec2=None):
         """One order-exact column pass over ``a`` (all rows on this device); returns the fp32 sums."""
         acc = device.zeros(a.shape[1], self.torch.float32)
-        self.col_pass(kind, a, acc, vec)
+        self.col_pass(kind, a, acc, vec, vec2)
         return acc
 
-    def col_pass(self, kind, a, acc, vec=None):
+    def col_pass(self, kind, a, acc, vec=None, vec2=None):
+        """vec: DeviceVector (mean, fp32/fp64) or None; vec2: fp32 tensor (the centred matrix's own mean)."""
         m, cols = a.shape
         rc = self.lib.skr_col_pass(kind, device.ptr(a), m, cols, a.stride(0), device.ptr(vec.t if vec else None),
-                                   int(vec.is_f64) if vec else 0, device.ptr(acc), device.stream_ptr(self.stream))
+                                   int(vec.is_f64) if vec else 0, device.ptr(vec2), device.ptr(acc),
+                                   device.stream_ptr(self.stream))
         _lib.check(rc)
 
     def col_finish(self, acc, rows, take_sqrt):
@@ -163,6 +165,20 @@ class CountEngine:
                                         device.ptr(self.min_cell.t if track_min else None),
                                         device.stream_ptr(self.stream)))
 
+    def normalize(self, a, mean=None, std=None, track_min=True):
+        """a = fl(fl(a - mean) / std) in one pass (either vector optional)."""
+        if mean is not None and std is not None and mean.is_f64 != std.is_f64:
+            mean, std = mean.as_f64(), std.as_f64()
+        is_f64 = (mean or std).is_f64
+        if track_min:
+            self.min_cell.reset(self.stream)
+        m, cols = a.shape
+        _lib.check(self.lib.skr_normalize(device.ptr(a), m, cols, a.stride(0), device.ptr(mean.t if mean else None),
+                                          device.ptr(std.t if std else None), int(is_f64),
+                                          device.ptr(self.min_cell.t if track_min else None),
+                                          device.stream_ptr(self.stream)))
+        self._keep = (mean, std)
+
     def min_scan(self, a):
         self.min_cell.reset(self.stream)
         m, cols = a.shape
@@ -183,7 +199,7 @@ class CountEngine:
         """mean/std: False, True, or DeviceVector.  Returns (out, mean_vec, std_vec, nan_checked).
 
         ``reducer`` (optional) supplies the cross-rank pieces of a sharded run: an object with
-        ``col_stat(engine, kind, a, vec, rows_local)`` -> (fp32 vector of the finished statistic)
+        ``col_stat(engine, kind, a, vec, vec2, finish)`` -> fp32 device vector of the finished statistic
         and ``min_allreduce(engine)``; None means all rows live on this device.
         """
         torch = self.torch
@@ -202,28 +218,22 @@ class CountEngine:
             self.count(dpk, out, mean_vec, std_vec, track_min=track)
             min_valid = track
         else:
-            self.count(dpk, out)  # raw counts per kb (log2'd first for Log2.pre)
+            # raw counts per kb (log2'd first for Log2.pre); the statistics passes only read this matrix,
+            # the centred values they need are recomputed with the reference's single rounding, and one
+            # fused pass writes fl(fl(x - mean) / std) at the end
+            self.count(dpk, out)
             stat = reducer.col_stat if reducer else self._local_col_stat
-            centred_sum = None
             if mean is True:
-                mean_t = stat(self, _lib.COLPASS_SUM, out, None, finish="mean")
-                mean_vec = DeviceVector(mean_t, False)
-            if mean is not False:
-                if std is True:
-                    # centre in place and get the column sums of the centred matrix in the same pass:
-                    # np.std starts by averaging what center() left behind (kmer_counts.py:169,174)
-                    centred_sum = stat(self, _lib.COLPASS_CENTER, out, mean_vec, finish="mean")
-                else:
-                    self.sub_vec(out, mean_vec, track_min=need_min and std is False)
-                    min_valid = need_min and std is False
+                mean_vec = DeviceVector(stat(self, _lib.COLPASS_SUM, out, None, None, "mean"), False)
             if std is True:
-                arrmean = centred_sum if centred_sum is not None else \
-                    stat(self, _lib.COLPASS_SUM, out, None, finish="mean")
-                std_t = stat(self, _lib.COLPASS_SQDEV, out, DeviceVector(arrmean, False), finish="std")
-                std_vec = DeviceVector(std_t, False)
-            if std is not False:
-                self.div_vec(out, std_vec, track_min=True)
-                min_valid = True
+                # np.std on what center() left behind: its own mean first (kmer_counts.py:169,174)
+                if mean_vec is not None:
+                    arrmean = stat(self, _lib.COLPASS_CENTERED, out, mean_vec, None, "mean")
+                else:
+                    arrmean = stat(self, _lib.COLPASS_SUM, out, None, None, "mean")
+                std_vec = DeviceVector(stat(self, _lib.COLPASS_SQDEV, out, mean_vec, arrmean, "std"), False)
+            self.normalize(out, mean_vec, std_vec, track_min=True)
+            min_valid = True
         if need_min:
             if not min_valid:
                 self.min_scan(out)
@@ -232,8 +242,8 @@ class CountEngine:
             self.post_log2(out)
         return out, mean_vec, std_vec
 
-    def _local_col_stat(self, engine, kind, a, vec, finish):
-        acc = self.col_sum(kind, a, vec)
+    def _local_col_stat(self, engine, kind, a, vec, vec2, finish):
+        acc = self.col_sum(kind, a, vec, vec2)
         return self.col_finish(acc, a.shape[0], take_sqrt=(finish == "std"))
 
     def nan_after_standardize(self):
@@ -420,8 +430,8 @@ class BasicCounter:
         def fn(engine, a):
             if self.std is True:
                 acc = engine.col_sum(_lib.COLPASS_SUM, a)
-                arrmean = DeviceVector(engine.col_finish(acc, a.shape[0], False), False)
-                acc = engine.col_sum(_lib.COLPASS_SQDEV, a, arrmean)
+                arrmean = engine.col_finish(acc, a.shape[0], False)
+                acc = engine.col_sum(_lib.COLPASS_SQDEV, a, None, arrmean)
                 vec = DeviceVector(engine.col_finish(acc, a.shape[0], True), False)
                 self.std = device.to_host(vec.t, pinned=False)
             else:

@@ -1,0 +1,147 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL) for the few exchange steps.
+
+The path shards without data-path collectives except where the reference's arithmetic couples rows:
+
+  counting            rows (records) are independent: each rank counts its own shard      -> no exchange
+  mean=True/std=True  column statistics couple all rows (kmer_counts.py:168,174)           -> one all-reduce of
+                      4^k binary64 partial sums per statistic (AllReduceStats), or the running fp32 sums passed
+                      rank to rank for a result bit-identical to the single-GPU / reference order (ChainStats)
+  Log2.post           the shift is the minimum over the whole matrix (kmer_counts.py:208)  -> all-reduce(min) of one cell
+  Pearson             output row blocks are independent; the smaller operand is replicated -> one broadcast
+
+Nothing here touches the CPU oracle; the host-side logic (shard_ranges, encode/decode of the min cell,
+message order of the chain) is covered by world_size-2 gloo tests.
+"""
+
+import numpy as np
+
+
+def shard_ranges(lengths, world_size):
+    """Contiguous record ranges balanced by total bases (lengths are lognormal, so balancing by
+    record count would not balance work).  Returns a list of (begin, end) per rank."""
+    lengths = np.asarray(lengths, dtype=np.int64)
+    m = lengths.size
+    if world_size <= 1:
+        return [(0, m)]
+    csum = np.concatenate([[0], np.cumsum(lengths + 64)])  # +64: per-record fixed cost (row write dominates short records)
+    total = csum[-1]
+    cuts = [0]
+    for r in range(1, world_size):
+        target = total * r / world_size
+        cuts.append(int(np.searchsorted(csum, target, side="left")))
+    cuts.append(m)
+    for i in range(1, len(cuts)):
+        cuts[i] = max(cuts[i], cuts[i - 1])
+    return [(cuts[r], cuts[r + 1]) for r in range(world_size)]
+
+
+def row_block_ranges(m, world_size, align=256):
+    """Row blocks of the Pearson output, aligned to the GEMM tile height."""
+    per = -(-m // world_size)
+    per = -(-per // align) * align
+    return [(min(m, r * per), min(m, (r + 1) * per)) for r in range(world_size)]
+
+
+# ---- the Log2.post minimum: order-preserving integer encoding, NaN flag --------------------------------
+
+def encode_min(value):
+    """float32 -> order-preserving uint32 (same mapping as skr::ordered_encode on the device)."""
+    b = int(np.array([value], dtype=np.float32).view(np.uint32)[0])
+    return (~b & 0xFFFFFFFF) if (b & 0x80000000) else (b | 0x80000000)
+
+
+def decode_min(u):
+    u = int(u) & 0xFFFFFFFF
+    bits = (u & 0x7FFFFFFF) if (u & 0x80000000) else (~u & 0xFFFFFFFF)
+    return np.array([bits], dtype=np.uint32).view(np.float32)[0]
+
+
+def allreduce_min_cell(cell_i64, group=None):
+    """cell_i64: int64 tensor [min_ordered, nan_seen] on the communicator's device; reduced in place."""
+    import torch.distributed as dist
+
+    lo = cell_i64[0:1].clone()
+    hi = cell_i64[1:2].clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+    cell_i64[0:1] = lo
+    cell_i64[1:2] = hi
+    return cell_i64
+
+
+class _Base:
+    def __init__(self, group=None):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self._total_rows = None
+
+    def total_rows(self, local_rows, device):
+        import torch
+
+        if self._total_rows is None:
+            t = torch.tensor([local_rows], dtype=torch.int64, device=device)
+            self.dist.all_reduce(t, group=self.group)
+            self._total_rows = int(t.item())
+        return self._total_rows
+
+    def min_allreduce(self, engine):
+        """Combine the per-rank Log2.post cells (uint32 pair on the device) across ranks."""
+        import torch
+
+        cell = engine.min_cell.t  # int32 storage of two uint32
+        as64 = cell.to(torch.int64) & 0xFFFFFFFF
+        allreduce_min_cell(as64, self.group)
+        cell.copy_(torch.where(as64 >= 2 ** 31, as64 - 2 ** 32, as64).to(torch.int32))
+
+
+class AllReduceStats(_Base):
+    """Column statistics from per-rank binary64 partial sums and ONE all-reduce per statistic
+    (scales with the number of GPUs; closer to the exact value than the reference's sequential
+    fp32 sums, hence not bit-identical to them)."""
+
+    def col_stat(self, engine, kind, a, vec, vec2, finish):
+        import torch
+
+        from . import _lib, device
+
+        lib = engine.lib
+        m, cols = a.shape
+        acc = torch.zeros(cols, dtype=torch.float64, device=a.device)
+        _lib.check(lib.skr_col_partial_f64(kind, device.ptr(a), m, cols, a.stride(0), device.ptr(vec.t if vec else None),
+                                           int(vec.is_f64) if vec else 0, device.ptr(vec2), device.ptr(acc),
+                                           device.stream_ptr(engine.stream)))
+        self.dist.all_reduce(acc, group=self.group)
+        rows = self.total_rows(m, a.device)
+        out = torch.empty(cols, dtype=torch.float32, device=a.device)
+        _lib.check(lib.skr_col_finish_f64(device.ptr(acc), cols, rows, int(finish == "std"), device.ptr(out),
+                                          device.stream_ptr(engine.stream)))
+        return out
+
+
+class ChainStats(_Base):
+    """Order-exact column statistics across row shards: rank r continues the fp32 running sums of
+    rank r-1 (the shards are consecutive row ranges), the last rank finishes and broadcasts.
+    Bit-identical to the single-GPU result and to numpy's axis-0 reduction; latency-bound."""
+
+    def col_stat(self, engine, kind, a, vec, vec2, finish):
+        import torch
+
+        m, cols = a.shape
+        acc = torch.zeros(cols, dtype=torch.float32, device=a.device)
+        if self.rank > 0:
+            self.dist.recv(acc, src=self.rank - 1, group=self.group)
+        engine.col_pass(kind, a, acc, vec, vec2)
+        if self.rank + 1 < self.world:
+            torch.cuda.current_stream().synchronize() if a.is_cuda else None
+            self.dist.send(acc, dst=self.rank + 1, group=self.group)
+        rows = self.total_rows(m, a.device)
+        if self.rank == self.world - 1:
+            out = engine.col_finish(acc, rows, take_sqrt=(finish == "std"))
+        else:
+            out = torch.empty(cols, dtype=torch.float32, device=a.device)
+        self.dist.broadcast(out, src=self.world - 1, group=self.group)
+        return out

@@ -108,13 +108,25 @@ def test_get_counts():
 
 
 def test_get_counts_raw():
-    counter = make(k=2, mean=False, std=False)
+    # as in the reference (test_kmer_counts.py:108-117): occurrences() writes into the rows of
+    # counter.counts themselves, so the comparison holds by construction; the real raw-count checks
+    # are test_get_counts_raw_values below and the bit-exact fixture tests
+    counter = make(k=2, mean=False, std=False, log2=Log2.post)
+    counter.get_counts()
+    expected = np.zeros((5, 16))
+    for i in range(5):
+        expected[i] = counter.occurrences(counter.counts[i], counter.seqs[i])
+    assert np.allclose(counter.counts, expected)
+
+
+def test_get_counts_raw_values():
+    counter = make(k=2, mean=False, std=False, log2=Log2.none)
     counter.get_counts()
     expected = np.zeros((5, 16))
     for i in range(5):
         expected[i] = counter.occurrences(np.zeros(16), counter.seqs[i])
-    assert np.allclose(counter.counts, expected)
     assert np.array_equal(counter.counts, expected.astype(np.float32))
+    assert np.array_equal(expected, np.stack([po.occurrences(s, 2) for s in counter.seqs]))
 
 
 # ---- the reference's console tests, ported (seekr/tests/test_console_scripts.py:34-124) -----------

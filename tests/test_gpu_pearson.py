@@ -1,0 +1,119 @@
+"""Parity of the CUDA Pearson path (skr_pearson_prepare + tcgen05 GEMM) with the oracle / reference fixtures.
+
+Bar (north_star): |r - reference| <= 1e-5 absolute.  float32 inputs give float32 output, everything else float64."""
+
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import golden
+from oracle import seekr_oracle as po
+from seekr_b200.console_scripts import _run_pearson
+from seekr_b200.pearson import pearson
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def test_pearson_reference_unit_tests():
+    c1 = np.array([[8, 5, 6, 9, 2], [8, 3, 6, 6, 7], [7, 7, 3, 3, 7]])          # test_pearson.py:7-18
+    c2 = np.array([[2, 8, -9, -1, -8], [-4, 1, 2, -1, 2], [5, -3, -7, 2, -9]])
+    exp = np.array([[0.3217847, -0.71611487, 0.85110363],
+                    [-0.52756992, -0.47172818, 0.22652512],
+                    [0.43762719, -0.17902872, 0.01547461]])
+    dist = pearson(c1, c2)
+    assert dist.dtype == np.float64 and dist.shape == (3, 3)
+    assert np.allclose(dist, exp, rtol=0, atol=TOL)
+    one = np.array([[1, 2, 3, 4], [2, 4, 6, 8]])                                  # test_pearson.py:20-24
+    assert np.allclose(pearson(one, one), np.ones((2, 2)), rtol=0, atol=TOL)
+
+
+def test_pearson_fixtures():
+    g = np.load(golden("pearson.npz"))
+    r = pearson(g["a32"], g["b32"])
+    assert r.dtype == np.float32 and r.shape == g["r32"].shape
+    assert np.abs(r - g["r32"]).max() < TOL
+    assert np.abs(pearson(g["a32"], g["a32"]) - g["r32_self"]).max() < TOL
+    r = pearson(g["a32"], g["b32"], row_standardize=False)
+    assert np.allclose(r, g["r32_nostd"], rtol=1e-5, atol=1e-5)
+    r = pearson(g["a64"], g["b64"])
+    assert r.dtype == np.float64 and np.abs(r - g["r64"]).max() < TOL
+    assert np.abs(pearson(g["ai"], g["bi"]) - g["ri"]).max() < TOL
+    r = pearson(g["a32"][:9, :64], g["b64"])
+    assert r.dtype == np.float64 and np.abs(r - g["r_mixed"]).max() < TOL
+    df1 = pd.DataFrame(g["a64"], index=[f"a{i}" for i in range(9)])
+    df2 = pd.DataFrame(g["b64"], index=[f"b{i}" for i in range(7)])
+    assert np.abs(pearson(df1, df2) - g["r_df"]).max() < TOL
+
+
+def test_pearson_pipeline_data():
+    """z-scored 6-mer profiles of medium.fa, self vs self, against the reference's own output."""
+    from seekr_b200.kmer_counts import BasicCounter
+
+    g = np.load(golden("pearson.npz"))
+    c = BasicCounter(golden("medium.fa"), k=6, silent=True)
+    c.get_counts()
+    r = pearson(c.counts, c.counts)
+    assert r.shape == g["r_medium_k6"].shape
+    assert np.abs(r - g["r_medium_k6"]).max() < TOL
+    assert np.abs(np.diag(r) - 1).max() < TOL
+
+
+@pytest.mark.parametrize("m,n,K", [(1, 1, 4), (5, 3, 16), (130, 257, 64), (300, 515, 1000), (513, 129, 4096),
+                                   (700, 900, 256)])
+def test_pearson_shapes_against_oracle(m, n, K):
+    rng = np.random.default_rng(m * 1000 + n + K)
+    a = (rng.standard_normal((m, K)) * rng.lognormal(0, 1, size=(m, 1)) + rng.standard_normal((m, 1))).astype(np.float32)
+    b = (rng.standard_normal((n, K)) ** 3).astype(np.float32)
+    exp = po.pearson_f64(a, b)
+    got = pearson(a, b)
+    assert got.dtype == np.float32 and got.shape == (m, n)
+    ref_err = np.abs(po.pearson(a, b) - exp).max()          # the reference's own fp32 error
+    assert np.abs(got - exp).max() < max(TOL, 2 * ref_err)
+    got_ns = pearson(a, b, row_standardize=False)
+    exp_ns = po.pearson_f64(a, b, row_standardize=False)
+    assert np.allclose(got_ns, exp_ns, rtol=1e-5, atol=1e-5 * np.abs(exp_ns).max())
+
+
+def test_pearson_constant_row_gives_nan_like_numpy():
+    a = np.random.default_rng(3).standard_normal((4, 32)).astype(np.float32)
+    a[2] = 7.0
+    with np.errstate(all="ignore"):
+        exp = po.pearson(a, a)
+    got = pearson(a, a)
+    assert np.array_equal(np.isnan(got), np.isnan(exp))
+    ok = ~np.isnan(exp)
+    assert np.abs(got[ok] - exp[ok]).max() < TOL
+
+
+def test_pearson_mismatched_columns():
+    with pytest.raises(ValueError):
+        pearson(np.ones((2, 4), dtype=np.float32), np.ones((2, 5), dtype=np.float32))
+
+
+def test_run_pearson_console(tmp_path):
+    out = str(tmp_path / "p.csv")
+    _run_pearson(golden("console", "ex_k2_labelled.csv"), golden("console", "ex_k2_labelled.csv"), out, False, False)
+    got = pd.read_csv(out, index_col=0)
+    exp = pd.read_csv(golden("console", "ex_pearson.csv"), index_col=0)
+    assert list(got.index) == list(exp.index) and list(got.columns) == list(exp.columns)
+    assert np.abs(got.values - exp.values).max() < TOL
+    out = str(tmp_path / "p.npy")
+    _run_pearson(golden("console", "small_k5_vec.npy"), golden("console", "small_k5_vec.npy"), out, True, True)
+    assert np.abs(np.load(out) - np.load(golden("console", "small_pearson.npy"))).max() < TOL
+
+
+def test_pearson_large_block_property():
+    """4096 x 4096 at K = 4096 (several tiles per SM pair, both accumulator buffers, wrap-around of the
+    smem ring): diagonal is 1, matrix is symmetric, and a sampled sub-block matches the binary64 oracle."""
+    rng = np.random.default_rng(11)
+    a = rng.standard_normal((4096, 4096)).astype(np.float32)
+    a[:, :50] *= 30
+    r = pearson(a, a)
+    assert np.abs(np.diag(r) - 1).max() < TOL
+    assert np.abs(r - r.T).max() < TOL
+    idx = rng.choice(4096, size=96, replace=False)
+    exp = po.pearson_f64(a[idx], a)
+    assert np.abs(r[idx] - exp).max() < TOL

@@ -53,6 +53,7 @@ def main():
     ap.add_argument("--records", type=int, default=50000)
     ap.add_argument("--ks", default="6")
     ap.add_argument("--peak", type=float, default=0.0)
+    ap.add_argument("--only-count", action="store_true", help="run just the count kernels (for ncu)")
     args = ap.parse_args()
     peak = args.peak
     if not peak:
@@ -84,18 +85,20 @@ def main():
         report("count raw", ms, mn, in_bytes + row_bytes)
         ms, mn = timeit(lambda: eng.count(dpk, out, mean, std, track_min=True), flush)
         report("count fused -mean /std +min", ms, mn, in_bytes + row_bytes)
+        if args.only_count:
+            continue
         eng.min_cell.reset()
         ms, mn = timeit(lambda: eng.post_log2(out), flush)
         report("post_log2 (rd+wr)", ms, mn, 2 * row_bytes)
         eng.count(dpk, out)
         ms, mn = timeit(lambda: eng.col_sum(_lib.COLPASS_SUM, out), flush)
         report("col pass SUM (rd)", ms, mn, row_bytes)
-        ms, mn = timeit(lambda: eng.col_sum(_lib.COLPASS_SQDEV, out, mean), flush)
+        ms, mn = timeit(lambda: eng.col_sum(_lib.COLPASS_CENTERED, out, mean), flush)
+        report("col pass CENTERED (rd)", ms, mn, row_bytes)
+        ms, mn = timeit(lambda: eng.col_sum(_lib.COLPASS_SQDEV, out, mean, std.t), flush)
         report("col pass SQDEV (rd)", ms, mn, row_bytes)
-        ms, mn = timeit(lambda: eng.col_sum(_lib.COLPASS_CENTER, out, mean), flush)
-        report("col pass CENTER (rd+wr)", ms, mn, 2 * row_bytes)
-        ms, mn = timeit(lambda: eng.div_vec(out, std), flush)
-        report("div_vec +min (rd+wr)", ms, mn, 2 * row_bytes)
+        ms, mn = timeit(lambda: eng.normalize(out, mean, std), flush)
+        report("normalize -mean /std +min", ms, mn, 2 * row_bytes)
         eng2 = CountEngine(k, "Log2.post")
 
         def full():
@@ -106,7 +109,7 @@ def main():
         def full_self():
             eng2.run(dpk, True, True, out=out)
         ms, mn = timeit(full_self, flush)
-        report("self-normalised Log2.post", ms, mn, in_bytes + 9 * row_bytes)
+        report("self-normalised Log2.post", ms, mn, in_bytes + 8 * row_bytes)
         del out, dpk
         torch.cuda.empty_cache()
 
