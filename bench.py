@@ -1,0 +1,431 @@
+#!/usr/bin/env python
+"""bench.py -- the measurement contract for the SEEKR hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): synthetic GENCODE-lncRNA-shaped set, 50 000 transcripts per GPU
+(lognormal length 500 bp - 20 kb, seed 50000 + rank), k = 6.  One step =
+    A. norm_vectors   counts -> order-exact column mean/std -> fused normalise -> Log2.post
+                      (BasicCounter(fasta, k=6).get_counts(), what seekr_norm_vectors runs)
+    B. count + norm   counts with the mean/std vectors of A, Log2.post  (seekr_kmer_counts -mv -sv)
+    C. Pearson        the normalised matrix of B against the reference set (rank 0's matrix), m x n, K = 4096
+`value` is transcripts/s of phase B with the packed input already in HBM (the BASELINE metric
+"transcripts/s (6-mer count+norm)"); Pearson pairs/s and the norm_vectors rate are reported in the same
+line under "pearson" / "norm_vectors".  `e2e` is the same metric through the public API
+(BasicCounter(fasta).get_counts() / pearson(counts, counts)) from a FASTA file to host numpy arrays.
+Device times are CUDA events on the launching stream, max over ranks; L2 is flushed between steps.
+"""
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+K_MER = 6
+METRIC = "transcripts/s (6-mer count+norm)"
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as handle:
+            d = json.load(handle)
+        return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d["bf16_tflops"]),
+                "bf16_tflops_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "source": "measured"}
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def algorithmic_bytes(lengths, k, log2_post):
+    """per transcript ceil(L/4) codes + ceil(L/8) mask + 12 (offset, length) + 4*4^k output row;
+    the Log2.post pass adds a read and a write of the row."""
+    lengths = np.asarray(lengths, dtype=np.int64)
+    per = (lengths + 3) // 4 + (lengths + 7) // 8 + 12 + 4 * 4 ** k
+    count = float(per.sum())
+    post = float(2 * 4 * 4 ** k * lengths.size) if log2_post else 0.0
+    return count, post
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [v for v in sm if v > 0]
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ==================================================================================================
+# CPU side: the oracle port timed on the host cores (cpu_baseline leg and --impl reference)
+# ==================================================================================================
+
+def cpu_count_norm(letters, offs, mean, std, threads=0):
+    """The reference's count+normalise path restated in C (oracle/skr_oracle.c), all host threads."""
+    from oracle import c_oracle
+
+    t0 = time.perf_counter()
+    raw = c_oracle.raw_counts(None, K_MER, letters=letters, offs=offs, threads=threads)
+    out, _, _ = c_oracle.normalise(raw, mean, std, "Log2.post")
+    return time.perf_counter() - t0, out
+
+
+def cpu_python_loop_rate(letters, offs, n=150):
+    """The reference's own pure-Python loop (oracle/seekr_oracle.py restates it line by line): one core."""
+    from oracle import seekr_oracle as po
+
+    text = letters[:int(offs[n])].tobytes().decode("ascii")
+    seqs = [text[int(offs[i]):int(offs[i + 1])] for i in range(n)]
+    t0 = time.perf_counter()
+    po.get_counts(seqs, k=K_MER, mean=False, std=False, log2="Log2.none")
+    return n / (time.perf_counter() - t0)
+
+
+def cpu_pearson(rows, cols, seed=7):
+    from oracle import seekr_oracle as po
+
+    rng = np.random.default_rng(seed)
+    a = rng.standard_normal((rows, cols), dtype=np.float32)
+    po.pearson(a[:256], a[:256])
+    t0 = time.perf_counter()
+    po.pearson(a, a)
+    return time.perf_counter() - t0
+
+
+def cpu_vectors(letters, offs):
+    from oracle import c_oracle
+
+    raw = c_oracle.raw_counts(None, K_MER, letters=letters, offs=offs)
+    _, mean, std = c_oracle.normalise(raw, True, True, "Log2.none")
+    return mean, std
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port) on the box's host cores, same metric."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import c_oracle
+    from seekr_b200 import synth
+
+    cores = c_oracle.max_threads()
+    sample = min(args.records, 20000)
+    letters, offs = synth.sequences_bytes(sample, seed=50000)
+    mean, std = cpu_vectors(letters, offs)
+    for _ in range(args.warmup):
+        cpu_count_norm(letters, offs, mean, std)
+    times = [cpu_count_norm(letters, offs, mean, std)[0] for _ in range(args.steps)]
+    value = sample / float(np.mean(times))
+    prow = min(6000, args.records)
+    tp = cpu_pearson(prow, 4 ** K_MER)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "transcripts/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(times)) * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 chain -> f32", "data": "synthetic",
+        "config": {"workload": "synthetic lncRNA-shaped transcripts, k=6, count + normalise with mean/std vectors, Log2.post",
+                   "records": sample, "k": K_MER},
+        "cpu_baseline": {"value": value, "unit": "transcripts/s", "cores": cores, "kind": "port",
+                         "sample": "%d of the %d transcripts per step, C restatement of the reference (oracle/skr_oracle.c), "
+                                   "OpenMP over records; the reference itself is single-threaded Python" % (sample, args.records)},
+        "pearson": {"metric": "Pearson pairs/s", "value": prow * prow / tp, "unit": "pairs/s",
+                    "sample": "%d x %d, K=4096, numpy (OpenBLAS sgemm), all cores" % (prow, prow)},
+        "e2e": {"value": value, "unit": "transcripts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ==================================================================================================
+# GPU side
+# ==================================================================================================
+
+def pack_on_host(letters, offs):
+    from seekr_b200 import _lib
+    from seekr_b200.fasta_reader import PackedFasta, alphabet_lut
+
+    lib = _lib.load()
+    lut = alphabet_lut("AGTC")
+    out = ctypes.c_void_p()
+    _lib.check(lib.skr_pack_sequences(ctypes.c_void_p(letters.ctypes.data), ctypes.c_void_p(offs.ctypes.data),
+                                      len(offs) - 1, ctypes.c_void_p(lut.ctypes.data), 0, 1, ctypes.byref(out)))
+    return PackedFasta(out, None)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from seekr_b200 import _lib, device, parallel, synth
+    from seekr_b200 import pearson as skr_pearson
+    from seekr_b200.kmer_counts import BasicCounter, CountEngine, DeviceVector
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device; there is no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    lib = _lib.load()
+    peaks = measured_peaks()
+
+    m = args.records
+    cols = 4 ** K_MER
+    letters, offs = synth.sequences_bytes(m, seed=50000 + rank)
+    lengths = np.diff(offs)
+    packed = pack_on_host(letters, offs)
+
+    eng_vec = CountEngine(K_MER, "Log2.post")      # phase A
+    eng_cnt = CountEngine(K_MER, "Log2.post")      # phase B
+    dpk = eng_cnt.upload(packed)
+    out_a = device.empty((m, cols), torch.float32)
+    out_b = device.empty((m, cols), torch.float32)
+    n_ref = args.pearson_n if args.pearson_n else m
+    r_dev = device.empty((m, n_ref), torch.float32)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    reducer = parallel.AllReduceStats() if world > 1 else None
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    kern_count_ms, kern_gemm_ms = [], []
+
+    def step(timed):
+        flush.zero_()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e = [ev() for _ in range(8)]
+        # ---- A: norm_vectors --------------------------------------------------------------------
+        e[0].record()
+        _, mean_vec, std_vec = eng_vec.run(dpk, True, True, out=out_a, reducer=reducer)
+        e[1].record()
+        # ---- B: count + normalise with the vectors, Log2.post ------------------------------------
+        e[2].record()
+        eng_cnt.count(dpk, out_b, mean_vec, std_vec, track_min=True)
+        e[3].record()
+        if reducer:
+            reducer.min_allreduce(eng_cnt)
+        eng_cnt.post_log2(out_b)
+        e[4].record()
+        # ---- C: Pearson against the reference set (rank 0's matrix) ------------------------------
+        pa = skr_pearson.prepare(out_b, True)
+        if world > 1:
+            pb = skr_pearson.PreparedRows(pa.rows, pa.K, pa.hi.clone(), pa.lo.clone(), pa.scale.clone())
+            for t in (pb.hi, pb.lo, pb.scale):
+                dist.broadcast(t, src=0)
+        else:
+            pb = pa
+        if n_ref != m:
+            pb = skr_pearson.PreparedRows(n_ref, pb.K, pb.hi, pb.lo, pb.scale)
+        e[5].record()
+        skr_pearson.gemm_block(pa, 0, m, pb, r_dev, 1.0 / cols)
+        e[6].record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        if timed:
+            kern_count_ms.append(e[2].elapsed_time(e[3]))
+            kern_gemm_ms.append(e[5].elapsed_time(e[6]))
+        return e[0].elapsed_time(e[1]), e[2].elapsed_time(e[4]), e[4].elapsed_time(e[6])
+
+    for _ in range(args.warmup):
+        step(False)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    lib.skr_launch_count(1)
+    tot = np.zeros(3)
+    for _ in range(args.steps):
+        tot += np.array(step(True))
+    launches = int(lib.skr_launch_count(0))
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor(list(tot) + [float(np.mean(kern_count_ms)), float(np.mean(kern_gemm_ms))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_a, t_b, t_c, k_count, k_gemm = (float(v) for v in t.cpu())
+    t_a, t_b, t_c = t_a / args.steps, t_b / args.steps, t_c / args.steps
+
+    # ---- end to end through the public API (FASTA file -> host numpy), every rank on its own shard -----
+    tmpdir = tempfile.mkdtemp(prefix="skr_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    fasta = os.path.join(tmpdir, "shard%d.fa" % rank)
+    fasta_bytes = synth.write_fasta(fasta, m, seed=50000 + rank)
+    mean_host = device.to_host(mean_vec.t, pinned=False)
+    std_host = device.to_host(std_vec.t, pinned=False)
+    e2e_times, e2e_p_times = [], []
+    counts_host = None
+    p_rows = min(m, args.e2e_pearson_rows)
+    for it in range(1 + max(1, min(args.steps, 3))):
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        counter = BasicCounter(fasta, k=K_MER, mean=mean_host, std=std_host, log2="Log2.post", silent=True)
+        counter.get_counts()
+        t1 = time.perf_counter()
+        counts_host = counter.counts
+        slab_bytes = counter._packed.slab_bytes
+        sub = counts_host[:p_rows]
+        r_host = skr_pearson.pearson(sub, sub)
+        t2 = time.perf_counter()
+        if it > 0:  # first pass warms the pinned pools
+            e2e_times.append(t1 - t0)
+            e2e_p_times.append(t2 - t1)
+        del r_host, counter
+    e2e_t = torch.tensor([float(np.mean(e2e_times)), float(np.mean(e2e_p_times))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_count_s, e2e_pearson_s = (float(v) for v in e2e_t.cpu())
+    try:
+        os.remove(fasta)
+        os.rmdir(tmpdir)
+    except OSError:
+        pass
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle port on the host cores --------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import c_oracle
+
+        cores = c_oracle.max_threads()
+        sample = min(m, 20000)
+        sl, so = letters[:int(offs[sample])], offs[:sample + 1].copy()
+        t_cpu, cpu_out = cpu_count_norm(sl, so, mean_host, std_host)
+        parity = float(np.abs(cpu_out - counts_host[:sample]).max())
+        py_rate = cpu_python_loop_rate(letters, offs)
+        prow = min(6000, m)
+        t_cpu_p = cpu_pearson(prow, cols)
+        cpu = {"value": sample / t_cpu, "unit": "transcripts/s", "cores": cores, "kind": "port",
+               "sample": "first %d of the %d transcripts, C restatement of the reference (oracle/skr_oracle.c) with OpenMP "
+                         "over records; max |gpu - cpu| on that sample = %.2e" % (sample, m, parity),
+               "reference_python_loop": {"value": py_rate, "unit": "transcripts/s", "cores": 1,
+                                         "sample": "150 transcripts, raw counts, the reference's pure-Python loop"},
+               "pearson": {"value": prow * prow / t_cpu_p, "unit": "pairs/s", "cores": cores,
+                           "sample": "%d x %d, K=4096, numpy OpenBLAS sgemm" % (prow, prow)}}
+
+    count_bytes, post_bytes = algorithmic_bytes(lengths, K_MER, True)
+    ach = count_bytes / (k_count * 1e-3) / 1e9
+    flops = 2.0 * m * n_ref * cols
+    gemm_tf = flops / (k_gemm * 1e-3) / 1e12
+    total_tr = m * world
+    line = {
+        "metric": METRIC,
+        "value": total_tr / (t_b * 1e-3),
+        "unit": "transcripts/s",
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": t_a + t_b + t_c,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "u16 counts -> f64 per-kb chain -> f32 (counting); f16 hi/lo split x3 MMAs -> f32 (Pearson)",
+        "data": "synthetic",
+        "config": {"workload": "configs[1]: synthetic lncRNA-shaped set, k=6: norm_vectors + counts (mean/std vectors, Log2.post) "
+                               "+ Pearson vs the reference set", "records_per_gpu": m, "k": K_MER,
+                   "mean_length": float(lengths.mean()), "pearson_m_per_gpu": m, "pearson_n": n_ref, "pearson_K": cols,
+                   "sharding": "records per rank (counting), output row blocks per rank (Pearson)",
+                   "column_stats": "order-exact (bit-identical to numpy)" if world == 1 else "binary64 partials + one all-reduce",
+                   "l2": "flushed between steps (256 MiB write)"},
+        "phases_ms": {"norm_vectors": t_a, "count_norm": t_b, "pearson": t_c},
+        "norm_vectors": {"value": total_tr / (t_a * 1e-3), "unit": "transcripts/s"},
+        "pearson": {"metric": "Pearson pairs/s", "value": world * m * n_ref / (t_c * 1e-3), "unit": "pairs/s",
+                    "gemm_kernel_ms": k_gemm,
+                    "roofline": {"bound": "tensor", "achieved": gemm_tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                                 "frac": gemm_tf / peaks["bf16_tflops_sustained"], "traffic": None,
+                                 "executed_tflops": 3 * gemm_tf, "executed_frac": 3 * gemm_tf / peaks["bf16_tflops_sustained"],
+                                 "note": "achieved = algorithmic 2*m*n*K / GEMM kernel time; 3 fp16 MMAs are executed per "
+                                         "algorithmic product (hi*hi + hi*lo + lo*hi); peak = %s sustained dense bf16/fp16"
+                                         % peaks["source"]},
+                    "e2e": {"value": world * p_rows * p_rows / e2e_pearson_s, "unit": "pairs/s", "rows": p_rows,
+                            "h2d_bytes_per_step": p_rows * cols * 4, "d2h_bytes_per_step": p_rows * p_rows * 4}},
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                     "traffic": None, "kernel": "count_kernel<6> (fused -mean, /std, min)", "kernel_ms": k_count,
+                     "algorithmic_bytes_per_launch": count_bytes, "peak_source": peaks["source"]},
+        "cpu_baseline": cpu,
+        "e2e": {"value": total_tr / e2e_count_s, "unit": "transcripts/s", "h2d_bytes_per_step": int(slab_bytes + 2 * cols * 4),
+                "d2h_bytes_per_step": int(m * cols * 4), "fasta_bytes": int(fasta_bytes),
+                "path": "BasicCounter(fasta, k=6, mean=vec, std=vec, log2='Log2.post').get_counts() -> numpy"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--records", type=int, default=50000, help="transcripts per GPU")
+    ap.add_argument("--pearson-n", type=int, default=0, help="rows of the Pearson reference set (default: records)")
+    ap.add_argument("--e2e-pearson-rows", type=int, default=16384,
+                    help="rows of the end-to-end pearson() call (host round trip of rows^2 floats)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -47,7 +47,76 @@ struct CountParams {
     SkrMinCell* min_cell;
     unsigned int* work_counter;
     uint32_t* spill;  // [gridDim.x][kBins] 32-bit counts for records longer than one segment
+    // records the warp kernel hands over to the CTA kernel (too long for one warp): list + its length
+    uint32_t* long_list;
+    unsigned int* long_count;
 };
+
+// counts of 4 consecutive bins -> the reference's float32 values (per-kb chain, log2.pre, -mean, /std)
+template <bool kVecF64>
+__device__ __forceinline__ void finish4(const uint32_t (&c4)[4], const float* tab, double inc, const CountParams& p, int q,
+                                        float (&r)[4]) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        if (c4[e] < kTab) {
+            r[e] = tab[c4[e]];
+        } else {
+            float v = __double2float_rn(skr::chain_sum(inc, c4[e]));
+            if (p.log2_pre) v = log2f(__fadd_rn(v, 1.0f));
+            r[e] = v;
+        }
+    }
+    if (p.mean) {
+        if constexpr (kVecF64) {
+            const double* mv = reinterpret_cast<const double*>(p.mean) + 4 * q;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) r[e] = __double2float_rn(__dsub_rn((double)r[e], __ldg(mv + e)));
+        } else {
+            const float4 mv = __ldg(reinterpret_cast<const float4*>(p.mean) + q);
+            r[0] = __fsub_rn(r[0], mv.x); r[1] = __fsub_rn(r[1], mv.y);
+            r[2] = __fsub_rn(r[2], mv.z); r[3] = __fsub_rn(r[3], mv.w);
+        }
+    }
+    if (p.std_) {
+        if constexpr (kVecF64) {
+            const double* sv = reinterpret_cast<const double*>(p.std_) + 4 * q;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) r[e] = __double2float_rn(__ddiv_rn((double)r[e], __ldg(sv + e)));
+        } else {
+            const float4 sv = __ldg(reinterpret_cast<const float4*>(p.std_) + q);
+            r[0] = __fdiv_rn(r[0], sv.x); r[1] = __fdiv_rn(r[1], sv.y);
+            r[2] = __fdiv_rn(r[2], sv.z); r[3] = __fdiv_rn(r[3], sv.w);
+        }
+    }
+}
+
+// 16 window starts of one chunk -> shared-memory histogram (two 16-bit sub-counters per word).
+// x: 32 bases (2 bits each, first base in the top bits); mb: the chunk's 16+K-1 mask bits; nv: valid windows.
+template <int K>
+__device__ __forceinline__ void count_chunk(uint32_t* hist, uint64_t x, uint32_t mb, int nv) {
+    constexpr uint32_t kMask = (1u << (2 * K)) - 1;
+    if (mb == 0 && nv == 16) {
+        // all 16 + K - 1 bases equal (homopolymer run): one add of 16 instead of 16 colliding adds
+        const uint64_t same = (x ^ (x << 2)) >> (64 - 2 * (16 + K - 2));
+        if (same == 0) {
+            const uint32_t kmer = (uint32_t)(x >> (64 - 2 * K)) & kMask;
+            atomicAdd(&hist[kmer >> 1], 16u << ((kmer & 1) * 16));
+            return;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const uint32_t kmer = (uint32_t)(x >> (64 - 2 * (j + K))) & kMask;
+            atomicAdd(&hist[kmer >> 1], 1u << ((kmer & 1) * 16));
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const uint32_t kmer = (uint32_t)(x >> (64 - 2 * (j + K))) & kMask;
+            const uint32_t bad = (mb >> (16 - 1 - j)) & ((1u << K) - 1);
+            if (j < nv && bad == 0) atomicAdd(&hist[kmer >> 1], 1u << ((kmer & 1) * 16));
+        }
+    }
+}
 
 template <int K, bool kVecF64, typename OutT>
 __global__ void __launch_bounds__(CountCfg<K>::kThreads) count_kernel(const CountParams p) {
@@ -68,7 +137,11 @@ __global__ void __launch_bounds__(CountCfg<K>::kThreads) count_kernel(const Coun
     uint32_t* spill = p.spill + (size_t)blockIdx.x * Cfg::kBins;
 
     for (;;) {
-        if (tid == 0) s_rec = (long long)atomicAdd(p.work_counter, 1u);
+        if (tid == 0) {
+            long long r = (long long)atomicAdd(p.work_counter, 1u);
+            if (p.long_list) r = r < (long long)*p.long_count ? (long long)p.long_list[r] : p.m;
+            s_rec = r;
+        }
         __syncthreads();  // also orders the previous record's histogram reads before the zeroing below
         const long long rec = s_rec;
         if (rec >= p.m) break;
@@ -110,36 +183,7 @@ __global__ void __launch_bounds__(CountCfg<K>::kThreads) count_kernel(const Coun
                 const uint32_t mb = (uint32_t)((m64 << (16 * (int)(c & 1))) >> (64 - (16 + K - 1)));
                 const long long left = nwin - c * 16;
                 const int nv = left < 16 ? (int)left : 16;
-                uint32_t prev = 0xFFFFFFFFu, run = 0;
-                if (mb == 0 && nv == 16) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const uint32_t kmer = (uint32_t)(x >> (64 - 2 * (j + K))) & (Cfg::kBins - 1);
-                        if (kmer == prev) {
-                            ++run;
-                        } else {
-                            if (run) atomicAdd(&hist[prev >> 1], run << ((prev & 1) * 16));
-                            prev = kmer;
-                            run = 1;
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const uint32_t kmer = (uint32_t)(x >> (64 - 2 * (j + K))) & (Cfg::kBins - 1);
-                        const uint32_t bad = (mb >> (16 - 1 - j)) & ((1u << K) - 1);
-                        if (j < nv && bad == 0) {
-                            if (kmer == prev) {
-                                ++run;
-                            } else {
-                                if (run) atomicAdd(&hist[prev >> 1], run << ((prev & 1) * 16));
-                                prev = kmer;
-                                run = 1;
-                            }
-                        }
-                    }
-                }
-                if (run) atomicAdd(&hist[prev >> 1], run << ((prev & 1) * 16));
+                count_chunk<K>(hist, x, mb, nv);
             }
             __syncthreads();
             if (nseg > 1) {
@@ -178,38 +222,7 @@ __global__ void __launch_bounds__(CountCfg<K>::kThreads) count_kernel(const Coun
                 reinterpret_cast<double2*>(orow)[2 * q + 1] = make_double2(r[2], r[3]);
             } else {
                 float r[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    if (c4[e] < kTab) {
-                        r[e] = s_tab[c4[e]];
-                    } else {
-                        float v = __double2float_rn(skr::chain_sum(inc, c4[e]));
-                        if (p.log2_pre) v = log2f(__fadd_rn(v, 1.0f));
-                        r[e] = v;
-                    }
-                }
-                if (p.mean) {
-                    if constexpr (kVecF64) {
-                        const double* mv = reinterpret_cast<const double*>(p.mean) + 4 * q;
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) r[e] = __double2float_rn(__dsub_rn((double)r[e], __ldg(mv + e)));
-                    } else {
-                        const float4 mv = __ldg(reinterpret_cast<const float4*>(p.mean) + q);
-                        r[0] = __fsub_rn(r[0], mv.x); r[1] = __fsub_rn(r[1], mv.y);
-                        r[2] = __fsub_rn(r[2], mv.z); r[3] = __fsub_rn(r[3], mv.w);
-                    }
-                }
-                if (p.std_) {
-                    if constexpr (kVecF64) {
-                        const double* sv = reinterpret_cast<const double*>(p.std_) + 4 * q;
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) r[e] = __double2float_rn(__ddiv_rn((double)r[e], __ldg(sv + e)));
-                    } else {
-                        const float4 sv = __ldg(reinterpret_cast<const float4*>(p.std_) + q);
-                        r[0] = __fdiv_rn(r[0], sv.x); r[1] = __fdiv_rn(r[1], sv.y);
-                        r[2] = __fdiv_rn(r[2], sv.z); r[3] = __fdiv_rn(r[3], sv.w);
-                    }
-                }
+                finish4<kVecF64>(c4, s_tab, inc, p, q, r);
                 if (p.min_cell) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) skr::min_update(r[e], tmin, tnan);
@@ -223,6 +236,119 @@ __global__ void __launch_bounds__(CountCfg<K>::kThreads) count_kernel(const Coun
     if (p.min_cell) skr::min_commit<T>(tmin, tnan, s_wmin, s_wnan, p.min_cell);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Warp-per-record variant for k <= 6.  A record of a few thousand bases is too little work for a
+// CTA: the CTA kernel above spends its time in barriers and serialized latencies (work counter,
+// lengths, offsets, codes).  Here every warp owns a private histogram (<= 8 KB) and runs records
+// end to end with no block-level synchronisation; the next record's index and metadata are
+// fetched while the current one is processed.  Records longer than kLongWin windows are pushed
+// to a list that the CTA kernel drains afterwards (256 threads and the 32-bit spill path).
+// ---------------------------------------------------------------------------------------------
+constexpr long long kLongWin = 32768;
+
+template <int K>
+struct WarpCfg {
+    static constexpr int kBins = 1 << (2 * K);
+    static constexpr int kWords = kBins / 2;
+    static constexpr int kWarps = K == 6 ? 4 : 8;
+    static constexpr int kThreads = 32 * kWarps;
+    static constexpr size_t kSmem = (size_t)kWarps * (kWords * 4 + kTab * 4);
+};
+
+template <int K, bool kVecF64>
+__global__ void __launch_bounds__(WarpCfg<K>::kThreads) count_warp_kernel(const CountParams p) {
+    using Cfg = WarpCfg<K>;
+    extern __shared__ __align__(16) uint32_t smem_w[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* hist = smem_w + warp * Cfg::kWords;
+    float* tab = reinterpret_cast<float*>(smem_w + Cfg::kWarps * Cfg::kWords) + warp * kTab;
+    float tmin = INFINITY;
+    int tnan = 0;
+
+    auto fetch = [&]() -> long long {
+        unsigned int r = 0;
+        if (lane == 0) r = atomicAdd(p.work_counter, 1u);
+        return (long long)__shfl_sync(0xFFFFFFFFu, r, 0);
+    };
+    long long rec = fetch();
+    uint32_t L = 0;
+    uint64_t b0 = 0;
+    if (rec < p.m) { L = __ldg(p.len + rec); b0 = __ldg(p.blk_off + rec); }
+
+    while (rec < p.m) {
+        const long long next = fetch();  // in flight while this record is processed
+        const long long nwin = (long long)L - K + 1;
+        if (nwin > kLongWin) {
+            if (lane == 0) p.long_list[atomicAdd(p.long_count, 1u)] = (uint32_t)rec;
+        } else {
+            const uint32_t* __restrict__ cw = p.codes + b0 * 4;
+            const uint32_t* __restrict__ mw = p.mask + b0 * 2;
+            const int nchunks = nwin > 0 ? (int)((nwin + 15) / 16) : 0;
+            // first chunk's words are requested before the histogram is cleared
+            uint32_t w0 = 0, w1 = 0, m0 = 0, m1 = 0;
+            if (lane < nchunks) {
+                w0 = __ldg(cw + lane); w1 = __ldg(cw + lane + 1);
+                m0 = __ldg(mw + (lane >> 1)); m1 = __ldg(mw + (lane >> 1) + 1);
+            }
+            if constexpr (Cfg::kWords % 128 == 0) {
+                for (int i = lane; i < Cfg::kWords / 4; i += 32) reinterpret_cast<uint4*>(hist)[i] = make_uint4(0, 0, 0, 0);
+            } else {
+                for (int i = lane; i < Cfg::kWords; i += 32) hist[i] = 0;
+            }
+            const double inc = nwin > 0 ? 1000.0 / (double)nwin : 0.0;
+#pragma unroll
+            for (int c = lane; c < kTab; c += 32) {
+                float v = __double2float_rn(skr::chain_sum(inc, (uint32_t)c));
+                if (p.log2_pre) v = log2f(__fadd_rn(v, 1.0f));
+                tab[c] = v;
+            }
+            __syncwarp();
+            for (int c = lane; c < nchunks; c += 32) {
+                const int cn = c + 32;
+                uint32_t n0 = 0, n1 = 0, q0 = 0, q1 = 0;
+                if (cn < nchunks) {  // next iteration's words
+                    n0 = __ldg(cw + cn); n1 = __ldg(cw + cn + 1);
+                    q0 = __ldg(mw + (cn >> 1)); q1 = __ldg(mw + (cn >> 1) + 1);
+                }
+                const uint64_t x = ((uint64_t)w0 << 32) | w1;
+                const uint64_t m64 = ((uint64_t)m0 << 32) | m1;
+                const uint32_t mb = (uint32_t)((m64 << (16 * (c & 1))) >> (64 - (16 + K - 1)));
+                const long long left = nwin - (long long)c * 16;
+                count_chunk<K>(hist, x, mb, left < 16 ? (int)left : 16);
+                w0 = n0; w1 = n1; m0 = q0; m1 = q1;
+            }
+            __syncwarp();
+            float* __restrict__ orow = reinterpret_cast<float*>(p.out) + (size_t)rec * (size_t)p.ld_out;
+            for (int q = lane; q < Cfg::kBins / 4; q += 32) {
+                const uint2 v = reinterpret_cast<const uint2*>(hist)[q];
+                const uint32_t c4[4] = {v.x & 0xFFFFu, v.x >> 16, v.y & 0xFFFFu, v.y >> 16};
+                float r[4];
+                finish4<kVecF64>(c4, tab, inc, p, q, r);
+                if (p.min_cell) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) skr::min_update(r[e], tmin, tnan);
+                }
+                reinterpret_cast<float4*>(orow)[q] = make_float4(r[0], r[1], r[2], r[3]);
+            }
+            __syncwarp();  // histogram and table are reused by the next record
+        }
+        rec = next;
+        if (rec < p.m) { L = __ldg(p.len + rec); b0 = __ldg(p.blk_off + rec); }
+    }
+    if (p.min_cell) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            tmin = fminf(tmin, __shfl_xor_sync(0xFFFFFFFFu, tmin, o));
+            tnan |= __shfl_xor_sync(0xFFFFFFFFu, tnan, o);
+        }
+        if (lane == 0) {
+            if (tmin < INFINITY) atomicMin(&p.min_cell->min_ordered, skr::ordered_encode(tmin));
+            if (tnan) atomicOr(&p.min_cell->nan_seen, 1u);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // per-device scratch: work counters (a ring, so launches on different streams do not share one)
 // and the per-CTA spill rows
@@ -232,15 +358,24 @@ struct DeviceScratch {
     int next_counter = 0;
     uint32_t* spill = nullptr;
     size_t spill_bytes = 0;
+    uint32_t* long_list = nullptr;
+    size_t long_cap = 0;
     int num_sms = 0;
 };
-constexpr int kCounterRing = 256;
+constexpr int kCounterRing = 1024;  // 4 counters per launch
 std::mutex g_scratch_mu;
 std::unordered_map<int, DeviceScratch> g_scratch;
 
-int get_scratch(int dev, size_t spill_bytes, DeviceScratch** out) {
+int get_scratch(int dev, size_t spill_bytes, size_t long_cap, DeviceScratch** out) {
     std::lock_guard<std::mutex> lock(g_scratch_mu);
     DeviceScratch& s = g_scratch[dev];
+    if (s.long_cap < long_cap) {
+        if (s.long_list) SKR_CUDA_CHECK(cudaFree(s.long_list));
+        s.long_list = nullptr;
+        s.long_cap = 0;
+        SKR_CUDA_CHECK(cudaMalloc(&s.long_list, long_cap * sizeof(uint32_t)));
+        s.long_cap = long_cap;
+    }
     if (!s.counters) {
         SKR_CUDA_CHECK(cudaMalloc(&s.counters, kCounterRing * sizeof(unsigned int)));
         SKR_CUDA_CHECK(cudaDeviceGetAttribute(&s.num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -260,28 +395,56 @@ template <int K, bool kVecF64, typename OutT>
 int launch_count(CountParams p, cudaStream_t stream) {
     using Cfg = CountCfg<K>;
     auto kern = count_kernel<K, kVecF64, OutT>;
-    int dev = 0;
+    int dev = 0, sms = 0;
     SKR_CUDA_CHECK(cudaGetDevice(&dev));
-    static thread_local int configured_dev[16] = {0};
-    (void)configured_dev;
+    SKR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     SKR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem));
     int per_sm = 0;
     SKR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Cfg::kThreads, Cfg::kSmem));
     if (per_sm < 1) return skr::fail(SKR_ERR_CUDA, "count kernel for k=%d does not fit on this device", K);
+    // the warp-per-record kernel takes k <= 6 with float output; it leaves records that are too long for
+    // one warp on a list which the CTA kernel then drains
+    constexpr bool kUseWarp = K <= 6 && sizeof(OutT) == 4;
+    if (kUseWarp && p.m > 0xFFFFFFFFll) return skr::fail(SKR_ERR_ARG, "skr_count: more than 2^32 records");
     DeviceScratch* sc = nullptr;
-    int sms = 0;
-    SKR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    long long grid = (long long)sms * per_sm;
-    if (grid > p.m) grid = p.m;
-    int rc = get_scratch(dev, (size_t)sms * per_sm * Cfg::kBins * 4, &sc);
+    int rc = get_scratch(dev, (size_t)sms * per_sm * Cfg::kBins * 4, kUseWarp ? (size_t)p.m : 0, &sc);
     if (rc != SKR_OK) return rc;
+    unsigned int* ctr;
     {
         std::lock_guard<std::mutex> lock(g_scratch_mu);
-        p.work_counter = sc->counters + sc->next_counter;
-        sc->next_counter = (sc->next_counter + 1) % kCounterRing;
+        ctr = sc->counters + sc->next_counter;
+        sc->next_counter = (sc->next_counter + 4) % kCounterRing;
     }
+    SKR_CUDA_CHECK(cudaMemsetAsync(ctr, 0, 4 * sizeof(unsigned int), stream));
     p.spill = sc->spill;
-    SKR_CUDA_CHECK(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned int), stream));
+    long long grid = (long long)sms * per_sm;
+    if constexpr (kUseWarp) {
+        using W = WarpCfg<K>;
+        auto wkern = count_warp_kernel<K, kVecF64>;
+        SKR_CUDA_CHECK(cudaFuncSetAttribute(wkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W::kSmem));
+        int wper_sm = 0;
+        SKR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wper_sm, wkern, W::kThreads, W::kSmem));
+        if (wper_sm < 1) return skr::fail(SKR_ERR_CUDA, "warp count kernel for k=%d does not fit on this device", K);
+        long long wgrid = (long long)sms * wper_sm;
+        const long long need = (p.m + W::kWarps - 1) / W::kWarps;
+        if (wgrid > need) wgrid = need;
+        CountParams wp = p;
+        wp.work_counter = ctr;
+        wp.long_list = sc->long_list;
+        wp.long_count = ctr + 1;
+        wkern<<<(unsigned)wgrid, W::kThreads, W::kSmem, stream>>>(wp);
+        SKR_LAUNCH_CHECK();
+        // long records (rare): the CTA kernel reads the list length on the device
+        p.work_counter = ctr + 2;
+        p.long_list = sc->long_list;
+        p.long_count = ctr + 1;
+        if (grid > sms) grid = sms;
+    } else {
+        p.work_counter = ctr;
+        p.long_list = nullptr;
+        p.long_count = nullptr;
+        if (grid > p.m) grid = p.m;
+    }
     kern<<<(unsigned)grid, Cfg::kThreads, Cfg::kSmem, stream>>>(p);
     SKR_LAUNCH_CHECK();
     return SKR_OK;

@@ -9,8 +9,8 @@ The path shards without data-path collectives except where the reference's arith
   Log2.post           the shift is the minimum over the whole matrix (kmer_counts.py:208)  -> all-reduce(min) of one cell
   Pearson             output row blocks are independent; the smaller operand is replicated -> one broadcast
 
-Nothing here touches the CPU oracle; the host-side logic (shard_ranges, encode/decode of the min cell,
-message order of the chain) is covered by world_size-2 gloo tests.
+The host-side logic (shard_ranges, encode/decode of the min cell, message order of the chain) is
+covered by world_size-2 gloo tests on the CPU.
 """
 
 import numpy as np
