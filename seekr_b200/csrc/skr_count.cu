@@ -297,11 +297,18 @@ __global__ void __launch_bounds__(WarpCfg<K>::kThreads) count_warp_kernel(const 
                 for (int i = lane; i < Cfg::kWords; i += 32) hist[i] = 0;
             }
             const double inc = nwin > 0 ? 1000.0 / (double)nwin : 0.0;
-#pragma unroll
-            for (int c = lane; c < kTab; c += 32) {
-                float v = __double2float_rn(skr::chain_sum(inc, (uint32_t)c));
-                if (p.log2_pre) v = log2f(__fadd_rn(v, 1.0f));
-                tab[c] = v;
+            if (lane == 0) {  // the literal chain: 63 dependent binary64 adds, cheap in issue slots
+                double acc = 0.0;
+                tab[0] = 0.0f;
+#pragma unroll 9
+                for (int c = 1; c < kTab; ++c) {
+                    acc = __dadd_rn(acc, inc);
+                    tab[c] = __double2float_rn(acc);
+                }
+            }
+            if (p.log2_pre) {
+                __syncwarp();
+                for (int c = lane; c < kTab; c += 32) tab[c] = log2f(__fadd_rn(tab[c], 1.0f));
             }
             __syncwarp();
             for (int c = lane; c < nchunks; c += 32) {
@@ -337,6 +344,7 @@ __global__ void __launch_bounds__(WarpCfg<K>::kThreads) count_warp_kernel(const 
         if (rec < p.m) { L = __ldg(p.len + rec); b0 = __ldg(p.blk_off + rec); }
     }
     if (p.min_cell) {
+        if (tmin != tmin) { tnan = 1; tmin = INFINITY; }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             tmin = fminf(tmin, __shfl_xor_sync(0xFFFFFFFFu, tmin, o));

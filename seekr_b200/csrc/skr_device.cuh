@@ -111,13 +111,16 @@ __device__ __forceinline__ uint32_t ordered_encode(float f) {
 __device__ __forceinline__ float ordered_decode(uint32_t u) {
     return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
 }
+// tmin carries the NaN itself (min.NaN propagates it), so one instruction per value suffices;
+// tnan is only folded in when the running value is committed.
 __device__ __forceinline__ void min_update(float v, float& tmin, int& tnan) {
-    if (v != v) tnan = 1;
-    else tmin = fminf(tmin, v);
+    (void)tnan;
+    asm("min.NaN.f32 %0, %0, %1;" : "+f"(tmin) : "f"(v));
 }
 
 template <int T>
 __device__ __forceinline__ void min_commit(float tmin, int tnan, float* s_wmin, int* s_wnan, SkrMinCell* cell) {
+    if (tmin != tmin) { tnan = 1; tmin = INFINITY; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         tmin = fminf(tmin, __shfl_xor_sync(0xFFFFFFFFu, tmin, o));
