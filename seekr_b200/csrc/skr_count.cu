@@ -23,7 +23,7 @@
 namespace {
 
 constexpr int kSegChunks = 4095;  // 4095 chunks x 16 windows = 65 520 < 65 536 increments per segment
-constexpr int kTab = 64;          // counts below this are looked up, larger ones take the generic chain_sum
+constexpr int kTab = 32;          // counts below this are looked up, larger ones take the generic chain_sum
 
 template <int K>
 struct CountCfg {
@@ -52,19 +52,25 @@ struct CountParams {
     unsigned int* long_count;
 };
 
-// counts of 4 consecutive bins -> the reference's float32 values (per-kb chain, log2.pre, -mean, /std)
+// value of a bin whose count is beyond the table (rare: low-complexity records); kept out of line so the
+// hot epilogue stays small in the instruction cache
+__device__ __noinline__ float slow_bin_value(double inc, uint32_t c, int log2_pre) {
+    float v = __double2float_rn(skr::chain_sum(inc, c));
+    if (log2_pre) v = log2f(__fadd_rn(v, 1.0f));
+    return v;
+}
+
+// counts of 4 consecutive bins -> the reference's float32 values (per-kb chain, log2.pre, -mean, /std).
+// packed = the two histogram words (four 16-bit counts) when every count fits the table.
 template <bool kVecF64>
 __device__ __forceinline__ void finish4(const uint32_t (&c4)[4], const float* tab, double inc, const CountParams& p, int q,
                                         float (&r)[4]) {
+    if (((c4[0] | c4[1] | c4[2] | c4[3]) & ~(uint32_t)(kTab - 1)) == 0) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        if (c4[e] < kTab) {
-            r[e] = tab[c4[e]];
-        } else {
-            float v = __double2float_rn(skr::chain_sum(inc, c4[e]));
-            if (p.log2_pre) v = log2f(__fadd_rn(v, 1.0f));
-            r[e] = v;
-        }
+        for (int e = 0; e < 4; ++e) r[e] = tab[c4[e]];
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) r[e] = c4[e] < kTab ? tab[c4[e]] : slow_bin_value(inc, c4[e], p.log2_pre);
     }
     if (p.mean) {
         if constexpr (kVecF64) {
@@ -95,7 +101,14 @@ __device__ __forceinline__ void finish4(const uint32_t (&c4)[4], const float* ta
 template <int K>
 __device__ __forceinline__ void count_chunk(uint32_t* hist, uint64_t x, uint32_t mb, int nv) {
     constexpr uint32_t kMask = (1u << (2 * K)) - 1;
-    if (mb == 0 && nv == 16) {
+    uint32_t ok = 0xFFFFu;  // bit 15-j: window j is counted
+    if (mb != 0 || nv != 16) {
+        // window j is bad if any of its K mask bits is set: OR the mask with itself shifted by 1..K-1
+        uint32_t bad = mb;
+#pragma unroll
+        for (int i = 1; i < K; ++i) bad |= mb << i;
+        ok = ~(bad >> (K - 1)) & 0xFFFFu & ~(0xFFFFu >> nv);
+    } else {
         // all 16 + K - 1 bases equal (homopolymer run): one add of 16 instead of 16 colliding adds
         const uint64_t same = (x ^ (x << 2)) >> (64 - 2 * (16 + K - 2));
         if (same == 0) {
@@ -103,18 +116,11 @@ __device__ __forceinline__ void count_chunk(uint32_t* hist, uint64_t x, uint32_t
             atomicAdd(&hist[kmer >> 1], 16u << ((kmer & 1) * 16));
             return;
         }
+    }
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const uint32_t kmer = (uint32_t)(x >> (64 - 2 * (j + K))) & kMask;
-            atomicAdd(&hist[kmer >> 1], 1u << ((kmer & 1) * 16));
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const uint32_t kmer = (uint32_t)(x >> (64 - 2 * (j + K))) & kMask;
-            const uint32_t bad = (mb >> (16 - 1 - j)) & ((1u << K) - 1);
-            if (j < nv && bad == 0) atomicAdd(&hist[kmer >> 1], 1u << ((kmer & 1) * 16));
-        }
+    for (int j = 0; j < 16; ++j) {
+        const uint32_t kmer = (uint32_t)(x >> (64 - 2 * (j + K))) & kMask;
+        if (ok & (0x8000u >> j)) atomicAdd(&hist[kmer >> 1], 1u << ((kmer & 1) * 16));
     }
 }
 
@@ -238,12 +244,14 @@ __global__ void __launch_bounds__(CountCfg<K>::kThreads) count_kernel(const Coun
 
 
 // ---------------------------------------------------------------------------------------------
-// Warp-per-record variant for k <= 6.  A record of a few thousand bases is too little work for a
-// CTA: the CTA kernel above spends its time in barriers and serialized latencies (work counter,
-// lengths, offsets, codes).  Here every warp owns a private histogram (<= 8 KB) and runs records
-// end to end with no block-level synchronisation; the next record's index and metadata are
-// fetched while the current one is processed.  Records longer than kLongWin windows are pushed
-// to a list that the CTA kernel drains afterwards (256 threads and the 32-bit spill path).
+// Team-per-record variant for k <= 6 (the headline path).  A record of a few thousand bases is too
+// little work for 256 threads: the CTA kernel above spends its time in barriers and serialized
+// latencies (work counter, lengths, offsets, codes).  Here a small team owns a private histogram
+// and runs records end to end; the next record's index is fetched while the current one is
+// processed.  k <= 5: team = one warp (histogram <= 2 KB, 8 teams per CTA, __syncwarp only).
+// k = 6: team = one 64-thread CTA (8 KB histogram -> 27 CTAs = 54 warps per SM; a one-warp team would
+// cap the SM at 27 warps and leave the issue slots idle).  Records longer than kLongWin windows are
+// pushed to a list that the CTA kernel drains afterwards (256 threads and the 32-bit spill path).
 // ---------------------------------------------------------------------------------------------
 constexpr long long kLongWin = 32768;
 
@@ -251,33 +259,49 @@ template <int K>
 struct WarpCfg {
     static constexpr int kBins = 1 << (2 * K);
     static constexpr int kWords = kBins / 2;
-    static constexpr int kWarps = K == 6 ? 4 : 8;
-    static constexpr int kThreads = 32 * kWarps;
-    static constexpr size_t kSmem = (size_t)kWarps * (kWords * 4 + kTab * 4);
+    static constexpr int kTeam = K == 6 ? 64 : 32;       // threads per record
+    static constexpr int kTeams = K == 6 ? 1 : 8;        // records in flight per CTA
+    static constexpr int kThreads = kTeam * kTeams;
+    static constexpr size_t kSmem = (size_t)kTeams * (kWords * 4 + kTab * 4);
+    static constexpr int kMinCtas = K == 6 ? 24 : 8;     // register cap: 48 / 64 resident warps per SM
 };
 
 template <int K, bool kVecF64>
-__global__ void __launch_bounds__(WarpCfg<K>::kThreads) count_warp_kernel(const CountParams p) {
+__global__ void __launch_bounds__(WarpCfg<K>::kThreads, WarpCfg<K>::kMinCtas) count_warp_kernel(const CountParams p) {
     using Cfg = WarpCfg<K>;
+    constexpr int TT = Cfg::kTeam;
     extern __shared__ __align__(16) uint32_t smem_w[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t* hist = smem_w + warp * Cfg::kWords;
-    float* tab = reinterpret_cast<float*>(smem_w + Cfg::kWarps * Cfg::kWords) + warp * kTab;
+    __shared__ long long s_next;
+    __shared__ float s_wmin[2];
+    __shared__ int s_wnan[2];
+    const int team = threadIdx.x / TT, lane = threadIdx.x % TT;  // lane: index inside the team
+    uint32_t* hist = smem_w + team * Cfg::kWords;
+    float* tab = reinterpret_cast<float*>(smem_w + Cfg::kTeams * Cfg::kWords) + team * kTab;
     float tmin = INFINITY;
     int tnan = 0;
 
-    auto fetch = [&]() -> long long {
-        unsigned int r = 0;
-        if (lane == 0) r = atomicAdd(p.work_counter, 1u);
-        return (long long)__shfl_sync(0xFFFFFFFFu, r, 0);
+    auto team_sync = [&]() {
+        if constexpr (TT == 32) __syncwarp(); else __syncthreads();
     };
-    long long rec = fetch();
-    uint32_t L = 0;
-    uint64_t b0 = 0;
-    if (rec < p.m) { L = __ldg(p.len + rec); b0 = __ldg(p.blk_off + rec); }
+    // the team leader draws the next record index; everybody learns it at the next team_sync
+    auto draw = [&]() -> long long {
+        return lane == 0 ? (long long)atomicAdd(p.work_counter, 1u) : 0;
+    };
+    auto share = [&](long long mine) -> long long {
+        if constexpr (TT == 32) {
+            return (long long)__shfl_sync(0xFFFFFFFFu, (unsigned int)mine, 0);
+        } else {
+            if (lane == 0) s_next = mine;
+            __syncthreads();
+            return s_next;
+        }
+    };
+    long long rec = share(draw());
 
     while (rec < p.m) {
-        const long long next = fetch();  // in flight while this record is processed
+        const long long mine_next = draw();  // in flight while this record is processed
+        const uint32_t L = __ldg(p.len + rec);
+        const uint64_t b0 = __ldg(p.blk_off + rec);
         const long long nwin = (long long)L - K + 1;
         if (nwin > kLongWin) {
             if (lane == 0) p.long_list[atomicAdd(p.long_count, 1u)] = (uint32_t)rec;
@@ -291,28 +315,26 @@ __global__ void __launch_bounds__(WarpCfg<K>::kThreads) count_warp_kernel(const 
                 w0 = __ldg(cw + lane); w1 = __ldg(cw + lane + 1);
                 m0 = __ldg(mw + (lane >> 1)); m1 = __ldg(mw + (lane >> 1) + 1);
             }
-            if constexpr (Cfg::kWords % 128 == 0) {
-                for (int i = lane; i < Cfg::kWords / 4; i += 32) reinterpret_cast<uint4*>(hist)[i] = make_uint4(0, 0, 0, 0);
+            if constexpr (Cfg::kWords % 4 == 0) {
+                for (int i = lane; i < Cfg::kWords / 4; i += TT) reinterpret_cast<uint4*>(hist)[i] = make_uint4(0, 0, 0, 0);
             } else {
-                for (int i = lane; i < Cfg::kWords; i += 32) hist[i] = 0;
+                for (int i = lane; i < Cfg::kWords; i += TT) hist[i] = 0;
             }
             const double inc = nwin > 0 ? 1000.0 / (double)nwin : 0.0;
-            if (lane == 0) {  // the literal chain: 63 dependent binary64 adds, cheap in issue slots
+            if (lane == TT - 1) {  // the literal chain: kTab-1 dependent binary64 adds, cheap in issue slots
                 double acc = 0.0;
-                tab[0] = 0.0f;
-#pragma unroll 9
+                tab[0] = p.log2_pre ? log2f(1.0f) : 0.0f;
+#pragma unroll 8
                 for (int c = 1; c < kTab; ++c) {
                     acc = __dadd_rn(acc, inc);
-                    tab[c] = __double2float_rn(acc);
+                    float v = __double2float_rn(acc);
+                    if (p.log2_pre) v = log2f(__fadd_rn(v, 1.0f));
+                    tab[c] = v;
                 }
             }
-            if (p.log2_pre) {
-                __syncwarp();
-                for (int c = lane; c < kTab; c += 32) tab[c] = log2f(__fadd_rn(tab[c], 1.0f));
-            }
-            __syncwarp();
-            for (int c = lane; c < nchunks; c += 32) {
-                const int cn = c + 32;
+            team_sync();
+            for (int c = lane; c < nchunks; c += TT) {
+                const int cn = c + TT;
                 uint32_t n0 = 0, n1 = 0, q0 = 0, q1 = 0;
                 if (cn < nchunks) {  // next iteration's words
                     n0 = __ldg(cw + cn); n1 = __ldg(cw + cn + 1);
@@ -325,9 +347,9 @@ __global__ void __launch_bounds__(WarpCfg<K>::kThreads) count_warp_kernel(const 
                 count_chunk<K>(hist, x, mb, left < 16 ? (int)left : 16);
                 w0 = n0; w1 = n1; m0 = q0; m1 = q1;
             }
-            __syncwarp();
+            team_sync();
             float* __restrict__ orow = reinterpret_cast<float*>(p.out) + (size_t)rec * (size_t)p.ld_out;
-            for (int q = lane; q < Cfg::kBins / 4; q += 32) {
+            for (int q = lane; q < Cfg::kBins / 4; q += TT) {
                 const uint2 v = reinterpret_cast<const uint2*>(hist)[q];
                 const uint32_t c4[4] = {v.x & 0xFFFFu, v.x >> 16, v.y & 0xFFFFu, v.y >> 16};
                 float r[4];
@@ -338,21 +360,24 @@ __global__ void __launch_bounds__(WarpCfg<K>::kThreads) count_warp_kernel(const 
                 }
                 reinterpret_cast<float4*>(orow)[q] = make_float4(r[0], r[1], r[2], r[3]);
             }
-            __syncwarp();  // histogram and table are reused by the next record
         }
-        rec = next;
-        if (rec < p.m) { L = __ldg(p.len + rec); b0 = __ldg(p.blk_off + rec); }
+        rec = share(mine_next);  // also separates this record's histogram reads from the next clearing
+        if constexpr (TT == 32) __syncwarp();
     }
     if (p.min_cell) {
-        if (tmin != tmin) { tnan = 1; tmin = INFINITY; }
+        if constexpr (TT == 32) {
+            if (tmin != tmin) { tnan = 1; tmin = INFINITY; }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            tmin = fminf(tmin, __shfl_xor_sync(0xFFFFFFFFu, tmin, o));
-            tnan |= __shfl_xor_sync(0xFFFFFFFFu, tnan, o);
-        }
-        if (lane == 0) {
-            if (tmin < INFINITY) atomicMin(&p.min_cell->min_ordered, skr::ordered_encode(tmin));
-            if (tnan) atomicOr(&p.min_cell->nan_seen, 1u);
+            for (int o = 16; o > 0; o >>= 1) {
+                tmin = fminf(tmin, __shfl_xor_sync(0xFFFFFFFFu, tmin, o));
+                tnan |= __shfl_xor_sync(0xFFFFFFFFu, tnan, o);
+            }
+            if (lane == 0) {
+                if (tmin < INFINITY) atomicMin(&p.min_cell->min_ordered, skr::ordered_encode(tmin));
+                if (tnan) atomicOr(&p.min_cell->nan_seen, 1u);
+            }
+        } else {
+            skr::min_commit<TT>(tmin, tnan, s_wmin, s_wnan, p.min_cell);
         }
     }
 }
@@ -434,7 +459,7 @@ int launch_count(CountParams p, cudaStream_t stream) {
         SKR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wper_sm, wkern, W::kThreads, W::kSmem));
         if (wper_sm < 1) return skr::fail(SKR_ERR_CUDA, "warp count kernel for k=%d does not fit on this device", K);
         long long wgrid = (long long)sms * wper_sm;
-        const long long need = (p.m + W::kWarps - 1) / W::kWarps;
+        const long long need = (p.m + W::kTeams - 1) / W::kTeams;
         if (wgrid > need) wgrid = need;
         CountParams wp = p;
         wp.work_counter = ctr;
