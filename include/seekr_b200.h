@@ -162,7 +162,8 @@ int skr_col_finish_f64(const double* d_acc, int64_t cols, int64_t total_rows, in
  * skr_pearson_prepare row-standardises (mean, std ddof=0; pearson.py:35-38) and splits every
  * value into two fp16 planes hi + lo (22 significant bits) after scaling the row by a power of
  * two; skr_pearson_gemm forms hi*hi' + hi*lo' + lo*hi' with tcgen05 MMAs (fp32 accumulation in
- * TMEM), un-scales and multiplies by alpha (= 1/K, pearson.py:41).
+ * TMEM), un-scales and multiplies by alpha (= 1/K, pearson.py:41).  symmetric != 0 (same operands,
+ * m == n, whole matrix in one call) computes only the tiles on and above the diagonal and mirrors them.
  * Planes are [rows_padded][k_padded] fp16, rows_padded % 128 == 0, k_padded % 64 == 0, zero filled.
  * ------------------------------------------------------------------------------------------ */
 int64_t skr_pearson_rows_padded(int64_t rows);
@@ -171,7 +172,7 @@ int skr_pearson_prepare(const void* d_a, int a_is_f64, int64_t rows, int64_t K, 
                         uint16_t* d_hi, uint16_t* d_lo, float* d_row_scale, void* stream);
 int skr_pearson_gemm(const uint16_t* d_a_hi, const uint16_t* d_a_lo, const float* d_a_scale, int64_t m,
                      const uint16_t* d_b_hi, const uint16_t* d_b_lo, const float* d_b_scale, int64_t n, int64_t K,
-                     double alpha, void* d_c, int c_is_f64, int64_t ldc, void* stream);
+                     double alpha, void* d_c, int c_is_f64, int64_t ldc, int symmetric, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Host <-> device plumbing used by the Python layer (thin wrappers; no reference counterpart)

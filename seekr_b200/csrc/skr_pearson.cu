@@ -172,6 +172,7 @@ struct GemmParams {
     void* c;
     long long ldc;
     int c_is_f64;
+    int symmetric;  // A == B, square tiles: only tiles with tn >= tm are computed, the rest is mirrored
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -266,15 +267,46 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int& tm, int& tn) {
-    const int per_group = kGroupM * tiles_n;
-    const int group = t / per_group;
-    const int first_m = group * kGroupM;
-    const int gsize = min(kGroupM, tiles_m - first_m);
-    const int r = t - group * per_group;
-    tm = first_m + r % gsize;
-    tn = r / gsize;
+// Tile order: groups of kGroupM tile-rows sweep the tile-columns, so the CTAs running at the same time
+// share a handful of A and B slabs in L2.  Symmetric mode keeps the order but skips tiles below the diagonal.
+__device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int symmetric, int& tm, int& tn) {
+    if (!symmetric) {
+        const int per_group = kGroupM * tiles_n;
+        const int group = t / per_group;
+        const int first_m = group * kGroupM;
+        const int gsize = min(kGroupM, tiles_m - first_m);
+        const int r = t - group * per_group;
+        tm = first_m + r % gsize;
+        tn = r / gsize;
+        return;
+    }
+    int first_m = 0, r = t;
+    for (;;) {  // at most tiles_m / kGroupM iterations
+        const int R = min(kGroupM, tiles_m - first_m);
+        const int ncols = tiles_n - first_m;                      // tile-columns first_m .. tiles_n-1
+        const int size = R * (R + 1) / 2 + (ncols - R) * R;       // columns 0..R-1 hold 1..R tiles, the rest R each
+        if (r < size) {
+            const int tri = R * (R + 1) / 2;
+            int c, lm;
+            if (r < tri) {
+                c = 0;
+                while ((c + 1) * (c + 2) / 2 <= r) ++c;
+                lm = r - c * (c + 1) / 2;
+            } else {
+                const int rr = r - tri;
+                c = R + rr / R;
+                lm = rr % R;
+            }
+            tm = first_m + lm;
+            tn = first_m + c;
+            return;
+        }
+        r -= size;
+        first_m += kGroupM;
+    }
 }
+
+__host__ __device__ inline long long symmetric_tile_count(int tiles) { return (long long)tiles * (tiles + 1) / 2; }
 
 template <int kCG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -297,7 +329,7 @@ pearson_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     const bool leader = cta_rank == 0;
     const int cluster_id = blockIdx.x / kCG;
     const int num_clusters = gridDim.x / kCG;
-    const int num_tiles = p.tiles_m * p.tiles_n;
+    const int num_tiles = p.symmetric ? (int)symmetric_tile_count(p.tiles_m) : p.tiles_m * p.tiles_n;
 
     if (warp == 0 && lane == 0) {
         skr::tma_prefetch_desc(&map_a_hi);
@@ -340,7 +372,7 @@ pearson_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
             uint32_t phase = 0;
             for (int t = cluster_id; t < num_tiles; t += num_clusters) {
                 int tm, tn;
-                tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
+                tile_coords(t, p.tiles_m, p.tiles_n, p.symmetric, tm, tn);
                 const int a_row = (tm * kCG + (int)cta_rank) * kBM;
                 const int b_row = tn * kBN + (int)cta_rank * Cfg::kBNLocal;
                 for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -404,7 +436,7 @@ pearson_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
         uint32_t acc_phase = 0;
         for (int t = cluster_id; t < num_tiles; t += num_clusters) {
             int tm, tn;
-            tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
+            tile_coords(t, p.tiles_m, p.tiles_n, p.symmetric, tm, tn);
             float sum[128];
 #pragma unroll
             for (int i = 0; i < 128; ++i) sum[i] = 0.0f;
@@ -453,6 +485,19 @@ pearson_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                             if (col0 + i < p.n) dst[i] = (double)(sum[c + i] * rs * __ldg(p.b_scale + col0 + i));
                     }
                 }
+                if (p.symmetric && tn != tm) {
+                    // mirror: C[col][row]; the 32 lanes of a warp hold consecutive rows, so each store
+                    // instruction writes 32 consecutive elements of one output row (coalesced)
+#pragma unroll 8
+                    for (int c = 0; c < 128; ++c) {
+                        const long long col = colbase + c;
+                        if (col < p.n) {
+                            const float val = sum[c] * rs * __ldg(p.b_scale + col);
+                            if (!p.c_is_f64) reinterpret_cast<float*>(p.c)[col * p.ldc + row] = val;
+                            else reinterpret_cast<double*>(p.c)[col * p.ldc + row] = (double)val;
+                        }
+                    }
+                }
             }
         }
     }
@@ -478,7 +523,9 @@ int launch_gemm(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtens
     SKR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     p.tiles_m = (int)((p.m + kBM * kCG - 1) / (kBM * kCG));
     p.tiles_n = (int)((p.n + kBN - 1) / kBN);
-    long long clusters = (long long)p.tiles_m * p.tiles_n;
+    if (p.symmetric && (kBM * kCG != kBN || p.tiles_m != p.tiles_n))
+        return skr::fail(SKR_ERR_ARG, "skr_pearson_gemm: symmetric mode needs square tiles (cta_group 2) and m == n");
+    long long clusters = p.symmetric ? symmetric_tile_count(p.tiles_m) : (long long)p.tiles_m * p.tiles_n;
     if (clusters > sms / kCG) clusters = sms / kCG;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(clusters * kCG));
@@ -523,8 +570,10 @@ extern "C" int skr_pearson_prepare(const void* d_a, int a_is_f64, int64_t rows, 
 
 extern "C" int skr_pearson_gemm(const uint16_t* d_a_hi, const uint16_t* d_a_lo, const float* d_a_scale, int64_t m,
                                 const uint16_t* d_b_hi, const uint16_t* d_b_lo, const float* d_b_scale, int64_t n,
-                                int64_t K, double alpha, void* d_c, int c_is_f64, int64_t ldc, void* stream) {
+                                int64_t K, double alpha, void* d_c, int c_is_f64, int64_t ldc, int symmetric, void* stream) {
     if (m <= 0 || n <= 0) return SKR_OK;
+    if (symmetric && (d_a_hi != d_b_hi || d_a_lo != d_b_lo || m != n))
+        return skr::fail(SKR_ERR_ARG, "skr_pearson_gemm: symmetric mode needs identical operands");
     if (!d_a_hi || !d_a_lo || !d_a_scale || !d_b_hi || !d_b_lo || !d_b_scale || !d_c || K <= 0)
         return skr::fail(SKR_ERR_ARG, "skr_pearson_gemm: null argument");
     if (ldc < n) return skr::fail(SKR_ERR_ARG, "skr_pearson_gemm: ldc < n");
@@ -535,6 +584,7 @@ extern "C" int skr_pearson_gemm(const uint16_t* d_a_hi, const uint16_t* d_a_lo, 
         return skr::fail(SKR_ERR_ARG, "skr_pearson_gemm: problem too large");
     int cg = 2;
     if (const char* env = getenv("SEEKR_B200_GEMM_CTA_GROUP")) cg = atoi(env) == 1 ? 1 : 2;
+    if (cg == 1) symmetric = 0;  // 128 x 256 tiles are not square: compute the full matrix
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     const uint32_t b_box_rows = cg == 2 ? 128 : 256;
     int rc;
@@ -556,6 +606,7 @@ extern "C" int skr_pearson_gemm(const uint16_t* d_a_hi, const uint16_t* d_a_lo, 
     p.c = d_c;
     p.ldc = ldc;
     p.c_is_f64 = c_is_f64;
+    p.symmetric = symmetric;
     cudaStream_t s = (cudaStream_t)stream;
     return cg == 2 ? launch_gemm<2>(ma_hi, ma_lo, mb_hi, mb_lo, p, s) : launch_gemm<1>(ma_hi, ma_lo, mb_hi, mb_lo, p, s);
 }

@@ -77,8 +77,9 @@ def prepare(x, row_standardize=True, stream=None):
     return PreparedRows(rows, K, hi, lo, scale)
 
 
-def gemm_block(pa, row0, nrows, pb, out, alpha, stream=None):
-    """out[nrows x n] = alpha * A[row0:row0+nrows] . B^T from prepared planes (row0 % 128 == 0)."""
+def gemm_block(pa, row0, nrows, pb, out, alpha, stream=None, symmetric=False):
+    """out[nrows x n] = alpha * A[row0:row0+nrows] . B^T from prepared planes (row0 % 128 == 0).
+    symmetric: pa is pb and the block is the whole matrix -> only the upper-triangle tiles are computed."""
     lib = _lib.load()
     kp = pa.hi.shape[1]
     esz = 2
@@ -92,6 +93,7 @@ def gemm_block(pa, row0, nrows, pb, out, alpha, stream=None):
     _lib.check(lib.skr_pearson_gemm(ctypes.c_void_p(a_hi), ctypes.c_void_p(a_lo), ctypes.c_void_p(a_sc), nrows,
                                     device.ptr(pb.hi), device.ptr(pb.lo), device.ptr(pb.scale), pb.rows, pa.K,
                                     float(alpha), device.ptr(out), int(out.dtype == torch.float64), out.stride(0),
+                                    int(bool(symmetric and pa is pb and row0 == 0 and nrows == pb.rows)),
                                     device.stream_ptr(stream)))
 
 
@@ -101,11 +103,12 @@ def pearson_device(pa, pb, out_f64=False, out=None, stream=None):
     if out is None:
         out = device.empty((pa.rows, pb.rows), torch.float64 if out_f64 else torch.float32)
     if pa.rows and pb.rows:
-        gemm_block(pa, 0, pa.rows, pb, out, 1.0 / pa.K, stream)
+        gemm_block(pa, 0, pa.rows, pb, out, 1.0 / pa.K, stream, symmetric=pa is pb)
     return out
 
 
 _BLOCK_BYTES = 1 << 31  # device staging per output row block (two in flight)
+_SYMMETRIC_MAX_BYTES = 48 << 30  # self-vs-self results up to this size are formed in one device buffer
 
 
 def pearson(counts1, counts2, row_standardize=True, outfile=None):
@@ -132,26 +135,37 @@ def pearson(counts1, counts2, row_standardize=True, outfile=None):
 
     esz = 8 if out_f64 else 4
     dist = device.pinned_empty((m, n), np_dtype)
-    block = max(128, min(m, (_BLOCK_BYTES // (n * esz)) // 128 * 128))
     compute = torch.cuda.current_stream()
     copy = torch.cuda.Stream()
-    bufs = [device.empty((min(block, m), n), torch.float64 if out_f64 else torch.float32) for _ in range(2)]
-    done = [None, None]      # copy finished reading bufs[i]
     alpha = 1.0 / K
-    for bi, row0 in enumerate(range(0, m, block)):
-        nrows = min(block, m - row0)
-        buf = bufs[bi & 1]
-        if done[bi & 1] is not None:
-            compute.wait_event(done[bi & 1])
-        gemm_block(pa, row0, nrows, pb, buf, alpha, compute)
+    tdtype = torch.float64 if out_f64 else torch.float32
+    free_bytes = torch.cuda.mem_get_info()[0]
+    if pa is pb and m * n * esz <= min(_SYMMETRIC_MAX_BYTES, free_bytes // 2):
+        # self vs self: half the tiles, mirrored by the epilogue; the result streams back in row blocks
+        full = device.empty((m, n), tdtype)
+        gemm_block(pa, 0, m, pb, full, alpha, compute, symmetric=True)
         ready = torch.cuda.Event()
         ready.record(compute)
         copy.wait_event(ready)
-        _lib.check(lib.skr_copy_d2h(device.host_ptr(dist[row0:row0 + nrows]), device.ptr(buf), nrows * n * esz,
-                                    device.stream_ptr(copy)))
-        ev = torch.cuda.Event()
-        ev.record(copy)
-        done[bi & 1] = ev
+        _lib.check(lib.skr_copy_d2h(device.host_ptr(dist), device.ptr(full), m * n * esz, device.stream_ptr(copy)))
+    else:
+        block = max(128, min(m, (_BLOCK_BYTES // (n * esz)) // 128 * 128))
+        bufs = [device.empty((min(block, m), n), tdtype) for _ in range(2)]
+        done = [None, None]      # copy finished reading bufs[i]
+        for bi, row0 in enumerate(range(0, m, block)):
+            nrows = min(block, m - row0)
+            buf = bufs[bi & 1]
+            if done[bi & 1] is not None:
+                compute.wait_event(done[bi & 1])
+            gemm_block(pa, row0, nrows, pb, buf, alpha, compute)
+            ready = torch.cuda.Event()
+            ready.record(compute)
+            copy.wait_event(ready)
+            _lib.check(lib.skr_copy_d2h(device.host_ptr(dist[row0:row0 + nrows]), device.ptr(buf), nrows * n * esz,
+                                        device.stream_ptr(copy)))
+            ev = torch.cuda.Event()
+            ev.record(copy)
+            done[bi & 1] = ev
     copy.synchronize()
     compute.synchronize()
     if outfile:

@@ -117,3 +117,15 @@ def test_pearson_large_block_property():
     idx = rng.choice(4096, size=96, replace=False)
     exp = po.pearson_f64(a[idx], a)
     assert np.abs(r[idx] - exp).max() < TOL
+
+
+@pytest.mark.parametrize("m,K", [(257, 64), (700, 333), (1500, 4096)])
+def test_symmetric_path_equals_general_path(m, K):
+    """pearson(a, a) takes the upper-triangle + mirror path; pearson(a, copy) computes every tile."""
+    rng = np.random.default_rng(m)
+    a = (rng.standard_normal((m, K)) * rng.lognormal(0, 0.7, size=(m, 1))).astype(np.float32)
+    sym = pearson(a, a)
+    gen = pearson(a, a.copy())
+    assert np.abs(sym - gen).max() < 2e-6
+    assert np.abs(sym - sym.T).max() < 2e-6
+    assert np.abs(sym - po.pearson_f64(a, a)).max() < TOL
