@@ -485,19 +485,6 @@ pearson_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                             if (col0 + i < p.n) dst[i] = (double)(sum[c + i] * rs * __ldg(p.b_scale + col0 + i));
                     }
                 }
-                if (p.symmetric && tn != tm) {
-                    // mirror: C[col][row]; the 32 lanes of a warp hold consecutive rows, so each store
-                    // instruction writes 32 consecutive elements of one output row (coalesced)
-#pragma unroll 8
-                    for (int c = 0; c < 128; ++c) {
-                        const long long col = colbase + c;
-                        if (col < p.n) {
-                            const float val = sum[c] * rs * __ldg(p.b_scale + col);
-                            if (!p.c_is_f64) reinterpret_cast<float*>(p.c)[col * p.ldc + row] = val;
-                            else reinterpret_cast<double*>(p.c)[col * p.ldc + row] = (double)val;
-                        }
-                    }
-                }
             }
         }
     }
@@ -509,6 +496,37 @@ pearson_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
             asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
         else
             asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+
+// Symmetric mode: the GEMM wrote the 256 x 256 tiles on and above the diagonal; this fills every tile
+// below it with the transpose of its mirror image (32 x 32 blocks through shared memory, coalesced
+// reads and writes; ~2 passes over half the matrix at HBM speed).
+template <typename T>
+__global__ void __launch_bounds__(256) mirror_lower_kernel(T* __restrict__ c, long long n, long long ldc, int tiles) {
+    __shared__ T tile[32][33];
+    // blockIdx.x enumerates strictly-lower tile pairs (tm > tn), blockIdx.y the 64 sub-blocks of a tile
+    long long t = blockIdx.x;
+    int tm = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5) + 1;  // t = tm(tm-1)/2 + tn, tn < tm
+    while ((long long)tm * (tm - 1) / 2 > t) --tm;
+    while ((long long)(tm + 1) * tm / 2 <= t) ++tm;
+    const int tn = (int)(t - (long long)tm * (tm - 1) / 2);
+    if (tm >= tiles) return;
+    const int sb_r = blockIdx.y >> 3, sb_c = blockIdx.y & 7;  // sub-block of the destination tile
+    const long long dr0 = (long long)tm * kBN + sb_r * 32, dc0 = (long long)tn * kBN + sb_c * 32;  // destination origin
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    // source block = C[dc0 .. dc0+31][dr0 .. dr0+31]
+#pragma unroll
+    for (int i = ty; i < 32; i += 8) {
+        const long long sr = dc0 + i, sc = dr0 + tx;
+        if (sr < n && sc < n) tile[i][tx] = c[sr * ldc + sc];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = ty; i < 32; i += 8) {
+        const long long r = dr0 + i, cc = dc0 + tx;
+        if (r < n && cc < n) c[r * ldc + cc] = tile[tx][i];
     }
 }
 
@@ -541,6 +559,13 @@ int launch_gemm(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtens
     cfg.numAttrs = 1;
     SKR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, mb_hi, mb_lo, p));
     SKR_LAUNCH_CHECK();
+    if (p.symmetric && p.tiles_m > 1) {
+        const long long pairs = (long long)p.tiles_m * (p.tiles_m - 1) / 2;
+        dim3 grid((unsigned)pairs, 64);
+        if (p.c_is_f64) mirror_lower_kernel<double><<<grid, 256, 0, stream>>>((double*)p.c, p.n, p.ldc, p.tiles_m);
+        else mirror_lower_kernel<float><<<grid, 256, 0, stream>>>((float*)p.c, p.n, p.ldc, p.tiles_m);
+        SKR_LAUNCH_CHECK();
+    }
     return SKR_OK;
 }
 
