@@ -111,6 +111,24 @@ int skr_count(const uint32_t* d_codes, const uint32_t* d_mask, const uint64_t* d
               const uint32_t* d_lengths, int64_t m, int k, int log2_pre, const void* d_mean, const void* d_std,
               int vec_is_f64, void* d_out, int out_is_f64, int64_t ld_out, SkrMinCell* d_min, void* stream);
 
+/* Deferred normalisation for Log2.post with known, finite mean / positive std vectors (the
+ * seekr_kmer_counts -mv -sv path): the count kernel writes the un-normalised values and keeps the
+ * per-column minimum (float bits, +inf initialised by skr_colmin_reset); because rounded subtraction and
+ * division by a positive number are monotone, min_ij fl(fl(x_ij - mean_j)/std_j) = min_j fl(fl(xmin_j -
+ * mean_j)/std_j), which skr_colmin_finish puts into the min cell; skr_normalize_post_log2 then applies
+ * -mean, /std, +|min|, +1, log2 in one element-wise pass (same roundings as kmer_counts.py:169,175,207-209).
+ * Sharded runs all-reduce(min) the column array before finishing.  skr_vec_check sets bit 0 of *d_flag
+ * if a vector element is not finite and bit 1 if one is <= 0 (callers fall back to the fused path then). */
+int skr_colmin_reset(uint32_t* d_colmin, int64_t cols, void* stream);
+int skr_count_colmin(const uint32_t* d_codes, const uint32_t* d_mask, const uint64_t* d_block_offsets,
+                     const uint32_t* d_lengths, int64_t m, int k, int log2_pre, float* d_out, int64_t ld_out,
+                     uint32_t* d_colmin, void* stream);
+int skr_colmin_finish(const uint32_t* d_colmin, int64_t cols, const void* d_mean, const void* d_std, int vec_is_f64,
+                      SkrMinCell* d_min, void* stream);
+int skr_normalize_post_log2(float* d_a, int64_t m, int64_t cols, int64_t ld, const void* d_mean, const void* d_std,
+                            int vec_is_f64, const SkrMinCell* d_min, void* stream);
+int skr_vec_check(const void* d_vec, int vec_is_f64, int64_t n, int* d_flag, void* stream);
+
 /* a = log2(a + 1)                                   (BasicCounter.log2_norm, kmer_counts.py:189-192) */
 int skr_log2_norm(float* d_a, int64_t m, int64_t cols, int64_t ld, void* stream);
 /* a = log2((a + |min|) + 1), min read from the device cell; NaN min -> all NaN   (kmer_counts.py:207-209) */

@@ -50,7 +50,42 @@ struct CountParams {
     // records the warp kernel hands over to the CTA kernel (too long for one warp): list + its length
     uint32_t* long_list;
     unsigned int* long_count;
+    // per-column minimum of the values written (float bits; values are >= 0 on this path), for the
+    // Log2.post shift when normalisation is deferred to the element-wise pass
+    uint32_t* colmin;
 };
+
+// Running per-column minimum of non-negative values (their float bits order like unsigned integers).
+// The cached read may be stale; a stale (larger) value only costs a redundant update.  Zero is the
+// floor of this path, so it is stored plainly (every writer writes the same value).
+__device__ __forceinline__ void colmin_update(uint32_t* colmin, int q, const float (&r)[4]) {
+    const uint4 cm = *reinterpret_cast<const uint4*>(colmin + 4 * q);
+    const uint32_t cur[4] = {cm.x, cm.y, cm.z, cm.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const uint32_t b = __float_as_uint(r[e]);
+        if (b < cur[e]) {
+            if (b == 0) colmin[4 * q + e] = 0;
+            else atomicMin(&colmin[4 * q + e], b);
+        }
+    }
+}
+
+// shared-memory accesses by 32-bit shared-window address: the generic-pointer forms make the compiler
+// rebuild the window base (S2UR SR_CgaCtaId, ...) at every access, 4 extra instructions per window
+__device__ __forceinline__ void red_add_shared(uint32_t addr, uint32_t inc, uint32_t pred) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p red.shared.add.u32 [%0], %1;\n}" ::"r"(addr), "r"(inc), "r"(pred) : "memory");
+}
+__device__ __forceinline__ uint2 lds_v2(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
 
 // value of a bin whose count is beyond the table (rare: low-complexity records); kept out of line so the
 // hot epilogue stays small in the instruction cache
@@ -63,14 +98,15 @@ __device__ __noinline__ float slow_bin_value(double inc, uint32_t c, int log2_pr
 // counts of 4 consecutive bins -> the reference's float32 values (per-kb chain, log2.pre, -mean, /std).
 // packed = the two histogram words (four 16-bit counts) when every count fits the table.
 template <bool kVecF64>
-__device__ __forceinline__ void finish4(const uint32_t (&c4)[4], const float* tab, double inc, const CountParams& p, int q,
+__device__ __forceinline__ void finish4(const uint32_t (&c4)[4], uint32_t tab_addr, double inc, const CountParams& p, int q,
                                         float (&r)[4]) {
     if (((c4[0] | c4[1] | c4[2] | c4[3]) & ~(uint32_t)(kTab - 1)) == 0) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) r[e] = tab[c4[e]];
+        for (int e = 0; e < 4; ++e) r[e] = lds_f32(tab_addr + c4[e] * 4);
     } else {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) r[e] = c4[e] < kTab ? tab[c4[e]] : slow_bin_value(inc, c4[e], p.log2_pre);
+        for (int e = 0; e < 4; ++e)
+            r[e] = c4[e] < kTab ? lds_f32(tab_addr + c4[e] * 4) : slow_bin_value(inc, c4[e], p.log2_pre);
     }
     if (p.mean) {
         if constexpr (kVecF64) {
@@ -98,8 +134,9 @@ __device__ __forceinline__ void finish4(const uint32_t (&c4)[4], const float* ta
 
 // 16 window starts of one chunk -> shared-memory histogram (two 16-bit sub-counters per word).
 // x: 32 bases (2 bits each, first base in the top bits); mb: the chunk's 16+K-1 mask bits; nv: valid windows.
+// hist_addr: shared-window address of the histogram.  Bin b lives in word b>>1, half b&1.
 template <int K>
-__device__ __forceinline__ void count_chunk(uint32_t* hist, uint64_t x, uint32_t mb, int nv) {
+__device__ __forceinline__ void count_chunk(uint32_t hist_addr, uint64_t x, uint32_t mb, int nv) {
     constexpr uint32_t kMask = (1u << (2 * K)) - 1;
     uint32_t ok = 0xFFFFu;  // bit 15-j: window j is counted
     if (mb != 0 || nv != 16) {
@@ -113,14 +150,17 @@ __device__ __forceinline__ void count_chunk(uint32_t* hist, uint64_t x, uint32_t
         const uint64_t same = (x ^ (x << 2)) >> (64 - 2 * (16 + K - 2));
         if (same == 0) {
             const uint32_t kmer = (uint32_t)(x >> (64 - 2 * K)) & kMask;
-            atomicAdd(&hist[kmer >> 1], 16u << ((kmer & 1) * 16));
+            red_add_shared(hist_addr + (kmer >> 1) * 4, 16u << ((kmer & 1) * 16), 1u);
             return;
         }
     }
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-        const uint32_t kmer = (uint32_t)(x >> (64 - 2 * (j + K))) & kMask;
-        if (ok & (0x8000u >> j)) atomicAdd(&hist[kmer >> 1], 1u << ((kmer & 1) * 16));
+        // t = k-mer shifted left by one: bits [2K..1] = k-mer, so (t & mask) is the byte offset of its word / 2
+        const uint32_t t = (uint32_t)(x >> (64 - 2 * (j + K) - 1));
+        const uint32_t off = t & ((kMask >> 1) << 2);               // (kmer >> 1) * 4
+        const uint32_t inc = 1u << ((t << 3) & 16);                  // kmer & 1 ? 0x10000 : 1
+        red_add_shared(hist_addr + off, inc, ok & (0x8000u >> j));
     }
 }
 
@@ -189,7 +229,7 @@ __global__ void __launch_bounds__(CountCfg<K>::kThreads) count_kernel(const Coun
                 const uint32_t mb = (uint32_t)((m64 << (16 * (int)(c & 1))) >> (64 - (16 + K - 1)));
                 const long long left = nwin - c * 16;
                 const int nv = left < 16 ? (int)left : 16;
-                count_chunk<K>(hist, x, mb, nv);
+                count_chunk<K>(skr::smem_u32(hist), x, mb, nv);
             }
             __syncthreads();
             if (nseg > 1) {
@@ -228,7 +268,8 @@ __global__ void __launch_bounds__(CountCfg<K>::kThreads) count_kernel(const Coun
                 reinterpret_cast<double2*>(orow)[2 * q + 1] = make_double2(r[2], r[3]);
             } else {
                 float r[4];
-                finish4<kVecF64>(c4, s_tab, inc, p, q, r);
+                finish4<kVecF64>(c4, skr::smem_u32(s_tab), inc, p, q, r);
+                if (p.colmin) colmin_update(p.colmin, q, r);
                 if (p.min_cell) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) skr::min_update(r[e], tmin, tnan);
@@ -277,6 +318,7 @@ __global__ void __launch_bounds__(WarpCfg<K>::kThreads, WarpCfg<K>::kMinCtas) co
     const int team = threadIdx.x / TT, lane = threadIdx.x % TT;  // lane: index inside the team
     uint32_t* hist = smem_w + team * Cfg::kWords;
     float* tab = reinterpret_cast<float*>(smem_w + Cfg::kTeams * Cfg::kWords) + team * kTab;
+    const uint32_t hist_addr = skr::smem_u32(hist), tab_addr = skr::smem_u32(tab);
     float tmin = INFINITY;
     int tnan = 0;
 
@@ -344,16 +386,17 @@ __global__ void __launch_bounds__(WarpCfg<K>::kThreads, WarpCfg<K>::kMinCtas) co
                 const uint64_t m64 = ((uint64_t)m0 << 32) | m1;
                 const uint32_t mb = (uint32_t)((m64 << (16 * (c & 1))) >> (64 - (16 + K - 1)));
                 const long long left = nwin - (long long)c * 16;
-                count_chunk<K>(hist, x, mb, left < 16 ? (int)left : 16);
+                count_chunk<K>(hist_addr, x, mb, left < 16 ? (int)left : 16);
                 w0 = n0; w1 = n1; m0 = q0; m1 = q1;
             }
             team_sync();
             float* __restrict__ orow = reinterpret_cast<float*>(p.out) + (size_t)rec * (size_t)p.ld_out;
             for (int q = lane; q < Cfg::kBins / 4; q += TT) {
-                const uint2 v = reinterpret_cast<const uint2*>(hist)[q];
+                const uint2 v = lds_v2(hist_addr + q * 8);
                 const uint32_t c4[4] = {v.x & 0xFFFFu, v.x >> 16, v.y & 0xFFFFu, v.y >> 16};
                 float r[4];
-                finish4<kVecF64>(c4, tab, inc, p, q, r);
+                finish4<kVecF64>(c4, tab_addr, inc, p, q, r);
+                if (p.colmin) colmin_update(p.colmin, q, r);
                 if (p.min_cell) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) skr::min_update(r[e], tmin, tnan);
@@ -493,15 +536,16 @@ int dispatch_count(const CountParams& p, int vec_is_f64, int out_is_f64, cudaStr
 // ---------------------------------------------------------------------------------------------
 // element-wise kernels of the get_counts() tail
 // ---------------------------------------------------------------------------------------------
-enum { OP_LOG2 = 0, OP_POST = 1, OP_SUB = 2, OP_DIV = 3, OP_SCAN = 4, OP_NORM = 5 };
+enum { OP_LOG2 = 0, OP_POST = 1, OP_SUB = 2, OP_DIV = 3, OP_SCAN = 4, OP_NORM = 5, OP_NORMPOST = 6 };
 
 template <int OP, bool kVecF64>
 __device__ __forceinline__ float ew_apply(float v, const void* vec, const void* vec2, long long col, float shift) {
-    if constexpr (OP == OP_NORM) {  // fl(fl(v - mean) / std), either vector optional
+    if constexpr (OP == OP_NORM || OP == OP_NORMPOST) {  // fl(fl(v - mean) / std), either vector optional
         if (vec) v = kVecF64 ? __double2float_rn(__dsub_rn((double)v, __ldg((const double*)vec + col)))
                              : __fsub_rn(v, __ldg((const float*)vec + col));
         if (vec2) v = kVecF64 ? __double2float_rn(__ddiv_rn((double)v, __ldg((const double*)vec2 + col)))
                               : __fdiv_rn(v, __ldg((const float*)vec2 + col));
+        if constexpr (OP == OP_NORMPOST) v = log2f(__fadd_rn(__fadd_rn(v, shift), 1.0f));  // then the Log2.post tail
         return v;
     }
     if constexpr (OP == OP_LOG2) return log2f(__fadd_rn(v, 1.0f));
@@ -524,7 +568,7 @@ __global__ void __launch_bounds__(256) ew_kernel(float* a, long long m, long lon
     __shared__ float s_wmin[8];
     __shared__ int s_wnan[8];
     float shift = 0.0f;
-    if constexpr (OP == OP_POST) {
+    if constexpr (OP == OP_POST || OP == OP_NORMPOST) {
         // np.abs(np.min(counts)): NaN anywhere makes the shift NaN, hence the whole matrix (kmer_counts.py:208)
         shift = min_in->nan_seen ? __int_as_float(0x7FC00000) : fabsf(skr::ordered_decode(min_in->min_ordered));
     }
@@ -586,6 +630,40 @@ int launch_ew(float* a, long long m, long long cols, long long ld, const void* v
     return SKR_OK;
 }
 
+// min over columns of fl(fl(colmin_j - mean_j) / std_j): the matrix-wide minimum of the normalised values
+// when every std_j is positive and finite (rounded subtraction and division are monotone)
+template <bool kVecF64>
+__global__ void __launch_bounds__(256) colmin_finish_kernel(const uint32_t* colmin, long long cols, const void* mean,
+                                                            const void* std_, SkrMinCell* cell) {
+    __shared__ float s_wmin[8];
+    __shared__ int s_wnan[8];
+    float tmin = INFINITY;
+    int tnan = 0;
+    for (long long j = threadIdx.x; j < cols; j += 256) {
+        float v = __uint_as_float(colmin[j]);
+        v = ew_apply<OP_NORM, kVecF64>(v, mean, std_, j, 0.0f);
+        skr::min_update(v, tmin, tnan);
+    }
+    skr::min_commit<256>(tmin, tnan, s_wmin, s_wnan, cell);
+}
+
+__global__ void colmin_reset_kernel(uint32_t* colmin, long long cols) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < cols) colmin[j] = 0x7F800000u;  // +inf
+}
+
+// flag |= 1 if any element is not finite, |= 2 if any element is <= 0
+template <typename T>
+__global__ void vec_check_kernel(const T* v, long long n, int* flag) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const double x = (double)v[j];
+    int f = 0;
+    if (!(x - x == 0.0)) f |= 1;
+    if (!(x > 0.0)) f |= 2;
+    if (f) atomicOr(flag, f);
+}
+
 __global__ void min_reset_kernel(SkrMinCell* cell) {
     cell->min_ordered = skr::ordered_encode(INFINITY);
     cell->nan_seen = 0;
@@ -640,6 +718,75 @@ extern "C" int skr_count(const uint32_t* d_codes, const uint32_t* d_mask, const 
         case 7: return dispatch_count<7>(p, vec_is_f64, out_is_f64, s);
         default: return dispatch_count<8>(p, vec_is_f64, out_is_f64, s);
     }
+}
+
+extern "C" int skr_colmin_reset(uint32_t* d_colmin, int64_t cols, void* stream) {
+    if (cols <= 0) return SKR_OK;
+    if (!d_colmin) return skr::fail(SKR_ERR_ARG, "skr_colmin_reset: null");
+    colmin_reset_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_colmin, cols);
+    SKR_LAUNCH_CHECK();
+    return SKR_OK;
+}
+
+extern "C" int skr_count_colmin(const uint32_t* d_codes, const uint32_t* d_mask, const uint64_t* d_block_offsets,
+                                const uint32_t* d_lengths, int64_t m, int k, int log2_pre, float* d_out, int64_t ld_out,
+                                uint32_t* d_colmin, void* stream) {
+    if (m == 0) return SKR_OK;
+    if (!d_codes || !d_mask || !d_block_offsets || !d_lengths || !d_out || !d_colmin || m < 0)
+        return skr::fail(SKR_ERR_ARG, "skr_count_colmin: null or negative argument");
+    if (k < 1 || k > 8) return skr::fail(SKR_ERR_ARG, "skr_count_colmin: k=%d not supported (1 <= k <= 8)", k);
+    const int64_t bins = (int64_t)1 << (2 * k);
+    if (ld_out < bins || ((uintptr_t)d_out & 15) || (ld_out % 4) || ((uintptr_t)d_colmin & 15))
+        return skr::fail(SKR_ERR_ARG, "skr_count_colmin: bad pitch or alignment");
+    CountParams p{};
+    p.codes = d_codes;
+    p.mask = d_mask;
+    p.blk_off = d_block_offsets;
+    p.len = d_lengths;
+    p.m = m;
+    p.log2_pre = log2_pre;
+    p.out = d_out;
+    p.ld_out = ld_out;
+    p.colmin = d_colmin;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (k) {
+        case 1: return dispatch_count<1>(p, 0, 0, s);
+        case 2: return dispatch_count<2>(p, 0, 0, s);
+        case 3: return dispatch_count<3>(p, 0, 0, s);
+        case 4: return dispatch_count<4>(p, 0, 0, s);
+        case 5: return dispatch_count<5>(p, 0, 0, s);
+        case 6: return dispatch_count<6>(p, 0, 0, s);
+        case 7: return dispatch_count<7>(p, 0, 0, s);
+        default: return dispatch_count<8>(p, 0, 0, s);
+    }
+}
+
+extern "C" int skr_colmin_finish(const uint32_t* d_colmin, int64_t cols, const void* d_mean, const void* d_std,
+                                 int vec_is_f64, SkrMinCell* d_min, void* stream) {
+    if (!d_colmin || !d_min || cols <= 0) return skr::fail(SKR_ERR_ARG, "skr_colmin_finish: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    min_reset_kernel<<<1, 1, 0, s>>>(d_min);
+    SKR_LAUNCH_CHECK();
+    if (vec_is_f64) colmin_finish_kernel<true><<<1, 256, 0, s>>>(d_colmin, cols, d_mean, d_std, d_min);
+    else colmin_finish_kernel<false><<<1, 256, 0, s>>>(d_colmin, cols, d_mean, d_std, d_min);
+    SKR_LAUNCH_CHECK();
+    return SKR_OK;
+}
+
+extern "C" int skr_normalize_post_log2(float* d_a, int64_t m, int64_t cols, int64_t ld, const void* d_mean,
+                                       const void* d_std, int vec_is_f64, const SkrMinCell* d_min, void* stream) {
+    if (!d_min) return skr::fail(SKR_ERR_ARG, "skr_normalize_post_log2: null min cell");
+    return launch_ew<OP_NORMPOST>(d_a, m, cols, ld, d_mean, vec_is_f64, d_min, nullptr, (cudaStream_t)stream, d_std);
+}
+
+extern "C" int skr_vec_check(const void* d_vec, int vec_is_f64, int64_t n, int* d_flag, void* stream) {
+    if (n <= 0) return SKR_OK;
+    if (!d_vec || !d_flag) return skr::fail(SKR_ERR_ARG, "skr_vec_check: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (vec_is_f64) vec_check_kernel<double><<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const double*)d_vec, n, d_flag);
+    else vec_check_kernel<float><<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const float*)d_vec, n, d_flag);
+    SKR_LAUNCH_CHECK();
+    return SKR_OK;
 }
 
 extern "C" int skr_log2_norm(float* d_a, int64_t m, int64_t cols, int64_t ld, void* stream) {

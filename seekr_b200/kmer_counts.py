@@ -66,21 +66,45 @@ def _vector_for(value, cols):
 
 
 class DeviceVector:
-    """A mean/std vector resident on the device, fp32 or fp64."""
+    """A mean/std vector resident on the device, fp32 or fp64.
 
-    def __init__(self, tensor, is_f64):
+    ``finite`` / ``positive`` say whether every element is finite / > 0 (None = not known yet; resolved
+    on the device by ``check()``).  The deferred-normalisation path needs a finite mean and a finite,
+    positive std (kmer_counts.CountEngine.run)."""
+
+    def __init__(self, tensor, is_f64, finite=None, positive=None):
         self.t = tensor
         self.is_f64 = is_f64
+        self.finite = finite
+        self.positive = positive
 
     @classmethod
     def from_host(cls, value, cols):
         vec, is_f64 = _vector_for(value, cols)
-        return cls(device.to_device(vec), is_f64)
+        with np.errstate(all="ignore"):
+            finite = bool(np.all(np.isfinite(vec)))
+            positive = bool(np.all(vec > 0))
+        return cls(device.to_device(vec), is_f64, finite, positive)
 
     def as_f64(self):
         import torch
 
-        return self if self.is_f64 else DeviceVector(self.t.to(torch.float64), True)
+        return self if self.is_f64 else DeviceVector(self.t.to(torch.float64), True, self.finite, self.positive)
+
+    def check(self, stream=None):
+        """Resolve finite / positive with skr_vec_check (one 4-byte read-back)."""
+        if self.finite is None or self.positive is None:
+            import torch
+
+            flag = device.zeros(1, torch.int32)
+            _lib.check(_lib.load().skr_vec_check(device.ptr(self.t), int(self.is_f64), self.t.numel(), device.ptr(flag),
+                                                 device.stream_ptr(stream)))
+            host = np.zeros(1, dtype=np.int32)
+            device.d2h(host, flag, stream)
+            device.sync(stream)
+            self.finite = not (int(host[0]) & 1)
+            self.positive = not (int(host[0]) & 2)
+        return self
 
 
 class CountEngine:
@@ -97,7 +121,8 @@ class CountEngine:
         self.log2 = log2
         self.stream = stream
         self.min_cell = device.MinCell()
-        self.nan_cell = device.MinCell()
+        self.count_events = None  # set to a list to collect (start, end) CUDA events around every count launch
+        self.deferred = True      # allow the deferred-normalisation path for Log2.post with known vectors
 
     # -- building blocks ------------------------------------------------------------------------
     def upload(self, packed):
@@ -121,13 +146,39 @@ class CountEngine:
         log2_pre = 1 if self.log2 == "Log2.pre" else 0
         if track_min:
             self.min_cell.reset(self.stream)
+        ev = self._event_start()
         rc = self.lib.skr_count(
             dpk.codes, dpk.mask, dpk.blk_off, dpk.lengths, dpk.m, self.k, 0 if out_is_f64 else log2_pre,
             device.ptr(mean.t if mean else None), device.ptr(std.t if std else None), int(vec_is_f64),
             device.ptr(out), int(out_is_f64), out.stride(0), device.ptr(self.min_cell.t if track_min else None),
             device.stream_ptr(self.stream))
         _lib.check(rc)
+        self._event_end(ev)
         self._keep = (mean, std)  # converted vectors must outlive the launch
+
+    def _event_start(self):
+        if self.count_events is None:
+            return None
+        ev = self.torch.cuda.Event(enable_timing=True)
+        ev.record(self.stream if self.stream is not None else self.torch.cuda.current_stream())
+        return ev
+
+    def _event_end(self, start):
+        if start is None:
+            return
+        end = self.torch.cuda.Event(enable_timing=True)
+        end.record(self.stream if self.stream is not None else self.torch.cuda.current_stream())
+        self.count_events.append((start, end))
+
+    def count_colmin(self, dpk, out, colmin):
+        """Un-normalised counts (log2'd for Log2.pre) + running per-column minimum (skr_count_colmin)."""
+        log2_pre = 1 if self.log2 == "Log2.pre" else 0
+        _lib.check(self.lib.skr_colmin_reset(device.ptr(colmin), colmin.numel(), device.stream_ptr(self.stream)))
+        ev = self._event_start()
+        _lib.check(self.lib.skr_count_colmin(dpk.codes, dpk.mask, dpk.blk_off, dpk.lengths, dpk.m, self.k, log2_pre,
+                                             device.ptr(out), out.stride(0), device.ptr(colmin),
+                                             device.stream_ptr(self.stream)))
+        self._event_end(ev)
 
     def col_sum(self, kind, a, vec=None, vec2=None):
         """One order-exact column pass over ``a`` (all rows on this device); returns the fp32 sums."""
@@ -212,6 +263,28 @@ class CountEngine:
         mean_vec = mean if isinstance(mean, DeviceVector) else None
         std_vec = std if isinstance(std, DeviceVector) else None
 
+        if mean is not True and std is not True and need_min and (mean_vec or std_vec) and self.deferred \
+                and self._benign(mean_vec, std_vec):
+            # Log2.post with known, well-behaved vectors: the count kernel only tracks per-column minima
+            # (the shift follows from them because rounded -mean, /std>0 are monotone) and the element-wise
+            # pass, which is bandwidth-bound anyway, does -mean, /std, +|min|, +1, log2 in one go
+            if mean_vec is not None and std_vec is not None and mean_vec.is_f64 != std_vec.is_f64:
+                mean_vec, std_vec = mean_vec.as_f64(), std_vec.as_f64()
+            is_f64 = (mean_vec or std_vec).is_f64
+            colmin = device.empty(self.cols, torch.int32)
+            self.count_colmin(dpk, out, colmin)
+            if reducer:
+                reducer.colmin_allreduce(colmin)
+            sp = device.stream_ptr(self.stream)
+            _lib.check(self.lib.skr_colmin_finish(device.ptr(colmin), self.cols, device.ptr(mean_vec.t if mean_vec else None),
+                                                  device.ptr(std_vec.t if std_vec else None), int(is_f64),
+                                                  device.ptr(self.min_cell.t), sp))
+            _lib.check(self.lib.skr_normalize_post_log2(device.ptr(out), m, self.cols, out.stride(0),
+                                                        device.ptr(mean_vec.t if mean_vec else None),
+                                                        device.ptr(std_vec.t if std_vec else None), int(is_f64),
+                                                        device.ptr(self.min_cell.t), sp))
+            self._keep = (mean_vec, std_vec, colmin)
+            return out, mean_vec, std_vec
         if mean is not True and std is not True:
             # every vector is known up front: one fused launch (+ the Log2.post pass)
             track = need_min or std is not False
@@ -241,6 +314,15 @@ class CountEngine:
                 reducer.min_allreduce(self)
             self.post_log2(out)
         return out, mean_vec, std_vec
+
+    def _benign(self, mean_vec, std_vec):
+        if mean_vec is not None and not mean_vec.check(self.stream).finite:
+            return False
+        if std_vec is not None:
+            std_vec.check(self.stream)
+            if not (std_vec.finite and std_vec.positive):
+                return False
+        return True
 
     def _local_col_stat(self, engine, kind, a, vec, vec2, finish):
         acc = self.col_sum(kind, a, vec, vec2)

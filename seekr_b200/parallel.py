@@ -88,6 +88,11 @@ class _Base:
             self._total_rows = int(t.item())
         return self._total_rows
 
+    def colmin_allreduce(self, colmin):
+        """Per-column minima of non-negative floats, stored as their bit patterns in an int32 tensor:
+        the integer order is the float order, so a plain MIN all-reduce merges the shards."""
+        self.dist.all_reduce(colmin, op=self.dist.ReduceOp.MIN, group=self.group)
+
     def min_allreduce(self, engine):
         """Combine the per-rank Log2.post cells (uint32 pair on the device) across ranks."""
         import torch

@@ -391,3 +391,49 @@ def test_full_size_properties():
     text = letters.tobytes().decode("ascii")
     sub = [text[offs[i]:offs[i + 1]] for i in rows]
     assert np.array_equal(dev[torch.from_numpy(rows).cuda()].cpu().numpy(), c_oracle.raw_counts(sub, 6))
+
+
+def test_deferred_normalisation_is_bit_identical_to_fused():
+    """Log2.post with known vectors: column-minimum shift + one element-wise pass == fused kernel + post pass."""
+    seqs = synth.seq_strings(400, seed=8, stress=True, lo=60, hi=4000)
+    for k in (3, 6):
+        sub = [s for s in seqs if len(s) != k - 1]
+        raw = c_oracle.raw_counts(sub, k)
+        mean = raw.mean(axis=0).astype(np.float32)
+        std = (raw.std(axis=0) + 0.125).astype(np.float32)
+        packed = PackedFasta.from_sequences(sub, pinned=True)
+        outs = []
+        for deferred in (True, False):
+            eng = CountEngine(k, "Log2.post")
+            eng.deferred = deferred
+            dpk = eng.upload(packed)
+            out, _, _ = eng.run(dpk, DeviceVector.from_host(mean, 4 ** k), DeviceVector.from_host(std, 4 ** k))
+            outs.append(out.cpu().numpy())
+        assert np.array_equal(outs[0], outs[1])
+        exp, _, _ = c_oracle.normalise(raw, mean, std, "Log2.post")
+        assert np.allclose(outs[0], exp, rtol=0, atol=TOL)
+        # float64 vectors and mean-only / std-only variants
+        for mv, sv in ((mean.astype(np.float64), std.astype(np.float64)), (mean, False), (False, std)):
+            c = BasicCounter(k=k, mean=mv, std=sv, log2="Log2.post", silent=True)
+            c.seqs = sub
+            c.get_counts()
+            exp, _, _ = c_oracle.normalise(raw, mv, sv, "Log2.post")
+            assert np.allclose(c.counts, exp, rtol=0, atol=TOL)
+
+
+def test_badly_behaved_vectors_take_the_fused_path(capsys):
+    """A zero / negative / NaN std breaks monotonicity: the engine must fall back and still match the reference."""
+    seqs = synth.seq_strings(60, seed=9, lo=60, hi=900)
+    raw = c_oracle.raw_counts(seqs, 3)
+    mean = raw.mean(axis=0).astype(np.float32)
+    for bad in (0.0, -1.5, np.nan):
+        std = (raw.std(axis=0) + 0.5).astype(np.float32)
+        std[7] = bad
+        c = BasicCounter(k=3, mean=mean, std=std, log2="Log2.post", silent=True)
+        c.seqs = seqs
+        c.get_counts()
+        with np.errstate(all="ignore"):
+            exp, _, _ = c_oracle.normalise(raw, mean, std, "Log2.post")
+        assert np.allclose(c.counts, exp, rtol=0, atol=TOL, equal_nan=True)
+        warned = "WARNING: You have `np.nan` values" in capsys.readouterr().out
+        assert warned == bool(np.isnan(exp).any())

@@ -1,0 +1,68 @@
+"""Run under torchrun on N >= 2 GPUs: sharded counts / Pearson equal the single-GPU results (dev tool + test body)."""
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from seekr_b200 import sharded, synth  # noqa: E402
+from seekr_b200.kmer_counts import BasicCounter  # noqa: E402
+from seekr_b200.pearson import pearson  # noqa: E402
+
+
+def main():
+    rank, world = sharded.init()
+    path = os.path.join(tempfile.gettempdir(), "skr_multi_check.fa")
+    if rank == 0:
+        synth.write_fasta(path, 3000, seed=123, stress=True, lo=30, hi=6000)
+    dist.barrier()
+    k = 5
+    results = {}
+    for stats in ("chain", "allreduce"):
+        for mode in ("Log2.post", "Log2.none"):
+            local, (b, e), mean, std, full = sharded.get_counts(path, k=k, log2=mode, stats=stats, gather=True)
+            results[(stats, mode)] = (local, b, e, mean, std, full)
+    vec_local, (vb, ve), _, _, vec_full = sharded.get_counts(path, k=k, mean=results[("chain", "Log2.none")][3],
+                                                             std=results[("chain", "Log2.none")][4], log2="Log2.post",
+                                                             gather=True)
+    r_local = sharded.pearson_rows(vec_local, vec_full if rank == 0 else None)
+    ok = True
+    if rank == 0:
+        for mode in ("Log2.post", "Log2.none"):
+            ref = BasicCounter(path, k=k, log2=mode, silent=True)
+            ref.get_counts()
+            local, b, e, mean, std, full = results[("chain", mode)]
+            exact = np.array_equal(mean, ref.mean) and np.array_equal(std, ref.std, equal_nan=True) and \
+                np.array_equal(full, ref.counts, equal_nan=True)
+            print("chain %s: bit-identical to 1 GPU: %s" % (mode, exact))
+            ok &= bool(exact)
+            local, b, e, mean, std, full = results[("allreduce", mode)]
+            dm = float(np.nanmax(np.abs(mean - ref.mean) / np.abs(ref.mean)))
+            ds = float(np.nanmax(np.abs(std - ref.std) / np.abs(ref.std)))
+            dc = float(np.nanmax(np.abs(full - ref.counts)))
+            print("allreduce %s: rel diff mean %.2e std %.2e, max abs diff counts %.2e" % (mode, dm, ds, dc))
+            ok &= dm < 1e-5 and ds < 1e-4 and dc < 1e-3
+        ref = BasicCounter(path, k=k, mean=results[("chain", "Log2.none")][3], std=results[("chain", "Log2.none")][4],
+                           log2="Log2.post", silent=True)
+        ref.get_counts()
+        same = np.array_equal(vec_full, ref.counts, equal_nan=True)
+        print("vectors + Log2.post sharded == 1 GPU: %s" % same)
+        ok &= bool(same)
+        r_ref = pearson(ref.counts, ref.counts)
+        d = float(np.nanmax(np.abs(r_local - r_ref[vb:ve])))
+        print("pearson row block vs 1 GPU: max abs diff %.2e" % d)
+        ok &= d < 2e-6
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, src=0)
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("MULTI_GPU_CHECK", "PASS" if ok else "FAIL")
+    sys.exit(0 if int(flag.item()) else 1)
+
+
+if __name__ == "__main__":
+    main()
