@@ -60,6 +60,7 @@ struct CountParams {
 // floor of this path, so it is stored plainly (every writer writes the same value).
 __device__ __forceinline__ void colmin_update(uint32_t* colmin, int q, const float (&r)[4]) {
     const uint4 cm = *reinterpret_cast<const uint4*>(colmin + 4 * q);
+    if ((cm.x | cm.y | cm.z | cm.w) == 0) return;  // the usual state once a few records have been seen
     const uint32_t cur[4] = {cm.x, cm.y, cm.z, cm.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -561,7 +562,26 @@ __device__ __forceinline__ float ew_apply(float v, const void* vec, const void* 
     return v;
 }
 
-// Rows are contiguous when ld == cols; the vector path needs cols % 4 == 0 and 16-byte aligned rows.
+// Element-wise kernels walk the matrix column-quad by column-quad: a thread owns four consecutive
+// columns (blockIdx.x * 256 + threadIdx.x) and strides over rows (blockIdx.y, gridDim.y), so its mean /
+// std values are loaded once into registers and no index division is needed; a warp reads 512
+// contiguous bytes of a row per step.  The vector path needs cols % 4 == 0 and 16-byte aligned rows.
+template <int OP, bool kVecF64>
+__device__ __forceinline__ float ew_apply_reg(float v, double m64, double s64, float m32, float s32, bool has_mean,
+                                              bool has_std, float shift) {
+    if constexpr (OP == OP_LOG2) return log2f(__fadd_rn(v, 1.0f));
+    if constexpr (OP == OP_POST) return log2f(__fadd_rn(__fadd_rn(v, shift), 1.0f));
+    if constexpr (OP == OP_SUB) return kVecF64 ? __double2float_rn(__dsub_rn((double)v, m64)) : __fsub_rn(v, m32);
+    if constexpr (OP == OP_DIV) return kVecF64 ? __double2float_rn(__ddiv_rn((double)v, m64)) : __fdiv_rn(v, m32);
+    if constexpr (OP == OP_NORM || OP == OP_NORMPOST) {
+        if (has_mean) v = kVecF64 ? __double2float_rn(__dsub_rn((double)v, m64)) : __fsub_rn(v, m32);
+        if (has_std) v = kVecF64 ? __double2float_rn(__ddiv_rn((double)v, s64)) : __fdiv_rn(v, s32);
+        if constexpr (OP == OP_NORMPOST) v = log2f(__fadd_rn(__fadd_rn(v, shift), 1.0f));
+        return v;
+    }
+    return v;
+}
+
 template <int OP, bool kVecF64, bool kVec4>
 __global__ void __launch_bounds__(256) ew_kernel(float* a, long long m, long long cols, long long ld, const void* vec,
                                                  const void* vec2, const SkrMinCell* min_in, SkrMinCell* min_out) {
@@ -574,31 +594,39 @@ __global__ void __launch_bounds__(256) ew_kernel(float* a, long long m, long lon
     }
     float tmin = INFINITY;
     int tnan = 0;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    if constexpr (kVec4) {
-        const long long c4 = cols / 4;
-        const long long total = m * c4;
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-            const long long r = i / c4, q = i - r * c4;
-            float4* ptr = reinterpret_cast<float4*>(a + r * ld) + q;
-            float4 v = *ptr;
-            v.x = ew_apply<OP, kVecF64>(v.x, vec, vec2, 4 * q + 0, shift);
-            v.y = ew_apply<OP, kVecF64>(v.y, vec, vec2, 4 * q + 1, shift);
-            v.z = ew_apply<OP, kVecF64>(v.z, vec, vec2, 4 * q + 2, shift);
-            v.w = ew_apply<OP, kVecF64>(v.w, vec, vec2, 4 * q + 3, shift);
-            if (min_out) {
-                skr::min_update(v.x, tmin, tnan); skr::min_update(v.y, tmin, tnan);
-                skr::min_update(v.z, tmin, tnan); skr::min_update(v.w, tmin, tnan);
-            }
-            if constexpr (OP != OP_SCAN) *ptr = v;
+    constexpr int W = kVec4 ? 4 : 1;
+    const long long q = (long long)blockIdx.x * 256 + threadIdx.x;  // column group
+    const long long col0 = q * W;
+    if (col0 < cols) {
+        // this thread's slice of the vectors (vec: mean or the single operand; vec2: std)
+        float m32[W], s32[W];
+        double m64[W], s64[W];
+#pragma unroll
+        for (int e = 0; e < W; ++e) {
+            m32[e] = s32[e] = 0.0f;
+            m64[e] = s64[e] = 0.0;
+            if (vec) { if (kVecF64) m64[e] = ((const double*)vec)[col0 + e]; else m32[e] = ((const float*)vec)[col0 + e]; }
+            if (vec2) { if (kVecF64) s64[e] = ((const double*)vec2)[col0 + e]; else s32[e] = ((const float*)vec2)[col0 + e]; }
         }
-    } else {
-        const long long total = m * cols;
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-            const long long r = i / cols, c = i - r * cols;
-            float v = ew_apply<OP, kVecF64>(a[r * ld + c], vec, vec2, c, shift);
-            if (min_out) skr::min_update(v, tmin, tnan);
-            if constexpr (OP != OP_SCAN) a[r * ld + c] = v;
+        const bool has_mean = vec != nullptr, has_std = vec2 != nullptr;
+        for (long long r = blockIdx.y; r < m; r += gridDim.y) {
+            if constexpr (kVec4) {
+                float4* ptr = reinterpret_cast<float4*>(a + r * ld) + q;
+                float4 v = *ptr;
+                v.x = ew_apply_reg<OP, kVecF64>(v.x, m64[0], s64[0], m32[0], s32[0], has_mean, has_std, shift);
+                v.y = ew_apply_reg<OP, kVecF64>(v.y, m64[1], s64[1], m32[1], s32[1], has_mean, has_std, shift);
+                v.z = ew_apply_reg<OP, kVecF64>(v.z, m64[2], s64[2], m32[2], s32[2], has_mean, has_std, shift);
+                v.w = ew_apply_reg<OP, kVecF64>(v.w, m64[3], s64[3], m32[3], s32[3], has_mean, has_std, shift);
+                if (min_out) {
+                    skr::min_update(v.x, tmin, tnan); skr::min_update(v.y, tmin, tnan);
+                    skr::min_update(v.z, tmin, tnan); skr::min_update(v.w, tmin, tnan);
+                }
+                if constexpr (OP != OP_SCAN) *ptr = v;
+            } else {
+                float v = ew_apply_reg<OP, kVecF64>(a[r * ld + col0], m64[0], s64[0], m32[0], s32[0], has_mean, has_std, shift);
+                if (min_out) skr::min_update(v, tmin, tnan);
+                if constexpr (OP != OP_SCAN) a[r * ld + col0] = v;
+            }
         }
     }
     if (min_out) skr::min_commit<256>(tmin, tnan, s_wmin, s_wnan, min_out);
@@ -614,12 +642,15 @@ int launch_ew(float* a, long long m, long long cols, long long ld, const void* v
     int dev = 0, sms = 0;
     SKR_CUDA_CHECK(cudaGetDevice(&dev));
     SKR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const long long work = vec4 ? m * (cols / 4) : m * cols;
-    long long grid = (work + 255) / 256;
-    const long long cap = (long long)sms * 8;  // 8 resident CTAs of 256 threads per SM, grid-stride beyond that
-    if (grid > cap) grid = cap;
+    const long long groups = vec4 ? cols / 4 : cols;
+    const long long gx = (groups + 255) / 256;
+    long long gy = ((long long)sms * 8 + gx - 1) / gx;  // ~8 resident CTAs of 256 threads per SM
+    if (gy > m) gy = m;
+    if (gy > 65535) gy = 65535;
+    if (gx > 0x7FFFFFFFll) return skr::fail(SKR_ERR_ARG, "matrix too wide");
+    dim3 grid((unsigned)gx, (unsigned)gy);
     auto go = [&](auto kern) {
-        kern<<<(unsigned)grid, 256, 0, stream>>>(a, m, cols, ld, vec, vec2, min_in, min_out);
+        kern<<<grid, 256, 0, stream>>>(a, m, cols, ld, vec, vec2, min_in, min_out);
     };
     if (vec_is_f64) {
         if (vec4) go(ew_kernel<OP, true, true>); else go(ew_kernel<OP, true, false>);

@@ -316,12 +316,24 @@ class CountEngine:
         return out, mean_vec, std_vec
 
     def _benign(self, mean_vec, std_vec):
-        if mean_vec is not None and not mean_vec.check(self.stream).finite:
+        """Finite mean and finite, positive std?  Host-born vectors already know; device-born ones are
+        checked with skr_vec_check, both through a single 8-byte read-back."""
+        todo = [v for v in (mean_vec, std_vec) if v is not None and (v.finite is None or v.positive is None)]
+        if todo:
+            flags = device.zeros(2, self.torch.int32)
+            for i, v in enumerate(todo):
+                _lib.check(self.lib.skr_vec_check(device.ptr(v.t), int(v.is_f64), v.t.numel(),
+                                                  ctypes.c_void_p(flags.data_ptr() + 4 * i), device.stream_ptr(self.stream)))
+            host = np.zeros(2, dtype=np.int32)
+            device.d2h(host, flags, self.stream)
+            device.sync(self.stream)
+            for i, v in enumerate(todo):
+                v.finite = not (int(host[i]) & 1)
+                v.positive = not (int(host[i]) & 2)
+        if mean_vec is not None and not mean_vec.finite:
             return False
-        if std_vec is not None:
-            std_vec.check(self.stream)
-            if not (std_vec.finite and std_vec.positive):
-                return False
+        if std_vec is not None and not (std_vec.finite and std_vec.positive):
+            return False
         return True
 
     def _local_col_stat(self, engine, kind, a, vec, vec2, finish):
