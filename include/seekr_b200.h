@@ -113,7 +113,7 @@ int skr_count(const uint32_t* d_codes, const uint32_t* d_mask, const uint64_t* d
 
 /* Deferred normalisation for Log2.post with known, finite mean / positive std vectors (the
  * seekr_kmer_counts -mv -sv path): the count kernel writes the un-normalised values and keeps the
- * per-column minimum (float bits, +inf initialised by skr_colmin_reset); because rounded subtraction and
+ * per-column minimum (float bits, +inf initialised by skr_colmin_reset; completed by skr_colmin_scan); because rounded subtraction and
  * division by a positive number are monotone, min_ij fl(fl(x_ij - mean_j)/std_j) = min_j fl(fl(xmin_j -
  * mean_j)/std_j), which skr_colmin_finish puts into the min cell; skr_normalize_post_log2 then applies
  * -mean, /std, +|min|, +1, log2 in one element-wise pass (same roundings as kmer_counts.py:169,175,207-209).
@@ -123,6 +123,8 @@ int skr_colmin_reset(uint32_t* d_colmin, int64_t cols, void* stream);
 int skr_count_colmin(const uint32_t* d_codes, const uint32_t* d_mask, const uint64_t* d_block_offsets,
                      const uint32_t* d_lengths, int64_t m, int k, int log2_pre, float* d_out, int64_t ld_out,
                      uint32_t* d_colmin, void* stream);
+/* columns in which no record had a zero count still hold +inf after skr_count_colmin: reduce them over the rows */
+int skr_colmin_scan(const float* d_a, int64_t m, int64_t cols, int64_t ld, uint32_t* d_colmin, void* stream);
 int skr_colmin_finish(const uint32_t* d_colmin, int64_t cols, const void* d_mean, const void* d_std, int vec_is_f64,
                       SkrMinCell* d_min, void* stream);
 int skr_normalize_post_log2(float* d_a, int64_t m, int64_t cols, int64_t ld, const void* d_mean, const void* d_std,
@@ -163,8 +165,10 @@ enum {
  * skr_normalize writes the final matrix once.  d_vec: mean vector (fp32 or fp64), d_vec2: fp32. */
 int skr_col_pass(int kind, const float* d_a, int64_t m, int64_t cols, int64_t ld, const void* d_vec, int vec_is_f64,
                  const float* d_vec2, float* d_acc, void* stream);
-/* mean[j] = (float)((double)acc[j] / rows);  std[j] = sqrtf((float)((double)acc[j] / rows)) */
-int skr_col_finish(const float* d_acc, int64_t cols, int64_t total_rows, int take_sqrt, float* d_out, void* stream);
+/* mean[j] = (float)((double)acc[j] / rows);  std[j] = sqrtf((float)((double)acc[j] / rows)).
+ * d_flag (optional, one int): bit 0 set if a result is not finite, bit 1 if a result is <= 0. */
+int skr_col_finish(const float* d_acc, int64_t cols, int64_t total_rows, int take_sqrt, float* d_out, int* d_flag,
+                   void* stream);
 
 /* Scalable passes for sharded runs: per-column binary64 partial sums computed row-parallel
  * (to be summed across ranks with one all-reduce), kinds as above.  More accurate than the
@@ -172,7 +176,7 @@ int skr_col_finish(const float* d_acc, int64_t cols, int64_t total_rows, int tak
 int skr_col_partial_f64(int kind, const float* d_a, int64_t m, int64_t cols, int64_t ld, const void* d_vec,
                         int vec_is_f64, const float* d_vec2, double* d_acc, void* stream);
 int skr_col_finish_f64(const double* d_acc, int64_t cols, int64_t total_rows, int take_sqrt, float* d_out,
-                       void* stream);
+                       int* d_flag, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Pearson   (replaces seekr/pearson.py:32-44)

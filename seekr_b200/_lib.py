@@ -53,6 +53,7 @@ SIGNATURES = {
     "skr_count": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _int, _vp, _vp, _int, _vp, _int, _i64, _vp, _vp]),
     "skr_colmin_reset": (_int, [_vp, _i64, _vp]),
     "skr_count_colmin": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _int, _vp, _i64, _vp, _vp]),
+    "skr_colmin_scan": (_int, [_vp, _i64, _i64, _i64, _vp, _vp]),
     "skr_colmin_finish": (_int, [_vp, _i64, _vp, _vp, _int, _vp, _vp]),
     "skr_normalize_post_log2": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _int, _vp, _vp]),
     "skr_vec_check": (_int, [_vp, _int, _i64, _vp, _vp]),
@@ -63,9 +64,9 @@ SIGNATURES = {
     "skr_normalize": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _int, _vp, _vp]),
     "skr_min_scan": (_int, [_vp, _i64, _i64, _i64, _vp, _vp]),
     "skr_col_pass": (_int, [_int, _vp, _i64, _i64, _i64, _vp, _int, _vp, _vp, _vp]),
-    "skr_col_finish": (_int, [_vp, _i64, _i64, _int, _vp, _vp]),
+    "skr_col_finish": (_int, [_vp, _i64, _i64, _int, _vp, _vp, _vp]),
     "skr_col_partial_f64": (_int, [_int, _vp, _i64, _i64, _i64, _vp, _int, _vp, _vp, _vp]),
-    "skr_col_finish_f64": (_int, [_vp, _i64, _i64, _int, _vp, _vp]),
+    "skr_col_finish_f64": (_int, [_vp, _i64, _i64, _int, _vp, _vp, _vp]),
     "skr_pearson_rows_padded": (_i64, [_i64]),
     "skr_pearson_k_padded": (_i64, [_i64]),
     "skr_pearson_prepare": (_int, [_vp, _int, _i64, _i64, _i64, _int, _vp, _vp, _vp, _vp]),

@@ -109,21 +109,33 @@ __global__ void __launch_bounds__(64) col_pass_kernel(const __grid_constant__ CU
     if (active) acc_io[col] = acc;
 }
 
-__global__ void col_finish_kernel(const float* acc, long long cols, long long rows, int take_sqrt, float* out) {
+// flag (optional): bit 0 set if any result is not finite, bit 1 if any result is <= 0
+__device__ __forceinline__ void note_flag(float v, int* flag) {
+    if (!flag) return;
+    int f = 0;
+    if (!(v - v == 0.0f)) f |= 1;
+    if (!(v > 0.0f)) f |= 2;
+    if (f) atomicOr(flag, f);
+}
+
+__global__ void col_finish_kernel(const float* acc, long long cols, long long rows, int take_sqrt, float* out, int* flag) {
     const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= cols) return;
     // numpy divides the fp32 sum by the row count in binary64 and rounds to fp32 (_methods.py:_mean/_var)
     float v = __double2float_rn(__ddiv_rn((double)acc[j], (double)rows));
     if (take_sqrt) v = __fsqrt_rn(v);
     out[j] = v;
+    note_flag(v, flag);
 }
 
-__global__ void col_finish_f64_kernel(const double* acc, long long cols, long long rows, int take_sqrt, float* out) {
+__global__ void col_finish_f64_kernel(const double* acc, long long cols, long long rows, int take_sqrt, float* out,
+                                      int* flag) {
     const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= cols) return;
     double v = acc[j] / (double)rows;
     if (take_sqrt) v = sqrt(v);
     out[j] = (float)v;
+    note_flag((float)v, flag);
 }
 
 // Row-parallel binary64 partial sums: a CTA covers 128 columns x a slab of rows; thread = column.
@@ -195,11 +207,12 @@ extern "C" int skr_col_pass(int kind, const float* d_a, int64_t m, int64_t cols,
 }
 
 extern "C" int skr_col_finish(const float* d_acc, int64_t cols, int64_t total_rows, int take_sqrt, float* d_out,
-                              void* stream) {
+                              int* d_flag, void* stream) {
     if (cols <= 0) return SKR_OK;
     if (!d_acc || !d_out || total_rows <= 0) return skr::fail(SKR_ERR_ARG, "skr_col_finish: bad argument");
+    if (d_flag) SKR_CUDA_CHECK(cudaMemsetAsync(d_flag, 0, sizeof(int), (cudaStream_t)stream));
     col_finish_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_acc, cols, total_rows, take_sqrt,
-                                                                                      d_out);
+                                                                                      d_out, d_flag);
     SKR_LAUNCH_CHECK();
     return SKR_OK;
 }
@@ -239,11 +252,12 @@ extern "C" int skr_col_partial_f64(int kind, const float* d_a, int64_t m, int64_
 }
 
 extern "C" int skr_col_finish_f64(const double* d_acc, int64_t cols, int64_t total_rows, int take_sqrt, float* d_out,
-                                  void* stream) {
+                                  int* d_flag, void* stream) {
     if (cols <= 0) return SKR_OK;
     if (!d_acc || !d_out || total_rows <= 0) return skr::fail(SKR_ERR_ARG, "skr_col_finish_f64: bad argument");
+    if (d_flag) SKR_CUDA_CHECK(cudaMemsetAsync(d_flag, 0, sizeof(int), (cudaStream_t)stream));
     col_finish_f64_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_acc, cols, total_rows,
-                                                                                          take_sqrt, d_out);
+                                                                                          take_sqrt, d_out, d_flag);
     SKR_LAUNCH_CHECK();
     return SKR_OK;
 }

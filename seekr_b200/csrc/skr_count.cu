@@ -55,21 +55,14 @@ struct CountParams {
     uint32_t* colmin;
 };
 
-// Running per-column minimum of non-negative values (their float bits order like unsigned integers).
-// The cached read may be stale; a stale (larger) value only costs a redundant update.  Zero is the
-// floor of this path, so it is stored plainly (every writer writes the same value).
-__device__ __forceinline__ void colmin_update(uint32_t* colmin, int q, const float (&r)[4]) {
-    const uint4 cm = *reinterpret_cast<const uint4*>(colmin + 4 * q);
-    if ((cm.x | cm.y | cm.z | cm.w) == 0) return;  // the usual state once a few records have been seen
-    const uint32_t cur[4] = {cm.x, cm.y, cm.z, cm.w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const uint32_t b = __float_as_uint(r[e]);
-        if (b < cur[e]) {
-            if (b == 0) colmin[4 * q + e] = 0;
-            else atomicMin(&colmin[4 * q + e], b);
-        }
-    }
+// Column minima for the deferred Log2.post path.  Values on that path are >= 0 and almost every column
+// holds a zero somewhere, so the count kernels only remember, per thread, WHICH of its (at most 64)
+// columns has seen a zero (one 64-bit mask in registers, the thread -> column mapping is the same for
+// every record) and store 0 into colmin[] for those at the end.  Columns that never saw a zero keep
+// +inf and are scanned afterwards by colmin_scan_kernel.
+__device__ __forceinline__ void zero_note(unsigned long long& seen, int step, const uint32_t (&c4)[4]) {
+    const uint32_t m4 = (c4[0] == 0 ? 1u : 0u) | (c4[1] == 0 ? 2u : 0u) | (c4[2] == 0 ? 4u : 0u) | (c4[3] == 0 ? 8u : 0u);
+    seen |= (unsigned long long)m4 << (4 * step);
 }
 
 // shared-memory accesses by 32-bit shared-window address: the generic-pointer forms make the compiler
@@ -181,6 +174,8 @@ __global__ void __launch_bounds__(CountCfg<K>::kThreads) count_kernel(const Coun
     const int tid = threadIdx.x;
     float tmin = INFINITY;
     int tnan = 0;
+    unsigned long long zero_seen = 0;  // bit 4*step+e: column 4*(tid + step*T)+e held a zero count in some record
+    static_assert(Cfg::kBins / 4 <= 16 * T || true, "");
     uint32_t* spill = p.spill + (size_t)blockIdx.x * Cfg::kBins;
 
     for (;;) {
@@ -270,7 +265,7 @@ __global__ void __launch_bounds__(CountCfg<K>::kThreads) count_kernel(const Coun
             } else {
                 float r[4];
                 finish4<kVecF64>(c4, skr::smem_u32(s_tab), inc, p, q, r);
-                if (p.colmin) colmin_update(p.colmin, q, r);
+                if (p.colmin) zero_note(zero_seen, (q - tid) / T, c4);
                 if (p.min_cell) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) skr::min_update(r[e], tmin, tnan);
@@ -282,6 +277,12 @@ __global__ void __launch_bounds__(CountCfg<K>::kThreads) count_kernel(const Coun
     }
 
     if (p.min_cell) skr::min_commit<T>(tmin, tnan, s_wmin, s_wnan, p.min_cell);
+    if (p.colmin) {
+        for (int st = 0; st * T + tid < Cfg::kBins / 4; ++st)
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if ((zero_seen >> (4 * st + e)) & 1ull) p.colmin[4 * (tid + st * T) + e] = 0u;
+    }
 }
 
 
@@ -322,6 +323,7 @@ __global__ void __launch_bounds__(WarpCfg<K>::kThreads, WarpCfg<K>::kMinCtas) co
     const uint32_t hist_addr = skr::smem_u32(hist), tab_addr = skr::smem_u32(tab);
     float tmin = INFINITY;
     int tnan = 0;
+    unsigned long long zero_seen = 0;  // bit 4*step+e: column 4*(lane + step*TT)+e held a zero count in some record
 
     auto team_sync = [&]() {
         if constexpr (TT == 32) __syncwarp(); else __syncthreads();
@@ -397,7 +399,7 @@ __global__ void __launch_bounds__(WarpCfg<K>::kThreads, WarpCfg<K>::kMinCtas) co
                 const uint32_t c4[4] = {v.x & 0xFFFFu, v.x >> 16, v.y & 0xFFFFu, v.y >> 16};
                 float r[4];
                 finish4<kVecF64>(c4, tab_addr, inc, p, q, r);
-                if (p.colmin) colmin_update(p.colmin, q, r);
+                if (p.colmin) zero_note(zero_seen, (q - lane) / TT, c4);
                 if (p.min_cell) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) skr::min_update(r[e], tmin, tnan);
@@ -407,6 +409,12 @@ __global__ void __launch_bounds__(WarpCfg<K>::kThreads, WarpCfg<K>::kMinCtas) co
         }
         rec = share(mine_next);  // also separates this record's histogram reads from the next clearing
         if constexpr (TT == 32) __syncwarp();
+    }
+    if (p.colmin) {
+        for (int st = 0; st * TT + lane < Cfg::kBins / 4; ++st)
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if ((zero_seen >> (4 * st + e)) & 1ull) p.colmin[4 * (lane + st * TT) + e] = 0u;
     }
     if (p.min_cell) {
         if constexpr (TT == 32) {
@@ -661,6 +669,32 @@ int launch_ew(float* a, long long m, long long cols, long long ld, const void* v
     return SKR_OK;
 }
 
+// Columns whose minimum is still unknown (+inf: no record had a zero count there) are reduced over all
+// rows here: one warp per strip of 32 columns, coalesced 128-byte reads; strips without such a column exit
+// at once, which is the normal case for k >= 5 (every k-mer is absent from some transcript).
+__global__ void __launch_bounds__(256) colmin_scan_kernel(const float* __restrict__ a, long long m, long long cols,
+                                                          long long ld, long long rows_per_slab, uint32_t* colmin) {
+    const long long strip = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const long long col = strip * 32 + lane;
+    const bool need = col < cols && colmin[col] != 0u;  // +inf, or a minimum other slabs are still lowering
+    if (!__any_sync(0xFFFFFFFFu, need)) return;
+    const long long r0 = (long long)blockIdx.y * rows_per_slab, r1 = min(m, r0 + rows_per_slab);
+    uint32_t best = 0x7F800000u;
+    if (col < cols) {
+        long long r = r0;
+        for (; r + 8 <= r1; r += 8) {
+            uint32_t v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __float_as_uint(a[(r + u) * ld + col]);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) best = min(best, v[u]);
+        }
+        for (; r < r1; ++r) best = min(best, __float_as_uint(a[r * ld + col]));
+    }
+    if (need && best != 0x7F800000u) atomicMin(&colmin[col], best);
+}
+
 // min over columns of fl(fl(colmin_j - mean_j) / std_j): the matrix-wide minimum of the normalised values
 // when every std_j is positive and finite (rounded subtraction and division are monotone)
 template <bool kVecF64>
@@ -790,6 +824,19 @@ extern "C" int skr_count_colmin(const uint32_t* d_codes, const uint32_t* d_mask,
         case 7: return dispatch_count<7>(p, 0, 0, s);
         default: return dispatch_count<8>(p, 0, 0, s);
     }
+}
+
+extern "C" int skr_colmin_scan(const float* d_a, int64_t m, int64_t cols, int64_t ld, uint32_t* d_colmin, void* stream) {
+    if (m <= 0 || cols <= 0) return SKR_OK;
+    if (!d_a || !d_colmin) return skr::fail(SKR_ERR_ARG, "skr_colmin_scan: null argument");
+    const long long strips = (cols + 31) / 32;
+    const long long rows_per_slab = 1024;
+    long long slabs = (m + rows_per_slab - 1) / rows_per_slab;
+    if (slabs > 65535) return skr::fail(SKR_ERR_ARG, "skr_colmin_scan: too many rows");
+    dim3 grid((unsigned)((strips + 7) / 8), (unsigned)slabs);
+    colmin_scan_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_a, m, cols, ld, rows_per_slab, d_colmin);
+    SKR_LAUNCH_CHECK();
+    return SKR_OK;
 }
 
 extern "C" int skr_colmin_finish(const uint32_t* d_colmin, int64_t cols, const void* d_mean, const void* d_std,

@@ -72,11 +72,12 @@ class DeviceVector:
     on the device by ``check()``).  The deferred-normalisation path needs a finite mean and a finite,
     positive std (kmer_counts.CountEngine.run)."""
 
-    def __init__(self, tensor, is_f64, finite=None, positive=None):
+    def __init__(self, tensor, is_f64, finite=None, positive=None, flag=None):
         self.t = tensor
         self.is_f64 = is_f64
         self.finite = finite
         self.positive = positive
+        self.flag = flag  # device int written by skr_col_finish: bit 0 not finite, bit 1 not positive
 
     @classmethod
     def from_host(cls, value, cols):
@@ -194,10 +195,10 @@ class CountEngine:
                                    device.stream_ptr(self.stream))
         _lib.check(rc)
 
-    def col_finish(self, acc, rows, take_sqrt):
+    def col_finish(self, acc, rows, take_sqrt, flag=None):
         out = device.empty(acc.shape[0], self.torch.float32)
         _lib.check(self.lib.skr_col_finish(device.ptr(acc), acc.shape[0], rows, int(take_sqrt), device.ptr(out),
-                                           device.stream_ptr(self.stream)))
+                                           device.ptr(flag), device.stream_ptr(self.stream)))
         return out
 
     def sub_vec(self, a, vec, track_min=False):
@@ -273,9 +274,10 @@ class CountEngine:
             is_f64 = (mean_vec or std_vec).is_f64
             colmin = device.empty(self.cols, torch.int32)
             self.count_colmin(dpk, out, colmin)
+            sp = device.stream_ptr(self.stream)
+            _lib.check(self.lib.skr_colmin_scan(device.ptr(out), m, self.cols, out.stride(0), device.ptr(colmin), sp))
             if reducer:
                 reducer.colmin_allreduce(colmin)
-            sp = device.stream_ptr(self.stream)
             _lib.check(self.lib.skr_colmin_finish(device.ptr(colmin), self.cols, device.ptr(mean_vec.t if mean_vec else None),
                                                   device.ptr(std_vec.t if std_vec else None), int(is_f64),
                                                   device.ptr(self.min_cell.t), sp))
@@ -296,15 +298,18 @@ class CountEngine:
             # fused pass writes fl(fl(x - mean) / std) at the end
             self.count(dpk, out)
             stat = reducer.col_stat if reducer else self._local_col_stat
+            flags = device.empty(2, torch.int32)
             if mean is True:
-                mean_vec = DeviceVector(stat(self, _lib.COLPASS_SUM, out, None, None, "mean"), False)
+                mean_vec = DeviceVector(stat(self, _lib.COLPASS_SUM, out, None, None, "mean", flags[0:1]), False,
+                                        flag=flags[0:1])
             if std is True:
                 # np.std on what center() left behind: its own mean first (kmer_counts.py:169,174)
                 if mean_vec is not None:
                     arrmean = stat(self, _lib.COLPASS_CENTERED, out, mean_vec, None, "mean")
                 else:
                     arrmean = stat(self, _lib.COLPASS_SUM, out, None, None, "mean")
-                std_vec = DeviceVector(stat(self, _lib.COLPASS_SQDEV, out, mean_vec, arrmean, "std"), False)
+                std_vec = DeviceVector(stat(self, _lib.COLPASS_SQDEV, out, mean_vec, arrmean, "std", flags[1:2]), False,
+                                       flag=flags[1:2])
             self.normalize(out, mean_vec, std_vec, track_min=True)
             min_valid = True
         if need_min:
@@ -322,8 +327,12 @@ class CountEngine:
         if todo:
             flags = device.zeros(2, self.torch.int32)
             for i, v in enumerate(todo):
-                _lib.check(self.lib.skr_vec_check(device.ptr(v.t), int(v.is_f64), v.t.numel(),
-                                                  ctypes.c_void_p(flags.data_ptr() + 4 * i), device.stream_ptr(self.stream)))
+                dst = ctypes.c_void_p(flags.data_ptr() + 4 * i)
+                if v.flag is not None:   # written by skr_col_finish when the vector was made: just fetch it
+                    flags[i:i + 1].copy_(v.flag)
+                else:
+                    _lib.check(self.lib.skr_vec_check(device.ptr(v.t), int(v.is_f64), v.t.numel(), dst,
+                                                      device.stream_ptr(self.stream)))
             host = np.zeros(2, dtype=np.int32)
             device.d2h(host, flags, self.stream)
             device.sync(self.stream)
@@ -336,9 +345,9 @@ class CountEngine:
             return False
         return True
 
-    def _local_col_stat(self, engine, kind, a, vec, vec2, finish):
+    def _local_col_stat(self, engine, kind, a, vec, vec2, finish, flag=None):
         acc = self.col_sum(kind, a, vec, vec2)
-        return self.col_finish(acc, a.shape[0], take_sqrt=(finish == "std"))
+        return self.col_finish(acc, a.shape[0], take_sqrt=(finish == "std"), flag=flag)
 
     def nan_after_standardize(self):
         """True when the standardised matrix held a NaN (the reference's warning, kmer_counts.py:176)."""

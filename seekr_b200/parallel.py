@@ -108,7 +108,7 @@ class AllReduceStats(_Base):
     (scales with the number of GPUs; closer to the exact value than the reference's sequential
     fp32 sums, hence not bit-identical to them)."""
 
-    def col_stat(self, engine, kind, a, vec, vec2, finish):
+    def col_stat(self, engine, kind, a, vec, vec2, finish, flag=None):
         import torch
 
         from . import _lib, device
@@ -123,7 +123,7 @@ class AllReduceStats(_Base):
         rows = self.total_rows(m, a.device)
         out = torch.empty(cols, dtype=torch.float32, device=a.device)
         _lib.check(lib.skr_col_finish_f64(device.ptr(acc), cols, rows, int(finish == "std"), device.ptr(out),
-                                          device.stream_ptr(engine.stream)))
+                                          device.ptr(flag), device.stream_ptr(engine.stream)))
         return out
 
 
@@ -132,7 +132,7 @@ class ChainStats(_Base):
     rank r-1 (the shards are consecutive row ranges), the last rank finishes and broadcasts.
     Bit-identical to the single-GPU result and to numpy's axis-0 reduction; latency-bound."""
 
-    def col_stat(self, engine, kind, a, vec, vec2, finish):
+    def col_stat(self, engine, kind, a, vec, vec2, finish, flag=None):
         import torch
 
         m, cols = a.shape
@@ -145,8 +145,10 @@ class ChainStats(_Base):
             self.dist.send(acc, dst=self.rank + 1, group=self.group)
         rows = self.total_rows(m, a.device)
         if self.rank == self.world - 1:
-            out = engine.col_finish(acc, rows, take_sqrt=(finish == "std"))
+            out = engine.col_finish(acc, rows, take_sqrt=(finish == "std"), flag=flag)
         else:
             out = torch.empty(cols, dtype=torch.float32, device=a.device)
         self.dist.broadcast(out, src=self.world - 1, group=self.group)
+        if flag is not None:
+            self.dist.broadcast(flag, src=self.world - 1, group=self.group)
         return out

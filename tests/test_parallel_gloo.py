@@ -58,7 +58,7 @@ class FakeEngine:
                 y = (d * d).astype(np.float32)
             s += y
 
-    def col_finish(self, acc, rows, take_sqrt):
+    def col_finish(self, acc, rows, take_sqrt, flag=None):
         v = (acc.numpy().astype(np.float64) / rows).astype(np.float32)
         return torch.from_numpy(np.sqrt(v) if take_sqrt else v)
 
