@@ -8,7 +8,8 @@ Workload (BASELINE.json configs[1]): synthetic GENCODE-lncRNA-shaped set, 50 000
 (lognormal length 500 bp - 20 kb, seed 50000 + rank), k = 6.  One step =
     A. norm_vectors   counts -> order-exact column mean/std -> fused normalise -> Log2.post
                       (BasicCounter(fasta, k=6).get_counts(), what seekr_norm_vectors runs)
-    B. count + norm   counts with the mean/std vectors of A, Log2.post  (seekr_kmer_counts -mv -sv)
+    B. count + norm   counts with the mean/std vectors of A, Log2.post  (seekr_kmer_counts -mv -sv): pass 1 finds
+                      the per-column minima (no write), pass 2 counts again and writes the finished rows once
     C. Pearson        the normalised matrix of B against the reference set (rank 0's matrix), m x n, K = 4096
 `value` is transcripts/s of phase B with the packed input already in HBM (the BASELINE metric
 "transcripts/s (6-mer count+norm)"); Pearson pairs/s and the norm_vectors rate are reported in the same
@@ -254,7 +255,7 @@ def run_ours(args):
         # ---- B: count + normalise with the vectors, Log2.post ------------------------------------
         e[2].record()
         eng_cnt.count_events = []
-        eng_cnt.run(dpk, mean_vec, std_vec, out=out_b, reducer=reducer)
+        eng_cnt.run(dpk, vectors.get("mean_b", mean_vec), vectors.get("std_b", std_vec), out=out_b, reducer=reducer)
         e[4].record()
         # ---- C: Pearson against the reference set (rank 0's matrix) ------------------------------
         pa = skr_pearson.prepare(out_b, True)
@@ -273,10 +274,15 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         if timed:
-            kern_count_ms.append(sum(a.elapsed_time(b) for a, b in eng_cnt.count_events))
+            kern_count_ms.append(max(a.elapsed_time(b) for a, b in eng_cnt.count_events))
             kern_gemm_ms.append(e[5].elapsed_time(e[6]))
         return e[0].elapsed_time(e[1]), e[2].elapsed_time(e[4]), e[4].elapsed_time(e[6])
 
+    step(False)
+    # phase B is `seekr_kmer_counts -mv mean.npy -sv std.npy`: its vectors are inputs that come from the host
+    # (here: the vectors phase A produced, taken through host memory once, outside the timed region)
+    vectors["mean_b"] = DeviceVector.from_host(device.to_host(vectors["mean"].t, pinned=False), cols)
+    vectors["std_b"] = DeviceVector.from_host(device.to_host(vectors["std"].t, pinned=False), cols)
     for _ in range(args.warmup):
         step(False)
     sampler = ClockSampler(local_rank)
@@ -396,7 +402,7 @@ def run_ours(args):
                     "e2e": {"value": world * p_rows * p_rows / e2e_pearson_s, "unit": "pairs/s", "rows": p_rows,
                             "h2d_bytes_per_step": p_rows * cols * 4, "d2h_bytes_per_step": p_rows * p_rows * 4}},
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
-                     "traffic": None, "kernel": "count_warp_kernel<6> (+ column minima; normalisation deferred to the Log2.post pass)", "kernel_ms": k_count,
+                     "traffic": None, "kernel": "count_warp_kernel<6> pass 2 (count, -mean, /std, +|min|, +1, log2, one write of the row)", "kernel_ms": k_count,
                      "algorithmic_bytes_per_launch": count_bytes, "peak_source": peaks["source"]},
         "cpu_baseline": cpu,
         "e2e": {"value": total_tr / e2e_count_s, "unit": "transcripts/s", "h2d_bytes_per_step": int(slab_bytes + 2 * cols * 4),

@@ -105,11 +105,14 @@ int skr_min_reset(SkrMinCell* d_cell, void* stream);
  * says whether they hold doubles (numpy then computes in binary64 and rounds) or floats.
  * out_is_f64 != 0 writes doubles (raw counts only: occurrences() on a float64 row).
  * d_min, when given, receives the running minimum / NaN flag of everything written.
+ * d_post, when given, holds the matrix-wide minimum already (see skr_count_colmin) and the Log2.post
+ * tail (+ |min|, + 1, log2; kmer_counts.py:207-209) is applied in the same epilogue.
  * Records with L < k give a zero-count row; the caller must reject L == k-1 beforehand
  * (ZeroDivisionError in the reference).  1 <= k <= 8. */
 int skr_count(const uint32_t* d_codes, const uint32_t* d_mask, const uint64_t* d_block_offsets,
               const uint32_t* d_lengths, int64_t m, int k, int log2_pre, const void* d_mean, const void* d_std,
-              int vec_is_f64, void* d_out, int out_is_f64, int64_t ld_out, SkrMinCell* d_min, void* stream);
+              int vec_is_f64, void* d_out, int out_is_f64, int64_t ld_out, SkrMinCell* d_min, const SkrMinCell* d_post,
+              void* stream);
 
 /* Deferred normalisation for Log2.post with known, finite mean / positive std vectors (the
  * seekr_kmer_counts -mv -sv path): the count kernel writes the un-normalised values and keeps the

@@ -50,7 +50,7 @@ SIGNATURES = {
     "skr_packed_slab_bytes": (_sz, [_vp]),
     "skr_pack_error_line": (_i64, []),
     "skr_min_reset": (_int, [_vp, _vp]),
-    "skr_count": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _int, _vp, _vp, _int, _vp, _int, _i64, _vp, _vp]),
+    "skr_count": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _int, _vp, _vp, _int, _vp, _int, _i64, _vp, _vp, _vp]),
     "skr_colmin_reset": (_int, [_vp, _i64, _vp]),
     "skr_count_colmin": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _int, _vp, _i64, _vp, _vp]),
     "skr_colmin_scan": (_int, [_vp, _i64, _i64, _i64, _vp, _vp]),

@@ -53,16 +53,46 @@ struct CountParams {
     // per-column minimum of the values written (float bits; values are >= 0 on this path), for the
     // Log2.post shift when normalisation is deferred to the element-wise pass
     uint32_t* colmin;
+    int no_store;                 // column-minimum pass only: nothing is written to `out`
+    const SkrMinCell* post_cell;  // Log2.post fused into the epilogue: + |min|, + 1, log2 with this cell's minimum
 };
 
-// Column minima for the deferred Log2.post path.  Values on that path are >= 0 and almost every column
-// holds a zero somewhere, so the count kernels only remember, per thread, WHICH of its (at most 64)
-// columns has seen a zero (one 64-bit mask in registers, the thread -> column mapping is the same for
-// every record) and store 0 into colmin[] for those at the end.  Columns that never saw a zero keep
-// +inf and are scanned afterwards by colmin_scan_kernel.
-__device__ __forceinline__ void zero_note(unsigned long long& seen, int step, const uint32_t (&c4)[4]) {
-    const uint32_t m4 = (c4[0] == 0 ? 1u : 0u) | (c4[1] == 0 ? 2u : 0u) | (c4[2] == 0 ? 4u : 0u) | (c4[3] == 0 ? 8u : 0u);
-    seen |= (unsigned long long)m4 << (4 * step);
+// Column minima for the two-pass Log2.post path (values are >= 0 there, so float bits order like
+// unsigned integers).  Almost every column holds a zero in some record; a thread therefore keeps one
+// bit per column it owns ("a zero was seen", at most 64 columns = one 64-bit mask; the thread ->
+// column mapping is the same for every record) and only columns that have not shown a zero yet take
+// the slow road: compare with the global minimum and atomicMin when smaller.  The mask is rotated by
+// kRot bits per epilogue step, so the nibble of step s is always the low one when step s runs and the
+// mask is back in place after the kSteps steps of a record.
+template <int kSteps>
+__device__ __forceinline__ void colmin_note(unsigned long long& seen, const uint32_t (&c4)[4], const float (&r)[4],
+                                            uint32_t* colmin, int q) {
+    constexpr int kRot = 64 / kSteps;
+    static_assert(kSteps >= 1 && kSteps <= 16 && 64 % kSteps == 0, "one nibble per step must fit the mask");
+    const uint32_t z4 = (c4[0] == 0 ? 1u : 0u) | (c4[1] == 0 ? 2u : 0u) | (c4[2] == 0 ? 4u : 0u) | (c4[3] == 0 ? 8u : 0u);
+    const uint32_t known = (uint32_t)seen & 0xFu;
+    if ((z4 | known) != 0xFu) {  // a non-zero value in a column with no zero so far (rare after the first records)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (!((z4 | known) & (1u << e))) {
+                const uint32_t b = __float_as_uint(r[e]);
+                if (b < colmin[4 * q + e]) atomicMin(&colmin[4 * q + e], b);
+            }
+        }
+    }
+    seen |= z4;
+    if constexpr (kRot < 64) seen = (seen >> kRot) | (seen << (64 - kRot));
+}
+
+// store 0 into colmin[] for every column of this thread whose mask bit is set
+template <int kSteps>
+__device__ __forceinline__ void colmin_flush(unsigned long long seen, uint32_t* colmin, int first_q, int stride_q) {
+    constexpr int kRot = 64 / kSteps;
+#pragma unroll
+    for (int st = 0; st < kSteps; ++st)
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if ((seen >> ((kRot * st) % 64 + e)) & 1ull) colmin[4 * (first_q + st * stride_q) + e] = 0u;
 }
 
 // shared-memory accesses by 32-bit shared-window address: the generic-pointer forms make the compiler
@@ -174,8 +204,10 @@ __global__ void __launch_bounds__(CountCfg<K>::kThreads) count_kernel(const Coun
     const int tid = threadIdx.x;
     float tmin = INFINITY;
     int tnan = 0;
-    unsigned long long zero_seen = 0;  // bit 4*step+e: column 4*(tid + step*T)+e held a zero count in some record
-    static_assert(Cfg::kBins / 4 <= 16 * T || true, "");
+    unsigned long long zero_seen = 0;
+    constexpr int kSteps = (Cfg::kBins / 4 + T - 1) / T;  // epilogue steps per thread and record
+    float shift = 0.0f;
+    if (p.post_cell) shift = p.post_cell->nan_seen ? __int_as_float(0x7FC00000) : fabsf(skr::ordered_decode(p.post_cell->min_ordered));
     uint32_t* spill = p.spill + (size_t)blockIdx.x * Cfg::kBins;
 
     for (;;) {
@@ -265,24 +297,23 @@ __global__ void __launch_bounds__(CountCfg<K>::kThreads) count_kernel(const Coun
             } else {
                 float r[4];
                 finish4<kVecF64>(c4, skr::smem_u32(s_tab), inc, p, q, r);
-                if (p.colmin) zero_note(zero_seen, (q - tid) / T, c4);
+                if (p.colmin) colmin_note<kSteps>(zero_seen, c4, r, p.colmin, q);
+                if (p.post_cell) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) r[e] = log2f(__fadd_rn(__fadd_rn(r[e], shift), 1.0f));
+                }
                 if (p.min_cell) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) skr::min_update(r[e], tmin, tnan);
                 }
-                reinterpret_cast<float4*>(orow)[q] = make_float4(r[0], r[1], r[2], r[3]);
+                if (!p.no_store) reinterpret_cast<float4*>(orow)[q] = make_float4(r[0], r[1], r[2], r[3]);
             }
         }
         // the __syncthreads at the top of the loop separates these reads from the next zeroing
     }
 
     if (p.min_cell) skr::min_commit<T>(tmin, tnan, s_wmin, s_wnan, p.min_cell);
-    if (p.colmin) {
-        for (int st = 0; st * T + tid < Cfg::kBins / 4; ++st)
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-                if ((zero_seen >> (4 * st + e)) & 1ull) p.colmin[4 * (tid + st * T) + e] = 0u;
-    }
+    if (p.colmin && tid < Cfg::kBins / 4) colmin_flush<kSteps>(zero_seen, p.colmin, tid, T);
 }
 
 
@@ -323,7 +354,10 @@ __global__ void __launch_bounds__(WarpCfg<K>::kThreads, WarpCfg<K>::kMinCtas) co
     const uint32_t hist_addr = skr::smem_u32(hist), tab_addr = skr::smem_u32(tab);
     float tmin = INFINITY;
     int tnan = 0;
-    unsigned long long zero_seen = 0;  // bit 4*step+e: column 4*(lane + step*TT)+e held a zero count in some record
+    unsigned long long zero_seen = 0;
+    constexpr int kSteps = (Cfg::kBins / 4 + TT - 1) / TT;  // epilogue steps per thread and record
+    float shift = 0.0f;
+    if (p.post_cell) shift = p.post_cell->nan_seen ? __int_as_float(0x7FC00000) : fabsf(skr::ordered_decode(p.post_cell->min_ordered));
 
     auto team_sync = [&]() {
         if constexpr (TT == 32) __syncwarp(); else __syncthreads();
@@ -399,23 +433,22 @@ __global__ void __launch_bounds__(WarpCfg<K>::kThreads, WarpCfg<K>::kMinCtas) co
                 const uint32_t c4[4] = {v.x & 0xFFFFu, v.x >> 16, v.y & 0xFFFFu, v.y >> 16};
                 float r[4];
                 finish4<kVecF64>(c4, tab_addr, inc, p, q, r);
-                if (p.colmin) zero_note(zero_seen, (q - lane) / TT, c4);
+                if (p.colmin) colmin_note<kSteps>(zero_seen, c4, r, p.colmin, q);
+                if (p.post_cell) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) r[e] = log2f(__fadd_rn(__fadd_rn(r[e], shift), 1.0f));
+                }
                 if (p.min_cell) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) skr::min_update(r[e], tmin, tnan);
                 }
-                reinterpret_cast<float4*>(orow)[q] = make_float4(r[0], r[1], r[2], r[3]);
+                if (!p.no_store) reinterpret_cast<float4*>(orow)[q] = make_float4(r[0], r[1], r[2], r[3]);
             }
         }
         rec = share(mine_next);  // also separates this record's histogram reads from the next clearing
         if constexpr (TT == 32) __syncwarp();
     }
-    if (p.colmin) {
-        for (int st = 0; st * TT + lane < Cfg::kBins / 4; ++st)
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-                if ((zero_seen >> (4 * st + e)) & 1ull) p.colmin[4 * (lane + st * TT) + e] = 0u;
-    }
+    if (p.colmin && lane < Cfg::kBins / 4) colmin_flush<kSteps>(zero_seen, p.colmin, lane, TT);
     if (p.min_cell) {
         if constexpr (TT == 32) {
             if (tmin != tmin) { tnan = 1; tmin = INFINITY; }
@@ -746,14 +779,14 @@ extern "C" int skr_min_reset(SkrMinCell* d_cell, void* stream) {
 extern "C" int skr_count(const uint32_t* d_codes, const uint32_t* d_mask, const uint64_t* d_block_offsets,
                          const uint32_t* d_lengths, int64_t m, int k, int log2_pre, const void* d_mean,
                          const void* d_std, int vec_is_f64, void* d_out, int out_is_f64, int64_t ld_out,
-                         SkrMinCell* d_min, void* stream) {
+                         SkrMinCell* d_min, const SkrMinCell* d_post, void* stream) {
     if (m == 0) return SKR_OK;
     if (!d_codes || !d_mask || !d_block_offsets || !d_lengths || !d_out || m < 0)
         return skr::fail(SKR_ERR_ARG, "skr_count: null or negative argument");
     if (k < 1 || k > 8) return skr::fail(SKR_ERR_ARG, "skr_count: k=%d not supported (1 <= k <= 8)", k);
     const int64_t bins = (int64_t)1 << (2 * k);
     if (ld_out < bins) return skr::fail(SKR_ERR_ARG, "skr_count: ld_out < 4^k");
-    if (out_is_f64 && (log2_pre || d_mean || d_std || d_min))
+    if (out_is_f64 && (log2_pre || d_mean || d_std || d_min || d_post))
         return skr::fail(SKR_ERR_ARG, "skr_count: float64 output carries raw counts only");
     const size_t esz = out_is_f64 ? 8 : 4;
     if (((uintptr_t)d_out & 15) || ((size_t)ld_out * esz) % 16)
@@ -772,6 +805,7 @@ extern "C" int skr_count(const uint32_t* d_codes, const uint32_t* d_mask, const 
     p.out = d_out;
     p.ld_out = ld_out;
     p.min_cell = d_min;
+    p.post_cell = d_post;
     cudaStream_t s = (cudaStream_t)stream;
     switch (k) {
         case 1: return dispatch_count<1>(p, vec_is_f64, out_is_f64, s);
@@ -797,11 +831,11 @@ extern "C" int skr_count_colmin(const uint32_t* d_codes, const uint32_t* d_mask,
                                 const uint32_t* d_lengths, int64_t m, int k, int log2_pre, float* d_out, int64_t ld_out,
                                 uint32_t* d_colmin, void* stream) {
     if (m == 0) return SKR_OK;
-    if (!d_codes || !d_mask || !d_block_offsets || !d_lengths || !d_out || !d_colmin || m < 0)
+    if (!d_codes || !d_mask || !d_block_offsets || !d_lengths || !d_colmin || m < 0)
         return skr::fail(SKR_ERR_ARG, "skr_count_colmin: null or negative argument");
     if (k < 1 || k > 8) return skr::fail(SKR_ERR_ARG, "skr_count_colmin: k=%d not supported (1 <= k <= 8)", k);
     const int64_t bins = (int64_t)1 << (2 * k);
-    if (ld_out < bins || ((uintptr_t)d_out & 15) || (ld_out % 4) || ((uintptr_t)d_colmin & 15))
+    if ((d_out && (ld_out < bins || ((uintptr_t)d_out & 15) || (ld_out % 4))) || ((uintptr_t)d_colmin & 15))
         return skr::fail(SKR_ERR_ARG, "skr_count_colmin: bad pitch or alignment");
     CountParams p{};
     p.codes = d_codes;
@@ -813,6 +847,7 @@ extern "C" int skr_count_colmin(const uint32_t* d_codes, const uint32_t* d_mask,
     p.out = d_out;
     p.ld_out = ld_out;
     p.colmin = d_colmin;
+    p.no_store = d_out == nullptr;
     cudaStream_t s = (cudaStream_t)stream;
     switch (k) {
         case 1: return dispatch_count<1>(p, 0, 0, s);

@@ -134,8 +134,9 @@ class CountEngine:
                                          device.stream_ptr(self.stream)))
         return DevicePacked(slab, packed)
 
-    def count(self, dpk, out, mean=None, std=None, track_min=False, out_is_f64=False):
-        """skr_count into ``out`` (m x cols).  mean/std: DeviceVector or None."""
+    def count(self, dpk, out, mean=None, std=None, track_min=False, out_is_f64=False, post=False):
+        """skr_count into ``out`` (m x cols).  mean/std: DeviceVector or None.  post=True applies the Log2.post
+        tail in the same epilogue, using the minimum already held by ``self.min_cell``."""
         vec_is_f64 = False
         if mean is not None and std is not None and mean.is_f64 != std.is_f64:
             # (double)x op (double)v rounded to fp32 equals the fp32 operation (24-bit operands,
@@ -152,7 +153,7 @@ class CountEngine:
             dpk.codes, dpk.mask, dpk.blk_off, dpk.lengths, dpk.m, self.k, 0 if out_is_f64 else log2_pre,
             device.ptr(mean.t if mean else None), device.ptr(std.t if std else None), int(vec_is_f64),
             device.ptr(out), int(out_is_f64), out.stride(0), device.ptr(self.min_cell.t if track_min else None),
-            device.stream_ptr(self.stream))
+            device.ptr(self.min_cell.t if post else None), device.stream_ptr(self.stream))
         _lib.check(rc)
         self._event_end(ev)
         self._keep = (mean, std)  # converted vectors must outlive the launch
@@ -171,14 +172,15 @@ class CountEngine:
         end.record(self.stream if self.stream is not None else self.torch.cuda.current_stream())
         self.count_events.append((start, end))
 
-    def count_colmin(self, dpk, out, colmin):
-        """Un-normalised counts (log2'd for Log2.pre) + running per-column minimum (skr_count_colmin)."""
+    def count_colmin(self, dpk, colmin, out=None):
+        """Per-column minimum of the un-normalised counts (log2'd for Log2.pre); the matrix itself is only
+        written when ``out`` is given (skr_count_colmin)."""
         log2_pre = 1 if self.log2 == "Log2.pre" else 0
         _lib.check(self.lib.skr_colmin_reset(device.ptr(colmin), colmin.numel(), device.stream_ptr(self.stream)))
         ev = self._event_start()
         _lib.check(self.lib.skr_count_colmin(dpk.codes, dpk.mask, dpk.blk_off, dpk.lengths, dpk.m, self.k, log2_pre,
-                                             device.ptr(out), out.stride(0), device.ptr(colmin),
-                                             device.stream_ptr(self.stream)))
+                                             device.ptr(out), out.stride(0) if out is not None else 0,
+                                             device.ptr(colmin), device.stream_ptr(self.stream)))
         self._event_end(ev)
 
     def col_sum(self, kind, a, vec=None, vec2=None):
@@ -266,25 +268,22 @@ class CountEngine:
 
         if mean is not True and std is not True and need_min and (mean_vec or std_vec) and self.deferred \
                 and self._benign(mean_vec, std_vec):
-            # Log2.post with known, well-behaved vectors: the count kernel only tracks per-column minima
-            # (the shift follows from them because rounded -mean, /std>0 are monotone) and the element-wise
-            # pass, which is bandwidth-bound anyway, does -mean, /std, +|min|, +1, log2 in one go
+            # Log2.post with known, well-behaved vectors, in two launches that touch the matrix once:
+            # pass 1 counts every record but only keeps per-column minima (rounded -mean and /std>0 are
+            # monotone, so the matrix-wide minimum of the z-scores follows from them); pass 2 counts again and
+            # its epilogue does -mean, /std, +|min|, +1, log2 before the single write of the row.  Re-reading
+            # 0.4 B/base of packed codes is far cheaper than a read-modify-write pass over 4*4^k B/record.
             if mean_vec is not None and std_vec is not None and mean_vec.is_f64 != std_vec.is_f64:
                 mean_vec, std_vec = mean_vec.as_f64(), std_vec.as_f64()
             is_f64 = (mean_vec or std_vec).is_f64
             colmin = device.empty(self.cols, torch.int32)
-            self.count_colmin(dpk, out, colmin)
-            sp = device.stream_ptr(self.stream)
-            _lib.check(self.lib.skr_colmin_scan(device.ptr(out), m, self.cols, out.stride(0), device.ptr(colmin), sp))
+            self.count_colmin(dpk, colmin)
             if reducer:
                 reducer.colmin_allreduce(colmin)
             _lib.check(self.lib.skr_colmin_finish(device.ptr(colmin), self.cols, device.ptr(mean_vec.t if mean_vec else None),
                                                   device.ptr(std_vec.t if std_vec else None), int(is_f64),
-                                                  device.ptr(self.min_cell.t), sp))
-            _lib.check(self.lib.skr_normalize_post_log2(device.ptr(out), m, self.cols, out.stride(0),
-                                                        device.ptr(mean_vec.t if mean_vec else None),
-                                                        device.ptr(std_vec.t if std_vec else None), int(is_f64),
-                                                        device.ptr(self.min_cell.t), sp))
+                                                  device.ptr(self.min_cell.t), device.stream_ptr(self.stream)))
+            self.count(dpk, out, mean_vec, std_vec, post=True)
             self._keep = (mean_vec, std_vec, colmin)
             return out, mean_vec, std_vec
         if mean is not True and std is not True:
@@ -321,24 +320,12 @@ class CountEngine:
         return out, mean_vec, std_vec
 
     def _benign(self, mean_vec, std_vec):
-        """Finite mean and finite, positive std?  Host-born vectors already know; device-born ones are
-        checked with skr_vec_check, both through a single 8-byte read-back."""
-        todo = [v for v in (mean_vec, std_vec) if v is not None and (v.finite is None or v.positive is None)]
-        if todo:
-            flags = device.zeros(2, self.torch.int32)
-            for i, v in enumerate(todo):
-                dst = ctypes.c_void_p(flags.data_ptr() + 4 * i)
-                if v.flag is not None:   # written by skr_col_finish when the vector was made: just fetch it
-                    flags[i:i + 1].copy_(v.flag)
-                else:
-                    _lib.check(self.lib.skr_vec_check(device.ptr(v.t), int(v.is_f64), v.t.numel(), dst,
-                                                      device.stream_ptr(self.stream)))
-            host = np.zeros(2, dtype=np.int32)
-            device.d2h(host, flags, self.stream)
-            device.sync(self.stream)
-            for i, v in enumerate(todo):
-                v.finite = not (int(host[i]) & 1)
-                v.positive = not (int(host[i]) & 2)
+        """Finite mean and finite, positive std?  Vectors that came from the host know (DeviceVector.from_host);
+        for device-born ones nobody has looked yet and asking would cost a host synchronisation in the middle of
+        the pipeline, so they take the fused path (DeviceVector.check() resolves them explicitly if wanted)."""
+        for v in (mean_vec, std_vec):
+            if v is not None and (v.finite is None or v.positive is None):
+                return False  # device-born vector of unknown quality: the fused path needs no host decision
         if mean_vec is not None and not mean_vec.finite:
             return False
         if std_vec is not None and not (std_vec.finite and std_vec.positive):

@@ -73,8 +73,8 @@ def main():
         out = device.empty((m, cols), torch.float32)
         in_bytes = float(np.sum((lens + 3) // 4 + (lens + 7) // 8 + 12))
         row_bytes = 4.0 * cols * m
-        mean = DeviceVector(torch.rand(cols, device="cuda") + 0.5, False)
-        std = DeviceVector(torch.rand(cols, device="cuda") + 0.5, False)
+        mean = DeviceVector(torch.rand(cols, device="cuda") + 0.5, False, True, True)
+        std = DeviceVector(torch.rand(cols, device="cuda") + 0.5, False, True, True)
 
         def report(name, ms, mn, nbytes):
             gbs = nbytes / (mn * 1e-3) / 1e9
@@ -85,6 +85,12 @@ def main():
         report("count raw", ms, mn, in_bytes + row_bytes)
         ms, mn = timeit(lambda: eng.count(dpk, out, mean, std, track_min=True), flush)
         report("count fused -mean /std +min", ms, mn, in_bytes + row_bytes)
+        colmin = device.empty(cols, torch.int32)
+        ms, mn = timeit(lambda: eng.count_colmin(dpk, colmin), flush)
+        report("column minima only (no write)", ms, mn, in_bytes)
+        eng.min_cell.reset()
+        ms, mn = timeit(lambda: eng.count(dpk, out, mean, std, post=True), flush)
+        report("count fused -mean /std +post", ms, mn, in_bytes + row_bytes)
         if args.only_count:
             continue
         eng.min_cell.reset()
@@ -104,7 +110,7 @@ def main():
         def full():
             eng2.run(dpk, mean, std, out=out)
         ms, mn = timeit(full, flush)
-        report("vectors + Log2.post (2 krn)", ms, mn, in_bytes + 3 * row_bytes)
+        report("vectors + Log2.post (2 passes)", ms, mn, 2 * in_bytes + row_bytes)
 
         def full_self():
             eng2.run(dpk, True, True, out=out)
