@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -540,6 +541,8 @@ int launch_count(CountParams p, cudaStream_t stream) {
         using W = WarpCfg<K>;
         auto wkern = count_warp_kernel<K, kVecF64>;
         SKR_CUDA_CHECK(cudaFuncSetAttribute(wkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W::kSmem));
+        if (const char* env = getenv("SEEKR_B200_COUNT_CARVEOUT"))  // experiment knob: % of the SM's 228 KB given to smem
+            SKR_CUDA_CHECK(cudaFuncSetAttribute(wkern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(env)));
         int wper_sm = 0;
         SKR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wper_sm, wkern, W::kThreads, W::kSmem));
         if (wper_sm < 1) return skr::fail(SKR_ERR_CUDA, "warp count kernel for k=%d does not fit on this device", K);

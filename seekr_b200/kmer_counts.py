@@ -123,7 +123,9 @@ class CountEngine:
         self.stream = stream
         self.min_cell = device.MinCell()
         self.count_events = None  # set to a list to collect (start, end) CUDA events around every count launch
-        self.deferred = True      # allow the deferred-normalisation path for Log2.post with known vectors
+        # two-pass Log2.post (column minima first, then count + normalise + post in one epilogue): measured
+        # equal to fused count + post pass on B200 (both ~0.6 ms for 50k transcripts, instruction-bound), so off
+        self.deferred = False
 
     # -- building blocks ------------------------------------------------------------------------
     def upload(self, packed):
