@@ -505,28 +505,49 @@ pearson_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
 // reads and writes; ~2 passes over half the matrix at HBM speed).
 template <typename T>
 __global__ void __launch_bounds__(256) mirror_lower_kernel(T* __restrict__ c, long long n, long long ldc, int tiles) {
-    __shared__ T tile[32][33];
-    // blockIdx.x enumerates strictly-lower tile pairs (tm > tn), blockIdx.y the 64 sub-blocks of a tile
+    // 64 x 64 blocks: 16 sub-blocks per 256 x 256 tile; 128-bit reads and writes when the block is interior
+    __shared__ T tile[64][65];
     long long t = blockIdx.x;
     int tm = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5) + 1;  // t = tm(tm-1)/2 + tn, tn < tm
     while ((long long)tm * (tm - 1) / 2 > t) --tm;
     while ((long long)(tm + 1) * tm / 2 <= t) ++tm;
     const int tn = (int)(t - (long long)tm * (tm - 1) / 2);
     if (tm >= tiles) return;
-    const int sb_r = blockIdx.y >> 3, sb_c = blockIdx.y & 7;  // sub-block of the destination tile
-    const long long dr0 = (long long)tm * kBN + sb_r * 32, dc0 = (long long)tn * kBN + sb_c * 32;  // destination origin
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    // source block = C[dc0 .. dc0+31][dr0 .. dr0+31]
+    const int sb_r = blockIdx.y >> 2, sb_c = blockIdx.y & 3;  // sub-block of the destination tile
+    const long long dr0 = (long long)tm * kBN + sb_r * 64, dc0 = (long long)tn * kBN + sb_c * 64;  // destination origin
+    constexpr int V = 16 / sizeof(T);       // elements per 128-bit access
+    constexpr int TX = 64 / V;              // threads across a 64-wide row
+    constexpr int TY = 256 / TX;            // rows per sweep
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    const bool interior = dr0 + 64 <= n && dc0 + 64 <= n && (ldc % V) == 0;
+    // source block = C[dc0 .. dc0+63][dr0 .. dr0+63]
+    if (interior) {
+        for (int i = ty; i < 64; i += TY) {
+            const float4 v = *reinterpret_cast<const float4*>(c + (dc0 + i) * ldc + dr0 + tx * V);
+            const T* e = reinterpret_cast<const T*>(&v);
 #pragma unroll
-    for (int i = ty; i < 32; i += 8) {
-        const long long sr = dc0 + i, sc = dr0 + tx;
-        if (sr < n && sc < n) tile[i][tx] = c[sr * ldc + sc];
-    }
-    __syncthreads();
+            for (int j = 0; j < V; ++j) tile[i][tx * V + j] = e[j];
+        }
+        __syncthreads();
+        for (int i = ty; i < 64; i += TY) {
+            float4 v;
+            T* e = reinterpret_cast<T*>(&v);
 #pragma unroll
-    for (int i = ty; i < 32; i += 8) {
-        const long long r = dr0 + i, cc = dc0 + tx;
-        if (r < n && cc < n) c[r * ldc + cc] = tile[tx][i];
+            for (int j = 0; j < V; ++j) e[j] = tile[tx * V + j][i];
+            *reinterpret_cast<float4*>(c + (dr0 + i) * ldc + dc0 + tx * V) = v;
+        }
+    } else {
+        for (int i = threadIdx.x / 64; i < 64; i += 4) {
+            const int j = threadIdx.x % 64;
+            const long long sr = dc0 + i, sc = dr0 + j;
+            if (sr < n && sc < n) tile[i][j] = c[sr * ldc + sc];
+        }
+        __syncthreads();
+        for (int i = threadIdx.x / 64; i < 64; i += 4) {
+            const int j = threadIdx.x % 64;
+            const long long r = dr0 + i, cc = dc0 + j;
+            if (r < n && cc < n) c[r * ldc + cc] = tile[j][i];
+        }
     }
 }
 
@@ -561,7 +582,7 @@ int launch_gemm(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtens
     SKR_LAUNCH_CHECK();
     if (p.symmetric && p.tiles_m > 1) {
         const long long pairs = (long long)p.tiles_m * (p.tiles_m - 1) / 2;
-        dim3 grid((unsigned)pairs, 64);
+        dim3 grid((unsigned)pairs, 16);
         if (p.c_is_f64) mirror_lower_kernel<double><<<grid, 256, 0, stream>>>((double*)p.c, p.n, p.ldc, p.tiles_m);
         else mirror_lower_kernel<float><<<grid, 256, 0, stream>>>((float*)p.c, p.n, p.ldc, p.tiles_m);
         SKR_LAUNCH_CHECK();
