@@ -48,6 +48,18 @@ def measured_peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def ncu_traffic(key, applicable):
+    """DRAM bytes per launch of the dominant kernels, from the committed ncu captures (profiles/ncu_traffic.json);
+    None when the run is not the captured workload."""
+    if not applicable:
+        return None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as handle:
+            return json.load(handle)[key]["bytes"]
+    except Exception:
+        return None
+
+
 def algorithmic_bytes(lengths, k, log2_post):
     """SURVEY 8(d): per transcript ceil(L/4) codes + ceil(L/8) mask + 12 (offset, length) + 4*4^k output row;
     the Log2.post pass adds a read and a write of the row."""
@@ -56,6 +68,16 @@ def algorithmic_bytes(lengths, k, log2_post):
     count = float(per.sum())
     post = float(2 * 4 * 4 ** k * lengths.size) if log2_post else 0.0
     return count, post
+
+
+def make_config(m, world, mean_length, n_ref):
+    cols = 4 ** K_MER
+    return {"workload": "configs[1]: synthetic lncRNA-shaped set, k=6: norm_vectors + counts (mean/std vectors, Log2.post) "
+                        "+ Pearson vs the reference set", "records_per_gpu": m, "k": K_MER,
+            "mean_length": mean_length, "pearson_m_per_gpu": m, "pearson_n": n_ref, "pearson_K": cols,
+            "sharding": "records per rank (counting), output row blocks per rank (Pearson)",
+            "column_stats": "order-exact (bit-identical to numpy)" if world == 1 else "binary64 partials + one all-reduce",
+            "l2": "flushed between steps (256 MiB write)"}
 
 
 class ClockSampler:
@@ -172,8 +194,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "transcripts/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(times)) * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 chain -> f32", "data": "synthetic",
-        "config": {"workload": "synthetic lncRNA-shaped transcripts, k=6, count + normalise with mean/std vectors, Log2.post",
-                   "records": sample, "k": K_MER},
+        "config": dict(make_config(args.records, max(1, args.gpus), float(np.diff(offs).mean()),
+                                   args.pearson_n if args.pearson_n else args.records),
+                       cpu_sample_records=sample, cpu_path="count + normalise with vectors + Log2.post from letters "
+                       "already in memory (no FASTA parsing, which favours this arm)"),
         "cpu_baseline": {"value": value, "unit": "transcripts/s", "cores": cores, "kind": "port",
                          "sample": "%d of the %d transcripts per step, C restatement of the reference (oracle/skr_oracle.c), "
                                    "OpenMP over records; the reference itself is single-threaded Python" % (sample, args.records)},
@@ -381,19 +405,15 @@ def run_ours(args):
         "vs_baseline": None,
         "dtype": "u16 counts -> f64 per-kb chain -> f32 (counting); f16 hi/lo split x3 MMAs -> f32 (Pearson)",
         "data": "synthetic",
-        "config": {"workload": "configs[1]: synthetic lncRNA-shaped set, k=6: norm_vectors + counts (mean/std vectors, Log2.post) "
-                               "+ Pearson vs the reference set", "records_per_gpu": m, "k": K_MER,
-                   "mean_length": float(lengths.mean()), "pearson_m_per_gpu": m, "pearson_n": n_ref, "pearson_K": cols,
-                   "sharding": "records per rank (counting), output row blocks per rank (Pearson)",
-                   "column_stats": "order-exact (bit-identical to numpy)" if world == 1 else "binary64 partials + one all-reduce",
-                   "l2": "flushed between steps (256 MiB write)"},
+        "config": make_config(m, world, float(lengths.mean()), n_ref),
         "phases_ms": {"norm_vectors": t_a, "count_norm": t_b, "pearson": t_c},
         "norm_vectors": {"value": total_tr / (t_a * 1e-3), "unit": "transcripts/s"},
         "pearson": {"metric": "Pearson pairs/s", "value": world * m * n_ref / (t_c * 1e-3), "unit": "pairs/s",
                     "gemm_kernel_ms": k_gemm,
                     "symmetric": bool(world == 1 and n_ref == m),
                     "roofline": {"bound": "tensor", "achieved": gemm_tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                                 "frac": gemm_tf / peaks["bf16_tflops_sustained"], "traffic": None,
+                                 "frac": gemm_tf / peaks["bf16_tflops_sustained"],
+                                 "traffic": ncu_traffic("pearson_gemm_kernel", world == 1 and m == 50000 and n_ref == m),
                                  "executed_tflops": exec_ratio * gemm_tf, "executed_frac": exec_ratio * gemm_tf / peaks["bf16_tflops_sustained"],
                                  "note": "achieved = algorithmic 2*m*n*K / GEMM kernel time; 3 fp16 MMAs are executed per "
                                          "computed product (hi*hi + hi*lo + lo*hi); self-vs-self computes the tiles on and "
@@ -402,7 +422,7 @@ def run_ours(args):
                     "e2e": {"value": world * p_rows * p_rows / e2e_pearson_s, "unit": "pairs/s", "rows": p_rows,
                             "h2d_bytes_per_step": p_rows * cols * 4, "d2h_bytes_per_step": p_rows * p_rows * 4}},
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
-                     "traffic": None, "kernel": "count_warp_kernel<6> (count + per-kb chain + -mean + /std + running min, one write of the row)", "kernel_ms": k_count,
+                     "traffic": ncu_traffic("count_kernel", m == 50000), "kernel": "count_warp_kernel<6> (count + per-kb chain + -mean + /std + running min, one write of the row)", "kernel_ms": k_count,
                      "algorithmic_bytes_per_launch": count_bytes, "peak_source": peaks["source"]},
         "cpu_baseline": cpu,
         "e2e": {"value": total_tr / e2e_count_s, "unit": "transcripts/s", "h2d_bytes_per_step": int(slab_bytes + 2 * cols * 4),
