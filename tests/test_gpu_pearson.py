@@ -129,3 +129,25 @@ def test_symmetric_path_equals_general_path(m, K):
     assert np.abs(sym - gen).max() < 2e-6
     assert np.abs(sym - sym.T).max() < 2e-6
     assert np.abs(sym - po.pearson_f64(a, a)).max() < TOL
+
+
+def test_pearson_streams_row_blocks(monkeypatch):
+    """Outputs larger than the staging budget are produced in row blocks (double-buffered D2H)."""
+    import seekr_b200.pearson as mod
+
+    monkeypatch.setattr(mod, "_BLOCK_BYTES", 300 * 777 * 4 // 3)     # forces ~4 blocks of 128 rows
+    rng = np.random.default_rng(21)
+    a = rng.standard_normal((300, 512)).astype(np.float32)
+    b = rng.standard_normal((777, 512)).astype(np.float32)
+    got = pearson(a, b)
+    assert np.abs(got - po.pearson_f64(a, b)).max() < TOL
+
+
+def test_pearson_k7_columns():
+    """BASELINE config 5 shape in miniature: K = 4^7 = 16 384 columns, query vs reference."""
+    rng = np.random.default_rng(22)
+    q = (rng.poisson(0.3, size=(384, 16384)) * rng.uniform(0.1, 3, size=(384, 1))).astype(np.float32)
+    r = (rng.poisson(0.3, size=(200, 16384)) * rng.uniform(0.1, 3, size=(200, 1))).astype(np.float32)
+    got = pearson(q, r)
+    assert got.shape == (384, 200)
+    assert np.abs(got - po.pearson_f64(q, r)).max() < TOL
