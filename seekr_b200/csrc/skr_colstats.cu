@@ -94,26 +94,15 @@ __global__ void __launch_bounds__(64) col_pass_kernel(const __grid_constant__ CU
         const uint32_t ph = (uint32_t)((t / kStages) & 1);
         skr::mbar_wait(&full_bar[s], ph);
         const int rows = (int)min((long long)kTileRows, m - t * kTileRows);
-        // the adds form one dependent fp32 chain (4 cycles each); the shared loads of the next 8 rows are
-        // issued before the current 8 adds so their ~30-cycle latency hides behind the chain
+        // (issuing the next batch's shared loads ahead of the current adds was tried: 1.5-2x slower, the
+        // extra register moves sit on the dependent chain; the 8-load / 8-add batches below are the fast form)
         int r = 0;
-        float x[8], nx[8];
-        if (rows >= 8) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) x[u] = tiles[s][u][lane];
-        }
         for (; r + 8 <= rows; r += 8) {
-            const bool more = r + 16 <= rows;
-            if (more) {
+            float x[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) nx[u] = tiles[s][r + 8 + u][lane];
-            }
+            for (int u = 0; u < 8; ++u) x[u] = tiles[s][r + u][lane];
 #pragma unroll
             for (int u = 0; u < 8; ++u) step(x[u]);
-            if (more) {
-#pragma unroll
-                for (int u = 0; u < 8; ++u) x[u] = nx[u];
-            }
         }
         for (; r < rows; ++r) step(tiles[s][r][lane]);
         __syncwarp();
