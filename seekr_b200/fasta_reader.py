@@ -39,6 +39,16 @@ def alphabet_lut(alphabet="AGTC"):
     return lut
 
 
+def default_pack_threads():
+    """Host threads for the packer: all cores, divided among the ranks of a torchrun launch on this node."""
+    cores = os.cpu_count() or 1
+    try:
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
+    except ValueError:
+        local_world = 1
+    return max(1, min(64, cores // max(1, local_world)))
+
+
 class PackedFasta:
     """Owner of one SkrPacked handle plus the source text it was parsed from."""
 
@@ -72,6 +82,8 @@ class PackedFasta:
     def from_buffer(cls, text, alphabet="AGTC", pinned=False, nthreads=0, _lut=None, _lib_=None):
         lib = _lib_ or _lib.load()
         lut = _lut if _lut is not None else alphabet_lut(alphabet)
+        if nthreads <= 0 and len(text) > (1 << 22):
+            nthreads = default_pack_threads()
         n = len(text)
         if n:
             view = np.frombuffer(text, dtype=np.uint8)

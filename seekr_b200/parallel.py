@@ -57,15 +57,16 @@ def decode_min(u):
 
 
 def allreduce_min_cell(cell_i64, group=None):
-    """cell_i64: int64 tensor [min_ordered, nan_seen] on the communicator's device; reduced in place."""
+    """cell_i64: int64 tensor [min_ordered, nan_seen] on the communicator's device; reduced in place with ONE
+    collective: a rank that saw a NaN contributes -1, which wins the MIN and marks the result as NaN."""
+    import torch
     import torch.distributed as dist
 
-    lo = cell_i64[0:1].clone()
-    hi = cell_i64[1:2].clone()
-    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
-    dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
-    cell_i64[0:1] = lo
-    cell_i64[1:2] = hi
+    key = torch.where(cell_i64[1:2] > 0, torch.full_like(cell_i64[0:1], -1), cell_i64[0:1])
+    dist.all_reduce(key, op=dist.ReduceOp.MIN, group=group)
+    nan = (key < 0).to(torch.int64)
+    cell_i64[0:1] = torch.where(key < 0, cell_i64[0:1], key)
+    cell_i64[1:2] = nan
     return cell_i64
 
 

@@ -69,10 +69,14 @@ def _worker(rank, world, port, a, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         # ---- Log2.post cell ---------------------------------------------------------------------
-        mine = [(-3.5, 0), (-7.25, 1)][rank]
+        mine = [(-3.5, 0), (-7.25, 0)][rank]
         cell = torch.tensor([parallel.encode_min(mine[0]), mine[1]], dtype=torch.int64)
         parallel.allreduce_min_cell(cell)
-        assert parallel.decode_min(int(cell[0])) == np.float32(-7.25) and int(cell[1]) == 1
+        assert parallel.decode_min(int(cell[0])) == np.float32(-7.25) and int(cell[1]) == 0
+        mine = [(0.25, 0), (-7.25, 1)][rank]       # a NaN on any rank makes the whole result NaN (np.min semantics)
+        cell = torch.tensor([parallel.encode_min(mine[0]), mine[1]], dtype=torch.int64)
+        parallel.allreduce_min_cell(cell)
+        assert int(cell[1]) == 1
         # ---- order-exact chain over two row shards --------------------------------------------------
         ranges = parallel.shard_ranges(np.full(a.shape[0], 100), world)
         b, e = ranges[rank]
