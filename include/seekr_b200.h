@@ -107,12 +107,14 @@ int skr_min_reset(SkrMinCell* d_cell, void* stream);
  * d_min, when given, receives the running minimum / NaN flag of everything written.
  * d_post, when given, holds the matrix-wide minimum already (see skr_count_colmin) and the Log2.post
  * tail (+ |min|, + 1, log2; kmer_counts.py:207-209) is applied in the same epilogue.
+ * d_rstd, when given (fp32 vectors only), holds RN(1/std) from skr_reciprocal and switches the division to
+ * a 5-instruction correctly rounded form; the caller guarantees 2^-40 <= std <= 2^40 and |mean| <= 2^40.
  * Records with L < k give a zero-count row; the caller must reject L == k-1 beforehand
  * (ZeroDivisionError in the reference).  1 <= k <= 8. */
 int skr_count(const uint32_t* d_codes, const uint32_t* d_mask, const uint64_t* d_block_offsets,
               const uint32_t* d_lengths, int64_t m, int k, int log2_pre, const void* d_mean, const void* d_std,
               int vec_is_f64, void* d_out, int out_is_f64, int64_t ld_out, SkrMinCell* d_min, const SkrMinCell* d_post,
-              void* stream);
+              const float* d_rstd, void* stream);
 
 /* Deferred normalisation for Log2.post with known, finite mean / positive std vectors (the
  * seekr_kmer_counts -mv -sv path): the count kernel writes the un-normalised values and keeps the
@@ -133,6 +135,11 @@ int skr_colmin_finish(const uint32_t* d_colmin, int64_t cols, const void* d_mean
 int skr_normalize_post_log2(float* d_a, int64_t m, int64_t cols, int64_t ld, const void* d_mean, const void* d_std,
                             int vec_is_f64, const SkrMinCell* d_min, void* stream);
 int skr_vec_check(const void* d_vec, int vec_is_f64, int64_t n, int* d_flag, void* stream);
+/* out[j] = RN(1 / v[j]) */
+int skr_reciprocal(const float* d_vec, int64_t n, float* d_out, void* stream);
+/* counts operand pairs (of n generated on the device) for which the reciprocal-based division differs from
+ * IEEE division; *d_mismatches must be zeroed by the caller */
+int skr_selftest_division(uint64_t n, uint64_t seed, uint64_t* d_mismatches, void* stream);
 
 /* a = log2(a + 1)                                   (BasicCounter.log2_norm, kmer_counts.py:189-192) */
 int skr_log2_norm(float* d_a, int64_t m, int64_t cols, int64_t ld, void* stream);

@@ -50,13 +50,15 @@ SIGNATURES = {
     "skr_packed_slab_bytes": (_sz, [_vp]),
     "skr_pack_error_line": (_i64, []),
     "skr_min_reset": (_int, [_vp, _vp]),
-    "skr_count": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _int, _vp, _vp, _int, _vp, _int, _i64, _vp, _vp, _vp]),
+    "skr_count": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _int, _vp, _vp, _int, _vp, _int, _i64, _vp, _vp, _vp, _vp]),
     "skr_colmin_reset": (_int, [_vp, _i64, _vp]),
     "skr_count_colmin": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _int, _vp, _i64, _vp, _vp]),
     "skr_colmin_scan": (_int, [_vp, _i64, _i64, _i64, _vp, _vp]),
     "skr_colmin_finish": (_int, [_vp, _i64, _vp, _vp, _int, _vp, _vp]),
     "skr_normalize_post_log2": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _int, _vp, _vp]),
     "skr_vec_check": (_int, [_vp, _int, _i64, _vp, _vp]),
+    "skr_reciprocal": (_int, [_vp, _i64, _vp, _vp]),
+    "skr_selftest_division": (_int, [ctypes.c_uint64, ctypes.c_uint64, _vp, _vp]),
     "skr_log2_norm": (_int, [_vp, _i64, _i64, _i64, _vp]),
     "skr_post_log2": (_int, [_vp, _i64, _i64, _i64, _vp, _vp]),
     "skr_sub_vec": (_int, [_vp, _i64, _i64, _i64, _vp, _int, _vp, _vp]),

@@ -79,7 +79,10 @@ __global__ void __launch_bounds__(64) col_pass_kernel(const __grid_constant__ CU
     }
     // one IEEE operation per step, exactly the reference's sequence: counts -= mean (one rounding),
     // np.std: x - arrmean, square, sequential fp32 sum (kmer_counts.py:169,174; numpy _methods.py:_var)
-    auto step = [&](float x) {
+    // value() is the per-element work that does not depend on the running sum; the adds form one
+    // dependent fp32 chain (4 cycles each).  Rows are taken 32 at a time: 32 shared loads + value()s are
+    // issued back to back, then the 32 chained adds, so the ~30-cycle load latency is paid once per 32 rows.
+    auto value = [&](float x) -> float {
         float y = x;
         if (KIND != SKR_COLPASS_SUM && has_vec)
             y = kVecF64 ? __double2float_rn(__dsub_rn((double)x, vd)) : __fsub_rn(x, vf);
@@ -87,24 +90,22 @@ __global__ void __launch_bounds__(64) col_pass_kernel(const __grid_constant__ CU
             const float d = __fsub_rn(y, v2);
             y = __fmul_rn(d, d);
         }
-        acc = __fadd_rn(acc, y);
+        return y;
     };
     for (long long t = 0; t < ntiles; ++t) {
         const int s = (int)(t % kStages);
         const uint32_t ph = (uint32_t)((t / kStages) & 1);
         skr::mbar_wait(&full_bar[s], ph);
         const int rows = (int)min((long long)kTileRows, m - t * kTileRows);
-        // (issuing the next batch's shared loads ahead of the current adds was tried: 1.5-2x slower, the
-        // extra register moves sit on the dependent chain; the 8-load / 8-add batches below are the fast form)
         int r = 0;
-        for (; r + 8 <= rows; r += 8) {
-            float x[8];
+        for (; r + 32 <= rows; r += 32) {
+            float y[32];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) x[u] = tiles[s][r + u][lane];
+            for (int u = 0; u < 32; ++u) y[u] = value(tiles[s][r + u][lane]);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) step(x[u]);
+            for (int u = 0; u < 32; ++u) acc = __fadd_rn(acc, y[u]);
         }
-        for (; r < rows; ++r) step(tiles[s][r][lane]);
+        for (; r < rows; ++r) acc = __fadd_rn(acc, value(tiles[s][r][lane]));
         __syncwarp();
         if (lane == 0) skr::mbar_arrive(&empty_bar[s]);
     }

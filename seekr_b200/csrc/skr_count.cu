@@ -54,6 +54,7 @@ struct CountParams {
     // per-column minimum of the values written (float bits; values are >= 0 on this path), for the
     // Log2.post shift when normalisation is deferred to the element-wise pass
     uint32_t* colmin;
+    const float* rstd;            // RN(1/std) per column: enables the 5-instruction exact division (fp32 vectors only)
     int no_store;                 // column-minimum pass only: nothing is written to `out`
     const SkrMinCell* post_cell;  // Log2.post fused into the epilogue: + |min|, + 1, log2 with this cell's minimum
 };
@@ -120,6 +121,21 @@ __device__ __noinline__ float slow_bin_value(double inc, uint32_t c, int log2_pr
     return v;
 }
 
+// Correctly rounded a / b from y = RN(1/b) with two Newton corrections on the quotient (Markstein: when y is
+// the correctly rounded reciprocal and q is within one ulp of a/b, q + (a - b*q)*y rounds to RN(a/b); the first
+// correction makes q faithful, the second makes it exact).  Valid when no intermediate over/underflows: the
+// caller only enables it for |b| in [2^-40, 2^40] and |a| in {0} U [2^-60, 2^40] (checked on the host for the
+// vectors, true by construction for per-kb counts).  5 instructions instead of the 14 of the generic
+// div.rn.f32 sequence (MUFU.RCP, FCHK, 5 FFMA, branch, slow-path call); verified against __fdiv_rn on
+// 2^32 operand pairs by skr_selftest_division (tests/test_gpu_counts.py).
+__device__ __forceinline__ float div_by_rcp(float a, float b, float y) {
+    float q = __fmul_rn(a, y);
+    float r = __fmaf_rn(-b, q, a);
+    q = __fmaf_rn(r, y, q);
+    r = __fmaf_rn(-b, q, a);
+    return __fmaf_rn(r, y, q);
+}
+
 // counts of 4 consecutive bins -> the reference's float32 values (per-kb chain, log2.pre, -mean, /std).
 // packed = the two histogram words (four 16-bit counts) when every count fits the table.
 template <bool kVecF64>
@@ -151,8 +167,14 @@ __device__ __forceinline__ void finish4(const uint32_t (&c4)[4], uint32_t tab_ad
             for (int e = 0; e < 4; ++e) r[e] = __double2float_rn(__ddiv_rn((double)r[e], __ldg(sv + e)));
         } else {
             const float4 sv = __ldg(reinterpret_cast<const float4*>(p.std_) + q);
-            r[0] = __fdiv_rn(r[0], sv.x); r[1] = __fdiv_rn(r[1], sv.y);
-            r[2] = __fdiv_rn(r[2], sv.z); r[3] = __fdiv_rn(r[3], sv.w);
+            if (p.rstd) {
+                const float4 yv = __ldg(reinterpret_cast<const float4*>(p.rstd) + q);
+                r[0] = div_by_rcp(r[0], sv.x, yv.x); r[1] = div_by_rcp(r[1], sv.y, yv.y);
+                r[2] = div_by_rcp(r[2], sv.z, yv.z); r[3] = div_by_rcp(r[3], sv.w, yv.w);
+            } else {
+                r[0] = __fdiv_rn(r[0], sv.x); r[1] = __fdiv_rn(r[1], sv.y);
+                r[2] = __fdiv_rn(r[2], sv.z); r[3] = __fdiv_rn(r[3], sv.w);
+            }
         }
     }
 }
@@ -765,6 +787,32 @@ __global__ void vec_check_kernel(const T* v, long long n, int* flag) {
     if (f) atomicOr(flag, f);
 }
 
+__global__ void reciprocal_kernel(const float* v, long long n, float* out) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) out[j] = __frcp_rn(v[j]);
+}
+
+// operand pairs from a counter-based hash: a = +-m1 * 2^ea (ea in [-60, 40], 1/64 of them exactly 0), b = m2 * 2^eb
+// (eb in [-40, 40]); counts results of div_by_rcp that differ from __fdiv_rn
+__global__ void selftest_division_kernel(unsigned long long n, unsigned long long seed, unsigned long long* bad) {
+    unsigned long long local = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        unsigned long long h = (i + seed) * 0x9E3779B97F4A7C15ull;
+        h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32; h *= 0x94D049BB133111EBull; h ^= h >> 29;
+        const uint32_t ma = (uint32_t)h & 0x7FFFFFu, mb = (uint32_t)(h >> 23) & 0x7FFFFFu;
+        const int ea = (int)((h >> 46) % 101) - 60, eb = (int)((h >> 53) % 81) - 40;
+        float a = __uint_as_float(((uint32_t)(ea + 127) << 23) | ma);
+        if ((h >> 60) & 1) a = -a;
+        if (((h >> 40) & 63) == 0) a = 0.0f;
+        const float b = __uint_as_float(((uint32_t)(eb + 127) << 23) | mb);
+        const float want = __fdiv_rn(a, b);
+        const float got = div_by_rcp(a, b, __frcp_rn(b));
+        if (__float_as_uint(want) != __float_as_uint(got)) ++local;
+    }
+    if (local) atomicAdd(bad, local);
+}
+
 __global__ void min_reset_kernel(SkrMinCell* cell) {
     cell->min_ordered = skr::ordered_encode(INFINITY);
     cell->nan_seen = 0;
@@ -782,8 +830,10 @@ extern "C" int skr_min_reset(SkrMinCell* d_cell, void* stream) {
 extern "C" int skr_count(const uint32_t* d_codes, const uint32_t* d_mask, const uint64_t* d_block_offsets,
                          const uint32_t* d_lengths, int64_t m, int k, int log2_pre, const void* d_mean,
                          const void* d_std, int vec_is_f64, void* d_out, int out_is_f64, int64_t ld_out,
-                         SkrMinCell* d_min, const SkrMinCell* d_post, void* stream) {
+                         SkrMinCell* d_min, const SkrMinCell* d_post, const float* d_rstd, void* stream) {
     if (m == 0) return SKR_OK;
+    if (d_rstd && (!d_std || vec_is_f64 || ((uintptr_t)d_rstd & 15)))
+        return skr::fail(SKR_ERR_ARG, "skr_count: the reciprocal vector goes with an aligned fp32 std vector");
     if (!d_codes || !d_mask || !d_block_offsets || !d_lengths || !d_out || m < 0)
         return skr::fail(SKR_ERR_ARG, "skr_count: null or negative argument");
     if (k < 1 || k > 8) return skr::fail(SKR_ERR_ARG, "skr_count: k=%d not supported (1 <= k <= 8)", k);
@@ -809,6 +859,7 @@ extern "C" int skr_count(const uint32_t* d_codes, const uint32_t* d_mask, const 
     p.ld_out = ld_out;
     p.min_cell = d_min;
     p.post_cell = d_post;
+    p.rstd = d_rstd;
     cudaStream_t s = (cudaStream_t)stream;
     switch (k) {
         case 1: return dispatch_count<1>(p, vec_is_f64, out_is_f64, s);
@@ -893,6 +944,21 @@ extern "C" int skr_normalize_post_log2(float* d_a, int64_t m, int64_t cols, int6
                                        const void* d_std, int vec_is_f64, const SkrMinCell* d_min, void* stream) {
     if (!d_min) return skr::fail(SKR_ERR_ARG, "skr_normalize_post_log2: null min cell");
     return launch_ew<OP_NORMPOST>(d_a, m, cols, ld, d_mean, vec_is_f64, d_min, nullptr, (cudaStream_t)stream, d_std);
+}
+
+extern "C" int skr_reciprocal(const float* d_vec, int64_t n, float* d_out, void* stream) {
+    if (n <= 0) return SKR_OK;
+    if (!d_vec || !d_out) return skr::fail(SKR_ERR_ARG, "skr_reciprocal: null argument");
+    reciprocal_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_vec, n, d_out);
+    SKR_LAUNCH_CHECK();
+    return SKR_OK;
+}
+
+extern "C" int skr_selftest_division(uint64_t n, uint64_t seed, uint64_t* d_mismatches, void* stream) {
+    if (!d_mismatches) return skr::fail(SKR_ERR_ARG, "skr_selftest_division: null argument");
+    selftest_division_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(n, seed, (unsigned long long*)d_mismatches);
+    SKR_LAUNCH_CHECK();
+    return SKR_OK;
 }
 
 extern "C" int skr_vec_check(const void* d_vec, int vec_is_f64, int64_t n, int* d_flag, void* stream) {

@@ -72,12 +72,15 @@ class DeviceVector:
     on the device by ``check()``).  The deferred-normalisation path needs a finite mean and a finite,
     positive std (kmer_counts.CountEngine.run)."""
 
-    def __init__(self, tensor, is_f64, finite=None, positive=None, flag=None):
+    def __init__(self, tensor, is_f64, finite=None, positive=None, flag=None, well_scaled=False):
         self.t = tensor
         self.is_f64 = is_f64
         self.finite = finite
         self.positive = positive
         self.flag = flag  # device int written by skr_col_finish: bit 0 not finite, bit 1 not positive
+        # every |element| in [2^-40, 2^40] (known for host-born vectors): allows the reciprocal-based division
+        self.well_scaled = well_scaled
+        self._rcp = None
 
     @classmethod
     def from_host(cls, value, cols):
@@ -85,7 +88,22 @@ class DeviceVector:
         with np.errstate(all="ignore"):
             finite = bool(np.all(np.isfinite(vec)))
             positive = bool(np.all(vec > 0))
-        return cls(device.to_device(vec), is_f64, finite, positive)
+            mag = np.abs(vec.astype(np.float64))
+            well_scaled = finite and bool(np.all((mag >= 2.0 ** -40) & (mag <= 2.0 ** 40)))
+            bounded = finite and bool(np.all(mag <= 2.0 ** 40))
+        obj = cls(device.to_device(vec), is_f64, finite, positive, well_scaled=well_scaled)
+        obj.bounded = bounded
+        return obj
+
+    def reciprocal(self, stream=None):
+        """RN(1/v) on the device (fp32 vectors), cached."""
+        if self._rcp is None:
+            import torch
+
+            self._rcp = torch.empty_like(self.t)
+            _lib.check(_lib.load().skr_reciprocal(device.ptr(self.t), self.t.numel(), device.ptr(self._rcp),
+                                                 device.stream_ptr(stream)))
+        return self._rcp
 
     def as_f64(self):
         import torch
@@ -123,6 +141,7 @@ class CountEngine:
         self.stream = stream
         self.min_cell = device.MinCell()
         self.count_events = None  # set to a list to collect (start, end) CUDA events around every count launch
+        self.fast_division = True
         # two-pass Log2.post (column minima first, then count + normalise + post in one epilogue): measured
         # equal to fused count + post pass on B200 (both ~0.6 ms for 50k transcripts, instruction-bound), so off
         self.deferred = False
@@ -150,12 +169,17 @@ class CountEngine:
         log2_pre = 1 if self.log2 == "Log2.pre" else 0
         if track_min:
             self.min_cell.reset(self.stream)
+        # exact 5-instruction division when the vectors are fp32 and of sane magnitude (host-known)
+        rstd = None
+        if (std is not None and not vec_is_f64 and std.well_scaled and std.positive
+                and (mean is None or getattr(mean, "bounded", False)) and self.fast_division):
+            rstd = std.reciprocal(self.stream)
         ev = self._event_start()
         rc = self.lib.skr_count(
             dpk.codes, dpk.mask, dpk.blk_off, dpk.lengths, dpk.m, self.k, 0 if out_is_f64 else log2_pre,
             device.ptr(mean.t if mean else None), device.ptr(std.t if std else None), int(vec_is_f64),
             device.ptr(out), int(out_is_f64), out.stride(0), device.ptr(self.min_cell.t if track_min else None),
-            device.ptr(self.min_cell.t if post else None), device.stream_ptr(self.stream))
+            device.ptr(self.min_cell.t if post else None), device.ptr(rstd), device.stream_ptr(self.stream))
         _lib.check(rc)
         self._event_end(ev)
         self._keep = (mean, std)  # converted vectors must outlive the launch

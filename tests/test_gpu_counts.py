@@ -439,3 +439,36 @@ def test_badly_behaved_vectors_take_the_fused_path(capsys):
         # the reference warns when the matrix holds a NaN right after standardisation (kmer_counts.py:176)
         warned = "WARNING: You have `np.nan` values" in capsys.readouterr().out
         assert warned == bool(np.isnan(z).any())
+
+
+def test_reciprocal_division_is_ieee_exact():
+    """The 5-instruction division (y = RN(1/b), two Newton corrections) equals div.rn.f32 on 2^32 operand pairs
+    drawn over the exponent ranges the count kernel can meet (|a| in {0} U [2^-60, 2^40], b in [2^-40, 2^40])."""
+    import torch
+
+    lib = _lib.load()
+    bad = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for seed in (1, 0xDEADBEEF):
+        _lib.check(lib.skr_selftest_division(1 << 31, seed, device.ptr(bad), device.stream_ptr()))
+    torch.cuda.synchronize()
+    assert int(bad.item()) == 0
+
+
+def test_fast_division_path_is_bit_identical():
+    seqs = synth.seq_strings(500, seed=10, stress=True, lo=60, hi=5000)
+    for k in (4, 6):
+        sub = [s for s in seqs if len(s) != k - 1]
+        raw = c_oracle.raw_counts(sub, k)
+        mean = raw.mean(axis=0).astype(np.float32)
+        std = (raw.std(axis=0) * np.float32(1.37) + np.float32(1e-3)).astype(np.float32)
+        packed = PackedFasta.from_sequences(sub, pinned=True)
+        outs = []
+        for fast in (True, False):
+            eng = CountEngine(k, "Log2.none")
+            eng.fast_division = fast
+            dpk = eng.upload(packed)
+            out, _, _ = eng.run(dpk, DeviceVector.from_host(mean, 4 ** k), DeviceVector.from_host(std, 4 ** k))
+            outs.append(out.cpu().numpy())
+        assert np.array_equal(outs[0], outs[1])
+        exp, _, _ = c_oracle.normalise(raw, mean, std, "Log2.none")
+        assert np.array_equal(outs[0], exp)
