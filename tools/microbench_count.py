@@ -73,8 +73,9 @@ def main():
         out = device.empty((m, cols), torch.float32)
         in_bytes = float(np.sum((lens + 3) // 4 + (lens + 7) // 8 + 12))
         row_bytes = 4.0 * cols * m
-        mean = DeviceVector(torch.rand(cols, device="cuda") + 0.5, False, True, True)
-        std = DeviceVector(torch.rand(cols, device="cuda") + 0.5, False, True, True)
+        rng = np.random.default_rng(1)
+        mean = DeviceVector.from_host((rng.random(cols) + 0.5).astype(np.float32), cols)
+        std = DeviceVector.from_host((rng.random(cols) + 0.5).astype(np.float32), cols)
 
         def report(name, ms, mn, nbytes):
             gbs = nbytes / (mn * 1e-3) / 1e9
@@ -85,6 +86,10 @@ def main():
         report("count raw", ms, mn, in_bytes + row_bytes)
         ms, mn = timeit(lambda: eng.count(dpk, out, mean, std, track_min=True), flush)
         report("count fused -mean /std +min", ms, mn, in_bytes + row_bytes)
+        eng.fast_division = False
+        ms, mn = timeit(lambda: eng.count(dpk, out, mean, std, track_min=True), flush)
+        report("  (generic div.rn.f32 path)", ms, mn, in_bytes + row_bytes)
+        eng.fast_division = True
         colmin = device.empty(cols, torch.int32)
         ms, mn = timeit(lambda: eng.count_colmin(dpk, colmin), flush)
         report("column minima only (no write)", ms, mn, in_bytes)
