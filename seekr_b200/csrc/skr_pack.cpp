@@ -316,27 +316,6 @@ struct ChunkResult {
     uint64_t err_off = UINT64_MAX;
     int err_code = 0;
     bool first_line_not_header = false;
-    // records that start in this chunk are packed straight into these thread-local arrays while the text
-    // is scanned (one pass over the text); every record is block aligned, so the arrays are copied into
-    // the final slab with one memcpy each once the global block offsets are known
-    struct Buf {  // uninitialised, growable word array (std::vector would zero-fill it first)
-        uint32_t* p = nullptr;
-        size_t cap = 0;
-        Buf() = default;
-        Buf(const Buf&) = delete;
-        Buf& operator=(const Buf&) = delete;
-        ~Buf() { free(p); }
-        uint32_t* data() const { return p; }
-        size_t size() const { return cap; }
-        void resize(size_t n) {  // keeps the contents
-            if (n <= cap) return;
-            p = (uint32_t*)realloc(p, n * sizeof(uint32_t));
-            cap = n;
-        }
-    };
-    Buf codes, mask;
-    size_t used_c = 0, used_m = 0;  // words in use
-    uint64_t blocks = 0;
 };
 
 void build_lut2(const uint8_t* lut, uint8_t* lut2) {
@@ -540,24 +519,6 @@ extern "C" int skr_pack_fasta_buffer(const void* text_v, size_t nbytes, const ui
         const char* to = text + nbytes * (size_t)(t + 1) / (size_t)T;
         bool in_record = false;  // a header that started in this chunk is open
         bool beyond = false;     // phase 2: lines that start past `to` (they finish our last record)
-        R.codes.resize((size_t)(to - from) / 4 + 64);
-        R.mask.resize((size_t)(to - from) / 8 + 64);
-        BitWriter w{R.codes.data(), R.mask.data()};
-        auto close_record = [&]() {  // pad the open record to its block boundary
-            if (!in_record) return;
-            const uint64_t nb = (R.recs.back().bases + 63) / 64;
-            w.finish(R.codes.data() + (R.blocks + nb) * 4, R.mask.data() + (R.blocks + nb) * 2);
-            R.blocks += nb;
-        };
-        auto reserve_for = [&](size_t nbases) {  // room for nbases more bases plus the padding of a record
-            const size_t uc = (size_t)(w.cw - R.codes.data()), um = (size_t)(w.mw - R.mask.data());
-            if (uc + nbases / 16 + 8 > R.codes.size() || um + nbases / 32 + 8 > R.mask.size()) {
-                R.codes.resize(std::max(R.codes.size() * 2, uc + nbases / 16 + 64));
-                R.mask.resize(std::max(R.mask.size() * 2, um + nbases / 32 + 64));
-                w.cw = R.codes.data() + uc;
-                w.mw = R.mask.data() + um;
-            }
-        };
         auto on_line = [&](const char* a, const char* b) -> bool {
             const char* la = a;
             const char* lb = b;
@@ -570,7 +531,6 @@ extern "C" int skr_pack_fasta_buffer(const void* text_v, size_t nbytes, const ui
             }
             if (*la == '>') {
                 if (beyond) return false;  // next chunk's record: our last record is complete
-                close_record();
                 Rec r;
                 r.hdr_off = (uint64_t)(la - text);
                 r.hdr_len = (uint64_t)(lb - la);
@@ -588,11 +548,7 @@ extern "C" int skr_pack_fasta_buffer(const void* text_v, size_t nbytes, const ui
             Rec& r = R.recs.back();
             if (r.body_len == 0) r.body_off = (uint64_t)(a - text);
             r.body_len = (uint64_t)(b - text) - r.body_off;
-            const size_t n = (size_t)(lb - la);
-            r.bases += n;
-            reserve_for(n);
-            if (al.ok) pack_segment_avx2(w, la, lb, al, end);
-            else for (const char* p = la; p < lb; ++p) w.put(lut2[(unsigned char)*p]);
+            r.bases += (uint64_t)(lb - la);
             return true;
         };
         const char* next = use_avx2 ? for_each_line_avx2(text, from, to, end, on_line)
@@ -602,10 +558,6 @@ extern "C" int skr_pack_fasta_buffer(const void* text_v, size_t nbytes, const ui
             if (use_avx2) for_each_line_avx2(text, next, end, end, on_line);
             else for_each_line(text, next, end, end, on_line);
         }
-        reserve_for(0);
-        close_record();
-        R.used_c = (size_t)(w.cw - R.codes.data());
-        R.used_m = (size_t)(w.mw - R.mask.data());
     });
 
     // the earliest error wins: the reference stops at the first offending line
@@ -658,28 +610,38 @@ extern "C" int skr_pack_fasta_buffer(const void* text_v, size_t nbytes, const ui
     P->header_spans.resize((size_t)m * 2);
     P->body_spans.resize((size_t)m * 2);
     const auto t_alloc = now();
-    // thread t's records are consecutive: its packed words go to the slab in one piece
-    std::vector<uint64_t> block_base((size_t)T + 1, 0), rec_base((size_t)T + 1, 0);
-    for (int t = 0; t < T; ++t) {
-        block_base[t + 1] = block_base[t] + res[t].blocks;
-        rec_base[t + 1] = rec_base[t] + res[t].recs.size();
-    }
-    run_threads(T, [&](int t) {
-        const ChunkResult& R = res[t];
-        if (R.blocks) {
-            memcpy(P->codes + block_base[t] * 4, R.codes.data(), (size_t)R.blocks * 16);
-            memcpy(P->mask + block_base[t] * 2, R.mask.data(), (size_t)R.blocks * 8);
-        }
-        for (size_t j = 0; j < R.recs.size(); ++j) {
-            const size_t i = (size_t)rec_base[t] + j;
-            P->header_spans[2 * i] = R.recs[j].hdr_off;
-            P->header_spans[2 * i + 1] = R.recs[j].hdr_len;
-            P->body_spans[2 * i] = R.recs[j].body_off;
-            P->body_spans[2 * i + 1] = R.recs[j].body_len;
+    std::atomic<int64_t> next_rec{0};
+    run_threads(T, [&](int) {
+        for (;;) {
+            int64_t i0 = next_rec.fetch_add(64);
+            if (i0 >= m) break;
+            int64_t i1 = std::min(m, i0 + 64);
+            for (int64_t i = i0; i < i1; ++i) {
+                const Rec& r = recs[i];
+                P->header_spans[2 * i] = r.hdr_off;
+                P->header_spans[2 * i + 1] = r.hdr_len;
+                P->body_spans[2 * i] = r.body_off;
+                P->body_spans[2 * i + 1] = r.body_len;
+                uint64_t b0 = P->blk_off[i], b1 = P->blk_off[i + 1];
+                BitWriter w{P->codes + b0 * 4, P->mask + b0 * 2};
+                const char* bs = text + r.body_off;
+                const char* be = bs + r.body_len;
+                if (r.body_len) {
+                    auto pack_line = [&](const char* a, const char* b) -> bool {
+                        strip(a, b);
+                        if (al.ok) pack_segment_avx2(w, a, b, al, end);
+                        else for (const char* p = a; p < b; ++p) w.put(lut2[(unsigned char)*p]);
+                        return true;
+                    };
+                    if (use_avx2) for_each_line_avx2(bs, bs, be, be, pack_line);
+                    else for_each_line(bs, bs, be, be, pack_line);
+                }
+                w.finish(P->codes + b1 * 4, P->mask + b1 * 2);
+            }
         }
     });
     if (profile)
-        fprintf(stderr, "skr_pack: %d threads, scan+pack %.2f ms, merge+alloc %.2f ms, copy %.2f ms (%zu bytes, %lld records)\n", T,
+        fprintf(stderr, "skr_pack: %d threads, scan %.2f ms, merge+alloc %.2f ms, pack %.2f ms (%zu bytes, %lld records)\n", T,
                 ms(t_start, t_pass1), ms(t_pass1, t_alloc), ms(t_alloc, now()), nbytes, (long long)m);
     *out = P;
     return SKR_OK;
