@@ -8,7 +8,7 @@
 // dependent add chain is 4 cycles per row, about the time HBM needs to deliver the row anyway,
 // provided the loads never stall it (no pass writes the matrix: the centred values are recomputed
 // where needed, with the same single rounding): a CTA owns a strip of 32 columns; one producer thread
-// streams [128 rows x 32 columns] boxes of the strip through a 4-deep shared-memory ring with
+// streams [128 rows x 32 columns] boxes of the strip through a 8-deep shared-memory ring with
 // TMA (cp.async.bulk.tensor + mbarrier), and one consumer warp (lane = column) walks the rows.
 // The running sums enter and leave through d_acc, so row shards on several GPUs can be chained.
 //
@@ -22,9 +22,10 @@
 
 namespace {
 
-constexpr int kStripCols = 32;
-constexpr int kTileRows = 128;
-constexpr int kStages = 4;
+constexpr int kGroups = 1;                  // independent columns (add chains) per consumer lane (2 was slower: half the CTAs)
+constexpr int kStripCols = 32 * kGroups;
+constexpr int kTileRows = 256;
+constexpr int kStages = 6;
 constexpr int kTileBytes = kTileRows * kStripCols * 4;  // 16 KB
 
 template <int KIND, bool kVecF64>
@@ -63,53 +64,81 @@ __global__ void __launch_bounds__(64) col_pass_kernel(const __grid_constant__ CU
         return;
     }
 
-    // consumer warp: lane = column of the strip
-    const long long col = col0 + lane;
-    const bool active = col < cols;
-    float acc = active ? acc_io[col] : 0.0f;
-    float vf = 0.0f, v2 = 0.0f;
-    double vd = 0.0;
+    // consumer warp: lane owns columns col0 + lane + 32*g (g < kGroups).  The adds of one column form a
+    // dependent fp32 chain (4 cycles each) and the warp issues in order, so a single chain leaves the issue
+    // slot idle most of the time; kGroups independent chains per lane are interleaved to fill it.
+    float acc[kGroups], vf[kGroups], v2[kGroups];
+    double vd[kGroups];
+    bool active[kGroups];
     const bool has_vec = vec != nullptr;
-    if (active) {
-        if (has_vec) {
-            if (kVecF64) vd = reinterpret_cast<const double*>(vec)[col];
-            else vf = reinterpret_cast<const float*>(vec)[col];
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) {
+        const long long col = col0 + lane + 32 * g;
+        active[g] = col < cols;
+        acc[g] = active[g] ? acc_io[col] : 0.0f;
+        vf[g] = v2[g] = 0.0f;
+        vd[g] = 0.0;
+        if (active[g]) {
+            if (has_vec) {
+                if (kVecF64) vd[g] = reinterpret_cast<const double*>(vec)[col];
+                else vf[g] = reinterpret_cast<const float*>(vec)[col];
+            }
+            if (KIND == SKR_COLPASS_SQDEV) v2[g] = vec2[col];
         }
-        if (KIND == SKR_COLPASS_SQDEV) v2 = vec2[col];
     }
     // one IEEE operation per step, exactly the reference's sequence: counts -= mean (one rounding),
-    // np.std: x - arrmean, square, sequential fp32 sum (kmer_counts.py:169,174; numpy _methods.py:_var)
-    // value() is the per-element work that does not depend on the running sum; the adds form one
-    // dependent fp32 chain (4 cycles each).  Rows are taken 32 at a time: 32 shared loads + value()s are
-    // issued back to back, then the 32 chained adds, so the ~30-cycle load latency is paid once per 32 rows.
-    auto value = [&](float x) -> float {
+    // np.std: x - arrmean, square, sequential fp32 sum (kmer_counts.py:169,174; numpy _methods.py:_var).
+    // value() is the per-element work that does not depend on the running sum.
+    auto value = [&](float x, int g) -> float {
         float y = x;
         if (KIND != SKR_COLPASS_SUM && has_vec)
-            y = kVecF64 ? __double2float_rn(__dsub_rn((double)x, vd)) : __fsub_rn(x, vf);
+            y = kVecF64 ? __double2float_rn(__dsub_rn((double)x, vd[g])) : __fsub_rn(x, vf[g]);
         if (KIND == SKR_COLPASS_SQDEV) {
-            const float d = __fsub_rn(y, v2);
+            const float d = __fsub_rn(y, v2[g]);
             y = __fmul_rn(d, d);
         }
         return y;
     };
+    // Register window of kWin rows: right after row r has been added, its register is refilled with row
+    // r + kWin of the same tile, so every dependent add (4 cycles) has an independent shared load next to it
+    // in program order and the in-order warp never waits for a load (the refill is consumed kWin adds later).
+    constexpr int kWin = 16;
+    static_assert(kTileRows % kWin == 0, "tile rows must be a multiple of the window");
     for (long long t = 0; t < ntiles; ++t) {
         const int s = (int)(t % kStages);
         const uint32_t ph = (uint32_t)((t / kStages) & 1);
         skr::mbar_wait(&full_bar[s], ph);
         const int rows = (int)min((long long)kTileRows, m - t * kTileRows);
-        int r = 0;
-        for (; r + 32 <= rows; r += 32) {
-            float y[32];
+        if (rows == kTileRows) {
+            float y[kWin][kGroups];
 #pragma unroll
-            for (int u = 0; u < 32; ++u) y[u] = value(tiles[s][r + u][lane]);
+            for (int u = 0; u < kWin; ++u)
 #pragma unroll
-            for (int u = 0; u < 32; ++u) acc = __fadd_rn(acc, y[u]);
+                for (int g = 0; g < kGroups; ++g) y[u][g] = value(tiles[s][u][lane + 32 * g], g);
+            for (int r = 0; r < kTileRows - kWin; r += kWin) {
+#pragma unroll
+                for (int u = 0; u < kWin; ++u)
+#pragma unroll
+                    for (int g = 0; g < kGroups; ++g) {
+                        acc[g] = __fadd_rn(acc[g], y[u][g]);
+                        y[u][g] = value(tiles[s][r + kWin + u][lane + 32 * g], g);
+                    }
+            }
+#pragma unroll
+            for (int u = 0; u < kWin; ++u)
+#pragma unroll
+                for (int g = 0; g < kGroups; ++g) acc[g] = __fadd_rn(acc[g], y[u][g]);
+        } else {
+            for (int r = 0; r < rows; ++r)
+#pragma unroll
+                for (int g = 0; g < kGroups; ++g) acc[g] = __fadd_rn(acc[g], value(tiles[s][r][lane + 32 * g], g));
         }
-        for (; r < rows; ++r) acc = __fadd_rn(acc, value(tiles[s][r][lane]));
         __syncwarp();
         if (lane == 0) skr::mbar_arrive(&empty_bar[s]);
     }
-    if (active) acc_io[col] = acc;
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g)
+        if (active[g]) acc_io[col0 + lane + 32 * g] = acc[g];
 }
 
 // flag (optional): bit 0 set if any result is not finite, bit 1 if any result is <= 0
