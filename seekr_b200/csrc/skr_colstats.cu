@@ -8,8 +8,9 @@
 // dependent add chain is 4 cycles per row, about the time HBM needs to deliver the row anyway,
 // provided the loads never stall it (no pass writes the matrix: the centred values are recomputed
 // where needed, with the same single rounding): a CTA owns a strip of 32 columns; one producer thread
-// streams [128 rows x 32 columns] boxes of the strip through a 8-deep shared-memory ring with
-// TMA (cp.async.bulk.tensor + mbarrier), and one consumer warp (lane = column) walks the rows.
+// streams [192 rows x 32 columns] boxes of the strip through an 8-deep shared-memory ring with
+// TMA (cp.async.bulk.tensor + mbarrier), and three consumer warps (lane = column) take turns: load a
+// tile into registers, then run its adds when the running sums arrive from the previous tile.
 // The running sums enter and leave through d_acc, so row shards on several GPUs can be chained.
 //
 // Scalable passes (skr_col_partial_f64): row-parallel binary64 partial sums for one all-reduce.
@@ -22,19 +23,29 @@
 
 namespace {
 
-constexpr int kGroups = 1;                  // independent columns (add chains) per consumer lane (2 was slower: half the CTAs)
-constexpr int kStripCols = 32 * kGroups;
-constexpr int kTileRows = 256;
-constexpr int kStages = 6;
-constexpr int kTileBytes = kTileRows * kStripCols * 4;  // 16 KB
+constexpr int kStripCols = 32;
+constexpr int kTileRows = 192;
+constexpr int kStages = 8;
+constexpr int kRelay = 3;  // consumer warps taking turns on the add chain
+constexpr int kTileBytes = kTileRows * kStripCols * 4;  // 24 KB
+constexpr int kColThreads = 32 * (1 + kRelay);
+
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+    asm volatile("barrier.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+    asm volatile("barrier.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
 
 template <int KIND, bool kVecF64>
-__global__ void __launch_bounds__(64) col_pass_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ a,
-                                                      long long m, long long cols, long long ld, const void* vec,
-                                                      const float* vec2, float* acc_io) {
+__global__ void __launch_bounds__(kColThreads) col_pass_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                               const float* __restrict__ a, long long m, long long cols,
+                                                               long long ld, const void* vec, const float* vec2,
+                                                               float* acc_io) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t full_bar[kStages];
     __shared__ uint64_t empty_bar[kStages];
+    __shared__ float relay_acc[32];
     float(*tiles)[kTileRows][kStripCols] = reinterpret_cast<float(*)[kTileRows][kStripCols]>(smem_raw);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -50,7 +61,7 @@ __global__ void __launch_bounds__(64) col_pass_kernel(const __grid_constant__ CU
     }
     __syncthreads();
 
-    if (warp == 1) {
+    if (warp == 0) {
         if (lane == 0) {
             skr::tma_prefetch_desc(&tmap);
             for (long long t = 0; t < ntiles; ++t) {
@@ -64,81 +75,83 @@ __global__ void __launch_bounds__(64) col_pass_kernel(const __grid_constant__ CU
         return;
     }
 
-    // consumer warp: lane owns columns col0 + lane + 32*g (g < kGroups).  The adds of one column form a
-    // dependent fp32 chain (4 cycles each) and the warp issues in order, so a single chain leaves the issue
-    // slot idle most of the time; kGroups independent chains per lane are interleaved to fill it.
-    float acc[kGroups], vf[kGroups], v2[kGroups];
-    double vd[kGroups];
-    bool active[kGroups];
+    // Consumer warps (lane = column col0 + lane).  The adds of one column are a dependent fp32 chain, 4 cycles
+    // per row, and that chain is the whole critical path.  Shared loads cannot feed it directly: a warp has six
+    // scoreboards, so at most a handful of loads are individually tracked and an add that waits for its operand
+    // also waits for younger loads on the same scoreboard (measured: 7.6 cycles per row with loads and adds
+    // interleaved).  So kRelay warps take turns: a warp copies its whole tile into registers (value() applied,
+    // off the chain), gives the slot back to the producer, then waits for the running sums from the warp that
+    // holds the previous tile, runs kTileRows register-only adds and passes the sums on through shared memory.
+    const int cw = warp - 1;
+    const long long col = col0 + lane;
+    const bool active = col < cols;
     const bool has_vec = vec != nullptr;
-#pragma unroll
-    for (int g = 0; g < kGroups; ++g) {
-        const long long col = col0 + lane + 32 * g;
-        active[g] = col < cols;
-        acc[g] = active[g] ? acc_io[col] : 0.0f;
-        vf[g] = v2[g] = 0.0f;
-        vd[g] = 0.0;
-        if (active[g]) {
-            if (has_vec) {
-                if (kVecF64) vd[g] = reinterpret_cast<const double*>(vec)[col];
-                else vf[g] = reinterpret_cast<const float*>(vec)[col];
-            }
-            if (KIND == SKR_COLPASS_SQDEV) v2[g] = vec2[col];
+    float vf = 0.0f, v2 = 0.0f;
+    double vd = 0.0;
+    if (active) {
+        if (has_vec) {
+            if (kVecF64) vd = reinterpret_cast<const double*>(vec)[col];
+            else vf = reinterpret_cast<const float*>(vec)[col];
         }
+        if (KIND == SKR_COLPASS_SQDEV) v2 = vec2[col];
     }
     // one IEEE operation per step, exactly the reference's sequence: counts -= mean (one rounding),
     // np.std: x - arrmean, square, sequential fp32 sum (kmer_counts.py:169,174; numpy _methods.py:_var).
-    // value() is the per-element work that does not depend on the running sum.
-    auto value = [&](float x, int g) -> float {
+    auto value = [&](float x) -> float {
         float y = x;
         if (KIND != SKR_COLPASS_SUM && has_vec)
-            y = kVecF64 ? __double2float_rn(__dsub_rn((double)x, vd[g])) : __fsub_rn(x, vf[g]);
+            y = kVecF64 ? __double2float_rn(__dsub_rn((double)x, vd)) : __fsub_rn(x, vf);
         if (KIND == SKR_COLPASS_SQDEV) {
-            const float d = __fsub_rn(y, v2[g]);
+            const float d = __fsub_rn(y, v2);
             y = __fmul_rn(d, d);
         }
         return y;
     };
-    // Register window of kWin rows: right after row r has been added, its register is refilled with row
-    // r + kWin of the same tile, so every dependent add (4 cycles) has an independent shared load next to it
-    // in program order and the in-order warp never waits for a load (the refill is consumed kWin adds later).
-    constexpr int kWin = 16;
-    static_assert(kTileRows % kWin == 0, "tile rows must be a multiple of the window");
-    for (long long t = 0; t < ntiles; ++t) {
+    float acc = 0.0f;
+    const uint32_t relay_slot = (uint32_t)__cvta_generic_to_shared(&relay_acc[lane]);
+    auto relay_load = [&]() -> float {  // address formed before the barrier, so the hand-over is barrier + one load
+        float v;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(relay_slot) : "memory");
+        return v;
+    };
+    for (long long t = cw; t < ntiles; t += kRelay) {
         const int s = (int)(t % kStages);
         const uint32_t ph = (uint32_t)((t / kStages) & 1);
-        skr::mbar_wait(&full_bar[s], ph);
         const int rows = (int)min((long long)kTileRows, m - t * kTileRows);
+        skr::mbar_wait(&full_bar[s], ph);
         if (rows == kTileRows) {
-            float y[kWin][kGroups];
+            float y[kTileRows];
 #pragma unroll
-            for (int u = 0; u < kWin; ++u)
-#pragma unroll
-                for (int g = 0; g < kGroups; ++g) y[u][g] = value(tiles[s][u][lane + 32 * g], g);
-            for (int r = 0; r < kTileRows - kWin; r += kWin) {
-#pragma unroll
-                for (int u = 0; u < kWin; ++u)
-#pragma unroll
-                    for (int g = 0; g < kGroups; ++g) {
-                        acc[g] = __fadd_rn(acc[g], y[u][g]);
-                        y[u][g] = value(tiles[s][r + kWin + u][lane + 32 * g], g);
-                    }
+            for (int r = 0; r < kTileRows; ++r) y[r] = value(tiles[s][r][lane]);
+            __syncwarp();
+            if (lane == 0) skr::mbar_arrive(&empty_bar[s]);
+            if (t == 0) {
+                acc = active ? acc_io[col] : 0.0f;
+            } else {
+                named_bar_sync(1 + cw, 64);
+                acc = relay_load();
             }
 #pragma unroll
-            for (int u = 0; u < kWin; ++u)
-#pragma unroll
-                for (int g = 0; g < kGroups; ++g) acc[g] = __fadd_rn(acc[g], y[u][g]);
-        } else {
-            for (int r = 0; r < rows; ++r)
-#pragma unroll
-                for (int g = 0; g < kGroups; ++g) acc[g] = __fadd_rn(acc[g], value(tiles[s][r][lane + 32 * g], g));
+            for (int r = 0; r < kTileRows; ++r) acc = __fadd_rn(acc, y[r]);
+        } else {  // ragged last tile
+            if (t == 0) {
+                acc = active ? acc_io[col] : 0.0f;
+            } else {
+                named_bar_sync(1 + cw, 64);
+                acc = relay_load();
+            }
+#pragma unroll 8
+            for (int r = 0; r < rows; ++r) acc = __fadd_rn(acc, value(tiles[s][r][lane]));
+            __syncwarp();
+            if (lane == 0) skr::mbar_arrive(&empty_bar[s]);
         }
-        __syncwarp();
-        if (lane == 0) skr::mbar_arrive(&empty_bar[s]);
+        if (t + 1 < ntiles) {
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(relay_slot), "f"(acc) : "memory");
+            named_bar_arrive(1 + (cw + 1) % kRelay, 64);
+        } else if (active) {
+            acc_io[col] = acc;
+        }
     }
-#pragma unroll
-    for (int g = 0; g < kGroups; ++g)
-        if (active[g]) acc_io[col0 + lane + 32 * g] = acc[g];
 }
 
 // flag (optional): bit 0 set if any result is not finite, bit 1 if any result is <= 0
@@ -221,7 +234,7 @@ extern "C" int skr_col_pass(int kind, const float* d_a, int64_t m, int64_t cols,
     do {                                                                                                       \
         auto kern = col_pass_kernel<KIND, F64>;                                                                \
         SKR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-        kern<<<grid, 64, smem, s>>>(tmap, d_a, m, cols, ld, d_vec, d_vec2, d_acc);                             \
+        kern<<<grid, kColThreads, smem, s>>>(tmap, d_a, m, cols, ld, d_vec, d_vec2, d_acc);                             \
     } while (0)
     switch (kind) {
         case SKR_COLPASS_SUM: SKR_COL_LAUNCH(SKR_COLPASS_SUM, false); break;

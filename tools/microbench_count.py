@@ -37,9 +37,12 @@ def timeit(fn, flush, reps=5, warm=2):
         fn()
     ts = []
     for _ in range(reps):
-        flush.zero_()
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # no synchronise after the flush: while the GPU is busy flushing, the host gets ahead and enqueues
+        # fn's launches, so the events bracket kernel time and not the host's launch latency
+        flush.zero_()
+        flush.zero_()
         a.record()
         fn()
         b.record()
