@@ -182,30 +182,44 @@ __device__ __forceinline__ void finish4(const uint32_t (&c4)[4], uint32_t tab_ad
 // 16 window starts of one chunk -> shared-memory histogram (two 16-bit sub-counters per word).
 // x: 32 bases (2 bits each, first base in the top bits); mb: the chunk's 16+K-1 mask bits; nv: valid windows.
 // hist_addr: shared-window address of the histogram.  Bin b lives in word b>>1, half b&1.
-template <int K>
+__device__ __forceinline__ void red_add_shared_always(uint32_t addr, uint32_t inc) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(inc) : "memory");
+}
+
+// kAligned: hist_addr is a multiple of the histogram size, so base | offset replaces base + offset and the
+// word address is a single three-input logic operation on the shifted k-mer.
+template <int K, bool kAligned = false>
 __device__ __forceinline__ void count_chunk(uint32_t hist_addr, uint64_t x, uint32_t mb, int nv) {
     constexpr uint32_t kMask = (1u << (2 * K)) - 1;
-    uint32_t ok = 0xFFFFu;  // bit 15-j: window j is counted
-    if (mb != 0 || nv != 16) {
-        // window j is bad if any of its K mask bits is set: OR the mask with itself shifted by 1..K-1
-        uint32_t bad = mb;
-#pragma unroll
-        for (int i = 1; i < K; ++i) bad |= mb << i;
-        ok = ~(bad >> (K - 1)) & 0xFFFFu & ~(0xFFFFu >> nv);
-    } else {
+    constexpr uint32_t kOffMask = (kMask >> 1) << 2;  // (kmer >> 1) * 4 out of t = kmer << 1
+    if (mb == 0 && nv == 16) {
         // all 16 + K - 1 bases equal (homopolymer run): one add of 16 instead of 16 colliding adds
         const uint64_t same = (x ^ (x << 2)) >> (64 - 2 * (16 + K - 2));
         if (same == 0) {
             const uint32_t kmer = (uint32_t)(x >> (64 - 2 * K)) & kMask;
-            red_add_shared(hist_addr + (kmer >> 1) * 4, 16u << ((kmer & 1) * 16), 1u);
+            red_add_shared_always(hist_addr + (kmer >> 1) * 4, 16u << ((kmer & 1) * 16));
             return;
         }
+        // the common case: every window counts, no predicates (5 instructions per window:
+        // funnel shift, address, half select, increment, red)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const uint32_t t = (uint32_t)(x >> (64 - 2 * (j + K) - 1));
+            const uint32_t addr = kAligned ? ((t & kOffMask) | hist_addr) : hist_addr + (t & kOffMask);
+            red_add_shared_always(addr, (t & 2u) ? 0x10000u : 1u);
+        }
+        return;
     }
+    // window j is bad if any of its K mask bits is set: OR the mask with itself shifted by 1..K-1
+    uint32_t bad = mb;
+#pragma unroll
+    for (int i = 1; i < K; ++i) bad |= mb << i;
+    const uint32_t ok = ~(bad >> (K - 1)) & 0xFFFFu & ~(0xFFFFu >> nv);  // bit 15-j: window j is counted
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
         // t = k-mer shifted left by one: bits [2K..1] = k-mer, so (t & mask) is the byte offset of its word / 2
         const uint32_t t = (uint32_t)(x >> (64 - 2 * (j + K) - 1));
-        const uint32_t off = t & ((kMask >> 1) << 2);               // (kmer >> 1) * 4
+        const uint32_t off = t & kOffMask;
         const uint32_t inc = 1u << ((t << 3) & 16);                  // kmer & 1 ? 0x10000 : 1
         red_add_shared(hist_addr + off, inc, ok & (0x8000u >> j));
     }
@@ -491,6 +505,342 @@ __global__ void __launch_bounds__(WarpCfg<K>::kThreads, WarpCfg<K>::kMinCtas) co
 }
 
 // ---------------------------------------------------------------------------------------------
+// Batch kernel (k = 6, float32 output): a persistent CTA of 16 worker warps + 1 bookkeeping warp takes
+// kB consecutive records at a time.
+//   count phase   the batch's windows are cut into units of 32 (two chunks that share their code and mask
+//                 words) and dealt round-robin to the 512 worker threads, whatever record they belong to, so
+//                 the threads stay busy on short and long records alike; each record has its own histogram.
+//   epilogue      thread w owns bin quads w and w + 512 of EVERY record.  Its slices of mean / std / 1/std
+//                 are loaded once per kernel and stay in registers, so the normalisation costs no memory
+//                 traffic at all (the warp kernel re-reads 48 KB of vectors from L2 per record, which made
+//                 it latency-bound: 0.32 ms fused against 0.21 ms raw).  Each warp writes 512 contiguous
+//                 bytes per step; the histogram words are zeroed as they are read.
+//   bookkeeping   warp 16 draws the next batch, reads its lengths / offsets, runs the kTab-entry binary64
+//                 value chains and the unit prefix while the workers are busy (double-buffered BatchMeta).
+// ---------------------------------------------------------------------------------------------
+template <int K>
+struct BatchCfg {
+    static constexpr int kBins = 1 << (2 * K);
+    static constexpr int kWords = kBins / 2;
+    static constexpr int kHistBytes = kWords * 4;
+    static constexpr int kWorkers = 512;
+    static constexpr int kThreads = kWorkers + 32;
+    static constexpr int kB = 8;                        // records per batch
+    static constexpr int kQ = kBins / 4 / kWorkers;     // bin quads per worker thread
+    // histograms start at a multiple of their size (count_chunk<K, true>): one histogram of slack
+    static constexpr size_t kSmem = (size_t)(kB + 1) * kHistBytes;
+    static_assert(kBins / 4 % kWorkers == 0 && kQ >= 1, "every worker owns whole quads of every record");
+};
+
+template <int kB>
+struct BatchMeta {
+    alignas(128) float tab[kB][kTab];  // 128-byte rows: table address | 4*count
+    long long rec0;                    // first record of the batch, < 0: no more work
+    int nrec;
+    uint32_t prefix[kB + 1];           // units (32 windows) before record r
+    long long nwin[kB];
+    unsigned long long b0[kB];         // first 64-base block
+    double inc[kB];
+    int store[kB];                     // 0: the row is produced elsewhere (long record list)
+};
+static_assert(kTab * 4 == 128, "table rows are addressed by OR");
+
+__device__ __forceinline__ void sts_zero_v2(uint32_t addr) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %1};" ::"r"(addr), "r"(0u) : "memory");
+}
+
+// Epilogue flavours, so that the common cases carry no dead predicated instructions (the kernel is bound by
+// instruction issue):  kBatchPlain  no vectors / column minima / fused Log2.post,
+//                      kBatchFast   fp32 mean, std and 1/std, no column minima / fused Log2.post,
+//                      kBatchAny    everything decided at run time.
+enum { kBatchAny = 0, kBatchPlain = 1, kBatchFast = 2 };
+
+template <int K, bool kVecF64, int kMode, bool kMin>
+__global__ void __launch_bounds__(BatchCfg<K>::kThreads, 2) count_batch_kernel(const CountParams p) {
+    using Cfg = BatchCfg<K>;
+    constexpr int kB = Cfg::kB, kW = Cfg::kWorkers, kQ = Cfg::kQ;
+    static_assert(!(kVecF64 && kMode != kBatchAny), "binary64 vectors take the generic epilogue");
+    extern __shared__ __align__(16) uint32_t smem_b[];
+    __shared__ BatchMeta<kB> s_meta[2];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const bool worker = tid < kW;
+    const uint32_t raw_addr = skr::smem_u32(smem_b);
+    const uint32_t hist_addr = (raw_addr + Cfg::kHistBytes - 1) & ~(uint32_t)(Cfg::kHistBytes - 1);
+
+    float tmin = INFINITY;
+    int tnan = 0;
+    float shift = 0.0f;
+    if (kMode == kBatchAny && p.post_cell)
+        shift = p.post_cell->nan_seen ? __int_as_float(0x7FC00000) : fabsf(skr::ordered_decode(p.post_cell->min_ordered));
+
+    // this thread's slices of the vectors (fp32 vectors only; binary64 vectors are read in the epilogue)
+    float4 mv[kQ], sv[kQ], yv[kQ];
+    uint32_t cmin[kQ][4];
+#pragma unroll
+    for (int j = 0; j < kQ; ++j) {
+        mv[j] = sv[j] = yv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) cmin[j][e] = 0xFFFFFFFFu;
+    }
+    if (worker) {
+        if constexpr (!kVecF64 && kMode != kBatchPlain) {
+#pragma unroll
+            for (int j = 0; j < kQ; ++j) {
+                const int q = tid + j * kW;
+                if (p.mean) mv[j] = __ldg(reinterpret_cast<const float4*>(p.mean) + q);
+                if (p.std_) sv[j] = __ldg(reinterpret_cast<const float4*>(p.std_) + q);
+                if (p.std_ && p.rstd) yv[j] = __ldg(reinterpret_cast<const float4*>(p.rstd) + q);
+            }
+        }
+        uint4* h4 = reinterpret_cast<uint4*>(smem_b + (hist_addr - raw_addr) / 4);
+        for (int i = tid; i < kB * Cfg::kWords / 4; i += kW) h4[i] = make_uint4(0, 0, 0, 0);
+    }
+
+    // bookkeeping warp: fill s_meta[buf] for the next batch
+    auto produce = [&](int buf) {
+        BatchMeta<kB>& mt = s_meta[buf];
+        long long b = 0;
+        if (lane == 0) b = (long long)atomicAdd(p.work_counter, 1u);
+        b = __shfl_sync(0xFFFFFFFFu, b, 0);
+        const long long rec0 = b * kB;
+        const int nrec = rec0 < p.m ? (int)min((long long)kB, p.m - rec0) : 0;
+        uint32_t units = 0;
+        if (lane < kB) {
+            long long nwin = 0;
+            unsigned long long b0 = 0;
+            int store = 0;
+            if (lane < nrec) {
+                const long long rec = rec0 + lane;
+                nwin = (long long)__ldg(p.len + rec) - K + 1;
+                b0 = __ldg(p.blk_off + rec);
+                store = 1;
+                if (nwin > kLongWin) {
+                    p.long_list[atomicAdd(p.long_count, 1u)] = (uint32_t)rec;
+                    store = 0;
+                    nwin = 0;
+                }
+                if (nwin < 0) nwin = 0;
+            }
+            const double inc = nwin > 0 ? 1000.0 / (double)nwin : 0.0;
+            mt.nwin[lane] = nwin;
+            mt.b0[lane] = b0;
+            mt.inc[lane] = inc;
+            mt.store[lane] = store;
+            units = (uint32_t)((nwin + 31) / 32);
+            double acc = 0.0;  // the literal chain of kmer_counts.py:144-150 for counts below kTab
+            mt.tab[lane][0] = p.log2_pre ? log2f(1.0f) : 0.0f;
+#pragma unroll 8
+            for (int c = 1; c < kTab; ++c) {
+                acc = __dadd_rn(acc, inc);
+                float v = __double2float_rn(acc);
+                if (p.log2_pre) v = log2f(__fadd_rn(v, 1.0f));
+                mt.tab[lane][c] = v;
+            }
+        }
+        uint32_t incl = units;  // inclusive scan over the first kB lanes
+#pragma unroll
+        for (int o = 1; o < kB; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        if (lane < kB) mt.prefix[lane + 1] = incl;
+        if (lane == 0) {
+            mt.prefix[0] = 0;
+            mt.rec0 = nrec > 0 ? rec0 : -1;
+            mt.nrec = nrec;
+        }
+    };
+
+    if (!worker) produce(0);
+    __syncthreads();
+
+    for (int it = 0;; ++it) {
+        const BatchMeta<kB>& mt = s_meta[it & 1];
+        if (mt.rec0 < 0) break;
+        if (!worker) {
+            produce((it + 1) & 1);
+        } else {
+            // ---- count phase ----
+            const uint32_t total = mt.prefix[kB];
+            auto locate = [&](uint32_t g, int& r, uint32_t& u) {
+                r = 0;
+                uint32_t before = 0;
+#pragma unroll
+                for (int i = 1; i < kB; ++i) {
+                    const uint32_t pf = mt.prefix[i];  // broadcast shared loads
+                    if (g >= pf) { r = i; before = pf; }
+                }
+                u = g - before;
+            };
+            uint32_t w0 = 0, w1 = 0, w2 = 0, m0 = 0, m1 = 0, u = 0;
+            int r = 0;
+            uint32_t g = (uint32_t)tid;
+            if (g < total) {
+                locate(g, r, u);
+                const uint32_t* cw = p.codes + mt.b0[r] * 4 + 2 * u;
+                const uint32_t* mw = p.mask + mt.b0[r] * 2 + u;
+                w0 = __ldg(cw); w1 = __ldg(cw + 1); w2 = __ldg(cw + 2);
+                m0 = __ldg(mw); m1 = __ldg(mw + 1);
+            }
+            while (g < total) {
+                const uint32_t gn = g + kW;
+                uint32_t n0 = 0, n1 = 0, n2 = 0, q0 = 0, q1 = 0, un = 0;
+                int rn = 0;
+                if (gn < total) {  // next unit's words are in flight while this one is counted
+                    locate(gn, rn, un);
+                    const uint32_t* cw = p.codes + mt.b0[rn] * 4 + 2 * un;
+                    const uint32_t* mw = p.mask + mt.b0[rn] * 2 + un;
+                    n0 = __ldg(cw); n1 = __ldg(cw + 1); n2 = __ldg(cw + 2);
+                    q0 = __ldg(mw); q1 = __ldg(mw + 1);
+                }
+                const uint32_t h = hist_addr + (uint32_t)r * Cfg::kHistBytes;
+                const uint64_t m64 = ((uint64_t)m0 << 32) | m1;
+                const long long left = mt.nwin[r] - (long long)u * 32;
+                count_chunk<K, true>(h, ((uint64_t)w0 << 32) | w1, (uint32_t)(m64 >> (64 - (16 + K - 1))),
+                                     left < 16 ? (int)left : 16);
+                if (left > 16)
+                    count_chunk<K, true>(h, ((uint64_t)w1 << 32) | w2, (uint32_t)((m64 << 16) >> (64 - (16 + K - 1))),
+                                         left < 32 ? (int)(left - 16) : 16);
+                w0 = n0; w1 = n1; w2 = n2; m0 = q0; m1 = q1; u = un; r = rn; g = gn;
+            }
+        }
+        __syncthreads();
+        if (worker) {
+            // ---- epilogue ----
+            const int nrec = mt.nrec;
+            for (int r = 0; r < nrec; ++r) {
+                if (!mt.store[r]) continue;
+                const uint32_t tab_addr = skr::smem_u32(&mt.tab[r][0]);
+                float* __restrict__ orow = reinterpret_cast<float*>(p.out) + (size_t)(mt.rec0 + r) * (size_t)p.ld_out;
+#pragma unroll
+                for (int j = 0; j < kQ; ++j) {
+                    const int q = tid + j * kW;
+                    const uint32_t a = hist_addr + (uint32_t)r * Cfg::kHistBytes + (uint32_t)q * 8;
+                    const uint2 v = lds_v2(a);
+                    sts_zero_v2(a);
+                    float x[4];
+                    if (((v.x | v.y) & ~(uint32_t)((kTab - 1) * 0x10001u)) == 0) {
+                        // every count is below kTab: table address | 4 * count
+                        x[0] = lds_f32(tab_addr | ((v.x << 2) & 0x7Cu));
+                        x[1] = lds_f32(tab_addr | ((v.x >> 14) & 0x7Cu));
+                        x[2] = lds_f32(tab_addr | ((v.y << 2) & 0x7Cu));
+                        x[3] = lds_f32(tab_addr | ((v.y >> 14) & 0x7Cu));
+                    } else {
+                        const uint32_t c4[4] = {v.x & 0xFFFFu, v.x >> 16, v.y & 0xFFFFu, v.y >> 16};
+                        const double inc = mt.inc[r];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            x[e] = c4[e] < kTab ? lds_f32(tab_addr + c4[e] * 4) : slow_bin_value(inc, c4[e], p.log2_pre);
+                    }
+                    if constexpr (kMode == kBatchFast) {
+                        x[0] = div_by_rcp(__fsub_rn(x[0], mv[j].x), sv[j].x, yv[j].x);
+                        x[1] = div_by_rcp(__fsub_rn(x[1], mv[j].y), sv[j].y, yv[j].y);
+                        x[2] = div_by_rcp(__fsub_rn(x[2], mv[j].z), sv[j].z, yv[j].z);
+                        x[3] = div_by_rcp(__fsub_rn(x[3], mv[j].w), sv[j].w, yv[j].w);
+                    } else if constexpr (kMode == kBatchAny) {
+                        if constexpr (kVecF64) {
+                            if (p.mean) {
+                                const double* mp = reinterpret_cast<const double*>(p.mean) + 4 * q;
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) x[e] = __double2float_rn(__dsub_rn((double)x[e], __ldg(mp + e)));
+                            }
+                            if (p.std_) {
+                                const double* sp = reinterpret_cast<const double*>(p.std_) + 4 * q;
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) x[e] = __double2float_rn(__ddiv_rn((double)x[e], __ldg(sp + e)));
+                            }
+                        } else {
+                            if (p.mean) {
+                                x[0] = __fsub_rn(x[0], mv[j].x); x[1] = __fsub_rn(x[1], mv[j].y);
+                                x[2] = __fsub_rn(x[2], mv[j].z); x[3] = __fsub_rn(x[3], mv[j].w);
+                            }
+                            if (p.std_) {
+                                if (p.rstd) {
+                                    x[0] = div_by_rcp(x[0], sv[j].x, yv[j].x); x[1] = div_by_rcp(x[1], sv[j].y, yv[j].y);
+                                    x[2] = div_by_rcp(x[2], sv[j].z, yv[j].z); x[3] = div_by_rcp(x[3], sv[j].w, yv[j].w);
+                                } else {
+                                    x[0] = __fdiv_rn(x[0], sv[j].x); x[1] = __fdiv_rn(x[1], sv[j].y);
+                                    x[2] = __fdiv_rn(x[2], sv[j].z); x[3] = __fdiv_rn(x[3], sv[j].w);
+                                }
+                            }
+                        }
+                        if (p.colmin) {  // values are >= 0 on this path: float bits order like unsigned integers
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) cmin[j][e] = min(cmin[j][e], __float_as_uint(x[e]));
+                        }
+                        if (p.post_cell) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) x[e] = log2f(__fadd_rn(__fadd_rn(x[e], shift), 1.0f));
+                        }
+                    }
+                    if constexpr (kMin) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) skr::min_update(x[e], tmin, tnan);
+                    }
+                    if (kMode != kBatchAny || !p.no_store)
+                        reinterpret_cast<float4*>(orow)[q] = make_float4(x[0], x[1], x[2], x[3]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    if (worker) {
+        if (kMode == kBatchAny && p.colmin) {
+#pragma unroll
+            for (int j = 0; j < kQ; ++j)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int col = 4 * (tid + j * kW) + e;
+                    if (cmin[j][e] < p.colmin[col]) atomicMin(&p.colmin[col], cmin[j][e]);
+                }
+        }
+        if constexpr (kMin) {
+            if (tmin != tmin) { tnan = 1; tmin = INFINITY; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                tmin = fminf(tmin, __shfl_xor_sync(0xFFFFFFFFu, tmin, o));
+                tnan |= __shfl_xor_sync(0xFFFFFFFFu, tnan, o);
+            }
+            if (lane == 0) {
+                if (tmin < INFINITY) atomicMin(&p.min_cell->min_ordered, skr::ordered_encode(tmin));
+                if (tnan) atomicOr(&p.min_cell->nan_seen, 1u);
+            }
+        }
+    }
+}
+
+template <int K, bool kVecF64, int kMode, bool kMin>
+int launch_batch(const CountParams& wp, int sms, cudaStream_t stream) {
+    using B = BatchCfg<K>;
+    auto bkern = count_batch_kernel<K, kVecF64, kMode, kMin>;
+    SKR_CUDA_CHECK(cudaFuncSetAttribute(bkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B::kSmem));
+    int bper_sm = 0;
+    SKR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bper_sm, bkern, B::kThreads, B::kSmem));
+    if (bper_sm < 1) return skr::fail(SKR_ERR_CUDA, "batch count kernel for k=%d does not fit on this device", K);
+    long long bgrid = (long long)sms * bper_sm;
+    const long long bneed = (wp.m + B::kB - 1) / B::kB;
+    if (bgrid > bneed) bgrid = bneed;
+    bkern<<<(unsigned)bgrid, B::kThreads, B::kSmem, stream>>>(wp);
+    return SKR_OK;
+}
+
+template <int K, bool kVecF64>
+int dispatch_batch(const CountParams& wp, int sms, cudaStream_t stream) {
+    const bool plain = !wp.mean && !wp.std_ && !wp.colmin && !wp.post_cell && !wp.no_store;
+    const bool fast = !kVecF64 && wp.mean && wp.std_ && wp.rstd && !wp.colmin && !wp.post_cell && !wp.no_store;
+    const bool mn = wp.min_cell != nullptr;
+    if constexpr (!kVecF64) {
+        if (plain) return mn ? launch_batch<K, false, kBatchPlain, true>(wp, sms, stream)
+                             : launch_batch<K, false, kBatchPlain, false>(wp, sms, stream);
+        if (fast) return mn ? launch_batch<K, false, kBatchFast, true>(wp, sms, stream)
+                            : launch_batch<K, false, kBatchFast, false>(wp, sms, stream);
+    }
+    return mn ? launch_batch<K, kVecF64, kBatchAny, true>(wp, sms, stream)
+              : launch_batch<K, kVecF64, kBatchAny, false>(wp, sms, stream);
+}
+
+// ---------------------------------------------------------------------------------------------
 // per-device scratch: work counters (a ring, so launches on different streams do not share one)
 // and the per-CTA spill rows
 // ---------------------------------------------------------------------------------------------
@@ -568,6 +918,8 @@ int launch_count(CountParams p, cudaStream_t stream) {
         int wper_sm = 0;
         SKR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wper_sm, wkern, W::kThreads, W::kSmem));
         if (wper_sm < 1) return skr::fail(SKR_ERR_CUDA, "warp count kernel for k=%d does not fit on this device", K);
+        if (const char* env = getenv("SEEKR_B200_COUNT_CTAS_PER_SM"))  // experiment knob: resident CTAs per SM
+            if (atoi(env) > 0 && atoi(env) < wper_sm) wper_sm = atoi(env);
         long long wgrid = (long long)sms * wper_sm;
         const long long need = (p.m + W::kTeams - 1) / W::kTeams;
         if (wgrid > need) wgrid = need;
@@ -575,7 +927,16 @@ int launch_count(CountParams p, cudaStream_t stream) {
         wp.work_counter = ctr;
         wp.long_list = sc->long_list;
         wp.long_count = ctr + 1;
-        wkern<<<(unsigned)wgrid, W::kThreads, W::kSmem, stream>>>(wp);
+        bool batch = false;
+        if constexpr (K == 6) {
+            const char* env = getenv("SEEKR_B200_COUNT_KERNEL");  // experiment knob: "warp" selects the team-per-record kernel
+            batch = !(env && env[0] == 'w');
+            if (batch) {
+                rc = dispatch_batch<K, kVecF64>(wp, sms, stream);
+                if (rc != SKR_OK) return rc;
+            }
+        }
+        if (!batch) wkern<<<(unsigned)wgrid, W::kThreads, W::kSmem, stream>>>(wp);
         SKR_LAUNCH_CHECK();
         // long records (rare): the CTA kernel reads the list length on the device
         p.work_counter = ctr + 2;
