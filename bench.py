@@ -425,7 +425,7 @@ def run_ours(args):
                     "e2e": {"value": world * p_rows * p_rows / e2e_pearson_s, "unit": "pairs/s", "rows": p_rows,
                             "h2d_bytes_per_step": p_rows * cols * 4, "d2h_bytes_per_step": p_rows * p_rows * 4}},
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
-                     "traffic": ncu_traffic("count_kernel", m == 50000), "kernel": "count_warp_kernel<6> (count + per-kb chain + -mean + /std + running min, one write of the row)", "kernel_ms": k_count,
+                     "traffic": ncu_traffic("count_kernel", m == 50000), "kernel": "count_batch_kernel<6> (count + per-kb chain + -mean + /std + running min, one write of the row)", "kernel_ms": k_count,
                      "algorithmic_bytes_per_launch": count_bytes, "peak_source": peaks["source"]},
         "cpu_baseline": cpu,
         "e2e": {"value": total_tr / e2e_count_s, "unit": "transcripts/s", "h2d_bytes_per_step": int(slab_bytes + 2 * cols * 4),
