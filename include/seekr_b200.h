@@ -207,6 +207,40 @@ int skr_pearson_gemm(const uint16_t* d_a_hi, const uint16_t* d_a_lo, const float
                      double alpha, void* d_c, int c_is_f64, int64_t ldc, int symmetric, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Consumers of the r matrix (the reference runs them as Python loops)
+ *
+ * skr_pval_empirical   replaces find_pval.py:157-159: p[i][j] = count(background > r[i][j]) / N, the
+ *                      division in binary64, stored in r's type.  d_sorted_bg is the background in
+ *                      ascending order (float32 or float64, no NaN).
+ * skr_pval_dist        replaces find_pval.py:126-128 for the closed-form scipy.stats families below:
+ *                      p = 1 - dist(shape, loc, scale).cdf(r), evaluated in binary64 (support handling and
+ *                      invalid parameters as rv_continuous.cdf).  shape is ignored by families without one.
+ * skr_triu_extract     replaces find_dist.py:163: c[np.triu_indices(n, k=1)] (row-major) into d_out, which
+ *                      holds skr_triu_count(n) = n(n-1)/2 values.
+ * skr_pearson_pairs    r of npairs (i, j) pairs from prepared planes (find_dist.py:160-169 needs only a random
+ *                      subset of the triangle): out[q] = alpha * <a_i, b_j>, binary64 accumulation.
+ * ------------------------------------------------------------------------------------------ */
+enum {
+    SKR_DIST_NORM = 0,     /* scipy.stats.norm                */
+    SKR_DIST_LOGNORM = 1,  /* lognorm(s)      shape = s       */
+    SKR_DIST_CAUCHY = 2,
+    SKR_DIST_EXPON = 3,
+    SKR_DIST_RAYLEIGH = 4,
+    SKR_DIST_UNIFORM = 5,
+    SKR_DIST_PARETO = 6,   /* pareto(b)       shape = b       */
+    SKR_DIST_EXPONPOW = 7  /* exponpow(b)     shape = b       */
+};
+int skr_pval_empirical(const void* d_r, int r_is_f64, int64_t m, int64_t n, int64_t ld, const void* d_sorted_bg,
+                       int bg_is_f64, int64_t N, void* d_p, int64_t ldp, void* stream);
+int skr_pval_dist(const void* d_r, int r_is_f64, int64_t m, int64_t n, int64_t ld, int kind, double shape, double loc,
+                  double scale, void* d_p, int64_t ldp, void* stream);
+int64_t skr_triu_count(int64_t n);
+int skr_triu_extract(const void* d_c, int c_is_f64, int64_t n, int64_t ld, void* d_out, void* stream);
+int skr_pearson_pairs(const uint16_t* d_a_hi, const uint16_t* d_a_lo, const float* d_a_scale, const uint16_t* d_b_hi,
+                      const uint16_t* d_b_lo, const float* d_b_scale, int64_t K, const int64_t* d_i, const int64_t* d_j,
+                      int64_t npairs, double alpha, float* d_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Host <-> device plumbing used by the Python layer (thin wrappers; no reference counterpart)
  * ------------------------------------------------------------------------------------------ */
 int skr_host_alloc(size_t bytes, void** out); /* pinned host memory from the library's pool */

@@ -233,3 +233,85 @@ def pearson(counts1, counts2, row_standardize=True):
 def pearson_f64(counts1, counts2, row_standardize=True):
     """binary64 'truth' used to separate our error from the reference's own fp32 error."""
     return pearson(np.asarray(counts1, dtype=np.float64), np.asarray(counts2, dtype=np.float64), row_standardize)
+
+
+# ---------------------------------------------------------------------------------------------
+# Consumers of the r matrix (SURVEY 8f rows 1-2): seekr/find_dist.py:160-169, seekr/find_pval.py:126-171.
+# Pinned by tests/golden/pval/ (outputs of the unmodified reference, tests/golden/make_golden_pval.py).
+# The distribution mode leans on scipy.stats in the reference; the closed forms below restate
+# scipy 1.18.1 scipy/stats/_continuous_distns.py (_cdf bodies) + rv_continuous.cdf (support handling).
+# ---------------------------------------------------------------------------------------------
+def triu_flat(sim):
+    """sim[np.triu_indices(n, k=1)] (find_dist.py:163): strict upper triangle, row-major."""
+    sim = np.asarray(sim)
+    n = sim.shape[0]
+    return np.concatenate([sim[i, i + 1:] for i in range(n)]) if n > 1 else sim[:0, 0]
+
+
+def pval_empirical(sim, fitres):
+    """p[i, j] = np.sum(fitres > sim[i, j]) / len(fitres), stored in sim's dtype (find_pval.py:153-159)."""
+    sim = np.asarray(sim)
+    srt = np.sort(np.asarray(fitres))
+    total = len(srt)
+    # count(fitres > x) = N - upper_bound(sorted, x); NaN compares false with everything
+    if srt.dtype == np.float32 and sim.dtype == np.float32:
+        ub = np.searchsorted(srt, sim, side="right")
+    else:
+        ub = np.searchsorted(srt.astype(np.float64), sim.astype(np.float64), side="right")
+    cnt = np.where(np.isnan(sim), 0, total - ub)
+    return (cnt / total).astype(sim.dtype)
+
+
+def _ndtr(x):
+    from math import erf, erfc, sqrt
+
+    def one(a):
+        v = a * (1.0 / sqrt(2.0))
+        z = abs(v)
+        if z < 1.0:
+            return 0.5 + 0.5 * erf(v)
+        y = 0.5 * erfc(z)
+        return 1.0 - y if v > 0 else y
+
+    return np.vectorize(one, otypes=[np.float64])(x)
+
+
+def dist_cdf(family, x, shape=None):
+    """CDF of the standardised variable x for the closed-form families of find_dist's 'common10' list."""
+    x = np.asarray(x, dtype=np.float64)
+    with np.errstate(all="ignore"):
+        if family == "norm":
+            c, lower, upper = _ndtr(x), -np.inf, np.inf
+        elif family == "lognorm":
+            c, lower, upper = _ndtr(np.log(np.where(x > 0, x, 1.0)) / shape), 0.0, np.inf
+        elif family == "cauchy":
+            c, lower, upper = np.arctan2(1.0, -x) / np.pi, -np.inf, np.inf
+        elif family == "expon":
+            c, lower, upper = -np.expm1(-x), 0.0, np.inf
+        elif family == "rayleigh":
+            c, lower, upper = -np.expm1(-0.5 * x ** 2), 0.0, np.inf
+        elif family == "uniform":
+            c, lower, upper = x, 0.0, 1.0
+        elif family == "pareto":
+            c, lower, upper = 1 - np.where(x > 1, x, 1.0) ** (-shape), 1.0, np.inf
+        elif family == "exponpow":
+            c, lower, upper = -np.expm1(-np.expm1(np.where(x > 0, x, 0.0) ** shape)), 0.0, np.inf
+        else:
+            raise ValueError("no closed form restated for %r" % (family,))
+    out = np.where(x <= lower, 0.0, np.where(x >= upper, 1.0, c))
+    return np.where(np.isnan(x), np.nan, out)
+
+
+SHAPED = {"lognorm", "pareto", "exponpow"}
+
+
+def pval_dist(sim, family, params):
+    """1 - dist(*params).cdf(sim[i, j]) stored in sim's dtype (find_pval.py:114-128); params = shapes, loc, scale."""
+    sim = np.asarray(sim)
+    params = tuple(float(p) for p in params)
+    shape = params[0] if family in SHAPED else None
+    loc, scale = params[-2], params[-1]
+    valid = scale > 0 and (shape is None or shape > 0)
+    x = (sim.astype(np.float64) - loc) / scale
+    c = dist_cdf(family, x, shape) if valid else np.full(sim.shape, np.nan)
+    return (1 - c).astype(sim.dtype)

@@ -73,6 +73,11 @@ SIGNATURES = {
     "skr_pearson_k_padded": (_i64, [_i64]),
     "skr_pearson_prepare": (_int, [_vp, _int, _i64, _i64, _i64, _int, _vp, _vp, _vp, _vp]),
     "skr_pearson_gemm": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _dbl, _vp, _int, _i64, _int, _vp]),
+    "skr_pval_empirical": (_int, [_vp, _int, _i64, _i64, _i64, _vp, _int, _i64, _vp, _i64, _vp]),
+    "skr_pval_dist": (_int, [_vp, _int, _i64, _i64, _i64, _int, _dbl, _dbl, _dbl, _vp, _i64, _vp]),
+    "skr_triu_count": (_i64, [_i64]),
+    "skr_triu_extract": (_int, [_vp, _int, _i64, _i64, _vp, _vp]),
+    "skr_pearson_pairs": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _dbl, _vp, _vp]),
     "skr_host_alloc": (_int, [_sz, ctypes.POINTER(_vp)]),
     "skr_host_free": (None, [_vp]),
     "skr_host_pool_trim": (None, []),
