@@ -472,3 +472,49 @@ def test_fast_division_path_is_bit_identical():
         assert np.array_equal(outs[0], outs[1])
         exp, _, _ = c_oracle.normalise(raw, mean, std, "Log2.none")
         assert np.array_equal(outs[0], exp)
+
+
+def test_batch_kernel_matches_team_kernel(monkeypatch):
+    """k = 6 runs count_batch_kernel by default; SEEKR_B200_COUNT_KERNEL=warp selects the team-per-record kernel.
+    Both must give the same bits for every epilogue flavour, on a set with N / lower case / homopolymers /
+    records shorter than k / a 70 kb record, and record counts that are not a multiple of the batch size."""
+    import torch
+
+    k = 6
+    for m in (1, 7, 8, 9, 203):
+        seqs = synth.seq_strings(max(m, 8), seed=100 + m, stress=True, lo=30, hi=4000)[:m]
+        seqs = [s for s in seqs if len(s) != k - 1]
+        packed = PackedFasta.from_sequences(seqs, pinned=True)
+        raw = c_oracle.raw_counts(seqs, k)
+        mean = (raw.mean(axis=0) + 0.01).astype(np.float32)
+        std = (raw.std(axis=0) + 0.25).astype(np.float32)
+        outs = {}
+        for kernel in ("batch", "warp"):
+            if kernel == "warp":
+                monkeypatch.setenv("SEEKR_B200_COUNT_KERNEL", "warp")
+            else:
+                monkeypatch.delenv("SEEKR_B200_COUNT_KERNEL", raising=False)
+            res = []
+            for mode in ("Log2.none", "Log2.pre", "Log2.post"):
+                for vec_dtype, fast in ((None, True), (np.float32, True), (np.float32, False), (np.float64, True)):
+                    eng = CountEngine(k, mode)
+                    eng.fast_division = fast
+                    dpk = eng.upload(packed)
+                    mv = sv = None
+                    if vec_dtype is not None:
+                        mv = DeviceVector.from_host(mean.astype(vec_dtype), 4 ** k)
+                        sv = DeviceVector.from_host(std.astype(vec_dtype), 4 ** k)
+                    out, _, _ = eng.run(dpk, mv if mv is not None else False, sv if sv is not None else False)
+                    torch.cuda.synchronize()
+                    res.append(out.cpu().numpy().copy())
+            # deferred organisation (column minima + fused post) exercises colmin / no_store / post_cell
+            eng = CountEngine(k, "Log2.post")
+            eng.deferred = True
+            dpk = eng.upload(packed)
+            out, _, _ = eng.run(dpk, DeviceVector.from_host(mean, 4 ** k), DeviceVector.from_host(std, 4 ** k))
+            torch.cuda.synchronize()
+            res.append(out.cpu().numpy().copy())
+            outs[kernel] = res
+        for a, b in zip(outs["batch"], outs["warp"]):
+            assert np.array_equal(a, b, equal_nan=True), m
+        assert np.array_equal(outs["batch"][0], raw)
