@@ -6,8 +6,9 @@
 
 Workload (BASELINE.json configs[1]): synthetic GENCODE-lncRNA-shaped set, 50 000 transcripts per GPU
 (lognormal length 500 bp - 20 kb, seed 50000 + rank), k = 6.  One step =
-    A. norm_vectors   counts -> order-exact column mean/std -> fused normalise -> Log2.post
-                      (BasicCounter(fasta, k=6).get_counts(), what seekr_norm_vectors runs)
+    A. norm_vectors   counts -> order-exact column mean/std (BasicCounter(fasta, k=6).get_norm_vectors(), what
+                      seekr_norm_vectors runs: the vectors are its only output, so the final normalise and
+                      Log2.post passes over the matrix are not executed)
     B. count + norm   counts with the mean/std vectors of A, Log2.post  (seekr_kmer_counts -mv -sv): the count
                       kernel with fused -mean, /std and running minimum, then the Log2.post pass
     C. Pearson        the normalised matrix of B against the reference set (rank 0's matrix), m x n, K = 4096
@@ -273,7 +274,7 @@ def run_ours(args):
         e = [ev() for _ in range(8)]
         # ---- A: norm_vectors --------------------------------------------------------------------
         e[0].record()
-        _, mean_vec, std_vec = eng_vec.run(dpk, True, True, out=out_a, reducer=reducer)
+        _, mean_vec, std_vec = eng_vec.run(dpk, True, True, out=out_a, reducer=reducer, vectors_only=True)
         vectors["mean"], vectors["std"] = mean_vec, std_vec
         e[1].record()
         # ---- B: count + normalise with the vectors, Log2.post ------------------------------------

@@ -131,7 +131,7 @@ def console_pearson(argv=None):
 def _run_norm_vectors(fasta, mean_vector, std_vector, log2, kmer):
     # console_scripts.py:659-663
     counter = BasicCounter(fasta, k=int(kmer), log2=log2)
-    counter.get_counts()
+    counter.get_norm_vectors()  # get_counts() minus the passes that only produce the discarded matrix
     np.save(mean_vector, counter.mean)
     np.save(std_vector, counter.std)
 

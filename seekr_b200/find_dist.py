@@ -117,7 +117,7 @@ def find_dist(inputseq='default', k_mer=4, log2='Log2.post', models='common10', 
 
     # normalisation vectors of the background set, saved where the reference saves them (find_dist.py:141-147)
     bkg_norm_counter = BasicCounter(inputseq, log2=log2, k=k_mer, silent=True)
-    bkg_norm_counter.get_counts()
+    bkg_norm_counter.get_norm_vectors()
     mean_path = f'bkg_mean_{k_mer}mers.npy'
     std_path = f'bkg_std_{k_mer}mers.npy'
     np.save(mean_path, bkg_norm_counter.mean)

@@ -275,8 +275,13 @@ class CountEngine:
         _lib.check(self.lib.skr_log2_norm(device.ptr(a), m, cols, a.stride(0), device.stream_ptr(self.stream)))
 
     # -- the whole tail of get_counts() (kmer_counts.py:199-209) ----------------------------------
-    def run(self, dpk, mean, std, out=None, reducer=None):
-        """mean/std: False, True, or DeviceVector.  Returns (out, mean_vec, std_vec, nan_checked).
+    def run(self, dpk, mean, std, out=None, reducer=None, vectors_only=False):
+        """mean/std: False, True, or DeviceVector.  Returns (out, mean_vec, std_vec).
+
+        ``vectors_only`` (with mean=True and/or std=True) stops once the vectors exist: the final normalise and
+        Log2.post passes over the matrix are what seekr_norm_vectors throws away (console_scripts.py:659-663 only
+        saves counter.mean and counter.std).  ``self.vector_nan`` then tells whether the standardised matrix would
+        have held a NaN (a zero / non-finite std or a non-finite mean), i.e. whether the reference warns.
 
         ``reducer`` (optional) supplies the cross-rank pieces of a sharded run: an object with
         ``col_stat(engine, kind, a, vec, vec2, finish)`` -> fp32 device vector of the finished statistic
@@ -323,7 +328,7 @@ class CountEngine:
             # fused pass writes fl(fl(x - mean) / std) at the end
             self.count(dpk, out)
             stat = reducer.col_stat if reducer else self._local_col_stat
-            flags = device.empty(2, torch.int32)
+            flags = device.zeros(2, torch.int32)
             if mean is True:
                 mean_vec = DeviceVector(stat(self, _lib.COLPASS_SUM, out, None, None, "mean", flags[0:1]), False,
                                         flag=flags[0:1])
@@ -335,6 +340,10 @@ class CountEngine:
                     arrmean = stat(self, _lib.COLPASS_SUM, out, None, None, "mean")
                 std_vec = DeviceVector(stat(self, _lib.COLPASS_SQDEV, out, mean_vec, arrmean, "std", flags[1:2]), False,
                                        flag=flags[1:2])
+            if vectors_only:
+                bits = flags.cpu().numpy()
+                self.vector_nan = bool((mean is True and bits[0] & 1) or (std is True and bits[1] & 3))
+                return out, mean_vec, std_vec
             self.normalize(out, mean_vec, std_vec, track_min=True)
             min_valid = True
         if need_min:
@@ -596,6 +605,34 @@ class BasicCounter:
         if bar is not None:
             bar.update(packed.m)
             bar.close()
+
+    def get_norm_vectors(self):
+        """mean / std vectors of this FASTA file without the final matrix: what seekr_norm_vectors needs
+        (console_scripts.py:659-663 runs get_counts() and keeps only .mean and .std).  Same vectors, same
+        NaN warning as get_counts(); .counts is left untouched."""
+        device.require_cuda()
+        if not (self.mean is True and self.std is True):
+            self.get_counts()  # a supplied vector: nothing to skip that is worth a second code path
+            return self.mean, self.std
+        packed = self._get_packed()
+        cols = self.alpha_len ** self.k
+        lengths = packed.lengths
+        if lengths.size and np.any(lengths.astype(np.int64) - self.k + 1 == 0):
+            raise ZeroDivisionError("division by zero")
+        if not 1 <= self.k <= 8:
+            raise NotImplementedError("seekr_b200 counts k-mers for 1 <= k <= 8, got k=%r" % (self.k,))
+        if packed.m == 0:
+            self.get_counts()
+            return self.mean, self.std
+        engine = CountEngine(self.k, self.log2)
+        mean = self.mean if isinstance(self.mean, bool) else DeviceVector.from_host(self.mean, cols)
+        std = self.std if isinstance(self.std, bool) else DeviceVector.from_host(self.std, cols)
+        _, mean_vec, std_vec = engine.run(engine.upload(packed), mean, std, vectors_only=True)
+        self.mean = device.to_host(mean_vec.t, pinned=False)
+        self.std = device.to_host(std_vec.t, pinned=False)
+        if engine.vector_nan:
+            print(_NAN_WARNING)
+        return self.mean, self.std
 
     def save(self, names=None):
         """Saves the counts appropriately based on current settings (kmer_counts.py:211-241):

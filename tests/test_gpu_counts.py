@@ -518,3 +518,29 @@ def test_batch_kernel_matches_team_kernel(monkeypatch):
         for a, b in zip(outs["batch"], outs["warp"]):
             assert np.array_equal(a, b, equal_nan=True), m
         assert np.array_equal(outs["batch"][0], raw)
+
+
+@pytest.mark.parametrize("mode", ["Log2.post", "Log2.pre", "Log2.none"])
+def test_norm_vectors_fast_path_equals_get_counts(mode, tmp_path, capsys):
+    """seekr_norm_vectors only keeps .mean / .std (console_scripts.py:659-663): get_norm_vectors() skips the
+    final matrix passes and must give the same vectors (bit for bit) and the same NaN warning."""
+    path = golden("medium.fa")
+    full = BasicCounter(path, k=4, log2=mode, silent=True)
+    full.get_counts()
+    fast = BasicCounter(path, k=4, log2=mode, silent=True)
+    mean, std = fast.get_norm_vectors()
+    assert np.array_equal(mean, full.mean) and np.array_equal(std, full.std)
+    assert fast.counts is None
+    capsys.readouterr()
+    # a constant column (k=1 on a homopolymer set) has std 0: both paths warn
+    homo = str(tmp_path / "homo.fa")
+    with open(homo, "w") as handle:
+        handle.write(">a\nAAAAAAAA\n>b\nAAAAAAAAAAAA\n")
+    a = BasicCounter(homo, k=1, log2=mode, silent=True)
+    a.get_counts()
+    warned_full = "np.nan" in capsys.readouterr().out
+    b = BasicCounter(homo, k=1, log2=mode, silent=True)
+    b.get_norm_vectors()
+    warned_fast = "np.nan" in capsys.readouterr().out
+    assert warned_full and warned_fast
+    assert np.array_equal(a.std, b.std) and np.array_equal(a.mean, b.mean)
