@@ -136,6 +136,17 @@ __device__ __forceinline__ float div_by_rcp(float a, float b, float y) {
     return __fmaf_rn(r, y, q);
 }
 
+// two lanes of (x - mean) / std at once: nm = -mean, nb = -std, y = RN(1/std); the same operations as
+// __fsub_rn + div_by_rcp on each lane (x + (-m) is x - m; packed fp32x2 instructions round to nearest, no ftz)
+__device__ __forceinline__ uint64_t sub_div_by_rcp2(uint64_t x, uint64_t nm, uint64_t nb, uint64_t y) {
+    const uint64_t a = skr::f2_add(x, nm);
+    uint64_t q = skr::f2_mul(a, y);
+    uint64_t r = skr::f2_fma(nb, q, a);
+    q = skr::f2_fma(r, y, q);
+    r = skr::f2_fma(nb, q, a);
+    return skr::f2_fma(r, y, q);
+}
+
 // counts of 4 consecutive bins -> the reference's float32 values (per-kb chain, log2.pre, -mean, /std).
 // packed = the two histogram words (four 16-bit counts) when every count fits the table.
 template <bool kVecF64>
@@ -590,6 +601,10 @@ __global__ void __launch_bounds__(BatchCfg<K>::kThreads, 2) count_batch_kernel(c
                 if (p.mean) mv[j] = __ldg(reinterpret_cast<const float4*>(p.mean) + q);
                 if (p.std_) sv[j] = __ldg(reinterpret_cast<const float4*>(p.std_) + q);
                 if (p.std_ && p.rstd) yv[j] = __ldg(reinterpret_cast<const float4*>(p.rstd) + q);
+                if constexpr (kMode == kBatchFast) {
+                    mv[j] = make_float4(-mv[j].x, -mv[j].y, -mv[j].z, -mv[j].w);
+                    sv[j] = make_float4(-sv[j].x, -sv[j].y, -sv[j].z, -sv[j].w);
+                }
             }
         }
         uint4* h4 = reinterpret_cast<uint4*>(smem_b + (hist_addr - raw_addr) / 4);
@@ -733,10 +748,14 @@ __global__ void __launch_bounds__(BatchCfg<K>::kThreads, 2) count_batch_kernel(c
                             x[e] = c4[e] < kTab ? lds_f32(tab_addr + c4[e] * 4) : slow_bin_value(inc, c4[e], p.log2_pre);
                     }
                     if constexpr (kMode == kBatchFast) {
-                        x[0] = div_by_rcp(__fsub_rn(x[0], mv[j].x), sv[j].x, yv[j].x);
-                        x[1] = div_by_rcp(__fsub_rn(x[1], mv[j].y), sv[j].y, yv[j].y);
-                        x[2] = div_by_rcp(__fsub_rn(x[2], mv[j].z), sv[j].z, yv[j].z);
-                        x[3] = div_by_rcp(__fsub_rn(x[3], mv[j].w), sv[j].w, yv[j].w);
+                        // mv / sv hold -mean / -std in this flavour (negated once, after the load); FADD2 / FMUL2 /
+                        // FFMA2 do two columns per issue slot
+                        const uint64_t z0 = sub_div_by_rcp2(skr::f2_pack(x[0], x[1]), skr::f2_pack(mv[j].x, mv[j].y),
+                                                            skr::f2_pack(sv[j].x, sv[j].y), skr::f2_pack(yv[j].x, yv[j].y));
+                        const uint64_t z1 = sub_div_by_rcp2(skr::f2_pack(x[2], x[3]), skr::f2_pack(mv[j].z, mv[j].w),
+                                                            skr::f2_pack(sv[j].z, sv[j].w), skr::f2_pack(yv[j].z, yv[j].w));
+                        skr::f2_unpack(z0, x[0], x[1]);
+                        skr::f2_unpack(z1, x[2], x[3]);
                     } else if constexpr (kMode == kBatchAny) {
                         if constexpr (kVecF64) {
                             if (p.mean) {
