@@ -860,44 +860,31 @@ int dispatch_batch(const CountParams& wp, int sms, cudaStream_t stream) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// per-device scratch: work counters (a ring, so launches on different streams do not share one)
-// and the per-CTA spill rows
+// per-device scratch: work counters (a ring, so launches on different streams do not share one).
+// The per-CTA spill rows and the long-record list are stream-ordered allocations of each launch
+// (cudaMallocAsync / cudaFreeAsync), so concurrent launches on different streams never share them;
+// the default memory pool is told to keep its memory across synchronisations.
 // ---------------------------------------------------------------------------------------------
 struct DeviceScratch {
     unsigned int* counters = nullptr;
     int next_counter = 0;
-    uint32_t* spill = nullptr;
-    size_t spill_bytes = 0;
-    uint32_t* long_list = nullptr;
-    size_t long_cap = 0;
-    int num_sms = 0;
 };
 constexpr int kCounterRing = 1024;  // 4 counters per launch
 std::mutex g_scratch_mu;
 std::unordered_map<int, DeviceScratch> g_scratch;
 
-int get_scratch(int dev, size_t spill_bytes, size_t long_cap, DeviceScratch** out) {
+int next_counters(int dev, unsigned int** out) {
     std::lock_guard<std::mutex> lock(g_scratch_mu);
     DeviceScratch& s = g_scratch[dev];
-    if (s.long_cap < long_cap) {
-        if (s.long_list) SKR_CUDA_CHECK(cudaFree(s.long_list));
-        s.long_list = nullptr;
-        s.long_cap = 0;
-        SKR_CUDA_CHECK(cudaMalloc(&s.long_list, long_cap * sizeof(uint32_t)));
-        s.long_cap = long_cap;
-    }
     if (!s.counters) {
         SKR_CUDA_CHECK(cudaMalloc(&s.counters, kCounterRing * sizeof(unsigned int)));
-        SKR_CUDA_CHECK(cudaDeviceGetAttribute(&s.num_sms, cudaDevAttrMultiProcessorCount, dev));
+        cudaMemPool_t pool;
+        SKR_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev));
+        uint64_t keep = UINT64_MAX;
+        SKR_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     }
-    if (s.spill_bytes < spill_bytes) {
-        if (s.spill) SKR_CUDA_CHECK(cudaFree(s.spill));  // synchronises: older launches are done with it
-        s.spill = nullptr;
-        s.spill_bytes = 0;
-        SKR_CUDA_CHECK(cudaMalloc(&s.spill, spill_bytes));
-        s.spill_bytes = spill_bytes;
-    }
-    *out = &s;
+    *out = s.counters + s.next_counter;
+    s.next_counter = (s.next_counter + 4) % kCounterRing;
     return SKR_OK;
 }
 
@@ -916,17 +903,12 @@ int launch_count(CountParams p, cudaStream_t stream) {
     // one warp on a list which the CTA kernel then drains
     constexpr bool kUseWarp = K <= 6 && sizeof(OutT) == 4;
     if (kUseWarp && p.m > 0xFFFFFFFFll) return skr::fail(SKR_ERR_ARG, "skr_count: more than 2^32 records");
-    DeviceScratch* sc = nullptr;
-    int rc = get_scratch(dev, (size_t)sms * per_sm * Cfg::kBins * 4, kUseWarp ? (size_t)p.m : 0, &sc);
+    unsigned int* ctr = nullptr;
+    int rc = next_counters(dev, &ctr);
     if (rc != SKR_OK) return rc;
-    unsigned int* ctr;
-    {
-        std::lock_guard<std::mutex> lock(g_scratch_mu);
-        ctr = sc->counters + sc->next_counter;
-        sc->next_counter = (sc->next_counter + 4) % kCounterRing;
-    }
     SKR_CUDA_CHECK(cudaMemsetAsync(ctr, 0, 4 * sizeof(unsigned int), stream));
-    p.spill = sc->spill;
+    uint32_t* long_list = nullptr;
+    if (kUseWarp) SKR_CUDA_CHECK(cudaMallocAsync(&long_list, (size_t)p.m * sizeof(uint32_t), stream));
     long long grid = (long long)sms * per_sm;
     if constexpr (kUseWarp) {
         using W = WarpCfg<K>;
@@ -944,7 +926,7 @@ int launch_count(CountParams p, cudaStream_t stream) {
         if (wgrid > need) wgrid = need;
         CountParams wp = p;
         wp.work_counter = ctr;
-        wp.long_list = sc->long_list;
+        wp.long_list = long_list;
         wp.long_count = ctr + 1;
         bool batch = false;
         if constexpr (K == 6) {
@@ -959,7 +941,7 @@ int launch_count(CountParams p, cudaStream_t stream) {
         SKR_LAUNCH_CHECK();
         // long records (rare): the CTA kernel reads the list length on the device
         p.work_counter = ctr + 2;
-        p.long_list = sc->long_list;
+        p.long_list = long_list;
         p.long_count = ctr + 1;
         if (grid > sms) grid = sms;
     } else {
@@ -968,8 +950,11 @@ int launch_count(CountParams p, cudaStream_t stream) {
         p.long_count = nullptr;
         if (grid > p.m) grid = p.m;
     }
+    SKR_CUDA_CHECK(cudaMallocAsync(&p.spill, (size_t)grid * Cfg::kBins * sizeof(uint32_t), stream));
     kern<<<(unsigned)grid, Cfg::kThreads, Cfg::kSmem, stream>>>(p);
     SKR_LAUNCH_CHECK();
+    SKR_CUDA_CHECK(cudaFreeAsync(p.spill, stream));
+    if (long_list) SKR_CUDA_CHECK(cudaFreeAsync(long_list, stream));
     return SKR_OK;
 }
 

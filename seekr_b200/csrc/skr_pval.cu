@@ -202,11 +202,6 @@ __global__ void __launch_bounds__(256) pearson_pairs_kernel(const __half* __rest
     }
 }
 
-struct PvalScratch {
-    uint32_t* lut = nullptr;
-};
-PvalScratch g_pval[64];
-
 int grid_for(long long total, int threads) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -236,12 +231,10 @@ extern "C" int skr_pval_empirical(const void* d_r, int r_is_f64, int64_t m, int6
     if (m <= 0 || n <= 0) return SKR_OK;
     if (!d_r || !d_p || !d_sorted_bg || N <= 0) return skr::fail(SKR_ERR_ARG, "skr_pval_empirical: bad argument");
     if (ld < n || ldp < n) return skr::fail(SKR_ERR_ARG, "skr_pval_empirical: leading dimension smaller than n");
-    int dev = 0;
-    SKR_CUDA_CHECK(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64) return skr::fail(SKR_ERR_ARG, "skr_pval_empirical: device index out of range");
     if (N >= 0xFFFFFFFFll) return skr::fail(SKR_ERR_ARG, "skr_pval_empirical: more than 2^32 - 1 background values");
-    if (!g_pval[dev].lut) SKR_CUDA_CHECK(cudaMalloc(&g_pval[dev].lut, (size_t)(kBins + 1) * sizeof(uint32_t)));
-    uint32_t* lut = g_pval[dev].lut;
+    // the table is stream-ordered scratch: concurrent calls on other streams get their own
+    uint32_t* lut = nullptr;
+    SKR_CUDA_CHECK(cudaMallocAsync(&lut, (size_t)(kBins + 1) * sizeof(uint32_t), (cudaStream_t)stream));
     cudaStream_t s = (cudaStream_t)stream;
     const bool f32 = !r_is_f64 && !bg_is_f64;
     const int lut_blocks = (kBins + 1 + 255) / 256;
@@ -256,6 +249,7 @@ extern "C" int skr_pval_empirical(const void* d_r, int r_is_f64, int64_t m, int6
     else { if (bg_is_f64) SKR_PVAL_LAUNCH(float, double, double); else SKR_PVAL_LAUNCH(float, float, float); }
 #undef SKR_PVAL_LAUNCH
     SKR_LAUNCH_CHECK();
+    SKR_CUDA_CHECK(cudaFreeAsync(lut, s));
     return SKR_OK;
 }
 
