@@ -241,6 +241,25 @@ int skr_pearson_pairs(const uint16_t* d_a_hi, const uint16_t* d_a_lo, const floa
                       int64_t npairs, double alpha, float* d_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Collectives over NVLink peer memory (one process per GPU; SURVEY section 8e: the Log2.post minimum
+ * of kmer_counts.py:207-208 spans all row shards)
+ *
+ * skr_peer_alloc / open / close / free   an exchange buffer (cudaMalloc, zeroed) and its 64-byte CUDA IPC
+ *                      handle; a peer process maps it with skr_peer_open.
+ * skr_min_exchange     all-reduce of the minimum cell in ONE single-warp kernel: every rank stores its cell,
+ *                      tagged with `epoch`, into every peer's buffer (P2P stores) and reduces the `world` cells
+ *                      that arrive in its own.  d_peers[t] = rank t's buffer as mapped here (d_peers[rank] = own
+ *                      buffer), each 2 * world 64-bit words.  epoch starts at 1 and grows by 1 per call on every
+ *                      rank.  *d_err becomes 1 if a peer did not show up within 4 s.
+ * ------------------------------------------------------------------------------------------ */
+int skr_peer_alloc(size_t bytes, void** d_out, unsigned char* handle64);
+int skr_peer_open(const unsigned char* handle64, void** d_out);
+int skr_peer_close(void* d_ptr);
+int skr_peer_free(void* d_ptr);
+int skr_min_exchange(SkrMinCell* d_cell, void* const* d_peers, int world, int rank, uint64_t epoch, int* d_err,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Host <-> device plumbing used by the Python layer (thin wrappers; no reference counterpart)
  * ------------------------------------------------------------------------------------------ */
 int skr_host_alloc(size_t bytes, void** out); /* pinned host memory from the library's pool */

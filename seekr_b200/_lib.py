@@ -78,6 +78,11 @@ SIGNATURES = {
     "skr_triu_count": (_i64, [_i64]),
     "skr_triu_extract": (_int, [_vp, _int, _i64, _i64, _vp, _vp]),
     "skr_pearson_pairs": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _dbl, _vp, _vp]),
+    "skr_peer_alloc": (_int, [_sz, ctypes.POINTER(_vp), _vp]),
+    "skr_peer_open": (_int, [_vp, ctypes.POINTER(_vp)]),
+    "skr_peer_close": (_int, [_vp]),
+    "skr_peer_free": (_int, [_vp]),
+    "skr_min_exchange": (_int, [_vp, _vp, _int, _int, ctypes.c_uint64, _vp, _vp]),
     "skr_host_alloc": (_int, [_sz, ctypes.POINTER(_vp)]),
     "skr_host_free": (None, [_vp]),
     "skr_host_pool_trim": (None, []),

@@ -70,6 +70,67 @@ def allreduce_min_cell(cell_i64, group=None):
     return cell_i64
 
 
+class PeerMinExchange:
+    """All-reduce of the Log2.post minimum cell through NVLink peer memory (csrc/skr_peer.cu): every rank maps
+    every other rank's exchange buffer (CUDA IPC) once; an exchange is then ONE single-warp kernel per rank that
+    stores its cell into all peers and reduces the cells arriving in its own buffer."""
+
+    def __init__(self, group=None):
+        import ctypes
+
+        import numpy as np
+        import torch
+        import torch.distributed as dist
+
+        from . import _lib, device
+
+        self.lib = _lib.load()
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > 32:
+            raise ValueError("peer exchange handles up to 32 ranks")
+        own = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        _lib.check(self.lib.skr_peer_alloc(2 * self.world * 8, ctypes.byref(own), handle))
+        self._own = own
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self._opened = []
+        ptrs = []
+        for t in range(self.world):
+            if t == self.rank:
+                ptrs.append(own.value)
+                continue
+            mapped = ctypes.c_void_p()
+            buf = (ctypes.c_ubyte * 64).from_buffer_copy(handles[t])
+            _lib.check(self.lib.skr_peer_open(buf, ctypes.byref(mapped)))
+            self._opened.append(mapped)
+            ptrs.append(mapped.value)
+        self.table = device.to_device(np.asarray(ptrs, dtype=np.int64))
+        self.err = device.zeros(1, torch.int32)
+        self.epoch = 0
+        torch.cuda.synchronize()
+        dist.barrier(group=group)  # every buffer is mapped and zeroed before anybody stores into it
+
+    def exchange(self, engine):
+        from . import _lib, device
+
+        self.epoch += 1
+        _lib.check(self.lib.skr_min_exchange(device.ptr(engine.min_cell.t), device.ptr(self.table), self.world, self.rank,
+                                             self.epoch, device.ptr(self.err), device.stream_ptr(engine.stream)))
+
+    def check(self):
+        if int(self.err.item()):
+            raise RuntimeError("peer-memory minimum exchange timed out: a rank did not take part within 4 s")
+
+    def close(self):
+        for mapped in self._opened:
+            self.lib.skr_peer_close(mapped)
+        self._opened = []
+        if self._own is not None:
+            self.lib.skr_peer_free(self._own)
+            self._own = None
+
+
 class _Base:
     def __init__(self, group=None):
         import torch.distributed as dist
@@ -95,13 +156,34 @@ class _Base:
         self.dist.all_reduce(colmin, op=self.dist.ReduceOp.MIN, group=self.group)
 
     def min_allreduce(self, engine):
-        """Combine the per-rank Log2.post cells (uint32 pair on the device) across ranks."""
+        """Combine the per-rank Log2.post cells (uint32 pair on the device) across ranks.  On CUDA this is one
+        single-warp kernel over NVLink peer memory (PeerMinExchange); SEEKR_B200_MIN_EXCHANGE=nccl, or a box
+        without CUDA IPC between the ranks, takes the library all-reduce instead."""
+        import os
+
         import torch
 
         cell = engine.min_cell.t  # int32 storage of two uint32
+        if cell.is_cuda and os.environ.get("SEEKR_B200_MIN_EXCHANGE", "peer") != "nccl":
+            if getattr(self, "_peer", None) is None and not getattr(self, "_peer_failed", False):
+                try:
+                    self._peer = PeerMinExchange(self.group)
+                except Exception as exc:  # no IPC / no peer access: still a GPU collective, just not ours
+                    import warnings
+
+                    warnings.warn("peer-memory minimum exchange unavailable (%s); using the NCCL all-reduce" % (exc,))
+                    self._peer_failed = True
+            if getattr(self, "_peer", None) is not None:
+                self._peer.exchange(engine)
+                return
         as64 = cell.to(torch.int64) & 0xFFFFFFFF
         allreduce_min_cell(as64, self.group)
         cell.copy_(torch.where(as64 >= 2 ** 31, as64 - 2 ** 32, as64).to(torch.int32))
+
+    def check(self):
+        """Raise if a peer-memory exchange timed out (call where results reach the host anyway)."""
+        if getattr(self, "_peer", None) is not None:
+            self._peer.check()
 
 
 class AllReduceStats(_Base):

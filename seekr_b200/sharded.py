@@ -101,6 +101,7 @@ def get_counts(fasta, k=6, mean=True, std=True, log2="Log2.post", alphabet="AGTC
     out = device.empty((end - begin, cols), torch.float32)
     out, mean_vec, std_vec = engine.run(dpk, mean_arg, std_arg, out=out, reducer=reducer)
     local = device.to_host(out)
+    reducer.check()
     mean_h = device.to_host(mean_vec.t, pinned=False) if mean is True else mean
     std_h = device.to_host(std_vec.t, pinned=False) if std is True else std
     full = None

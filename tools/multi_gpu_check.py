@@ -55,6 +55,49 @@ def main():
         d = float(np.nanmax(np.abs(r_local - r_ref[vb:ve])))
         print("pearson row block vs 1 GPU: max abs diff %.2e" % d)
         ok &= d < 2e-6
+    # the peer-memory minimum exchange against the NCCL all-reduce, 200 epochs of random cells (some with NaN flags)
+    from seekr_b200 import parallel
+    from seekr_b200.kmer_counts import CountEngine
+
+    eng = CountEngine(k, "Log2.post")
+    peer, nccl = parallel.AllReduceStats(), parallel.AllReduceStats()
+    rng = np.random.default_rng(1000 + rank)
+    same = True
+    for it in range(200):
+        raw = np.array([rng.integers(0, 2 ** 32), 1 if rng.random() < 0.1 else 0], dtype=np.uint32).view(np.int32)
+        eng.min_cell.t.copy_(torch.from_numpy(raw.copy()).to("cuda"))
+        peer.min_allreduce(eng)
+        a = eng.min_cell.t.cpu().numpy().copy()
+        eng.min_cell.t.copy_(torch.from_numpy(raw.copy()).to("cuda"))
+        os.environ["SEEKR_B200_MIN_EXCHANGE"] = "nccl"
+        nccl.min_allreduce(eng)
+        os.environ.pop("SEEKR_B200_MIN_EXCHANGE")
+        b = eng.min_cell.t.cpu().numpy().copy()
+        same &= bool(a[1] == b[1] and (a[1] != 0 or a[0] == b[0]))
+    peer.check()
+    uses_peer = getattr(peer, "_peer", None) is not None
+    t = torch.tensor([1 if (same and uses_peer) else 0], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("peer-memory min exchange == NCCL all-reduce over 200 epochs (peer path active: %s): %s" % (uses_peer, bool(t.item())))
+        ok &= bool(t.item())
+    torch.cuda.synchronize()
+    t0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for name, red in (("peer", peer), ("nccl", nccl)):
+        if name == "nccl":
+            os.environ["SEEKR_B200_MIN_EXCHANGE"] = "nccl"
+        for _ in range(5):
+            red.min_allreduce(eng)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0[0].record()
+        for _ in range(50):
+            red.min_allreduce(eng)
+        t0[1].record()
+        torch.cuda.synchronize()
+        os.environ.pop("SEEKR_B200_MIN_EXCHANGE", None)
+        if rank == 0:
+            print("min all-reduce via %s: %.1f us per call" % (name, t0[0].elapsed_time(t0[1]) * 1e3 / 50))
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)
     dist.barrier()
