@@ -18,7 +18,7 @@
 //     Accumulator promotion.  The tensor core adds into its fp32 accumulator with truncation, so a
 //     long K loop drifts low by ~3.5e-8 per MMA (measured: 2.7e-5 on the diagonal at K = 4096, far
 //     outside the 1e-5 parity band, and growing with K).  The K loop is therefore cut into chunks of
-//     kChunkKb k-blocks: each chunk accumulates from zero into one of two TMEM buffers (2 x 256
+//     chunk_kb k-blocks: each chunk accumulates from zero into one of two TMEM buffers (2 x 256
 //     columns) and the epilogue warps drain the finished chunk with tcgen05.ld and add it, with
 //     round-to-nearest fp32 adds, to running sums they keep in registers (8 warps x 128 columns,
 //     register budget moved from the control warps with setmaxnreg) while the next chunk's MMAs run
@@ -146,7 +146,7 @@ constexpr int kBK = 64;         // fp16 elements per k-block = one 128-byte swiz
 constexpr int kUmmaK = 16;
 constexpr int kGemmThreads = 384;  // warps 0-3: control (TMA, MMA, TMEM alloc, spare); warps 4-11: epilogue
 constexpr int kEpiThreads = 256;
-constexpr int kChunkKb = 4;        // k-blocks accumulated in TMEM before promotion to the fp32 register sums
+constexpr int kChunkKbDefault = 2;        // k-blocks accumulated in TMEM before promotion to the fp32 register sums
 constexpr int kCtrlRegs = 56;
 constexpr int kEpiRegs = 224;
 constexpr int kTmemCols = 512;  // two 256-column accumulators
@@ -165,6 +165,7 @@ struct GemmCfg {
 struct GemmParams {
     long long m, n;            // valid rows of A / B
     int num_kb;                // k-blocks of 64
+    int chunk_kb;              // k-blocks accumulated in TMEM before promotion (see the header comment)
     int tiles_m, tiles_n;
     float alpha;
     const float* a_scale;
@@ -398,11 +399,11 @@ pearson_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-                for (int kb0 = 0; kb0 < p.num_kb; kb0 += kChunkKb) {
+                for (int kb0 = 0; kb0 < p.num_kb; kb0 += p.chunk_kb) {
                     skr::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kBN);
-                    const int kb1 = min(p.num_kb, kb0 + kChunkKb);
+                    const int kb1 = min(p.num_kb, kb0 + p.chunk_kb);
                     for (int kb = kb0; kb < kb1; ++kb) {
                         skr::mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
@@ -440,7 +441,7 @@ pearson_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
             float sum[128];
 #pragma unroll
             for (int i = 0; i < 128; ++i) sum[i] = 0.0f;
-            for (int kb0 = 0; kb0 < p.num_kb; kb0 += kChunkKb) {
+            for (int kb0 = 0; kb0 < p.num_kb; kb0 += p.chunk_kb) {
                 skr::mbar_wait(&tmem_full_bar[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kBN + half * 128);
@@ -646,6 +647,16 @@ extern "C" int skr_pearson_gemm(const uint16_t* d_a_hi, const uint16_t* d_a_lo, 
     p.m = m;
     p.n = n;
     p.num_kb = (int)(kp / kBK);
+    // Promotion interval.  Two error sources pull in opposite directions on count-like rows (a few big z-scores
+    // among thousands of small ones): inside a chunk the tensor core truncates every addend to the accumulator's
+    // ulp, so small products that share a chunk with a large one lose low bits (grows with the chunk); across
+    // chunks the fp32 running sum, once it holds the large product, rounds each of the many similar small chunk
+    // values the same way (grows with the number of chunks).  Measured max |r - binary64| over sparsity 0.8 ... 0.01
+    // and K = 4096 ... 65 536 (tools/pearson_error_sweep.py, profiles/r01_pearson_error_sweep.txt):
+    // 1 k-block 1.4e-5, 2 k-blocks 7.4e-6, 4 k-blocks 8.2e-6 -- hence 2.
+    p.chunk_kb = kChunkKbDefault;
+    if (const char* env = getenv("SEEKR_B200_GEMM_CHUNK"))  // experiment knob
+        if (atoi(env) >= 1 && atoi(env) <= 64) p.chunk_kb = atoi(env);
     p.alpha = (float)alpha;
     p.a_scale = d_a_scale;
     p.b_scale = d_b_scale;

@@ -151,3 +151,42 @@ def test_pearson_k7_columns():
     got = pearson(q, r)
     assert got.shape == (384, 200)
     assert np.abs(got - po.pearson_f64(q, r)).max() < TOL
+
+
+def test_pearson_k8_columns():
+    """BASELINE config 4 at its widest: K = 4^8 = 65 536 columns (1024 k-blocks, 256 promoted TMEM chunks per tile)."""
+    rng = np.random.default_rng(23)
+    q = (rng.poisson(0.05, size=(200, 65536)) * rng.uniform(0.1, 3, size=(200, 1))).astype(np.float32)
+    got = pearson(q, q)
+    want = po.pearson_f64(q, q)
+    assert got.shape == (200, 200) and got.dtype == np.float32
+    assert np.abs(got - want).max() < TOL
+    print("K=65536 max |diag - 1| = %.2e, max |r - f64| = %.2e" % (np.abs(np.diag(got) - 1).max(), np.abs(got - want).max()))
+
+
+@pytest.mark.parametrize("k", [7, 8])
+def test_wide_k_pipeline_matches_oracle(k):
+    """config 4, k = 7 and 8 end to end: counts (CTA kernel with spill rows) -> own mean/std -> Log2.post -> Pearson."""
+    from oracle import c_oracle
+    from seekr_b200 import synth
+    from seekr_b200.kmer_counts import BasicCounter
+
+    seqs = synth.seq_strings(48, seed=300 + k, lo=400, hi=9000)
+    raw = c_oracle.raw_counts(seqs, k)
+    # (a) self-normalised, no log: unseen k-mers have std 0 -> NaN columns, exactly as in the reference
+    exp, mean, std = c_oracle.normalise(raw, True, True, "Log2.none")
+    counter = BasicCounter(k=k, log2="Log2.none", silent=True)
+    counter.seqs = seqs
+    counter.get_counts()
+    assert np.array_equal(counter.mean, mean) and np.array_equal(counter.std, std, equal_nan=True)
+    assert np.array_equal(counter.counts, exp, equal_nan=True)
+    assert k == 7 or np.isnan(exp).any()
+    # (b) supplied vectors + Log2.post, then Pearson of the normalised matrix with itself
+    vm = raw.mean(axis=0).astype(np.float32)
+    vs = (raw.std(axis=0) + 0.25).astype(np.float32)
+    exp, _, _ = c_oracle.normalise(raw, vm, vs, "Log2.post")
+    counter = BasicCounter(k=k, mean=vm, std=vs, log2="Log2.post", silent=True)
+    counter.seqs = seqs
+    counter.get_counts()
+    assert np.abs(counter.counts - exp).max() < TOL
+    assert np.abs(pearson(counter.counts, counter.counts) - po.pearson_f64(exp, exp)).max() < TOL
