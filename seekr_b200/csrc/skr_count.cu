@@ -566,11 +566,12 @@ __device__ __forceinline__ void sts_zero_v2(uint32_t addr) {
 //                      kBatchAny    everything decided at run time.
 enum { kBatchAny = 0, kBatchPlain = 1, kBatchFast = 2 };
 
-template <int K, bool kVecF64, int kMode, bool kMin>
+template <int K, bool kVecF64, int kMode, bool kMin, bool kColmin = false>
 __global__ void __launch_bounds__(BatchCfg<K>::kThreads, 2) count_batch_kernel(const CountParams p) {
     using Cfg = BatchCfg<K>;
     constexpr int kB = Cfg::kB, kW = Cfg::kWorkers, kQ = Cfg::kQ;
     static_assert(!(kVecF64 && kMode != kBatchAny), "binary64 vectors take the generic epilogue");
+    static_assert(!kColmin || kMode == kBatchPlain, "kColmin: column minima of the plain values (kBatchAny decides at run time)");
     extern __shared__ __align__(16) uint32_t smem_b[];
     __shared__ BatchMeta<kB> s_meta[2];
     const int tid = threadIdx.x, lane = tid & 31;
@@ -792,6 +793,10 @@ __global__ void __launch_bounds__(BatchCfg<K>::kThreads, 2) count_batch_kernel(c
                             for (int e = 0; e < 4; ++e) x[e] = log2f(__fadd_rn(__fadd_rn(x[e], shift), 1.0f));
                         }
                     }
+                    if constexpr (kColmin) {  // plain values are >= 0: float bits order like unsigned integers
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) cmin[j][e] = min(cmin[j][e], __float_as_uint(x[e]));
+                    }
                     if constexpr (kMin) {
 #pragma unroll
                         for (int e = 0; e < 4; ++e) skr::min_update(x[e], tmin, tnan);
@@ -805,7 +810,7 @@ __global__ void __launch_bounds__(BatchCfg<K>::kThreads, 2) count_batch_kernel(c
     }
 
     if (worker) {
-        if (kMode == kBatchAny && p.colmin) {
+        if (kColmin || (kMode == kBatchAny && p.colmin)) {
 #pragma unroll
             for (int j = 0; j < kQ; ++j)
 #pragma unroll
@@ -829,10 +834,10 @@ __global__ void __launch_bounds__(BatchCfg<K>::kThreads, 2) count_batch_kernel(c
     }
 }
 
-template <int K, bool kVecF64, int kMode, bool kMin>
+template <int K, bool kVecF64, int kMode, bool kMin, bool kColmin = false>
 int launch_batch(const CountParams& wp, int sms, cudaStream_t stream) {
     using B = BatchCfg<K>;
-    auto bkern = count_batch_kernel<K, kVecF64, kMode, kMin>;
+    auto bkern = count_batch_kernel<K, kVecF64, kMode, kMin, kColmin>;
     SKR_CUDA_CHECK(cudaFuncSetAttribute(bkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B::kSmem));
     int bper_sm = 0;
     SKR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bper_sm, bkern, B::kThreads, B::kSmem));
@@ -846,10 +851,12 @@ int launch_batch(const CountParams& wp, int sms, cudaStream_t stream) {
 
 template <int K, bool kVecF64>
 int dispatch_batch(const CountParams& wp, int sms, cudaStream_t stream) {
-    const bool plain = !wp.mean && !wp.std_ && !wp.colmin && !wp.post_cell && !wp.no_store;
+    const bool plain = !wp.mean && !wp.std_ && !wp.post_cell && !wp.no_store;
     const bool fast = !kVecF64 && wp.mean && wp.std_ && wp.rstd && !wp.colmin && !wp.post_cell && !wp.no_store;
     const bool mn = wp.min_cell != nullptr;
     if constexpr (!kVecF64) {
+        if (plain && wp.colmin) return mn ? launch_batch<K, false, kBatchPlain, true, true>(wp, sms, stream)
+                                          : launch_batch<K, false, kBatchPlain, false, true>(wp, sms, stream);
         if (plain) return mn ? launch_batch<K, false, kBatchPlain, true>(wp, sms, stream)
                              : launch_batch<K, false, kBatchPlain, false>(wp, sms, stream);
         if (fast) return mn ? launch_batch<K, false, kBatchFast, true>(wp, sms, stream)

@@ -145,6 +145,7 @@ class CountEngine:
         # two-pass Log2.post (column minima first, then count + normalise + post in one epilogue): measured
         # equal to fused count + post pass on B200 (both ~0.6 ms for 50k transcripts, instruction-bound), so off
         self.deferred = False
+        self.fused_tail = True   # self-normalised Log2.post: column minima from the count kernel, one tail pass
 
     # -- building blocks ------------------------------------------------------------------------
     def upload(self, packed):
@@ -326,7 +327,16 @@ class CountEngine:
             # raw counts per kb (log2'd first for Log2.pre); the statistics passes only read this matrix,
             # the centred values they need are recomputed with the reference's single rounding, and one
             # fused pass writes fl(fl(x - mean) / std) at the end
-            self.count(dpk, out)
+            # Log2.post: the count kernel also keeps the per-column minima of the raw values, from which the
+            # matrix-wide minimum of the z-scores follows once the vectors exist (monotone roundings), so that the
+            # tail is ONE pass (-mean, /std, +|min|, +1, log2) instead of a normalise pass and a Log2.post pass
+            fused_tail = need_min and not vectors_only and self.fused_tail
+            colmin = None
+            if fused_tail:
+                colmin = device.empty(self.cols, torch.int32)
+                self.count_colmin(dpk, colmin, out=out)
+            else:
+                self.count(dpk, out)
             stat = reducer.col_stat if reducer else self._local_col_stat
             flags = device.zeros(2, torch.int32)
             if mean is True:
@@ -344,6 +354,28 @@ class CountEngine:
                 bits = flags.cpu().numpy()
                 self.vector_nan = bool((mean is True and bits[0] & 1) or (std is True and bits[1] & 3))
                 return out, mean_vec, std_vec
+            if fused_tail:
+                bits = flags.cpu().numpy()  # the one host decision of this path (a few microseconds of sync)
+                ok_mean = mean_vec is None or (mean is True and not bits[0] & 1) or (mean is not True and mean_vec.finite)
+                ok_std = std_vec is None or (std is True and not bits[1] & 3) or \
+                    (std is not True and std_vec.finite and std_vec.positive)
+                if ok_mean and ok_std and (mean_vec is not None or std_vec is not None):
+                    mv, sv = mean_vec, std_vec
+                    if mv is not None and sv is not None and mv.is_f64 != sv.is_f64:
+                        mv, sv = mv.as_f64(), sv.as_f64()
+                    is_f64 = (mv or sv).is_f64
+                    if reducer:
+                        reducer.colmin_allreduce(colmin)
+                    _lib.check(self.lib.skr_colmin_finish(device.ptr(colmin), self.cols, device.ptr(mv.t if mv else None),
+                                                          device.ptr(sv.t if sv else None), int(is_f64),
+                                                          device.ptr(self.min_cell.t), device.stream_ptr(self.stream)))
+                    m_rows, ncols = out.shape
+                    _lib.check(self.lib.skr_normalize_post_log2(device.ptr(out), m_rows, ncols, out.stride(0),
+                                                                device.ptr(mv.t if mv else None), device.ptr(sv.t if sv else None),
+                                                                int(is_f64), device.ptr(self.min_cell.t),
+                                                                device.stream_ptr(self.stream)))
+                    self._keep = (mv, sv, colmin)
+                    return out, mean_vec, std_vec
             self.normalize(out, mean_vec, std_vec, track_min=True)
             min_valid = True
         if need_min:

@@ -181,6 +181,13 @@ def test_wide_k_pipeline_matches_oracle(k):
     assert np.array_equal(counter.mean, mean) and np.array_equal(counter.std, std, equal_nan=True)
     assert np.array_equal(counter.counts, exp, equal_nan=True)
     assert k == 7 or np.isnan(exp).any()
+    if k == 7:  # every 7-mer occurs somewhere: the self-normalised Log2.post tail (column minima -> one fused pass)
+        exp_post, mean_p, std_p = c_oracle.normalise(raw, True, True, "Log2.post")
+        post = BasicCounter(k=k, log2="Log2.post", silent=True)
+        post.seqs = seqs
+        post.get_counts()
+        assert np.array_equal(post.mean, mean_p) and np.array_equal(post.std, std_p)
+        assert np.abs(post.counts - exp_post).max() < TOL
     # (b) supplied vectors + Log2.post, then Pearson of the normalised matrix with itself
     vm = raw.mean(axis=0).astype(np.float32)
     vs = (raw.std(axis=0) + 0.25).astype(np.float32)
