@@ -260,6 +260,18 @@ int skr_min_exchange(SkrMinCell* d_cell, void* const* d_peers, int world, int ra
                      void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Text output of a host float32 matrix (replaces the DataFrame.to_csv / np.savetxt
+ * calls of kmer_counts.py:235-241), formatted on `threads` host threads (0 = all), byte-identical to them:
+ *   style 0  pandas' cell text for float32 (numpy's shortest round-trip repr; NaN -> empty cell)
+ *   style 1  "%1.6f" (np.savetxt)
+ * header (header_len bytes, may be NULL) is written first; labels + label_offs[m+1] (may be NULL) give the
+ * already CSV-quoted first field of every row.  skr_format_f32 formats n values, one per line (for tests).
+ * ------------------------------------------------------------------------------------------ */
+int skr_csv_write(const char* path, const float* data, int64_t m, int64_t cols, int64_t ld, const char* header,
+                  int64_t header_len, const char* labels, const int64_t* label_offs, int style, int threads);
+int skr_format_f32(const float* values, int64_t n, int style, char* out, int64_t capacity, int64_t* written);
+
+/* ------------------------------------------------------------------------------------------
  * Host <-> device plumbing used by the Python layer (thin wrappers; no reference counterpart)
  * ------------------------------------------------------------------------------------------ */
 int skr_host_alloc(size_t bytes, void** out); /* pinned host memory from the library's pool */

@@ -680,14 +680,15 @@ class BasicCounter:
         if self.binary:
             np.save(self.outfile, self.counts)
         elif self.label:
-            from pandas import DataFrame
-
             if names is None:
                 names = Reader(self.infasta).get_headers()
-            df = DataFrame(data=self.counts, index=names, columns=self.kmers)
-            df.to_csv(self.outfile)
+            if not _write_csv(self.outfile, self.counts, names, self.kmers):
+                from pandas import DataFrame
+
+                DataFrame(data=self.counts, index=names, columns=self.kmers).to_csv(self.outfile)
         else:
-            np.savetxt(self.outfile, self.counts, delimiter=",", fmt="%1.6f")
+            if not _write_csv(self.outfile, self.counts, None, None):
+                np.savetxt(self.outfile, self.counts, delimiter=",", fmt="%1.6f")
 
     def make_count_file(self, names=None):
         """get_counts() then save() when an outfile was given (kmer_counts.py:243-262)."""
@@ -695,6 +696,48 @@ class BasicCounter:
         if self.outfile is not None:
             self.save(names)
         return self.counts
+
+
+def _write_csv(path, counts, names, columns):
+    """The text forms of save() written by the library's multi-threaded formatter (skr_csv_write), byte for byte
+    what DataFrame.to_csv (labelled) / np.savetxt(fmt="%1.6f") (bare) produce for a float32 matrix; returns False
+    (caller uses pandas / numpy) for anything else than a C-contiguous 2-D float32 array written to a path."""
+    import csv
+    import io
+
+    import os
+
+    if not (isinstance(counts, np.ndarray) and counts.dtype == np.float32 and counts.ndim == 2 and counts.flags["C_CONTIGUOUS"]):
+        return False
+    if not (isinstance(path, (str, bytes)) or hasattr(path, "__fspath__")):
+        return False  # an open file object: pandas / numpy know what to do with it
+    path = os.fspath(path)
+    lib = _lib.load()
+    m, cols = counts.shape
+    header = labels = offs = None
+    style = 1
+    if names is not None:
+        style = 0
+        names = list(names)
+        if len(names) != m or len(columns) != cols:
+            return False  # let pandas raise its own error
+        text = io.StringIO()
+        writer = csv.writer(text, lineterminator="\n")  # pandas' defaults: QUOTE_MINIMAL, '"', doubled quotes
+        writer.writerow([""] + [str(c) for c in columns])
+        header = text.getvalue().encode("utf-8")
+        parts = []
+        for name in names:
+            text = io.StringIO()
+            csv.writer(text, lineterminator="\n").writerow([name, ""])  # two fields: a lone empty field would be quoted
+            parts.append(text.getvalue()[:-2].encode("utf-8"))
+        offs = np.zeros(m + 1, dtype=np.int64)
+        np.cumsum([len(p) for p in parts], out=offs[1:])
+        labels = b"".join(parts)
+    data_ptr = counts.ctypes.data if counts.size else None
+    _lib.check(lib.skr_csv_write(path if isinstance(path, bytes) else path.encode(), data_ptr, m, cols, counts.strides[0] // 4 if m else cols,
+                                 header, len(header) if header else 0, labels, offs.ctypes.data if offs is not None else None,
+                                 style, 0))
+    return True
 
 
 def _pinned_ok():
