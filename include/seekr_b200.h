@@ -258,6 +258,15 @@ int skr_peer_close(void* d_ptr);
 int skr_peer_free(void* d_ptr);
 int skr_min_exchange(SkrMinCell* d_cell, void* const* d_peers, int world, int rank, uint64_t epoch, int* d_err,
                      void* stream);
+/* skr_colstat_exchange   all-reduce(sum) of the n binary64 column partials of skr_col_partial_f64 over the ranks,
+ *                      fused with skr_col_finish_f64 (divide by the total row count, optional sqrt, fp32, quality
+ *                      flag) in ONE kernel: P2P stores of the partials into every peer, an epoch flag per rank, a
+ *                      rank-ordered sum (all ranks get the same bits).  Peer buffers hold
+ *                      skr_colstat_exchange_bytes(world, n_cap) bytes, zero-initialised (skr_peer_alloc). */
+int64_t skr_colstat_exchange_bytes(int world, int64_t n_cap);
+int skr_colstat_exchange(const double* d_acc, void* const* d_peers, int world, int rank, uint64_t epoch, int64_t n,
+                         int64_t n_cap, int64_t total_rows, int take_sqrt, float* d_out, int* d_flag, int* d_err,
+                         void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Text output of a host float32 matrix (replaces the DataFrame.to_csv / np.savetxt

@@ -66,6 +66,79 @@ __global__ void min_exchange_kernel(SkrMinCell* cell, unsigned long long* const*
     }
 }
 
+// All-reduce(sum) of n binary64 column partials fused with the finishing step of the column statistics
+// (skr_col_finish_f64: / total rows, optional sqrt, one rounding to fp32, quality flag).  Exchange buffer of a rank:
+// [2 parities][world][n_cap] doubles, then [2][world] 64-bit flags, then one 32-bit CTA counter.  Every CTA stores
+// its slice of this rank's partials into every peer (P2P stores), fences, and counts itself done; the last CTA
+// of the rank publishes the epoch flag to all peers.  Each CTA then waits until the flags of all ranks carry the
+// epoch and adds the `world` slices in rank order, so every rank computes the same bits.  A rank's CTAs never
+// wait for their own rank's later CTAs (stores come first), and peers do not depend on us: no circular wait.
+__global__ void __launch_bounds__(256) colstat_exchange_kernel(const double* __restrict__ acc, unsigned char* const* peers,
+                                                               int world, int rank, unsigned long long epoch, long long n,
+                                                               long long n_cap, long long total_rows, int take_sqrt,
+                                                               float* __restrict__ out, int* flag, int* err) {
+    const unsigned long long parity = epoch & 1ull;
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t flags_off = (size_t)2 * world * n_cap * sizeof(double);
+    const size_t counter_off = flags_off + (size_t)2 * world * sizeof(unsigned long long);
+    if (j < n) {
+        const double v = acc[j];
+        for (int t = 0; t < world; ++t) {
+            double* dst = reinterpret_cast<double*>(peers[t]) + (parity * world + rank) * n_cap + j;
+            asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(dst), "d"(v) : "memory");
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ int s_bad;
+    if (threadIdx.x == 0) {
+        s_bad = 0;
+        unsigned int* counter = reinterpret_cast<unsigned int*>(peers[rank] + counter_off);
+        const unsigned int done = atomicAdd(counter, 1u);
+        if (done == gridDim.x - 1) {  // every CTA of this rank has stored and fenced
+            *counter = 0u;
+            __threadfence_system();
+            for (int t = 0; t < world; ++t) {
+                unsigned long long* f = reinterpret_cast<unsigned long long*>(peers[t] + flags_off) + parity * world + rank;
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
+            }
+        }
+        const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(peers[rank] + flags_off) + parity * world;
+        const unsigned long long t0 = globaltimer_ns();
+        for (int t = 0; t < world; ++t) {
+            for (;;) {
+                unsigned long long f;
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(mine + t) : "memory");
+                if (f == epoch) break;
+                if (globaltimer_ns() - t0 > kSpinLimitNs) {
+                    atomicExch(err, 1);
+                    s_bad = 1;
+                    break;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (j >= n || s_bad) return;
+    const double* slices = reinterpret_cast<const double*>(peers[rank]) + parity * world * n_cap;
+    double sum = 0.0;
+    for (int t = 0; t < world; ++t) {
+        double v;
+        asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(slices + (size_t)t * n_cap + j) : "memory");
+        sum += v;
+    }
+    double r = sum / (double)total_rows;
+    if (take_sqrt) r = sqrt(r);
+    const float o = (float)r;
+    out[j] = o;
+    if (flag) {
+        int bits = 0;
+        if (!(o - o == 0.0f)) bits |= 1;
+        if (!(o > 0.0f)) bits |= 2;
+        if (bits) atomicOr(flag, bits);
+    }
+}
+
 }  // namespace
 
 extern "C" int skr_peer_alloc(size_t bytes, void** d_out, unsigned char* handle64) {
@@ -110,6 +183,28 @@ extern "C" int skr_min_exchange(SkrMinCell* d_cell, void* const* d_peers, int wo
         return skr::fail(SKR_ERR_ARG, "skr_min_exchange: world must be 1..32 and 0 <= rank < world");
     if (epoch == 0 || epoch >= (1ull << 31)) return skr::fail(SKR_ERR_ARG, "skr_min_exchange: epoch must be 1 .. 2^31 - 1");
     min_exchange_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_cell, (unsigned long long* const*)d_peers, world, rank, epoch, d_err);
+    SKR_LAUNCH_CHECK();
+    return SKR_OK;
+}
+
+extern "C" int64_t skr_colstat_exchange_bytes(int world, int64_t n_cap) {
+    return (int64_t)2 * world * n_cap * 8 + (int64_t)2 * world * 8 + 64;
+}
+
+extern "C" int skr_colstat_exchange(const double* d_acc, void* const* d_peers, int world, int rank, uint64_t epoch, int64_t n,
+                                    int64_t n_cap, int64_t total_rows, int take_sqrt, float* d_out, int* d_flag, int* d_err,
+                                    void* stream) {
+    if (n <= 0) return SKR_OK;
+    if (!d_acc || !d_peers || !d_out || !d_err || total_rows <= 0) return skr::fail(SKR_ERR_ARG, "skr_colstat_exchange: bad argument");
+    if (world < 1 || world > 64 || rank < 0 || rank >= world || n > n_cap)
+        return skr::fail(SKR_ERR_ARG, "skr_colstat_exchange: bad world / rank / capacity");
+    if (epoch == 0) return skr::fail(SKR_ERR_ARG, "skr_colstat_exchange: epoch starts at 1");
+    const long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 4) return skr::fail(SKR_ERR_ARG, "skr_colstat_exchange: vector too long for a co-resident grid");
+    if (d_flag) SKR_CUDA_CHECK(cudaMemsetAsync(d_flag, 0, sizeof(int), (cudaStream_t)stream));
+    colstat_exchange_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_acc, (unsigned char* const*)d_peers, world, rank,
+                                                                                 epoch, n, n_cap, total_rows, take_sqrt, d_out,
+                                                                                 d_flag, d_err);
     SKR_LAUNCH_CHECK();
     return SKR_OK;
 }

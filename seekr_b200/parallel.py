@@ -70,12 +70,11 @@ def allreduce_min_cell(cell_i64, group=None):
     return cell_i64
 
 
-class PeerMinExchange:
-    """All-reduce of the Log2.post minimum cell through NVLink peer memory (csrc/skr_peer.cu): every rank maps
-    every other rank's exchange buffer (CUDA IPC) once; an exchange is then ONE single-warp kernel per rank that
-    stores its cell into all peers and reduces the cells arriving in its own buffer."""
+class _PeerBuffer:
+    """An exchange buffer of `nbytes` on every rank, mapped into every other rank through CUDA IPC; `table` is the
+    device array of the `world` base addresses as seen from this process (entry `rank` = the own buffer)."""
 
-    def __init__(self, group=None):
+    def __init__(self, nbytes, group=None):
         import ctypes
 
         import numpy as np
@@ -86,11 +85,9 @@ class PeerMinExchange:
 
         self.lib = _lib.load()
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        if self.world > 32:
-            raise ValueError("peer exchange handles up to 32 ranks")
         own = ctypes.c_void_p()
         handle = (ctypes.c_ubyte * 64)()
-        _lib.check(self.lib.skr_peer_alloc(2 * self.world * 8, ctypes.byref(own), handle))
+        _lib.check(self.lib.skr_peer_alloc(int(nbytes), ctypes.byref(own), handle))
         self._own = own
         handles = [None] * self.world
         dist.all_gather_object(handles, bytes(handle), group=group)
@@ -111,16 +108,9 @@ class PeerMinExchange:
         torch.cuda.synchronize()
         dist.barrier(group=group)  # every buffer is mapped and zeroed before anybody stores into it
 
-    def exchange(self, engine):
-        from . import _lib, device
-
-        self.epoch += 1
-        _lib.check(self.lib.skr_min_exchange(device.ptr(engine.min_cell.t), device.ptr(self.table), self.world, self.rank,
-                                             self.epoch, device.ptr(self.err), device.stream_ptr(engine.stream)))
-
-    def check(self):
+    def check(self, what):
         if int(self.err.item()):
-            raise RuntimeError("peer-memory minimum exchange timed out: a rank did not take part within 4 s")
+            raise RuntimeError("peer-memory %s timed out: a rank did not take part within 4 s" % what)
 
     def close(self):
         for mapped in self._opened:
@@ -129,6 +119,54 @@ class PeerMinExchange:
         if self._own is not None:
             self.lib.skr_peer_free(self._own)
             self._own = None
+
+
+class PeerMinExchange(_PeerBuffer):
+    """All-reduce of the Log2.post minimum cell through NVLink peer memory (csrc/skr_peer.cu): every rank maps
+    every other rank's exchange buffer once; an exchange is then ONE single-warp kernel per rank that stores its
+    cell into all peers and reduces the cells arriving in its own buffer."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+
+        if dist.get_world_size(group) > 32:
+            raise ValueError("peer exchange handles up to 32 ranks")
+        super().__init__(2 * dist.get_world_size(group) * 8, group)
+
+    def exchange(self, engine):
+        from . import _lib, device
+
+        self.epoch += 1
+        _lib.check(self.lib.skr_min_exchange(device.ptr(engine.min_cell.t), device.ptr(self.table), self.world, self.rank,
+                                             self.epoch, device.ptr(self.err), device.stream_ptr(engine.stream)))
+
+    def check(self):
+        super().check("minimum exchange")
+
+
+class PeerColStatExchange(_PeerBuffer):
+    """All-reduce(sum) of the binary64 column partials fused with the finish of the statistic (csrc/skr_peer.cu):
+    one kernel stores the partials into every peer, flags the epoch, sums the `world` slices in rank order and
+    writes the fp32 mean / std vector -- the same bits on every rank."""
+
+    def __init__(self, cols, group=None):
+        import torch.distributed as dist
+
+        from . import _lib
+
+        self.cols = int(cols)
+        super().__init__(int(_lib.load().skr_colstat_exchange_bytes(dist.get_world_size(group), self.cols)), group)
+
+    def reduce_finish(self, engine, acc, total_rows, take_sqrt, out, flag):
+        from . import _lib, device
+
+        self.epoch += 1
+        _lib.check(self.lib.skr_colstat_exchange(device.ptr(acc), device.ptr(self.table), self.world, self.rank, self.epoch,
+                                                 acc.numel(), self.cols, int(total_rows), int(take_sqrt), device.ptr(out),
+                                                 device.ptr(flag), device.ptr(self.err), device.stream_ptr(engine.stream)))
+
+    def check(self):
+        super().check("column-statistics exchange")
 
 
 class _Base:
@@ -184,6 +222,8 @@ class _Base:
         """Raise if a peer-memory exchange timed out (call where results reach the host anyway)."""
         if getattr(self, "_peer", None) is not None:
             self._peer.check()
+        for peer in getattr(self, "_colstat_peers", {}).values():
+            peer.check()
 
 
 class AllReduceStats(_Base):
@@ -202,12 +242,33 @@ class AllReduceStats(_Base):
         _lib.check(lib.skr_col_partial_f64(kind, device.ptr(a), m, cols, a.stride(0), device.ptr(vec.t if vec else None),
                                            int(vec.is_f64) if vec else 0, device.ptr(vec2), device.ptr(acc),
                                            device.stream_ptr(engine.stream)))
-        self.dist.all_reduce(acc, group=self.group)
         rows = self.total_rows(m, a.device)
         out = torch.empty(cols, dtype=torch.float32, device=a.device)
+        peer = self._colstat_peer(cols) if a.is_cuda else None
+        if peer is not None:
+            peer.reduce_finish(engine, acc, rows, finish == "std", out, flag)  # all-reduce + finish, one kernel
+            return out
+        self.dist.all_reduce(acc, group=self.group)
         _lib.check(lib.skr_col_finish_f64(device.ptr(acc), cols, rows, int(finish == "std"), device.ptr(out),
                                           device.ptr(flag), device.stream_ptr(engine.stream)))
         return out
+
+    def _colstat_peer(self, cols):
+        import os
+
+        if os.environ.get("SEEKR_B200_COLSTAT_EXCHANGE", "peer") == "nccl" or getattr(self, "_colstat_failed", False):
+            return None
+        peers = self.__dict__.setdefault("_colstat_peers", {})
+        if cols not in peers:
+            try:
+                peers[cols] = PeerColStatExchange(cols, self.group)
+            except Exception as exc:
+                import warnings
+
+                warnings.warn("peer-memory column-statistics exchange unavailable (%s); using the NCCL all-reduce" % (exc,))
+                self._colstat_failed = True
+                return None
+        return peers[cols]
 
 
 class ChainStats(_Base):

@@ -98,6 +98,38 @@ def main():
         os.environ.pop("SEEKR_B200_MIN_EXCHANGE", None)
         if rank == 0:
             print("min all-reduce via %s: %.1f us per call" % (name, t0[0].elapsed_time(t0[1]) * 1e3 / 50))
+    # fused column-statistics exchange (all-reduce + finish in one kernel) against NCCL all-reduce + finish kernel
+    from seekr_b200 import _lib as skr_lib
+
+    a = torch.rand(2000 + 100 * rank, 4 ** k, device="cuda")
+    outs = {}
+    for name in ("peer", "nccl"):
+        red = parallel.AllReduceStats()
+        if name == "nccl":
+            os.environ["SEEKR_B200_COLSTAT_EXCHANGE"] = "nccl"
+        fl = torch.zeros(1, dtype=torch.int32, device="cuda")
+        outs[name] = red.col_stat(eng, skr_lib.COLPASS_SUM, a, None, None, "mean", fl).cpu().numpy()
+        for _ in range(5):
+            red.col_stat(eng, skr_lib.COLPASS_SUM, a, None, None, "mean", fl)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0[0].record()
+        for _ in range(50):
+            red.col_stat(eng, skr_lib.COLPASS_SUM, a, None, None, "mean", fl)
+        t0[1].record()
+        torch.cuda.synchronize()
+        red.check()
+        os.environ.pop("SEEKR_B200_COLSTAT_EXCHANGE", None)
+        if rank == 0:
+            print("column mean over shards via %s: %.1f us per statistic (partial sums + all-reduce + finish)"
+                  % (name, t0[0].elapsed_time(t0[1]) * 1e3 / 50))
+    close = bool(np.max(np.abs(outs["peer"] - outs["nccl"]) / np.abs(outs["nccl"])) < 2e-7)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, outs["peer"].tobytes())
+    same_bits = all(g == gathered[0] for g in gathered)
+    if rank == 0:
+        print("fused column-statistics exchange == NCCL path (1 ulp): %s; identical bits on all ranks: %s" % (close, same_bits))
+        ok &= close and same_bits
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)
     dist.barrier()
