@@ -70,6 +70,16 @@ def allreduce_min_cell(cell_i64, group=None):
     return cell_i64
 
 
+_PEER_CACHE = {}  # (kind, group, size) -> exchange object: the IPC mappings are made once per process
+
+
+def _peer_cached(kind, group, size, make):
+    key = (kind, id(group) if group is not None else None, size)
+    if key not in _PEER_CACHE:
+        _PEER_CACHE[key] = make()
+    return _PEER_CACHE[key]
+
+
 class _PeerBuffer:
     """An exchange buffer of `nbytes` on every rank, mapped into every other rank through CUDA IPC; `table` is the
     device array of the `world` base addresses as seen from this process (entry `rank` = the own buffer)."""
@@ -205,7 +215,7 @@ class _Base:
         if cell.is_cuda and os.environ.get("SEEKR_B200_MIN_EXCHANGE", "peer") != "nccl":
             if getattr(self, "_peer", None) is None and not getattr(self, "_peer_failed", False):
                 try:
-                    self._peer = PeerMinExchange(self.group)
+                    self._peer = _peer_cached("min", self.group, 0, lambda: PeerMinExchange(self.group))
                 except Exception as exc:  # no IPC / no peer access: still a GPU collective, just not ours
                     import warnings
 
@@ -261,7 +271,7 @@ class AllReduceStats(_Base):
         peers = self.__dict__.setdefault("_colstat_peers", {})
         if cols not in peers:
             try:
-                peers[cols] = PeerColStatExchange(cols, self.group)
+                peers[cols] = _peer_cached("colstat", self.group, cols, lambda: PeerColStatExchange(cols, self.group))
             except Exception as exc:
                 import warnings
 
