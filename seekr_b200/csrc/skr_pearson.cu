@@ -137,6 +137,101 @@ __global__ void __launch_bounds__(kPrepThreads) prepare_kernel(const T* __restri
     if (threadIdx.x == 0) row_scale[row] = (float)ldexp(1.0, -e);
 }
 
+// float32 rows of at most 16 * kPrepThreads columns (k <= 6): the row is read ONCE with 128-bit loads and stays in
+// registers for the three statistics passes and the split; hi / lo leave as 64-bit stores.  Same operations per
+// element as prepare_kernel<float>; only the order of the binary64 partial sums differs.
+template <int kVecs>
+__global__ void __launch_bounds__(kPrepThreads) prepare_rows_kernel(const float* __restrict__ a, long long rows, long long K,
+                                                                    long long ld, long long kp, int standardize,
+                                                                    __half* __restrict__ hi, __half* __restrict__ lo,
+                                                                    float* __restrict__ row_scale) {
+    __shared__ double s_d[kPrepThreads / 32];
+    __shared__ float s_f[kPrepThreads / 32];
+    const long long row = blockIdx.x;
+    uint2* hrow = reinterpret_cast<uint2*>(hi + row * kp);
+    uint2* lrow = reinterpret_cast<uint2*>(lo + row * kp);
+    const long long nv = kp / 4;  // 4-element groups of the padded row
+    if (row >= rows) {
+        for (long long g = threadIdx.x; g < nv; g += kPrepThreads) hrow[g] = lrow[g] = make_uint2(0u, 0u);
+        if (threadIdx.x == 0) row_scale[row] = 0.0f;
+        return;
+    }
+    const float4* x4 = reinterpret_cast<const float4*>(a + row * ld);
+    const long long kv = K / 4;
+    float4 x[kVecs];
+#pragma unroll
+    for (int v = 0; v < kVecs; ++v) {
+        const long long g = (long long)v * kPrepThreads + threadIdx.x;
+        x[v] = g < kv ? __ldg(x4 + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    auto valid = [&](int v) { return (long long)v * kPrepThreads + threadIdx.x < kv; };
+    float mean = 0.0f, mean2 = 0.0f, sd = 1.0f, amax;
+    if (standardize) {
+        double s = 0.0;
+#pragma unroll
+        for (int v = 0; v < kVecs; ++v)
+            if (valid(v)) s += ((double)x[v].x + (double)x[v].y) + ((double)x[v].z + (double)x[v].w);
+        mean = (float)(block_sum(s, s_d) / (double)K);
+        double s2 = 0.0;
+#pragma unroll
+        for (int v = 0; v < kVecs; ++v)
+            if (valid(v)) {
+                x[v].x = __fsub_rn(x[v].x, mean); x[v].y = __fsub_rn(x[v].y, mean);
+                x[v].z = __fsub_rn(x[v].z, mean); x[v].w = __fsub_rn(x[v].w, mean);
+                s2 += ((double)x[v].x + (double)x[v].y) + ((double)x[v].z + (double)x[v].w);
+            }
+        mean2 = (float)(block_sum(s2, s_d) / (double)K);
+        double q = 0.0;
+        float mx = 0.0f;
+#pragma unroll
+        for (int v = 0; v < kVecs; ++v)
+            if (valid(v)) {
+                const float e0 = __fsub_rn(x[v].x, mean2), e1 = __fsub_rn(x[v].y, mean2);
+                const float e2 = __fsub_rn(x[v].z, mean2), e3 = __fsub_rn(x[v].w, mean2);
+                q += ((double)__fmul_rn(e0, e0) + (double)__fmul_rn(e1, e1)) + ((double)__fmul_rn(e2, e2) + (double)__fmul_rn(e3, e3));
+                mx = fmaxf(fmaxf(mx, fmaxf(fabsf(x[v].x), fabsf(x[v].y))), fmaxf(fabsf(x[v].z), fabsf(x[v].w)));
+            }
+        sd = (float)sqrt((double)(float)(block_sum(q, s_d) / (double)K));
+        amax = block_max(mx, s_f) / fabsf(sd);
+    } else {
+        float mx = 0.0f;
+#pragma unroll
+        for (int v = 0; v < kVecs; ++v)
+            if (valid(v)) mx = fmaxf(fmaxf(mx, fmaxf(fabsf(x[v].x), fabsf(x[v].y))), fmaxf(fabsf(x[v].z), fabsf(x[v].w)));
+        amax = block_max(mx, s_f);
+    }
+    int e = 0;
+    if (amax > 0.0f && amax < INFINITY) {
+        int ex;
+        frexpf(amax, &ex);
+        e = max(-100, min(100, 15 - ex));
+    }
+    const float up = (float)ldexp(1.0, e);
+    auto split = [&](float d, __half& hh, __half& ll) {
+        float y = standardize ? __fdiv_rn(d, sd) : d;
+        y = __fmul_rn(y, up);  // exact: a power of two
+        hh = __float2half_rn(y);
+        ll = __float2half_rn(__fsub_rn(y, __half2float(hh)));  // y - hi is exact in fp32
+    };
+#pragma unroll
+    for (int v = 0; v < kVecs; ++v) {
+        const long long g = (long long)v * kPrepThreads + threadIdx.x;
+        if (g >= nv) continue;
+        __half h[4], l[4];
+        if (g < kv) {
+            split(x[v].x, h[0], l[0]); split(x[v].y, h[1], l[1]);
+            split(x[v].z, h[2], l[2]); split(x[v].w, h[3], l[3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h[i] = l[i] = __float2half_rn(0.0f);
+        }
+        hrow[g] = *reinterpret_cast<const uint2*>(h);
+        lrow[g] = *reinterpret_cast<const uint2*>(l);
+    }
+    // padded tail beyond kVecs * kPrepThreads groups cannot exist: the host checks kp / 4 <= kVecs * kPrepThreads
+    if (threadIdx.x == 0) row_scale[row] = (float)ldexp(1.0, -e);
+}
+
 // ---------------------------------------------------------------------------------------------
 // K4: tcgen05 GEMM
 // ---------------------------------------------------------------------------------------------
@@ -504,33 +599,36 @@ pearson_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
 // Symmetric mode: the GEMM wrote the 256 x 256 tiles on and above the diagonal; this fills every tile
 // below it with the transpose of its mirror image (32 x 32 blocks through shared memory, coalesced
 // reads and writes; ~2 passes over half the matrix at HBM speed).
-template <typename T>
+template <typename T, int MB>
 __global__ void __launch_bounds__(256) mirror_lower_kernel(T* __restrict__ c, long long n, long long ldc, int tiles) {
-    // 64 x 64 blocks: 16 sub-blocks per 256 x 256 tile; 128-bit reads and writes when the block is interior
-    __shared__ T tile[64][65];
+    // MB x MB blocks ((256 / MB)^2 sub-blocks per 256 x 256 tile) through padded shared memory; 128-bit reads and
+    // writes when the block is interior.
+    extern __shared__ __align__(16) unsigned char mirror_smem[];
+    T(*tile)[MB + 1] = reinterpret_cast<T(*)[MB + 1]>(mirror_smem);
+    constexpr int SB = kBN / MB;  // sub-blocks per tile side
     long long t = blockIdx.x;
     int tm = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5) + 1;  // t = tm(tm-1)/2 + tn, tn < tm
     while ((long long)tm * (tm - 1) / 2 > t) --tm;
     while ((long long)(tm + 1) * tm / 2 <= t) ++tm;
     const int tn = (int)(t - (long long)tm * (tm - 1) / 2);
     if (tm >= tiles) return;
-    const int sb_r = blockIdx.y >> 2, sb_c = blockIdx.y & 3;  // sub-block of the destination tile
-    const long long dr0 = (long long)tm * kBN + sb_r * 64, dc0 = (long long)tn * kBN + sb_c * 64;  // destination origin
+    const int sb_r = blockIdx.y / SB, sb_c = blockIdx.y % SB;  // sub-block of the destination tile
+    const long long dr0 = (long long)tm * kBN + sb_r * MB, dc0 = (long long)tn * kBN + sb_c * MB;  // destination origin
     constexpr int V = 16 / sizeof(T);       // elements per 128-bit access
-    constexpr int TX = 64 / V;              // threads across a 64-wide row
+    constexpr int TX = MB / V;              // threads across an MB-wide row
     constexpr int TY = 256 / TX;            // rows per sweep
     const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
-    const bool interior = dr0 + 64 <= n && dc0 + 64 <= n && (ldc % V) == 0;
-    // source block = C[dc0 .. dc0+63][dr0 .. dr0+63]
+    const bool interior = dr0 + MB <= n && dc0 + MB <= n && (ldc % V) == 0;
+    // source block = C[dc0 .. dc0+MB-1][dr0 .. dr0+MB-1]
     if (interior) {
-        for (int i = ty; i < 64; i += TY) {
+        for (int i = ty; i < MB; i += TY) {
             const float4 v = *reinterpret_cast<const float4*>(c + (dc0 + i) * ldc + dr0 + tx * V);
             const T* e = reinterpret_cast<const T*>(&v);
 #pragma unroll
             for (int j = 0; j < V; ++j) tile[i][tx * V + j] = e[j];
         }
         __syncthreads();
-        for (int i = ty; i < 64; i += TY) {
+        for (int i = ty; i < MB; i += TY) {
             float4 v;
             T* e = reinterpret_cast<T*>(&v);
 #pragma unroll
@@ -538,14 +636,14 @@ __global__ void __launch_bounds__(256) mirror_lower_kernel(T* __restrict__ c, lo
             *reinterpret_cast<float4*>(c + (dr0 + i) * ldc + dc0 + tx * V) = v;
         }
     } else {
-        for (int i = threadIdx.x / 64; i < 64; i += 4) {
-            const int j = threadIdx.x % 64;
+        for (int i = threadIdx.x / MB; i < MB; i += 256 / MB) {
+            const int j = threadIdx.x % MB;
             const long long sr = dc0 + i, sc = dr0 + j;
             if (sr < n && sc < n) tile[i][j] = c[sr * ldc + sc];
         }
         __syncthreads();
-        for (int i = threadIdx.x / 64; i < 64; i += 4) {
-            const int j = threadIdx.x % 64;
+        for (int i = threadIdx.x / MB; i < MB; i += 256 / MB) {
+            const int j = threadIdx.x % MB;
             const long long r = dr0 + i, cc = dc0 + j;
             if (r < n && cc < n) c[r * ldc + cc] = tile[j][i];
         }
@@ -583,9 +681,19 @@ int launch_gemm(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtens
     SKR_LAUNCH_CHECK();
     if (p.symmetric && p.tiles_m > 1) {
         const long long pairs = (long long)p.tiles_m * (p.tiles_m - 1) / 2;
-        dim3 grid((unsigned)pairs, 16);
-        if (p.c_is_f64) mirror_lower_kernel<double><<<grid, 256, 0, stream>>>((double*)p.c, p.n, p.ldc, p.tiles_m);
-        else mirror_lower_kernel<float><<<grid, 256, 0, stream>>>((float*)p.c, p.n, p.ldc, p.tiles_m);
+        if (p.c_is_f64) {
+            constexpr int MB = 64;
+            constexpr int smem = MB * (MB + 1) * (int)sizeof(double);
+            dim3 grid((unsigned)pairs, (kBN / MB) * (kBN / MB));
+            mirror_lower_kernel<double, MB><<<grid, 256, smem, stream>>>((double*)p.c, p.n, p.ldc, p.tiles_m);
+        } else {
+            constexpr int MB = 64;  // 128 x 128 blocks (512-byte segments, 66 KB of shared memory) measured slower: 2.9 vs 2.2 ms
+            constexpr int smem = MB * (MB + 1) * (int)sizeof(float);
+            auto kern = mirror_lower_kernel<float, MB>;
+            SKR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            dim3 grid((unsigned)pairs, (kBN / MB) * (kBN / MB));
+            kern<<<grid, 256, smem, stream>>>((float*)p.c, p.n, p.ldc, p.tiles_m);
+        }
         SKR_LAUNCH_CHECK();
     }
     return SKR_OK;
@@ -605,7 +713,12 @@ extern "C" int skr_pearson_prepare(const void* d_a, int a_is_f64, int64_t rows, 
     const int64_t rp = skr_pearson_rows_padded(rows), kp = skr_pearson_k_padded(K);
     if (rp > 0x7FFFFFFFll) return skr::fail(SKR_ERR_ARG, "skr_pearson_prepare: too many rows");
     cudaStream_t s = (cudaStream_t)stream;
-    if (a_is_f64)
+    const bool reg_path = !a_is_f64 && K % 4 == 0 && ld % 4 == 0 && (((uintptr_t)d_a & 15) == 0) && kp / 4 <= 4 * kPrepThreads &&
+                          !getenv("SEEKR_B200_PREPARE_GENERIC");
+    if (reg_path)
+        prepare_rows_kernel<4><<<(unsigned)rp, kPrepThreads, 0, s>>>((const float*)d_a, rows, K, ld, kp, row_standardize,
+                                                                     (__half*)d_hi, (__half*)d_lo, d_row_scale);
+    else if (a_is_f64)
         prepare_kernel<double><<<(unsigned)rp, kPrepThreads, 0, s>>>((const double*)d_a, rows, K, ld, kp, row_standardize,
                                                                      (__half*)d_hi, (__half*)d_lo, d_row_scale);
     else
