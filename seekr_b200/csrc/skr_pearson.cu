@@ -261,6 +261,8 @@ struct GemmParams {
     long long m, n;            // valid rows of A / B
     int num_kb;                // k-blocks of 64
     int chunk_kb;              // k-blocks accumulated in TMEM before promotion (see the header comment)
+    int accumulate;            // add to what C already holds (K segments after the first)
+    int do_mirror;             // symmetric mode: fill the lower triangle after this launch (last K segment)
     int tiles_m, tiles_n;
     float alpha;
     const float* a_scale;
@@ -568,17 +570,23 @@ pearson_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                             o.y = sum[c + 1] * rs * bs.y;
                             o.z = sum[c + 2] * rs * bs.z;
                             o.w = sum[c + 3] * rs * bs.w;
+                            if (p.accumulate) {
+                                const float4 prev = *reinterpret_cast<const float4*>(dst);
+                                o.x += prev.x; o.y += prev.y; o.z += prev.z; o.w += prev.w;
+                            }
                             *reinterpret_cast<float4*>(dst) = o;
                         } else {
 #pragma unroll
                             for (int i = 0; i < 4; ++i)
-                                if (col0 + i < p.n) dst[i] = sum[c + i] * rs * __ldg(p.b_scale + col0 + i);
+                                if (col0 + i < p.n)
+                                    dst[i] = sum[c + i] * rs * __ldg(p.b_scale + col0 + i) + (p.accumulate ? dst[i] : 0.0f);
                         }
                     } else {
                         double* dst = reinterpret_cast<double*>(p.c) + row * p.ldc + col0;
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
-                            if (col0 + i < p.n) dst[i] = (double)(sum[c + i] * rs * __ldg(p.b_scale + col0 + i));
+                            if (col0 + i < p.n)
+                                dst[i] = (double)(sum[c + i] * rs * __ldg(p.b_scale + col0 + i)) + (p.accumulate ? dst[i] : 0.0);
                     }
                 }
             }
@@ -679,7 +687,7 @@ int launch_gemm(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtens
     cfg.numAttrs = 1;
     SKR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, mb_hi, mb_lo, p));
     SKR_LAUNCH_CHECK();
-    if (p.symmetric && p.tiles_m > 1) {
+    if (p.symmetric && p.do_mirror && p.tiles_m > 1) {
         const long long pairs = (long long)p.tiles_m * (p.tiles_m - 1) / 2;
         if (p.c_is_f64) {
             constexpr int MB = 64;
@@ -745,21 +753,33 @@ extern "C" int skr_pearson_gemm(const uint16_t* d_a_hi, const uint16_t* d_a_lo, 
     int cg = 2;
     if (const char* env = getenv("SEEKR_B200_GEMM_CTA_GROUP")) cg = atoi(env) == 1 ? 1 : 2;
     if (cg == 1) symmetric = 0;  // 128 x 256 tiles are not square: compute the full matrix
-    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     const uint32_t b_box_rows = cg == 2 ? 128 : 256;
-    int rc;
-    if ((rc = skr::make_tmap_2d(&ma_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d_a_hi, (uint64_t)kp, (uint64_t)mp,
+    // K segments: beyond kSegKb k-blocks the contraction is cut into launches that add into C, so the running
+    // sums of the promotion never see more than kSegKb / chunk_kb chunk values (their systematic rounding on
+    // count-like rows grows with that number); the segment results are combined by 2 ... 8 fp32 adds in C.
+    int seg_kb = 128;  // 8192 columns
+    if (const char* env = getenv("SEEKR_B200_GEMM_SEGMENT")) seg_kb = atoi(env) > 0 ? atoi(env) : 0x7FFFFFFF;
+    const int total_kb = (int)(kp / kBK);
+    int rc = SKR_OK;
+    for (int kb_first = 0; kb_first < total_kb; kb_first += seg_kb) {
+    const int kb_count = total_kb - kb_first < seg_kb ? total_kb - kb_first : seg_kb;
+    const size_t koff = (size_t)kb_first * kBK;  // elements into every plane row (a multiple of 64: 128-byte aligned)
+    const uint64_t kw = (uint64_t)kb_count * kBK;
+    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+    if ((rc = skr::make_tmap_2d(&ma_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d_a_hi + koff, kw, (uint64_t)mp,
                                 (uint64_t)kp * 2, kBK, kBM, CU_TENSOR_MAP_SWIZZLE_128B)) != SKR_OK) return rc;
-    if ((rc = skr::make_tmap_2d(&ma_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d_a_lo, (uint64_t)kp, (uint64_t)mp,
+    if ((rc = skr::make_tmap_2d(&ma_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d_a_lo + koff, kw, (uint64_t)mp,
                                 (uint64_t)kp * 2, kBK, kBM, CU_TENSOR_MAP_SWIZZLE_128B)) != SKR_OK) return rc;
-    if ((rc = skr::make_tmap_2d(&mb_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d_b_hi, (uint64_t)kp, (uint64_t)np_,
+    if ((rc = skr::make_tmap_2d(&mb_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d_b_hi + koff, kw, (uint64_t)np_,
                                 (uint64_t)kp * 2, kBK, b_box_rows, CU_TENSOR_MAP_SWIZZLE_128B)) != SKR_OK) return rc;
-    if ((rc = skr::make_tmap_2d(&mb_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d_b_lo, (uint64_t)kp, (uint64_t)np_,
+    if ((rc = skr::make_tmap_2d(&mb_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d_b_lo + koff, kw, (uint64_t)np_,
                                 (uint64_t)kp * 2, kBK, b_box_rows, CU_TENSOR_MAP_SWIZZLE_128B)) != SKR_OK) return rc;
     GemmParams p{};
     p.m = m;
     p.n = n;
-    p.num_kb = (int)(kp / kBK);
+    p.num_kb = kb_count;
+    p.accumulate = kb_first > 0;
+    p.do_mirror = kb_first + kb_count >= total_kb;
     // Promotion interval.  Two error sources pull in opposite directions on count-like rows (a few big z-scores
     // among thousands of small ones): inside a chunk the tensor core truncates every addend to the accumulator's
     // ulp, so small products that share a chunk with a large one lose low bits (grows with the chunk); across
@@ -778,5 +798,8 @@ extern "C" int skr_pearson_gemm(const uint16_t* d_a_hi, const uint16_t* d_a_lo, 
     p.c_is_f64 = c_is_f64;
     p.symmetric = symmetric;
     cudaStream_t s = (cudaStream_t)stream;
-    return cg == 2 ? launch_gemm<2>(ma_hi, ma_lo, mb_hi, mb_lo, p, s) : launch_gemm<1>(ma_hi, ma_lo, mb_hi, mb_lo, p, s);
+    rc = cg == 2 ? launch_gemm<2>(ma_hi, ma_lo, mb_hi, mb_lo, p, s) : launch_gemm<1>(ma_hi, ma_lo, mb_hi, mb_lo, p, s);
+    if (rc != SKR_OK) return rc;
+    }  // K segments
+    return rc;
 }
