@@ -125,7 +125,9 @@ def find_dist(inputseq='default', k_mer=4, log2='Log2.post', models='common10', 
 
     bkg_counter = BasicCounter(inputseq, mean=mean_path, std=std_path, k=k_mer, silent=True)
     bkg_counter.make_count_file()
-    sim_triu = background_r(bkg_counter.counts, subsetting=subsetting, subset_size=subset_size)
+    device_counts = getattr(bkg_counter, "counts_device", None)  # still on the device after get_counts()
+    sim_triu = background_r(device_counts if device_counts is not None else bkg_counter.counts,
+                            subsetting=subsetting, subset_size=subset_size)
 
     if not fit_model:
         if plotfit:

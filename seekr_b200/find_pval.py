@@ -107,6 +107,12 @@ def _pvalues(counts1, counts2, transform):
     return out
 
 
+def _device_counts(counter):
+    """The count matrix where get_counts() left it on the device (no second upload); the host copy otherwise."""
+    dev = getattr(counter, "counts_device", None)
+    return dev if dev is not None and tuple(dev.shape) == tuple(counter.counts.shape) else counter.counts
+
+
 def find_pval(seq1file, seq2file, mean_path, std_path, k_mer, fitres, log2='Log2.post', bestfit=1, outputname=None,
               progress_bar=True):
     """Same arguments, printed diagnostics and return values as seekr/find_pval.py:70-183."""
@@ -143,7 +149,7 @@ def find_pval(seq1file, seq2file, mean_path, std_path, k_mer, fitres, log2='Log2
             print('No p value is calculated. The output is None.')
             return None
         distname, _, params = fitres[bestfit - 1]
-        p_values = _pvalues(t1.counts, t2.counts, lambda r, p: pval_dist_device(r, distname, params, out=p))
+        p_values = _pvalues(_device_counts(t1), _device_counts(t2), lambda r, p: pval_dist_device(r, distname, params, out=p))
     elif isinstance(fitres, np.ndarray):
         if len(fitres.shape) != 1:
             print('The dimension of fitres as a numpy array is wrong. fitres should be a 1D numpy array.')
@@ -151,7 +157,7 @@ def find_pval(seq1file, seq2file, mean_path, std_path, k_mer, fitres, log2='Log2
             print('No p value is calculated. The output is None.')
             return None
         background = _sorted_background(fitres)
-        p_values = _pvalues(t1.counts, t2.counts, lambda r, p: pval_empirical_device(r, background, out=p))
+        p_values = _pvalues(_device_counts(t1), _device_counts(t2), lambda r, p: pval_empirical_device(r, background, out=p))
     else:
         print('fitres should be the output of find_dist. It should be either a list of distributions or a numpy array.')
         print('No p value is calculated. The output is None.')
