@@ -241,6 +241,29 @@ int skr_pearson_pairs(const uint16_t* d_a_hi, const uint16_t* d_a_lo, const floa
                       int64_t npairs, double alpha, float* d_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Similarity graph of an r matrix (the numeric front half of seekr/kmer_leiden.py)
+ *
+ * skr_sim_threshold    replaces kmer_leiden.py:91-94 in place on the device:
+ *                      c[c < cutoff] = 0, then (zero_diagonal) np.fill_diagonal(c, 0).  The comparison is made
+ *                      in the matrix's type with the cutoff converted to it, as numpy does for a Python scalar;
+ *                      NaN entries stay NaN.
+ * skr_sim_edge_offsets replaces the counting half of kmer_leiden.py:103-104 ((df.values > 0)): entry (i, j) of
+ *                      the thresholded, zero-diagonal matrix is positive iff the ORIGINAL value x has
+ *                      !(x < cutoff) && x > 0 && i != j, so d_c is the untouched r matrix.  Writes the CSR row
+ *                      offsets: d_offsets[0] = 0, d_offsets[i+1] - d_offsets[i] = edges of row i
+ *                      (upper_only != 0: only j > i, one entry per undirected edge).  d_offsets holds m+1 values.
+ * skr_sim_edge_fill    replaces kmer_leiden.py:104 (df.values[df.values > 0].flatten()) and np.nonzero of the
+ *                      adjacency: edges in row-major order, d_src (may be NULL for CSR form) / d_dst int32,
+ *                      d_weight in the matrix's type; each array holds d_offsets[m] entries.
+ * ------------------------------------------------------------------------------------------ */
+int skr_sim_threshold(void* d_c, int c_is_f64, int64_t m, int64_t n, int64_t ld, double cutoff, int zero_diagonal,
+                      void* stream);
+int skr_sim_edge_offsets(const void* d_c, int c_is_f64, int64_t m, int64_t n, int64_t ld, double cutoff,
+                         int upper_only, int64_t* d_offsets, void* stream);
+int skr_sim_edge_fill(const void* d_c, int c_is_f64, int64_t m, int64_t n, int64_t ld, double cutoff, int upper_only,
+                      const int64_t* d_offsets, int32_t* d_src, int32_t* d_dst, void* d_weight, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Collectives over NVLink peer memory (one process per GPU; SURVEY section 8e: the Log2.post minimum
  * of kmer_counts.py:207-208 spans all row shards)
  *
@@ -279,6 +302,27 @@ int skr_colstat_exchange(const double* d_acc, void* const* d_peers, int world, i
 int skr_csv_write(const char* path, const float* data, int64_t m, int64_t cols, int64_t ld, const char* header,
                   int64_t header_len, const char* labels, const int64_t* label_offs, int style, int threads);
 int skr_format_f32(const float* values, int64_t n, int style, char* out, int64_t capacity, int64_t* written);
+
+/* ------------------------------------------------------------------------------------------
+ * Text input of a labelled count matrix (replaces pd.read_csv(path, index_col=0) of
+ * console_scripts.py:628-629 for the files kmer_counts.py:235-238 writes): parsed on `threads` host threads
+ * (0 = all) into binary64 with the same bits as pandas' default C parser (its 17-digit accumulate-and-scale
+ * procedure is restated, including its rounding errors).  Files outside the plain form (quotes, labels pandas
+ * would convert, cells that are not plain numbers, ragged rows) return SKR_CSV_UNSUPPORTED: use pandas.
+ * The table owns its memory until skr_csv_free; labels / columns are concatenated bytes with rows+1 / cols+1 offsets.
+ * ------------------------------------------------------------------------------------------ */
+#define SKR_CSV_UNSUPPORTED 100
+typedef struct SkrCsvTable SkrCsvTable;
+int skr_csv_read(const char* path, int threads, SkrCsvTable** out);
+void skr_csv_free(SkrCsvTable* t);
+int64_t skr_csv_rows(const SkrCsvTable* t);
+int64_t skr_csv_cols(const SkrCsvTable* t);
+const double* skr_csv_values(const SkrCsvTable* t);
+const char* skr_csv_labels(const SkrCsvTable* t);
+const int64_t* skr_csv_label_offsets(const SkrCsvTable* t);
+const char* skr_csv_columns(const SkrCsvTable* t);
+const int64_t* skr_csv_column_offsets(const SkrCsvTable* t);
+int skr_csv_all_integer(const SkrCsvTable* t); /* 1: every cell is an integer literal (pandas: int64 columns) */
 
 /* ------------------------------------------------------------------------------------------
  * Host <-> device plumbing used by the Python layer (thin wrappers; no reference counterpart)

@@ -315,3 +315,27 @@ def pval_dist(sim, family, params):
     x = (sim.astype(np.float64) - loc) / scale
     c = dist_cdf(family, x, shape) if valid else np.full(sim.shape, np.nan)
     return (1 - c).astype(sim.dtype)
+
+
+# ---------------------------------------------------------------------------------------------
+# Similarity graph: the numeric statements of seekr/kmer_leiden.py:91-104 before the
+# hand-over to networkx / igraph.  Pinned by tests/golden/leiden/ (the matrix, boolean adjacency and weight
+# vector the unmodified reference passes to those libraries, recorded by tests/golden/make_golden_leiden.py).
+# ---------------------------------------------------------------------------------------------
+def leiden_adjacency(sim, pearsoncutoff=0):
+    """ld_sim[ld_sim < pearsoncutoff] = 0 ; np.fill_diagonal(ld_sim, 0) (kmer_leiden.py:91-94), on a copy."""
+    adj = np.array(sim, copy=True)
+    adj[adj < pearsoncutoff] = 0
+    np.fill_diagonal(adj, 0)
+    return adj
+
+
+def leiden_edges(sim, pearsoncutoff=0, upper_only=False):
+    """(rows, cols, weights) of (df.values > 0) in row-major order, weights = df.values[df.values > 0]
+    (kmer_leiden.py:103-104); upper_only keeps j > i, the one entry per undirected edge."""
+    adj = leiden_adjacency(sim, pearsoncutoff)
+    positive = adj > 0
+    if upper_only:
+        positive &= np.triu(np.ones(adj.shape, dtype=bool), k=1)
+    rows, cols = np.nonzero(positive)
+    return rows, cols, adj[positive]

@@ -18,6 +18,7 @@ SKR_ERR_IO = 3
 SKR_ERR_NOMEM = 4
 SKR_ERR_FASTA_BLANK = 5
 SKR_ERR_FASTA_HEADER = 6
+SKR_CSV_UNSUPPORTED = 100
 
 COLPASS_SUM = 0
 COLPASS_CENTERED = 1
@@ -78,6 +79,9 @@ SIGNATURES = {
     "skr_triu_count": (_i64, [_i64]),
     "skr_triu_extract": (_int, [_vp, _int, _i64, _i64, _vp, _vp]),
     "skr_pearson_pairs": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _dbl, _vp, _vp]),
+    "skr_sim_threshold": (_int, [_vp, _int, _i64, _i64, _i64, _dbl, _int, _vp]),
+    "skr_sim_edge_offsets": (_int, [_vp, _int, _i64, _i64, _i64, _dbl, _int, _vp, _vp]),
+    "skr_sim_edge_fill": (_int, [_vp, _int, _i64, _i64, _i64, _dbl, _int, _vp, _vp, _vp, _vp, _vp]),
     "skr_peer_alloc": (_int, [_sz, ctypes.POINTER(_vp), _vp]),
     "skr_peer_open": (_int, [_vp, ctypes.POINTER(_vp)]),
     "skr_peer_close": (_int, [_vp]),
@@ -87,6 +91,16 @@ SIGNATURES = {
     "skr_colstat_exchange": (_int, [_vp, _vp, _int, _int, ctypes.c_uint64, _i64, _i64, _i64, _int, _vp, _vp, _vp, _vp]),
     "skr_csv_write": (_int, [ctypes.c_char_p, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _int, _int]),
     "skr_format_f32": (_int, [_vp, _i64, _int, _vp, _i64, ctypes.POINTER(_i64)]),
+    "skr_csv_read": (_int, [ctypes.c_char_p, _int, ctypes.POINTER(_vp)]),
+    "skr_csv_free": (None, [_vp]),
+    "skr_csv_rows": (_i64, [_vp]),
+    "skr_csv_cols": (_i64, [_vp]),
+    "skr_csv_values": (_vp, [_vp]),
+    "skr_csv_labels": (_vp, [_vp]),
+    "skr_csv_label_offsets": (_vp, [_vp]),
+    "skr_csv_columns": (_vp, [_vp]),
+    "skr_csv_column_offsets": (_vp, [_vp]),
+    "skr_csv_all_integer": (_int, [_vp]),
     "skr_host_alloc": (_int, [_sz, ctypes.POINTER(_vp)]),
     "skr_host_free": (None, [_vp]),
     "skr_host_pool_trim": (None, []),

@@ -95,6 +95,18 @@ def console_kmer_counts(argv=None):
                      args.log2, args.remove_labels, args.mean_vector, args.std_vector, args.alphabet)
 
 
+def _read_labelled_csv(path):
+    """pd.read_csv(path, index_col=0) -> (values, index labels): the library's multi-threaded parser for the plain
+    files seekr_kmer_counts writes (same binary64 bits as pandas), pandas for everything else."""
+    from . import csv_reader
+
+    parsed = csv_reader.read_counts_csv(path) if isinstance(path, str) else None
+    if parsed is not None:
+        return parsed[0], parsed[1]
+    frame = pd.read_csv(path, index_col=0)
+    return frame, frame.index.values
+
+
 def _run_pearson(counts1, counts2, outfile, binary_input, binary_output):
     # console_scripts.py:620-638
     names1 = None
@@ -103,10 +115,9 @@ def _run_pearson(counts1, counts2, outfile, binary_input, binary_output):
         counts1 = np.load(counts1)
         counts2 = np.load(counts2)
     else:
-        counts1 = pd.read_csv(counts1, index_col=0)
-        counts2 = pd.read_csv(counts2, index_col=0)
-        names1 = counts1.index.values
-        names2 = counts2.index.values
+        same_file = counts1 == counts2
+        counts1, names1 = _read_labelled_csv(counts1)
+        counts2, names2 = (counts1, names1) if same_file else _read_labelled_csv(counts2)
 
     if binary_output:
         pearson.pearson(counts1, counts2, outfile=outfile)

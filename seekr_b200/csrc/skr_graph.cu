@@ -1,0 +1,341 @@
+// Similarity graph of a Pearson matrix: the numeric front half of seekr/kmer_leiden.py (lines 91-107).
+//
+//   ld_sim[ld_sim < pearsoncutoff] = 0 ; np.fill_diagonal(ld_sim, 0)            -> skr_sim_threshold (in place)
+//   (df.values > 0) adjacency + df.values[df.values > 0] weights (row-major)   -> skr_sim_edge_offsets + skr_sim_edge_fill
+//
+// An entry (i, j) of the thresholded matrix is positive exactly when the ORIGINAL value x satisfies
+// !(x < cutoff) && x > 0 && i != j (NaN < cutoff is false, so NaN survives the threshold, and NaN > 0 is false, so it
+// is no edge), hence the edge kernels work on the untouched r matrix and never need the dense thresholded copy.
+// The comparison is made in the matrix's own type with the cutoff converted to it (numpy: a Python scalar is weak).
+//
+// All three passes are HBM-bound streams over the m x n matrix: a CTA owns a row at a time, a thread two
+// 16-byte vectors per step, both loads issued before either is used.  Edges come out in row-major order
+// (np.nonzero order): per-row counts -> one exclusive scan -> ordered compaction inside each row with a
+// ballot-free block scan of per-thread counts.
+#include <cuda_runtime.h>
+
+#include "skr_common.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+template <typename T>
+struct Vec;
+template <>
+struct Vec<float> {
+    using type = float4;
+    static constexpr int N = 4;
+};
+template <>
+struct Vec<double> {
+    using type = double2;
+    static constexpr int N = 2;
+};
+
+template <typename T>
+__device__ __forceinline__ void load_vec(const T* p, T (&v)[Vec<T>::N]) {
+    typename Vec<T>::type q = *reinterpret_cast<const typename Vec<T>::type*>(p);
+    const T* e = reinterpret_cast<const T*>(&q);
+#pragma unroll
+    for (int u = 0; u < Vec<T>::N; ++u) v[u] = e[u];
+}
+
+__device__ __forceinline__ void store_vec(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void store_vec(double* p, const double (&v)[2]) {
+    *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+}
+
+template <typename T>
+__device__ __forceinline__ bool is_edge(T x, T cut, long long i, long long j, long long jmin) {
+    return !(x < cut) && x > T(0) && i != j && j >= jmin;
+}
+
+// Row i, elements [j0, j0 + N): vector load when the whole vector is inside the row and aligned, else scalars
+// (out-of-range lanes read as 0, which is never an edge).
+template <typename T, bool ALIGNED>
+__device__ __forceinline__ void load_row(const T* row, long long j0, long long n, T (&v)[Vec<T>::N]) {
+    constexpr int N = Vec<T>::N;
+    if (ALIGNED && j0 + N <= n) {
+        load_vec<T>(row + j0, v);
+    } else {
+#pragma unroll
+        for (int u = 0; u < N; ++u) v[u] = (j0 + u < n) ? row[j0 + u] : T(0);
+    }
+}
+
+template <typename T, bool ALIGNED>
+__global__ void __launch_bounds__(kThreads) sim_threshold_kernel(T* c, long long m, long long n, long long ld, T cut,
+                                                                 int zero_diag) {
+    constexpr int N = Vec<T>::N;
+    for (long long i = blockIdx.x; i < m; i += gridDim.x) {
+        T* row = c + i * ld;
+        for (long long j0 = (long long)threadIdx.x * N; j0 < n; j0 += (long long)kThreads * N) {
+            T v[N];
+            load_row<T, ALIGNED>(row, j0, n, v);
+            bool touched = false;
+#pragma unroll
+            for (int u = 0; u < N; ++u) {
+                const bool z = (v[u] < cut) || (zero_diag && j0 + u == i);
+                if (z) v[u] = T(0);
+                touched |= z;
+            }
+            if (!touched) continue;  // rows of a dense similarity matrix above the cutoff are left unwritten
+            if (ALIGNED && j0 + N <= n) {
+                store_vec(row + j0, v);
+            } else {
+#pragma unroll
+                for (int u = 0; u < N; ++u)
+                    if (j0 + u < n) row[j0 + u] = v[u];
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ int warp_sum(int x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+
+template <typename T, bool ALIGNED>
+__global__ void __launch_bounds__(kThreads) sim_edge_count_kernel(const T* __restrict__ c, long long m, long long n,
+                                                                  long long ld, T cut, int upper_only,
+                                                                  long long* __restrict__ row_counts) {
+    constexpr int N = Vec<T>::N;
+    constexpr long long STEP = (long long)kThreads * N;
+    __shared__ int warp_tot[kThreads / 32];
+    for (long long i = blockIdx.x; i < m; i += gridDim.x) {
+        const T* row = c + i * ld;
+        const long long jmin = upper_only ? i + 1 : 0;
+        long long j0 = jmin / STEP * STEP + (long long)threadIdx.x * N;  // whole steps before jmin hold no edge
+        long long cnt = 0;
+        for (; j0 < n; j0 += 2 * STEP) {
+            T a[N], b[N];
+            load_row<T, ALIGNED>(row, j0, n, a);
+            load_row<T, ALIGNED>(row, j0 + STEP, n, b);
+#pragma unroll
+            for (int u = 0; u < N; ++u) {
+                cnt += is_edge<T>(a[u], cut, i, j0 + u, jmin);
+                cnt += is_edge<T>(b[u], cut, i, j0 + STEP + u, jmin);
+            }
+        }
+        int w = warp_sum((int)cnt);  // a row holds fewer than 2^31 entries (checked on the host)
+        if ((threadIdx.x & 31) == 0) warp_tot[threadIdx.x >> 5] = w;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            long long t = 0;
+#pragma unroll
+            for (int q = 0; q < kThreads / 32; ++q) t += warp_tot[q];
+            row_counts[i] = t;
+        }
+        __syncthreads();
+    }
+}
+
+// offsets[0] = 0, offsets[i+1] = offsets[i] + counts[i]; counts and offsets + 1 may alias (in-place inclusive scan).
+__global__ void __launch_bounds__(1024) sim_scan_kernel(const long long* counts, long long m, long long* offsets) {
+    __shared__ long long warp_tot[32];
+    __shared__ long long carry_s;
+    if (threadIdx.x == 0) {
+        carry_s = 0;
+        offsets[0] = 0;
+    }
+    __syncthreads();
+    for (long long base = 0; base < m; base += 1024) {
+        const long long idx = base + threadIdx.x;
+        long long x = idx < m ? counts[idx] : 0;
+        long long incl = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            long long y = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((threadIdx.x & 31) >= o) incl += y;
+        }
+        if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            long long t = warp_tot[threadIdx.x], s = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                long long y = __shfl_up_sync(0xffffffffu, s, o);
+                if (threadIdx.x >= o) s += y;
+            }
+            warp_tot[threadIdx.x] = s - t;  // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        const long long carry = carry_s;
+        incl += warp_tot[threadIdx.x >> 5] + carry;
+        if (idx < m) offsets[idx + 1] = incl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = incl;
+        __syncthreads();
+    }
+}
+
+template <typename T, bool ALIGNED>
+__global__ void __launch_bounds__(kThreads) sim_edge_fill_kernel(const T* __restrict__ c, long long m, long long n,
+                                                                 long long ld, T cut, int upper_only,
+                                                                 const long long* __restrict__ offsets,
+                                                                 int* __restrict__ src, int* __restrict__ dst,
+                                                                 T* __restrict__ weight) {
+    constexpr int N = Vec<T>::N;
+    constexpr long long STEP = (long long)kThreads * N;
+    __shared__ int warp_tot[2][kThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long long i = blockIdx.x; i < m; i += gridDim.x) {
+        long long out = offsets[i];
+        if (offsets[i + 1] == out) continue;  // uniform over the CTA
+        const T* row = c + i * ld;
+        const long long jmin = upper_only ? i + 1 : 0;
+        int buf = 0;
+        for (long long j0 = jmin / STEP * STEP + (long long)threadIdx.x * N; j0 - (long long)threadIdx.x * N < n;
+             j0 += 2 * STEP) {
+            // the thread's 2N elements are NOT contiguous (a at j0, b at j0 + STEP): order within the step is
+            // all a-parts of the CTA first, then all b-parts
+            T a[N], b[N];
+            load_row<T, ALIGNED>(row, j0, n, a);
+            load_row<T, ALIGNED>(row, j0 + STEP, n, b);
+            unsigned ma = 0, mb = 0;
+#pragma unroll
+            for (int u = 0; u < N; ++u) {
+                ma |= (unsigned)is_edge<T>(a[u], cut, i, j0 + u, jmin) << u;
+                mb |= (unsigned)is_edge<T>(b[u], cut, i, j0 + STEP + u, jmin) << u;
+            }
+            const int ca = __popc(ma), cb = __popc(mb);
+            // packed pair scan: low half counts the a-parts, high half the b-parts (each < 2^16 per CTA step)
+            unsigned incl = (unsigned)ca | ((unsigned)cb << 16);
+            const unsigned own = incl;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += y;
+            }
+            if (lane == 31) warp_tot[buf][warp] = (int)incl;
+            __syncthreads();
+            unsigned before = 0, total = 0;
+#pragma unroll
+            for (int q = 0; q < kThreads / 32; ++q) {
+                const unsigned t = (unsigned)warp_tot[buf][q];
+                if (q < warp) before += t;
+                total += t;
+            }
+            const unsigned excl = incl - own + before;
+            const long long pa = out + (excl & 0xffffu);
+            const long long pb = out + (total & 0xffffu) + (excl >> 16);
+            int k = 0;
+#pragma unroll
+            for (int u = 0; u < N; ++u)
+                if (ma >> u & 1) {
+                    if (src) src[pa + k] = (int)i;
+                    dst[pa + k] = (int)(j0 + u);
+                    weight[pa + k] = a[u];
+                    ++k;
+                }
+            k = 0;
+#pragma unroll
+            for (int u = 0; u < N; ++u)
+                if (mb >> u & 1) {
+                    if (src) src[pb + k] = (int)i;
+                    dst[pb + k] = (int)(j0 + STEP + u);
+                    weight[pb + k] = b[u];
+                    ++k;
+                }
+            out += (total & 0xffffu) + (total >> 16);
+            buf ^= 1;  // the next step's totals go to the other slot: one barrier per step is enough
+        }
+        __syncthreads();
+    }
+}
+
+int row_grid(long long m) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long grid = (long long)sms * 8;  // 8 resident CTAs of 256 threads per SM, grid-stride over rows
+    return (int)(grid < m ? grid : m);
+}
+
+bool vec_aligned(const void* p, long long ld, int elem) {
+    return (reinterpret_cast<uintptr_t>(p) % 16 == 0) && ((ld * elem) % 16 == 0);
+}
+
+int check_matrix(const char* who, const void* d_c, int64_t m, int64_t n, int64_t ld) {
+    if (!d_c) return skr::fail(SKR_ERR_ARG, "%s: null matrix", who);
+    if (ld < n) return skr::fail(SKR_ERR_ARG, "%s: leading dimension smaller than n", who);
+    if (m >= (1ll << 31) || n >= (1ll << 31)) return skr::fail(SKR_ERR_ARG, "%s: more than 2^31-1 rows or columns", who);
+    return SKR_OK;
+}
+
+}  // namespace
+
+extern "C" int skr_sim_threshold(void* d_c, int c_is_f64, int64_t m, int64_t n, int64_t ld, double cutoff,
+                                 int zero_diagonal, void* stream) {
+    if (m <= 0 || n <= 0) return SKR_OK;
+    if (int rc = check_matrix("skr_sim_threshold", d_c, m, n, ld)) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int grid = row_grid(m);
+    const bool al = vec_aligned(d_c, ld, c_is_f64 ? 8 : 4);
+    const long long M = m, N = n, LD = ld;
+    if (c_is_f64) {
+        if (al) sim_threshold_kernel<double, true><<<grid, kThreads, 0, s>>>((double*)d_c, M, N, LD, cutoff, zero_diagonal);
+        else sim_threshold_kernel<double, false><<<grid, kThreads, 0, s>>>((double*)d_c, M, N, LD, cutoff, zero_diagonal);
+    } else {
+        const float cut = (float)cutoff;
+        if (al) sim_threshold_kernel<float, true><<<grid, kThreads, 0, s>>>((float*)d_c, M, N, LD, cut, zero_diagonal);
+        else sim_threshold_kernel<float, false><<<grid, kThreads, 0, s>>>((float*)d_c, M, N, LD, cut, zero_diagonal);
+    }
+    SKR_LAUNCH_CHECK();
+    return SKR_OK;
+}
+
+extern "C" int skr_sim_edge_offsets(const void* d_c, int c_is_f64, int64_t m, int64_t n, int64_t ld, double cutoff,
+                                    int upper_only, int64_t* d_offsets, void* stream) {
+    if (!d_offsets) return skr::fail(SKR_ERR_ARG, "skr_sim_edge_offsets: null offsets");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (m <= 0 || n <= 0) {
+        SKR_CUDA_CHECK(cudaMemsetAsync(d_offsets, 0, sizeof(int64_t) * (size_t)((m > 0 ? m : 0) + 1), s));
+        return SKR_OK;
+    }
+    if (int rc = check_matrix("skr_sim_edge_offsets", d_c, m, n, ld)) return rc;
+    const int grid = row_grid(m);
+    const bool al = vec_aligned(d_c, ld, c_is_f64 ? 8 : 4);
+    const long long M = m, N = n, LD = ld;
+    long long* counts = (long long*)d_offsets + 1;  // scanned in place
+    if (c_is_f64) {
+        if (al) sim_edge_count_kernel<double, true><<<grid, kThreads, 0, s>>>((const double*)d_c, M, N, LD, cutoff, upper_only, counts);
+        else sim_edge_count_kernel<double, false><<<grid, kThreads, 0, s>>>((const double*)d_c, M, N, LD, cutoff, upper_only, counts);
+    } else {
+        const float cut = (float)cutoff;
+        if (al) sim_edge_count_kernel<float, true><<<grid, kThreads, 0, s>>>((const float*)d_c, M, N, LD, cut, upper_only, counts);
+        else sim_edge_count_kernel<float, false><<<grid, kThreads, 0, s>>>((const float*)d_c, M, N, LD, cut, upper_only, counts);
+    }
+    SKR_LAUNCH_CHECK();
+    sim_scan_kernel<<<1, 1024, 0, s>>>(counts, M, (long long*)d_offsets);
+    SKR_LAUNCH_CHECK();
+    return SKR_OK;
+}
+
+extern "C" int skr_sim_edge_fill(const void* d_c, int c_is_f64, int64_t m, int64_t n, int64_t ld, double cutoff,
+                                 int upper_only, const int64_t* d_offsets, int32_t* d_src, int32_t* d_dst,
+                                 void* d_weight, void* stream) {
+    if (m <= 0 || n <= 0) return SKR_OK;
+    if (int rc = check_matrix("skr_sim_edge_fill", d_c, m, n, ld)) return rc;
+    if (!d_offsets || !d_dst || !d_weight) return skr::fail(SKR_ERR_ARG, "skr_sim_edge_fill: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int grid = row_grid(m);
+    const bool al = vec_aligned(d_c, ld, c_is_f64 ? 8 : 4);
+    const long long M = m, N = n, LD = ld;
+    const long long* off = (const long long*)d_offsets;
+    if (c_is_f64) {
+        if (al) sim_edge_fill_kernel<double, true><<<grid, kThreads, 0, s>>>((const double*)d_c, M, N, LD, cutoff, upper_only, off, d_src, d_dst, (double*)d_weight);
+        else sim_edge_fill_kernel<double, false><<<grid, kThreads, 0, s>>>((const double*)d_c, M, N, LD, cutoff, upper_only, off, d_src, d_dst, (double*)d_weight);
+    } else {
+        const float cut = (float)cutoff;
+        if (al) sim_edge_fill_kernel<float, true><<<grid, kThreads, 0, s>>>((const float*)d_c, M, N, LD, cut, upper_only, off, d_src, d_dst, (float*)d_weight);
+        else sim_edge_fill_kernel<float, false><<<grid, kThreads, 0, s>>>((const float*)d_c, M, N, LD, cut, upper_only, off, d_src, d_dst, (float*)d_weight);
+    }
+    SKR_LAUNCH_CHECK();
+    return SKR_OK;
+}

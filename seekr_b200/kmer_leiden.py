@@ -1,0 +1,105 @@
+"""Similarity graph behind the reference's ``kmer_leiden`` (seekr/kmer_leiden.py:64-107), on the device.
+
+The reference forms ``pearson(counts, counts)`` on the host, zeroes every r below ``pearsoncutoff`` and the
+diagonal, wraps the dense n x n matrix in a DataFrame and hands networkx / igraph a Python list of lists
+(kmer_leiden.py:88-104) -- at 50 000 transcripts that is a 10 GB matrix turned into 2.5e9 Python objects.
+Here the r matrix never leaves the GPU: the symmetric GEMM fills it, and what travels to the host is the edge
+list igraph needs (``skr_sim_edge_offsets`` + ``skr_sim_edge_fill``, row-major = ``np.nonzero`` order) or, for
+callers that do want the DataFrame, the thresholded matrix (``skr_sim_threshold``).
+
+The community detection itself (leidenalg on the igraph graph), the layout and the plots are library work in
+the reference and stay with those libraries: ``leiden_inputs`` returns exactly what they are given.
+"""
+
+import numpy as np
+
+from . import _lib, device
+from . import pearson as skr_pearson
+from .fasta_reader import Reader
+from .kmer_counts import BasicCounter
+
+
+def _device_matrix(sim):
+    torch = device.require_cuda()
+    if isinstance(sim, torch.Tensor):
+        if sim.dim() != 2 or sim.dtype not in (torch.float32, torch.float64) or sim.stride(1) != 1:
+            raise ValueError("similarity matrix must be a 2-D float32 / float64 tensor with unit column stride")
+        return sim, True
+    arr = np.asarray(sim)
+    if arr.ndim != 2:
+        raise ValueError("similarity matrix must be 2-D")
+    if arr.dtype not in (np.float32, np.float64):
+        arr = arr.astype(np.float64)
+    return device.to_device(np.ascontiguousarray(arr)), False
+
+
+def threshold_similarity(sim, pearsoncutoff=0, zero_diagonal=True):
+    """kmer_leiden.py:91-94: ``sim[sim < pearsoncutoff] = 0; np.fill_diagonal(sim, 0)``.
+
+    A device tensor is modified in place and returned; a host array is left alone and a new host array returned."""
+    torch = device.require_cuda()
+    lib = _lib.load()
+    dev, on_device = _device_matrix(sim)
+    m, n = int(dev.shape[0]), int(dev.shape[1])
+    _lib.check(lib.skr_sim_threshold(device.ptr(dev), int(dev.dtype == torch.float64), m, n, dev.stride(0) if m else n,
+                                     float(pearsoncutoff), int(bool(zero_diagonal)), device.stream_ptr(None)))
+    return dev if on_device else device.to_host(dev, pinned=False)
+
+
+def similarity_edges(sim, pearsoncutoff=0, upper_only=False, return_offsets=False, with_sources=True):
+    """Edges of the thresholded, zero-diagonal similarity matrix without forming it (kmer_leiden.py:91-104).
+
+    Returns ``(rows, cols, weights)`` as host arrays (int32, int32, sim's dtype) in row-major order: the order of
+    ``np.nonzero(adj > 0)`` and ``adj[adj > 0]``.  ``upper_only`` keeps j > i (one entry per undirected edge).
+    ``return_offsets`` appends the CSR row offsets (int64, m + 1)."""
+    torch = device.require_cuda()
+    lib = _lib.load()
+    dev, _ = _device_matrix(sim)
+    m, n = int(dev.shape[0]), int(dev.shape[1])
+    is64 = int(dev.dtype == torch.float64)
+    ld = dev.stride(0) if m else n
+    stream = device.stream_ptr(None)
+    offsets = device.empty((m + 1,), torch.int64)
+    _lib.check(lib.skr_sim_edge_offsets(device.ptr(dev), is64, m, n, ld, float(pearsoncutoff), int(bool(upper_only)),
+                                        device.ptr(offsets), stream))
+    total = int(offsets[m].item())  # the one host round trip: sizes the edge arrays
+    cols = device.empty((total,), torch.int32)
+    rows = device.empty((total,), torch.int32) if with_sources else None
+    weights = device.empty((total,), dev.dtype)
+    if total:
+        _lib.check(lib.skr_sim_edge_fill(device.ptr(dev), is64, m, n, ld, float(pearsoncutoff), int(bool(upper_only)),
+                                         device.ptr(offsets), device.ptr(rows) if with_sources else None,
+                                         device.ptr(cols), device.ptr(weights), stream))
+    out = (device.to_host(rows, pinned=False) if with_sources else None, device.to_host(cols, pinned=False),
+           device.to_host(weights, pinned=False))
+    if return_offsets:
+        out = out + (device.to_host(offsets, pinned=False),)
+    return out
+
+
+def leiden_inputs(inputfile, mean, std, k, pearsoncutoff=0, upper_only=True, dense=False):
+    """kmer_leiden.py:70-104 up to the hand-over to igraph: counts with the given vectors -> r -> graph.
+
+    Returns a dict: ``names`` (headers without '>'), ``rows`` / ``cols`` / ``weights`` (the edge list; with
+    ``upper_only=False`` the order and multiplicity of ``df.values[df.values > 0]``), ``offsets`` (CSR), and with
+    ``dense=True`` also ``adjacency``, the thresholded host matrix the reference wraps in a DataFrame.
+    Returns None (after the reference's messages) when the vectors do not match 4**k (kmer_leiden.py:74-78)."""
+    meanfile = np.load(mean) if isinstance(mean, str) else np.asarray(mean)
+    stdfile = np.load(std) if isinstance(std, str) else np.asarray(std)
+    if len(meanfile) != 4 ** k or len(stdfile) != 4 ** k:
+        print('kmer size is not compatible with the normalization mean and/or std files.')
+        print('Please make sure the normalization mean and std files are generated using the same kmer size as specified here in k.')
+        print('No Leiden community is calculated or plotted. The output is None.')
+        return None
+    device.require_cuda()
+    counter = BasicCounter(inputfile, mean=mean, std=std, k=k, silent=True)
+    counter.make_count_file()
+    names = [h[1:] for h in Reader(inputfile).get_headers()]
+    counts = getattr(counter, "counts_device", None)  # still on the device after get_counts()
+    prepared = skr_pearson.prepare(counts if counts is not None else counter.counts)
+    sim = skr_pearson.pearson_device(prepared, prepared)
+    rows, cols, weights, offsets = similarity_edges(sim, pearsoncutoff, upper_only=upper_only, return_offsets=True)
+    out = {"names": names, "rows": rows, "cols": cols, "weights": weights, "offsets": offsets}
+    if dense:
+        out["adjacency"] = device.to_host(threshold_similarity(sim, pearsoncutoff), pinned=False)
+    return out

@@ -1,0 +1,134 @@
+"""GPU parity tests for the similarity graph through the C ABI: thresholding and the edge list
+of kmer_leiden.py:91-104, bit-exact against the oracle and against what the unmodified reference handed to
+networkx / igraph (tests/golden/leiden/)."""
+
+import os
+
+import numpy as np
+import pytest
+
+from oracle import seekr_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(__file__)
+GOLD = os.path.join(HERE, "golden", "leiden")
+MEDIUM = os.path.join(HERE, "golden", "medium.fa")
+CASES = [("c0", 0), ("c005", 0.05), ("c012", 0.12), ("cneg", -0.05)]
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return dict(np.load(os.path.join(GOLD, "leiden.npz")))
+
+
+def _check_edges(sim, cutoff, upper_only):
+    from seekr_b200 import kmer_leiden as kl
+
+    rows, cols, weights, offsets = kl.similarity_edges(sim, cutoff, upper_only=upper_only, return_offsets=True)
+    er, ec, ew = oracle.leiden_edges(sim, cutoff, upper_only=upper_only)
+    assert rows.dtype == np.int32 and cols.dtype == np.int32 and weights.dtype == sim.dtype
+    assert np.array_equal(rows, er) and np.array_equal(cols, ec)
+    assert np.array_equal(weights, ew)
+    assert np.array_equal(offsets, np.concatenate([[0], np.cumsum(np.bincount(er, minlength=sim.shape[0]))]))
+    crows, ccols, cweights = kl.similarity_edges(sim, cutoff, upper_only=upper_only, with_sources=False)
+    assert crows is None and np.array_equal(ccols, ec) and np.array_equal(cweights, ew)
+
+
+@pytest.mark.parametrize("tag,cutoff", CASES)
+def test_threshold_and_edges_bit_exact_on_the_reference_r_matrix(gold, tag, cutoff):
+    from seekr_b200 import kmer_leiden as kl
+
+    sim = gold["sim"]
+    adj = kl.threshold_similarity(sim, cutoff)
+    assert adj.dtype == np.float32 and np.array_equal(adj, gold["adj_" + tag])
+    rows, cols, weights = kl.similarity_edges(sim, cutoff)
+    assert np.array_equal(weights, gold["weight_" + tag])
+    n = sim.shape[0]
+    expected = np.unpackbits(gold["bool_" + tag], axis=1)[:, :n].astype(bool)
+    assert np.array_equal(np.stack(np.nonzero(expected)), np.stack([rows, cols]))
+    _check_edges(sim, cutoff, upper_only=True)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape", [(1, 1), (3, 5), (257, 1023), (130, 4099), (2100, 2100), (40, 9001)])
+def test_ragged_shapes_nan_and_both_types(dtype, shape):
+    from seekr_b200 import kmer_leiden as kl
+
+    rng = np.random.default_rng(shape[0] * 7919 + shape[1])
+    sim = rng.uniform(-1, 1, size=shape).astype(dtype)
+    sim[rng.random(shape) < 0.01] = np.nan
+    sim[rng.random(shape) < 0.01] = 0.0
+    sim[rng.random(shape) < 0.01] = -0.0
+    sim[rng.random(shape) < 0.005] = np.inf
+    for cutoff in (0, 0.7, -0.3, 2.0):
+        assert np.array_equal(kl.threshold_similarity(sim, cutoff), oracle.leiden_adjacency(sim, cutoff), equal_nan=True)
+        for upper_only in (False, True):
+            _check_edges(sim, cutoff, upper_only)
+    # without the diagonal step
+    keep = kl.threshold_similarity(sim, 0.1, zero_diagonal=False)
+    exp = sim.copy()
+    exp[exp < 0.1] = 0
+    assert np.array_equal(keep, exp, equal_nan=True)
+
+
+def test_python_scalar_cutoff_is_compared_in_the_matrix_type():
+    from seekr_b200 import kmer_leiden as kl
+
+    sim = np.array([[0.0, 0.7], [0.7, 0.0]], dtype=np.float32)
+    assert kl.threshold_similarity(sim, 0.7)[0, 1] == np.float32(0.7)
+    assert kl.threshold_similarity(sim.astype(np.float64), 0.7)[0, 1] == 0.0
+    assert len(kl.similarity_edges(sim, 0.7)[2]) == 2
+    assert len(kl.similarity_edges(sim.astype(np.float64), 0.7)[2]) == 0
+
+
+def test_device_views_with_a_row_pitch_and_in_place_threshold():
+    import torch
+
+    from seekr_b200 import device, kmer_leiden as kl
+
+    rng = np.random.default_rng(5)
+    host = rng.uniform(-1, 1, size=(300, 780)).astype(np.float32)
+    big = device.to_device(host)
+    for view, ref in ((big[:, 3:700], host[:, 3:700]), (big[10:200, 4:604], host[10:200, 4:604]),
+                      (big[:, 0:701], host[:, 0:701]), (big[:, 8:778], host[:, 8:778])):
+        rows, cols, weights = kl.similarity_edges(view, 0.2)
+        er, ec, ew = oracle.leiden_edges(ref, 0.2)
+        assert np.array_equal(rows, er) and np.array_equal(cols, ec) and np.array_equal(weights, ew)
+    out = kl.threshold_similarity(big[10:200, 4:604], 0.2)
+    assert isinstance(out, torch.Tensor)
+    exp = host.copy()
+    exp[10:200, 4:604] = oracle.leiden_adjacency(host[10:200, 4:604], 0.2)
+    assert np.array_equal(big.cpu().numpy(), exp)
+
+
+def test_empty_inputs():
+    from seekr_b200 import kmer_leiden as kl
+
+    for shape in ((0, 0), (0, 5), (4, 0)):
+        sim = np.zeros(shape, dtype=np.float32)
+        rows, cols, weights, offsets = kl.similarity_edges(sim, 0, return_offsets=True)
+        assert len(rows) == len(cols) == len(weights) == 0 and np.array_equal(offsets, np.zeros(shape[0] + 1))
+        assert kl.threshold_similarity(sim, 0).shape == shape
+
+
+def test_leiden_inputs_from_fasta(gold):
+    from seekr_b200 import kmer_leiden as kl
+
+    mean, std = os.path.join(GOLD, "mean_k4.npy"), os.path.join(GOLD, "std_k4.npy")
+    assert kl.leiden_inputs(MEDIUM, mean, std, 5) is None  # kmer_leiden.py:74-78
+    for tag, cutoff in CASES:
+        got = kl.leiden_inputs(MEDIUM, mean, std, 4, pearsoncutoff=cutoff, upper_only=False, dense=True)
+        assert got["names"] == list(gold["names"])
+        ref_adj = gold["adj_" + tag]
+        # r itself is within 1e-5 of the reference (sgemm summation order), so an entry may change sides only
+        # when the reference's r is that close to the cutoff or to zero
+        sim = gold["sim"]
+        near = (np.abs(sim - np.float32(cutoff)) < 1e-5) | (np.abs(sim) < 1e-5)
+        assert np.all((np.abs(got["adjacency"] - ref_adj) < 1e-5) | near)
+        mine = np.zeros(ref_adj.shape, dtype=bool)
+        mine[got["rows"], got["cols"]] = True
+        assert np.all((mine == (ref_adj > 0)) | near)
+        assert np.array_equal(got["adjacency"][got["rows"], got["cols"]], got["weights"])
+        upper = kl.leiden_inputs(MEDIUM, mean, std, 4, pearsoncutoff=cutoff)
+        assert np.all(upper["cols"] > upper["rows"]) and abs(2 * len(upper["weights"]) - len(got["weights"])) <= near.sum()
