@@ -228,7 +228,9 @@ enum {
     SKR_DIST_RAYLEIGH = 4,
     SKR_DIST_UNIFORM = 5,
     SKR_DIST_PARETO = 6,   /* pareto(b)       shape = b       */
-    SKR_DIST_EXPONPOW = 7  /* exponpow(b)     shape = b       */
+    SKR_DIST_EXPONPOW = 7, /* exponpow(b)     shape = b       */
+    SKR_DIST_GAMMA = 8,    /* gamma(a)        shape = a   cdf = gammainc(a, x)        (regularised incomplete gamma) */
+    SKR_DIST_CHI2 = 9      /* chi2(df)        shape = df  cdf = gammainc(df/2, x/2)                                  */
 };
 int skr_pval_empirical(const void* d_r, int r_is_f64, int64_t m, int64_t n, int64_t ld, const void* d_sorted_bg,
                        int bg_is_f64, int64_t N, void* d_p, int64_t ldp, void* stream);

@@ -296,13 +296,22 @@ def dist_cdf(family, x, shape=None):
             c, lower, upper = 1 - np.where(x > 1, x, 1.0) ** (-shape), 1.0, np.inf
         elif family == "exponpow":
             c, lower, upper = -np.expm1(-np.expm1(np.where(x > 0, x, 0.0) ** shape)), 0.0, np.inf
+        elif family == "gamma":
+            # gamma._cdf = scipy.special.gammainc(a, x): the reference's own third-party call, not restated
+            from scipy import special
+
+            c, lower, upper = special.gammainc(shape, np.where(x > 0, x, 0.0)), 0.0, np.inf
+        elif family == "chi2":
+            from scipy import special  # chi2._cdf = scipy.special.chdtr(df, x)
+
+            c, lower, upper = special.chdtr(shape, np.where(x > 0, x, 0.0)), 0.0, np.inf
         else:
             raise ValueError("no closed form restated for %r" % (family,))
     out = np.where(x <= lower, 0.0, np.where(x >= upper, 1.0, c))
     return np.where(np.isnan(x), np.nan, out)
 
 
-SHAPED = {"lognorm", "pareto", "exponpow"}
+SHAPED = {"lognorm", "pareto", "exponpow", "gamma", "chi2"}
 
 
 def pval_dist(sim, family, params):

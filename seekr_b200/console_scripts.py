@@ -120,7 +120,7 @@ def _run_pearson(counts1, counts2, outfile, binary_input, binary_output):
         counts2, names2 = (counts1, names1) if same_file else _read_labelled_csv(counts2)
 
     if binary_output:
-        pearson.pearson(counts1, counts2, outfile=outfile)
+        pearson.pearson_to_npy(counts1, counts2, outfile)  # the return value of pearson() is dropped here
     else:
         dist = pearson.pearson(counts1, counts2)
         dist = pd.DataFrame(dist, names1, names2)

@@ -120,8 +120,48 @@ __device__ __forceinline__ double ndtr(double a) {
     return x > 0 ? 1.0 - y : y;
 }
 
-__device__ __forceinline__ double dist_cdf(int kind, double x, double shape) {
+// Regularised lower incomplete gamma P(a, x) in binary64 (scipy.special.gammainc behind gamma._cdf, chdtr behind
+// chi2._cdf): power series for x < a + 1, modified-Lentz continued fraction of Q = 1 - P otherwise.  The factor
+// x^a e^-x / Gamma(a) is formed as exp(c0 - a (mu - log1p(mu))), mu = (x - a) / a, with
+// c0 = a ln a - a - lgamma(a) computed once on the host in extended precision: the large terms a ln x, x and
+// lgamma(a) never meet in binary64, so the relative error stays near 1e-15 (a |mu| eps) instead of a ln(a) eps.
+__device__ double igam_p(double a, double x, double c0) {
+    if (x <= 0.0) return 0.0;
+    if (x == INFINITY) return 1.0;
+    const double mu = (x - a) / a;
+    const double pre = exp(c0 - a * (mu - log1p(mu)));
+    const int kMaxIter = 1 << 20;
+    if (x < a + 1.0) {
+        double ap = a, del = 1.0 / a, sum = del;
+        for (int i = 0; i < kMaxIter; ++i) {
+            ap += 1.0;
+            del *= x / ap;
+            sum += del;
+            if (del < sum * 1e-17) break;
+        }
+        return fmin(sum * pre, 1.0);
+    }
+    const double tiny = 1e-300;
+    double b = x + 1.0 - a, c = 1.0 / tiny, d = 1.0 / b, h = d;
+    for (int i = 1; i <= kMaxIter; ++i) {
+        const double an = -(double)i * ((double)i - a);
+        b += 2.0;
+        d = an * d + b;
+        if (fabs(d) < tiny) d = tiny;
+        c = b + an / c;
+        if (fabs(c) < tiny) c = tiny;
+        d = 1.0 / d;
+        const double del = d * c;
+        h *= del;
+        if (fabs(del - 1.0) < 2e-16) break;
+    }
+    return 1.0 - pre * h;
+}
+
+__device__ __forceinline__ double dist_cdf(int kind, double x, double shape, double aux) {
     switch (kind) {
+        case SKR_DIST_GAMMA: return igam_p(shape, x, aux);
+        case SKR_DIST_CHI2: return igam_p(0.5 * shape, 0.5 * x, aux);
         case SKR_DIST_NORM: return ndtr(x);
         case SKR_DIST_LOGNORM: return x <= 0.0 ? 0.0 : ndtr(log(x) / shape);
         case SKR_DIST_CAUCHY: return atan2(1.0, -x) / 3.14159265358979323846;
@@ -136,8 +176,8 @@ __device__ __forceinline__ double dist_cdf(int kind, double x, double shape) {
 
 template <typename T>
 __global__ void __launch_bounds__(256) pval_dist_kernel(const T* __restrict__ r, long long m, long long n, long long ld,
-                                                        int kind, double shape, double loc, double scale, int valid,
-                                                        T* __restrict__ p, long long ldp) {
+                                                        int kind, double shape, double aux, double loc, double scale,
+                                                        int valid, T* __restrict__ p, long long ldp) {
     for (long long row = blockIdx.y; row < m; row += gridDim.y) {
         const T* rr = r + row * ld;
         T* pr = p + row * ldp;
@@ -146,7 +186,7 @@ __global__ void __launch_bounds__(256) pval_dist_kernel(const T* __restrict__ r,
             double c;
             if (!valid || x != x) c = NAN;
             else if (x == INFINITY) c = 1.0;
-            else c = dist_cdf(kind, x, shape);
+            else c = dist_cdf(kind, x, shape, aux);
             pr[j] = (T)(1.0 - c);
         }
     }
@@ -258,14 +298,21 @@ extern "C" int skr_pval_dist(const void* d_r, int r_is_f64, int64_t m, int64_t n
     if (m <= 0 || n <= 0) return SKR_OK;
     if (!d_r || !d_p) return skr::fail(SKR_ERR_ARG, "skr_pval_dist: null argument");
     if (ld < n || ldp < n) return skr::fail(SKR_ERR_ARG, "skr_pval_dist: leading dimension smaller than n");
-    if (kind < SKR_DIST_NORM || kind > SKR_DIST_EXPONPOW) return skr::fail(SKR_ERR_ARG, "skr_pval_dist: unknown family %d", kind);
-    const bool needs_shape = kind == SKR_DIST_LOGNORM || kind == SKR_DIST_PARETO || kind == SKR_DIST_EXPONPOW;
+    if (kind < SKR_DIST_NORM || kind > SKR_DIST_CHI2) return skr::fail(SKR_ERR_ARG, "skr_pval_dist: unknown family %d", kind);
+    const bool needs_shape = kind == SKR_DIST_LOGNORM || kind == SKR_DIST_PARETO || kind == SKR_DIST_EXPONPOW ||
+                             kind == SKR_DIST_GAMMA || kind == SKR_DIST_CHI2;
     // rv_continuous._argcheck: shape parameters must be > 0; scale must be > 0; otherwise every value is NaN
     const int valid = (scale > 0.0) && (!needs_shape || shape > 0.0) && std::isfinite(loc);
+    double aux = 0.0;
+    if (valid && (kind == SKR_DIST_GAMMA || kind == SKR_DIST_CHI2)) {
+        // c0 = a ln a - a - lgamma(a) in extended precision (see igam_p)
+        const long double a = kind == SKR_DIST_CHI2 ? 0.5L * (long double)shape : (long double)shape;
+        aux = (double)(a * logl(a) - a - lgammal(a));
+    }
     const dim3 grid = grid_2d(m, n);
     cudaStream_t s = (cudaStream_t)stream;
-    if (r_is_f64) pval_dist_kernel<double><<<grid, 256, 0, s>>>((const double*)d_r, m, n, ld, kind, shape, loc, scale, valid, (double*)d_p, ldp);
-    else pval_dist_kernel<float><<<grid, 256, 0, s>>>((const float*)d_r, m, n, ld, kind, shape, loc, scale, valid, (float*)d_p, ldp);
+    if (r_is_f64) pval_dist_kernel<double><<<grid, 256, 0, s>>>((const double*)d_r, m, n, ld, kind, shape, aux, loc, scale, valid, (double*)d_p, ldp);
+    else pval_dist_kernel<float><<<grid, 256, 0, s>>>((const float*)d_r, m, n, ld, kind, shape, aux, loc, scale, valid, (float*)d_p, ldp);
     SKR_LAUNCH_CHECK();
     return SKR_OK;
 }

@@ -19,6 +19,7 @@ from .kmer_counts import BasicCounter
 FAMILIES = {
     "norm": (0, False), "lognorm": (1, True), "cauchy": (2, False), "expon": (3, False),
     "rayleigh": (4, False), "uniform": (5, False), "pareto": (6, True), "exponpow": (7, True),
+    "gamma": (8, True), "chi2": (9, True),
 }
 
 

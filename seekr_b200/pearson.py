@@ -171,3 +171,94 @@ def pearson(counts1, counts2, row_standardize=True, outfile=None):
     if outfile:
         np.save(outfile, dist)
     return dist
+
+
+def pearson_to_npy(counts1, counts2, outfile, row_standardize=True, block_bytes=1 << 30):
+    """``pearson(counts1, counts2, outfile=outfile)`` for callers that drop the return value
+    (console_scripts.py:633-634): the same ``.npy`` bytes as ``np.save``, written block by block.
+
+    The m x n result never exists in host memory: the GEMM fills one of two device row blocks while the previous
+    one travels to one of two pinned staging buffers and a writer thread appends the block before to the file --
+    a 250 000 x 50 000 result (50 GB) needs two staging blocks instead of 50 GB of pinned memory."""
+    import os
+    import queue
+    import threading
+
+    torch = device.require_cuda()
+    lib = _lib.load()
+    if not isinstance(outfile, (str, os.PathLike)):  # an open file object: np.save's own path
+        pearson(counts1, counts2, row_standardize, outfile)
+        return
+    a, a_dev = _as_matrix(counts1)
+    b, b_dev = _as_matrix(counts2)
+    if a.shape[1] != b.shape[1]:
+        raise ValueError("shapes %s and %s not aligned: %d (dim 1) != %d (dim 1)"
+                         % (tuple(a.shape), tuple(b.shape), a.shape[1], b.shape[1]))
+    m, n, K = int(a.shape[0]), int(b.shape[0]), int(a.shape[1])
+    out_f64 = not (_is_f32(a, a_dev) and _is_f32(b, b_dev))
+    np_dtype = np.dtype(np.float64 if out_f64 else np.float32)
+    if m == 0 or n == 0 or K == 0:
+        pearson(counts1, counts2, row_standardize, outfile)
+        return
+    path = os.fspath(outfile)
+    if not path.endswith(".npy"):
+        path += ".npy"  # np.save appends the suffix
+    pa = prepare(counts1, row_standardize)
+    pb = pa if counts2 is counts1 else prepare(counts2, row_standardize)
+    esz = np_dtype.itemsize
+    block = max(128, min((m + 127) // 128 * 128, (int(block_bytes) // (n * esz)) // 128 * 128))
+    tdtype = torch.float64 if out_f64 else torch.float32
+    dev_bufs = [device.empty((min(block, m), n), tdtype) for _ in range(2)]
+    host_bufs = [device.pinned_empty((min(block, m), n), np_dtype) for _ in range(2)]
+    compute = torch.cuda.current_stream()
+    copy = torch.cuda.Stream()
+    alpha = 1.0 / K
+    jobs = queue.Queue()
+    free_host = [threading.Semaphore(1), threading.Semaphore(1)]
+    failure = []
+
+    def writer(handle):
+        while True:
+            job = jobs.get()
+            if job is None:
+                return
+            slot, nrows, event = job
+            try:
+                event.synchronize()
+                if not failure:
+                    handle.write(memoryview(host_bufs[slot][:nrows]).cast("B"))
+            except Exception as exc:  # reported by the caller's thread
+                failure.append(exc)
+            finally:
+                free_host[slot].release()
+
+    with open(path, "wb") as handle:
+        np.lib.format.write_array_header_1_0(handle, {"descr": np.lib.format.dtype_to_descr(np_dtype),
+                                                      "fortran_order": False, "shape": (m, n)})
+        thread = threading.Thread(target=writer, args=(handle,), daemon=True)
+        thread.start()
+        try:
+            dev_free = [None, None]  # copy finished reading dev_bufs[i]
+            for bi, row0 in enumerate(range(0, m, block)):
+                nrows = min(block, m - row0)
+                slot = bi & 1
+                if dev_free[slot] is not None:
+                    compute.wait_event(dev_free[slot])
+                gemm_block(pa, row0, nrows, pb, dev_bufs[slot], alpha, compute)
+                ready = torch.cuda.Event()
+                ready.record(compute)
+                free_host[slot].acquire()  # the writer is done with this staging buffer
+                copy.wait_event(ready)
+                _lib.check(lib.skr_copy_d2h(device.host_ptr(host_bufs[slot]), device.ptr(dev_bufs[slot]),
+                                            nrows * n * esz, device.stream_ptr(copy)))
+                done = torch.cuda.Event()
+                done.record(copy)
+                dev_free[slot] = done
+                jobs.put((slot, nrows, done))
+        finally:
+            jobs.put(None)
+            thread.join()
+        copy.synchronize()
+        compute.synchronize()
+    if failure:
+        raise failure[0]

@@ -68,6 +68,13 @@ FAMILIES = [
     ("exponpow", (1.7, -0.5, 0.9)),
     ("norm", (0.0, -1.0)),
     ("pareto", (-2.0, 0.0, 1.0)),
+    ("gamma", (2.5, -0.4, 0.12)),
+    ("gamma", (120.0, -2.1, 0.0175)),
+    ("gamma", (0.6, -0.3, 0.2)),
+    ("gamma", (4200.0, -7.0, 0.00167)),
+    ("chi2", (7.0, -0.5, 0.07)),
+    ("chi2", (300.0, -3.2, 0.0107)),
+    ("gamma", (-1.0, 0.0, 1.0)),
 ]
 
 

@@ -197,3 +197,57 @@ def test_wide_k_pipeline_matches_oracle(k):
     counter.get_counts()
     assert np.abs(counter.counts - exp).max() < TOL
     assert np.abs(pearson(counter.counts, counter.counts) - po.pearson_f64(exp, exp)).max() < TOL
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_streamed_npy_is_the_file_np_save_writes(tmp_path, dtype):
+    """pearson_to_npy (seekr_pearson -bo, console_scripts.py:633-634) writes the bytes of
+    pearson(..., outfile=...) block by block: ragged last block, several blocks in flight, '.npy' appended."""
+    from seekr_b200.pearson import pearson_to_npy
+
+    rng = np.random.default_rng(21)
+    a = rng.standard_normal((700, 333)).astype(dtype)
+    b = rng.standard_normal((450, 333)).astype(dtype)
+    whole = str(tmp_path / "whole.npy")
+    r = pearson(a, b, outfile=whole)
+    for block_bytes in (1 << 30, 128 * 450 * np.dtype(dtype).itemsize, 256 * 450 * np.dtype(dtype).itemsize):
+        streamed = str(tmp_path / "streamed")  # no suffix: np.save would append it
+        pearson_to_npy(a, b, streamed, block_bytes=block_bytes)
+        assert open(streamed + ".npy", "rb").read() == open(whole, "rb").read()
+        os.remove(streamed + ".npy")
+    assert np.load(whole).dtype == r.dtype
+    # self vs self: pearson() mirrors the upper tiles, the streamed form computes every row block
+    pearson_to_npy(a, a, str(tmp_path / "self.npy"), block_bytes=128 * 700 * np.dtype(dtype).itemsize)
+    got = np.load(str(tmp_path / "self.npy"))
+    assert got.dtype == r.dtype and np.abs(got - pearson(a, a)).max() < 1e-6
+    # empty inputs go through pearson()
+    pearson_to_npy(a[:0], b, str(tmp_path / "empty.npy"))
+    assert np.load(str(tmp_path / "empty.npy")).shape == (0, 450)
+
+
+def test_run_pearson_console_reads_csv_through_the_library(tmp_path, monkeypatch):
+    """seekr_pearson a.csv b.csv: the labelled CSVs seekr writes are parsed by skr_csv_read (pandas' bits),
+    not by pd.read_csv; labels and r come out as with pandas."""
+    import seekr_b200.console_scripts as cs
+
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal((40, 64)).astype(np.float32)
+    y = rng.standard_normal((30, 64)).astype(np.float32)
+    fa, fb = str(tmp_path / "a.csv"), str(tmp_path / "b.csv")
+    pd.DataFrame(x, index=[">a%d" % i for i in range(40)], columns=["k%d" % i for i in range(64)]).to_csv(fa)
+    pd.DataFrame(y, index=[">b%d" % i for i in range(30)], columns=["k%d" % i for i in range(64)]).to_csv(fb)
+    out_pandas = str(tmp_path / "pandas.csv")
+    monkeypatch.setattr("seekr_b200.csv_reader.read_counts_csv", lambda path, threads=0: None)
+    cs._run_pearson(fa, fb, out_pandas, False, False)
+    monkeypatch.undo()
+
+    def no_pandas(*args, **kwargs):
+        raise AssertionError("pd.read_csv must not be needed for a plain labelled CSV")
+
+    monkeypatch.setattr(cs.pd, "read_csv", no_pandas)
+    out_lib = str(tmp_path / "lib.csv")
+    cs._run_pearson(fa, fb, out_lib, False, False)
+    monkeypatch.undo()
+    assert open(out_lib).read() == open(out_pandas).read()
+    exp = po.pearson_f64(pd.read_csv(fa, index_col=0).values, pd.read_csv(fb, index_col=0).values)
+    assert np.abs(pd.read_csv(out_lib, index_col=0).values - exp).max() < TOL

@@ -78,4 +78,5 @@ def test_find_pval_format_checks_mirror_the_reference():
     assert fp.check_main_list([("lognorm", np.float32(0.1), (0.5, 0.0, 1.0)), ("norm", 0.2, (0.0, 1.0))])
     assert not fp.check_main_list([("norm", 0.1, [0.0, 1.0])])
     assert not fp.check_main_list([("norm", 0.1)])
-    assert set(fp.FAMILIES) == {"norm", "lognorm", "cauchy", "expon", "rayleigh", "uniform", "pareto", "exponpow"}
+    assert set(fp.FAMILIES) == {"norm", "lognorm", "cauchy", "expon", "rayleigh", "uniform", "pareto", "exponpow",
+                                "gamma", "chi2"}  # the whole 'common10' list of find_dist.py
