@@ -251,13 +251,16 @@ int skr_pearson_pairs(const uint16_t* d_a_hi, const uint16_t* d_a_lo, const floa
  *                      NaN entries stay NaN.
  * skr_sim_edge_offsets replaces the counting half of kmer_leiden.py:103-104 ((df.values > 0)): entry (i, j) of
  *                      the thresholded, zero-diagonal matrix is positive iff the ORIGINAL value x has
- *                      !(x < cutoff) && x > 0 && i != j, so d_c is the untouched r matrix.  Writes the CSR row
- *                      offsets: d_offsets[0] = 0, d_offsets[i+1] - d_offsets[i] = edges of row i
- *                      (upper_only != 0: only j > i, one entry per undirected edge).  d_offsets holds m+1 values.
+ *                      !(x < cutoff) && x > 0 && i != j, so d_c is the untouched r matrix.  Writes offsets per
+ *                      (row, column slice): d_offsets holds m * SKR_SIM_SLICES + 1 values, d_offsets[0] = 0, row i's
+ *                      edges start at d_offsets[i * SKR_SIM_SLICES] (every SKR_SIM_SLICES-th value is the CSR row
+ *                      offset) and the last value is the edge count (upper_only != 0: only j > i, one entry per
+ *                      undirected edge).
  * skr_sim_edge_fill    replaces kmer_leiden.py:104 (df.values[df.values > 0].flatten()) and np.nonzero of the
  *                      adjacency: edges in row-major order, d_src (may be NULL for CSR form) / d_dst int32,
- *                      d_weight in the matrix's type; each array holds d_offsets[m] entries.
+ *                      d_weight in the matrix's type; each array holds d_offsets[m * SKR_SIM_SLICES] entries.
  * ------------------------------------------------------------------------------------------ */
+#define SKR_SIM_SLICES 8 /* column slices per row in d_offsets */
 int skr_sim_threshold(void* d_c, int c_is_f64, int64_t m, int64_t n, int64_t ld, double cutoff, int zero_diagonal,
                       void* stream);
 int skr_sim_edge_offsets(const void* d_c, int c_is_f64, int64_t m, int64_t n, int64_t ld, double cutoff,

@@ -19,6 +19,7 @@ SKR_ERR_NOMEM = 4
 SKR_ERR_FASTA_BLANK = 5
 SKR_ERR_FASTA_HEADER = 6
 SKR_CSV_UNSUPPORTED = 100
+SIM_SLICES = 8  # SKR_SIM_SLICES
 
 COLPASS_SUM = 0
 COLPASS_CENTERED = 1

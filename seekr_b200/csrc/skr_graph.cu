@@ -8,10 +8,10 @@
 // is no edge), hence the edge kernels work on the untouched r matrix and never need the dense thresholded copy.
 // The comparison is made in the matrix's own type with the cutoff converted to it (numpy: a Python scalar is weak).
 //
-// All three passes are HBM-bound streams over the m x n matrix: a CTA owns a row at a time, a thread two
-// 16-byte vectors per step, both loads issued before either is used.  Edges come out in row-major order
-// (np.nonzero order): per-row counts -> one exclusive scan -> ordered compaction inside each row with a
-// ballot-free block scan of per-thread counts.
+// All three passes are HBM-bound streams over the m x n matrix with 16-byte loads, several issued before the first
+// is used.  Edges come out in row-major order (np.nonzero order): counts per (row, column slice) -> one exclusive
+// scan -> ordered compaction inside each slice by the warp that owns it (shuffle scan of per-lane counts, no
+// CTA-wide barrier; steps without an edge cost one ballot).
 #include <cuda_runtime.h>
 
 #include "skr_common.h"
@@ -100,153 +100,151 @@ __device__ __forceinline__ int warp_sum(int x) {
     return x;
 }
 
+// Work item = (row, slice): a row is cut into kSlices column slices of `width` elements (a multiple of the
+// 32 * N elements a warp loads at once), and every warp of the grid takes items round-robin on its own -- no CTA-wide
+// barrier anywhere.  Item q = row * kSlices + slice counts into counts[q]; the scan over all items gives every
+// item its place in the edge arrays, rows in order and slices in column order inside a row.
+constexpr int kSlices = SKR_SIM_SLICES;
+
 template <typename T, bool ALIGNED>
 __global__ void __launch_bounds__(kThreads) sim_edge_count_kernel(const T* __restrict__ c, long long m, long long n,
-                                                                  long long ld, T cut, int upper_only,
-                                                                  long long* __restrict__ row_counts) {
+                                                                  long long ld, long long width, T cut, int upper_only,
+                                                                  long long* __restrict__ counts) {
     constexpr int N = Vec<T>::N;
-    constexpr long long STEP = (long long)kThreads * N;
-    __shared__ int warp_tot[kThreads / 32];
-    for (long long i = blockIdx.x; i < m; i += gridDim.x) {
-        const T* row = c + i * ld;
+    constexpr long long STEP = 32ll * N;
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * kThreads + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * kThreads) >> 5;
+    for (long long q = warp0; q < m * kSlices; q += nwarps) {
+        const long long i = q / kSlices, sl = q - i * kSlices;
         const long long jmin = upper_only ? i + 1 : 0;
-        long long j0 = jmin / STEP * STEP + (long long)threadIdx.x * N;  // whole steps before jmin hold no edge
-        long long cnt = 0;
-        for (; j0 < n; j0 += 2 * STEP) {
-            T a[N], b[N];
-            load_row<T, ALIGNED>(row, j0, n, a);
-            load_row<T, ALIGNED>(row, j0 + STEP, n, b);
+        const long long jend = (sl + 1) * width < n ? (sl + 1) * width : n;
+        long long jbeg = sl * width;
+        if (jbeg < jmin) jbeg = jmin / STEP * STEP;  // whole steps before jmin hold no edge (jmin >= jbeg: same grid)
+        int cnt = 0;
+        const T* row = c + i * ld;
+        for (long long j0 = jbeg + (long long)lane * N; j0 - (long long)lane * N < jend; j0 += 4 * STEP) {
+            T v[4][N];
 #pragma unroll
-            for (int u = 0; u < N; ++u) {
-                cnt += is_edge<T>(a[u], cut, i, j0 + u, jmin);
-                cnt += is_edge<T>(b[u], cut, i, j0 + STEP + u, jmin);
-            }
-        }
-        int w = warp_sum((int)cnt);  // a row holds fewer than 2^31 entries (checked on the host)
-        if ((threadIdx.x & 31) == 0) warp_tot[threadIdx.x >> 5] = w;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            long long t = 0;
+            for (int w = 0; w < 4; ++w) load_row<T, ALIGNED>(row, j0 + w * STEP, jend, v[w]);
 #pragma unroll
-            for (int q = 0; q < kThreads / 32; ++q) t += warp_tot[q];
-            row_counts[i] = t;
+            for (int w = 0; w < 4; ++w)
+#pragma unroll
+                for (int u = 0; u < N; ++u) cnt += is_edge<T>(v[w][u], cut, i, j0 + w * STEP + u, jmin);
         }
-        __syncthreads();
+        cnt = warp_sum(cnt);
+        if (lane == 0) counts[q] = cnt;
     }
 }
 
 // offsets[0] = 0, offsets[i+1] = offsets[i] + counts[i]; counts and offsets + 1 may alias (in-place inclusive scan).
-__global__ void __launch_bounds__(1024) sim_scan_kernel(const long long* counts, long long m, long long* offsets) {
+// One CTA: every thread sums a run of consecutive counts, the 1024 run totals are scanned through shared memory,
+// and every thread walks its run again writing the running offsets (2 M counts of a 250 000-row matrix: two
+// passes of ~2 000 cached loads per thread instead of 2 000 CTA-wide scan rounds).
+__global__ void __launch_bounds__(1024) sim_scan_kernel(const long long* counts, long long total, long long* offsets) {
     __shared__ long long warp_tot[32];
-    __shared__ long long carry_s;
-    if (threadIdx.x == 0) {
-        carry_s = 0;
-        offsets[0] = 0;
+    const long long chunk = (total + 1023) / 1024;
+    const long long beg = (long long)threadIdx.x * chunk < total ? (long long)threadIdx.x * chunk : total;
+    const long long end = beg + chunk < total ? beg + chunk : total;
+    long long sum = 0;
+#pragma unroll 4
+    for (long long k = beg; k < end; ++k) sum += counts[k];
+    long long incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long y = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((threadIdx.x & 31) >= o) incl += y;
     }
+    if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
     __syncthreads();
-    for (long long base = 0; base < m; base += 1024) {
-        const long long idx = base + threadIdx.x;
-        long long x = idx < m ? counts[idx] : 0;
-        long long incl = x;
+    if (threadIdx.x < 32) {
+        const long long t = warp_tot[threadIdx.x];
+        long long sc = t;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            long long y = __shfl_up_sync(0xffffffffu, incl, o);
-            if ((threadIdx.x & 31) >= o) incl += y;
+            const long long y = __shfl_up_sync(0xffffffffu, sc, o);
+            if (threadIdx.x >= o) sc += y;
         }
-        if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            long long t = warp_tot[threadIdx.x], s = t;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                long long y = __shfl_up_sync(0xffffffffu, s, o);
-                if (threadIdx.x >= o) s += y;
-            }
-            warp_tot[threadIdx.x] = s - t;  // exclusive prefix of the warp totals
-        }
-        __syncthreads();
-        const long long carry = carry_s;
-        incl += warp_tot[threadIdx.x >> 5] + carry;
-        if (idx < m) offsets[idx + 1] = incl;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry_s = incl;
-        __syncthreads();
+        warp_tot[threadIdx.x] = sc - t;  // exclusive prefix of the warp totals
+    }
+    __syncthreads();
+    long long run = incl - sum + warp_tot[threadIdx.x >> 5];
+    if (threadIdx.x == 0) offsets[0] = 0;
+    for (long long k = beg; k < end; ++k) {
+        run += counts[k];
+        offsets[k + 1] = run;
     }
 }
 
 template <typename T, bool ALIGNED>
 __global__ void __launch_bounds__(kThreads) sim_edge_fill_kernel(const T* __restrict__ c, long long m, long long n,
-                                                                 long long ld, T cut, int upper_only,
+                                                                 long long ld, long long width, T cut, int upper_only,
                                                                  const long long* __restrict__ offsets,
                                                                  int* __restrict__ src, int* __restrict__ dst,
                                                                  T* __restrict__ weight) {
     constexpr int N = Vec<T>::N;
-    constexpr long long STEP = (long long)kThreads * N;
-    __shared__ int warp_tot[2][kThreads / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (long long i = blockIdx.x; i < m; i += gridDim.x) {
-        long long out = offsets[i];
-        if (offsets[i + 1] == out) continue;  // uniform over the CTA
-        const T* row = c + i * ld;
+    constexpr long long STEP = 32ll * N;
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * kThreads + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * kThreads) >> 5;
+    for (long long q = warp0; q < m * kSlices; q += nwarps) {
+        long long out = offsets[q];
+        if (offsets[q + 1] == out) continue;  // uniform over the warp
+        const long long i = q / kSlices, sl = q - i * kSlices;
         const long long jmin = upper_only ? i + 1 : 0;
-        int buf = 0;
-        for (long long j0 = jmin / STEP * STEP + (long long)threadIdx.x * N; j0 - (long long)threadIdx.x * N < n;
-             j0 += 2 * STEP) {
-            // the thread's 2N elements are NOT contiguous (a at j0, b at j0 + STEP): order within the step is
-            // all a-parts of the CTA first, then all b-parts
+        const long long jend = (sl + 1) * width < n ? (sl + 1) * width : n;
+        long long jbeg = sl * width;
+        if (jbeg < jmin) jbeg = jmin / STEP * STEP;
+        const T* row = c + i * ld;
+        for (long long j0 = jbeg + (long long)lane * N; j0 - (long long)lane * N < jend; j0 += 2 * STEP) {
+            // column order inside the double step: the 32 a-vectors (j0 ...), then the 32 b-vectors (j0 + STEP ...)
             T a[N], b[N];
-            load_row<T, ALIGNED>(row, j0, n, a);
-            load_row<T, ALIGNED>(row, j0 + STEP, n, b);
+            load_row<T, ALIGNED>(row, j0, jend, a);
+            load_row<T, ALIGNED>(row, j0 + STEP, jend, b);
             unsigned ma = 0, mb = 0;
 #pragma unroll
             for (int u = 0; u < N; ++u) {
                 ma |= (unsigned)is_edge<T>(a[u], cut, i, j0 + u, jmin) << u;
                 mb |= (unsigned)is_edge<T>(b[u], cut, i, j0 + STEP + u, jmin) << u;
             }
-            const int ca = __popc(ma), cb = __popc(mb);
-            // packed pair scan: low half counts the a-parts, high half the b-parts (each < 2^16 per CTA step)
-            unsigned incl = (unsigned)ca | ((unsigned)cb << 16);
-            const unsigned own = incl;
+            if (__ballot_sync(0xffffffffu, (ma | mb) != 0) == 0) continue;  // sparse graphs: most steps hold no edge
+            // packed warp scan: low half counts the a-parts, high half the b-parts (each at most 32 * N)
+            const unsigned own = (unsigned)__popc(ma) | ((unsigned)__popc(mb) << 16);
+            unsigned incl = own;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
+                const unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
                 if (lane >= o) incl += y;
             }
-            if (lane == 31) warp_tot[buf][warp] = (int)incl;
-            __syncthreads();
-            unsigned before = 0, total = 0;
-#pragma unroll
-            for (int q = 0; q < kThreads / 32; ++q) {
-                const unsigned t = (unsigned)warp_tot[buf][q];
-                if (q < warp) before += t;
-                total += t;
-            }
-            const unsigned excl = incl - own + before;
-            const long long pa = out + (excl & 0xffffu);
-            const long long pb = out + (total & 0xffffu) + (excl >> 16);
-            int k = 0;
+            const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+            const unsigned excl = incl - own;
+            long long pa = out + (excl & 0xffffu);
+            long long pb = out + (total & 0xffffu) + (excl >> 16);
 #pragma unroll
             for (int u = 0; u < N; ++u)
                 if (ma >> u & 1) {
-                    if (src) src[pa + k] = (int)i;
-                    dst[pa + k] = (int)(j0 + u);
-                    weight[pa + k] = a[u];
-                    ++k;
+                    if (src) src[pa] = (int)i;
+                    dst[pa] = (int)(j0 + u);
+                    weight[pa] = a[u];
+                    ++pa;
                 }
-            k = 0;
 #pragma unroll
             for (int u = 0; u < N; ++u)
                 if (mb >> u & 1) {
-                    if (src) src[pb + k] = (int)i;
-                    dst[pb + k] = (int)(j0 + STEP + u);
-                    weight[pb + k] = b[u];
-                    ++k;
+                    if (src) src[pb] = (int)i;
+                    dst[pb] = (int)(j0 + STEP + u);
+                    weight[pb] = b[u];
+                    ++pb;
                 }
             out += (total & 0xffffu) + (total >> 16);
-            buf ^= 1;  // the next step's totals go to the other slot: one barrier per step is enough
         }
-        __syncthreads();
     }
+}
+
+// slice width: ceil(n / kSlices) rounded up to the 256 elements a warp covers with two float4 (four double2) loads
+long long slice_width(long long n) {
+    const long long w = (n + kSlices - 1) / kSlices;
+    return (w + 255) / 256 * 256;
 }
 
 int row_grid(long long m) {
@@ -295,24 +293,24 @@ extern "C" int skr_sim_edge_offsets(const void* d_c, int c_is_f64, int64_t m, in
     if (!d_offsets) return skr::fail(SKR_ERR_ARG, "skr_sim_edge_offsets: null offsets");
     cudaStream_t s = (cudaStream_t)stream;
     if (m <= 0 || n <= 0) {
-        SKR_CUDA_CHECK(cudaMemsetAsync(d_offsets, 0, sizeof(int64_t) * (size_t)((m > 0 ? m : 0) + 1), s));
+        SKR_CUDA_CHECK(cudaMemsetAsync(d_offsets, 0, sizeof(int64_t) * (size_t)((m > 0 ? m : 0) * kSlices + 1), s));
         return SKR_OK;
     }
     if (int rc = check_matrix("skr_sim_edge_offsets", d_c, m, n, ld)) return rc;
     const int grid = row_grid(m);
     const bool al = vec_aligned(d_c, ld, c_is_f64 ? 8 : 4);
-    const long long M = m, N = n, LD = ld;
+    const long long M = m, N = n, LD = ld, W = slice_width(n);
     long long* counts = (long long*)d_offsets + 1;  // scanned in place
     if (c_is_f64) {
-        if (al) sim_edge_count_kernel<double, true><<<grid, kThreads, 0, s>>>((const double*)d_c, M, N, LD, cutoff, upper_only, counts);
-        else sim_edge_count_kernel<double, false><<<grid, kThreads, 0, s>>>((const double*)d_c, M, N, LD, cutoff, upper_only, counts);
+        if (al) sim_edge_count_kernel<double, true><<<grid, kThreads, 0, s>>>((const double*)d_c, M, N, LD, W, cutoff, upper_only, counts);
+        else sim_edge_count_kernel<double, false><<<grid, kThreads, 0, s>>>((const double*)d_c, M, N, LD, W, cutoff, upper_only, counts);
     } else {
         const float cut = (float)cutoff;
-        if (al) sim_edge_count_kernel<float, true><<<grid, kThreads, 0, s>>>((const float*)d_c, M, N, LD, cut, upper_only, counts);
-        else sim_edge_count_kernel<float, false><<<grid, kThreads, 0, s>>>((const float*)d_c, M, N, LD, cut, upper_only, counts);
+        if (al) sim_edge_count_kernel<float, true><<<grid, kThreads, 0, s>>>((const float*)d_c, M, N, LD, W, cut, upper_only, counts);
+        else sim_edge_count_kernel<float, false><<<grid, kThreads, 0, s>>>((const float*)d_c, M, N, LD, W, cut, upper_only, counts);
     }
     SKR_LAUNCH_CHECK();
-    sim_scan_kernel<<<1, 1024, 0, s>>>(counts, M, (long long*)d_offsets);
+    sim_scan_kernel<<<1, 1024, 0, s>>>(counts, M * kSlices, (long long*)d_offsets);
     SKR_LAUNCH_CHECK();
     return SKR_OK;
 }
@@ -326,15 +324,15 @@ extern "C" int skr_sim_edge_fill(const void* d_c, int c_is_f64, int64_t m, int64
     cudaStream_t s = (cudaStream_t)stream;
     const int grid = row_grid(m);
     const bool al = vec_aligned(d_c, ld, c_is_f64 ? 8 : 4);
-    const long long M = m, N = n, LD = ld;
+    const long long M = m, N = n, LD = ld, W = slice_width(n);
     const long long* off = (const long long*)d_offsets;
     if (c_is_f64) {
-        if (al) sim_edge_fill_kernel<double, true><<<grid, kThreads, 0, s>>>((const double*)d_c, M, N, LD, cutoff, upper_only, off, d_src, d_dst, (double*)d_weight);
-        else sim_edge_fill_kernel<double, false><<<grid, kThreads, 0, s>>>((const double*)d_c, M, N, LD, cutoff, upper_only, off, d_src, d_dst, (double*)d_weight);
+        if (al) sim_edge_fill_kernel<double, true><<<grid, kThreads, 0, s>>>((const double*)d_c, M, N, LD, W, cutoff, upper_only, off, d_src, d_dst, (double*)d_weight);
+        else sim_edge_fill_kernel<double, false><<<grid, kThreads, 0, s>>>((const double*)d_c, M, N, LD, W, cutoff, upper_only, off, d_src, d_dst, (double*)d_weight);
     } else {
         const float cut = (float)cutoff;
-        if (al) sim_edge_fill_kernel<float, true><<<grid, kThreads, 0, s>>>((const float*)d_c, M, N, LD, cut, upper_only, off, d_src, d_dst, (float*)d_weight);
-        else sim_edge_fill_kernel<float, false><<<grid, kThreads, 0, s>>>((const float*)d_c, M, N, LD, cut, upper_only, off, d_src, d_dst, (float*)d_weight);
+        if (al) sim_edge_fill_kernel<float, true><<<grid, kThreads, 0, s>>>((const float*)d_c, M, N, LD, W, cut, upper_only, off, d_src, d_dst, (float*)d_weight);
+        else sim_edge_fill_kernel<float, false><<<grid, kThreads, 0, s>>>((const float*)d_c, M, N, LD, W, cut, upper_only, off, d_src, d_dst, (float*)d_weight);
     }
     SKR_LAUNCH_CHECK();
     return SKR_OK;

@@ -59,10 +59,11 @@ def similarity_edges(sim, pearsoncutoff=0, upper_only=False, return_offsets=Fals
     is64 = int(dev.dtype == torch.float64)
     ld = dev.stride(0) if m else n
     stream = device.stream_ptr(None)
-    offsets = device.empty((m + 1,), torch.int64)
+    slices = _lib.SIM_SLICES  # offsets per (row, column slice); every slices-th value is the CSR row offset
+    offsets = device.empty((m * slices + 1,), torch.int64)
     _lib.check(lib.skr_sim_edge_offsets(device.ptr(dev), is64, m, n, ld, float(pearsoncutoff), int(bool(upper_only)),
                                         device.ptr(offsets), stream))
-    total = int(offsets[m].item())  # the one host round trip: sizes the edge arrays
+    total = int(offsets[m * slices].item())  # the one host round trip: sizes the edge arrays
     cols = device.empty((total,), torch.int32)
     rows = device.empty((total,), torch.int32) if with_sources else None
     weights = device.empty((total,), dev.dtype)
@@ -73,7 +74,7 @@ def similarity_edges(sim, pearsoncutoff=0, upper_only=False, return_offsets=Fals
     out = (device.to_host(rows, pinned=False) if with_sources else None, device.to_host(cols, pinned=False),
            device.to_host(weights, pinned=False))
     if return_offsets:
-        out = out + (device.to_host(offsets, pinned=False),)
+        out = out + (device.to_host(offsets[::slices].contiguous(), pinned=False),)
     return out
 
 

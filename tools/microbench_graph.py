@@ -32,13 +32,13 @@ def main():
     sim = sim + sim.T
     sim.fill_diagonal_(1.0)
     stream = device.stream_ptr(None)
-    offsets = torch.empty(n + 1, dtype=torch.int64, device="cuda")
+    offsets = torch.empty(n * _lib.SIM_SLICES + 1, dtype=torch.int64, device="cuda")
     nbytes = n * n * 4
     for cutoff, upper in ((0.0, 0), (0.0, 1), (0.15, 0), (0.15, 1), (0.3, 0)):
         def count():
             _lib.check(lib.skr_sim_edge_offsets(device.ptr(sim), 0, n, n, n, cutoff, upper, device.ptr(offsets), stream))
         ms_c = timed(count)
-        total = int(offsets[n].item())
+        total = int(offsets[n * _lib.SIM_SLICES].item())
         dst = torch.empty(total, dtype=torch.int32, device="cuda")
         src = torch.empty(total, dtype=torch.int32, device="cuda")
         w = torch.empty(total, dtype=torch.float32, device="cuda")
