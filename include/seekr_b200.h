@@ -301,12 +301,16 @@ int skr_colstat_exchange(const double* d_acc, void* const* d_peers, int world, i
  * calls of kmer_counts.py:235-241), formatted on `threads` host threads (0 = all), byte-identical to them:
  *   style 0  pandas' cell text for float32 (numpy's shortest round-trip repr; NaN -> empty cell)
  *   style 1  "%1.6f" (np.savetxt)
+ *   style 2  data is a float64 matrix (ld in elements): pandas' cell text for float64 (shortest round-trip repr,
+ *            positional for 1e-4 <= |x| < 1e16; NaN -> empty cell) -- the seekr_pearson CSV output of
+ *            console_scripts.py:636-638
  * header (header_len bytes, may be NULL) is written first; labels + label_offs[m+1] (may be NULL) give the
  * already CSV-quoted first field of every row.  skr_format_f32 formats n values, one per line (for tests).
  * ------------------------------------------------------------------------------------------ */
-int skr_csv_write(const char* path, const float* data, int64_t m, int64_t cols, int64_t ld, const char* header,
+int skr_csv_write(const char* path, const void* data, int64_t m, int64_t cols, int64_t ld, const char* header,
                   int64_t header_len, const char* labels, const int64_t* label_offs, int style, int threads);
 int skr_format_f32(const float* values, int64_t n, int style, char* out, int64_t capacity, int64_t* written);
+int skr_format_f64(const double* values, int64_t n, char* out, int64_t capacity, int64_t* written); /* style 2 */
 
 /* ------------------------------------------------------------------------------------------
  * Text input of a labelled count matrix (replaces pd.read_csv(path, index_col=0) of

@@ -92,6 +92,7 @@ SIGNATURES = {
     "skr_colstat_exchange": (_int, [_vp, _vp, _int, _int, ctypes.c_uint64, _i64, _i64, _i64, _int, _vp, _vp, _vp, _vp]),
     "skr_csv_write": (_int, [ctypes.c_char_p, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _int, _int]),
     "skr_format_f32": (_int, [_vp, _i64, _int, _vp, _i64, ctypes.POINTER(_i64)]),
+    "skr_format_f64": (_int, [_vp, _i64, _vp, _i64, ctypes.POINTER(_i64)]),
     "skr_csv_read": (_int, [ctypes.c_char_p, _int, ctypes.POINTER(_vp)]),
     "skr_csv_free": (None, [_vp]),
     "skr_csv_rows": (_i64, [_vp]),

@@ -123,8 +123,13 @@ def _run_pearson(counts1, counts2, outfile, binary_input, binary_output):
         pearson.pearson_to_npy(counts1, counts2, outfile)  # the return value of pearson() is dropped here
     else:
         dist = pearson.pearson(counts1, counts2)
-        dist = pd.DataFrame(dist, names1, names2)
-        dist.to_csv(outfile)
+        from .kmer_counts import _write_csv
+
+        # DataFrame(dist, names1, names2).to_csv(outfile), formatted on all host threads (same bytes)
+        rows = names1 if names1 is not None else range(dist.shape[0])
+        cols = names2 if names2 is not None else range(dist.shape[1])
+        if not _write_csv(outfile, dist, rows, cols):
+            pd.DataFrame(dist, names1, names2).to_csv(outfile)
 
 
 def console_pearson(argv=None):

@@ -81,6 +81,65 @@ inline char* format_f32_repr(char* out, float v) {
     return out;
 }
 
+// float64 cell text of DataFrame.to_csv: the shortest digits that round-trip as binary64 (Python / numpy repr),
+// positional for 1e-4 <= |x| < 1e16, otherwise d.ddde+XX; NaN -> empty cell.  Needs up to 26 characters.
+inline char* format_f64_repr(char* out, double v) {
+    if (v != v) return out;
+    if (std::isinf(v)) {
+        if (v < 0) *out++ = '-';
+        memcpy(out, "inf", 3);
+        return out + 3;
+    }
+    if (v == 0.0) {
+        if (std::signbit(v)) *out++ = '-';
+        memcpy(out, "0.0", 3);
+        return out + 3;
+    }
+    char sci[40];
+    auto res = std::to_chars(sci, sci + sizeof(sci), v, std::chars_format::scientific);
+    char* p = sci;
+    if (*p == '-') { *out++ = '-'; ++p; }
+    char digits[24];
+    int nd = 0;
+    for (; p < res.ptr && *p != 'e'; ++p)
+        if (*p != '.') digits[nd++] = *p;
+    ++p;
+    int esign = 1;
+    if (*p == '-') { esign = -1; ++p; } else if (*p == '+') { ++p; }
+    int e10 = 0;
+    for (; p < res.ptr; ++p) e10 = e10 * 10 + (*p - '0');
+    e10 *= esign;
+    if (e10 >= -4 && e10 < 16) {
+        if (e10 >= 0) {
+            for (int i = 0; i <= e10; ++i) *out++ = i < nd ? digits[i] : '0';
+            *out++ = '.';
+            if (nd > e10 + 1) {
+                for (int i = e10 + 1; i < nd; ++i) *out++ = digits[i];
+            } else {
+                *out++ = '0';
+            }
+        } else {
+            *out++ = '0';
+            *out++ = '.';
+            for (int i = 0; i < -e10 - 1; ++i) *out++ = '0';
+            for (int i = 0; i < nd; ++i) *out++ = digits[i];
+        }
+    } else {
+        *out++ = digits[0];
+        if (nd > 1) {
+            *out++ = '.';
+            for (int i = 1; i < nd; ++i) *out++ = digits[i];
+        }
+        *out++ = 'e';
+        *out++ = e10 < 0 ? '-' : '+';
+        const int a = e10 < 0 ? -e10 : e10;
+        if (a < 10) *out++ = '0';
+        auto r2 = std::to_chars(out, out + 4, a);
+        out = r2.ptr;
+    }
+    return out;
+}
+
 inline char* format_f32_fixed6(char* out, float v) {
     if (v != v) { memcpy(out, "nan", 3); return out + 3; }
     if (std::isinf(v)) {
@@ -95,7 +154,7 @@ inline char* format_f32_fixed6(char* out, float v) {
 
 constexpr size_t kMaxCell = 56;
 
-void format_rows(const float* data, int64_t r0, int64_t r1, int64_t cols, int64_t ld, const char* labels,
+void format_rows(const void* data_any, int64_t r0, int64_t r1, int64_t cols, int64_t ld, const char* labels,
                  const int64_t* label_offs, int style, std::string& buf) {
     std::vector<char> line;
     for (int64_t r = r0; r < r1; ++r) {
@@ -107,10 +166,18 @@ void format_rows(const float* data, int64_t r0, int64_t r1, int64_t cols, int64_
             p += label_len;
             *p++ = ',';
         }
-        const float* row = data + r * ld;
-        for (int64_t c = 0; c < cols; ++c) {
-            p = style == 0 ? format_f32_repr(p, row[c]) : format_f32_fixed6(p, row[c]);
-            *p++ = c + 1 < cols ? ',' : '\n';
+        if (style == 2) {
+            const double* row = (const double*)data_any + r * ld;
+            for (int64_t c = 0; c < cols; ++c) {
+                p = format_f64_repr(p, row[c]);
+                *p++ = c + 1 < cols ? ',' : '\n';
+            }
+        } else {
+            const float* row = (const float*)data_any + r * ld;
+            for (int64_t c = 0; c < cols; ++c) {
+                p = style == 0 ? format_f32_repr(p, row[c]) : format_f32_fixed6(p, row[c]);
+                *p++ = c + 1 < cols ? ',' : '\n';
+            }
         }
         if (cols == 0) *p++ = '\n';
         buf.append(line.data(), (size_t)(p - line.data()));
@@ -131,9 +198,21 @@ extern "C" int skr_format_f32(const float* values, int64_t n, int style, char* o
     return SKR_OK;
 }
 
-extern "C" int skr_csv_write(const char* path, const float* data, int64_t m, int64_t cols, int64_t ld, const char* header,
+extern "C" int skr_format_f64(const double* values, int64_t n, char* out, int64_t capacity, int64_t* written) {
+    if (!values || !out || !written || n < 0) return skr::fail(SKR_ERR_ARG, "skr_format_f64: bad argument");
+    if (capacity < n * (int64_t)(kMaxCell + 1)) return skr::fail(SKR_ERR_ARG, "skr_format_f64: buffer too small");
+    char* p = out;
+    for (int64_t i = 0; i < n; ++i) {
+        p = format_f64_repr(p, values[i]);
+        *p++ = '\n';
+    }
+    *written = p - out;
+    return SKR_OK;
+}
+
+extern "C" int skr_csv_write(const char* path, const void* data, int64_t m, int64_t cols, int64_t ld, const char* header,
                              int64_t header_len, const char* labels, const int64_t* label_offs, int style, int threads) {
-    if (!path || (!data && m * cols > 0) || m < 0 || cols < 0 || ld < cols || (labels && !label_offs) || style < 0 || style > 1)
+    if (!path || (!data && m * cols > 0) || m < 0 || cols < 0 || ld < cols || (labels && !label_offs) || style < 0 || style > 2)
         return skr::fail(SKR_ERR_ARG, "skr_csv_write: bad argument");
     FILE* f = fopen(path, "wb");
     if (!f) return skr::fail(SKR_ERR_IO, "skr_csv_write: cannot open %s", path);

@@ -700,15 +700,18 @@ class BasicCounter:
 
 def _write_csv(path, counts, names, columns):
     """The text forms of save() written by the library's multi-threaded formatter (skr_csv_write), byte for byte
-    what DataFrame.to_csv (labelled) / np.savetxt(fmt="%1.6f") (bare) produce for a float32 matrix; returns False
-    (caller uses pandas / numpy) for anything else than a C-contiguous 2-D float32 array written to a path."""
+    what DataFrame.to_csv (labelled; float32 or float64 cells) / np.savetxt(fmt="%1.6f") (bare, float32) produce;
+    returns False (caller uses pandas / numpy) for anything else than a C-contiguous 2-D array written to a path."""
     import csv
     import io
 
     import os
 
-    if not (isinstance(counts, np.ndarray) and counts.dtype == np.float32 and counts.ndim == 2 and counts.flags["C_CONTIGUOUS"]):
+    if not (isinstance(counts, np.ndarray) and counts.dtype in (np.float32, np.float64) and counts.ndim == 2
+            and counts.flags["C_CONTIGUOUS"]):
         return False
+    if counts.dtype == np.float64 and names is None:
+        return False  # np.savetxt of a float64 matrix: numpy's own path
     if not (isinstance(path, (str, bytes)) or hasattr(path, "__fspath__")):
         return False  # an open file object: pandas / numpy know what to do with it
     path = os.fspath(path)
@@ -717,7 +720,7 @@ def _write_csv(path, counts, names, columns):
     header = labels = offs = None
     style = 1
     if names is not None:
-        style = 0
+        style = 0 if counts.dtype == np.float32 else 2  # 2: float64 cells (the seekr_pearson output)
         names = list(names)
         if len(names) != m or len(columns) != cols:
             return False  # let pandas raise its own error
@@ -734,7 +737,7 @@ def _write_csv(path, counts, names, columns):
         np.cumsum([len(p) for p in parts], out=offs[1:])
         labels = b"".join(parts)
     data_ptr = counts.ctypes.data if counts.size else None
-    _lib.check(lib.skr_csv_write(path if isinstance(path, bytes) else path.encode(), data_ptr, m, cols, counts.strides[0] // 4 if m else cols,
+    _lib.check(lib.skr_csv_write(path if isinstance(path, bytes) else path.encode(), data_ptr, m, cols, counts.strides[0] // counts.itemsize if m else cols,
                                  header, len(header) if header else 0, labels, offs.ctypes.data if offs is not None else None,
                                  style, 0))
     return True

@@ -98,3 +98,46 @@ def test_save_uses_the_writer_and_matches_the_reference_forms(tmp_path):
     bare.save()
     np.savetxt(tmp_path / "b_ref.csv", counts.astype(np.float64), delimiter=",", fmt="%1.6f")
     assert open(tmp_path / "b.csv", "rb").read() == open(tmp_path / "b_ref.csv", "rb").read()
+
+
+def test_float64_cell_text_equals_pandas():
+    # style 2: the cells of seekr_pearson's CSV output (console_scripts.py:636-638), float64 r values
+    import io
+
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    values = np.concatenate([
+        rng.standard_normal(50000), rng.standard_normal(50000) * 10.0 ** rng.integers(-320, 308, 50000),
+        rng.integers(0, 2 ** 64, 100000, dtype=np.uint64).view(np.float64),
+        np.array([0.0, -0.0, 1e16, 9999999999999998.0, 1e-4, 9.999e-5, 1e15, 123456789012345678.0, 1e22, 1e23, 5e-324,
+                  1.7976931348623157e308, np.inf, -np.inf, np.nan, 1.0, 100.0, 0.1, 0.30000000000000004]),
+        rng.standard_normal(20000).astype(np.float32).astype(np.float64)])
+    cap = values.size * 57
+    buf = ctypes.create_string_buffer(cap)
+    written = ctypes.c_int64()
+    _lib.check(lib.skr_format_f64(values.ctypes.data, values.size, ctypes.addressof(buf), cap, ctypes.byref(written)))
+    mine = buf.raw[:written.value].decode().split("\n")[:-1]
+    text = io.StringIO()
+    pd.DataFrame(values.reshape(-1, 1)).to_csv(text, header=False, index=False)
+    ref = ["" if cell == '""' else cell for cell in text.getvalue().split("\n")[:-1]]
+    assert mine == ref
+
+
+def test_labelled_float64_csv_equals_pandas(tmp_path):
+    rng = np.random.default_rng(4)
+    r = np.clip(rng.normal(0, 0.2, (120, 75)), -1, 1)
+    r[0, :4] = [np.nan, 1.0, -1.0, 1.0000000000000002]
+    names1 = np.array([">q%d|x" % i for i in range(120)], dtype=object)
+    names2 = np.array([">r%d" % i for i in range(75)], dtype=object)
+    ours, ref = str(tmp_path / "a.csv"), str(tmp_path / "b.csv")
+    assert _write_csv(ours, r, names1, names2)
+    pd.DataFrame(r, names1, names2).to_csv(ref)
+    assert open(ours, "rb").read() == open(ref, "rb").read()
+    # binary inputs: no names, pandas labels both axes 0..n-1
+    assert _write_csv(ours, r, range(120), range(75))
+    pd.DataFrame(r, None, None).to_csv(ref)
+    assert open(ours, "rb").read() == open(ref, "rb").read()
+    r32 = r.astype(np.float32)
+    assert _write_csv(ours, r32, range(120), range(75))
+    pd.DataFrame(r32, None, None).to_csv(ref)
+    assert open(ours, "rb").read() == open(ref, "rb").read()
