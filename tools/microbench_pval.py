@@ -32,7 +32,9 @@ def main():
     cases = [("empirical N=1e5", lambda: fp.pval_empirical_device(sim, srt, out=out)),
              ("norm", lambda: fp.pval_dist_device(sim, "norm", (0.02, 0.11), out=out)),
              ("lognorm", lambda: fp.pval_dist_device(sim, "lognorm", (0.35, -0.6, 0.55), out=out)),
-             ("cauchy", lambda: fp.pval_dist_device(sim, "cauchy", (0.01, 0.07), out=out))]
+             ("cauchy", lambda: fp.pval_dist_device(sim, "cauchy", (0.01, 0.07), out=out)),
+             ("gamma a=120", lambda: fp.pval_dist_device(sim, "gamma", (120.0, -2.1, 0.0175), out=out)),
+             ("chi2 df=7", lambda: fp.pval_dist_device(sim, "chi2", (7.0, -0.5, 0.07), out=out))]
     for name, fn in cases:
         ms = timed(fn)
         print("p-values %-16s 20000 x 50000: %7.2f ms  %6.0f GB/s algorithmic (8 B/value)  %6.1f G values/s"
