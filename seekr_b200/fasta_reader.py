@@ -209,7 +209,34 @@ class Reader:
         self.infasta = infasta
         self.outfasta = outfasta
         self.names = names
-        self.data = None
+        self._data = None
+        self._packed = None  # parsed but not yet decoded into ``data``
+
+    # ``data`` is filled as a side effect of get_lines / get_headers / get_seqs in the reference
+    # (fasta_reader.py:65-78).  get_headers() of a 100 MB file should not decode every sequence into a Python
+    # string (300 ms for 30 000 transcripts, against 5 ms for the headers), so the list is built on first use.
+    @property
+    def data(self):
+        if self._data is None and self._packed is not None:
+            self._data = self._lines_of(self._packed)
+            self._packed = None
+        return self._data
+
+    @data.setter
+    def data(self, value):
+        self._data = value
+        self._packed = None
+
+    @staticmethod
+    def _lines_of(packed):
+        if packed.m == 0:
+            return [""]  # what the reference produces for an empty file (fasta_reader.py:62)
+        data = []
+        headers = packed.headers()
+        for i in range(packed.m):
+            data.append(headers[i])
+            data.append(packed.sequence(i))
+        return data
 
     def _parse(self):
         # any 4-letter alphabet will do: only the record structure is used here
@@ -217,23 +244,21 @@ class Reader:
 
     def get_lines(self):
         """[header, SEQ, header, SEQ, ...] (fasta_reader.py:65-68)."""
-        packed = self._parse()
-        if packed.m == 0:
-            self.data = [""]  # what the reference produces for an empty file (fasta_reader.py:62)
-            return self.data
-        data = []
-        headers = packed.headers()
-        for i in range(packed.m):
-            data.append(headers[i])
-            data.append(packed.sequence(i))
-        self.data = data
-        return data
+        self._data = None
+        self._packed = self._parse()
+        return self.data
 
     def get_seqs(self):
         return self.get_lines()[1::2]
 
     def get_headers(self):
-        return self.get_lines()[::2]
+        """Header lines (with '>'); ``data`` is decoded only if somebody reads it afterwards."""
+        packed = self._parse()
+        self._data = None
+        self._packed = packed
+        if packed.m == 0:
+            return self.data[::2]
+        return packed.headers()
 
     def get_data(self, tuples_only=False):
         clean = self.get_lines()

@@ -124,6 +124,7 @@ def find_dist(inputseq='default', k_mer=4, log2='Log2.post', models='common10', 
     np.save(std_path, bkg_norm_counter.std)
 
     bkg_counter = BasicCounter(inputseq, mean=mean_path, std=std_path, k=k_mer, silent=True)
+    bkg_counter._device_only = True  # the counts are only pearson's input (find_dist.py:152-160)
     bkg_counter.make_count_file()
     device_counts = getattr(bkg_counter, "counts_device", None)  # still on the device after get_counts()
     sim_triu = background_r(device_counts if device_counts is not None else bkg_counter.counts,

@@ -111,7 +111,9 @@ def _pvalues(counts1, counts2, transform):
 def _device_counts(counter):
     """The count matrix where get_counts() left it on the device (no second upload); the host copy otherwise."""
     dev = getattr(counter, "counts_device", None)
-    return dev if dev is not None and tuple(dev.shape) == tuple(counter.counts.shape) else counter.counts
+    if dev is not None and (counter.counts is None or tuple(dev.shape) == tuple(counter.counts.shape)):
+        return dev
+    return counter.counts
 
 
 def find_pval(seq1file, seq2file, mean_path, std_path, k_mer, fitres, log2='Log2.post', bestfit=1, outputname=None,
@@ -130,11 +132,12 @@ def find_pval(seq1file, seq2file, mean_path, std_path, k_mer, fitres, log2='Log2
 
     t1 = BasicCounter(seq1file, mean=mean_path, std=std_path, k=k_mer, log2=log2, silent=True)
     t2 = BasicCounter(seq2file, mean=mean_path, std=std_path, k=k_mer, log2=log2, silent=True)
+    t1._device_only = t2._device_only = True  # the counts are only pearson's input (find_pval.py:96-100)
     t1.make_count_file()
     t2.make_count_file()
 
-    header1 = [i[1:] for i in Reader(seq1file).get_headers()]
-    header2 = [i[1:] for i in Reader(seq2file).get_headers()]
+    header1 = [i[1:] for i in t1._headers()]  # Reader(seq1file).get_headers() without a second parse
+    header2 = [i[1:] for i in t2._headers()]
     if len(header1) != len(set(header1)):
         print('The headers of seq1file is not unique.')
         print('Be carefule during further analysis as there are potential indexing problems.')

@@ -15,7 +15,6 @@ import numpy as np
 
 from . import _lib, device
 from . import pearson as skr_pearson
-from .fasta_reader import Reader
 from .kmer_counts import BasicCounter
 
 
@@ -87,15 +86,17 @@ def leiden_inputs(inputfile, mean, std, k, pearsoncutoff=0, upper_only=True, den
     Returns None (after the reference's messages) when the vectors do not match 4**k (kmer_leiden.py:74-78)."""
     meanfile = np.load(mean) if isinstance(mean, str) else np.asarray(mean)
     stdfile = np.load(std) if isinstance(std, str) else np.asarray(std)
-    if len(meanfile) != 4 ** k or len(stdfile) != 4 ** k:
+    # the reference's test, operator precedence included (kmer_leiden.py:74): a chained comparison around `|`
+    if len(meanfile) != 4 ** (k) | len(stdfile) != 4 ** (k):
         print('kmer size is not compatible with the normalization mean and/or std files.')
         print('Please make sure the normalization mean and std files are generated using the same kmer size as specified here in k.')
         print('No Leiden community is calculated or plotted. The output is None.')
         return None
     device.require_cuda()
     counter = BasicCounter(inputfile, mean=mean, std=std, k=k, silent=True)
+    counter._device_only = True  # t1.counts is only pearson's input here (kmer_leiden.py:79-88)
     counter.make_count_file()
-    names = [h[1:] for h in Reader(inputfile).get_headers()]
+    names = [h[1:] for h in counter._headers()]  # Reader(inputfile).get_headers() without a second parse
     counts = getattr(counter, "counts_device", None)  # still on the device after get_counts()
     prepared = skr_pearson.prepare(counts if counts is not None else counter.counts)
     sim = skr_pearson.pearson_device(prepared, prepared)

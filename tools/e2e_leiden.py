@@ -32,6 +32,27 @@ def main():
             dt = time.time() - t0
         print("%d transcripts, k=%d, pearsoncutoff=%g: %d undirected edges, FASTA -> edge list on the host in %.1f ms "
               "(second call; %.1f MB of edges)" % (m, k, cutoff, len(g["weights"]), dt * 1e3, len(g["weights"]) * 12 / 1e6))
+    # where the time goes (cutoff 0.1)
+    from seekr_b200 import device, pearson as sp
+    from seekr_b200.fasta_reader import Reader
+
+    def lap(label, fn):
+        torch.cuda.synchronize()
+        t0 = time.time()
+        out = fn()
+        torch.cuda.synchronize()
+        print("    %-46s %7.1f ms" % (label, (time.time() - t0) * 1e3))
+        return out
+
+    for rep in range(2):
+        print("  breakdown, pass %d" % rep)
+        counter = lap("BasicCounter(...)", lambda: BasicCounter(fasta, mean=mean, std=std, k=k, silent=True))
+        lap("make_count_file() (counts to the host too)", counter.make_count_file)
+        lap("Reader(fasta).get_headers()", lambda: [h[1:] for h in Reader(fasta).get_headers()])
+        prepared = lap("pearson.prepare(device counts)", lambda: sp.prepare(counter.counts_device))
+        sim = lap("pearson_device (symmetric GEMM)", lambda: sp.pearson_device(prepared, prepared))
+        lap("similarity_edges (offsets, fill, D2H)", lambda: kl.similarity_edges(sim, 0.1, upper_only=True, return_offsets=True))
+        del sim, prepared, counter
     # the reference's dense route for comparison: r matrix to the host, threshold + fill_diagonal + nonzero in numpy
     small = min(m, 8000)
     sub = os.path.join(tmp, "sub.fa")
