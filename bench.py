@@ -206,7 +206,7 @@ def run_reference(args):
                     "sample": "%d x %d, K=4096, numpy (OpenBLAS sgemm), all cores" % (prow, prow)},
         "e2e": {"value": value, "unit": "transcripts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -468,13 +468,36 @@ def run_ours(args):
         "gpu_launches": launches,
         "clocks": clocks,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+_JSON_FD = None
+
+
+def quiet_stdout():
+    """Send everything libraries write to stdout (NCCL prints its version banner there) to stderr: the only thing
+    on the real stdout is the one JSON line the contract asks for."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    text = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        os.write(1, text)
+    else:
+        os.write(_JSON_FD, text)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
