@@ -256,17 +256,22 @@ int skr_pearson_pairs(const uint16_t* d_a_hi, const uint16_t* d_a_lo, const floa
  *                      edges start at d_offsets[i * SKR_SIM_SLICES] (every SKR_SIM_SLICES-th value is the CSR row
  *                      offset) and the last value is the edge count (upper_only != 0: only j > i, one entry per
  *                      undirected edge).
+ *                      d_c may be a block of rows of a larger matrix (a row shard of a rank, or one of the row
+ *                      blocks a 250 000 x 250 000 result is produced in): row0 is the index of its first row in the
+ *                      whole matrix, which places the diagonal (column row0 + i) and the upper half; d_src holds
+ *                      whole-matrix row indices.  The same row0 applies to all three entry points.
  * skr_sim_edge_fill    replaces kmer_leiden.py:104 (df.values[df.values > 0].flatten()) and np.nonzero of the
  *                      adjacency: edges in row-major order, d_src (may be NULL for CSR form) / d_dst int32,
  *                      d_weight in the matrix's type; each array holds d_offsets[m * SKR_SIM_SLICES] entries.
  * ------------------------------------------------------------------------------------------ */
 #define SKR_SIM_SLICES 8 /* column slices per row in d_offsets */
-int skr_sim_threshold(void* d_c, int c_is_f64, int64_t m, int64_t n, int64_t ld, double cutoff, int zero_diagonal,
-                      void* stream);
-int skr_sim_edge_offsets(const void* d_c, int c_is_f64, int64_t m, int64_t n, int64_t ld, double cutoff,
+int skr_sim_threshold(void* d_c, int c_is_f64, int64_t m, int64_t n, int64_t ld, int64_t row0, double cutoff,
+                      int zero_diagonal, void* stream);
+int skr_sim_edge_offsets(const void* d_c, int c_is_f64, int64_t m, int64_t n, int64_t ld, int64_t row0, double cutoff,
                          int upper_only, int64_t* d_offsets, void* stream);
-int skr_sim_edge_fill(const void* d_c, int c_is_f64, int64_t m, int64_t n, int64_t ld, double cutoff, int upper_only,
-                      const int64_t* d_offsets, int32_t* d_src, int32_t* d_dst, void* d_weight, void* stream);
+int skr_sim_edge_fill(const void* d_c, int c_is_f64, int64_t m, int64_t n, int64_t ld, int64_t row0, double cutoff,
+                      int upper_only, const int64_t* d_offsets, int32_t* d_src, int32_t* d_dst, void* d_weight,
+                      void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Collectives over NVLink peer memory (one process per GPU; SURVEY section 8e: the Log2.post minimum

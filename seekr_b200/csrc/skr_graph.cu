@@ -74,7 +74,7 @@ __device__ __forceinline__ void load_row(const T* row, long long j0, long long n
 }
 
 template <typename T, bool ALIGNED>
-__global__ void __launch_bounds__(kThreads) sim_threshold_kernel(T* c, long long m, long long n, long long ld, T cut,
+__global__ void __launch_bounds__(kThreads) sim_threshold_kernel(T* c, long long m, long long n, long long ld, long long row0, T cut,
                                                                  int zero_diag) {
     constexpr int N = Vec<T>::N;
     for (long long i = blockIdx.x; i < m; i += gridDim.x) {
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(kThreads) sim_threshold_kernel(T* c, long long
             bool touched = false;
 #pragma unroll
             for (int u = 0; u < N; ++u) {
-                const bool z = (v[u] < cut) || (zero_diag && j0 + u == i);
+                const bool z = (v[u] < cut) || (zero_diag && j0 + u == row0 + i);
                 if (z) v[u] = T(0);
                 touched |= z;
             }
@@ -115,8 +115,8 @@ constexpr int kSlices = SKR_SIM_SLICES;
 
 template <typename T, bool ALIGNED>
 __global__ void __launch_bounds__(kThreads) sim_edge_count_kernel(const T* __restrict__ c, long long m, long long n,
-                                                                  long long ld, long long width, T cut, int upper_only,
-                                                                  long long* __restrict__ counts) {
+                                                                  long long ld, long long row0, long long width, T cut,
+                                                                  int upper_only, long long* __restrict__ counts) {
     constexpr int N = Vec<T>::N;
     constexpr long long STEP = 32ll * N;
     const int lane = threadIdx.x & 31;
@@ -127,7 +127,8 @@ __global__ void __launch_bounds__(kThreads) sim_edge_count_kernel(const T* __res
         // the grid holds a multiple of kSlices warps, so q0 % kSlices is fixed per warp: rotate the slice by the row
         // (with upper_only the left slices of a row are empty -- every warp gets its share of them)
         const long long i = q0 / kSlices, sl = (q0 + i) % kSlices, q = i * kSlices + sl;
-        const long long jmin = upper_only ? i + 1 : 0;
+        const long long g = row0 + i;  // row of the whole matrix: diagonal column, first column of the upper half
+        const long long jmin = upper_only ? g + 1 : 0;
         const long long jend = (sl + 1) * width < n ? (sl + 1) * width : n;
         long long jbeg = sl * width;
         if (jbeg < jmin) jbeg = jmin / STEP * STEP;  // whole steps before jmin hold no edge (jmin >= jbeg: same grid)
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(kThreads) sim_edge_count_kernel(const T* __res
 #pragma unroll
             for (int w = 0; w < 4; ++w) load_row<T, ALIGNED>(row, j0 + w * STEP, jend, v[w]);
             const long long base = j0 - (long long)lane * N;
-            if (base >= jmin && (i < base || i >= base + 4 * STEP)) {
+            if (base >= jmin && (g < base || g >= base + 4 * STEP)) {
                 // no diagonal element and nothing left of jmin in these four steps: one comparison per element
                 // (lanes beyond jend hold zeros)
 #pragma unroll
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(kThreads) sim_edge_count_kernel(const T* __res
 #pragma unroll
                 for (int w = 0; w < 4; ++w)
 #pragma unroll
-                    for (int u = 0; u < N; ++u) cnt += is_edge<T>(v[w][u], cut, i, j0 + w * STEP + u, jmin);
+                    for (int u = 0; u < N; ++u) cnt += is_edge<T>(v[w][u], cut, g, j0 + w * STEP + u, jmin);
             }
         }
         cnt = warp_sum(cnt);
@@ -225,8 +226,8 @@ __global__ void __launch_bounds__(kThreads) sim_chunk_scan_kernel(const long lon
 
 template <typename T, bool ALIGNED>
 __global__ void __launch_bounds__(kThreads) sim_edge_fill_kernel(const T* __restrict__ c, long long m, long long n,
-                                                                 long long ld, long long width, T cut, int upper_only,
-                                                                 const long long* __restrict__ offsets,
+                                                                 long long ld, long long row0, long long width, T cut,
+                                                                 int upper_only, const long long* __restrict__ offsets,
                                                                  int* __restrict__ src, int* __restrict__ dst,
                                                                  T* __restrict__ weight) {
     constexpr int N = Vec<T>::N;
@@ -243,7 +244,8 @@ __global__ void __launch_bounds__(kThreads) sim_edge_fill_kernel(const T* __rest
         const long long i = q0 / kSlices, sl = (q0 + i) % kSlices, q = i * kSlices + sl;  // as in the count kernel
         long long out = offsets[q];
         if (offsets[q + 1] == out) continue;  // uniform over the warp
-        const long long jmin = upper_only ? i + 1 : 0;
+        const long long g = row0 + i;  // row of the whole matrix: diagonal column, first column of the upper half
+        const long long jmin = upper_only ? g + 1 : 0;
         const long long jend = (sl + 1) * width < n ? (sl + 1) * width : n;
         long long jbeg = sl * width;
         if (jbeg < jmin) jbeg = jmin / STEP * STEP;
@@ -260,7 +262,7 @@ __global__ void __launch_bounds__(kThreads) sim_edge_fill_kernel(const T* __rest
             load_row<T, ALIGNED>(row, j0 + 3 * STEP, jend, nb);
             const long long base = j0 - (long long)lane * N;
             unsigned ma = 0, mb = 0;
-            if (base >= jmin && (i < base || i >= base + 2 * STEP)) {
+            if (base >= jmin && (g < base || g >= base + 2 * STEP)) {
 #pragma unroll
                 for (int u = 0; u < N; ++u) {
                     ma |= (unsigned)(a[u] >= thr) << u;
@@ -269,8 +271,8 @@ __global__ void __launch_bounds__(kThreads) sim_edge_fill_kernel(const T* __rest
             } else {
 #pragma unroll
                 for (int u = 0; u < N; ++u) {
-                    ma |= (unsigned)is_edge<T>(a[u], cut, i, j0 + u, jmin) << u;
-                    mb |= (unsigned)is_edge<T>(b[u], cut, i, j0 + STEP + u, jmin) << u;
+                    ma |= (unsigned)is_edge<T>(a[u], cut, g, j0 + u, jmin) << u;
+                    mb |= (unsigned)is_edge<T>(b[u], cut, g, j0 + STEP + u, jmin) << u;
                 }
             }
             if (__ballot_sync(0xffffffffu, (ma | mb) != 0) != 0) {  // sparse graphs: most steps hold no edge
@@ -305,7 +307,7 @@ __global__ void __launch_bounds__(kThreads) sim_edge_fill_kernel(const T* __rest
                     }
                 __syncwarp();
                 for (int r = lane; r < tt; r += 32) {
-                    if (src) src[out + r] = (int)i;
+                    if (src) src[out + r] = (int)g;
                     dst[out + r] = st_col[r];
                     weight[out + r] = st_w[r];
                 }
@@ -348,28 +350,28 @@ int check_matrix(const char* who, const void* d_c, int64_t m, int64_t n, int64_t
 
 }  // namespace
 
-extern "C" int skr_sim_threshold(void* d_c, int c_is_f64, int64_t m, int64_t n, int64_t ld, double cutoff,
+extern "C" int skr_sim_threshold(void* d_c, int c_is_f64, int64_t m, int64_t n, int64_t ld, int64_t row0, double cutoff,
                                  int zero_diagonal, void* stream) {
     if (m <= 0 || n <= 0) return SKR_OK;
     if (int rc = check_matrix("skr_sim_threshold", d_c, m, n, ld)) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     const int grid = row_grid(m);
     const bool al = vec_aligned(d_c, ld, c_is_f64 ? 8 : 4);
-    const long long M = m, N = n, LD = ld;
+    const long long M = m, N = n, LD = ld, R0 = row0;
     if (c_is_f64) {
-        if (al) sim_threshold_kernel<double, true><<<grid, kThreads, 0, s>>>((double*)d_c, M, N, LD, cutoff, zero_diagonal);
-        else sim_threshold_kernel<double, false><<<grid, kThreads, 0, s>>>((double*)d_c, M, N, LD, cutoff, zero_diagonal);
+        if (al) sim_threshold_kernel<double, true><<<grid, kThreads, 0, s>>>((double*)d_c, M, N, LD, R0, cutoff, zero_diagonal);
+        else sim_threshold_kernel<double, false><<<grid, kThreads, 0, s>>>((double*)d_c, M, N, LD, R0, cutoff, zero_diagonal);
     } else {
         const float cut = (float)cutoff;
-        if (al) sim_threshold_kernel<float, true><<<grid, kThreads, 0, s>>>((float*)d_c, M, N, LD, cut, zero_diagonal);
-        else sim_threshold_kernel<float, false><<<grid, kThreads, 0, s>>>((float*)d_c, M, N, LD, cut, zero_diagonal);
+        if (al) sim_threshold_kernel<float, true><<<grid, kThreads, 0, s>>>((float*)d_c, M, N, LD, R0, cut, zero_diagonal);
+        else sim_threshold_kernel<float, false><<<grid, kThreads, 0, s>>>((float*)d_c, M, N, LD, R0, cut, zero_diagonal);
     }
     SKR_LAUNCH_CHECK();
     return SKR_OK;
 }
 
-extern "C" int skr_sim_edge_offsets(const void* d_c, int c_is_f64, int64_t m, int64_t n, int64_t ld, double cutoff,
-                                    int upper_only, int64_t* d_offsets, void* stream) {
+extern "C" int skr_sim_edge_offsets(const void* d_c, int c_is_f64, int64_t m, int64_t n, int64_t ld, int64_t row0,
+                                    double cutoff, int upper_only, int64_t* d_offsets, void* stream) {
     if (!d_offsets) return skr::fail(SKR_ERR_ARG, "skr_sim_edge_offsets: null offsets");
     cudaStream_t s = (cudaStream_t)stream;
     if (m <= 0 || n <= 0) {
@@ -379,15 +381,15 @@ extern "C" int skr_sim_edge_offsets(const void* d_c, int c_is_f64, int64_t m, in
     if (int rc = check_matrix("skr_sim_edge_offsets", d_c, m, n, ld)) return rc;
     const int grid = row_grid(m);
     const bool al = vec_aligned(d_c, ld, c_is_f64 ? 8 : 4);
-    const long long M = m, N = n, LD = ld, W = slice_width(n);
+    const long long M = m, N = n, LD = ld, R0 = row0, W = slice_width(n);
     long long* counts = (long long*)d_offsets + 1;  // scanned in place
     if (c_is_f64) {
-        if (al) sim_edge_count_kernel<double, true><<<grid, kThreads, 0, s>>>((const double*)d_c, M, N, LD, W, cutoff, upper_only, counts);
-        else sim_edge_count_kernel<double, false><<<grid, kThreads, 0, s>>>((const double*)d_c, M, N, LD, W, cutoff, upper_only, counts);
+        if (al) sim_edge_count_kernel<double, true><<<grid, kThreads, 0, s>>>((const double*)d_c, M, N, LD, R0, W, cutoff, upper_only, counts);
+        else sim_edge_count_kernel<double, false><<<grid, kThreads, 0, s>>>((const double*)d_c, M, N, LD, R0, W, cutoff, upper_only, counts);
     } else {
         const float cut = (float)cutoff;
-        if (al) sim_edge_count_kernel<float, true><<<grid, kThreads, 0, s>>>((const float*)d_c, M, N, LD, W, cut, upper_only, counts);
-        else sim_edge_count_kernel<float, false><<<grid, kThreads, 0, s>>>((const float*)d_c, M, N, LD, W, cut, upper_only, counts);
+        if (al) sim_edge_count_kernel<float, true><<<grid, kThreads, 0, s>>>((const float*)d_c, M, N, LD, R0, W, cut, upper_only, counts);
+        else sim_edge_count_kernel<float, false><<<grid, kThreads, 0, s>>>((const float*)d_c, M, N, LD, R0, W, cut, upper_only, counts);
     }
     SKR_LAUNCH_CHECK();
     long long* partial = nullptr;  // stream-ordered scratch: concurrent calls on other streams get their own
@@ -400,24 +402,24 @@ extern "C" int skr_sim_edge_offsets(const void* d_c, int c_is_f64, int64_t m, in
     return SKR_OK;
 }
 
-extern "C" int skr_sim_edge_fill(const void* d_c, int c_is_f64, int64_t m, int64_t n, int64_t ld, double cutoff,
-                                 int upper_only, const int64_t* d_offsets, int32_t* d_src, int32_t* d_dst,
-                                 void* d_weight, void* stream) {
+extern "C" int skr_sim_edge_fill(const void* d_c, int c_is_f64, int64_t m, int64_t n, int64_t ld, int64_t row0,
+                                 double cutoff, int upper_only, const int64_t* d_offsets, int32_t* d_src,
+                                 int32_t* d_dst, void* d_weight, void* stream) {
     if (m <= 0 || n <= 0) return SKR_OK;
     if (int rc = check_matrix("skr_sim_edge_fill", d_c, m, n, ld)) return rc;
     if (!d_offsets || !d_dst || !d_weight) return skr::fail(SKR_ERR_ARG, "skr_sim_edge_fill: null argument");
     cudaStream_t s = (cudaStream_t)stream;
     const int grid = row_grid(m);
     const bool al = vec_aligned(d_c, ld, c_is_f64 ? 8 : 4);
-    const long long M = m, N = n, LD = ld, W = slice_width(n);
+    const long long M = m, N = n, LD = ld, R0 = row0, W = slice_width(n);
     const long long* off = (const long long*)d_offsets;
     if (c_is_f64) {
-        if (al) sim_edge_fill_kernel<double, true><<<grid, kThreads, 0, s>>>((const double*)d_c, M, N, LD, W, cutoff, upper_only, off, d_src, d_dst, (double*)d_weight);
-        else sim_edge_fill_kernel<double, false><<<grid, kThreads, 0, s>>>((const double*)d_c, M, N, LD, W, cutoff, upper_only, off, d_src, d_dst, (double*)d_weight);
+        if (al) sim_edge_fill_kernel<double, true><<<grid, kThreads, 0, s>>>((const double*)d_c, M, N, LD, R0, W, cutoff, upper_only, off, d_src, d_dst, (double*)d_weight);
+        else sim_edge_fill_kernel<double, false><<<grid, kThreads, 0, s>>>((const double*)d_c, M, N, LD, R0, W, cutoff, upper_only, off, d_src, d_dst, (double*)d_weight);
     } else {
         const float cut = (float)cutoff;
-        if (al) sim_edge_fill_kernel<float, true><<<grid, kThreads, 0, s>>>((const float*)d_c, M, N, LD, W, cut, upper_only, off, d_src, d_dst, (float*)d_weight);
-        else sim_edge_fill_kernel<float, false><<<grid, kThreads, 0, s>>>((const float*)d_c, M, N, LD, W, cut, upper_only, off, d_src, d_dst, (float*)d_weight);
+        if (al) sim_edge_fill_kernel<float, true><<<grid, kThreads, 0, s>>>((const float*)d_c, M, N, LD, R0, W, cut, upper_only, off, d_src, d_dst, (float*)d_weight);
+        else sim_edge_fill_kernel<float, false><<<grid, kThreads, 0, s>>>((const float*)d_c, M, N, LD, R0, W, cut, upper_only, off, d_src, d_dst, (float*)d_weight);
     }
     SKR_LAUNCH_CHECK();
     return SKR_OK;

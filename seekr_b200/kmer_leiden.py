@@ -32,25 +32,28 @@ def _device_matrix(sim):
     return device.to_device(np.ascontiguousarray(arr)), False
 
 
-def threshold_similarity(sim, pearsoncutoff=0, zero_diagonal=True):
+def threshold_similarity(sim, pearsoncutoff=0, zero_diagonal=True, row0=0):
     """kmer_leiden.py:91-94: ``sim[sim < pearsoncutoff] = 0; np.fill_diagonal(sim, 0)``.
 
-    A device tensor is modified in place and returned; a host array is left alone and a new host array returned."""
+    A device tensor is modified in place and returned; a host array is left alone and a new host array returned.
+    ``row0``: ``sim`` holds rows row0, row0+1, ... of the whole matrix (its diagonal is at column row0 + i)."""
     torch = device.require_cuda()
     lib = _lib.load()
     dev, on_device = _device_matrix(sim)
     m, n = int(dev.shape[0]), int(dev.shape[1])
     _lib.check(lib.skr_sim_threshold(device.ptr(dev), int(dev.dtype == torch.float64), m, n, dev.stride(0) if m else n,
-                                     float(pearsoncutoff), int(bool(zero_diagonal)), device.stream_ptr(None)))
+                                     int(row0), float(pearsoncutoff), int(bool(zero_diagonal)), device.stream_ptr(None)))
     return dev if on_device else device.to_host(dev, pinned=False)
 
 
-def similarity_edges(sim, pearsoncutoff=0, upper_only=False, return_offsets=False, with_sources=True):
+def similarity_edges(sim, pearsoncutoff=0, upper_only=False, return_offsets=False, with_sources=True, row0=0):
     """Edges of the thresholded, zero-diagonal similarity matrix without forming it (kmer_leiden.py:91-104).
 
     Returns ``(rows, cols, weights)`` as host arrays (int32, int32, sim's dtype) in row-major order: the order of
     ``np.nonzero(adj > 0)`` and ``adj[adj > 0]``.  ``upper_only`` keeps j > i (one entry per undirected edge).
-    ``return_offsets`` appends the CSR row offsets (int64, m + 1)."""
+    ``return_offsets`` appends the CSR row offsets (int64, m + 1).  ``row0``: ``sim`` is a block of rows of the whole
+    matrix starting at row row0 (a rank's shard, or one block of a result produced block by block); ``rows`` are
+    whole-matrix indices."""
     torch = device.require_cuda()
     lib = _lib.load()
     dev, _ = _device_matrix(sim)
@@ -60,14 +63,14 @@ def similarity_edges(sim, pearsoncutoff=0, upper_only=False, return_offsets=Fals
     stream = device.stream_ptr(None)
     slices = _lib.SIM_SLICES  # offsets per (row, column slice); every slices-th value is the CSR row offset
     offsets = device.empty((m * slices + 1,), torch.int64)
-    _lib.check(lib.skr_sim_edge_offsets(device.ptr(dev), is64, m, n, ld, float(pearsoncutoff), int(bool(upper_only)),
+    _lib.check(lib.skr_sim_edge_offsets(device.ptr(dev), is64, m, n, ld, int(row0), float(pearsoncutoff), int(bool(upper_only)),
                                         device.ptr(offsets), stream))
     total = int(offsets[m * slices].item())  # the one host round trip: sizes the edge arrays
     cols = device.empty((total,), torch.int32)
     rows = device.empty((total,), torch.int32) if with_sources else None
     weights = device.empty((total,), dev.dtype)
     if total:
-        _lib.check(lib.skr_sim_edge_fill(device.ptr(dev), is64, m, n, ld, float(pearsoncutoff), int(bool(upper_only)),
+        _lib.check(lib.skr_sim_edge_fill(device.ptr(dev), is64, m, n, ld, int(row0), float(pearsoncutoff), int(bool(upper_only)),
                                          device.ptr(offsets), device.ptr(rows) if with_sources else None,
                                          device.ptr(cols), device.ptr(weights), stream))
     # pageable destination: fresh pinned slabs for a 2.7 GB edge list cost more than they save (measured 1 199 ms
@@ -79,13 +82,17 @@ def similarity_edges(sim, pearsoncutoff=0, upper_only=False, return_offsets=Fals
     return out
 
 
-def leiden_inputs(inputfile, mean, std, k, pearsoncutoff=0, upper_only=True, dense=False):
+_SIM_MAX_BYTES = 96 << 30  # r matrices up to this size are formed whole on the device
+
+
+def leiden_inputs(inputfile, mean, std, k, pearsoncutoff=0, upper_only=True, dense=False, block_bytes=None):
     """kmer_leiden.py:70-104 up to the hand-over to igraph: counts with the given vectors -> r -> graph.
 
     Returns a dict: ``names`` (headers without '>'), ``rows`` / ``cols`` / ``weights`` (the edge list; with
     ``upper_only=False`` the order and multiplicity of ``df.values[df.values > 0]``), ``offsets`` (CSR), and with
     ``dense=True`` also ``adjacency``, the thresholded host matrix the reference wraps in a DataFrame.
-    Returns None (after the reference's messages) when the vectors do not match 4**k (kmer_leiden.py:74-78)."""
+    When the r matrix does not fit on the device (or exceeds ``block_bytes``) it is produced, scanned and dropped in
+    row blocks.  Returns None (after the reference's messages) when the vectors do not match 4**k (kmer_leiden.py:74-78)."""
     meanfile = np.load(mean) if isinstance(mean, str) else np.asarray(mean)
     stdfile = np.load(std) if isinstance(std, str) else np.asarray(std)
     # the reference's test, operator precedence included (kmer_leiden.py:74): a chained comparison around `|`
@@ -101,9 +108,35 @@ def leiden_inputs(inputfile, mean, std, k, pearsoncutoff=0, upper_only=True, den
     names = [h[1:] for h in counter._headers()]  # Reader(inputfile).get_headers() without a second parse
     counts = getattr(counter, "counts_device", None)  # still on the device after get_counts()
     prepared = skr_pearson.prepare(counts if counts is not None else counter.counts)
-    sim = skr_pearson.pearson_device(prepared, prepared)
-    rows, cols, weights, offsets = similarity_edges(sim, pearsoncutoff, upper_only=upper_only, return_offsets=True)
-    out = {"names": names, "rows": rows, "cols": cols, "weights": weights, "offsets": offsets}
+    del counts
+    counter.counts_device = None
+    n = prepared.rows
+    torch = device.require_cuda()
+    budget = int(block_bytes) if block_bytes else min(_SIM_MAX_BYTES, torch.cuda.mem_get_info()[0] // 2)
+    if n * n * 4 <= budget:
+        # the whole r matrix fits: symmetric GEMM (upper tiles + mirror), one extraction
+        sim = skr_pearson.pearson_device(prepared, prepared)
+        rows, cols, weights, offsets = similarity_edges(sim, pearsoncutoff, upper_only=upper_only, return_offsets=True)
+        out = {"names": names, "rows": rows, "cols": cols, "weights": weights, "offsets": offsets}
+        if dense:
+            out["adjacency"] = device.to_host(threshold_similarity(sim, pearsoncutoff), pinned=False)
+        return out
+    # r does not fit (250 000 transcripts: 250 GB): row blocks of r are formed, scanned for edges and dropped
+    block = max(128, (budget // (n * 4)) // 128 * 128)
+    buf = device.empty((min(block, n), n), torch.float32)
+    parts, row_offsets, dense_rows, total = [], [np.zeros(1, dtype=np.int64)], [], 0
+    for row0 in range(0, n, block):
+        nrows = min(block, n - row0)
+        skr_pearson.gemm_block(prepared, row0, nrows, prepared, buf, 1.0 / prepared.K)
+        r, c, w, off = similarity_edges(buf[:nrows], pearsoncutoff, upper_only=upper_only, return_offsets=True, row0=row0)
+        parts.append((r, c, w))
+        row_offsets.append(off[1:] + total)
+        total += int(off[-1])
+        if dense:
+            dense_rows.append(device.to_host(threshold_similarity(buf[:nrows], pearsoncutoff, row0=row0).contiguous(),
+                                             pinned=False))
+    out = {"names": names, "rows": np.concatenate([p[0] for p in parts]), "cols": np.concatenate([p[1] for p in parts]),
+           "weights": np.concatenate([p[2] for p in parts]), "offsets": np.concatenate(row_offsets)}
     if dense:
-        out["adjacency"] = device.to_host(threshold_similarity(sim, pearsoncutoff), pinned=False)
+        out["adjacency"] = np.concatenate(dense_rows, axis=0)
     return out

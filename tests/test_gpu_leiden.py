@@ -132,3 +132,45 @@ def test_leiden_inputs_from_fasta(gold):
         assert np.array_equal(got["adjacency"][got["rows"], got["cols"]], got["weights"])
         upper = kl.leiden_inputs(MEDIUM, mean, std, 4, pearsoncutoff=cutoff)
         assert np.all(upper["cols"] > upper["rows"]) and abs(2 * len(upper["weights"]) - len(got["weights"])) <= near.sum()
+
+
+@pytest.mark.parametrize("upper_only", [False, True])
+def test_row_blocks_of_a_larger_matrix(gold, upper_only):
+    """row0: a rank's row shard, or the row blocks a result too large for the device is produced in -- the pieces
+    concatenate to the whole-matrix answer (diagonal and upper half placed by the global row index)."""
+    from seekr_b200 import kmer_leiden as kl
+
+    sim = gold["sim"]
+    rng = np.random.default_rng(9)
+    wide = rng.uniform(-1, 1, size=(300, 300)).astype(np.float32)
+    for matrix, cuts in ((sim, (0, 50, 128, 160)), (wide, (0, 1, 129, 257, 300))):
+        for cutoff in (0, 0.05):
+            er, ec, ew = oracle.leiden_edges(matrix, cutoff, upper_only=upper_only)
+            parts = [kl.similarity_edges(matrix[a:b], cutoff, upper_only=upper_only, row0=a) for a, b in zip(cuts, cuts[1:])]
+            assert np.array_equal(np.concatenate([p[0] for p in parts]), er)
+            assert np.array_equal(np.concatenate([p[1] for p in parts]), ec)
+            assert np.array_equal(np.concatenate([p[2] for p in parts]), ew)
+            dense = np.concatenate([kl.threshold_similarity(matrix[a:b], cutoff, row0=a) for a, b in zip(cuts, cuts[1:])])
+            assert np.array_equal(dense, oracle.leiden_adjacency(matrix, cutoff))
+
+
+def test_leiden_inputs_in_row_blocks_equals_the_whole_matrix_route(gold):
+    from seekr_b200 import kmer_leiden as kl
+
+    mean, std = os.path.join(GOLD, "mean_k4.npy"), os.path.join(GOLD, "std_k4.npy")
+    sim = gold["sim"]
+    for cutoff in (0, 0.05):
+        whole = kl.leiden_inputs(MEDIUM, mean, std, 4, pearsoncutoff=cutoff, upper_only=False, dense=True)
+        blocks = kl.leiden_inputs(MEDIUM, mean, std, 4, pearsoncutoff=cutoff, upper_only=False, dense=True,
+                                  block_bytes=128 * 160 * 4)  # two row blocks: 128 + 32 rows
+        assert blocks["names"] == whole["names"] and blocks["adjacency"].shape == whole["adjacency"].shape
+        assert blocks["offsets"].shape == whole["offsets"].shape and blocks["offsets"][-1] == len(blocks["weights"])
+        near = (np.abs(sim - np.float32(cutoff)) < 1e-5) | (np.abs(sim) < 1e-5)
+        assert np.all((np.abs(blocks["adjacency"] - whole["adjacency"]) < 1e-5) | near)
+        a = np.zeros(sim.shape, dtype=bool)
+        a[whole["rows"], whole["cols"]] = True
+        b = np.zeros(sim.shape, dtype=bool)
+        b[blocks["rows"], blocks["cols"]] = True
+        assert np.all((a == b) | near)
+        assert np.array_equal(blocks["adjacency"][blocks["rows"], blocks["cols"]], blocks["weights"])
+        assert np.all(np.diff(blocks["offsets"]) == np.bincount(blocks["rows"], minlength=160))

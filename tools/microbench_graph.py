@@ -36,7 +36,7 @@ def main():
     nbytes = n * n * 4
     for cutoff, upper in ((0.0, 0), (0.0, 1), (0.15, 0), (0.15, 1), (0.3, 0)):
         def count():
-            _lib.check(lib.skr_sim_edge_offsets(device.ptr(sim), 0, n, n, n, cutoff, upper, device.ptr(offsets), stream))
+            _lib.check(lib.skr_sim_edge_offsets(device.ptr(sim), 0, n, n, n, 0, cutoff, upper, device.ptr(offsets), stream))
         ms_c = timed(count)
         total = int(offsets[n * _lib.SIM_SLICES].item())
         dst = torch.empty(total, dtype=torch.int32, device="cuda")
@@ -44,7 +44,7 @@ def main():
         w = torch.empty(total, dtype=torch.float32, device="cuda")
 
         def fill():
-            _lib.check(lib.skr_sim_edge_fill(device.ptr(sim), 0, n, n, n, cutoff, upper, device.ptr(offsets),
+            _lib.check(lib.skr_sim_edge_fill(device.ptr(sim), 0, n, n, n, 0, cutoff, upper, device.ptr(offsets),
                                              device.ptr(src), device.ptr(dst), device.ptr(w), stream))
         ms_f = timed(fill)
         read = nbytes * (0.5 if upper else 1.0)
@@ -70,7 +70,7 @@ def main():
     work = sim.clone()
 
     def thr():
-        _lib.check(lib.skr_sim_threshold(device.ptr(work), 0, n, n, n, 0.15, 1, stream))
+        _lib.check(lib.skr_sim_threshold(device.ptr(work), 0, n, n, n, 0, 0.15, 1, stream))
     work.copy_(sim)
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
