@@ -121,9 +121,10 @@ def get_counts(fasta, k=6, mean=True, std=True, log2="Log2.post", alphabet="AGTC
     return local, (begin, end), mean_h, std_h, full
 
 
-def pearson_rows(counts_local, counts_ref, row_standardize=True):
+def pearson_rows(counts_local, counts_ref, row_standardize=True, on_device=False):
     """Row block of pearson(counts1, counts2): this rank's rows of counts1 against ALL rows of counts2.
-    counts_ref is read on rank 0 only (other ranks may pass None); its split planes are broadcast."""
+    counts_ref is read on rank 0 only (other ranks may pass None); its split planes are broadcast.
+    on_device: return the device tensor (for consumers that keep working on the GPU) instead of a host array."""
     import torch
     import torch.distributed as dist
 
@@ -147,4 +148,15 @@ def pearson_rows(counts_local, counts_ref, row_standardize=True):
     out = device.empty((pa.rows, n), torch.float32)
     if pa.rows and n:
         skr_pearson.gemm_block(pa, 0, pa.rows, pb, out, 1.0 / K)
-    return device.to_host(out)
+    return out if on_device else device.to_host(out)
+
+
+def similarity_edges_rows(counts_local, row_begin, counts_full, pearsoncutoff=0, upper_only=True):
+    """This rank's part of the kmer_leiden similarity graph (kmer_leiden.py:88-104) when the transcripts are
+    sharded by rows: r of the local rows against all rows, then the edges of that row block with whole-matrix row
+    indices (``row_begin`` = index of the rank's first row).  No collective beyond pearson_rows' broadcast: the
+    ranks' edge lists, concatenated in rank order, are the whole-matrix list.  Returns (rows, cols, weights)."""
+    from . import kmer_leiden
+
+    r_local = pearson_rows(counts_local, counts_full, on_device=True)
+    return kmer_leiden.similarity_edges(r_local, pearsoncutoff, upper_only=upper_only, row0=int(row_begin))

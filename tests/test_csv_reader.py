@@ -132,3 +132,19 @@ def test_everything_else_goes_to_pandas(tmp_path, case):
 def test_missing_file_raises(tmp_path):
     with pytest.raises(Exception):
         csv_reader.read_counts_csv(str(tmp_path / "absent.csv"))
+
+
+def test_write_then_read_round_trip_at_count_matrix_width(tmp_path):
+    """2 000 x 4 096 float32 z-scores through skr_csv_write and back through skr_csv_read: the cells come back as
+    the binary64 values of the float32 numbers (the shortest float32 text names exactly one float32)."""
+    from seekr_b200.kmer_counts import _write_csv
+
+    rng = np.random.default_rng(12)
+    x = rng.standard_normal((2000, 4096)).astype(np.float32)
+    names = [">ENST%08d.%d|gene" % (i, i % 7) for i in range(2000)]
+    path = str(tmp_path / "counts.csv")
+    assert _write_csv(path, x, names, ["k%d" % i for i in range(4096)])
+    values, labels, columns = csv_reader.read_counts_csv(path)
+    assert values.dtype == np.float64 and values.shape == x.shape
+    assert np.array_equal(values.astype(np.float32), x)
+    assert list(labels) == names and columns[0] == "k0" and columns[-1] == "k4095"

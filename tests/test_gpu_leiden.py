@@ -174,3 +174,51 @@ def test_leiden_inputs_in_row_blocks_equals_the_whole_matrix_route(gold):
         assert np.all((a == b) | near)
         assert np.array_equal(blocks["adjacency"][blocks["rows"], blocks["cols"]], blocks["weights"])
         assert np.all(np.diff(blocks["offsets"]) == np.bincount(blocks["rows"], minlength=160))
+
+
+def test_full_size_properties_on_a_symmetric_matrix():
+    """n = 20 000 (1.6 GB, every slice and many items per warp): the directed list has twice the undirected edges,
+    counts / order / weights agree with a torch evaluation of the same predicate, offsets are the row histogram."""
+    import torch
+
+    from seekr_b200 import _lib, device
+
+    lib = _lib.load()
+    n = 20000
+    g = torch.Generator(device="cuda").manual_seed(3)
+    sim = torch.tanh(torch.randn(n, n, device="cuda", generator=g) * 0.1 + 0.01)
+    sim = torch.triu(sim, 1)
+    sim = sim + sim.T
+    sim.fill_diagonal_(1.0)
+    sim[17, 4000:4100] = float("nan")
+    sim[4000:4100, 17] = float("nan")  # symmetric, so that the directed count stays twice the undirected one
+    stream = device.stream_ptr(None)
+    slices = _lib.SIM_SLICES
+    totals = {}
+    for upper in (0, 1):
+        offsets = torch.empty(n * slices + 1, dtype=torch.int64, device="cuda")
+        _lib.check(lib.skr_sim_edge_offsets(device.ptr(sim), 0, n, n, n, 0, 0.12, upper, device.ptr(offsets), stream))
+        total = int(offsets[-1].item())
+        src = torch.empty(total, dtype=torch.int32, device="cuda")
+        dst = torch.empty(total, dtype=torch.int32, device="cuda")
+        w = torch.empty(total, dtype=torch.float32, device="cuda")
+        _lib.check(lib.skr_sim_edge_fill(device.ptr(sim), 0, n, n, n, 0, 0.12, upper, device.ptr(offsets), device.ptr(src),
+                                         device.ptr(dst), device.ptr(w), stream))
+        totals[upper] = total
+        assert bool((offsets[1:] >= offsets[:-1]).all())
+        rows_hist = torch.bincount(src.long(), minlength=n)
+        assert torch.equal(offsets[::slices][1:] - offsets[::slices][:-1], rows_hist)
+        key = src.long() * n + dst.long()
+        assert bool((key[1:] > key[:-1]).all()), "edges are not in row-major order"
+        assert torch.equal(sim[src.long(), dst.long()], w) and bool((w >= 0.12).all())
+        assert bool((dst > src).all()) if upper else bool((dst != src).all())
+        pos = 0
+        for r0 in range(0, n, 5000):  # the same predicate in torch, block by block
+            blk = sim[r0:r0 + 5000]
+            mask = (~(blk < 0.12)) & (blk > 0)
+            rows = torch.arange(r0, r0 + blk.shape[0], device="cuda")[:, None]
+            cols = torch.arange(n, device="cuda")[None, :]
+            mask &= (cols > rows) if upper else (cols != rows)
+            pos += int(mask.sum().item())
+        assert pos == total
+    assert totals[0] == 2 * totals[1] and totals[1] > 1000000

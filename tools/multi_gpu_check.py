@@ -30,6 +30,21 @@ def main():
                                                              gather=True)
     r_local = sharded.pearson_rows(vec_local, vec_full if rank == 0 else None)
     ok = True
+    # the rank's part of the similarity graph: edges of its row block, whole-matrix indices, no collective
+    e_rows, e_cols, e_w = sharded.similarity_edges_rows(vec_local, vb, vec_full if rank == 0 else None, 0.05, upper_only=True)
+    mask = ~(r_local < np.float32(0.05)) & (r_local > 0)
+    grow = vb + np.arange(r_local.shape[0])[:, None]
+    mask &= np.arange(r_local.shape[1])[None, :] > grow
+    xr, xc = np.nonzero(mask)
+    same_edges = np.array_equal(e_rows, xr + vb) and np.array_equal(e_cols, xc) and np.array_equal(e_w, r_local[mask])
+    flag = torch.tensor([1 if same_edges else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    counts_t = torch.tensor([len(e_w)], device="cuda")
+    dist.all_reduce(counts_t)
+    if rank == 0:
+        print("similarity graph per row shard (cutoff 0.05, upper half): equal to numpy on every rank's r block: %s, "
+              "%d undirected edges over all ranks" % (bool(flag.item()), int(counts_t.item())))
+        ok &= bool(flag.item())
     if rank == 0:
         for mode in ("Log2.post", "Log2.none"):
             ref = BasicCounter(path, k=k, log2=mode, silent=True)
