@@ -76,6 +76,11 @@ def pval_dist_device(r, distname, params, out=None, stream=None):
                         % (distname, 3 if has_shape else 2, len(params)))
     shape = params[0] if has_shape else 0.0
     loc, scale = params[-2], params[-1]
+    if distname in ("gamma", "chi2") and shape * (0.5 if distname == "chi2" else 1.0) > 1e6:
+        # series / continued fraction need ~10 sqrt(a) terms per value: beyond a = 1e6 that is minutes per 1e9 values
+        raise NotImplementedError("%s with shape %g: the incomplete-gamma evaluation on the device is limited to "
+                                  "a <= 1e6 (a fit this close to a normal distribution is better served by 'norm')"
+                                  % (distname, shape))
     if out is None:
         out = device.empty(tuple(r.shape), r.dtype)
     m, n = int(r.shape[0]), int(r.shape[1])

@@ -97,6 +97,8 @@ def test_distribution_mode_rejects_unknown_family(gold):
         fp.pval_dist_device(_dev(gold["sim"]), "weibull_min", (2.0, 0.0, 1.0))
     with pytest.raises(TypeError):
         fp.pval_dist_device(_dev(gold["sim"]), "lognorm", (0.0, 1.0))
+    with pytest.raises(NotImplementedError):
+        fp.pval_dist_device(_dev(gold["sim"]), "gamma", (5e6, -100.0, 2e-5))
 
 
 def test_find_pval_end_to_end_matches_reference(gold, tmp_path, capsys):
@@ -185,3 +187,22 @@ def test_pearson_pairs_against_binary64():
     got = fd.pearson_pairs(sp.prepare(a), sp.prepare(b), i, j)
     want = oracle.pearson_f64(a, b)[i, j]
     assert np.max(np.abs(got - want)) <= 2e-6
+
+
+@pytest.mark.parametrize("family", ["gamma", "chi2"])
+@pytest.mark.parametrize("a", [0.3, 1.0, 2.5, 20.0, 1000.0, 1e5])
+def test_incomplete_gamma_against_scipy_in_binary64(family, a):
+    """float64 r matrix, so nothing hides behind the rounding to float32: x spans a +- 3 sqrt(a) (and the lower tail
+    for small a); the oracle calls scipy.special.gammainc / chdtr, the functions behind gamma._cdf / chi2._cdf."""
+    from seekr_b200 import find_pval as fp
+
+    rng = np.random.default_rng(int(a * 10) + len(family))
+    r = rng.uniform(-1, 1, size=(64, 257))
+    shape = a if family == "gamma" else 2.0 * a
+    unit = 1.0 if family == "gamma" else 2.0  # chi2(df).cdf(x) = P(df/2, x/2)
+    scale = 1.0 / (3.0 * np.sqrt(a) * unit) if a > 1 else 1.0 / (6.0 * unit)
+    loc = -max(a, 1.0) * unit * scale
+    got = _host(fp.pval_dist_device(_dev(r), family, (shape, loc, scale)))
+    exp = oracle.pval_dist(r, family, (shape, loc, scale))
+    assert got.dtype == np.float64 and np.array_equal(np.isnan(got), np.isnan(exp))
+    assert np.abs(got - exp).max() <= (1e-13 if a >= 1e5 else 5e-15), np.abs(got - exp).max()
