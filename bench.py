@@ -512,6 +512,18 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return 0
+        # torchrun exports OMP_NUM_THREADS=1 to every rank; this arm is the CPU implementation on ALL host cores
+        # (OpenMP in the C port, OpenBLAS in numpy), and both read the variable when they load: start over with it set
+        want = str(os.cpu_count() or 1)
+        if os.environ.get("OMP_NUM_THREADS", want) != want and "SKR_BENCH_REEXEC" not in os.environ:
+            env = dict(os.environ, OMP_NUM_THREADS=want, OPENBLAS_NUM_THREADS=want, SKR_BENCH_REEXEC="1")
+            sys.stdout.flush()
+            sys.stderr.flush()
+            if _JSON_FD is not None:
+                os.dup2(_JSON_FD, 1)
+            os.execve(sys.executable, [sys.executable] + sys.argv, env)
         return run_reference(args)
     return run_ours(args)
 
