@@ -206,3 +206,19 @@ def test_incomplete_gamma_against_scipy_in_binary64(family, a):
     exp = oracle.pval_dist(r, family, (shape, loc, scale))
     assert got.dtype == np.float64 and np.array_equal(np.isnan(got), np.isnan(exp))
     assert np.abs(got - exp).max() <= (1e-13 if a >= 1e5 else 5e-15), np.abs(got - exp).max()
+
+
+def test_find_pval_with_a_gamma_fit_matches_reference(gold):
+    """find_pval(fitres = find_dist output whose best fit is gamma / chi2): FASTA -> counts -> r -> 1 - cdf on the device
+    against the unmodified reference (r itself agrees to 1e-5; |dp/dr| <= max pdf / scale, a few units here)."""
+    from seekr_b200 import find_pval as fp
+
+    kw = dict(seq1file=SMALL, seq2file=MEDIUM, mean_path=os.path.join(GOLD, "mean_k3.npy"),
+              std_path=os.path.join(GOLD, "std_k3.npy"), k_mer=3, log2="Log2.post", progress_bar=False)
+    for n, (family, params) in enumerate(gold["families"]):
+        if family not in ("gamma", "chi2") or params[0] <= 0 or params[0] > 1000:
+            continue
+        frame = fp.find_pval(fitres=[("norm", 5.0, (0.0, 1.0)), (family, 0.01, tuple(params))], bestfit=2, **kw)
+        assert list(frame.index) == list(gold["rows"]) and list(frame.columns) == list(gold["cols"])
+        got = frame.to_numpy()
+        assert got.dtype == np.float32 and np.abs(got - gold[f"{family}_{n}"]).max() < 2e-4, (family, params)
