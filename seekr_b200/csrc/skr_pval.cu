@@ -131,31 +131,56 @@ __device__ double igam_p(double a, double x, double c0) {
     const double mu = (x - a) / a;
     const double pre = exp(c0 - a * (mu - log1p(mu)));
     const int kMaxIter = 1 << 20;
+    // Both expansions run as numerator / denominator recurrences WITHOUT a division per term (a binary64 division is
+    // ~40 instructions, the recurrences are 4-6): the first version, `del *= x / ap` and Lentz' two divisions per
+    // step, took 234 ms per 1e9 values at a = 120.
     if (x < a + 1.0) {
-        double ap = a, del = 1.0 / a, sum = del;
+        // sum_n x^n / (a (a+1) ... (a+n)) = S_n / D_n:  N_n = N_{n-1} x,  S_n = S_{n-1} (a+n) + N_n,  D_n = D_{n-1} (a+n)
+        double ap = a, N = 1.0, S = 1.0, D = a;
         for (int i = 0; i < kMaxIter; ++i) {
             ap += 1.0;
-            del *= x / ap;
-            sum += del;
-            if (del < sum * 1e-17) break;
+            N *= x;
+            S = fma(S, ap, N);
+            D *= ap;
+            if (N < S * 1e-17) break;
+            if (D > 0x1p600) {  // exact rescaling by a power of two
+                N *= 0x1p-600;
+                S *= 0x1p-600;
+                D *= 0x1p-600;
+            }
         }
-        return fmin(sum * pre, 1.0);
+        return fmin(S / D * pre, 1.0);
     }
-    const double tiny = 1e-300;
-    double b = x + 1.0 - a, c = 1.0 / tiny, d = 1.0 / b, h = d;
+    // Q = pre * continued fraction, convergents p_k / q_k by the forward recurrence (the form cephes' igamc uses),
+    // compared every fourth step
+    double y = 1.0 - a, z = x + y + 1.0, c = 0.0;
+    double pkm2 = 1.0, qkm2 = x, pkm1 = x + 1.0, qkm1 = z * x;
+    double ans = pkm1 / qkm1;
     for (int i = 1; i <= kMaxIter; ++i) {
-        const double an = -(double)i * ((double)i - a);
-        b += 2.0;
-        d = an * d + b;
-        if (fabs(d) < tiny) d = tiny;
-        c = b + an / c;
-        if (fabs(c) < tiny) c = tiny;
-        d = 1.0 / d;
-        const double del = d * c;
-        h *= del;
-        if (fabs(del - 1.0) < 2e-16) break;
+        c += 1.0;
+        y += 1.0;
+        z += 2.0;
+        const double yc = y * c;
+        const double pk = fma(pkm1, z, -(pkm2 * yc));
+        const double qk = fma(qkm1, z, -(qkm2 * yc));
+        pkm2 = pkm1;
+        pkm1 = pk;
+        qkm2 = qkm1;
+        qkm1 = qk;
+        if (fabs(pk) > 0x1p500) {
+            pkm2 *= 0x1p-500;
+            pkm1 *= 0x1p-500;
+            qkm2 *= 0x1p-500;
+            qkm1 *= 0x1p-500;
+        }
+        if ((i & 3) == 0 && qk != 0.0) {
+            const double r = pk / qk;
+            const bool done = fabs(ans - r) <= fabs(r) * 1.2e-16;
+            ans = r;
+            if (done) break;
+        }
     }
-    return 1.0 - pre * h;
+    return 1.0 - pre * ans;
 }
 
 __device__ __forceinline__ double dist_cdf(int kind, double x, double shape, double aux) {
