@@ -69,6 +69,15 @@ int skr_pack_fasta_file(const char* path, const uint8_t* lut, int nthreads, int 
 int skr_pack_sequences(const void* letters, const int64_t* offs, int64_t m, const uint8_t* lut, int nthreads,
                        int pinned, SkrPacked** out);
 void skr_packed_free(SkrPacked* p);
+/* skr_pack_fasta_buffer in two halves for the streamed path: the call returns once the text has been scanned (the
+ * record table -- lengths, block offsets, header / body spans' offsets -- is final and every error of the
+ * synchronous call has been reported), while `nthreads` background threads fill codes and mask in record order.
+ * `text` must stay valid until skr_packed_wait returns.  skr_packed_wait_records blocks until records [0, upto)
+ * are packed (upto < 0: all); skr_packed_wait also ends the background threads; skr_packed_free waits first. */
+int skr_pack_fasta_buffer_async(const void* text, size_t nbytes, const uint8_t* lut, int nthreads, int pinned,
+                                SkrPacked** out);
+int skr_packed_wait_records(SkrPacked* p, int64_t upto);
+int skr_packed_wait(SkrPacked* p);
 
 int64_t skr_packed_num_records(const SkrPacked* p);
 int64_t skr_packed_num_blocks(const SkrPacked* p);  /* including the trailing pad block */
@@ -115,6 +124,89 @@ int skr_count(const uint32_t* d_codes, const uint32_t* d_mask, const uint64_t* d
               const uint32_t* d_lengths, int64_t m, int k, int log2_pre, const void* d_mean, const void* d_std,
               int vec_is_f64, void* d_out, int out_is_f64, int64_t ld_out, SkrMinCell* d_min, const SkrMinCell* d_post,
               const float* d_rstd, void* stream);
+
+/* Speculative Log2.post (seekr_kmer_counts -mv -sv, kmer_counts.py:207-209 in ONE pass over the matrix).
+ * With supplied vectors (finite mean, finite std > 0) the z-score fl(fl(x - mean_j) / std_j) is monotone in the
+ * count value x >= 0, so the matrix-wide minimum is min_j fl(fl(0 - mean_j) / std_j) whenever the arg-min column j*
+ * holds a zero count in some record -- which any realistic input does.  skr_post_spec derives that shift and j*
+ * from the vectors alone (identical on every rank of a sharded run: no collective before counting);
+ * skr_count_ex applies the Log2.post tail with it in its epilogue and sets zero_seen when it meets a zero count
+ * in column j*.  The fallback launches (count with a running minimum, skr_post_log2_skip) are enqueued behind
+ * it with d_skip = &zero_seen: they return at once when the speculation held, and redo the matrix the
+ * two-pass way when it did not -- the choice is made on the device, the host never waits. */
+typedef struct {
+    SkrMinCell shift;   /* the speculated matrix minimum, in the form the Log2.post tail reads (d_post) */
+    int32_t zero_col;   /* j*; -1 when there is nothing to speculate on */
+    uint32_t zero_seen; /* set by the count kernels once a record with a zero count in column j* was seen */
+} SkrPostSpec;
+int skr_post_spec(const void* d_mean, const void* d_std, int vec_is_f64, int64_t cols, SkrPostSpec* d_spec, void* stream);
+
+/* skr_count with every optional piece in one argument block (zero-initialise, then fill what is needed).
+ * Beyond skr_count's arguments:
+ *   d_colmin   per-column minima of the un-normalised values (what skr_count_colmin returns; no vectors then);
+ *              d_out may be NULL for a minima-only pass
+ *   d_colsum / d_colsq   accurate column statistics in the same pass (k = 6, plain counts): every thread sums
+ *              the values and squares of its own columns over its records in fp32 and adds them here (binary64
+ *              atomics, arrays zeroed by the caller) when it is done; skr_colstat_finish turns them into the
+ *              fp32 mean / std vectors (binary64: mean = S1/rows, var = S2/rows - mean^2).  Closer to the exact
+ *              value than numpy's sequential fp32 sums, hence not bit-identical to the reference
+ *              (skr_col_pass is the order-exact route); one exchange of 2 * 4^k doubles when sharded
+ *   d_spec     speculative Log2.post (above): d_post must point at d_spec->shift
+ *   d_skip     the launch returns at once when *d_skip != 0 */
+typedef struct {
+    const uint32_t* d_codes;
+    const uint32_t* d_mask;
+    const uint64_t* d_block_offsets;
+    const uint32_t* d_lengths;
+    int64_t m;
+    int32_t k;
+    int32_t log2_pre;
+    const void* d_mean;
+    const void* d_std;
+    const float* d_rstd;
+    int32_t vec_is_f64;
+    int32_t out_is_f64;
+    void* d_out;
+    int64_t ld_out;
+    SkrMinCell* d_min;
+    const SkrMinCell* d_post;
+    uint32_t* d_colmin;
+    double* d_colsum;
+    double* d_colsq;
+    SkrPostSpec* d_spec;
+    const uint32_t* d_skip;
+} SkrCountArgs;
+int skr_count_ex(const SkrCountArgs* args, void* stream);
+int skr_colstat_finish(const double* d_colsum, const double* d_colsq, int64_t cols, int64_t total_rows, float* d_mean,
+                       float* d_std, int* d_flags /* [2]: mean, std; bit 0 not finite, bit 1 not positive */, void* stream);
+/* skr_post_log2 that returns at once when *d_skip != 0 */
+int skr_post_log2_skip(float* d_a, int64_t m, int64_t cols, int64_t ld, const SkrMinCell* d_min, const uint32_t* d_skip,
+                       void* stream);
+
+/* Streamed get_counts() (replaces the read-everything / count-everything / copy-everything sequence of
+ * fasta_reader.py:41-63 + kmer_counts.py:196-200 when rows are independent once the vectors are known):
+ * follows a packer started with skr_pack_fasta_buffer_async chunk by chunk -- pack chunk i+2 || H2D chunk i+1 ||
+ * count chunk i || D2H chunk i-1 -- on two internal copy streams and the caller's `stream`.
+ *   count        template for the per-chunk skr_count_ex calls: k, log2_pre, vectors, d_out (the WHOLE m x ld_out
+ *                device matrix, rows are filled chunk by chunk), d_post / d_spec (speculative Log2.post), ...;
+ *                the four packed-input pointers and m are filled in per chunk
+ *   d_slab       device buffer of skr_packed_slab_bytes bytes: the packed arrays arrive here, same layout as the
+ *                host slab (afterwards it is a complete device copy, usable with skr_count)
+ *   h_out/h_ld   host destination (pitch in elements), or NULL to leave the result on the device;
+ *                h_out_pinned != 0: page-locked memory, written directly by the copy engine; 0: pageable memory,
+ *                reached through a ring of four small pinned slots drained by copy_threads host threads
+ *   chunk_records  0 = about 32 MB of output rows per chunk
+ * Returns when every row has reached the host (the copy streams are synchronised; `stream` is not). */
+typedef struct {
+    SkrCountArgs count;
+    void* d_slab;
+    float* h_out;
+    int64_t h_ld;
+    int32_t h_out_pinned;
+    int32_t copy_threads;
+    int64_t chunk_records;
+} SkrStreamArgs;
+int skr_stream_counts(SkrPacked* packed, const SkrStreamArgs* args, void* stream);
 
 /* Deferred normalisation for Log2.post with known, finite mean / positive std vectors (the
  * seekr_kmer_counts -mv -sv path): the count kernel writes the un-normalised values and keeps the
@@ -283,7 +375,7 @@ int skr_sim_edge_fill(const void* d_c, int c_is_f64, int64_t m, int64_t n, int64
  *                      tagged with `epoch`, into every peer's buffer (P2P stores) and reduces the `world` cells
  *                      that arrive in its own.  d_peers[t] = rank t's buffer as mapped here (d_peers[rank] = own
  *                      buffer), each 2 * world 64-bit words.  epoch starts at 1 and grows by 1 per call on every
- *                      rank.  *d_err becomes 1 if a peer did not show up within 4 s.
+ *                      rank.  *d_err becomes 1 if a peer did not show up within the spin limit.
  * ------------------------------------------------------------------------------------------ */
 int skr_peer_alloc(size_t bytes, void** d_out, unsigned char* handle64);
 int skr_peer_open(const unsigned char* handle64, void** d_out);
@@ -291,6 +383,11 @@ int skr_peer_close(void* d_ptr);
 int skr_peer_free(void* d_ptr);
 int skr_min_exchange(SkrMinCell* d_cell, void* const* d_peers, int world, int rank, uint64_t epoch, int* d_err,
                      void* stream);
+/* the same, but the launch returns at once when *d_skip != 0 (d_skip may be NULL); every rank must hold the same
+ * value there -- the speculative Log2.post route exchanges its flag first.  The spin limit of both exchanges is
+ * 60 s, or SEEKR_B200_PEER_TIMEOUT_S. */
+int skr_min_exchange_skip(SkrMinCell* d_cell, void* const* d_peers, int world, int rank, uint64_t epoch,
+                          const uint32_t* d_skip, int* d_err, void* stream);
 /* skr_colstat_exchange   all-reduce(sum) of the n binary64 column partials of skr_col_partial_f64 over the ranks,
  *                      fused with skr_col_finish_f64 (divide by the total row count, optional sqrt, fp32, quality
  *                      flag) in ONE kernel: P2P stores of the partials into every peer, an epoch flag per rank, a
@@ -342,6 +439,7 @@ int skr_csv_all_integer(const SkrCsvTable* t); /* 1: every cell is an integer li
  * Host <-> device plumbing used by the Python layer (thin wrappers; no reference counterpart)
  * ------------------------------------------------------------------------------------------ */
 int skr_host_alloc(size_t bytes, void** out); /* pinned host memory from the library's pool */
+int skr_host_alloc_pooled(size_t bytes, void** out); /* only if the pool holds a slab that large: *out = NULL otherwise */
 void skr_host_free(void* p);                  /* returns it to the pool */
 void skr_host_pool_trim(void);                /* releases every pooled slab */
 int skr_copy_h2d(void* d_dst, const void* h_src, size_t bytes, void* stream);

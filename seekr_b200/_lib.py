@@ -31,6 +31,31 @@ _int = ctypes.c_int
 _sz = ctypes.c_size_t
 _dbl = ctypes.c_double
 
+
+
+class CountArgs(ctypes.Structure):
+    """SkrCountArgs (include/seekr_b200.h): every optional piece of skr_count_ex in one block."""
+
+    _fields_ = [
+        ("d_codes", _vp), ("d_mask", _vp), ("d_block_offsets", _vp), ("d_lengths", _vp),
+        ("m", _i64), ("k", ctypes.c_int32), ("log2_pre", ctypes.c_int32),
+        ("d_mean", _vp), ("d_std", _vp), ("d_rstd", _vp),
+        ("vec_is_f64", ctypes.c_int32), ("out_is_f64", ctypes.c_int32),
+        ("d_out", _vp), ("ld_out", _i64),
+        ("d_min", _vp), ("d_post", _vp), ("d_colmin", _vp), ("d_colsum", _vp), ("d_colsq", _vp),
+        ("d_spec", _vp), ("d_skip", _vp),
+    ]
+
+
+class StreamArgs(ctypes.Structure):
+    """SkrStreamArgs (include/seekr_b200.h)."""
+
+    _fields_ = [
+        ("count", CountArgs), ("d_slab", _vp), ("h_out", _vp), ("h_ld", _i64),
+        ("h_out_pinned", ctypes.c_int32), ("copy_threads", ctypes.c_int32), ("chunk_records", _i64),
+    ]
+
+
 # name -> (restype, argtypes); kept in one table so tests can check it against the header
 SIGNATURES = {
     "skr_last_error": (ctypes.c_char_p, []),
@@ -39,6 +64,11 @@ SIGNATURES = {
     "skr_pack_fasta_file": (_int, [ctypes.c_char_p, _vp, _int, _int, ctypes.POINTER(_vp)]),
     "skr_pack_sequences": (_int, [_vp, _vp, _i64, _vp, _int, _int, ctypes.POINTER(_vp)]),
     "skr_packed_free": (None, [_vp]),
+    "skr_pack_fasta_buffer_async": (_int, [_vp, _sz, _vp, _int, _int, ctypes.POINTER(_vp)]),
+    "skr_packed_wait_records": (_int, [_vp, _i64]),
+    "skr_packed_wait": (_int, [_vp]),
+    "skr_stream_counts": (_int, [_vp, ctypes.POINTER(StreamArgs), _vp]),
+    "skr_host_alloc_pooled": (_int, [_sz, ctypes.POINTER(_vp)]),
     "skr_packed_num_records": (_i64, [_vp]),
     "skr_packed_num_blocks": (_i64, [_vp]),
     "skr_packed_total_bases": (_i64, [_vp]),
@@ -53,6 +83,10 @@ SIGNATURES = {
     "skr_pack_error_line": (_i64, []),
     "skr_min_reset": (_int, [_vp, _vp]),
     "skr_count": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _int, _vp, _vp, _int, _vp, _int, _i64, _vp, _vp, _vp, _vp]),
+    "skr_count_ex": (_int, [ctypes.POINTER(CountArgs), _vp]),
+    "skr_post_spec": (_int, [_vp, _vp, _int, _i64, _vp, _vp]),
+    "skr_colstat_finish": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "skr_post_log2_skip": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     "skr_colmin_reset": (_int, [_vp, _i64, _vp]),
     "skr_count_colmin": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _int, _vp, _i64, _vp, _vp]),
     "skr_colmin_scan": (_int, [_vp, _i64, _i64, _i64, _vp, _vp]),
@@ -88,6 +122,7 @@ SIGNATURES = {
     "skr_peer_close": (_int, [_vp]),
     "skr_peer_free": (_int, [_vp]),
     "skr_min_exchange": (_int, [_vp, _vp, _int, _int, ctypes.c_uint64, _vp, _vp]),
+    "skr_min_exchange_skip": (_int, [_vp, _vp, _int, _int, ctypes.c_uint64, _vp, _vp, _vp]),
     "skr_colstat_exchange_bytes": (_i64, [_int, _i64]),
     "skr_colstat_exchange": (_int, [_vp, _vp, _int, _int, ctypes.c_uint64, _i64, _i64, _i64, _int, _vp, _vp, _vp, _vp]),
     "skr_csv_write": (_int, [ctypes.c_char_p, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _int, _int]),

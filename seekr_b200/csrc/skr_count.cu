@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstddef>
 #include <cstdlib>
 #include <mutex>
 #include <unordered_map>
@@ -57,6 +58,14 @@ struct CountParams {
     const float* rstd;            // RN(1/std) per column: enables the 5-instruction exact division (fp32 vectors only)
     int no_store;                 // column-minimum pass only: nothing is written to `out`
     const SkrMinCell* post_cell;  // Log2.post fused into the epilogue: + |min|, + 1, log2 with this cell's minimum
+    // speculative Log2.post (skr_post_spec): the shift in post_cell was derived from the vectors alone and is the
+    // true matrix minimum iff some record has a zero count in column spec->zero_col; the kernel reports that
+    SkrPostSpec* spec;
+    const uint32_t* skip_flag;    // the launch does nothing when *skip_flag != 0 (device-side choice of the route)
+    // accurate column statistics (norm_vectors in one pass): per-column sum and sum of squares of the values
+    // written, accumulated in fp32 per thread over its records and added here in binary64 at the end
+    double* colsum;
+    double* colsq;
 };
 
 // Column minima for the two-pass Log2.post path (values are >= 0 there, so float bits order like
@@ -111,6 +120,17 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
     float v;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
     return v;
+}
+
+// log2 of the Log2.post tail, log2((z + |min|) + 1): the argument is >= 1 (or NaN), where MUFU.LG2 is within
+// 2^-22.6 absolute of the exact value per unit of magnitude (measured on B200: tools/log2_error.py, profiles/);
+// libdevice's log2f is a 25-instruction polynomial per element, which would triple the count kernel's epilogue.
+// Every Log2.post path of the library (fused epilogues and the element-wise passes) uses this one function, so
+// they agree bit for bit with each other; against numpy's log2 the values stay inside the 1e-5 parity band.
+__device__ __forceinline__ float log2_post(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 
 // value of a bin whose count is beyond the table (rare: low-complexity records); kept out of line so the
@@ -250,12 +270,16 @@ __global__ void __launch_bounds__(CountCfg<K>::kThreads) count_kernel(const Coun
     __shared__ double s_tab64[sizeof(OutT) == 8 ? kTab : 1];
 
     const int tid = threadIdx.x;
+    if (p.skip_flag && *p.skip_flag) return;
     float tmin = INFINITY;
     int tnan = 0;
     unsigned long long zero_seen = 0;
     constexpr int kSteps = (Cfg::kBins / 4 + T - 1) / T;  // epilogue steps per thread and record
     float shift = 0.0f;
     if (p.post_cell) shift = p.post_cell->nan_seen ? __int_as_float(0x7FC00000) : fabsf(skr::ordered_decode(p.post_cell->min_ordered));
+    int zq = -1, ze = 0;  // speculative Log2.post: quad / element of the arg-min column (skr_post_spec)
+    uint32_t zseen = 0;
+    if (p.spec && p.spec->zero_col >= 0) { zq = p.spec->zero_col >> 2; ze = p.spec->zero_col & 3; }
     uint32_t* spill = p.spill + (size_t)blockIdx.x * Cfg::kBins;
 
     for (;;) {
@@ -345,10 +369,11 @@ __global__ void __launch_bounds__(CountCfg<K>::kThreads) count_kernel(const Coun
             } else {
                 float r[4];
                 finish4<kVecF64>(c4, skr::smem_u32(s_tab), inc, p, q, r);
+                if (q == zq && (ze == 0 ? c4[0] : ze == 1 ? c4[1] : ze == 2 ? c4[2] : c4[3]) == 0) zseen = 1;
                 if (p.colmin) colmin_note<kSteps>(zero_seen, c4, r, p.colmin, q);
                 if (p.post_cell) {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) r[e] = log2f(__fadd_rn(__fadd_rn(r[e], shift), 1.0f));
+                    for (int e = 0; e < 4; ++e) r[e] = log2_post(__fadd_rn(__fadd_rn(r[e], shift), 1.0f));
                 }
                 if (p.min_cell) {
 #pragma unroll
@@ -360,6 +385,7 @@ __global__ void __launch_bounds__(CountCfg<K>::kThreads) count_kernel(const Coun
         // the __syncthreads at the top of the loop separates these reads from the next zeroing
     }
 
+    if (zseen) p.spec->zero_seen = 1u;
     if (p.min_cell) skr::min_commit<T>(tmin, tnan, s_wmin, s_wnan, p.min_cell);
     if (p.colmin && tid < Cfg::kBins / 4) colmin_flush<kSteps>(zero_seen, p.colmin, tid, T);
 }
@@ -397,6 +423,10 @@ __global__ void __launch_bounds__(WarpCfg<K>::kThreads, WarpCfg<K>::kMinCtas) co
     __shared__ float s_wmin[2];
     __shared__ int s_wnan[2];
     const int team = threadIdx.x / TT, lane = threadIdx.x % TT;  // lane: index inside the team
+    if (p.skip_flag && *p.skip_flag) return;
+    int zq = -1, ze = 0;  // speculative Log2.post: quad / element of the arg-min column (skr_post_spec)
+    uint32_t zseen = 0;
+    if (p.spec && p.spec->zero_col >= 0) { zq = p.spec->zero_col >> 2; ze = p.spec->zero_col & 3; }
     uint32_t* hist = smem_w + team * Cfg::kWords;
     float* tab = reinterpret_cast<float*>(smem_w + Cfg::kTeams * Cfg::kWords) + team * kTab;
     const uint32_t hist_addr = skr::smem_u32(hist), tab_addr = skr::smem_u32(tab);
@@ -481,10 +511,11 @@ __global__ void __launch_bounds__(WarpCfg<K>::kThreads, WarpCfg<K>::kMinCtas) co
                 const uint32_t c4[4] = {v.x & 0xFFFFu, v.x >> 16, v.y & 0xFFFFu, v.y >> 16};
                 float r[4];
                 finish4<kVecF64>(c4, tab_addr, inc, p, q, r);
+                if (q == zq && (ze == 0 ? c4[0] : ze == 1 ? c4[1] : ze == 2 ? c4[2] : c4[3]) == 0) zseen = 1;
                 if (p.colmin) colmin_note<kSteps>(zero_seen, c4, r, p.colmin, q);
                 if (p.post_cell) {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) r[e] = log2f(__fadd_rn(__fadd_rn(r[e], shift), 1.0f));
+                    for (int e = 0; e < 4; ++e) r[e] = log2_post(__fadd_rn(__fadd_rn(r[e], shift), 1.0f));
                 }
                 if (p.min_cell) {
 #pragma unroll
@@ -496,6 +527,7 @@ __global__ void __launch_bounds__(WarpCfg<K>::kThreads, WarpCfg<K>::kMinCtas) co
         rec = share(mine_next);  // also separates this record's histogram reads from the next clearing
         if constexpr (TT == 32) __syncwarp();
     }
+    if (zseen) p.spec->zero_seen = 1u;
     if (p.colmin && lane < Cfg::kBins / 4) colmin_flush<kSteps>(zero_seen, p.colmin, lane, TT);
     if (p.min_cell) {
         if constexpr (TT == 32) {
@@ -519,13 +551,18 @@ __global__ void __launch_bounds__(WarpCfg<K>::kThreads, WarpCfg<K>::kMinCtas) co
 // Batch kernel (k = 6, float32 output): a persistent CTA of 16 worker warps + 1 bookkeeping warp takes
 // kB consecutive records at a time.
 //   count phase   the batch's windows are cut into units of 32 (two chunks that share their code and mask
-//                 words) and dealt round-robin to the 512 worker threads, whatever record they belong to, so
-//                 the threads stay busy on short and long records alike; each record has its own histogram.
+//                 words).  Whole units of all records come first in the unit order, the (at most kB) ragged
+//                 tail units last, and the units are dealt round-robin to the 512 worker threads whatever
+//                 record they belong to: the threads stay busy on short and long records alike, and the
+//                 predicated path of a ragged unit is executed by one warp per batch instead of by every
+//                 warp that happens to hold the end of a record.  Each record has its own histogram.
 //   epilogue      thread w owns bin quads w and w + 512 of EVERY record.  Its slices of mean / std / 1/std
 //                 are loaded once per kernel and stay in registers, so the normalisation costs no memory
 //                 traffic at all (the warp kernel re-reads 48 KB of vectors from L2 per record, which made
-//                 it latency-bound: 0.32 ms fused against 0.21 ms raw).  Each warp writes 512 contiguous
-//                 bytes per step; the histogram words are zeroed as they are read.
+//                 it latency-bound: 0.32 ms fused against 0.21 ms raw).  The value table of a record (32
+//                 floats) sits in one register per lane and is read with an indexed warp shuffle: one
+//                 instruction per bin instead of address arithmetic + a shared load.  Each warp writes 512
+//                 contiguous bytes per step; the histogram words are zeroed as they are read.
 //   bookkeeping   warp 16 draws the next batch, reads its lengths / offsets, runs the kTab-entry binary64
 //                 value chains and the unit prefix while the workers are busy (double-buffered BatchMeta).
 // ---------------------------------------------------------------------------------------------
@@ -534,8 +571,12 @@ struct BatchCfg {
     static constexpr int kBins = 1 << (2 * K);
     static constexpr int kWords = kBins / 2;
     static constexpr int kHistBytes = kWords * 4;
+    // 512 threads, two CTAs per SM = 1024 threads = 64 registers each (with a 17th warp the limit was 56 and the
+    // epilogue spilled).  Every thread owns bin quads in the epilogue; in the count phase warp 15 keeps the books
+    // and the other 15 warps count.
     static constexpr int kWorkers = 512;
-    static constexpr int kThreads = kWorkers + 32;
+    static constexpr int kThreads = kWorkers;
+    static constexpr int kCounters = kWorkers - 32;
     static constexpr int kB = 8;                        // records per batch
     static constexpr int kQ = kBins / 4 / kWorkers;     // bin quads per worker thread
     // histograms start at a multiple of their size (count_chunk<K, true>): one histogram of slack
@@ -548,7 +589,7 @@ struct BatchMeta {
     alignas(128) float tab[kB][kTab];  // 128-byte rows: table address | 4*count
     long long rec0;                    // first record of the batch, < 0: no more work
     int nrec;
-    uint32_t prefix[kB + 1];           // units (32 windows) before record r
+    uint32_t prefix[kB + 1];           // whole units (32 windows) before record r
     long long nwin[kB];
     unsigned long long b0[kB];         // first 64-base block
     double inc[kB];
@@ -559,40 +600,187 @@ static_assert(kTab * 4 == 128, "table rows are addressed by OR");
 __device__ __forceinline__ void sts_zero_v2(uint32_t addr) {
     asm volatile("st.shared.v2.u32 [%0], {%1, %1};" ::"r"(addr), "r"(0u) : "memory");
 }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ unsigned long long lds_u64(uint32_t addr) {
+    unsigned long long v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr));
+    return v;
+}
+
+// 16 windows without a masked base and without a ragged end: no predicates
+template <int K>
+__device__ __forceinline__ void count_chunk_full(uint32_t hist_addr, uint64_t x) {
+    constexpr uint32_t kMask = (1u << (2 * K)) - 1;
+    constexpr uint32_t kOffMask = (kMask >> 1) << 2;
+    const uint64_t same = (x ^ (x << 2)) >> (64 - 2 * (16 + K - 2));
+    if (same == 0) {  // homopolymer run: one add of 16 instead of 16 colliding adds
+        const uint32_t kmer = (uint32_t)(x >> (64 - 2 * K)) & kMask;
+        red_add_shared_always(hist_addr | ((kmer >> 1) * 4), 16u << ((kmer & 1) * 16));
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const uint32_t t = (uint32_t)(x >> (64 - 2 * (j + K) - 1));
+        red_add_shared_always((t & kOffMask) | hist_addr, (t & 2u) ? 0x10000u : 1u);
+    }
+}
+
+// The count phase of one batch: out of line so that its registers (three code words and two mask words of the
+// current and of the next unit, the unit bookkeeping) are allocated apart from the epilogue's, which holds the
+// thread's slices of the mean / std / 1/std vectors; in one body the two sets together exceeded the 56 registers a
+// thread may have with 2 x 544 threads per SM, and the compiler spilled inside both hot loops.
+template <int K, int kB, int kW, bool kOverlap>
+__device__ __noinline__ void count_phase(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ mask,
+                                         uint32_t mt_addr, uint32_t hist_addr, uint32_t ready_addr, int tid) {
+    // mt_addr: shared-window address of the batch's BatchMeta (explicit ld.shared: a generic reference would make
+    // every access a generic load in an out-of-line function)
+    using Meta = BatchMeta<kB>;
+    constexpr uint32_t kHistBytes = (1u << (2 * K)) * 2;
+    constexpr uint32_t oPrefix = offsetof(Meta, prefix), oNwin = offsetof(Meta, nwin), oB0 = offsetof(Meta, b0);
+    // Unit order: the kB tail slots first (slot r = the ragged last unit of record r, possibly empty), then the
+    // whole units record after record.  A warp therefore leaves record r for good once the first unit of its
+    // next round lies beyond r's range, and says so on the record's mbarrier (kOverlap): the epilogue of the
+    // first records of a batch starts while the last ones are still being counted.
+    uint32_t pf[kB + 1];  // kB + whole units before record r: the unit index where record r's whole units start
+#pragma unroll
+    for (int i = 0; i <= kB; ++i) pf[i] = kB + lds_u32(mt_addr + oPrefix + 4 * i);
+    const uint32_t total = pf[kB];
+    const int lane = tid & 31;
+    auto locate = [&](uint32_t g, int& r, uint32_t& u) {
+        if (g < kB) {  // tail slot of record g: the unit after its whole units
+            r = (int)g;
+            u = (uint32_t)(lds_u64(mt_addr + oNwin + 8 * g) >> 5);
+            return;
+        }
+        r = 0;
+        uint32_t before = pf[0];
+#pragma unroll
+        for (int i = 1; i < kB; ++i)
+            if (g >= pf[i]) { r = i; before = pf[i]; }
+        u = g - before;
+    };
+    uint32_t w0 = 0, w1 = 0, w2 = 0, m0 = 0, m1 = 0, u = 0;
+    int r = 0;
+    uint32_t gbase = (uint32_t)(tid - lane);  // warp-uniform: the warp's units of this round are gbase .. gbase + 31
+    uint32_t g = gbase + lane;
+    if (g < total) {
+        locate(g, r, u);
+        const unsigned long long b0 = lds_u64(mt_addr + oB0 + 8 * (uint32_t)r);
+        const uint32_t* cw = codes + b0 * 4 + 2 * u;
+        const uint32_t* mw = mask + b0 * 2 + u;
+        w0 = __ldg(cw); w1 = __ldg(cw + 1); w2 = __ldg(cw + 2);
+        m0 = __ldg(mw); m1 = __ldg(mw + 1);
+    }
+    int arrived = 0;  // records [0, arrived) have this warp's arrival
+    for (; gbase < total; gbase += kW) {
+        if (g < total) {
+            const uint32_t gn = g + kW;
+            uint32_t n0 = 0, n1 = 0, n2 = 0, q0 = 0, q1 = 0, un = 0;
+            int rn = 0;
+            if (gn < total) {  // next unit's words are in flight while this one is counted
+                locate(gn, rn, un);
+                const unsigned long long b0 = lds_u64(mt_addr + oB0 + 8 * (uint32_t)rn);
+                const uint32_t* cw = codes + b0 * 4 + 2 * un;
+                const uint32_t* mw = mask + b0 * 2 + un;
+                n0 = __ldg(cw); n1 = __ldg(cw + 1); n2 = __ldg(cw + 2);
+                q0 = __ldg(mw); q1 = __ldg(mw + 1);
+            }
+            const uint32_t h = hist_addr + (uint32_t)r * kHistBytes;
+            const uint64_t m64 = ((uint64_t)m0 << 32) | m1;
+            if (g >= kB && (m64 >> (64 - (32 + K - 1))) == 0) {
+                count_chunk_full<K>(h, ((uint64_t)w0 << 32) | w1);
+                count_chunk_full<K>(h, ((uint64_t)w1 << 32) | w2);
+            } else {
+                // tail slot: nwin % 32 windows, 0 = nothing to do
+                const long long left = (long long)lds_u64(mt_addr + oNwin + 8 * (uint32_t)r) - (long long)u * 32;
+                if (left > 0)
+                    count_chunk<K, true>(h, ((uint64_t)w0 << 32) | w1, (uint32_t)(m64 >> (64 - (16 + K - 1))),
+                                         left < 16 ? (int)left : 16);
+                if (left > 16)
+                    count_chunk<K, true>(h, ((uint64_t)w1 << 32) | w2, (uint32_t)((m64 << 16) >> (64 - (16 + K - 1))),
+                                         left < 32 ? (int)(left - 16) : 16);
+            }
+            w0 = n0; w1 = n1; w2 = n2; m0 = q0; m1 = q1; u = un; r = rn; g = gn;
+        }
+        if constexpr (kOverlap) {
+            // records whose whole units end at or before the warp's next round are finished as far as this warp goes
+            __syncwarp();
+            const uint32_t next = gbase + kW;
+#pragma unroll
+            for (int i = 0; i < kB; ++i) {
+                if (i >= arrived && pf[i + 1] <= next) {
+                    if (lane == 0) skr::mbar_arrive_addr(ready_addr + 8 * i);
+                    arrived = i + 1;
+                }
+            }
+        }
+    }
+    if constexpr (kOverlap) {
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < kB; ++i)
+            if (i >= arrived && lane == 0) skr::mbar_arrive_addr(ready_addr + 8 * i);
+    }
+}
 
 // Epilogue flavours, so that the common cases carry no dead predicated instructions (the kernel is bound by
-// instruction issue):  kBatchPlain  no vectors / column minima / fused Log2.post,
-//                      kBatchFast   fp32 mean, std and 1/std, no column minima / fused Log2.post,
-//                      kBatchAny    everything decided at run time.
-enum { kBatchAny = 0, kBatchPlain = 1, kBatchFast = 2 };
+// instruction issue and the shared-memory pipe):
+//   kBatchPlain  no vectors / fused Log2.post  (optional: column minima, column sums for the statistics),
+//   kBatchFast   fp32 mean, std and 1/std, no column minima / fused Log2.post,
+//   kBatchPost   kBatchFast + the Log2.post tail with a shift known before the launch (skr_post_spec),
+//   kBatchAny    everything decided at run time.
+enum { kBatchAny = 0, kBatchPlain = 1, kBatchFast = 2, kBatchPost = 3 };
 
-template <int K, bool kVecF64, int kMode, bool kMin, bool kColmin = false>
+template <int K, bool kVecF64, int kMode, bool kMin, bool kColmin = false, bool kStats = false, bool kOverlap = true>
 __global__ void __launch_bounds__(BatchCfg<K>::kThreads, 2) count_batch_kernel(const CountParams p) {
     using Cfg = BatchCfg<K>;
     constexpr int kB = Cfg::kB, kW = Cfg::kWorkers, kQ = Cfg::kQ;
+    constexpr bool kRegVec = kMode == kBatchFast || kMode == kBatchPost;  // -mean, -std, 1/std in registers
     static_assert(!(kVecF64 && kMode != kBatchAny), "binary64 vectors take the generic epilogue");
     static_assert(!kColmin || kMode == kBatchPlain, "kColmin: column minima of the plain values (kBatchAny decides at run time)");
+    static_assert(!kStats || kMode == kBatchPlain, "kStats: column sums of the plain values");
+    static_assert(!(kMin && kMode == kBatchPost), "the speculative Log2.post epilogue needs no running minimum");
+    if (p.skip_flag && *p.skip_flag) return;
     extern __shared__ __align__(16) uint32_t smem_b[];
     __shared__ BatchMeta<kB> s_meta[2];
+    __shared__ __align__(8) uint64_t s_ready[kB];  // kOverlap: record r of the current batch is completely counted
     const int tid = threadIdx.x, lane = tid & 31;
-    const bool worker = tid < kW;
+    if constexpr (kOverlap) {
+        if (tid < kB) skr::mbar_init(&s_ready[tid], Cfg::kCounters / 32);  // one arrival per counting warp and batch
+        skr::fence_mbar_init();
+    }
+    constexpr bool worker = true;                 // every thread takes part in the epilogue
+    const bool counter = tid < Cfg::kCounters;    // count phase: warps 0..14 count, warp 15 prepares the next batch
     const uint32_t raw_addr = skr::smem_u32(smem_b);
     const uint32_t hist_addr = (raw_addr + Cfg::kHistBytes - 1) & ~(uint32_t)(Cfg::kHistBytes - 1);
 
     float tmin = INFINITY;
     int tnan = 0;
     float shift = 0.0f;
-    if (kMode == kBatchAny && p.post_cell)
+    if ((kMode == kBatchAny || kMode == kBatchPost) && p.post_cell)
         shift = p.post_cell->nan_seen ? __int_as_float(0x7FC00000) : fabsf(skr::ordered_decode(p.post_cell->min_ordered));
+    // speculative Log2.post: the thread that owns the arg-min column looks for a zero count there
+    int zoff = -1;       // byte offset of that column's histogram word inside a record's histogram
+    uint32_t zsh = 0;
+    uint32_t zseen = 0;
+    if ((kMode == kBatchAny || kMode == kBatchPost) && p.spec) {
+        const int zc = p.spec->zero_col;
+        if (zc >= 0 && ((zc >> 2) % kW) == tid) { zoff = (zc >> 1) * 4; zsh = (uint32_t)(zc & 1) * 16u; }
+    }
 
     // this thread's slices of the vectors (fp32 vectors only; binary64 vectors are read in the epilogue)
     float4 mv[kQ], sv[kQ], yv[kQ];
     uint32_t cmin[kQ][4];
+    float sx[kQ][4], sq[kQ][4];
 #pragma unroll
     for (int j = 0; j < kQ; ++j) {
         mv[j] = sv[j] = yv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) cmin[j][e] = 0xFFFFFFFFu;
+        for (int e = 0; e < 4; ++e) { cmin[j][e] = 0xFFFFFFFFu; sx[j][e] = 0.f; sq[j][e] = 0.f; }
     }
     if (worker) {
         if constexpr (!kVecF64 && kMode != kBatchPlain) {
@@ -602,7 +790,7 @@ __global__ void __launch_bounds__(BatchCfg<K>::kThreads, 2) count_batch_kernel(c
                 if (p.mean) mv[j] = __ldg(reinterpret_cast<const float4*>(p.mean) + q);
                 if (p.std_) sv[j] = __ldg(reinterpret_cast<const float4*>(p.std_) + q);
                 if (p.std_ && p.rstd) yv[j] = __ldg(reinterpret_cast<const float4*>(p.rstd) + q);
-                if constexpr (kMode == kBatchFast) {
+                if constexpr (kRegVec) {
                     mv[j] = make_float4(-mv[j].x, -mv[j].y, -mv[j].z, -mv[j].w);
                     sv[j] = make_float4(-sv[j].x, -sv[j].y, -sv[j].z, -sv[j].w);
                 }
@@ -642,7 +830,7 @@ __global__ void __launch_bounds__(BatchCfg<K>::kThreads, 2) count_batch_kernel(c
             mt.b0[lane] = b0;
             mt.inc[lane] = inc;
             mt.store[lane] = store;
-            units = (uint32_t)((nwin + 31) / 32);
+            units = (uint32_t)(nwin >> 5);  // whole units; the ragged rest is the record's tail unit
             double acc = 0.0;  // the literal chain of kmer_counts.py:144-150 for counts below kTab
             mt.tab[lane][0] = p.log2_pre ? log2f(1.0f) : 0.0f;
 #pragma unroll 8
@@ -667,96 +855,78 @@ __global__ void __launch_bounds__(BatchCfg<K>::kThreads, 2) count_batch_kernel(c
         }
     };
 
-    if (!worker) produce(0);
+    if (!counter) produce(0);
     __syncthreads();
 
     for (int it = 0;; ++it) {
         const BatchMeta<kB>& mt = s_meta[it & 1];
         if (mt.rec0 < 0) break;
-        if (!worker) {
+        if (!counter) {
             produce((it + 1) & 1);
         } else {
-            // ---- count phase ----
-            const uint32_t total = mt.prefix[kB];
-            auto locate = [&](uint32_t g, int& r, uint32_t& u) {
-                r = 0;
-                uint32_t before = 0;
-#pragma unroll
-                for (int i = 1; i < kB; ++i) {
-                    const uint32_t pf = mt.prefix[i];  // broadcast shared loads
-                    if (g >= pf) { r = i; before = pf; }
-                }
-                u = g - before;
-            };
-            uint32_t w0 = 0, w1 = 0, w2 = 0, m0 = 0, m1 = 0, u = 0;
-            int r = 0;
-            uint32_t g = (uint32_t)tid;
-            if (g < total) {
-                locate(g, r, u);
-                const uint32_t* cw = p.codes + mt.b0[r] * 4 + 2 * u;
-                const uint32_t* mw = p.mask + mt.b0[r] * 2 + u;
-                w0 = __ldg(cw); w1 = __ldg(cw + 1); w2 = __ldg(cw + 2);
-                m0 = __ldg(mw); m1 = __ldg(mw + 1);
-            }
-            while (g < total) {
-                const uint32_t gn = g + kW;
-                uint32_t n0 = 0, n1 = 0, n2 = 0, q0 = 0, q1 = 0, un = 0;
-                int rn = 0;
-                if (gn < total) {  // next unit's words are in flight while this one is counted
-                    locate(gn, rn, un);
-                    const uint32_t* cw = p.codes + mt.b0[rn] * 4 + 2 * un;
-                    const uint32_t* mw = p.mask + mt.b0[rn] * 2 + un;
-                    n0 = __ldg(cw); n1 = __ldg(cw + 1); n2 = __ldg(cw + 2);
-                    q0 = __ldg(mw); q1 = __ldg(mw + 1);
-                }
-                const uint32_t h = hist_addr + (uint32_t)r * Cfg::kHistBytes;
-                const uint64_t m64 = ((uint64_t)m0 << 32) | m1;
-                const long long left = mt.nwin[r] - (long long)u * 32;
-                count_chunk<K, true>(h, ((uint64_t)w0 << 32) | w1, (uint32_t)(m64 >> (64 - (16 + K - 1))),
-                                     left < 16 ? (int)left : 16);
-                if (left > 16)
-                    count_chunk<K, true>(h, ((uint64_t)w1 << 32) | w2, (uint32_t)((m64 << 16) >> (64 - (16 + K - 1))),
-                                         left < 32 ? (int)(left - 16) : 16);
-                w0 = n0; w1 = n1; w2 = n2; m0 = q0; m1 = q1; u = un; r = rn; g = gn;
-            }
+            count_phase<K, kB, Cfg::kCounters, kOverlap>(p.codes, p.mask, skr::smem_u32(&mt), hist_addr, skr::smem_u32(&s_ready[0]), tid);
         }
-        __syncthreads();
+        if constexpr (!kOverlap) __syncthreads();
         if (worker) {
             // ---- epilogue ----
             const int nrec = mt.nrec;
             for (int r = 0; r < nrec; ++r) {
+                if constexpr (kOverlap) skr::mbar_wait(&s_ready[r], (uint32_t)(it & 1));
                 if (!mt.store[r]) continue;
                 const uint32_t tab_addr = skr::smem_u32(&mt.tab[r][0]);
+                const float treg = lds_f32(tab_addr + (uint32_t)lane * 4);  // lane c holds the value of a bin seen c times
+                const uint32_t hrec = hist_addr + (uint32_t)r * Cfg::kHistBytes;
                 float* __restrict__ orow = reinterpret_cast<float*>(p.out) + (size_t)(mt.rec0 + r) * (size_t)p.ld_out;
+                if (zoff >= 0 && ((lds_u32(hrec + (uint32_t)zoff) >> zsh) & 0xFFFFu) == 0) zseen = 1;
+                // staged over the thread's quads so that their shared-memory loads, zeroing stores and table
+                // shuffles are in flight together (the asm wrappers are kept in program order by the compiler)
+                uint2 vq[kQ];
+#pragma unroll
+                for (int j = 0; j < kQ; ++j) vq[j] = lds_v2(hrec + (uint32_t)(tid + j * kW) * 8);
+#pragma unroll
+                for (int j = 0; j < kQ; ++j) sts_zero_v2(hrec + (uint32_t)(tid + j * kW) * 8);
 #pragma unroll
                 for (int j = 0; j < kQ; ++j) {
                     const int q = tid + j * kW;
-                    const uint32_t a = hist_addr + (uint32_t)r * Cfg::kHistBytes + (uint32_t)q * 8;
-                    const uint2 v = lds_v2(a);
-                    sts_zero_v2(a);
+                    const uint2 v = vq[j];
                     float x[4];
-                    if (((v.x | v.y) & ~(uint32_t)((kTab - 1) * 0x10001u)) == 0) {
-                        // every count is below kTab: table address | 4 * count
-                        x[0] = lds_f32(tab_addr | ((v.x << 2) & 0x7Cu));
-                        x[1] = lds_f32(tab_addr | ((v.x >> 14) & 0x7Cu));
-                        x[2] = lds_f32(tab_addr | ((v.y << 2) & 0x7Cu));
-                        x[3] = lds_f32(tab_addr | ((v.y >> 14) & 0x7Cu));
-                    } else {
+                    // indexed shuffles take the source lane modulo 32; counts of kTab and more are fixed up below
+                    x[0] = __shfl_sync(0xFFFFFFFFu, treg, (int)v.x);
+                    x[1] = __shfl_sync(0xFFFFFFFFu, treg, (int)(v.x >> 16));
+                    x[2] = __shfl_sync(0xFFFFFFFFu, treg, (int)v.y);
+                    x[3] = __shfl_sync(0xFFFFFFFFu, treg, (int)(v.y >> 16));
+                    if (((v.x | v.y) & ~(uint32_t)((kTab - 1) * 0x10001u)) != 0) {
                         const uint32_t c4[4] = {v.x & 0xFFFFu, v.x >> 16, v.y & 0xFFFFu, v.y >> 16};
                         const double inc = mt.inc[r];
 #pragma unroll
                         for (int e = 0; e < 4; ++e)
-                            x[e] = c4[e] < kTab ? lds_f32(tab_addr + c4[e] * 4) : slow_bin_value(inc, c4[e], p.log2_pre);
+                            if (c4[e] >= kTab) x[e] = slow_bin_value(inc, c4[e], p.log2_pre);
                     }
-                    if constexpr (kMode == kBatchFast) {
-                        // mv / sv hold -mean / -std in this flavour (negated once, after the load); FADD2 / FMUL2 /
+                    if constexpr (kStats) {  // column sums of the plain values (accurate norm_vectors)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            sx[j][e] = __fadd_rn(sx[j][e], x[e]);
+                            sq[j][e] = __fmaf_rn(x[e], x[e], sq[j][e]);
+                        }
+                    }
+                    if constexpr (kRegVec) {
+                        // mv / sv hold -mean / -std in these flavours (negated once, after the load); FADD2 / FMUL2 /
                         // FFMA2 do two columns per issue slot
-                        const uint64_t z0 = sub_div_by_rcp2(skr::f2_pack(x[0], x[1]), skr::f2_pack(mv[j].x, mv[j].y),
-                                                            skr::f2_pack(sv[j].x, sv[j].y), skr::f2_pack(yv[j].x, yv[j].y));
-                        const uint64_t z1 = sub_div_by_rcp2(skr::f2_pack(x[2], x[3]), skr::f2_pack(mv[j].z, mv[j].w),
-                                                            skr::f2_pack(sv[j].z, sv[j].w), skr::f2_pack(yv[j].z, yv[j].w));
+                        uint64_t z0 = sub_div_by_rcp2(skr::f2_pack(x[0], x[1]), skr::f2_pack(mv[j].x, mv[j].y),
+                                                      skr::f2_pack(sv[j].x, sv[j].y), skr::f2_pack(yv[j].x, yv[j].y));
+                        uint64_t z1 = sub_div_by_rcp2(skr::f2_pack(x[2], x[3]), skr::f2_pack(mv[j].z, mv[j].w),
+                                                      skr::f2_pack(sv[j].z, sv[j].w), skr::f2_pack(yv[j].z, yv[j].w));
+                        if constexpr (kMode == kBatchPost) {  // (z + |min|) + 1: two roundings, kmer_counts.py:208-209
+                            const uint64_t s2 = skr::f2_pack(shift, shift), one2 = skr::f2_pack(1.0f, 1.0f);
+                            z0 = skr::f2_add(skr::f2_add(z0, s2), one2);
+                            z1 = skr::f2_add(skr::f2_add(z1, s2), one2);
+                        }
                         skr::f2_unpack(z0, x[0], x[1]);
                         skr::f2_unpack(z1, x[2], x[3]);
+                        if constexpr (kMode == kBatchPost) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) x[e] = log2_post(x[e]);
+                        }
                     } else if constexpr (kMode == kBatchAny) {
                         if constexpr (kVecF64) {
                             if (p.mean) {
@@ -790,7 +960,7 @@ __global__ void __launch_bounds__(BatchCfg<K>::kThreads, 2) count_batch_kernel(c
                         }
                         if (p.post_cell) {
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) x[e] = log2f(__fadd_rn(__fadd_rn(x[e], shift), 1.0f));
+                            for (int e = 0; e < 4; ++e) x[e] = log2_post(__fadd_rn(__fadd_rn(x[e], shift), 1.0f));
                         }
                     }
                     if constexpr (kColmin) {  // plain values are >= 0: float bits order like unsigned integers
@@ -810,6 +980,7 @@ __global__ void __launch_bounds__(BatchCfg<K>::kThreads, 2) count_batch_kernel(c
     }
 
     if (worker) {
+        if (zseen) p.spec->zero_seen = 1u;
         if (kColmin || (kMode == kBatchAny && p.colmin)) {
 #pragma unroll
             for (int j = 0; j < kQ; ++j)
@@ -817,6 +988,16 @@ __global__ void __launch_bounds__(BatchCfg<K>::kThreads, 2) count_batch_kernel(c
                 for (int e = 0; e < 4; ++e) {
                     const int col = 4 * (tid + j * kW) + e;
                     if (cmin[j][e] < p.colmin[col]) atomicMin(&p.colmin[col], cmin[j][e]);
+                }
+        }
+        if constexpr (kStats) {
+#pragma unroll
+            for (int j = 0; j < kQ; ++j)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int col = 4 * (tid + j * kW) + e;
+                    atomicAdd(&p.colsum[col], (double)sx[j][e]);
+                    atomicAdd(&p.colsq[col], (double)sq[j][e]);
                 }
         }
         if constexpr (kMin) {
@@ -834,10 +1015,10 @@ __global__ void __launch_bounds__(BatchCfg<K>::kThreads, 2) count_batch_kernel(c
     }
 }
 
-template <int K, bool kVecF64, int kMode, bool kMin, bool kColmin = false>
+template <int K, bool kVecF64, int kMode, bool kMin, bool kColmin = false, bool kStats = false, bool kOverlap = true>
 int launch_batch(const CountParams& wp, int sms, cudaStream_t stream) {
     using B = BatchCfg<K>;
-    auto bkern = count_batch_kernel<K, kVecF64, kMode, kMin, kColmin>;
+    auto bkern = count_batch_kernel<K, kVecF64, kMode, kMin, kColmin, kStats, kOverlap>;
     SKR_CUDA_CHECK(cudaFuncSetAttribute(bkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B::kSmem));
     int bper_sm = 0;
     SKR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bper_sm, bkern, B::kThreads, B::kSmem));
@@ -852,16 +1033,30 @@ int launch_batch(const CountParams& wp, int sms, cudaStream_t stream) {
 template <int K, bool kVecF64>
 int dispatch_batch(const CountParams& wp, int sms, cudaStream_t stream) {
     const bool plain = !wp.mean && !wp.std_ && !wp.post_cell && !wp.no_store;
-    const bool fast = !kVecF64 && wp.mean && wp.std_ && wp.rstd && !wp.colmin && !wp.post_cell && !wp.no_store;
+    const bool regvec = !kVecF64 && wp.mean && wp.std_ && wp.rstd && !wp.colmin && !wp.no_store;
+    const bool fast = regvec && !wp.post_cell;
+    const bool post = regvec && wp.post_cell && !wp.min_cell;
     const bool mn = wp.min_cell != nullptr;
     if constexpr (!kVecF64) {
+        if (plain && wp.colsum) {
+            if (mn) return skr::fail(SKR_ERR_ARG, "skr_count: column sums and a running minimum are not combined");
+            return wp.colmin ? launch_batch<K, false, kBatchPlain, false, true, true>(wp, sms, stream)
+                             : launch_batch<K, false, kBatchPlain, false, false, true>(wp, sms, stream);
+        }
         if (plain && wp.colmin) return mn ? launch_batch<K, false, kBatchPlain, true, true>(wp, sms, stream)
                                           : launch_batch<K, false, kBatchPlain, false, true>(wp, sms, stream);
         if (plain) return mn ? launch_batch<K, false, kBatchPlain, true>(wp, sms, stream)
                              : launch_batch<K, false, kBatchPlain, false>(wp, sms, stream);
+        const char* env = getenv("SEEKR_B200_BATCH_OVERLAP");  // experiment knob: "0" = a CTA barrier between the phases
+        if (env && env[0] == '0') {
+            if (plain && !wp.colmin && !wp.colsum && !mn) return launch_batch<K, false, kBatchPlain, false, false, false, false>(wp, sms, stream);
+            if (post) return launch_batch<K, false, kBatchPost, false, false, false, false>(wp, sms, stream);
+        }
         if (fast) return mn ? launch_batch<K, false, kBatchFast, true>(wp, sms, stream)
                             : launch_batch<K, false, kBatchFast, false>(wp, sms, stream);
+        if (post) return launch_batch<K, false, kBatchPost, false>(wp, sms, stream);
     }
+    if (wp.colsum) return skr::fail(SKR_ERR_ARG, "skr_count: column sums go with plain counts (no vectors, no Log2.post)");
     return mn ? launch_batch<K, kVecF64, kBatchAny, true>(wp, sms, stream)
               : launch_batch<K, kVecF64, kBatchAny, false>(wp, sms, stream);
 }
@@ -984,11 +1179,11 @@ __device__ __forceinline__ float ew_apply(float v, const void* vec, const void* 
                              : __fsub_rn(v, __ldg((const float*)vec + col));
         if (vec2) v = kVecF64 ? __double2float_rn(__ddiv_rn((double)v, __ldg((const double*)vec2 + col)))
                               : __fdiv_rn(v, __ldg((const float*)vec2 + col));
-        if constexpr (OP == OP_NORMPOST) v = log2f(__fadd_rn(__fadd_rn(v, shift), 1.0f));  // then the Log2.post tail
+        if constexpr (OP == OP_NORMPOST) v = log2_post(__fadd_rn(__fadd_rn(v, shift), 1.0f));  // then the Log2.post tail
         return v;
     }
     if constexpr (OP == OP_LOG2) return log2f(__fadd_rn(v, 1.0f));
-    if constexpr (OP == OP_POST) return log2f(__fadd_rn(__fadd_rn(v, shift), 1.0f));
+    if constexpr (OP == OP_POST) return log2_post(__fadd_rn(__fadd_rn(v, shift), 1.0f));
     if constexpr (OP == OP_SUB) {
         if constexpr (kVecF64) return __double2float_rn(__dsub_rn((double)v, __ldg((const double*)vec + col)));
         else return __fsub_rn(v, __ldg((const float*)vec + col));
@@ -1008,13 +1203,13 @@ template <int OP, bool kVecF64>
 __device__ __forceinline__ float ew_apply_reg(float v, double m64, double s64, float m32, float s32, bool has_mean,
                                               bool has_std, float shift) {
     if constexpr (OP == OP_LOG2) return log2f(__fadd_rn(v, 1.0f));
-    if constexpr (OP == OP_POST) return log2f(__fadd_rn(__fadd_rn(v, shift), 1.0f));
+    if constexpr (OP == OP_POST) return log2_post(__fadd_rn(__fadd_rn(v, shift), 1.0f));
     if constexpr (OP == OP_SUB) return kVecF64 ? __double2float_rn(__dsub_rn((double)v, m64)) : __fsub_rn(v, m32);
     if constexpr (OP == OP_DIV) return kVecF64 ? __double2float_rn(__ddiv_rn((double)v, m64)) : __fdiv_rn(v, m32);
     if constexpr (OP == OP_NORM || OP == OP_NORMPOST) {
         if (has_mean) v = kVecF64 ? __double2float_rn(__dsub_rn((double)v, m64)) : __fsub_rn(v, m32);
         if (has_std) v = kVecF64 ? __double2float_rn(__ddiv_rn((double)v, s64)) : __fdiv_rn(v, s32);
-        if constexpr (OP == OP_NORMPOST) v = log2f(__fadd_rn(__fadd_rn(v, shift), 1.0f));
+        if constexpr (OP == OP_NORMPOST) v = log2_post(__fadd_rn(__fadd_rn(v, shift), 1.0f));
         return v;
     }
     return v;
@@ -1022,9 +1217,11 @@ __device__ __forceinline__ float ew_apply_reg(float v, double m64, double s64, f
 
 template <int OP, bool kVecF64, bool kVec4>
 __global__ void __launch_bounds__(256) ew_kernel(float* a, long long m, long long cols, long long ld, const void* vec,
-                                                 const void* vec2, const SkrMinCell* min_in, SkrMinCell* min_out) {
+                                                 const void* vec2, const SkrMinCell* min_in, SkrMinCell* min_out,
+                                                 const uint32_t* skip) {
     __shared__ float s_wmin[8];
     __shared__ int s_wnan[8];
+    if (skip && *skip) return;
     float shift = 0.0f;
     if constexpr (OP == OP_POST || OP == OP_NORMPOST) {
         // np.abs(np.min(counts)): NaN anywhere makes the shift NaN, hence the whole matrix (kmer_counts.py:208)
@@ -1072,7 +1269,8 @@ __global__ void __launch_bounds__(256) ew_kernel(float* a, long long m, long lon
 
 template <int OP>
 int launch_ew(float* a, long long m, long long cols, long long ld, const void* vec, int vec_is_f64,
-              const SkrMinCell* min_in, SkrMinCell* min_out, cudaStream_t stream, const void* vec2 = nullptr) {
+              const SkrMinCell* min_in, SkrMinCell* min_out, cudaStream_t stream, const void* vec2 = nullptr,
+              const uint32_t* skip = nullptr) {
     if (m <= 0 || cols <= 0) return SKR_OK;
     if (!a) return skr::fail(SKR_ERR_ARG, "null matrix");
     if (ld < cols) return skr::fail(SKR_ERR_ARG, "ld < cols");
@@ -1088,7 +1286,7 @@ int launch_ew(float* a, long long m, long long cols, long long ld, const void* v
     if (gx > 0x7FFFFFFFll) return skr::fail(SKR_ERR_ARG, "matrix too wide");
     dim3 grid((unsigned)gx, (unsigned)gy);
     auto go = [&](auto kern) {
-        kern<<<grid, 256, 0, stream>>>(a, m, cols, ld, vec, vec2, min_in, min_out);
+        kern<<<grid, 256, 0, stream>>>(a, m, cols, ld, vec, vec2, min_in, min_out, skip);
     };
     if (vec_is_f64) {
         if (vec4) go(ew_kernel<OP, true, true>); else go(ew_kernel<OP, true, false>);
@@ -1199,50 +1397,155 @@ extern "C" int skr_min_reset(SkrMinCell* d_cell, void* stream) {
     return SKR_OK;
 }
 
+extern "C" int skr_count_ex(const SkrCountArgs* a, void* stream) {
+    if (!a) return skr::fail(SKR_ERR_ARG, "skr_count_ex: null arguments");
+    const int64_t m = a->m;
+    const int k = a->k;
+    if (m == 0) return SKR_OK;
+    if (a->d_rstd && (!a->d_std || a->vec_is_f64 || ((uintptr_t)a->d_rstd & 15)))
+        return skr::fail(SKR_ERR_ARG, "skr_count: the reciprocal vector goes with an aligned fp32 std vector");
+    if (!a->d_codes || !a->d_mask || !a->d_block_offsets || !a->d_lengths || m < 0)
+        return skr::fail(SKR_ERR_ARG, "skr_count: null or negative argument");
+    if (!a->d_out && !a->d_colmin) return skr::fail(SKR_ERR_ARG, "skr_count: no output matrix (only a column-minimum pass may omit it)");
+    if (k < 1 || k > 8) return skr::fail(SKR_ERR_ARG, "skr_count: k=%d not supported (1 <= k <= 8)", k);
+    const int64_t bins = (int64_t)1 << (2 * k);
+    if (a->d_out && a->ld_out < bins) return skr::fail(SKR_ERR_ARG, "skr_count: ld_out < 4^k");
+    if (a->out_is_f64 && (a->log2_pre || a->d_mean || a->d_std || a->d_min || a->d_post || a->d_colmin || a->d_colsum || a->d_spec))
+        return skr::fail(SKR_ERR_ARG, "skr_count: float64 output carries raw counts only");
+    const size_t esz = a->out_is_f64 ? 8 : 4;
+    if (a->d_out && (((uintptr_t)a->d_out & 15) || ((size_t)a->ld_out * esz) % 16))
+        return skr::fail(SKR_ERR_ARG, "skr_count: output rows must be 16-byte aligned");
+    if ((a->d_mean && ((uintptr_t)a->d_mean & 15)) || (a->d_std && ((uintptr_t)a->d_std & 15)))
+        return skr::fail(SKR_ERR_ARG, "skr_count: mean/std vectors must be 16-byte aligned");
+    if (a->d_colmin && (a->d_mean || a->d_std || a->d_post || ((uintptr_t)a->d_colmin & 15)))
+        return skr::fail(SKR_ERR_ARG, "skr_count: column minima are those of the un-normalised values (16-byte aligned array)");
+    if ((a->d_colsum == nullptr) != (a->d_colsq == nullptr) || (a->d_colsum && (a->d_mean || a->d_std || a->d_post || !a->d_out)))
+        return skr::fail(SKR_ERR_ARG, "skr_count: column sums come in pairs and go with plain counts");
+    if (a->d_colsum && k != 6) return skr::fail(SKR_ERR_ARG, "skr_count: in-kernel column sums are implemented for k = 6");
+    if (a->d_spec && !a->d_post) return skr::fail(SKR_ERR_ARG, "skr_count: a speculation cell goes with a Log2.post shift");
+    CountParams p{};
+    p.codes = a->d_codes;
+    p.mask = a->d_mask;
+    p.blk_off = a->d_block_offsets;
+    p.len = a->d_lengths;
+    p.m = m;
+    p.log2_pre = a->log2_pre;
+    p.mean = a->d_mean;
+    p.std_ = a->d_std;
+    p.out = a->d_out;
+    p.ld_out = a->ld_out;
+    p.min_cell = a->d_min;
+    p.post_cell = a->d_post;
+    p.rstd = a->d_rstd;
+    p.colmin = a->d_colmin;
+    p.no_store = a->d_out == nullptr;
+    p.spec = a->d_spec;
+    p.skip_flag = a->d_skip;
+    p.colsum = a->d_colsum;
+    p.colsq = a->d_colsq;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (k) {
+        case 1: return dispatch_count<1>(p, a->vec_is_f64, a->out_is_f64, s);
+        case 2: return dispatch_count<2>(p, a->vec_is_f64, a->out_is_f64, s);
+        case 3: return dispatch_count<3>(p, a->vec_is_f64, a->out_is_f64, s);
+        case 4: return dispatch_count<4>(p, a->vec_is_f64, a->out_is_f64, s);
+        case 5: return dispatch_count<5>(p, a->vec_is_f64, a->out_is_f64, s);
+        case 6: return dispatch_count<6>(p, a->vec_is_f64, a->out_is_f64, s);
+        case 7: return dispatch_count<7>(p, a->vec_is_f64, a->out_is_f64, s);
+        default: return dispatch_count<8>(p, a->vec_is_f64, a->out_is_f64, s);
+    }
+}
+
 extern "C" int skr_count(const uint32_t* d_codes, const uint32_t* d_mask, const uint64_t* d_block_offsets,
                          const uint32_t* d_lengths, int64_t m, int k, int log2_pre, const void* d_mean,
                          const void* d_std, int vec_is_f64, void* d_out, int out_is_f64, int64_t ld_out,
                          SkrMinCell* d_min, const SkrMinCell* d_post, const float* d_rstd, void* stream) {
-    if (m == 0) return SKR_OK;
-    if (d_rstd && (!d_std || vec_is_f64 || ((uintptr_t)d_rstd & 15)))
-        return skr::fail(SKR_ERR_ARG, "skr_count: the reciprocal vector goes with an aligned fp32 std vector");
-    if (!d_codes || !d_mask || !d_block_offsets || !d_lengths || !d_out || m < 0)
-        return skr::fail(SKR_ERR_ARG, "skr_count: null or negative argument");
-    if (k < 1 || k > 8) return skr::fail(SKR_ERR_ARG, "skr_count: k=%d not supported (1 <= k <= 8)", k);
-    const int64_t bins = (int64_t)1 << (2 * k);
-    if (ld_out < bins) return skr::fail(SKR_ERR_ARG, "skr_count: ld_out < 4^k");
-    if (out_is_f64 && (log2_pre || d_mean || d_std || d_min || d_post))
-        return skr::fail(SKR_ERR_ARG, "skr_count: float64 output carries raw counts only");
-    const size_t esz = out_is_f64 ? 8 : 4;
-    if (((uintptr_t)d_out & 15) || ((size_t)ld_out * esz) % 16)
-        return skr::fail(SKR_ERR_ARG, "skr_count: output rows must be 16-byte aligned");
-    if ((d_mean && ((uintptr_t)d_mean & 15)) || (d_std && ((uintptr_t)d_std & 15)))
-        return skr::fail(SKR_ERR_ARG, "skr_count: mean/std vectors must be 16-byte aligned");
-    CountParams p{};
-    p.codes = d_codes;
-    p.mask = d_mask;
-    p.blk_off = d_block_offsets;
-    p.len = d_lengths;
-    p.m = m;
-    p.log2_pre = log2_pre;
-    p.mean = d_mean;
-    p.std_ = d_std;
-    p.out = d_out;
-    p.ld_out = ld_out;
-    p.min_cell = d_min;
-    p.post_cell = d_post;
-    p.rstd = d_rstd;
-    cudaStream_t s = (cudaStream_t)stream;
-    switch (k) {
-        case 1: return dispatch_count<1>(p, vec_is_f64, out_is_f64, s);
-        case 2: return dispatch_count<2>(p, vec_is_f64, out_is_f64, s);
-        case 3: return dispatch_count<3>(p, vec_is_f64, out_is_f64, s);
-        case 4: return dispatch_count<4>(p, vec_is_f64, out_is_f64, s);
-        case 5: return dispatch_count<5>(p, vec_is_f64, out_is_f64, s);
-        case 6: return dispatch_count<6>(p, vec_is_f64, out_is_f64, s);
-        case 7: return dispatch_count<7>(p, vec_is_f64, out_is_f64, s);
-        default: return dispatch_count<8>(p, vec_is_f64, out_is_f64, s);
+    if (!d_out && m != 0) return skr::fail(SKR_ERR_ARG, "skr_count: null or negative argument");
+    SkrCountArgs a{};
+    a.d_codes = d_codes;
+    a.d_mask = d_mask;
+    a.d_block_offsets = d_block_offsets;
+    a.d_lengths = d_lengths;
+    a.m = m;
+    a.k = k;
+    a.log2_pre = log2_pre;
+    a.d_mean = d_mean;
+    a.d_std = d_std;
+    a.d_rstd = d_rstd;
+    a.vec_is_f64 = vec_is_f64;
+    a.out_is_f64 = out_is_f64;
+    a.d_out = d_out;
+    a.ld_out = ld_out;
+    a.d_min = d_min;
+    a.d_post = d_post;
+    return skr_count_ex(&a, stream);
+}
+
+// Speculative Log2.post shift (see SkrPostSpec): min over the columns of the z-score of a ZERO count,
+// fl(fl(0 - mean_j) / std_j), and the first column that attains it.
+template <bool kVecF64>
+__global__ void __launch_bounds__(256) post_spec_kernel(const void* mean, const void* std_, long long cols, SkrPostSpec* spec) {
+    __shared__ float s_v[256];
+    __shared__ long long s_j[256];
+    float best = INFINITY;
+    long long bj = -1;
+    for (long long j = threadIdx.x; j < cols; j += 256) {
+        const float v = ew_apply<OP_NORM, kVecF64>(0.0f, mean, std_, j, 0.0f);
+        if (v < best) { best = v; bj = j; }  // strict: the first column wins inside a thread (ascending j)
     }
+    s_v[threadIdx.x] = best;
+    s_j[threadIdx.x] = bj;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int t = 1; t < 256; ++t)
+            if (s_j[t] >= 0 && (bj < 0 || s_v[t] < best || (s_v[t] == best && s_j[t] < bj))) { best = s_v[t]; bj = s_j[t]; }
+        spec->shift.min_ordered = skr::ordered_encode(bj >= 0 ? best : 0.0f);
+        spec->shift.nan_seen = 0;
+        spec->zero_col = (int32_t)bj;  // -1: nothing to speculate on (a NaN / +inf in every column): callers fall back
+        spec->zero_seen = 0;
+    }
+}
+
+extern "C" int skr_post_spec(const void* d_mean, const void* d_std, int vec_is_f64, int64_t cols, SkrPostSpec* d_spec,
+                             void* stream) {
+    if (!d_spec || cols <= 0 || (!d_mean && !d_std)) return skr::fail(SKR_ERR_ARG, "skr_post_spec: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (vec_is_f64) post_spec_kernel<true><<<1, 256, 0, s>>>(d_mean, d_std, cols, d_spec);
+    else post_spec_kernel<false><<<1, 256, 0, s>>>(d_mean, d_std, cols, d_spec);
+    SKR_LAUNCH_CHECK();
+    return SKR_OK;
+}
+
+// mean / std from the column sums the count kernel accumulated (accurate norm_vectors): binary64 throughout,
+// mean = S1 / rows, var = S2 / rows - mean^2 (clamped at 0), one rounding to fp32 each
+__global__ void colstat_finish_kernel(const double* colsum, const double* colsq, long long cols, long long rows,
+                                      float* mean, float* std_, int* flags) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= cols) return;
+    const double mu = colsum[j] / (double)rows;
+    double var = colsq[j] / (double)rows - mu * mu;
+    if (var < 0.0) var = 0.0;
+    const float mf = (float)mu, sf = (float)sqrt(var);
+    if (mean) mean[j] = mf;
+    if (std_) std_[j] = sf;
+    if (flags) {
+        int fm = 0, fs = 0;
+        if (!(mf - mf == 0.0f)) fm |= 1;
+        if (!(sf - sf == 0.0f)) fs |= 1;
+        if (!(sf > 0.0f)) fs |= 2;
+        if (fm) atomicOr(&flags[0], fm);
+        if (fs) atomicOr(&flags[1], fs);
+    }
+}
+
+extern "C" int skr_colstat_finish(const double* d_colsum, const double* d_colsq, int64_t cols, int64_t total_rows,
+                                  float* d_mean, float* d_std, int* d_flags, void* stream) {
+    if (cols <= 0) return SKR_OK;
+    if (!d_colsum || !d_colsq || total_rows <= 0) return skr::fail(SKR_ERR_ARG, "skr_colstat_finish: bad argument");
+    colstat_finish_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_colsum, d_colsq, cols, total_rows,
+                                                                                             d_mean, d_std, d_flags);
+    SKR_LAUNCH_CHECK();
+    return SKR_OK;
 }
 
 extern "C" int skr_colmin_reset(uint32_t* d_colmin, int64_t cols, void* stream) {
@@ -1257,34 +1560,19 @@ extern "C" int skr_count_colmin(const uint32_t* d_codes, const uint32_t* d_mask,
                                 const uint32_t* d_lengths, int64_t m, int k, int log2_pre, float* d_out, int64_t ld_out,
                                 uint32_t* d_colmin, void* stream) {
     if (m == 0) return SKR_OK;
-    if (!d_codes || !d_mask || !d_block_offsets || !d_lengths || !d_colmin || m < 0)
-        return skr::fail(SKR_ERR_ARG, "skr_count_colmin: null or negative argument");
-    if (k < 1 || k > 8) return skr::fail(SKR_ERR_ARG, "skr_count_colmin: k=%d not supported (1 <= k <= 8)", k);
-    const int64_t bins = (int64_t)1 << (2 * k);
-    if ((d_out && (ld_out < bins || ((uintptr_t)d_out & 15) || (ld_out % 4))) || ((uintptr_t)d_colmin & 15))
-        return skr::fail(SKR_ERR_ARG, "skr_count_colmin: bad pitch or alignment");
-    CountParams p{};
-    p.codes = d_codes;
-    p.mask = d_mask;
-    p.blk_off = d_block_offsets;
-    p.len = d_lengths;
-    p.m = m;
-    p.log2_pre = log2_pre;
-    p.out = d_out;
-    p.ld_out = ld_out;
-    p.colmin = d_colmin;
-    p.no_store = d_out == nullptr;
-    cudaStream_t s = (cudaStream_t)stream;
-    switch (k) {
-        case 1: return dispatch_count<1>(p, 0, 0, s);
-        case 2: return dispatch_count<2>(p, 0, 0, s);
-        case 3: return dispatch_count<3>(p, 0, 0, s);
-        case 4: return dispatch_count<4>(p, 0, 0, s);
-        case 5: return dispatch_count<5>(p, 0, 0, s);
-        case 6: return dispatch_count<6>(p, 0, 0, s);
-        case 7: return dispatch_count<7>(p, 0, 0, s);
-        default: return dispatch_count<8>(p, 0, 0, s);
-    }
+    if (!d_colmin) return skr::fail(SKR_ERR_ARG, "skr_count_colmin: null or negative argument");
+    SkrCountArgs a{};
+    a.d_codes = d_codes;
+    a.d_mask = d_mask;
+    a.d_block_offsets = d_block_offsets;
+    a.d_lengths = d_lengths;
+    a.m = m;
+    a.k = k;
+    a.log2_pre = log2_pre;
+    a.d_out = d_out;
+    a.ld_out = ld_out;
+    a.d_colmin = d_colmin;
+    return skr_count_ex(&a, stream);
 }
 
 extern "C" int skr_colmin_scan(const float* d_a, int64_t m, int64_t cols, int64_t ld, uint32_t* d_colmin, void* stream) {
@@ -1350,6 +1638,12 @@ extern "C" int skr_log2_norm(float* d_a, int64_t m, int64_t cols, int64_t ld, vo
 extern "C" int skr_post_log2(float* d_a, int64_t m, int64_t cols, int64_t ld, const SkrMinCell* d_min, void* stream) {
     if (!d_min) return skr::fail(SKR_ERR_ARG, "skr_post_log2: null min cell");
     return launch_ew<OP_POST>(d_a, m, cols, ld, nullptr, 0, d_min, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int skr_post_log2_skip(float* d_a, int64_t m, int64_t cols, int64_t ld, const SkrMinCell* d_min,
+                                  const uint32_t* d_skip, void* stream) {
+    if (!d_min) return skr::fail(SKR_ERR_ARG, "skr_post_log2_skip: null min cell");
+    return launch_ew<OP_POST>(d_a, m, cols, ld, nullptr, 0, d_min, nullptr, (cudaStream_t)stream, nullptr, d_skip);
 }
 
 extern "C" int skr_sub_vec(float* d_a, int64_t m, int64_t cols, int64_t ld, const void* d_vec, int vec_is_f64,

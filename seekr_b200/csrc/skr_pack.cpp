@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <unordered_map>
@@ -149,6 +150,27 @@ extern "C" int skr_host_alloc(size_t bytes, void** out) {
     return SKR_OK;
 }
 
+extern "C" int skr_host_alloc_pooled(size_t bytes, void** out) {
+    if (!out) return skr::fail(SKR_ERR_ARG, "skr_host_alloc_pooled: null out");
+    *out = nullptr;
+    Slab s;
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mu);
+        int best = -1;
+        for (size_t i = 0; i < g_pool.size(); ++i)
+            if (g_pool[i].cap >= bytes && (best < 0 || g_pool[i].cap < g_pool[best].cap)) best = (int)i;
+        if (best < 0) return SKR_OK;
+        s = g_pool[best];
+        g_pool.erase(g_pool.begin() + best);
+    }
+    {
+        std::lock_guard<std::mutex> lock(g_live_mu);
+        g_live[s.ptr] = s;
+    }
+    *out = s.ptr;
+    return SKR_OK;
+}
+
 extern "C" void skr_host_free(void* p) {
     if (!p) return;
     Slab s;
@@ -202,7 +224,10 @@ extern "C" int skr_device_count(int* out) {
     return SKR_OK;
 }
 
+struct PackJob;
+
 struct SkrPacked {
+    PackJob* job = nullptr;  // packing still running in the background (skr_pack_fasta_buffer_async)
     int64_t m = 0;
     int64_t nblocks = 0;  // including the trailing pad block
     int64_t total_bases = 0;
@@ -488,12 +513,124 @@ int alloc_packed(SkrPacked* P, int64_t m, const std::vector<uint64_t>& bases, bo
     return SKR_OK;
 }
 
+
+}  // namespace
+
+// The pack pass over the records found by the scan: groups of 64 records are drawn in record order by however many
+// threads run work(); done[g] is raised when group g is complete, so a consumer can follow the packed prefix.
+struct PackJob {
+    SkrPacked* P;
+    std::vector<Rec> recs;
+    const char* text;
+    const char* end;
+    SimdAlphabet al;
+    uint8_t lut2[256];
+    bool use_avx2;
+    int64_t m;
+    int64_t ngroups;
+    std::atomic<int64_t> next_rec{0};
+    std::unique_ptr<std::atomic<uint8_t>[]> done;
+    std::atomic<int64_t> watermark{0};  // groups [0, watermark) are known to be complete
+    std::vector<std::thread> threads;
+
+    static constexpr int64_t kGroup = 64;
+
+    PackJob(SkrPacked* P_, std::vector<Rec>&& recs_, const char* text_, const char* end_, const SimdAlphabet& al_,
+            const uint8_t* lut2_, bool use_avx2_)
+        : P(P_), recs(std::move(recs_)), text(text_), end(end_), al(al_), use_avx2(use_avx2_) {
+        memcpy(lut2, lut2_, 256);
+        m = (int64_t)recs.size();
+        ngroups = (m + kGroup - 1) / kGroup;
+        done.reset(new std::atomic<uint8_t>[(size_t)std::max<int64_t>(ngroups, 1)]);
+        for (int64_t g = 0; g < ngroups; ++g) done[g].store(0, std::memory_order_relaxed);
+    }
+
+    void work() {
+        for (;;) {
+            const int64_t i0 = next_rec.fetch_add(kGroup);
+            if (i0 >= m) break;
+            const int64_t i1 = std::min(m, i0 + kGroup);
+            for (int64_t i = i0; i < i1; ++i) {
+                const Rec& r = recs[i];
+                uint64_t b0 = P->blk_off[i], b1 = P->blk_off[i + 1];
+                BitWriter w{P->codes + b0 * 4, P->mask + b0 * 2};
+                const char* bs = text + r.body_off;
+                const char* be = bs + r.body_len;
+                if (r.body_len) {
+                    auto pack_line = [&](const char* a, const char* b) -> bool {
+                        strip(a, b);
+                        if (al.ok) pack_segment_avx2(w, a, b, al, end);
+                        else for (const char* p = a; p < b; ++p) w.put(lut2[(unsigned char)*p]);
+                        return true;
+                    };
+                    if (use_avx2) for_each_line_avx2(bs, bs, be, be, pack_line);
+                    else for_each_line(bs, bs, be, be, pack_line);
+                }
+                w.finish(P->codes + b1 * 4, P->mask + b1 * 2);
+            }
+            done[i0 / kGroup].store(1, std::memory_order_release);
+        }
+    }
+
+    void start(int nthreads) {
+        threads.reserve((size_t)nthreads);
+        for (int t = 0; t < nthreads; ++t) threads.emplace_back([this] { work(); });
+    }
+
+    // blocks until records [0, upto) are packed
+    void wait_records(int64_t upto) {
+        const int64_t need = std::min(ngroups, (upto + kGroup - 1) / kGroup);
+        int64_t w = watermark.load(std::memory_order_relaxed);
+        int spins = 0;
+        while (w < need) {
+            if (done[w].load(std::memory_order_acquire)) { ++w; continue; }
+            if (++spins < 2000) _mm_pause(); else std::this_thread::yield();
+        }
+        watermark.store(w, std::memory_order_relaxed);
+    }
+
+    void join() {
+        for (auto& t : threads) t.join();
+        threads.clear();
+    }
+};
+
+namespace {
 }  // namespace
 
 extern "C" int64_t skr_pack_error_line(void) { return g_error_line; }
 
+static int pack_fasta_buffer(const void* text_v, size_t nbytes, const uint8_t* lut, int nthreads, int pinned, bool async,
+                             SkrPacked** out);
+
 extern "C" int skr_pack_fasta_buffer(const void* text_v, size_t nbytes, const uint8_t* lut, int nthreads, int pinned,
                                      SkrPacked** out) {
+    return pack_fasta_buffer(text_v, nbytes, lut, nthreads, pinned, false, out);
+}
+
+extern "C" int skr_pack_fasta_buffer_async(const void* text_v, size_t nbytes, const uint8_t* lut, int nthreads, int pinned,
+                                           SkrPacked** out) {
+    return pack_fasta_buffer(text_v, nbytes, lut, nthreads, pinned, true, out);
+}
+
+extern "C" int skr_packed_wait_records(SkrPacked* p, int64_t upto) {
+    if (!p) return skr::fail(SKR_ERR_ARG, "skr_packed_wait_records: null handle");
+    if (p->job) p->job->wait_records(upto < 0 ? p->m : std::min(upto, p->m));
+    return SKR_OK;
+}
+
+extern "C" int skr_packed_wait(SkrPacked* p) {
+    if (!p) return skr::fail(SKR_ERR_ARG, "skr_packed_wait: null handle");
+    if (p->job) {
+        p->job->join();
+        delete p->job;
+        p->job = nullptr;
+    }
+    return SKR_OK;
+}
+
+static int pack_fasta_buffer(const void* text_v, size_t nbytes, const uint8_t* lut, int nthreads, int pinned, bool async,
+                             SkrPacked** out) {
     g_error_line = 0;
     if (!out || !lut || (!text_v && nbytes)) return skr::fail(SKR_ERR_ARG, "skr_pack_fasta_buffer: null argument");
     *out = nullptr;
@@ -609,37 +746,27 @@ extern "C" int skr_pack_fasta_buffer(const void* text_v, size_t nbytes, const ui
     if (rc != SKR_OK) { delete P; return rc; }
     P->header_spans.resize((size_t)m * 2);
     P->body_spans.resize((size_t)m * 2);
+    for (int64_t i = 0; i < m; ++i) {  // the spans belong to the record table: final before packing starts
+        P->header_spans[2 * i] = recs[i].hdr_off;
+        P->header_spans[2 * i + 1] = recs[i].hdr_len;
+        P->body_spans[2 * i] = recs[i].body_off;
+        P->body_spans[2 * i + 1] = recs[i].body_len;
+    }
     const auto t_alloc = now();
-    std::atomic<int64_t> next_rec{0};
-    run_threads(T, [&](int) {
-        for (;;) {
-            int64_t i0 = next_rec.fetch_add(64);
-            if (i0 >= m) break;
-            int64_t i1 = std::min(m, i0 + 64);
-            for (int64_t i = i0; i < i1; ++i) {
-                const Rec& r = recs[i];
-                P->header_spans[2 * i] = r.hdr_off;
-                P->header_spans[2 * i + 1] = r.hdr_len;
-                P->body_spans[2 * i] = r.body_off;
-                P->body_spans[2 * i + 1] = r.body_len;
-                uint64_t b0 = P->blk_off[i], b1 = P->blk_off[i + 1];
-                BitWriter w{P->codes + b0 * 4, P->mask + b0 * 2};
-                const char* bs = text + r.body_off;
-                const char* be = bs + r.body_len;
-                if (r.body_len) {
-                    auto pack_line = [&](const char* a, const char* b) -> bool {
-                        strip(a, b);
-                        if (al.ok) pack_segment_avx2(w, a, b, al, end);
-                        else for (const char* p = a; p < b; ++p) w.put(lut2[(unsigned char)*p]);
-                        return true;
-                    };
-                    if (use_avx2) for_each_line_avx2(bs, bs, be, be, pack_line);
-                    else for_each_line(bs, bs, be, be, pack_line);
-                }
-                w.finish(P->codes + b1 * 4, P->mask + b1 * 2);
-            }
-        }
-    });
+    PackJob* job = new PackJob(P, std::move(recs), text, end, al, lut2, use_avx2);
+    if (async) {
+        // the record table (lengths, block offsets) is final; codes and mask are filled by T background threads in
+        // record order, consumers follow the progress with skr_packed_wait_records
+        P->job = job;
+        job->start(T);
+        *out = P;
+        if (profile)
+            fprintf(stderr, "skr_pack (async): %d threads, scan %.2f ms, merge+alloc %.2f ms (%zu bytes, %lld records)\n", T,
+                    ms(t_start, t_pass1), ms(t_pass1, t_alloc), nbytes, (long long)m);
+        return SKR_OK;
+    }
+    run_threads(T, [&](int) { job->work(); });
+    delete job;
     if (profile)
         fprintf(stderr, "skr_pack: %d threads, scan %.2f ms, merge+alloc %.2f ms, pack %.2f ms (%zu bytes, %lld records)\n", T,
                 ms(t_start, t_pass1), ms(t_pass1, t_alloc), ms(t_alloc, now()), nbytes, (long long)m);
@@ -705,6 +832,7 @@ extern "C" int skr_pack_sequences(const void* letters_v, const int64_t* offs, in
 
 extern "C" void skr_packed_free(SkrPacked* p) {
     if (!p) return;
+    skr_packed_wait(p);  // background packing writes into the slab
     slab_free(p->slab);
     delete p;
 }

@@ -10,12 +10,26 @@
 // publish needs that peer's previous one), so the slot of epoch e is free again when epoch e + 2 is written.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+#include <cstring>
+
 #include "skr_common.h"
 #include "skr_device.cuh"
 
 namespace {
 
-constexpr unsigned long long kSpinLimitNs = 4000000000ull;  // a missing peer must not hang the GPU: 4 s, then error
+// A missing peer must not hang the GPU for ever: after the spin limit the kernel gives up and raises the error
+// flag (the caller then falls back to the library all-reduce or raises).  The default is generous (ranks of one
+// job may be seconds apart: FASTA parsing, a first pinned allocation); SEEKR_B200_PEER_TIMEOUT_S changes it.
+unsigned long long spin_limit_ns() {
+    static const unsigned long long v = [] {
+        const char* env = getenv("SEEKR_B200_PEER_TIMEOUT_S");
+        double s = env ? atof(env) : 60.0;
+        if (!(s > 0.0)) s = 60.0;
+        return (unsigned long long)(s * 1e9);
+    }();
+    return v;
+}
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
@@ -33,7 +47,9 @@ __device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long lon
 
 // peers[t]: address of rank t's exchange buffer as mapped into this process; layout [2 parities][world] words
 __global__ void min_exchange_kernel(SkrMinCell* cell, unsigned long long* const* peers, int world, int rank,
-                                    unsigned long long epoch, int* err) {
+                                    unsigned long long epoch, int* err, unsigned long long kSpinLimitNs,
+                                    const uint32_t* skip) {
+    if (skip && *skip) return;  // the same value on every rank (callers exchange the flag first)
     const int lane = threadIdx.x;
     const unsigned long long parity = epoch & 1ull;
     unsigned long long mine = 0;
@@ -76,7 +92,8 @@ __global__ void min_exchange_kernel(SkrMinCell* cell, unsigned long long* const*
 __global__ void __launch_bounds__(256) colstat_exchange_kernel(const double* __restrict__ acc, unsigned char* const* peers,
                                                                int world, int rank, unsigned long long epoch, long long n,
                                                                long long n_cap, long long total_rows, int take_sqrt,
-                                                               float* __restrict__ out, int* flag, int* err) {
+                                                               float* __restrict__ out, int* flag, int* err,
+                                                               unsigned long long kSpinLimitNs) {
     const unsigned long long parity = epoch & 1ull;
     const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t flags_off = (size_t)2 * world * n_cap * sizeof(double);
@@ -178,11 +195,17 @@ extern "C" int skr_peer_free(void* d_ptr) {
 
 extern "C" int skr_min_exchange(SkrMinCell* d_cell, void* const* d_peers, int world, int rank, uint64_t epoch, int* d_err,
                                 void* stream) {
+    return skr_min_exchange_skip(d_cell, d_peers, world, rank, epoch, nullptr, d_err, stream);
+}
+
+extern "C" int skr_min_exchange_skip(SkrMinCell* d_cell, void* const* d_peers, int world, int rank, uint64_t epoch,
+                                     const uint32_t* d_skip, int* d_err, void* stream) {
     if (!d_cell || !d_peers || !d_err) return skr::fail(SKR_ERR_ARG, "skr_min_exchange: null argument");
     if (world < 1 || world > 32 || rank < 0 || rank >= world)
         return skr::fail(SKR_ERR_ARG, "skr_min_exchange: world must be 1..32 and 0 <= rank < world");
     if (epoch == 0 || epoch >= (1ull << 31)) return skr::fail(SKR_ERR_ARG, "skr_min_exchange: epoch must be 1 .. 2^31 - 1");
-    min_exchange_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_cell, (unsigned long long* const*)d_peers, world, rank, epoch, d_err);
+    min_exchange_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_cell, (unsigned long long* const*)d_peers, world, rank, epoch, d_err,
+                                                            spin_limit_ns(), d_skip);
     SKR_LAUNCH_CHECK();
     return SKR_OK;
 }
@@ -204,7 +227,7 @@ extern "C" int skr_colstat_exchange(const double* d_acc, void* const* d_peers, i
     if (d_flag) SKR_CUDA_CHECK(cudaMemsetAsync(d_flag, 0, sizeof(int), (cudaStream_t)stream));
     colstat_exchange_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_acc, (unsigned char* const*)d_peers, world, rank,
                                                                                  epoch, n, n_cap, total_rows, take_sqrt, d_out,
-                                                                                 d_flag, d_err);
+                                                                                 d_flag, d_err, spin_limit_ns());
     SKR_LAUNCH_CHECK();
     return SKR_OK;
 }

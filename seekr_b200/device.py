@@ -68,6 +68,37 @@ def pinned_empty(shape, dtype):
     return arr
 
 
+_cold_results = 0
+
+
+def result_buffer(shape, dtype):
+    """Host array for a result that is about to be copied out of the device: (array, pinned).
+
+    A pinned slab from the library's pool when it holds one that large (the copy engine then writes the array
+    directly).  Otherwise the FIRST large result of a process goes to ordinary pageable memory -- page-locking
+    0.8 GB costs ~0.7 s, more than the whole one-shot ``seekr_kmer_counts`` run, and the streamed path reaches
+    pageable memory through a small pinned ring -- and from the second one on a pinned slab is allocated, which the
+    pool keeps for the calls that follow."""
+    global _cold_results
+    lib = _lib.load()
+    dtype = np.dtype(dtype)
+    shape = tuple(int(s) for s in shape)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+    if nbytes == 0:
+        return np.empty(shape, dtype=dtype), False
+    raw = ctypes.c_void_p()
+    _lib.check(lib.skr_host_alloc_pooled(nbytes, ctypes.byref(raw)))
+    if not raw.value:
+        if nbytes >= (64 << 20) and _cold_results == 0:
+            _cold_results += 1
+            return np.empty(shape, dtype=dtype), False
+        _lib.check(lib.skr_host_alloc(nbytes, ctypes.byref(raw)))
+    buf = (ctypes.c_char * nbytes).from_address(raw.value)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    weakref.finalize(buf, lib.skr_host_free, ctypes.c_void_p(raw.value))
+    return arr, True
+
+
 def host_ptr(arr):
     return ctypes.c_void_p(arr.ctypes.data)
 

@@ -70,16 +70,19 @@ class PackedFasta:
 
     # -- construction ---------------------------------------------------------------------------
     @classmethod
-    def from_file(cls, path, alphabet="AGTC", pinned=False, nthreads=0):
+    def from_file(cls, path, alphabet="AGTC", pinned=False, nthreads=0, background=False):
         lib = _lib.load()
         lut = alphabet_lut(alphabet)
         size = os.path.getsize(path)
         with open(path, "rb") as handle:
             text = mmap.mmap(handle.fileno(), 0, access=mmap.ACCESS_READ) if size else b""
-        return cls.from_buffer(text, alphabet, pinned, nthreads, _lut=lut, _lib_=lib)
+        return cls.from_buffer(text, alphabet, pinned, nthreads, _lut=lut, _lib_=lib, background=background)
 
     @classmethod
-    def from_buffer(cls, text, alphabet="AGTC", pinned=False, nthreads=0, _lut=None, _lib_=None):
+    def from_buffer(cls, text, alphabet="AGTC", pinned=False, nthreads=0, _lut=None, _lib_=None, background=False):
+        """background=True returns once the text has been scanned (records, lengths, every error of the synchronous
+        call); the code / mask words are packed by host threads behind the caller's back, in record order, and
+        ``wait()`` (implied by the ``codes`` / ``mask`` views) or the streamed count path picks them up."""
         lib = _lib_ or _lib.load()
         lut = _lut if _lut is not None else alphabet_lut(alphabet)
         if nthreads <= 0 and len(text) > (1 << 22):
@@ -91,10 +94,12 @@ class PackedFasta:
         else:
             addr = ctypes.c_void_p(0)
         out = ctypes.c_void_p()
-        rc = lib.skr_pack_fasta_buffer(addr, n, ctypes.c_void_p(lut.ctypes.data), nthreads, int(pinned),
-                                       ctypes.byref(out))
+        pack = lib.skr_pack_fasta_buffer_async if background else lib.skr_pack_fasta_buffer
+        rc = pack(addr, n, ctypes.c_void_p(lut.ctypes.data), nthreads, int(pinned), ctypes.byref(out))
         _lib.check(rc)
-        return cls(out, text)
+        obj = cls(out, text)
+        obj._pending = bool(background)
+        return obj
 
     @classmethod
     def from_sequences(cls, seqs, alphabet="AGTC", pinned=False, nthreads=0):
@@ -115,9 +120,16 @@ class PackedFasta:
         obj._seq_list = list(seqs)
         return obj
 
+    def wait(self):
+        """Block until a background packer (from_file(..., background=True)) has filled codes and mask."""
+        if getattr(self, "_pending", False) and self._h is not None:
+            _lib.check(self._lib.skr_packed_wait(self._h))
+            self._pending = False
+        return self
+
     def close(self):
         if self._h is not None:
-            self._lib.skr_packed_free(self._h)
+            self._lib.skr_packed_free(self._h)  # waits for a background packer first
             self._h = None
 
     def __del__(self):
@@ -144,10 +156,12 @@ class PackedFasta:
 
     @property
     def codes(self):
+        self.wait()
         return self._view(self._lib.skr_packed_codes, self.nblocks * 4, np.uint32)
 
     @property
     def mask(self):
+        self.wait()
         return self._view(self._lib.skr_packed_mask, self.nblocks * 2, np.uint32)
 
     def header(self, i):

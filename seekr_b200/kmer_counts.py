@@ -14,6 +14,7 @@ There is no CPU path: without the library or a CUDA device these methods raise.
 """
 
 import ctypes
+import os
 from itertools import product
 
 import numpy as np
@@ -126,6 +127,24 @@ class DeviceVector:
         return self
 
 
+class PostSpec:
+    """Device SkrPostSpec: the speculated Log2.post shift, its arg-min column and the "zero seen" flag."""
+
+    def __init__(self, engine, mean_vec, std_vec):
+        torch = engine.torch
+        self.t = device.empty(4, torch.int32)
+        self.flag = self.t[3:4]       # zero_seen: non-zero = the speculation held
+        self.cell = self.t[2:4]       # (zero_col, zero_seen) seen as a SkrMinCell: MIN / OR over ranks
+        is_f64 = (mean_vec or std_vec).is_f64
+        _lib.check(engine.lib.skr_post_spec(device.ptr(mean_vec.t if mean_vec else None),
+                                            device.ptr(std_vec.t if std_vec else None), int(is_f64), engine.cols,
+                                            device.ptr(self.t), device.stream_ptr(engine.stream)))
+
+    def held(self):
+        """True when some record had a zero count in the arg-min column (synchronises)."""
+        return bool(int(self.flag.item()))
+
+
 class CountEngine:
     """The get_counts() pipeline on device tensors.  Shared by BasicCounter, the sharded driver
     (seekr_b200.parallel) and bench.py, so the timed path and the API path are the same code."""
@@ -146,19 +165,33 @@ class CountEngine:
         # equal to fused count + post pass on B200 (both ~0.6 ms for 50k transcripts, instruction-bound), so off
         self.deferred = False
         self.fused_tail = True   # self-normalised Log2.post: column minima from the count kernel, one tail pass
+        # Log2.post with supplied vectors in ONE pass: the shift is derived from the vectors alone (PostSpec), the
+        # two-pass route is enqueued behind it and skips itself on the device when the speculation held
+        self.speculative = True
+        # mean=True / std=True from column sums accumulated inside the count kernel (binary64 finish; closer to the
+        # exact value than numpy's sequential fp32 sums, hence not bit-identical to the reference): off by default,
+        # the order-exact passes are the parity route
+        self.accurate_stats = False
+        self.spec = None
 
     # -- building blocks ------------------------------------------------------------------------
     def upload(self, packed):
         """PackedFasta -> one device slab (a single async copy; pinned when the packer was asked to)."""
         torch = self.torch
+        packed.wait()
         slab = torch.empty(max(packed.slab_bytes, 16), dtype=torch.uint8, device=device.current_device())
         _lib.check(self.lib.skr_copy_h2d(device.ptr(slab), ctypes.c_void_p(packed.slab_ptr), packed.slab_bytes,
                                          device.stream_ptr(self.stream)))
         return DevicePacked(slab, packed)
 
-    def count(self, dpk, out, mean=None, std=None, track_min=False, out_is_f64=False, post=False):
-        """skr_count into ``out`` (m x cols).  mean/std: DeviceVector or None.  post=True applies the Log2.post
-        tail in the same epilogue, using the minimum already held by ``self.min_cell``."""
+    def count(self, dpk, out, mean=None, std=None, track_min=False, out_is_f64=False, post=False, spec=None, skip=None,
+              colmin=None, colsums=None, rows=None):
+        """skr_count_ex into ``out`` (m x cols).  mean/std: DeviceVector or None.  post=True applies the Log2.post
+        tail in the same epilogue, using the minimum already held by ``self.min_cell``; ``spec`` (a PostSpec) does
+        the same with the speculated shift and lets the kernel report whether the speculation held; ``skip`` (device
+        uint32) turns the launch into a no-op when non-zero; ``colmin`` / ``colsums`` = (sum, sum of squares)
+        collect column minima / binary64 column sums of the plain values; ``rows`` = (begin, end) counts a record
+        sub-range into the same rows of ``out``."""
         vec_is_f64 = False
         if mean is not None and std is not None and mean.is_f64 != std.is_f64:
             # (double)x op (double)v rounded to fp32 equals the fp32 operation (24-bit operands,
@@ -175,13 +208,28 @@ class CountEngine:
         if (std is not None and not vec_is_f64 and std.well_scaled and std.positive
                 and (mean is None or getattr(mean, "bounded", False)) and self.fast_division):
             rstd = std.reciprocal(self.stream)
+        begin, end = rows if rows is not None else (0, dpk.m)
+        a = _lib.CountArgs()
+        a.d_codes, a.d_mask = dpk.codes, dpk.mask
+        a.d_block_offsets = ctypes.c_void_p(dpk.blk_off.value + 8 * begin)
+        a.d_lengths = ctypes.c_void_p(dpk.lengths.value + 4 * begin)
+        a.m, a.k, a.log2_pre = end - begin, self.k, 0 if out_is_f64 else log2_pre
+        a.d_mean, a.d_std, a.d_rstd = device.ptr(mean.t if mean else None), device.ptr(std.t if std else None), device.ptr(rstd)
+        a.vec_is_f64, a.out_is_f64 = int(vec_is_f64), int(out_is_f64)
+        if out is not None:
+            a.d_out = ctypes.c_void_p(out.data_ptr() + begin * out.stride(0) * out.element_size())
+            a.ld_out = out.stride(0)
+        a.d_min = device.ptr(self.min_cell.t if track_min else None)
+        if spec is not None:
+            a.d_post, a.d_spec = device.ptr(spec.t), device.ptr(spec.t)
+        elif post:
+            a.d_post = device.ptr(self.min_cell.t)
+        a.d_skip = device.ptr(skip)
+        a.d_colmin = device.ptr(colmin)
+        if colsums is not None:
+            a.d_colsum, a.d_colsq = device.ptr(colsums[0]), device.ptr(colsums[1])
         ev = self._event_start()
-        rc = self.lib.skr_count(
-            dpk.codes, dpk.mask, dpk.blk_off, dpk.lengths, dpk.m, self.k, 0 if out_is_f64 else log2_pre,
-            device.ptr(mean.t if mean else None), device.ptr(std.t if std else None), int(vec_is_f64),
-            device.ptr(out), int(out_is_f64), out.stride(0), device.ptr(self.min_cell.t if track_min else None),
-            device.ptr(self.min_cell.t if post else None), device.ptr(rstd), device.stream_ptr(self.stream))
-        _lib.check(rc)
+        _lib.check(self.lib.skr_count_ex(ctypes.byref(a), device.stream_ptr(self.stream)))
         self._event_end(ev)
         self._keep = (mean, std)  # converted vectors must outlive the launch
 
@@ -266,10 +314,10 @@ class CountEngine:
         _lib.check(self.lib.skr_min_scan(device.ptr(a), m, cols, a.stride(0), device.ptr(self.min_cell.t),
                                          device.stream_ptr(self.stream)))
 
-    def post_log2(self, a):
+    def post_log2(self, a, skip=None):
         m, cols = a.shape
-        _lib.check(self.lib.skr_post_log2(device.ptr(a), m, cols, a.stride(0), device.ptr(self.min_cell.t),
-                                          device.stream_ptr(self.stream)))
+        _lib.check(self.lib.skr_post_log2_skip(device.ptr(a), m, cols, a.stride(0), device.ptr(self.min_cell.t),
+                                               device.ptr(skip), device.stream_ptr(self.stream)))
 
     def log2_norm(self, a):
         m, cols = a.shape
@@ -318,6 +366,23 @@ class CountEngine:
             self.count(dpk, out, mean_vec, std_vec, post=True)
             self._keep = (mean_vec, std_vec, colmin)
             return out, mean_vec, std_vec
+        if mean is not True and std is not True and need_min and (mean_vec or std_vec) and self.speculative \
+                and self._benign(mean_vec, std_vec):
+            # Log2.post with known, well-behaved vectors in ONE pass over the matrix (kmer_counts.py:207-209):
+            # the shift |min| follows from the vectors alone whenever the arg-min column of the zero-count z-scores
+            # holds a zero count somewhere (PostSpec).  No collective before counting; a sharded run ORs the
+            # "zero seen" flags afterwards, and the two-pass route below is skipped on the device when it is set.
+            if mean_vec is not None and std_vec is not None and mean_vec.is_f64 != std_vec.is_f64:
+                mean_vec, std_vec = mean_vec.as_f64(), std_vec.as_f64()
+            spec = self.spec = PostSpec(self, mean_vec, std_vec)
+            self.count(dpk, out, mean_vec, std_vec, spec=spec)
+            if reducer:
+                reducer.flag_or(self, spec)
+            self.count(dpk, out, mean_vec, std_vec, track_min=True, skip=spec.flag)
+            if reducer:
+                reducer.min_allreduce(self, skip=spec.flag)
+            self.post_log2(out, skip=spec.flag)
+            return out, mean_vec, std_vec
         if mean is not True and std is not True:
             # every vector is known up front: one fused launch (+ the Log2.post pass)
             track = need_min or std is not False
@@ -334,22 +399,40 @@ class CountEngine:
             colmin = None
             if fused_tail:
                 colmin = device.empty(self.cols, torch.int32)
-                self.count_colmin(dpk, colmin, out=out)
-            else:
-                self.count(dpk, out)
-            stat = reducer.col_stat if reducer else self._local_col_stat
+                _lib.check(self.lib.skr_colmin_reset(device.ptr(colmin), self.cols, device.stream_ptr(self.stream)))
             flags = device.zeros(2, torch.int32)
-            if mean is True:
-                mean_vec = DeviceVector(stat(self, _lib.COLPASS_SUM, out, None, None, "mean", flags[0:1]), False,
-                                        flag=flags[0:1])
-            if std is True:
-                # np.std on what center() left behind: its own mean first (kmer_counts.py:169,174)
-                if mean_vec is not None:
-                    arrmean = stat(self, _lib.COLPASS_CENTERED, out, mean_vec, None, "mean")
-                else:
-                    arrmean = stat(self, _lib.COLPASS_SUM, out, None, None, "mean")
-                std_vec = DeviceVector(stat(self, _lib.COLPASS_SQDEV, out, mean_vec, arrmean, "std", flags[1:2]), False,
-                                       flag=flags[1:2])
+            if self.accurate_stats and self.k == 6:
+                # norm_vectors in ONE pass and (sharded) ONE exchange: the count kernel sums the values and the
+                # squares of every column while the rows are still in registers; binary64 finish.  Not the
+                # reference's sequential fp32 order (that is the route below), closer to the exact value.
+                sums = device.zeros((2, self.cols), torch.float64)
+                self.count(dpk, out, colmin=colmin, colsums=(sums[0], sums[1]))
+                if reducer:
+                    reducer.sum_allreduce(sums)
+                total = reducer.total_rows(m, out.device) if reducer else m
+                mean_t = device.empty(self.cols, torch.float32) if mean is True else None
+                std_t = device.empty(self.cols, torch.float32) if std is True else None
+                _lib.check(self.lib.skr_colstat_finish(device.ptr(sums[0]), device.ptr(sums[1]), self.cols, total,
+                                                       device.ptr(mean_t), device.ptr(std_t), device.ptr(flags),
+                                                       device.stream_ptr(self.stream)))
+                if mean is True:
+                    mean_vec = DeviceVector(mean_t, False, flag=flags[0:1])
+                if std is True:
+                    std_vec = DeviceVector(std_t, False, flag=flags[1:2])
+            else:
+                self.count(dpk, out, colmin=colmin)
+                stat = reducer.col_stat if reducer else self._local_col_stat
+                if mean is True:
+                    mean_vec = DeviceVector(stat(self, _lib.COLPASS_SUM, out, None, None, "mean", flags[0:1]), False,
+                                            flag=flags[0:1])
+                if std is True:
+                    # np.std on what center() left behind: its own mean first (kmer_counts.py:169,174)
+                    if mean_vec is not None:
+                        arrmean = stat(self, _lib.COLPASS_CENTERED, out, mean_vec, None, "mean")
+                    else:
+                        arrmean = stat(self, _lib.COLPASS_SUM, out, None, None, "mean")
+                    std_vec = DeviceVector(stat(self, _lib.COLPASS_SQDEV, out, mean_vec, arrmean, "std", flags[1:2]), False,
+                                           flag=flags[1:2])
             if vectors_only:
                 bits = flags.cpu().numpy()
                 self.vector_nan = bool((mean is True and bits[0] & 1) or (std is True and bits[1] & 3))
@@ -385,6 +468,65 @@ class CountEngine:
                 reducer.min_allreduce(self)
             self.post_log2(out)
         return out, mean_vec, std_vec
+
+    def run_streamed(self, packed, mean, std, want_host=True):
+        """get_counts() as a pipeline (skr_stream_counts): the packer's output is copied in, counted and copied out
+        chunk by chunk while the packer is still at work, so the end-to-end time is the longest stage (the D2H of
+        the matrix) instead of their sum.  Applies when rows are independent once the vectors are known: no
+        mean=True / std=True, and Log2.post only with well-behaved supplied vectors (speculated shift).  Returns
+        (device matrix, mean_vec, std_vec, host matrix or None), or None when the staged path must be used."""
+        torch = self.torch
+        if mean is True or std is True or packed.m == 0 or packed.slab_ptr is None:
+            return None
+        mean_vec = mean if isinstance(mean, DeviceVector) else None
+        std_vec = std if isinstance(std, DeviceVector) else None
+        post = self.log2 == "Log2.post"
+        if post and not (self.speculative and (mean_vec or std_vec) and self._benign(mean_vec, std_vec)):
+            return None
+        if mean_vec is not None and std_vec is not None and mean_vec.is_f64 != std_vec.is_f64:
+            mean_vec, std_vec = mean_vec.as_f64(), std_vec.as_f64()
+        vec_is_f64 = bool((mean_vec or std_vec).is_f64) if (mean_vec or std_vec) else False
+        m, cols = packed.m, self.cols
+        slab = torch.empty(max(packed.slab_bytes, 16), dtype=torch.uint8, device=device.current_device())
+        out = device.empty((m, cols), torch.float32)
+        host, pinned = (device.result_buffer((m, cols), np.float32) if want_host else (None, False))
+        rstd = None
+        if (std_vec is not None and not vec_is_f64 and std_vec.well_scaled and std_vec.positive
+                and (mean_vec is None or getattr(mean_vec, "bounded", False)) and self.fast_division):
+            rstd = std_vec.reciprocal(self.stream)
+        spec = self.spec = PostSpec(self, mean_vec, std_vec) if post else None
+        sa = _lib.StreamArgs()
+        a = sa.count
+        a.k, a.log2_pre = self.k, 1 if self.log2 == "Log2.pre" else 0
+        a.d_mean, a.d_std, a.d_rstd = device.ptr(mean_vec.t if mean_vec else None), device.ptr(std_vec.t if std_vec else None), device.ptr(rstd)
+        a.vec_is_f64 = int(vec_is_f64)
+        a.d_out, a.ld_out = device.ptr(out), out.stride(0)
+        if spec is not None:
+            a.d_post, a.d_spec = device.ptr(spec.t), device.ptr(spec.t)
+        if std_vec is not None and not post:
+            # the reference warns about NaNs after standardisation (kmer_counts.py:176): keep the running flag
+            self.min_cell.reset(self.stream)
+            a.d_min = device.ptr(self.min_cell.t)
+        sa.d_slab = device.ptr(slab)
+        if host is not None:
+            sa.h_out, sa.h_ld, sa.h_out_pinned = device.host_ptr(host), cols, int(pinned)
+        sa.copy_threads = max(2, min(8, (os.cpu_count() or 4) // 2))
+        _lib.check(self.lib.skr_stream_counts(packed._h, ctypes.byref(sa), device.stream_ptr(self.stream)))
+        device.sync(self.stream)
+        packed.wait()
+        self._keep = (mean_vec, std_vec, rstd)
+        self.std_applied = std_vec is not None
+        dpk = DevicePacked(slab, packed)
+        if spec is not None:
+            self.min_cell.reset(self.stream)  # no NaN is possible with well-behaved vectors
+            if not spec.held():
+                # no record had a zero count in the arg-min column (pathological input): the staged two-pass route
+                out, mean_vec, std_vec = self.run(dpk, mean_vec, std_vec, out=out)
+                if host is not None:
+                    device.d2h(host, out, self.stream)
+                    device.sync(self.stream)
+        self.last_packed_device = dpk
+        return out, mean_vec, std_vec, host
 
     def _benign(self, mean_vec, std_vec):
         """Finite mean and finite, positive std?  Vectors that came from the host know (DeviceVector.from_host);
@@ -449,7 +591,9 @@ class BasicCounter:
         self._seqs = None
         self.alphabet = alphabet
         if infasta is not None:
-            self._packed = PackedFasta.from_file(infasta, alphabet=alphabet, pinned=_pinned_ok())
+            # the text is scanned here (records, lengths, format errors); packing continues on host threads and
+            # get_counts() streams the packed words to the GPU as they appear
+            self._packed = PackedFasta.from_file(infasta, alphabet=alphabet, pinned=_pinned_ok(), background=_pinned_ok())
             self._seqs = LazySeqs(self._packed)
         self.outfile = outfile
         self.k = k
@@ -630,11 +774,17 @@ class BasicCounter:
         if packed.m == 0:
             self.counts = np.zeros([0, cols], dtype=np.float32)
             return
-        dpk = engine.upload(packed)
-        out, mean_vec, std_vec = engine.run(dpk, mean, std)
-        # consumers that keep working on the GPU (find_pval, find_dist, kmer_leiden) set _device_only: the m x 4^k
-        # matrix then stays in counts_device and is not copied to the host (0.8 GB at 50 000 x 4 096)
-        self.counts = None if getattr(self, "_device_only", False) else device.to_host(out)
+        device_only = getattr(self, "_device_only", False)
+        streamed = engine.run_streamed(packed, mean, std, want_host=not device_only)
+        if streamed is not None:
+            out, mean_vec, std_vec, host = streamed
+        else:
+            dpk = engine.upload(packed)
+            out, mean_vec, std_vec = engine.run(dpk, mean, std)
+            # consumers that keep working on the GPU (find_pval, find_dist, kmer_leiden) set _device_only: the m x 4^k
+            # matrix then stays in counts_device and is not copied to the host (0.8 GB at 50 000 x 4 096)
+            host = None if device_only else device.to_host(out)
+        self.counts = host
         self.counts_device = out
         if self.mean is True:
             self.mean = device.to_host(mean_vec.t, pinned=False)

@@ -120,7 +120,9 @@ class _PeerBuffer:
 
     def check(self, what):
         if int(self.err.item()):
-            raise RuntimeError("peer-memory %s timed out: a rank did not take part within 4 s" % what)
+            self.err.zero_()  # the object is cached per process: a later, healthy exchange must not raise again
+            raise RuntimeError("peer-memory %s timed out: a rank did not take part within the spin limit "
+                               "(SEEKR_B200_PEER_TIMEOUT_S, default 60 s); results of that call are invalid" % what)
 
     def close(self):
         for mapped in self._opened:
@@ -143,12 +145,15 @@ class PeerMinExchange(_PeerBuffer):
             raise ValueError("peer exchange handles up to 32 ranks")
         super().__init__(2 * dist.get_world_size(group) * 8, group)
 
-    def exchange(self, engine):
+    def exchange(self, engine, cell=None, skip=None):
+        """cell: int32 pair on the device seen as a SkrMinCell (default: the engine's minimum cell); skip: device
+        uint32, the launch is a no-op when it is non-zero (it must hold the same value on every rank)."""
         from . import _lib, device
 
         self.epoch += 1
-        _lib.check(self.lib.skr_min_exchange(device.ptr(engine.min_cell.t), device.ptr(self.table), self.world, self.rank,
-                                             self.epoch, device.ptr(self.err), device.stream_ptr(engine.stream)))
+        _lib.check(self.lib.skr_min_exchange_skip(device.ptr(engine.min_cell.t if cell is None else cell), device.ptr(self.table),
+                                                  self.world, self.rank, self.epoch, device.ptr(skip), device.ptr(self.err),
+                                                  device.stream_ptr(engine.stream)))
 
     def check(self):
         super().check("minimum exchange")
@@ -189,29 +194,48 @@ class _Base:
         self.world = dist.get_world_size(group)
         self._total_rows = None
 
+    def set_total_rows(self, total):
+        """Tell the reducer the row count over all ranks (callers that shard a known set do: no collective, no
+        host synchronisation inside the pipeline).  None goes back to asking the ranks on every call."""
+        self._total_rows = None if total is None else int(total)
+
     def total_rows(self, local_rows, device):
+        """Rows over all ranks: the value given to set_total_rows, else one all-reduce per call (never cached: the
+        same reducer may serve data sets of different sizes)."""
         import torch
 
-        if self._total_rows is None:
-            t = torch.tensor([local_rows], dtype=torch.int64, device=device)
-            self.dist.all_reduce(t, group=self.group)
-            self._total_rows = int(t.item())
-        return self._total_rows
+        if self._total_rows is not None:
+            return self._total_rows
+        t = torch.tensor([local_rows], dtype=torch.int64, device=device)
+        self.dist.all_reduce(t, group=self.group)
+        return int(t.item())
 
     def colmin_allreduce(self, colmin):
         """Per-column minima of non-negative floats, stored as their bit patterns in an int32 tensor:
         the integer order is the float order, so a plain MIN all-reduce merges the shards."""
         self.dist.all_reduce(colmin, op=self.dist.ReduceOp.MIN, group=self.group)
 
-    def min_allreduce(self, engine):
+    def sum_allreduce(self, sums):
+        """The ONE exchange of the accurate column statistics: 2 * 4^k binary64 column sums (kmer_counts.py:168,174
+        couple all rows), one all-reduce over NVLink."""
+        self.dist.all_reduce(sums, group=self.group)
+
+    def flag_or(self, engine, spec):
+        """OR of the "zero seen" flags of the speculative Log2.post route over the ranks: the (zero_col, zero_seen)
+        pair is exchanged as a minimum cell (MIN of the identical column index, OR of the flag)."""
+        self.min_allreduce(engine, cell=spec.cell)
+
+    def min_allreduce(self, engine, cell=None, skip=None):
         """Combine the per-rank Log2.post cells (uint32 pair on the device) across ranks.  On CUDA this is one
         single-warp kernel over NVLink peer memory (PeerMinExchange); SEEKR_B200_MIN_EXCHANGE=nccl, or a box
-        without CUDA IPC between the ranks, takes the library all-reduce instead."""
+        without CUDA IPC between the ranks, takes the library all-reduce instead.  ``skip`` (device uint32, the
+        same value on every rank) turns the peer kernel into a no-op; the library all-reduce ignores it, which is
+        harmless (it then reduces a cell nobody reads)."""
         import os
 
         import torch
 
-        cell = engine.min_cell.t  # int32 storage of two uint32
+        cell = engine.min_cell.t if cell is None else cell  # int32 storage of two uint32
         if cell.is_cuda and os.environ.get("SEEKR_B200_MIN_EXCHANGE", "peer") != "nccl":
             if getattr(self, "_peer", None) is None and not getattr(self, "_peer_failed", False):
                 try:
@@ -222,7 +246,7 @@ class _Base:
                     warnings.warn("peer-memory minimum exchange unavailable (%s); using the NCCL all-reduce" % (exc,))
                     self._peer_failed = True
             if getattr(self, "_peer", None) is not None:
-                self._peer.exchange(engine)
+                self._peer.exchange(engine, cell=cell, skip=skip)
                 return
         as64 = cell.to(torch.int64) & 0xFFFFFFFF
         allreduce_min_cell(as64, self.group)

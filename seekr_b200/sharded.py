@@ -98,6 +98,7 @@ def get_counts(fasta, k=6, mean=True, std=True, log2="Log2.post", alphabet="AGTC
     mean_arg = mean if isinstance(mean, bool) else DeviceVector.from_host(mean, cols)
     std_arg = std if isinstance(std, bool) else DeviceVector.from_host(std, cols)
     reducer = parallel.ChainStats() if stats == "chain" else parallel.AllReduceStats()
+    reducer.set_total_rows(packed.m)  # every rank parsed the whole file
     out = device.empty((end - begin, cols), torch.float32)
     out, mean_vec, std_vec = engine.run(dpk, mean_arg, std_arg, out=out, reducer=reducer)
     local = device.to_host(out)

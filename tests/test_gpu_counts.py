@@ -403,13 +403,16 @@ def test_deferred_normalisation_is_bit_identical_to_fused():
         std = (raw.std(axis=0) + 0.125).astype(np.float32)
         packed = PackedFasta.from_sequences(sub, pinned=True)
         outs = []
-        for deferred in (True, False):
+        for deferred, speculative in ((True, False), (False, False), (False, True)):
             eng = CountEngine(k, "Log2.post")
-            eng.deferred = deferred
+            eng.deferred, eng.speculative = deferred, speculative
             dpk = eng.upload(packed)
             out, _, _ = eng.run(dpk, DeviceVector.from_host(mean, 4 ** k), DeviceVector.from_host(std, 4 ** k))
             outs.append(out.cpu().numpy())
+            if speculative:
+                assert eng.spec.held()      # a zero count in the arg-min column: the one-pass result stands
         assert np.array_equal(outs[0], outs[1])
+        assert np.array_equal(outs[1], outs[2])
         exp, _, _ = c_oracle.normalise(raw, mean, std, "Log2.post")
         assert np.allclose(outs[0], exp, rtol=0, atol=TOL)
         # float64 vectors and mean-only / std-only variants
@@ -419,6 +422,114 @@ def test_deferred_normalisation_is_bit_identical_to_fused():
             c.get_counts()
             exp, _, _ = c_oracle.normalise(raw, mv, sv, "Log2.post")
             assert np.allclose(c.counts, exp, rtol=0, atol=TOL)
+
+
+def test_speculative_post_falls_back_when_the_speculation_fails():
+    """The speculated shift is the z-score of a ZERO count in the arg-min column; when no record has a zero there
+    the two-pass route behind it must redo the matrix (device-side choice) and give the reference's values."""
+    rng = np.random.default_rng(11)
+    for k in (2, 6):
+        # every record carries every k-mer of a poly-A run, so column 0 ('A' * k) is never zero
+        seqs = ["A" * (k + 3) + "".join(rng.choice(list("ACGT"), size=int(n))) for n in rng.integers(300, 900, size=120)]
+        raw = c_oracle.raw_counts(seqs, k)
+        mean = raw.mean(axis=0).astype(np.float32)
+        std = (raw.std(axis=0) + 0.5).astype(np.float32)
+        mean[0] = np.float32(50.0) + mean.max()  # (0 - mean) / std is smallest in column 0
+        packed = PackedFasta.from_sequences(seqs, pinned=True)
+        outs = []
+        for speculative in (True, False):
+            eng = CountEngine(k, "Log2.post")
+            eng.speculative = speculative
+            dpk = eng.upload(packed)
+            out, _, _ = eng.run(dpk, DeviceVector.from_host(mean, 4 ** k), DeviceVector.from_host(std, 4 ** k))
+            outs.append(out.cpu().numpy())
+            if speculative:
+                assert not eng.spec.held()
+        assert np.array_equal(outs[0], outs[1])
+        exp, _, _ = c_oracle.normalise(raw, mean, std, "Log2.post")
+        assert np.allclose(outs[0], exp, rtol=0, atol=TOL)
+        assert float(outs[0].min()) == 0.0  # the true minimum maps to log2(0 + 1)
+
+
+def test_speculative_post_record_ranges():
+    """Counting record sub-ranges with the speculated shift (the streamed get_counts() does) gives the same bits
+    as one launch over all records."""
+    seqs = synth.seq_strings(700, seed=21, stress=True, lo=40, hi=3000)
+    k = 6
+    seqs = [s for s in seqs if len(s) != k - 1]
+    raw = c_oracle.raw_counts(seqs, k)
+    mean = raw.mean(axis=0).astype(np.float32)
+    std = (raw.std(axis=0) + 0.125).astype(np.float32)
+    packed = PackedFasta.from_sequences(seqs, pinned=True)
+    eng = CountEngine(k, "Log2.post")
+    dpk = eng.upload(packed)
+    mv, sv = DeviceVector.from_host(mean, 4 ** k), DeviceVector.from_host(std, 4 ** k)
+    whole, _, _ = eng.run(dpk, mv, sv)
+    from seekr_b200.kmer_counts import PostSpec
+    spec = PostSpec(eng, mv, sv)
+    parts = device.zeros((len(seqs), 4 ** k), whole.dtype)
+    cuts = [0, 1, 9, 200, 201, 513, len(seqs)]
+    for a, b in zip(cuts, cuts[1:]):
+        eng.count(dpk, parts, mv, sv, spec=spec, rows=(a, b))
+    assert spec.held()
+    assert np.array_equal(parts.cpu().numpy(), whole.cpu().numpy())
+
+
+def test_accurate_column_statistics():
+    """mean=True / std=True from the column sums the count kernel accumulates (one pass, binary64 finish): closer to
+    the exact statistics than the reference's sequential fp32 sums, and the normalised matrix inside the parity band."""
+    seqs = synth.seq_strings(3000, seed=31, lo=300, hi=6000)
+    k = 6
+    raw = c_oracle.raw_counts(seqs, k)
+    exact_mean = raw.astype(np.float64).mean(axis=0)
+    exact_std = raw.astype(np.float64).std(axis=0)
+    ref_z, ref_mean, ref_std = c_oracle.normalise(raw, True, True, "Log2.post")
+    packed = PackedFasta.from_sequences(seqs, pinned=True)
+    eng = CountEngine(k, "Log2.post")
+    eng.accurate_stats = True
+    dpk = eng.upload(packed)
+    out, mean_vec, std_vec = eng.run(dpk, True, True)
+    got_mean, got_std = mean_vec.t.cpu().numpy(), std_vec.t.cpu().numpy()
+    err_mean, err_std = np.abs(got_mean - exact_mean).max(), np.abs(got_std - exact_std).max()
+    assert err_mean <= max(np.abs(ref_mean - exact_mean).max(), 1e-7)
+    assert err_std <= max(np.abs(ref_std - exact_std).max(), 1e-7)
+    assert np.allclose(got_mean, exact_mean, rtol=1e-6, atol=1e-7) and np.allclose(got_std, exact_std, rtol=1e-6, atol=1e-7)
+    # the matrix against the exact (binary64) normalisation: the reference's own matrix is further from it, because
+    # its sequential fp32 column sums are (that distance is what "accurate" buys; printed for the record)
+    z64 = (raw.astype(np.float64) - exact_mean) / exact_std
+    exact_z = np.log2(z64 + abs(z64.min()) + 1.0)
+    got = out.cpu().numpy()
+    print("accurate stats: max |ours - exact| %.2e, max |reference - exact| %.2e, max |ours - reference| %.2e"
+          % (np.abs(got - exact_z).max(), np.abs(ref_z - exact_z).max(), np.abs(got - ref_z).max()))
+    assert np.abs(got - exact_z).max() < TOL
+    assert np.abs(got - exact_z).max() <= np.abs(ref_z - exact_z).max() + 1e-6
+    # vectors only (seekr_norm_vectors): the same vectors up to the order in which the CTAs' partial sums meet
+    # (records are dealt to CTAs dynamically and the partials are added with atomics: the last bit may differ)
+    eng2 = CountEngine(k, "Log2.post")
+    eng2.accurate_stats = True
+    _, m2, s2 = eng2.run(dpk, True, True, vectors_only=True)
+    assert np.allclose(m2.t.cpu().numpy(), got_mean, rtol=1e-6, atol=0) and np.allclose(s2.t.cpu().numpy(), got_std, rtol=1e-6, atol=0)
+
+
+def test_log2_post_accuracy():
+    """The Log2.post tail uses the hardware log2 (MUFU.LG2; argument >= 1): its distance from the exact value stays
+    far inside the 1e-5 band over the range z-scores of count data can reach."""
+    import torch
+
+    x = np.concatenate([np.linspace(0.0, 63.0, 1 << 20), np.linspace(63.0, 65535.0, 1 << 20),
+                        np.random.default_rng(3).random(1 << 20) * 8.0]).astype(np.float32)
+    pad = (-x.size) % 4096
+    x = np.concatenate([x, np.zeros(pad, dtype=np.float32)]).reshape(-1, 4096)
+    eng = CountEngine(6, "Log2.post")
+    a = device.to_device(x)
+    eng.min_scan(a)                       # minimum 0 -> shift 0
+    eng.post_log2(a)
+    exact = np.log2(x.astype(np.float64) + 1.0)
+    err = np.abs(a.cpu().numpy().astype(np.float64) - exact)
+    small = x < 63.0
+    print("log2_post: max |err| %.3e for x+1 in [1, 64), %.3e up to 65536" % (err[small].max(), err.max()))
+    assert err[small].max() < 1e-6 and err.max() < 4e-6
+    torch.cuda.synchronize()
 
 
 def test_badly_behaved_vectors_take_the_fused_path(capsys):
@@ -544,3 +655,83 @@ def test_norm_vectors_fast_path_equals_get_counts(mode, tmp_path, capsys):
     warned_fast = "np.nan" in capsys.readouterr().out
     assert warned_full and warned_fast
     assert np.array_equal(a.std, b.std) and np.array_equal(a.mean, b.mean)
+
+
+@pytest.mark.parametrize("mode", ["Log2.post", "Log2.pre", "Log2.none"])
+def test_streamed_get_counts_equals_staged(mode, tmp_path):
+    """get_counts() from a FASTA file streams pack -> H2D -> count -> D2H chunk by chunk; the bits are those of the
+    staged engine path, through the pinned destination, the pageable one (pinned ring) and with ragged chunks."""
+    path = str(tmp_path / "s.fa")
+    synth.write_fasta(path, 1500, seed=77, stress=True, lo=30, hi=5000)
+    k = 6
+    seqs = [s for s in synth.seq_strings(1500, seed=77, stress=True, lo=30, hi=5000)]
+    raw = c_oracle.raw_counts(seqs, k)
+    mean = raw.mean(axis=0).astype(np.float32)
+    std = (raw.std(axis=0) + 0.125).astype(np.float32)
+    # staged reference result
+    packed = PackedFasta.from_file(path, pinned=True)
+    eng = CountEngine(k, mode)
+    staged, _, _ = eng.run(eng.upload(packed), DeviceVector.from_host(mean, 4 ** k), DeviceVector.from_host(std, 4 ** k))
+    staged = staged.cpu().numpy()
+    exp, _, _ = c_oracle.normalise(raw, mean, std, mode)
+    assert np.allclose(staged, exp, rtol=0, atol=TOL)
+    for pinned_result in (False, True):
+        device._cold_results = 0 if not pinned_result else 1
+        c = BasicCounter(path, k=k, mean=mean, std=std, log2=mode, silent=True)
+        c.get_counts()
+        assert np.array_equal(c.counts, staged), (mode, pinned_result)
+        assert np.array_equal(c.counts_device.cpu().numpy(), staged)
+    # explicit small chunks and the device-only form
+    packed = PackedFasta.from_file(path, pinned=True, background=True)
+    eng = CountEngine(k, mode)
+    got = eng.run_streamed(packed, DeviceVector.from_host(mean, 4 ** k), DeviceVector.from_host(std, 4 ** k), want_host=False)
+    assert got is not None and got[3] is None
+    assert np.array_equal(got[0].cpu().numpy(), staged)
+    # no vectors at all: Log2.post has no supplied vector to speculate on and takes the staged path
+    c = BasicCounter(path, k=k, mean=False, std=False, log2=mode, silent=True)
+    c.get_counts()
+    exp0, _, _ = c_oracle.normalise(raw, False, False, mode)
+    assert np.allclose(c.counts, exp0, rtol=0, atol=TOL)
+
+
+def test_full_size_log2_post_against_the_oracle():
+    """BASELINE configs[1] size: 50 000 transcripts, k = 6, supplied vectors, Log2.post in one pass (speculated shift);
+    a 5 000-row sample against the C restatement of the reference, the shift against the matrix's true minimum."""
+    import ctypes
+
+    import torch
+
+    m, k = 50000, 6
+    letters, offs = synth.sequences_bytes(m, seed=50000)
+    lut = np.full(256, 255, dtype=np.uint8)
+    for i, ch in enumerate("AGTC"):
+        lut[ord(ch)] = i
+    lib = _lib.load()
+    out = ctypes.c_void_p()
+    _lib.check(lib.skr_pack_sequences(ctypes.c_void_p(letters.ctypes.data), ctypes.c_void_p(offs.ctypes.data), m,
+                                      ctypes.c_void_p(lut.ctypes.data), 0, 1, ctypes.byref(out)))
+    packed = PackedFasta(out, None)
+    rows = np.sort(np.random.default_rng(2).choice(m, size=5000, replace=False))
+    sub_offs = np.zeros(rows.size + 1, dtype=np.int64)
+    np.cumsum(offs[rows + 1] - offs[rows], out=sub_offs[1:])
+    sub = np.concatenate([letters[offs[i]:offs[i + 1]] for i in rows])
+    raw = c_oracle.raw_counts(None, k, letters=sub, offs=sub_offs)
+    # vectors of the whole set (device, order-exact), taken through the host like seekr_kmer_counts -mv -sv does
+    eng = CountEngine(k, "Log2.post")
+    dpk = eng.upload(packed)
+    _, mv, sv = eng.run(dpk, True, True, vectors_only=True)
+    mean, std = mv.t.cpu().numpy(), sv.t.cpu().numpy()
+    dev, _, _ = eng.run(dpk, DeviceVector.from_host(mean, 4 ** k), DeviceVector.from_host(std, 4 ** k))
+    assert eng.spec.held()
+    assert float(dev.min().item()) == 0.0           # the true minimum lands on log2(0 + 1): the speculated shift is the true one
+    z, _, _ = c_oracle.normalise(raw.copy(), mean, std, "Log2.none")
+    shift = np.abs(((np.float32(0) - mean) / std).astype(np.float32).min())
+    exp = np.log2(((z + shift).astype(np.float32) + np.float32(1)).astype(np.float32))
+    got = dev[torch.from_numpy(rows).cuda()].cpu().numpy()
+    err = np.abs(got.astype(np.float64) - exp.astype(np.float64)).max()
+    assert err < TOL, err
+    # and through the staged two-pass route: same bits
+    eng2 = CountEngine(k, "Log2.post")
+    eng2.speculative = False
+    dev2, _, _ = eng2.run(dpk, DeviceVector.from_host(mean, 4 ** k), DeviceVector.from_host(std, 4 ** k))
+    assert torch.equal(dev, dev2)

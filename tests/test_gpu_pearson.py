@@ -251,3 +251,70 @@ def test_run_pearson_console_reads_csv_through_the_library(tmp_path, monkeypatch
     assert open(out_lib).read() == open(out_pandas).read()
     exp = po.pearson_f64(pd.read_csv(fa, index_col=0).values, pd.read_csv(fb, index_col=0).values)
     assert np.abs(pd.read_csv(out_lib, index_col=0).values - exp).max() < TOL
+
+
+# ---- the margin to the 1e-5 bar on the inputs that stress it, as assertions -------------------------------------
+
+@pytest.mark.parametrize("K", [4096, 16384, 65536])
+@pytest.mark.parametrize("lam", [0.8, 0.05, 0.01])
+def test_pearson_sparse_rows_stay_inside_the_bar(K, lam):
+    """Sparse count-like rows (a few large z-scores among thousands of small ones) are the worst case of the split
+    fp16 / fp32-accumulate contraction (profiles/r01_pearson_error_sweep.txt); float32 and float64 inputs, the
+    diagonal (r of a row with itself = 1) included."""
+    rng = np.random.default_rng(K + int(lam * 100))
+    m = 192
+    x = (rng.poisson(lam, size=(m, K)) * rng.uniform(0.1, 3, size=(m, 1))).astype(np.float32)
+    x[:, 0] += 1e-3  # no constant rows
+    z = np.log2(x + 1.0).astype(np.float32) if lam > 0.5 else x
+    want = po.pearson_f64(z, z)
+    for arr in (z, z.astype(np.float64)):
+        got = pearson(arr, arr)
+        assert got.dtype == arr.dtype
+        err = np.abs(got - want)
+        assert err.max() < 8e-6, (K, lam, arr.dtype, err.max())
+        assert np.abs(np.diag(got) - 1).max() < 8e-6
+
+
+def test_pearson_full_size_sampled_pairs():
+    """BASELINE configs[1] size on the device: 50 000 x 50 000 x 4 096, self-vs-self (upper tiles + mirror) and a
+    query set against a different reference set (every tile); 100 000 sampled pairs of each against a binary64
+    evaluation, the whole diagonal against 1, and symmetry of the mirrored matrix on the sampled pairs."""
+    import torch
+
+    from seekr_b200 import pearson as skr_pearson
+
+    m, K = 50000, 4096
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    # count-like rows: Poisson(0.8) windows per bin, scaled per row, log2(x + 1)
+    lam = torch.full((1,), 0.8, device="cuda").expand(m, K)
+    a = torch.log2(torch.poisson(lam, generator=gen) * (0.2 + torch.rand((m, 1), device="cuda", generator=gen) * 3) + 1).float()
+    pa = skr_pearson.prepare(a, True)
+    out = skr_pearson.pearson_device(pa, pa)
+
+    def exact(x, y, ii, jj):
+        za, zb = x[ii].double(), y[jj].double()
+        za = (za - za.mean(dim=1, keepdim=True)) / za.std(dim=1, unbiased=False, keepdim=True)
+        zb = (zb - zb.mean(dim=1, keepdim=True)) / zb.std(dim=1, unbiased=False, keepdim=True)
+        return (za * zb).sum(dim=1) / K
+
+    worst = 0.0
+    for chunk in range(10):
+        ii = torch.randint(0, m, (10000,), device="cuda", generator=gen)
+        jj = torch.randint(0, m, (10000,), device="cuda", generator=gen)
+        err = (out[ii, jj].double() - exact(a, a, ii, jj)).abs().max().item()
+        worst = max(worst, err)
+        assert torch.equal(out[ii, jj], out[jj, ii])
+    assert worst < 5e-6, worst
+    assert (torch.diagonal(out) - 1).abs().max().item() < 5e-6
+    del out
+    torch.cuda.empty_cache()
+    # query != reference: a second set of rows, every tile computed
+    b = torch.log2(torch.poisson(lam, generator=gen) * (0.2 + torch.rand((m, 1), device="cuda", generator=gen) * 3) + 1).float()
+    pb = skr_pearson.prepare(b, True)
+    out = skr_pearson.pearson_device(pa, pb)
+    worst = 0.0
+    for chunk in range(10):
+        ii = torch.randint(0, m, (10000,), device="cuda", generator=gen)
+        jj = torch.randint(0, m, (10000,), device="cuda", generator=gen)
+        worst = max(worst, (out[ii, jj].double() - exact(a, b, ii, jj)).abs().max().item())
+    assert worst < 5e-6, worst

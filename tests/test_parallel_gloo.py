@@ -92,6 +92,32 @@ def _worker(rank, world, port, a, out):
         arrmean = chain.col_stat(eng, 1, shard, Vec(mean), None, "mean")
         std = chain.col_stat(eng, 2, shard, Vec(mean), arrmean, "std")
         out[rank] = (mean.numpy().copy(), std.numpy().copy())
+        # ---- the reducer pieces of the one-pass routes (CPU tensors take the library collectives) -----------
+        red = parallel.AllReduceStats()
+        # (zero_col, zero_seen) of the speculative Log2.post: MIN of the identical column, OR of the flags
+        class Cell:
+            pass
+
+        eng2 = Cell()
+        eng2.min_cell = Cell()
+        eng2.min_cell.t = torch.tensor([0, 0], dtype=torch.int32)
+        eng2.stream = None
+        spec = Cell()
+        spec.cell = torch.tensor([17, 1 if rank == 1 else 0], dtype=torch.int32)
+        red.flag_or(eng2, spec)
+        assert spec.cell.tolist() == [17, 1]
+        spec.cell = torch.tensor([17, 0], dtype=torch.int32)
+        red.flag_or(eng2, spec)
+        assert spec.cell.tolist() == [17, 0]
+        # the single exchange of the accurate column statistics
+        sums = torch.tensor([[1.0 + rank, 2.0], [0.5, 4.0 * rank]], dtype=torch.float64)
+        red.sum_allreduce(sums)
+        assert sums.tolist() == [[3.0, 4.0], [1.0, 4.0]]
+        # row totals: asked for on every call unless the caller states them
+        assert red.total_rows(10 + rank, torch.device("cpu")) == 21
+        assert red.total_rows(5, torch.device("cpu")) == 10
+        red.set_total_rows(77)
+        assert red.total_rows(5, torch.device("cpu")) == 77
     finally:
         dist.destroy_process_group()
 

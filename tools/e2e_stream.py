@@ -1,0 +1,45 @@
+"""End-to-end time of BasicCounter(fasta, mean, std, Log2.post).get_counts(): streamed against staged (dev tool)."""
+import os, sys, time, tempfile
+import numpy as np
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+t_import = time.perf_counter()
+from seekr_b200 import device, synth
+from seekr_b200.fasta_reader import PackedFasta
+from seekr_b200.kmer_counts import BasicCounter, CountEngine, DeviceVector
+
+m = int(sys.argv[1]) if len(sys.argv) > 1 else 50000
+d = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+path = os.path.join(d, "s.fa")
+nbytes = synth.write_fasta(path, m, seed=50000)
+rng = np.random.default_rng(1)
+mean = (rng.random(4096) * 0.3 + 0.1).astype(np.float32)
+std = (rng.random(4096) * 0.3 + 0.2).astype(np.float32)
+torch.cuda.init(); torch.cuda.synchronize()
+print("host cores", os.cpu_count(), " fasta %.0f MB" % (nbytes / 1e6))
+prev = None
+for it in range(7):
+    t0 = time.perf_counter()
+    c = BasicCounter(path, k=6, mean=mean, std=std, log2="Log2.post", silent=True)
+    t1 = time.perf_counter()
+    c.get_counts()
+    t2 = time.perf_counter()
+    kind = "pinned" if device._cold_results and it >= 1 else "pageable"
+    print("iter %d: ctor (scan) %.1f ms  get_counts %.1f ms  total %.1f ms = %.2f M transcripts/s   [%s result]"
+          % (it, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t2 - t0) * 1e3, m / (t2 - t0) / 1e6, kind))
+    if prev is not None:
+        assert np.array_equal(prev, c.counts[:64])
+    prev = c.counts[:64].copy()
+    del c
+# staged path for comparison (what round 1 did): pack everything, upload, run, one D2H
+for it in range(3):
+    t0 = time.perf_counter()
+    packed = PackedFasta.from_file(path, pinned=True)
+    eng = CountEngine(6, "Log2.post")
+    out, _, _ = eng.run(eng.upload(packed), DeviceVector.from_host(mean, 4096), DeviceVector.from_host(std, 4096))
+    host = device.to_host(out)
+    t1 = time.perf_counter()
+    print("staged %d: %.1f ms = %.2f M transcripts/s" % (it, (t1 - t0) * 1e3, m / (t1 - t0) / 1e6))
+    assert np.array_equal(host[:64], prev)
+    del host, out
+os.remove(path); os.rmdir(d)

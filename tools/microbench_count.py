@@ -99,6 +99,16 @@ def main():
         eng.min_cell.reset()
         ms, mn = timeit(lambda: eng.count(dpk, out, mean, std, post=True), flush)
         report("count fused -mean /std +post", ms, mn, in_bytes + row_bytes)
+        from seekr_b200.kmer_counts import PostSpec
+        spec = PostSpec(eng, mean, std)
+        ms, mn = timeit(lambda: eng.count(dpk, out, mean, std, spec=spec), flush)
+        report("count + speculative Log2.post", ms, mn, in_bytes + row_bytes)
+        if k == 6:
+            sums = torch.zeros((2, cols), dtype=torch.float64, device="cuda")
+            ms, mn = timeit(lambda: eng.count(dpk, out, colsums=(sums[0], sums[1])), flush)
+            report("count raw + column sums", ms, mn, in_bytes + row_bytes)
+            ms, mn = timeit(lambda: eng.count(dpk, out, colmin=colmin, colsums=(sums[0], sums[1])), flush)
+            report("count raw + sums + col minima", ms, mn, in_bytes + row_bytes)
         if args.only_count:
             continue
         eng.min_cell.reset()
@@ -118,12 +128,28 @@ def main():
         def full():
             eng2.run(dpk, mean, std, out=out)
         ms, mn = timeit(full, flush)
-        report("vectors + Log2.post (2 passes)", ms, mn, 2 * in_bytes + row_bytes)
+        report("vectors + Log2.post (engine.run)", ms, mn, in_bytes + row_bytes)
 
         def full_self():
             eng2.run(dpk, True, True, out=out)
         ms, mn = timeit(full_self, flush)
         report("self-normalised Log2.post", ms, mn, in_bytes + 8 * row_bytes)
+        eng2.speculative = False
+        ms, mn = timeit(full, flush)
+        report("vectors + Log2.post, no speculation", ms, mn, 2 * in_bytes + 3 * row_bytes)
+        eng2.speculative = True
+        if k == 6:
+            eng2.accurate_stats = True
+            ms, mn = timeit(full_self, flush)
+            report("self-normalised, accurate stats", ms, mn, in_bytes + 3 * row_bytes)
+
+            def vec_only():
+                eng2.run(dpk, True, True, out=out, vectors_only=True)
+            ms, mn = timeit(vec_only, flush)
+            report("norm_vectors, accurate stats", ms, mn, in_bytes + row_bytes)
+            eng2.accurate_stats = False
+            ms, mn = timeit(vec_only, flush)
+            report("norm_vectors, order-exact", ms, mn, in_bytes + 4 * row_bytes)
         del out, dpk
         torch.cuda.empty_cache()
 
