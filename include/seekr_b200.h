@@ -130,14 +130,16 @@ int skr_count(const uint32_t* d_codes, const uint32_t* d_mask, const uint64_t* d
  * count value x >= 0, so the matrix-wide minimum is min_j fl(fl(0 - mean_j) / std_j) whenever the arg-min column j*
  * holds a zero count in some record -- which any realistic input does.  skr_post_spec derives that shift and j*
  * from the vectors alone (identical on every rank of a sharded run: no collective before counting);
- * skr_count_ex applies the Log2.post tail with it in its epilogue and sets zero_seen when it meets a zero count
- * in column j*.  The fallback launches (count with a running minimum, skr_post_log2_skip) are enqueued behind
- * it with d_skip = &zero_seen: they return at once when the speculation held, and redo the matrix the
- * two-pass way when it did not -- the choice is made on the device, the host never waits. */
+ * skr_count_ex applies the Log2.post tail with it in its epilogue and writes the run's epoch (spec_epoch, a
+ * non-zero number the caller changes from run to run, so the cell -- shift and j* depend on the vectors only --
+ * is set up once and never reset) into zero_seen when it meets a zero count in column j*.  The fallback launches
+ * (count with a running minimum, skr_post_log2_skip) are enqueued behind it with d_skip = &zero_seen and
+ * skip_value = that epoch: they return at once when the speculation held, and redo the matrix the two-pass way
+ * when it did not -- the choice is made on the device, the host never waits. */
 typedef struct {
     SkrMinCell shift;   /* the speculated matrix minimum, in the form the Log2.post tail reads (d_post) */
     int32_t zero_col;   /* j*; -1 when there is nothing to speculate on */
-    uint32_t zero_seen; /* set by the count kernels once a record with a zero count in column j* was seen */
+    uint32_t zero_seen; /* epoch of the last run in which a record with a zero count in column j* was seen */
 } SkrPostSpec;
 int skr_post_spec(const void* d_mean, const void* d_std, int vec_is_f64, int64_t cols, SkrPostSpec* d_spec, void* stream);
 
@@ -151,8 +153,11 @@ int skr_post_spec(const void* d_mean, const void* d_std, int vec_is_f64, int64_t
  *              fp32 mean / std vectors (binary64: mean = S1/rows, var = S2/rows - mean^2).  Closer to the exact
  *              value than numpy's sequential fp32 sums, hence not bit-identical to the reference
  *              (skr_col_pass is the order-exact route); one exchange of 2 * 4^k doubles when sharded
- *   d_spec     speculative Log2.post (above): d_post must point at d_spec->shift
- *   d_skip     the launch returns at once when *d_skip != 0 */
+ *   d_spec     speculative Log2.post (above): d_post must point at d_spec->shift; spec_epoch (0 = 1) is what the
+ *              kernel writes into d_spec->zero_seen
+ *   d_skip     the launch returns at once when *d_skip == skip_value (0 = 1)
+ *   d_min_reset  a minimum cell reset by the launch's first thread (the cell a launch BEHIND this one tracks:
+ *              saves the separate skr_min_reset launch of the fallback route) */
 typedef struct {
     const uint32_t* d_codes;
     const uint32_t* d_mask;
@@ -175,13 +180,19 @@ typedef struct {
     double* d_colsq;
     SkrPostSpec* d_spec;
     const uint32_t* d_skip;
+    uint32_t max_length; /* longest record of this launch if the caller knows it (0 = unknown): lets k <= 6 skip the
+                            launch that drains the list of records too long for the batch / team kernels */
+    uint32_t skip_value;
+    uint32_t spec_epoch;
+    uint32_t reserved;
+    SkrMinCell* d_min_reset;
 } SkrCountArgs;
 int skr_count_ex(const SkrCountArgs* args, void* stream);
 int skr_colstat_finish(const double* d_colsum, const double* d_colsq, int64_t cols, int64_t total_rows, float* d_mean,
                        float* d_std, int* d_flags /* [2]: mean, std; bit 0 not finite, bit 1 not positive */, void* stream);
-/* skr_post_log2 that returns at once when *d_skip != 0 */
+/* skr_post_log2 that returns at once when *d_skip == skip_value (0 = 1) */
 int skr_post_log2_skip(float* d_a, int64_t m, int64_t cols, int64_t ld, const SkrMinCell* d_min, const uint32_t* d_skip,
-                       void* stream);
+                       uint32_t skip_value, void* stream);
 
 /* Streamed get_counts() (replaces the read-everything / count-everything / copy-everything sequence of
  * fasta_reader.py:41-63 + kmer_counts.py:196-200 when rows are independent once the vectors are known):
@@ -383,11 +394,13 @@ int skr_peer_close(void* d_ptr);
 int skr_peer_free(void* d_ptr);
 int skr_min_exchange(SkrMinCell* d_cell, void* const* d_peers, int world, int rank, uint64_t epoch, int* d_err,
                      void* stream);
-/* the same, but the launch returns at once when *d_skip != 0 (d_skip may be NULL); every rank must hold the same
- * value there -- the speculative Log2.post route exchanges its flag first.  The spin limit of both exchanges is
- * 60 s, or SEEKR_B200_PEER_TIMEOUT_S. */
+/* the same, but the launch returns at once when *d_skip == skip_value (d_skip may be NULL; 0 = 1); every rank must
+ * hold the same value there -- the speculative Log2.post route exchanges its flag first.  flag_value != 0: the
+ * cell's second word is an epoch flag, set when it equals flag_value, and the OR over the ranks comes back as
+ * flag_value / 0 (SkrPostSpec.zero_seen seen as a cell together with zero_col).  The spin limit of both exchanges
+ * is 60 s, or SEEKR_B200_PEER_TIMEOUT_S. */
 int skr_min_exchange_skip(SkrMinCell* d_cell, void* const* d_peers, int world, int rank, uint64_t epoch,
-                          const uint32_t* d_skip, int* d_err, void* stream);
+                          const uint32_t* d_skip, uint32_t skip_value, uint32_t flag_value, int* d_err, void* stream);
 /* skr_colstat_exchange   all-reduce(sum) of the n binary64 column partials of skr_col_partial_f64 over the ranks,
  *                      fused with skr_col_finish_f64 (divide by the total row count, optional sqrt, fp32, quality
  *                      flag) in ONE kernel: P2P stores of the partials into every peer, an epoch flag per rank, a

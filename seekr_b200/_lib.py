@@ -43,7 +43,8 @@ class CountArgs(ctypes.Structure):
         ("vec_is_f64", ctypes.c_int32), ("out_is_f64", ctypes.c_int32),
         ("d_out", _vp), ("ld_out", _i64),
         ("d_min", _vp), ("d_post", _vp), ("d_colmin", _vp), ("d_colsum", _vp), ("d_colsq", _vp),
-        ("d_spec", _vp), ("d_skip", _vp),
+        ("d_spec", _vp), ("d_skip", _vp), ("max_length", ctypes.c_uint32), ("skip_value", ctypes.c_uint32),
+        ("spec_epoch", ctypes.c_uint32), ("reserved", ctypes.c_uint32), ("d_min_reset", _vp),
     ]
 
 
@@ -86,7 +87,7 @@ SIGNATURES = {
     "skr_count_ex": (_int, [ctypes.POINTER(CountArgs), _vp]),
     "skr_post_spec": (_int, [_vp, _vp, _int, _i64, _vp, _vp]),
     "skr_colstat_finish": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
-    "skr_post_log2_skip": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "skr_post_log2_skip": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, ctypes.c_uint32, _vp]),
     "skr_colmin_reset": (_int, [_vp, _i64, _vp]),
     "skr_count_colmin": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _int, _vp, _i64, _vp, _vp]),
     "skr_colmin_scan": (_int, [_vp, _i64, _i64, _i64, _vp, _vp]),
@@ -122,7 +123,7 @@ SIGNATURES = {
     "skr_peer_close": (_int, [_vp]),
     "skr_peer_free": (_int, [_vp]),
     "skr_min_exchange": (_int, [_vp, _vp, _int, _int, ctypes.c_uint64, _vp, _vp]),
-    "skr_min_exchange_skip": (_int, [_vp, _vp, _int, _int, ctypes.c_uint64, _vp, _vp, _vp]),
+    "skr_min_exchange_skip": (_int, [_vp, _vp, _int, _int, ctypes.c_uint64, _vp, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp]),
     "skr_colstat_exchange_bytes": (_i64, [_int, _i64]),
     "skr_colstat_exchange": (_int, [_vp, _vp, _int, _int, ctypes.c_uint64, _i64, _i64, _i64, _int, _vp, _vp, _vp, _vp]),
     "skr_csv_write": (_int, [ctypes.c_char_p, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _int, _int]),

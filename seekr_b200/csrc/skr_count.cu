@@ -16,8 +16,9 @@
 #include <cmath>
 #include <cstddef>
 #include <cstdlib>
+#include <map>
 #include <mutex>
-#include <unordered_map>
+#include <utility>
 
 #include "skr_common.h"
 #include "skr_device.cuh"
@@ -61,7 +62,11 @@ struct CountParams {
     // speculative Log2.post (skr_post_spec): the shift in post_cell was derived from the vectors alone and is the
     // true matrix minimum iff some record has a zero count in column spec->zero_col; the kernel reports that
     SkrPostSpec* spec;
-    const uint32_t* skip_flag;    // the launch does nothing when *skip_flag != 0 (device-side choice of the route)
+    const uint32_t* skip_flag;    // the launch does nothing when *skip_flag == skip_value (device-side choice of the route)
+    uint32_t skip_value;
+    uint32_t spec_epoch;          // written to spec->zero_seen when a zero count is met in the arg-min column
+    SkrMinCell* min_reset;        // reset at the start of the launch (the cell the two-pass route behind it will track)
+    uint32_t max_length;          // longest record of this launch when the caller knows it (0 = unknown)
     // accurate column statistics (norm_vectors in one pass): per-column sum and sum of squares of the values
     // written, accumulated in fp32 per thread over its records and added here in binary64 at the end
     double* colsum;
@@ -270,7 +275,8 @@ __global__ void __launch_bounds__(CountCfg<K>::kThreads) count_kernel(const Coun
     __shared__ double s_tab64[sizeof(OutT) == 8 ? kTab : 1];
 
     const int tid = threadIdx.x;
-    if (p.skip_flag && *p.skip_flag) return;
+    if (p.skip_flag && *p.skip_flag == p.skip_value) return;
+    if (p.min_reset && blockIdx.x == 0 && threadIdx.x == 0) { p.min_reset->min_ordered = skr::ordered_encode(INFINITY); p.min_reset->nan_seen = 0; }
     float tmin = INFINITY;
     int tnan = 0;
     unsigned long long zero_seen = 0;
@@ -385,7 +391,7 @@ __global__ void __launch_bounds__(CountCfg<K>::kThreads) count_kernel(const Coun
         // the __syncthreads at the top of the loop separates these reads from the next zeroing
     }
 
-    if (zseen) p.spec->zero_seen = 1u;
+    if (zseen) p.spec->zero_seen = p.spec_epoch;
     if (p.min_cell) skr::min_commit<T>(tmin, tnan, s_wmin, s_wnan, p.min_cell);
     if (p.colmin && tid < Cfg::kBins / 4) colmin_flush<kSteps>(zero_seen, p.colmin, tid, T);
 }
@@ -423,7 +429,8 @@ __global__ void __launch_bounds__(WarpCfg<K>::kThreads, WarpCfg<K>::kMinCtas) co
     __shared__ float s_wmin[2];
     __shared__ int s_wnan[2];
     const int team = threadIdx.x / TT, lane = threadIdx.x % TT;  // lane: index inside the team
-    if (p.skip_flag && *p.skip_flag) return;
+    if (p.skip_flag && *p.skip_flag == p.skip_value) return;
+    if (p.min_reset && blockIdx.x == 0 && threadIdx.x == 0) { p.min_reset->min_ordered = skr::ordered_encode(INFINITY); p.min_reset->nan_seen = 0; }
     int zq = -1, ze = 0;  // speculative Log2.post: quad / element of the arg-min column (skr_post_spec)
     uint32_t zseen = 0;
     if (p.spec && p.spec->zero_col >= 0) { zq = p.spec->zero_col >> 2; ze = p.spec->zero_col & 3; }
@@ -527,7 +534,7 @@ __global__ void __launch_bounds__(WarpCfg<K>::kThreads, WarpCfg<K>::kMinCtas) co
         rec = share(mine_next);  // also separates this record's histogram reads from the next clearing
         if constexpr (TT == 32) __syncwarp();
     }
-    if (zseen) p.spec->zero_seen = 1u;
+    if (zseen) p.spec->zero_seen = p.spec_epoch;
     if (p.colmin && lane < Cfg::kBins / 4) colmin_flush<kSteps>(zero_seen, p.colmin, lane, TT);
     if (p.min_cell) {
         if constexpr (TT == 32) {
@@ -633,40 +640,34 @@ __device__ __forceinline__ void count_chunk_full(uint32_t hist_addr, uint64_t x)
 // current and of the next unit, the unit bookkeeping) are allocated apart from the epilogue's, which holds the
 // thread's slices of the mean / std / 1/std vectors; in one body the two sets together exceeded the 56 registers a
 // thread may have with 2 x 544 threads per SM, and the compiler spilled inside both hot loops.
-template <int K, int kB, int kW, bool kOverlap>
+template <int K, int kB, int kW>
 __device__ __noinline__ void count_phase(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ mask,
-                                         uint32_t mt_addr, uint32_t hist_addr, uint32_t ready_addr, int tid) {
+                                         uint32_t mt_addr, uint32_t hist_addr, int tid) {
     // mt_addr: shared-window address of the batch's BatchMeta (explicit ld.shared: a generic reference would make
     // every access a generic load in an out-of-line function)
     using Meta = BatchMeta<kB>;
     constexpr uint32_t kHistBytes = (1u << (2 * K)) * 2;
     constexpr uint32_t oPrefix = offsetof(Meta, prefix), oNwin = offsetof(Meta, nwin), oB0 = offsetof(Meta, b0);
-    // Unit order: the kB tail slots first (slot r = the ragged last unit of record r, possibly empty), then the
-    // whole units record after record.  A warp therefore leaves record r for good once the first unit of its
-    // next round lies beyond r's range, and says so on the record's mbarrier (kOverlap): the epilogue of the
-    // first records of a batch starts while the last ones are still being counted.
-    uint32_t pf[kB + 1];  // kB + whole units before record r: the unit index where record r's whole units start
-#pragma unroll
-    for (int i = 0; i <= kB; ++i) pf[i] = kB + lds_u32(mt_addr + oPrefix + 4 * i);
-    const uint32_t total = pf[kB];
-    const int lane = tid & 31;
+    const uint32_t whole = lds_u32(mt_addr + oPrefix + 4 * kB);
+    const uint32_t total = whole + kB;  // whole units first, then one tail slot per record
     auto locate = [&](uint32_t g, int& r, uint32_t& u) {
-        if (g < kB) {  // tail slot of record g: the unit after its whole units
-            r = (int)g;
-            u = (uint32_t)(lds_u64(mt_addr + oNwin + 8 * g) >> 5);
+        if (g >= whole) {  // tail slot of record g - whole: the unit after its whole units (may be empty)
+            r = (int)(g - whole);
+            u = (uint32_t)(lds_u64(mt_addr + oNwin + 8 * (uint32_t)r) >> 5);
             return;
         }
         r = 0;
-        uint32_t before = pf[0];
+        uint32_t before = 0;
 #pragma unroll
-        for (int i = 1; i < kB; ++i)
-            if (g >= pf[i]) { r = i; before = pf[i]; }
+        for (int i = 1; i < kB; ++i) {
+            const uint32_t pf = lds_u32(mt_addr + oPrefix + 4 * i);  // broadcast shared loads
+            if (g >= pf) { r = i; before = pf; }
+        }
         u = g - before;
     };
     uint32_t w0 = 0, w1 = 0, w2 = 0, m0 = 0, m1 = 0, u = 0;
     int r = 0;
-    uint32_t gbase = (uint32_t)(tid - lane);  // warp-uniform: the warp's units of this round are gbase .. gbase + 31
-    uint32_t g = gbase + lane;
+    uint32_t g = (uint32_t)tid;
     if (g < total) {
         locate(g, r, u);
         const unsigned long long b0 = lds_u64(mt_addr + oB0 + 8 * (uint32_t)r);
@@ -675,55 +676,34 @@ __device__ __noinline__ void count_phase(const uint32_t* __restrict__ codes, con
         w0 = __ldg(cw); w1 = __ldg(cw + 1); w2 = __ldg(cw + 2);
         m0 = __ldg(mw); m1 = __ldg(mw + 1);
     }
-    int arrived = 0;  // records [0, arrived) have this warp's arrival
-    for (; gbase < total; gbase += kW) {
-        if (g < total) {
-            const uint32_t gn = g + kW;
-            uint32_t n0 = 0, n1 = 0, n2 = 0, q0 = 0, q1 = 0, un = 0;
-            int rn = 0;
-            if (gn < total) {  // next unit's words are in flight while this one is counted
-                locate(gn, rn, un);
-                const unsigned long long b0 = lds_u64(mt_addr + oB0 + 8 * (uint32_t)rn);
-                const uint32_t* cw = codes + b0 * 4 + 2 * un;
-                const uint32_t* mw = mask + b0 * 2 + un;
-                n0 = __ldg(cw); n1 = __ldg(cw + 1); n2 = __ldg(cw + 2);
-                q0 = __ldg(mw); q1 = __ldg(mw + 1);
-            }
-            const uint32_t h = hist_addr + (uint32_t)r * kHistBytes;
-            const uint64_t m64 = ((uint64_t)m0 << 32) | m1;
-            if (g >= kB && (m64 >> (64 - (32 + K - 1))) == 0) {
-                count_chunk_full<K>(h, ((uint64_t)w0 << 32) | w1);
-                count_chunk_full<K>(h, ((uint64_t)w1 << 32) | w2);
-            } else {
-                // tail slot: nwin % 32 windows, 0 = nothing to do
-                const long long left = (long long)lds_u64(mt_addr + oNwin + 8 * (uint32_t)r) - (long long)u * 32;
-                if (left > 0)
-                    count_chunk<K, true>(h, ((uint64_t)w0 << 32) | w1, (uint32_t)(m64 >> (64 - (16 + K - 1))),
-                                         left < 16 ? (int)left : 16);
-                if (left > 16)
-                    count_chunk<K, true>(h, ((uint64_t)w1 << 32) | w2, (uint32_t)((m64 << 16) >> (64 - (16 + K - 1))),
-                                         left < 32 ? (int)(left - 16) : 16);
-            }
-            w0 = n0; w1 = n1; w2 = n2; m0 = q0; m1 = q1; u = un; r = rn; g = gn;
+    while (g < total) {
+        const uint32_t gn = g + kW;
+        uint32_t n0 = 0, n1 = 0, n2 = 0, q0 = 0, q1 = 0, un = 0;
+        int rn = 0;
+        if (gn < total) {  // next unit's words are in flight while this one is counted
+            locate(gn, rn, un);
+            const unsigned long long b0 = lds_u64(mt_addr + oB0 + 8 * (uint32_t)rn);
+            const uint32_t* cw = codes + b0 * 4 + 2 * un;
+            const uint32_t* mw = mask + b0 * 2 + un;
+            n0 = __ldg(cw); n1 = __ldg(cw + 1); n2 = __ldg(cw + 2);
+            q0 = __ldg(mw); q1 = __ldg(mw + 1);
         }
-        if constexpr (kOverlap) {
-            // records whose whole units end at or before the warp's next round are finished as far as this warp goes
-            __syncwarp();
-            const uint32_t next = gbase + kW;
-#pragma unroll
-            for (int i = 0; i < kB; ++i) {
-                if (i >= arrived && pf[i + 1] <= next) {
-                    if (lane == 0) skr::mbar_arrive_addr(ready_addr + 8 * i);
-                    arrived = i + 1;
-                }
-            }
+        const uint32_t h = hist_addr + (uint32_t)r * kHistBytes;
+        const uint64_t m64 = ((uint64_t)m0 << 32) | m1;
+        if (g < whole && (m64 >> (64 - (32 + K - 1))) == 0) {
+            count_chunk_full<K>(h, ((uint64_t)w0 << 32) | w1);
+            count_chunk_full<K>(h, ((uint64_t)w1 << 32) | w2);
+        } else {
+            // tail slot: nwin % 32 windows, 0 = nothing to do
+            const long long left = (long long)lds_u64(mt_addr + oNwin + 8 * (uint32_t)r) - (long long)u * 32;
+            if (left > 0)
+                count_chunk<K, true>(h, ((uint64_t)w0 << 32) | w1, (uint32_t)(m64 >> (64 - (16 + K - 1))),
+                                     left < 16 ? (int)left : 16);
+            if (left > 16)
+                count_chunk<K, true>(h, ((uint64_t)w1 << 32) | w2, (uint32_t)((m64 << 16) >> (64 - (16 + K - 1))),
+                                     left < 32 ? (int)(left - 16) : 16);
         }
-    }
-    if constexpr (kOverlap) {
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < kB; ++i)
-            if (i >= arrived && lane == 0) skr::mbar_arrive_addr(ready_addr + 8 * i);
+        w0 = n0; w1 = n1; w2 = n2; m0 = q0; m1 = q1; u = un; r = rn; g = gn;
     }
 }
 
@@ -735,7 +715,7 @@ __device__ __noinline__ void count_phase(const uint32_t* __restrict__ codes, con
 //   kBatchAny    everything decided at run time.
 enum { kBatchAny = 0, kBatchPlain = 1, kBatchFast = 2, kBatchPost = 3 };
 
-template <int K, bool kVecF64, int kMode, bool kMin, bool kColmin = false, bool kStats = false, bool kOverlap = true>
+template <int K, bool kVecF64, int kMode, bool kMin, bool kColmin = false, bool kStats = false>
 __global__ void __launch_bounds__(BatchCfg<K>::kThreads, 2) count_batch_kernel(const CountParams p) {
     using Cfg = BatchCfg<K>;
     constexpr int kB = Cfg::kB, kW = Cfg::kWorkers, kQ = Cfg::kQ;
@@ -744,15 +724,11 @@ __global__ void __launch_bounds__(BatchCfg<K>::kThreads, 2) count_batch_kernel(c
     static_assert(!kColmin || kMode == kBatchPlain, "kColmin: column minima of the plain values (kBatchAny decides at run time)");
     static_assert(!kStats || kMode == kBatchPlain, "kStats: column sums of the plain values");
     static_assert(!(kMin && kMode == kBatchPost), "the speculative Log2.post epilogue needs no running minimum");
-    if (p.skip_flag && *p.skip_flag) return;
+    if (p.skip_flag && *p.skip_flag == p.skip_value) return;
+    if (p.min_reset && blockIdx.x == 0 && threadIdx.x == 0) { p.min_reset->min_ordered = skr::ordered_encode(INFINITY); p.min_reset->nan_seen = 0; }
     extern __shared__ __align__(16) uint32_t smem_b[];
     __shared__ BatchMeta<kB> s_meta[2];
-    __shared__ __align__(8) uint64_t s_ready[kB];  // kOverlap: record r of the current batch is completely counted
     const int tid = threadIdx.x, lane = tid & 31;
-    if constexpr (kOverlap) {
-        if (tid < kB) skr::mbar_init(&s_ready[tid], Cfg::kCounters / 32);  // one arrival per counting warp and batch
-        skr::fence_mbar_init();
-    }
     constexpr bool worker = true;                 // every thread takes part in the epilogue
     const bool counter = tid < Cfg::kCounters;    // count phase: warps 0..14 count, warp 15 prepares the next batch
     const uint32_t raw_addr = skr::smem_u32(smem_b);
@@ -864,31 +840,25 @@ __global__ void __launch_bounds__(BatchCfg<K>::kThreads, 2) count_batch_kernel(c
         if (!counter) {
             produce((it + 1) & 1);
         } else {
-            count_phase<K, kB, Cfg::kCounters, kOverlap>(p.codes, p.mask, skr::smem_u32(&mt), hist_addr, skr::smem_u32(&s_ready[0]), tid);
+            count_phase<K, kB, Cfg::kCounters>(p.codes, p.mask, skr::smem_u32(&mt), hist_addr, tid);
         }
-        if constexpr (!kOverlap) __syncthreads();
+        __syncthreads();
         if (worker) {
             // ---- epilogue ----
             const int nrec = mt.nrec;
             for (int r = 0; r < nrec; ++r) {
-                if constexpr (kOverlap) skr::mbar_wait(&s_ready[r], (uint32_t)(it & 1));
                 if (!mt.store[r]) continue;
                 const uint32_t tab_addr = skr::smem_u32(&mt.tab[r][0]);
                 const float treg = lds_f32(tab_addr + (uint32_t)lane * 4);  // lane c holds the value of a bin seen c times
                 const uint32_t hrec = hist_addr + (uint32_t)r * Cfg::kHistBytes;
                 float* __restrict__ orow = reinterpret_cast<float*>(p.out) + (size_t)(mt.rec0 + r) * (size_t)p.ld_out;
                 if (zoff >= 0 && ((lds_u32(hrec + (uint32_t)zoff) >> zsh) & 0xFFFFu) == 0) zseen = 1;
-                // staged over the thread's quads so that their shared-memory loads, zeroing stores and table
-                // shuffles are in flight together (the asm wrappers are kept in program order by the compiler)
-                uint2 vq[kQ];
-#pragma unroll
-                for (int j = 0; j < kQ; ++j) vq[j] = lds_v2(hrec + (uint32_t)(tid + j * kW) * 8);
-#pragma unroll
-                for (int j = 0; j < kQ; ++j) sts_zero_v2(hrec + (uint32_t)(tid + j * kW) * 8);
 #pragma unroll
                 for (int j = 0; j < kQ; ++j) {
                     const int q = tid + j * kW;
-                    const uint2 v = vq[j];
+                    const uint32_t a = hrec + (uint32_t)q * 8;
+                    const uint2 v = lds_v2(a);
+                    sts_zero_v2(a);
                     float x[4];
                     // indexed shuffles take the source lane modulo 32; counts of kTab and more are fixed up below
                     x[0] = __shfl_sync(0xFFFFFFFFu, treg, (int)v.x);
@@ -980,7 +950,7 @@ __global__ void __launch_bounds__(BatchCfg<K>::kThreads, 2) count_batch_kernel(c
     }
 
     if (worker) {
-        if (zseen) p.spec->zero_seen = 1u;
+        if (zseen) p.spec->zero_seen = p.spec_epoch;
         if (kColmin || (kMode == kBatchAny && p.colmin)) {
 #pragma unroll
             for (int j = 0; j < kQ; ++j)
@@ -1015,10 +985,10 @@ __global__ void __launch_bounds__(BatchCfg<K>::kThreads, 2) count_batch_kernel(c
     }
 }
 
-template <int K, bool kVecF64, int kMode, bool kMin, bool kColmin = false, bool kStats = false, bool kOverlap = true>
+template <int K, bool kVecF64, int kMode, bool kMin, bool kColmin = false, bool kStats = false>
 int launch_batch(const CountParams& wp, int sms, cudaStream_t stream) {
     using B = BatchCfg<K>;
-    auto bkern = count_batch_kernel<K, kVecF64, kMode, kMin, kColmin, kStats, kOverlap>;
+    auto bkern = count_batch_kernel<K, kVecF64, kMode, kMin, kColmin, kStats>;
     SKR_CUDA_CHECK(cudaFuncSetAttribute(bkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B::kSmem));
     int bper_sm = 0;
     SKR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bper_sm, bkern, B::kThreads, B::kSmem));
@@ -1047,11 +1017,6 @@ int dispatch_batch(const CountParams& wp, int sms, cudaStream_t stream) {
                                           : launch_batch<K, false, kBatchPlain, false, true>(wp, sms, stream);
         if (plain) return mn ? launch_batch<K, false, kBatchPlain, true>(wp, sms, stream)
                              : launch_batch<K, false, kBatchPlain, false>(wp, sms, stream);
-        const char* env = getenv("SEEKR_B200_BATCH_OVERLAP");  // experiment knob: "0" = a CTA barrier between the phases
-        if (env && env[0] == '0') {
-            if (plain && !wp.colmin && !wp.colsum && !mn) return launch_batch<K, false, kBatchPlain, false, false, false, false>(wp, sms, stream);
-            if (post) return launch_batch<K, false, kBatchPost, false, false, false, false>(wp, sms, stream);
-        }
         if (fast) return mn ? launch_batch<K, false, kBatchFast, true>(wp, sms, stream)
                             : launch_batch<K, false, kBatchFast, false>(wp, sms, stream);
         if (post) return launch_batch<K, false, kBatchPost, false>(wp, sms, stream);
@@ -1071,13 +1036,17 @@ struct DeviceScratch {
     unsigned int* counters = nullptr;
     int next_counter = 0;
 };
-constexpr int kCounterRing = 1024;  // 4 counters per launch
+constexpr int kCounterRing = 1024;   // 4 counters per launch
+constexpr int kCounterBlock = 256;   // zeroed together, on the stream that is about to use them
 std::mutex g_scratch_mu;
-std::unordered_map<int, DeviceScratch> g_scratch;
+std::map<std::pair<int, cudaStream_t>, DeviceScratch> g_scratch;  // one ring per (device, stream)
 
-int next_counters(int dev, unsigned int** out) {
+// Four zeroed work counters for a launch on `stream`.  A ring belongs to one stream, so everything that touches it
+// is ordered by the stream: a block of 64 launches' worth of counters is cleared by ONE memset when the ring enters
+// it (its previous users are 192+ launches behind on the same stream), instead of one memset per launch.
+int next_counters(int dev, cudaStream_t stream, unsigned int** out) {
     std::lock_guard<std::mutex> lock(g_scratch_mu);
-    DeviceScratch& s = g_scratch[dev];
+    DeviceScratch& s = g_scratch[std::make_pair(dev, stream)];
     if (!s.counters) {
         SKR_CUDA_CHECK(cudaMalloc(&s.counters, kCounterRing * sizeof(unsigned int)));
         cudaMemPool_t pool;
@@ -1085,6 +1054,8 @@ int next_counters(int dev, unsigned int** out) {
         uint64_t keep = UINT64_MAX;
         SKR_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     }
+    if (s.next_counter % kCounterBlock == 0)
+        SKR_CUDA_CHECK(cudaMemsetAsync(s.counters + s.next_counter, 0, kCounterBlock * sizeof(unsigned int), stream));
     *out = s.counters + s.next_counter;
     s.next_counter = (s.next_counter + 4) % kCounterRing;
     return SKR_OK;
@@ -1106,11 +1077,12 @@ int launch_count(CountParams p, cudaStream_t stream) {
     constexpr bool kUseWarp = K <= 6 && sizeof(OutT) == 4;
     if (kUseWarp && p.m > 0xFFFFFFFFll) return skr::fail(SKR_ERR_ARG, "skr_count: more than 2^32 records");
     unsigned int* ctr = nullptr;
-    int rc = next_counters(dev, &ctr);
+    int rc = next_counters(dev, stream, &ctr);
     if (rc != SKR_OK) return rc;
-    SKR_CUDA_CHECK(cudaMemsetAsync(ctr, 0, 4 * sizeof(unsigned int), stream));
+    // no record is too long for the team / batch kernels (the caller knows the longest record): nothing to hand over
+    const bool no_long = kUseWarp && p.max_length > 0 && (long long)p.max_length - K + 1 <= kLongWin;
     uint32_t* long_list = nullptr;
-    if (kUseWarp) SKR_CUDA_CHECK(cudaMallocAsync(&long_list, (size_t)p.m * sizeof(uint32_t), stream));
+    if (kUseWarp && !no_long) SKR_CUDA_CHECK(cudaMallocAsync(&long_list, (size_t)p.m * sizeof(uint32_t), stream));
     long long grid = (long long)sms * per_sm;
     if constexpr (kUseWarp) {
         using W = WarpCfg<K>;
@@ -1141,6 +1113,7 @@ int launch_count(CountParams p, cudaStream_t stream) {
         }
         if (!batch) wkern<<<(unsigned)wgrid, W::kThreads, W::kSmem, stream>>>(wp);
         SKR_LAUNCH_CHECK();
+        if (no_long) return SKR_OK;
         // long records (rare): the CTA kernel reads the list length on the device
         p.work_counter = ctr + 2;
         p.long_list = long_list;
@@ -1218,10 +1191,10 @@ __device__ __forceinline__ float ew_apply_reg(float v, double m64, double s64, f
 template <int OP, bool kVecF64, bool kVec4>
 __global__ void __launch_bounds__(256) ew_kernel(float* a, long long m, long long cols, long long ld, const void* vec,
                                                  const void* vec2, const SkrMinCell* min_in, SkrMinCell* min_out,
-                                                 const uint32_t* skip) {
+                                                 const uint32_t* skip, uint32_t skip_value) {
     __shared__ float s_wmin[8];
     __shared__ int s_wnan[8];
-    if (skip && *skip) return;
+    if (skip && *skip == skip_value) return;
     float shift = 0.0f;
     if constexpr (OP == OP_POST || OP == OP_NORMPOST) {
         // np.abs(np.min(counts)): NaN anywhere makes the shift NaN, hence the whole matrix (kmer_counts.py:208)
@@ -1270,7 +1243,7 @@ __global__ void __launch_bounds__(256) ew_kernel(float* a, long long m, long lon
 template <int OP>
 int launch_ew(float* a, long long m, long long cols, long long ld, const void* vec, int vec_is_f64,
               const SkrMinCell* min_in, SkrMinCell* min_out, cudaStream_t stream, const void* vec2 = nullptr,
-              const uint32_t* skip = nullptr) {
+              const uint32_t* skip = nullptr, uint32_t skip_value = 1) {
     if (m <= 0 || cols <= 0) return SKR_OK;
     if (!a) return skr::fail(SKR_ERR_ARG, "null matrix");
     if (ld < cols) return skr::fail(SKR_ERR_ARG, "ld < cols");
@@ -1286,7 +1259,7 @@ int launch_ew(float* a, long long m, long long cols, long long ld, const void* v
     if (gx > 0x7FFFFFFFll) return skr::fail(SKR_ERR_ARG, "matrix too wide");
     dim3 grid((unsigned)gx, (unsigned)gy);
     auto go = [&](auto kern) {
-        kern<<<grid, 256, 0, stream>>>(a, m, cols, ld, vec, vec2, min_in, min_out, skip);
+        kern<<<grid, 256, 0, stream>>>(a, m, cols, ld, vec, vec2, min_in, min_out, skip, skip_value);
     };
     if (vec_is_f64) {
         if (vec4) go(ew_kernel<OP, true, true>); else go(ew_kernel<OP, true, false>);
@@ -1441,6 +1414,10 @@ extern "C" int skr_count_ex(const SkrCountArgs* a, void* stream) {
     p.no_store = a->d_out == nullptr;
     p.spec = a->d_spec;
     p.skip_flag = a->d_skip;
+    p.skip_value = a->skip_value ? a->skip_value : 1u;
+    p.spec_epoch = a->spec_epoch ? a->spec_epoch : 1u;
+    p.min_reset = a->d_min_reset;
+    p.max_length = a->max_length;
     p.colsum = a->d_colsum;
     p.colsq = a->d_colsq;
     cudaStream_t s = (cudaStream_t)stream;
@@ -1641,9 +1618,10 @@ extern "C" int skr_post_log2(float* d_a, int64_t m, int64_t cols, int64_t ld, co
 }
 
 extern "C" int skr_post_log2_skip(float* d_a, int64_t m, int64_t cols, int64_t ld, const SkrMinCell* d_min,
-                                  const uint32_t* d_skip, void* stream) {
+                                  const uint32_t* d_skip, uint32_t skip_value, void* stream) {
     if (!d_min) return skr::fail(SKR_ERR_ARG, "skr_post_log2_skip: null min cell");
-    return launch_ew<OP_POST>(d_a, m, cols, ld, nullptr, 0, d_min, nullptr, (cudaStream_t)stream, nullptr, d_skip);
+    return launch_ew<OP_POST>(d_a, m, cols, ld, nullptr, 0, d_min, nullptr, (cudaStream_t)stream, nullptr, d_skip,
+                              skip_value ? skip_value : 1u);
 }
 
 extern "C" int skr_sub_vec(float* d_a, int64_t m, int64_t cols, int64_t ld, const void* d_vec, int vec_is_f64,

@@ -325,6 +325,58 @@ SKR_AVX2 const char* for_each_line_avx2(const char* base, const char* from, cons
     return s;
 }
 
+// Line iteration with a fast lane for the bulk of a FASTA file: runs of "clean" sequence lines -- no '>' , no
+// whitespace other than the terminating '\n' (so nothing to strip, no '\r'), no blank line -- are consumed 32 bytes
+// at a time with three compares and a popcount, and reported once per run through clean(first_line_start,
+// bases, end_of_last_line); every other line goes through fn exactly as in for_each_line_avx2.  The effect on the
+// caller's state is the same as visiting the lines one by one (the per-line callback was the whole cost of the
+// scan: ~25 ns per 61-byte line).
+template <class Fn, class Clean>
+SKR_AVX2 const char* for_each_line_fast(const char* base, const char* from, const char* to, const char* end, Fn&& fn,
+                                        Clean&& clean) {
+    const char* s = from;
+    if (s > base) {
+        while (s < end) {
+            char prev = s[-1];
+            if (prev == '\n' || (prev == '\r' && *s != '\n')) break;
+            ++s;
+        }
+    }
+    const __m256i v_nl = _mm256_set1_epi8('\n'), v_gt = _mm256_set1_epi8('>');
+    const __m256i v_sp = _mm256_set1_epi8(0x20);
+    const char* lim = to < end ? to : end;
+    while (s < to && s < end) {
+        const char* p = s;
+        const char* last_nl = nullptr;
+        uint64_t nls = 0;
+        uint32_t carry = 1;  // s is a line start: a '\n' right here is a blank line
+        while (p + 32 <= lim) {
+            const __m256i v = _mm256_loadu_si256((const __m256i*)p);
+            const uint32_t nlm = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(v, v_nl));
+            // every byte <= 0x20 (all of str.strip's whitespace, and the other control characters for good measure)
+            const __m256i ws = _mm256_cmpeq_epi8(_mm256_min_epu8(v, v_sp), v);
+            const uint32_t spm = (uint32_t)_mm256_movemask_epi8(_mm256_or_si256(ws, _mm256_cmpeq_epi8(v, v_gt))) & ~nlm;
+            const uint32_t blank = nlm & ((nlm << 1) | carry);
+            if (spm | blank) break;
+            if (nlm) {
+                nls += (uint64_t)__builtin_popcount(nlm);
+                last_nl = p + (31 - __builtin_clz(nlm));
+            }
+            carry = nlm >> 31;
+            p += 32;
+        }
+        if (last_nl) {  // the complete clean lines s .. last_nl
+            if (!clean(s, (uint64_t)(last_nl - s) - (nls - 1), last_nl)) return nullptr;
+            s = last_nl + 1;
+            continue;
+        }
+        const char* nxt = for_each_line_avx2(base, s, s + 1, end, fn);  // exactly one line, the careful way
+        if (!nxt) return nullptr;
+        s = nxt;
+    }
+    return s;
+}
+
 inline void strip(const char*& a, const char*& b) {
     while (a < b && is_space((unsigned char)*a)) ++a;
     while (b > a && is_space((unsigned char)b[-1])) --b;
@@ -688,11 +740,25 @@ static int pack_fasta_buffer(const void* text_v, size_t nbytes, const uint8_t* l
             r.bases += (uint64_t)(lb - la);
             return true;
         };
-        const char* next = use_avx2 ? for_each_line_avx2(text, from, to, end, on_line)
-                                    : for_each_line(text, from, to, end, on_line);
+        auto on_clean = [&](const char* a, uint64_t nbases, const char* last_end) -> bool {
+            if (!in_record) {  // sequence lines of a record opened in an earlier chunk
+                if (t == 0) { R.first_line_not_header = true; return false; }
+                return true;
+            }
+            Rec& r = R.recs.back();
+            if (r.body_len == 0) r.body_off = (uint64_t)(a - text);
+            r.body_len = (uint64_t)(last_end - text) - r.body_off;
+            r.bases += nbases;
+            return true;
+        };
+        const bool fast = use_avx2 && !getenv("SKR_PACK_NO_FAST_SCAN");
+        const char* next = fast ? for_each_line_fast(text, from, to, end, on_line, on_clean)
+                                : (use_avx2 ? for_each_line_avx2(text, from, to, end, on_line)
+                                            : for_each_line(text, from, to, end, on_line));
         if (next && in_record && next < end) {
             beyond = true;
-            if (use_avx2) for_each_line_avx2(text, next, end, end, on_line);
+            if (fast) for_each_line_fast(text, next, end, end, on_line, on_clean);
+            else if (use_avx2) for_each_line_avx2(text, next, end, end, on_line);
             else for_each_line(text, next, end, end, on_line);
         }
     });

@@ -48,13 +48,17 @@ __device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long lon
 // peers[t]: address of rank t's exchange buffer as mapped into this process; layout [2 parities][world] words
 __global__ void min_exchange_kernel(SkrMinCell* cell, unsigned long long* const* peers, int world, int rank,
                                     unsigned long long epoch, int* err, unsigned long long kSpinLimitNs,
-                                    const uint32_t* skip) {
-    if (skip && *skip) return;  // the same value on every rank (callers exchange the flag first)
+                                    const uint32_t* skip, uint32_t skip_value, uint32_t flag_value) {
+    // skip: the same value on every rank (callers exchange the flag first).  flag_value != 0: the second word of
+    // the cell is a flag that counts as set when it EQUALS flag_value (the epoch scheme of the speculative
+    // Log2.post route), and the OR over the ranks is written back as flag_value / 0
+    if (skip && *skip == skip_value) return;
     const int lane = threadIdx.x;
     const unsigned long long parity = epoch & 1ull;
     unsigned long long mine = 0;
     if (lane < world) {
-        const unsigned long long word = (epoch << 33) | ((unsigned long long)(cell->nan_seen ? 1u : 0u) << 32) |
+        const uint32_t bit = flag_value ? (cell->nan_seen == flag_value ? 1u : 0u) : (cell->nan_seen ? 1u : 0u);
+        const unsigned long long word = (epoch << 33) | ((unsigned long long)bit << 32) |
                                         (unsigned long long)cell->min_ordered;
         st_sys_u64(peers[lane] + parity * world + rank, word);
         const unsigned long long* slot = peers[rank] + parity * world + lane;
@@ -78,7 +82,7 @@ __global__ void min_exchange_kernel(SkrMinCell* cell, unsigned long long* const*
     }
     if (lane == 0) {
         cell->min_ordered = mn;
-        cell->nan_seen = nan;
+        cell->nan_seen = flag_value ? (nan ? flag_value : 0u) : nan;
     }
 }
 
@@ -195,17 +199,18 @@ extern "C" int skr_peer_free(void* d_ptr) {
 
 extern "C" int skr_min_exchange(SkrMinCell* d_cell, void* const* d_peers, int world, int rank, uint64_t epoch, int* d_err,
                                 void* stream) {
-    return skr_min_exchange_skip(d_cell, d_peers, world, rank, epoch, nullptr, d_err, stream);
+    return skr_min_exchange_skip(d_cell, d_peers, world, rank, epoch, nullptr, 0, 0, d_err, stream);
 }
 
 extern "C" int skr_min_exchange_skip(SkrMinCell* d_cell, void* const* d_peers, int world, int rank, uint64_t epoch,
-                                     const uint32_t* d_skip, int* d_err, void* stream) {
+                                     const uint32_t* d_skip, uint32_t skip_value, uint32_t flag_value, int* d_err,
+                                     void* stream) {
     if (!d_cell || !d_peers || !d_err) return skr::fail(SKR_ERR_ARG, "skr_min_exchange: null argument");
     if (world < 1 || world > 32 || rank < 0 || rank >= world)
         return skr::fail(SKR_ERR_ARG, "skr_min_exchange: world must be 1..32 and 0 <= rank < world");
     if (epoch == 0 || epoch >= (1ull << 31)) return skr::fail(SKR_ERR_ARG, "skr_min_exchange: epoch must be 1 .. 2^31 - 1");
     min_exchange_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_cell, (unsigned long long* const*)d_peers, world, rank, epoch, d_err,
-                                                            spin_limit_ns(), d_skip);
+                                                            spin_limit_ns(), d_skip, skip_value ? skip_value : 1u, flag_value);
     SKR_LAUNCH_CHECK();
     return SKR_OK;
 }

@@ -67,6 +67,8 @@ class PackedFasta:
         self.off_mask = (lib.skr_packed_mask(handle) or 0) - base
         self.off_blk = (lib.skr_packed_block_offsets(handle) or 0) - base
         self.off_len = (lib.skr_packed_lengths(handle) or 0) - base
+        # the longest record (the record table is final even while a background packer still runs)
+        self.max_length = int(self.lengths.max()) if self.m else 0
 
     # -- construction ---------------------------------------------------------------------------
     @classmethod

@@ -128,21 +128,31 @@ class DeviceVector:
 
 
 class PostSpec:
-    """Device SkrPostSpec: the speculated Log2.post shift, its arg-min column and the "zero seen" flag."""
+    """Device SkrPostSpec: the speculated Log2.post shift, its arg-min column and the "zero seen" flag.
+
+    Shift and column depend on the vectors only, so the cell is set up once per vector pair (one tiny launch) and
+    reused; a run is identified by its epoch, which the count kernel writes into the flag word when it meets a zero
+    count in the arg-min column -- nothing is ever reset."""
 
     def __init__(self, engine, mean_vec, std_vec):
         torch = engine.torch
         self.t = device.empty(4, torch.int32)
-        self.flag = self.t[3:4]       # zero_seen: non-zero = the speculation held
+        self.flag = self.t[3:4]       # zero_seen: == epoch of the run when the speculation held
         self.cell = self.t[2:4]       # (zero_col, zero_seen) seen as a SkrMinCell: MIN / OR over ranks
+        self.epoch = 0
+        self.vectors = (mean_vec, std_vec)
         is_f64 = (mean_vec or std_vec).is_f64
         _lib.check(engine.lib.skr_post_spec(device.ptr(mean_vec.t if mean_vec else None),
                                             device.ptr(std_vec.t if std_vec else None), int(is_f64), engine.cols,
                                             device.ptr(self.t), device.stream_ptr(engine.stream)))
 
+    def next_epoch(self):
+        self.epoch = self.epoch % 0x7FFFFFFF + 1
+        return self.epoch
+
     def held(self):
-        """True when some record had a zero count in the arg-min column (synchronises)."""
-        return bool(int(self.flag.item()))
+        """True when some record of the last run had a zero count in the arg-min column (synchronises)."""
+        return int(self.flag.item()) == self.epoch
 
 
 class CountEngine:
@@ -185,11 +195,11 @@ class CountEngine:
         return DevicePacked(slab, packed)
 
     def count(self, dpk, out, mean=None, std=None, track_min=False, out_is_f64=False, post=False, spec=None, skip=None,
-              colmin=None, colsums=None, rows=None):
+              colmin=None, colsums=None, rows=None, reset_min=True):
         """skr_count_ex into ``out`` (m x cols).  mean/std: DeviceVector or None.  post=True applies the Log2.post
         tail in the same epilogue, using the minimum already held by ``self.min_cell``; ``spec`` (a PostSpec) does
-        the same with the speculated shift and lets the kernel report whether the speculation held; ``skip`` (device
-        uint32) turns the launch into a no-op when non-zero; ``colmin`` / ``colsums`` = (sum, sum of squares)
+        the same with the speculated shift and lets the kernel report whether the speculation held; ``skip`` (a
+        PostSpec) turns the launch into a no-op when that speculation held; ``colmin`` / ``colsums`` = (sum, sum of squares)
         collect column minima / binary64 column sums of the plain values; ``rows`` = (begin, end) counts a record
         sub-range into the same rows of ``out``."""
         vec_is_f64 = False
@@ -201,7 +211,7 @@ class CountEngine:
             if v is not None:
                 vec_is_f64 = v.is_f64
         log2_pre = 1 if self.log2 == "Log2.pre" else 0
-        if track_min:
+        if track_min and reset_min:
             self.min_cell.reset(self.stream)
         # exact 5-instruction division when the vectors are fp32 and of sane magnitude (host-known)
         rstd = None
@@ -221,10 +231,13 @@ class CountEngine:
             a.ld_out = out.stride(0)
         a.d_min = device.ptr(self.min_cell.t if track_min else None)
         if spec is not None:
-            a.d_post, a.d_spec = device.ptr(spec.t), device.ptr(spec.t)
+            a.d_post, a.d_spec, a.spec_epoch = device.ptr(spec.t), device.ptr(spec.t), spec.epoch
+            a.d_min_reset = device.ptr(self.min_cell.t)  # tracked by the two-pass route behind the speculation
         elif post:
             a.d_post = device.ptr(self.min_cell.t)
-        a.d_skip = device.ptr(skip)
+        a.d_skip = device.ptr(skip.flag if skip is not None else None)
+        a.skip_value = skip.epoch if skip is not None else 0
+        a.max_length = int(getattr(dpk, "max_length", 0))
         a.d_colmin = device.ptr(colmin)
         if colsums is not None:
             a.d_colsum, a.d_colsq = device.ptr(colsums[0]), device.ptr(colsums[1])
@@ -317,7 +330,16 @@ class CountEngine:
     def post_log2(self, a, skip=None):
         m, cols = a.shape
         _lib.check(self.lib.skr_post_log2_skip(device.ptr(a), m, cols, a.stride(0), device.ptr(self.min_cell.t),
-                                               device.ptr(skip), device.stream_ptr(self.stream)))
+                                               device.ptr(skip.flag if skip is not None else None),
+                                               skip.epoch if skip is not None else 0, device.stream_ptr(self.stream)))
+
+    def spec_for(self, mean_vec, std_vec):
+        """The engine's speculation cell for this vector pair (set up on first use), with a fresh epoch."""
+        spec = self.spec
+        if spec is None or spec.vectors[0] is not mean_vec or spec.vectors[1] is not std_vec:
+            spec = self.spec = PostSpec(self, mean_vec, std_vec)
+        spec.next_epoch()
+        return spec
 
     def log2_norm(self, a):
         m, cols = a.shape
@@ -374,14 +396,14 @@ class CountEngine:
             # "zero seen" flags afterwards, and the two-pass route below is skipped on the device when it is set.
             if mean_vec is not None and std_vec is not None and mean_vec.is_f64 != std_vec.is_f64:
                 mean_vec, std_vec = mean_vec.as_f64(), std_vec.as_f64()
-            spec = self.spec = PostSpec(self, mean_vec, std_vec)
+            spec = self.spec_for(mean_vec, std_vec)
             self.count(dpk, out, mean_vec, std_vec, spec=spec)
             if reducer:
                 reducer.flag_or(self, spec)
-            self.count(dpk, out, mean_vec, std_vec, track_min=True, skip=spec.flag)
+            self.count(dpk, out, mean_vec, std_vec, track_min=True, skip=spec, reset_min=False)  # reset by the launch above
             if reducer:
-                reducer.min_allreduce(self, skip=spec.flag)
-            self.post_log2(out, skip=spec.flag)
+                reducer.min_allreduce(self, skip=spec)
+            self.post_log2(out, skip=spec)
             return out, mean_vec, std_vec
         if mean is not True and std is not True:
             # every vector is known up front: one fused launch (+ the Log2.post pass)
@@ -434,8 +456,8 @@ class CountEngine:
                     std_vec = DeviceVector(stat(self, _lib.COLPASS_SQDEV, out, mean_vec, arrmean, "std", flags[1:2]), False,
                                            flag=flags[1:2])
             if vectors_only:
-                bits = flags.cpu().numpy()
-                self.vector_nan = bool((mean is True and bits[0] & 1) or (std is True and bits[1] & 3))
+                # `vector_nan` reads the two flag words when somebody asks (no host synchronisation in the pipeline)
+                self._vector_flags = (flags, mean is True, std is True)
                 return out, mean_vec, std_vec
             if fused_tail:
                 bits = flags.cpu().numpy()  # the one host decision of this path (a few microseconds of sync)
@@ -494,15 +516,16 @@ class CountEngine:
         if (std_vec is not None and not vec_is_f64 and std_vec.well_scaled and std_vec.positive
                 and (mean_vec is None or getattr(mean_vec, "bounded", False)) and self.fast_division):
             rstd = std_vec.reciprocal(self.stream)
-        spec = self.spec = PostSpec(self, mean_vec, std_vec) if post else None
+        spec = self.spec_for(mean_vec, std_vec) if post else None
         sa = _lib.StreamArgs()
         a = sa.count
+        a.max_length = int(getattr(packed, "max_length", 0) or 0)
         a.k, a.log2_pre = self.k, 1 if self.log2 == "Log2.pre" else 0
         a.d_mean, a.d_std, a.d_rstd = device.ptr(mean_vec.t if mean_vec else None), device.ptr(std_vec.t if std_vec else None), device.ptr(rstd)
         a.vec_is_f64 = int(vec_is_f64)
         a.d_out, a.ld_out = device.ptr(out), out.stride(0)
         if spec is not None:
-            a.d_post, a.d_spec = device.ptr(spec.t), device.ptr(spec.t)
+            a.d_post, a.d_spec, a.spec_epoch = device.ptr(spec.t), device.ptr(spec.t), spec.epoch
         if std_vec is not None and not post:
             # the reference warns about NaNs after standardisation (kmer_counts.py:176): keep the running flag
             self.min_cell.reset(self.stream)
@@ -545,6 +568,14 @@ class CountEngine:
         acc = self.col_sum(kind, a, vec, vec2)
         return self.col_finish(acc, a.shape[0], take_sqrt=(finish == "std"), flag=flag)
 
+    @property
+    def vector_nan(self):
+        """After run(..., vectors_only=True): would the standardised matrix have held a NaN (a zero / non-finite
+        std or a non-finite mean), i.e. does the reference warn?  Synchronises."""
+        flags, mean_true, std_true = self._vector_flags
+        bits = flags.cpu().numpy()
+        return bool((mean_true and bits[0] & 1) or (std_true and bits[1] & 3))
+
     def nan_after_standardize(self):
         """True when the standardised matrix held a NaN (the reference's warning, kmer_counts.py:176)."""
         if not getattr(self, "std_applied", False):
@@ -561,6 +592,7 @@ class DevicePacked:
         base = slab.data_ptr()
         self.m = packed.m
         self.total_bases = packed.total_bases
+        self.max_length = int(getattr(packed, "max_length", 0) or 0)  # 0 = unknown
         self.codes = ctypes.c_void_p(base + packed.off_codes)
         self.mask = ctypes.c_void_p(base + packed.off_mask)
         self.blk_off = ctypes.c_void_p(base + packed.off_blk)

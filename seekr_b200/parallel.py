@@ -145,15 +145,18 @@ class PeerMinExchange(_PeerBuffer):
             raise ValueError("peer exchange handles up to 32 ranks")
         super().__init__(2 * dist.get_world_size(group) * 8, group)
 
-    def exchange(self, engine, cell=None, skip=None):
-        """cell: int32 pair on the device seen as a SkrMinCell (default: the engine's minimum cell); skip: device
-        uint32, the launch is a no-op when it is non-zero (it must hold the same value on every rank)."""
+    def exchange(self, engine, cell=None, skip=None, flag_value=0):
+        """cell: int32 pair on the device seen as a SkrMinCell (default: the engine's minimum cell); skip: a PostSpec,
+        the launch is a no-op when that speculation held (the flag must hold the same value on every rank);
+        flag_value: the cell's second word is an epoch flag (set when equal to flag_value)."""
         from . import _lib, device
 
         self.epoch += 1
         _lib.check(self.lib.skr_min_exchange_skip(device.ptr(engine.min_cell.t if cell is None else cell), device.ptr(self.table),
-                                                  self.world, self.rank, self.epoch, device.ptr(skip), device.ptr(self.err),
-                                                  device.stream_ptr(engine.stream)))
+                                                  self.world, self.rank, self.epoch,
+                                                  device.ptr(skip.flag if skip is not None else None),
+                                                  skip.epoch if skip is not None else 0, int(flag_value),
+                                                  device.ptr(self.err), device.stream_ptr(engine.stream)))
 
     def check(self):
         super().check("minimum exchange")
@@ -223,9 +226,9 @@ class _Base:
     def flag_or(self, engine, spec):
         """OR of the "zero seen" flags of the speculative Log2.post route over the ranks: the (zero_col, zero_seen)
         pair is exchanged as a minimum cell (MIN of the identical column index, OR of the flag)."""
-        self.min_allreduce(engine, cell=spec.cell)
+        self.min_allreduce(engine, cell=spec.cell, flag_value=spec.epoch)
 
-    def min_allreduce(self, engine, cell=None, skip=None):
+    def min_allreduce(self, engine, cell=None, skip=None, flag_value=0):
         """Combine the per-rank Log2.post cells (uint32 pair on the device) across ranks.  On CUDA this is one
         single-warp kernel over NVLink peer memory (PeerMinExchange); SEEKR_B200_MIN_EXCHANGE=nccl, or a box
         without CUDA IPC between the ranks, takes the library all-reduce instead.  ``skip`` (device uint32, the
@@ -246,10 +249,14 @@ class _Base:
                     warnings.warn("peer-memory minimum exchange unavailable (%s); using the NCCL all-reduce" % (exc,))
                     self._peer_failed = True
             if getattr(self, "_peer", None) is not None:
-                self._peer.exchange(engine, cell=cell, skip=skip)
+                self._peer.exchange(engine, cell=cell, skip=skip, flag_value=flag_value)
                 return
         as64 = cell.to(torch.int64) & 0xFFFFFFFF
+        if flag_value:
+            as64[1:2] = (as64[1:2] == int(flag_value)).to(torch.int64)
         allreduce_min_cell(as64, self.group)
+        if flag_value:
+            as64[1:2] = as64[1:2] * int(flag_value)
         cell.copy_(torch.where(as64 >= 2 ** 31, as64 - 2 ** 32, as64).to(torch.int32))
 
     def check(self):

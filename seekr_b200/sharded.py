@@ -76,6 +76,7 @@ def upload_slice(engine, packed, begin, end):
 
     p = _P()
     p.m, p.total_bases, p.slab_bytes = m, sl.total_bases, total
+    p.max_length = int(lens.max()) if m else 0
     p.off_codes, p.off_mask, p.off_blk, p.off_len = starts
     return DevicePacked(slab, p)
 

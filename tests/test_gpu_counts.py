@@ -467,6 +467,7 @@ def test_speculative_post_record_ranges():
     whole, _, _ = eng.run(dpk, mv, sv)
     from seekr_b200.kmer_counts import PostSpec
     spec = PostSpec(eng, mv, sv)
+    spec.next_epoch()
     parts = device.zeros((len(seqs), 4 ** k), whole.dtype)
     cuts = [0, 1, 9, 200, 201, 513, len(seqs)]
     for a, b in zip(cuts, cuts[1:]):

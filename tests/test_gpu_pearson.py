@@ -303,7 +303,8 @@ def test_pearson_full_size_sampled_pairs():
         jj = torch.randint(0, m, (10000,), device="cuda", generator=gen)
         err = (out[ii, jj].double() - exact(a, a, ii, jj)).abs().max().item()
         worst = max(worst, err)
-        assert torch.equal(out[ii, jj], out[jj, ii])
+        # mirrored tiles are copies; inside a diagonal tile (i, j) and (j, i) are two accumulations of the same terms
+        assert (out[ii, jj] - out[jj, ii]).abs().max().item() < 2e-6
     assert worst < 5e-6, worst
     assert (torch.diagonal(out) - 1).abs().max().item() < 5e-6
     del out

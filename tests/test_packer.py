@@ -133,3 +133,56 @@ def test_pack_sequences_matches_pack_file():
     a = unpack(PackedFasta.from_file(golden("small.fa")))
     b = unpack(PackedFasta.from_sequences(seqs))
     assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+def _snapshot(packed):
+    packed.wait()
+    import ctypes
+    spans = lambda getter: np.array(packed._view(getter, 2 * packed.m, np.uint64))  # noqa: E731
+    return (packed.m, np.array(packed.lengths), np.array(packed.block_offsets), np.array(packed.codes), np.array(packed.mask),
+            spans(packed._lib.skr_packed_header_spans), spans(packed._lib.skr_packed_body_spans))
+
+
+def _same(a, b):
+    return a[0] == b[0] and all(np.array_equal(x, y) for x, y in zip(a[1:], b[1:]))
+
+
+@pytest.mark.parametrize("threads", [1, 3, 16])
+def test_fast_scan_lane_equals_line_by_line(threads, monkeypatch):
+    """The scan consumes runs of clean sequence lines 32 bytes at a time; the record table, the packed words and
+    the spans must be those of the line-by-line scan, whatever falls on a 32-byte boundary."""
+    rng = np.random.default_rng(threads)
+    texts = [synth.fasta_bytes(300, seed=3, stress=True, lo=10, hi=3000),
+             synth.fasta_bytes(200, seed=4, stress=False, wrap=31, lo=1, hi=400),
+             synth.fasta_bytes(200, seed=5, stress=False, wrap=32, lo=1, hi=400),
+             synth.fasta_bytes(200, seed=6, stress=True, wrap=33, lo=1, hi=400, newline=b"\r\n"),
+             synth.fasta_bytes(50, seed=7, wrap=60, lo=500, hi=900)[:-1]]          # no newline at the end
+    # hand-made: special bytes around block boundaries, leading / trailing blanks, '>' inside a sequence line
+    for shift in range(0, 70, 7):
+        body = b"ACGT" * 40
+        texts.append(b">h" + b"x" * shift + b"\n" + body[:61] + b"\n" + body[:32] + b"\n " + body[:30] + b" \n" +
+                     body[:5] + b">" + body[:20] + b"\n>second record\n" + body[:64] + b"\n" + body[:31] + b"\nAC\tGT\n")
+    for text in texts:
+        snaps = []
+        for no_fast in ("", "1"):
+            if no_fast:
+                monkeypatch.setenv("SKR_PACK_NO_FAST_SCAN", "1")
+            else:
+                monkeypatch.delenv("SKR_PACK_NO_FAST_SCAN", raising=False)
+            snaps.append(_snapshot(PackedFasta.from_buffer(text, nthreads=threads)))
+            snaps.append(_snapshot(PackedFasta.from_buffer(text, nthreads=threads, background=True)))
+        assert all(_same(snaps[0], other) for other in snaps[1:])
+    # errors are the same too: a blank line inside a clean run, at every offset of a 32-byte block
+    for pad in range(0, 40):
+        text = b">a\n" + b"A" * pad + b"\n" + b"C" * 60 + b"\n\n" + b"G" * 60 + b"\n"
+        for no_fast in ("", "1"):
+            if no_fast:
+                monkeypatch.setenv("SKR_PACK_NO_FAST_SCAN", "1")
+            else:
+                monkeypatch.delenv("SKR_PACK_NO_FAST_SCAN", raising=False)
+            if pad == 0:
+                with pytest.raises(IndexError):
+                    PackedFasta.from_buffer(text, nthreads=threads)
+            else:
+                with pytest.raises(IndexError):
+                    PackedFasta.from_buffer(text, nthreads=threads)

@@ -103,10 +103,11 @@ def _worker(rank, world, port, a, out):
         eng2.min_cell.t = torch.tensor([0, 0], dtype=torch.int32)
         eng2.stream = None
         spec = Cell()
-        spec.cell = torch.tensor([17, 1 if rank == 1 else 0], dtype=torch.int32)
+        spec.epoch = 5   # the flag word counts as set when it holds the run's epoch; a stale epoch does not
+        spec.cell = torch.tensor([17, 5 if rank == 1 else 4], dtype=torch.int32)
         red.flag_or(eng2, spec)
-        assert spec.cell.tolist() == [17, 1]
-        spec.cell = torch.tensor([17, 0], dtype=torch.int32)
+        assert spec.cell.tolist() == [17, 5]
+        spec.cell = torch.tensor([17, 4], dtype=torch.int32)
         red.flag_or(eng2, spec)
         assert spec.cell.tolist() == [17, 0]
         # the single exchange of the accurate column statistics

@@ -31,6 +31,16 @@ for it in range(7):
         assert np.array_equal(prev, c.counts[:64])
     prev = c.counts[:64].copy()
     del c
+import cProfile, pstats, io
+pr = cProfile.Profile()
+pr.enable()
+c = BasicCounter(path, k=6, mean=mean, std=std, log2="Log2.post", silent=True)
+c.get_counts()
+pr.disable()
+buf = io.StringIO()
+pstats.Stats(pr, stream=buf).sort_stats("cumulative").print_stats(28)
+print(buf.getvalue())
+del c
 # staged path for comparison (what round 1 did): pack everything, upload, run, one D2H
 for it in range(3):
     t0 = time.perf_counter()

@@ -101,6 +101,7 @@ def main():
         report("count fused -mean /std +post", ms, mn, in_bytes + row_bytes)
         from seekr_b200.kmer_counts import PostSpec
         spec = PostSpec(eng, mean, std)
+        spec.next_epoch()
         ms, mn = timeit(lambda: eng.count(dpk, out, mean, std, spec=spec), flush)
         report("count + speculative Log2.post", ms, mn, in_bytes + row_bytes)
         if k == 6:
