@@ -147,7 +147,7 @@ int skr_post_spec(const void* d_mean, const void* d_std, int vec_is_f64, int64_t
  * Beyond skr_count's arguments:
  *   d_colmin   per-column minima of the un-normalised values (what skr_count_colmin returns; no vectors then);
  *              d_out may be NULL for a minima-only pass
- *   d_colsum / d_colsq   accurate column statistics in the same pass (k = 6, plain counts): every thread sums
+ *   d_colsum / d_colsq   accurate column statistics in the same pass (k = 4, 5, 6, plain counts): every thread sums
  *              the values and squares of its own columns over its records in fp32 and adds them here (binary64
  *              atomics, arrays zeroed by the caller) when it is done; skr_colstat_finish turns them into the
  *              fp32 mean / std vectors (binary64: mean = S1/rows, var = S2/rows - mean^2).  Closer to the exact

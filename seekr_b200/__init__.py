@@ -21,7 +21,8 @@ def install_as_seekr():
     pkg.__path__ = []
     pkg.__version__ = __version__
     sys.modules["seekr"] = pkg
-    for name in ("kmer_counts", "pearson", "fasta_reader", "console_scripts", "my_tqdm", "find_pval", "find_dist"):
+    for name in ("kmer_counts", "pearson", "fasta_reader", "console_scripts", "my_tqdm", "find_pval", "find_dist",
+                 "kmer_leiden"):
         mod = importlib.import_module("seekr_b200." + name)
         sys.modules["seekr." + name] = mod
         setattr(pkg, name, mod)

@@ -66,6 +66,10 @@ struct CountParams {
     uint32_t skip_value;
     uint32_t spec_epoch;          // written to spec->zero_seen when a zero count is met in the arg-min column
     SkrMinCell* min_reset;        // reset at the start of the launch (the cell the two-pass route behind it will track)
+    // k >= 7: the finished values of a ZERO count in every column (vectors and Log2.post applied); a record of a few
+    // thousand windows leaves 80-95 % of 16 384 / 65 536 bins empty, and a quad of empty bins is copied from here
+    // (one 16-byte load from L2) instead of loading three vector quads and redoing the arithmetic
+    const float4* zero_row;
     uint32_t max_length;          // longest record of this launch when the caller knows it (0 = unknown)
     // accurate column statistics (norm_vectors in one pass): per-column sum and sum of squares of the values
     // written, accumulated in fp32 per thread over its records and added here in binary64 at the end
@@ -140,10 +144,29 @@ __device__ __forceinline__ float log2_post(float x) {
 
 // value of a bin whose count is beyond the table (rare: low-complexity records); kept out of line so the
 // hot epilogue stays small in the instruction cache
-__device__ __noinline__ float slow_bin_value(double inc, uint32_t c, int log2_pre) {
+__device__ __noinline__ float chain_bin_value(double inc, uint32_t c, int log2_pre) {
     float v = __double2float_rn(skr::chain_sum(inc, c));
     if (log2_pre) v = log2f(__fadd_rn(v, 1.0f));
     return v;
+}
+
+// Counts beyond the table.  The c-fold binary64 sum s differs from p = RN(c * inc) by less than c + 1 units in the
+// last place of p (every add rounds by at most half an ulp of a partial sum no larger than p, the product by half an
+// ulp), and fp32(s) = fp32(p) unless a float32 rounding boundary -- a binary64 whose low 29 mantissa bits are exactly
+// 2^28 -- lies that close to p.  So p decides in ~8 instructions whenever its low 29 bits are further than c + 2
+// from 2^28 (all but a fraction c * 2^-27 of the values); only the rest walk the exact chain.  Counts of 32 and
+// more are the rule for k <= 5 (256 / 1 024 bins for thousands of windows), where the chain made up 40 % of the
+// kernel's instructions (profiles/r02_ncu_count_k4_raw.txt).
+__device__ __forceinline__ float slow_bin_value(double inc, uint32_t c, int log2_pre) {
+    const double prod = __dmul_rn(inc, (double)c);
+    const int low = (int)((unsigned long long)__double_as_longlong(prod) & 0x1FFFFFFFull);
+    const uint32_t dist = (uint32_t)abs(low - 0x10000000);
+    if (c < 0x08000000u && dist > c + 2u) {
+        float v = __double2float_rn(prod);
+        if (log2_pre) v = log2f(__fadd_rn(v, 1.0f));
+        return v;
+    }
+    return chain_bin_value(inc, c, log2_pre);
 }
 
 // Correctly rounded a / b from y = RN(1/b) with two Newton corrections on the quotient (Markstein: when y is
@@ -172,18 +195,24 @@ __device__ __forceinline__ uint64_t sub_div_by_rcp2(uint64_t x, uint64_t nm, uin
     return skr::f2_fma(r, y, q);
 }
 
-// counts of 4 consecutive bins -> the reference's float32 values (per-kb chain, log2.pre, -mean, /std).
-// packed = the two histogram words (four 16-bit counts) when every count fits the table.
+__device__ __forceinline__ uint64_t f2_neg(uint64_t v) { return v ^ 0x8000000080000000ull; }
+
+// -mean, /std of 4 consecutive columns starting at 4 * q, with the reference's roundings (kmer_counts.py:169,175)
 template <bool kVecF64>
-__device__ __forceinline__ void finish4(const uint32_t (&c4)[4], uint32_t tab_addr, double inc, const CountParams& p, int q,
-                                        float (&r)[4]) {
-    if (((c4[0] | c4[1] | c4[2] | c4[3]) & ~(uint32_t)(kTab - 1)) == 0) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) r[e] = lds_f32(tab_addr + c4[e] * 4);
-    } else {
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-            r[e] = c4[e] < kTab ? lds_f32(tab_addr + c4[e] * 4) : slow_bin_value(inc, c4[e], p.log2_pre);
+__device__ __forceinline__ void normalize4(const CountParams& p, int q, float (&r)[4]) {
+    if constexpr (!kVecF64) {
+        if (p.mean && p.std_ && p.rstd) {  // two columns per instruction (packed fp32x2), exact reciprocal division
+            const float4 mv = __ldg(reinterpret_cast<const float4*>(p.mean) + q);
+            const float4 sv = __ldg(reinterpret_cast<const float4*>(p.std_) + q);
+            const float4 yv = __ldg(reinterpret_cast<const float4*>(p.rstd) + q);
+            const uint64_t z0 = sub_div_by_rcp2(skr::f2_pack(r[0], r[1]), f2_neg(skr::f2_pack(mv.x, mv.y)),
+                                                f2_neg(skr::f2_pack(sv.x, sv.y)), skr::f2_pack(yv.x, yv.y));
+            const uint64_t z1 = sub_div_by_rcp2(skr::f2_pack(r[2], r[3]), f2_neg(skr::f2_pack(mv.z, mv.w)),
+                                                f2_neg(skr::f2_pack(sv.z, sv.w)), skr::f2_pack(yv.z, yv.w));
+            skr::f2_unpack(z0, r[0], r[1]);
+            skr::f2_unpack(z1, r[2], r[3]);
+            return;
+        }
     }
     if (p.mean) {
         if constexpr (kVecF64) {
@@ -213,6 +242,21 @@ __device__ __forceinline__ void finish4(const uint32_t (&c4)[4], uint32_t tab_ad
             }
         }
     }
+}
+
+// counts of 4 consecutive bins -> the reference's float32 values (per-kb chain, log2.pre, -mean, /std).
+template <bool kVecF64>
+__device__ __forceinline__ void finish4(const uint32_t (&c4)[4], uint32_t tab_addr, double inc, const CountParams& p, int q,
+                                        float (&r)[4]) {
+    if (((c4[0] | c4[1] | c4[2] | c4[3]) & ~(uint32_t)(kTab - 1)) == 0) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) r[e] = lds_f32(tab_addr + c4[e] * 4);
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            r[e] = c4[e] < kTab ? lds_f32(tab_addr + c4[e] * 4) : slow_bin_value(inc, c4[e], p.log2_pre);
+    }
+    normalize4<kVecF64>(p, q, r);
 }
 
 // 16 window starts of one chunk -> shared-memory histogram (two 16-bit sub-counters per word).
@@ -374,13 +418,18 @@ __global__ void __launch_bounds__(CountCfg<K>::kThreads) count_kernel(const Coun
                 reinterpret_cast<double2*>(orow)[2 * q + 1] = make_double2(r[2], r[3]);
             } else {
                 float r[4];
-                finish4<kVecF64>(c4, skr::smem_u32(s_tab), inc, p, q, r);
+                if (p.zero_row && (c4[0] | c4[1] | c4[2] | c4[3]) == 0) {
+                    const float4 z = __ldg(p.zero_row + q);  // normalised and Log2.post-shifted already
+                    r[0] = z.x; r[1] = z.y; r[2] = z.z; r[3] = z.w;
+                } else {
+                    finish4<kVecF64>(c4, skr::smem_u32(s_tab), inc, p, q, r);
+                    if (p.post_cell && !p.colmin) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) r[e] = log2_post(__fadd_rn(__fadd_rn(r[e], shift), 1.0f));
+                    }
+                }
                 if (q == zq && (ze == 0 ? c4[0] : ze == 1 ? c4[1] : ze == 2 ? c4[2] : c4[3]) == 0) zseen = 1;
                 if (p.colmin) colmin_note<kSteps>(zero_seen, c4, r, p.colmin, q);
-                if (p.post_cell) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) r[e] = log2_post(__fadd_rn(__fadd_rn(r[e], shift), 1.0f));
-                }
                 if (p.min_cell) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) skr::min_update(r[e], tmin, tnan);
@@ -581,14 +630,30 @@ struct BatchCfg {
     // 512 threads, two CTAs per SM = 1024 threads = 64 registers each (with a 17th warp the limit was 56 and the
     // epilogue spilled).  Every thread owns bin quads in the epilogue; in the count phase warp 15 keeps the books
     // and the other 15 warps count.
-    static constexpr int kWorkers = 512;
+    // k = 7: 32 KB per histogram, so one CTA of 1024 threads per SM with five records per batch
+    static constexpr int kWorkers = K >= 7 ? 1024 : 512;
     static constexpr int kThreads = kWorkers;
+    static constexpr int kCtasPerSm = K >= 7 ? 1 : 2;
     static constexpr int kCounters = kWorkers - 32;
-    static constexpr int kB = 8;                        // records per batch
-    static constexpr int kQ = kBins / 4 / kWorkers;     // bin quads per worker thread
-    // histograms start at a multiple of their size (count_chunk<K, true>): one histogram of slack
+    static constexpr int kQuads = kBins / 4;
+    // k = 6: a thread owns kQ = 2 quads of EVERY record.  k = 4, 5: a histogram has fewer quads than the CTA has
+    // threads, so the threads form kG groups of kQuads threads; group g takes records g, g + kG, ... of the batch
+    // in the epilogue (a thread still owns fixed columns, so its vector slices stay in registers), and a batch holds
+    // many more records, which also evens out the count phase (units per thread 6.7 instead of 1.7).
+    // k = 7: kQ = 4 quads per thread; their vector slices (48 registers) do not fit beside the epilogue, so the
+    // epilogue runs in kChunks = 2 passes over the batch with kQc = 2 quads' slices re-read (L2) before each pass:
+    // 192 KB of vector reads per batch of five records instead of 192 KB per record.
+    static constexpr int kQ = kQuads >= kWorkers ? kQuads / kWorkers : 1;
+    static constexpr int kG = kQuads >= kWorkers ? 1 : kWorkers / kQuads;
+    static constexpr int kQc = kQ > 2 ? 2 : kQ;       // quads whose vector slices are in registers at a time
+    static constexpr int kChunks = kQ / kQc;
+    static constexpr int kB = K >= 7 ? 5 : (K == 6 ? 8 : 32);  // records per batch
+    // histograms start at a multiple of their size (count_chunk_full): one histogram of slack
     static constexpr size_t kSmem = (size_t)(kB + 1) * kHistBytes;
-    static_assert(kBins / 4 % kWorkers == 0 && kQ >= 1, "every worker owns whole quads of every record");
+    static_assert(kQuads % 32 == 0, "a warp works on one record at a time in the epilogue (table lookups are warp shuffles)");
+    static_assert((kQuads >= kWorkers && kQuads % kWorkers == 0) || kWorkers % kQuads == 0, "whole quads per thread / whole groups per CTA");
+    static_assert(kB % 32 == 0 || kB < 32, "the bookkeeping warp handles the records of a batch 32 at a time");
+    static_assert(kQ % kQc == 0, "whole chunks");
 };
 
 template <int kB>
@@ -650,20 +715,34 @@ __device__ __noinline__ void count_phase(const uint32_t* __restrict__ codes, con
     constexpr uint32_t oPrefix = offsetof(Meta, prefix), oNwin = offsetof(Meta, nwin), oB0 = offsetof(Meta, b0);
     const uint32_t whole = lds_u32(mt_addr + oPrefix + 4 * kB);
     const uint32_t total = whole + kB;  // whole units first, then one tail slot per record
+    // cursor of the incremental search (large batches): record cr holds the whole units [cbase, cnext)
+    int cr = 0;
+    uint32_t cbase = 0, cnext = lds_u32(mt_addr + oPrefix + 4);
     auto locate = [&](uint32_t g, int& r, uint32_t& u) {
         if (g >= whole) {  // tail slot of record g - whole: the unit after its whole units (may be empty)
             r = (int)(g - whole);
             u = (uint32_t)(lds_u64(mt_addr + oNwin + 8 * (uint32_t)r) >> 5);
             return;
         }
-        r = 0;
-        uint32_t before = 0;
+        if constexpr (kB <= 8) {
+            r = 0;
+            uint32_t before = 0;
 #pragma unroll
-        for (int i = 1; i < kB; ++i) {
-            const uint32_t pf = lds_u32(mt_addr + oPrefix + 4 * i);  // broadcast shared loads
-            if (g >= pf) { r = i; before = pf; }
+            for (int i = 1; i < kB; ++i) {
+                const uint32_t pf = lds_u32(mt_addr + oPrefix + 4 * i);  // broadcast shared loads
+                if (g >= pf) { r = i; before = pf; }
+            }
+            u = g - before;
+        } else {
+            // a thread's unit indices only grow, so the record is found by walking on from the previous one
+            while (g >= cnext) {  // g < whole = prefix[kB], so cr stays below kB
+                ++cr;
+                cbase = cnext;
+                cnext = lds_u32(mt_addr + oPrefix + 4 * (uint32_t)(cr + 1));
+            }
+            r = cr;
+            u = g - cbase;
         }
-        u = g - before;
     };
     uint32_t w0 = 0, w1 = 0, w2 = 0, m0 = 0, m1 = 0, u = 0;
     int r = 0;
@@ -716,9 +795,11 @@ __device__ __noinline__ void count_phase(const uint32_t* __restrict__ codes, con
 enum { kBatchAny = 0, kBatchPlain = 1, kBatchFast = 2, kBatchPost = 3 };
 
 template <int K, bool kVecF64, int kMode, bool kMin, bool kColmin = false, bool kStats = false>
-__global__ void __launch_bounds__(BatchCfg<K>::kThreads, 2) count_batch_kernel(const CountParams p) {
+__global__ void __launch_bounds__(BatchCfg<K>::kThreads, BatchCfg<K>::kCtasPerSm) count_batch_kernel(const CountParams p) {
     using Cfg = BatchCfg<K>;
-    constexpr int kB = Cfg::kB, kW = Cfg::kWorkers, kQ = Cfg::kQ;
+    constexpr int kB = Cfg::kB, kW = Cfg::kWorkers, kQ = Cfg::kQ, kG = Cfg::kG, kQc = Cfg::kQc, kChunks = Cfg::kChunks;
+    static_assert(kChunks == 1 || (!kColmin && !kStats && kMode != kBatchAny),
+                  "k = 7 runs the plain, fast and post flavours here; the others stay with the CTA-per-record kernel");
     constexpr bool kRegVec = kMode == kBatchFast || kMode == kBatchPost;  // -mean, -std, 1/std in registers
     static_assert(!(kVecF64 && kMode != kBatchAny), "binary64 vectors take the generic epilogue");
     static_assert(!kColmin || kMode == kBatchPlain, "kColmin: column minima of the plain values (kBatchAny decides at run time)");
@@ -731,6 +812,8 @@ __global__ void __launch_bounds__(BatchCfg<K>::kThreads, 2) count_batch_kernel(c
     const int tid = threadIdx.x, lane = tid & 31;
     constexpr bool worker = true;                 // every thread takes part in the epilogue
     const bool counter = tid < Cfg::kCounters;    // count phase: warps 0..14 count, warp 15 prepares the next batch
+    const int gi = kG > 1 ? tid / Cfg::kQuads : 0;    // epilogue group: records gi, gi + kG, ... of a batch
+    const int qb = kG > 1 ? tid % Cfg::kQuads : tid;  // first bin quad of this thread
     const uint32_t raw_addr = skr::smem_u32(smem_b);
     const uint32_t hist_addr = (raw_addr + Cfg::kHistBytes - 1) & ~(uint32_t)(Cfg::kHistBytes - 1);
 
@@ -745,33 +828,39 @@ __global__ void __launch_bounds__(BatchCfg<K>::kThreads, 2) count_batch_kernel(c
     uint32_t zseen = 0;
     if ((kMode == kBatchAny || kMode == kBatchPost) && p.spec) {
         const int zc = p.spec->zero_col;
-        if (zc >= 0 && ((zc >> 2) % kW) == tid) { zoff = (zc >> 1) * 4; zsh = (uint32_t)(zc & 1) * 16u; }
+        if (zc >= 0 && (kG > 1 ? (zc >> 2) == qb : ((zc >> 2) % kW) == tid)) { zoff = (zc >> 1) * 4; zsh = (uint32_t)(zc & 1) * 16u; }
     }
 
     // this thread's slices of the vectors (fp32 vectors only; binary64 vectors are read in the epilogue)
-    float4 mv[kQ], sv[kQ], yv[kQ];
-    uint32_t cmin[kQ][4];
-    float sx[kQ][4], sq[kQ][4];
+    float4 mv[kQc], sv[kQc], yv[kQc];
+    uint32_t cmin[kQc][4];
+    float sx[kQc][4], sq[kQc][4];
 #pragma unroll
-    for (int j = 0; j < kQ; ++j) {
-        mv[j] = sv[j] = yv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < kQc; ++j) {
+        if constexpr (!kRegVec) mv[j] = sv[j] = yv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int e = 0; e < 4; ++e) { cmin[j][e] = 0xFFFFFFFFu; sx[j][e] = 0.f; sq[j][e] = 0.f; }
     }
-    if (worker) {
-        if constexpr (!kVecF64 && kMode != kBatchPlain) {
+    // the thread's slices of the vectors for the quads of chunk `ch` (fp32 vectors)
+    auto load_vectors = [&](int ch) {
 #pragma unroll
-            for (int j = 0; j < kQ; ++j) {
-                const int q = tid + j * kW;
+        for (int j = 0; j < kQc; ++j) {
+            const int q = qb + (ch * kQc + j) * kW;
+            if constexpr (kRegVec) {  // all three vectors are there (dispatch): unconditional, negated once
+                const float4 m4 = __ldg(reinterpret_cast<const float4*>(p.mean) + q);
+                const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.std_) + q);
+                yv[j] = __ldg(reinterpret_cast<const float4*>(p.rstd) + q);
+                mv[j] = make_float4(-m4.x, -m4.y, -m4.z, -m4.w);
+                sv[j] = make_float4(-s4.x, -s4.y, -s4.z, -s4.w);
+            } else {
                 if (p.mean) mv[j] = __ldg(reinterpret_cast<const float4*>(p.mean) + q);
                 if (p.std_) sv[j] = __ldg(reinterpret_cast<const float4*>(p.std_) + q);
                 if (p.std_ && p.rstd) yv[j] = __ldg(reinterpret_cast<const float4*>(p.rstd) + q);
-                if constexpr (kRegVec) {
-                    mv[j] = make_float4(-mv[j].x, -mv[j].y, -mv[j].z, -mv[j].w);
-                    sv[j] = make_float4(-sv[j].x, -sv[j].y, -sv[j].z, -sv[j].w);
-                }
             }
         }
+    };
+    if (worker) {
+        if constexpr (!kVecF64 && kMode != kBatchPlain && kChunks == 1) load_vectors(0);  // once per kernel
         uint4* h4 = reinterpret_cast<uint4*>(smem_b + (hist_addr - raw_addr) / 4);
         for (int i = tid; i < kB * Cfg::kWords / 4; i += kW) h4[i] = make_uint4(0, 0, 0, 0);
     }
@@ -784,46 +873,52 @@ __global__ void __launch_bounds__(BatchCfg<K>::kThreads, 2) count_batch_kernel(c
         b = __shfl_sync(0xFFFFFFFFu, b, 0);
         const long long rec0 = b * kB;
         const int nrec = rec0 < p.m ? (int)min((long long)kB, p.m - rec0) : 0;
-        uint32_t units = 0;
-        if (lane < kB) {
-            long long nwin = 0;
-            unsigned long long b0 = 0;
-            int store = 0;
-            if (lane < nrec) {
-                const long long rec = rec0 + lane;
-                nwin = (long long)__ldg(p.len + rec) - K + 1;
-                b0 = __ldg(p.blk_off + rec);
-                store = 1;
-                if (nwin > kLongWin) {
-                    p.long_list[atomicAdd(p.long_count, 1u)] = (uint32_t)rec;
-                    store = 0;
-                    nwin = 0;
+        uint32_t carry = 0;  // whole units of the records handled in earlier rounds
+#pragma unroll 1
+        for (int r0 = 0; r0 < kB; r0 += 32) {
+            const int rr = r0 + lane;  // this lane's record of the round
+            uint32_t units = 0;
+            if (rr < kB) {
+                long long nwin = 0;
+                unsigned long long b0 = 0;
+                int store = 0;
+                if (rr < nrec) {
+                    const long long rec = rec0 + rr;
+                    nwin = (long long)__ldg(p.len + rec) - K + 1;
+                    b0 = __ldg(p.blk_off + rec);
+                    store = 1;
+                    if (nwin > kLongWin) {
+                        p.long_list[atomicAdd(p.long_count, 1u)] = (uint32_t)rec;
+                        store = 0;
+                        nwin = 0;
+                    }
+                    if (nwin < 0) nwin = 0;
                 }
-                if (nwin < 0) nwin = 0;
-            }
-            const double inc = nwin > 0 ? 1000.0 / (double)nwin : 0.0;
-            mt.nwin[lane] = nwin;
-            mt.b0[lane] = b0;
-            mt.inc[lane] = inc;
-            mt.store[lane] = store;
-            units = (uint32_t)(nwin >> 5);  // whole units; the ragged rest is the record's tail unit
-            double acc = 0.0;  // the literal chain of kmer_counts.py:144-150 for counts below kTab
-            mt.tab[lane][0] = p.log2_pre ? log2f(1.0f) : 0.0f;
+                const double inc = nwin > 0 ? 1000.0 / (double)nwin : 0.0;
+                mt.nwin[rr] = nwin;
+                mt.b0[rr] = b0;
+                mt.inc[rr] = inc;
+                mt.store[rr] = store;
+                units = (uint32_t)(nwin >> 5);  // whole units; the ragged rest is the record's tail unit
+                double acc = 0.0;  // the literal chain of kmer_counts.py:144-150 for counts below kTab
+                mt.tab[rr][0] = p.log2_pre ? log2f(1.0f) : 0.0f;
 #pragma unroll 8
-            for (int c = 1; c < kTab; ++c) {
-                acc = __dadd_rn(acc, inc);
-                float v = __double2float_rn(acc);
-                if (p.log2_pre) v = log2f(__fadd_rn(v, 1.0f));
-                mt.tab[lane][c] = v;
+                for (int c = 1; c < kTab; ++c) {
+                    acc = __dadd_rn(acc, inc);
+                    float v = __double2float_rn(acc);
+                    if (p.log2_pre) v = log2f(__fadd_rn(v, 1.0f));
+                    mt.tab[rr][c] = v;
+                }
             }
-        }
-        uint32_t incl = units;  // inclusive scan over the first kB lanes
+            uint32_t incl = units;  // inclusive scan over the lanes of the round
 #pragma unroll
-        for (int o = 1; o < kB; o <<= 1) {
-            const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-            if (lane >= o) incl += up;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            if (rr < kB) mt.prefix[rr + 1] = carry + incl;
+            carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
         }
-        if (lane < kB) mt.prefix[lane + 1] = incl;
         if (lane == 0) {
             mt.prefix[0] = 0;
             mt.rec0 = nrec > 0 ? rec0 : -1;
@@ -846,16 +941,19 @@ __global__ void __launch_bounds__(BatchCfg<K>::kThreads, 2) count_batch_kernel(c
         if (worker) {
             // ---- epilogue ----
             const int nrec = mt.nrec;
-            for (int r = 0; r < nrec; ++r) {
+#pragma unroll 1
+            for (int ch = 0; ch < kChunks; ++ch) {
+            if constexpr (!kVecF64 && kMode != kBatchPlain && kChunks > 1) load_vectors(ch);  // once per batch and chunk
+            for (int r = gi; r < nrec; r += kG) {
                 if (!mt.store[r]) continue;
                 const uint32_t tab_addr = skr::smem_u32(&mt.tab[r][0]);
                 const float treg = lds_f32(tab_addr + (uint32_t)lane * 4);  // lane c holds the value of a bin seen c times
                 const uint32_t hrec = hist_addr + (uint32_t)r * Cfg::kHistBytes;
                 float* __restrict__ orow = reinterpret_cast<float*>(p.out) + (size_t)(mt.rec0 + r) * (size_t)p.ld_out;
-                if (zoff >= 0 && ((lds_u32(hrec + (uint32_t)zoff) >> zsh) & 0xFFFFu) == 0) zseen = 1;
+                if (ch == 0 && zoff >= 0 && ((lds_u32(hrec + (uint32_t)zoff) >> zsh) & 0xFFFFu) == 0) zseen = 1;
 #pragma unroll
-                for (int j = 0; j < kQ; ++j) {
-                    const int q = tid + j * kW;
+                for (int j = 0; j < kQc; ++j) {
+                    const int q = qb + (ch * kQc + j) * kW;
                     const uint32_t a = hrec + (uint32_t)q * 8;
                     const uint2 v = lds_v2(a);
                     sts_zero_v2(a);
@@ -945,6 +1043,7 @@ __global__ void __launch_bounds__(BatchCfg<K>::kThreads, 2) count_batch_kernel(c
                         reinterpret_cast<float4*>(orow)[q] = make_float4(x[0], x[1], x[2], x[3]);
                 }
             }
+            }
         }
         __syncthreads();
     }
@@ -953,19 +1052,19 @@ __global__ void __launch_bounds__(BatchCfg<K>::kThreads, 2) count_batch_kernel(c
         if (zseen) p.spec->zero_seen = p.spec_epoch;
         if (kColmin || (kMode == kBatchAny && p.colmin)) {
 #pragma unroll
-            for (int j = 0; j < kQ; ++j)
+            for (int j = 0; j < kQc; ++j)
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const int col = 4 * (tid + j * kW) + e;
+                    const int col = 4 * (qb + j * kW) + e;
                     if (cmin[j][e] < p.colmin[col]) atomicMin(&p.colmin[col], cmin[j][e]);
                 }
         }
         if constexpr (kStats) {
 #pragma unroll
-            for (int j = 0; j < kQ; ++j)
+            for (int j = 0; j < kQc; ++j)
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const int col = 4 * (tid + j * kW) + e;
+                    const int col = 4 * (qb + j * kW) + e;
                     atomicAdd(&p.colsum[col], (double)sx[j][e]);
                     atomicAdd(&p.colsq[col], (double)sq[j][e]);
                 }
@@ -1000,8 +1099,26 @@ int launch_batch(const CountParams& wp, int sms, cudaStream_t stream) {
     return SKR_OK;
 }
 
+// k = 7: the fast and post flavours only (vectors in registers, two chunk passes); false = not handled here
+template <int K>
+bool batch_handles(const CountParams& wp, int vec_is_f64) {
+    if (K <= 6) return true;
+    return !vec_is_f64 && wp.mean && wp.std_ && wp.rstd && !wp.colmin && !wp.no_store && !wp.colsum &&
+           !(wp.post_cell && wp.min_cell);
+}
+
 template <int K, bool kVecF64>
 int dispatch_batch(const CountParams& wp, int sms, cudaStream_t stream) {
+    if constexpr (K >= 7) {
+        if constexpr (kVecF64) {
+            return skr::fail(SKR_ERR_ARG, "skr_count: internal dispatch error");
+        } else {
+            const bool mn7 = wp.min_cell != nullptr;
+            if (wp.post_cell) return launch_batch<K, false, kBatchPost, false>(wp, sms, stream);
+            return mn7 ? launch_batch<K, false, kBatchFast, true>(wp, sms, stream)
+                       : launch_batch<K, false, kBatchFast, false>(wp, sms, stream);
+        }
+    } else {
     const bool plain = !wp.mean && !wp.std_ && !wp.post_cell && !wp.no_store;
     const bool regvec = !kVecF64 && wp.mean && wp.std_ && wp.rstd && !wp.colmin && !wp.no_store;
     const bool fast = regvec && !wp.post_cell;
@@ -1024,6 +1141,7 @@ int dispatch_batch(const CountParams& wp, int sms, cudaStream_t stream) {
     if (wp.colsum) return skr::fail(SKR_ERR_ARG, "skr_count: column sums go with plain counts (no vectors, no Log2.post)");
     return mn ? launch_batch<K, kVecF64, kBatchAny, true>(wp, sms, stream)
               : launch_batch<K, kVecF64, kBatchAny, false>(wp, sms, stream);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1061,6 +1179,23 @@ int next_counters(int dev, cudaStream_t stream, unsigned int** out) {
     return SKR_OK;
 }
 
+// zero_row[q] = what the epilogue makes of four empty bins in columns 4q .. 4q + 3: the same device functions, so
+// the same bits (value of a zero count is 0, also after log2(0 + 1))
+template <bool kVecF64>
+__global__ void __launch_bounds__(256) zero_row_kernel(const CountParams p, float4* zero_row, int quads) {
+    if (p.skip_flag && *p.skip_flag == p.skip_value) return;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= quads) return;
+    float r[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    normalize4<kVecF64>(p, q, r);
+    if (p.post_cell) {
+        const float shift = p.post_cell->nan_seen ? __int_as_float(0x7FC00000) : fabsf(skr::ordered_decode(p.post_cell->min_ordered));
+#pragma unroll
+        for (int e = 0; e < 4; ++e) r[e] = log2_post(__fadd_rn(__fadd_rn(r[e], shift), 1.0f));
+    }
+    zero_row[q] = make_float4(r[0], r[1], r[2], r[3]);
+}
+
 template <int K, bool kVecF64, typename OutT>
 int launch_count(CountParams p, cudaStream_t stream) {
     using Cfg = CountCfg<K>;
@@ -1072,46 +1207,52 @@ int launch_count(CountParams p, cudaStream_t stream) {
     int per_sm = 0;
     SKR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Cfg::kThreads, Cfg::kSmem));
     if (per_sm < 1) return skr::fail(SKR_ERR_CUDA, "count kernel for k=%d does not fit on this device", K);
-    // the warp-per-record kernel takes k <= 6 with float output; it leaves records that are too long for
-    // one warp on a list which the CTA kernel then drains
-    constexpr bool kUseWarp = K <= 6 && sizeof(OutT) == 4;
-    if (kUseWarp && p.m > 0xFFFFFFFFll) return skr::fail(SKR_ERR_ARG, "skr_count: more than 2^32 records");
+    // the team / batch kernels take k <= 6 with float output (and k = 7 with fp32 vectors in the fast / post
+    // flavours); they leave records that are too long for them on a list which the CTA kernel then drains
+    constexpr bool kTeamK = K <= 6 && sizeof(OutT) == 4;
+    constexpr bool kBatchOnly = K == 7 && sizeof(OutT) == 4 && !kVecF64;
+    const bool use_list = kTeamK || (kBatchOnly && batch_handles<K>(p, kVecF64));
+    if (use_list && p.m > 0xFFFFFFFFll) return skr::fail(SKR_ERR_ARG, "skr_count: more than 2^32 records");
     unsigned int* ctr = nullptr;
     int rc = next_counters(dev, stream, &ctr);
     if (rc != SKR_OK) return rc;
     // no record is too long for the team / batch kernels (the caller knows the longest record): nothing to hand over
-    const bool no_long = kUseWarp && p.max_length > 0 && (long long)p.max_length - K + 1 <= kLongWin;
+    const bool no_long = use_list && p.max_length > 0 && (long long)p.max_length - K + 1 <= kLongWin;
     uint32_t* long_list = nullptr;
-    if (kUseWarp && !no_long) SKR_CUDA_CHECK(cudaMallocAsync(&long_list, (size_t)p.m * sizeof(uint32_t), stream));
+    if (use_list && !no_long) SKR_CUDA_CHECK(cudaMallocAsync(&long_list, (size_t)p.m * sizeof(uint32_t), stream));
     long long grid = (long long)sms * per_sm;
-    if constexpr (kUseWarp) {
-        using W = WarpCfg<K>;
-        auto wkern = count_warp_kernel<K, kVecF64>;
-        SKR_CUDA_CHECK(cudaFuncSetAttribute(wkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W::kSmem));
-        if (const char* env = getenv("SEEKR_B200_COUNT_CARVEOUT"))  // experiment knob: % of the SM's 228 KB given to smem
-            SKR_CUDA_CHECK(cudaFuncSetAttribute(wkern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(env)));
-        int wper_sm = 0;
-        SKR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wper_sm, wkern, W::kThreads, W::kSmem));
-        if (wper_sm < 1) return skr::fail(SKR_ERR_CUDA, "warp count kernel for k=%d does not fit on this device", K);
-        if (const char* env = getenv("SEEKR_B200_COUNT_CTAS_PER_SM"))  // experiment knob: resident CTAs per SM
-            if (atoi(env) > 0 && atoi(env) < wper_sm) wper_sm = atoi(env);
-        long long wgrid = (long long)sms * wper_sm;
-        const long long need = (p.m + W::kTeams - 1) / W::kTeams;
-        if (wgrid > need) wgrid = need;
+    if (use_list) {
         CountParams wp = p;
         wp.work_counter = ctr;
         wp.long_list = long_list;
         wp.long_count = ctr + 1;
         bool batch = false;
-        if constexpr (K == 6) {
+        if constexpr (kBatchOnly || (kTeamK && K >= 4)) {
             const char* env = getenv("SEEKR_B200_COUNT_KERNEL");  // experiment knob: "warp" selects the team-per-record kernel
-            batch = !(env && env[0] == 'w');
+            batch = kBatchOnly || !(env && env[0] == 'w');
             if (batch) {
                 rc = dispatch_batch<K, kVecF64>(wp, sms, stream);
                 if (rc != SKR_OK) return rc;
             }
         }
-        if (!batch) wkern<<<(unsigned)wgrid, W::kThreads, W::kSmem, stream>>>(wp);
+        if constexpr (kTeamK) {
+            if (!batch) {
+                using W = WarpCfg<K>;
+                auto wkern = count_warp_kernel<K, kVecF64>;
+                SKR_CUDA_CHECK(cudaFuncSetAttribute(wkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W::kSmem));
+                if (const char* env = getenv("SEEKR_B200_COUNT_CARVEOUT"))  // experiment knob: % of the SM's 228 KB given to smem
+                    SKR_CUDA_CHECK(cudaFuncSetAttribute(wkern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(env)));
+                int wper_sm = 0;
+                SKR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wper_sm, wkern, W::kThreads, W::kSmem));
+                if (wper_sm < 1) return skr::fail(SKR_ERR_CUDA, "warp count kernel for k=%d does not fit on this device", K);
+                if (const char* env = getenv("SEEKR_B200_COUNT_CTAS_PER_SM"))  // experiment knob: resident CTAs per SM
+                    if (atoi(env) > 0 && atoi(env) < wper_sm) wper_sm = atoi(env);
+                long long wgrid = (long long)sms * wper_sm;
+                const long long need = (p.m + W::kTeams - 1) / W::kTeams;
+                if (wgrid > need) wgrid = need;
+                wkern<<<(unsigned)wgrid, W::kThreads, W::kSmem, stream>>>(wp);
+            }
+        }
         SKR_LAUNCH_CHECK();
         if (no_long) return SKR_OK;
         // long records (rare): the CTA kernel reads the list length on the device
@@ -1126,8 +1267,18 @@ int launch_count(CountParams p, cudaStream_t stream) {
         if (grid > p.m) grid = p.m;
     }
     SKR_CUDA_CHECK(cudaMallocAsync(&p.spill, (size_t)grid * Cfg::kBins * sizeof(uint32_t), stream));
+    float4* zero_row = nullptr;
+    if constexpr (K >= 7 && sizeof(OutT) == 4) {
+        if (!p.colmin && (p.mean || p.std_ || p.post_cell)) {
+            SKR_CUDA_CHECK(cudaMallocAsync(&zero_row, (size_t)Cfg::kBins * sizeof(float), stream));
+            zero_row_kernel<kVecF64><<<(Cfg::kBins / 4 + 255) / 256, 256, 0, stream>>>(p, zero_row, Cfg::kBins / 4);
+            SKR_LAUNCH_CHECK();
+            p.zero_row = zero_row;
+        }
+    }
     kern<<<(unsigned)grid, Cfg::kThreads, Cfg::kSmem, stream>>>(p);
     SKR_LAUNCH_CHECK();
+    if (zero_row) SKR_CUDA_CHECK(cudaFreeAsync(zero_row, stream));
     SKR_CUDA_CHECK(cudaFreeAsync(p.spill, stream));
     if (long_list) SKR_CUDA_CHECK(cudaFreeAsync(long_list, stream));
     return SKR_OK;
@@ -1394,7 +1545,7 @@ extern "C" int skr_count_ex(const SkrCountArgs* a, void* stream) {
         return skr::fail(SKR_ERR_ARG, "skr_count: column minima are those of the un-normalised values (16-byte aligned array)");
     if ((a->d_colsum == nullptr) != (a->d_colsq == nullptr) || (a->d_colsum && (a->d_mean || a->d_std || a->d_post || !a->d_out)))
         return skr::fail(SKR_ERR_ARG, "skr_count: column sums come in pairs and go with plain counts");
-    if (a->d_colsum && k != 6) return skr::fail(SKR_ERR_ARG, "skr_count: in-kernel column sums are implemented for k = 6");
+    if (a->d_colsum && (k < 4 || k > 6)) return skr::fail(SKR_ERR_ARG, "skr_count: in-kernel column sums are implemented for k = 4, 5, 6");
     if (a->d_spec && !a->d_post) return skr::fail(SKR_ERR_ARG, "skr_count: a speculation cell goes with a Log2.post shift");
     CountParams p{};
     p.codes = a->d_codes;

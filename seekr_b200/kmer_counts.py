@@ -423,7 +423,7 @@ class CountEngine:
                 colmin = device.empty(self.cols, torch.int32)
                 _lib.check(self.lib.skr_colmin_reset(device.ptr(colmin), self.cols, device.stream_ptr(self.stream)))
             flags = device.zeros(2, torch.int32)
-            if self.accurate_stats and self.k == 6:
+            if self.accurate_stats and 4 <= self.k <= 6:
                 # norm_vectors in ONE pass and (sharded) ONE exchange: the count kernel sums the values and the
                 # squares of every column while the rows are still in registers; binary64 finish.  Not the
                 # reference's sequential fp32 order (that is the route below), closer to the exact value.

@@ -140,3 +140,89 @@ def leiden_inputs(inputfile, mean, std, k, pearsoncutoff=0, upper_only=True, den
     if dense:
         out["adjacency"] = np.concatenate(dense_rows, axis=0)
     return out
+
+
+def kmer_leiden(inputfile, mean, std, k, algo='RBERVertexPartition', rs=1.0, pearsoncutoff=0, setseed=False,
+                edgecolormethod='gradient', edgethreshold=0.1, labelfontsize=12, plotname=None, csvfile=None):
+    """Same arguments as the reference's ``kmer_leiden`` (seekr/kmer_leiden.py:64-300).
+
+    The numeric front half -- counts, all-pairs r, threshold, edge list -- runs on the device (``leiden_inputs``);
+    the community detection is leidenalg's, on an igraph graph built from the edge list instead of from n x n Python
+    lists.  Both libraries are the reference's own dependencies and are imported here, when the function is called.
+    ``csvfile`` writes the reference's two files (``_nodes_leiden.csv``: Id, Label, Color = community number;
+    ``_edges_leiden.csv``: every upper-triangle pair with its thresholded weight); plotting (``plotname``) follows the
+    reference's networkx / matplotlib drawing when those are installed.  Both need the dense matrix on the host.
+    Returns None like the reference."""
+    import pandas as pd
+
+    inputs = leiden_inputs(inputfile, mean, std, k, pearsoncutoff=pearsoncutoff, upper_only=True,
+                           dense=bool(plotname or csvfile))
+    if inputs is None:
+        return None
+    try:
+        import igraph as ig
+        import leidenalg
+    except ImportError as exc:  # not a dependency of the hot path: say what is missing instead of failing obscurely
+        raise ImportError("kmer_leiden needs python-igraph and leidenalg for the community detection (%s); "
+                          "leiden_inputs() returns the graph they would be given" % exc)
+    names = inputs["names"]
+    graph = ig.Graph(n=len(names), edges=list(zip(inputs["rows"].tolist(), inputs["cols"].tolist())), directed=False)
+    graph.es["weight"] = inputs["weights"].tolist()
+    algos = {name: getattr(leidenalg, name) for name in
+             ("ModularityVertexPartition", "RBConfigurationVertexPartition", "RBERVertexPartition", "CPMVertexPartition",
+              "SurpriseVertexPartition", "SignificanceVertexPartition")}
+    seed = 1 if setseed is True else None
+    if algo == "SignificanceVertexPartition":
+        partition = leidenalg.find_partition(graph, algos[algo], seed=seed)
+    elif algo in ("SurpriseVertexPartition", "ModularityVertexPartition"):
+        partition = leidenalg.find_partition(graph, algos[algo], weights="weight", seed=seed)
+    else:
+        partition = leidenalg.find_partition(graph, algos[algo], weights="weight", resolution_parameter=rs, seed=seed)
+    if plotname:
+        _plot_communities(inputs, partition, edgecolormethod, edgethreshold, labelfontsize, plotname)
+    if csvfile:
+        labels, colors = [], []
+        for i, community in enumerate(partition):  # kmer_leiden.py:318-328
+            for node_index in community:
+                labels.append(names[node_index])
+                colors.append(i + 1)
+        pd.DataFrame({"Id": labels, "Label": labels, "Color": colors}).to_csv(f"{csvfile}_nodes_leiden.csv", index=False)
+        df = pd.DataFrame(inputs["adjacency"], columns=names, index=names)
+        mask = np.triu(np.ones(df.shape), k=1).astype(bool)
+        df_triu = df.where(mask).stack().reset_index()
+        df_triu.columns = ["Source", "Target", "Weight"]
+        df_triu.to_csv(f"{csvfile}_edges_leiden.csv", index=False)
+    return None
+
+
+def _plot_communities(inputs, partition, edgecolormethod, edgethreshold, labelfontsize, plotname):
+    """The reference's drawing (kmer_leiden.py:150-297): networkx spring layout, edges shaded by weight or by a
+    threshold, nodes coloured by community.  Library work on the host; needs networkx and matplotlib."""
+    import matplotlib.pyplot as plt
+    import networkx as nx
+    import pandas as pd
+
+    names = inputs["names"]
+    df = pd.DataFrame(inputs["adjacency"], columns=names, index=names)
+    graph = nx.from_pandas_adjacency(df)
+    weights = inputs["weights"]
+    if edgecolormethod == "threshold":
+        edge_colors = ["black" if w > edgethreshold else "grey" for w in weights]
+        edge_widths = [4 if w > edgethreshold else 1 for w in weights]
+    else:
+        if edgecolormethod != "gradient":
+            print("edgecolormethod must be either 'gradient' or 'threshold', use default 'gradient' now")
+        normalized = (weights - weights.min()) / (weights.max() - weights.min())
+        mapped = 0.1 + 0.9 * normalized
+        edge_colors = [(1 - w, 1 - w, 1 - w) for w in mapped]
+        edge_widths = [(1 + 3 * w) for w in mapped]
+    community_colors = plt.cm.rainbow(np.linspace(0, 1, max(partition.membership) + 1))
+    node_colors = [community_colors[c] for c in partition.membership]
+    pos = nx.spring_layout(graph, weight="weight")
+    plt.figure(figsize=(15, 15))
+    plt.gca().axis("off")
+    nx.draw_networkx_nodes(graph, pos, node_color=node_colors, node_size=500)
+    nx.draw_networkx_edges(graph, pos, edge_color=edge_colors, width=edge_widths)
+    nx.draw_networkx_labels(graph, pos, font_size=labelfontsize, font_family="sans-serif")
+    plt.tight_layout()
+    plt.savefig(f"{plotname}.pdf")

@@ -109,6 +109,26 @@ template <int WARPS> __global__ void v7_rmw32(uint32_t* out) {
     if ((threadIdx.x & 31) == 0) out[blockIdx.x * WARPS + (threadIdx.x >> 5)] = my[5];
 }
 
+// V8: key-width sweep for the small histograms of k = 4, 5 (256 / 1024 bins): red.shared on a CTA-shared histogram
+// of 2^bits bins, packed (two 16-bit sub-counters per word) or one 32-bit word per bin, optionally `rep` replicas
+// selected by lane (same-word collisions inside a warp are what slows small histograms down)
+__global__ void v8_bits(uint32_t* out, int bits, int packed, int rep) {
+    __shared__ uint32_t h[4096];
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    uint32_t s = threadIdx.x * 7919u + blockIdx.x * 104729u + 1;
+    const uint32_t mask = (1u << bits) - 1;
+    const uint32_t words = packed ? (1u << bits) / 2 : (1u << bits);
+    const uint32_t base = (threadIdx.x % rep) * words;
+    for (int it = 0; it < kIters; ++it) {
+        uint32_t k = lcg(s) & mask;
+        if (packed) atomicAdd(&h[base + (k >> 1)], 1u << ((k & 1) * 16));
+        else atomicAdd(&h[base + k], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) out[blockIdx.x] = h[5];
+}
+
 template <class F> void run(const char* name, F launch, int ctas, int threads, int sms, double ghz) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
     launch(); cudaDeviceSynchronize();
@@ -135,5 +155,15 @@ int main() {
     run("V3 tag check + rmw16 x4", [&] { v3_tag<4><<<sms * 4, 128>>>(out); }, sms * 4, 128, sms, ghz);
     run("V5 match only x4", [&] { v5_match_only<4><<<sms * 8, 128>>>(out); }, sms * 8, 128, sms, ghz);
     run("V6 lcg only x4", [&] { v6_lcg_only<4><<<sms * 8, 128>>>(out); }, sms * 8, 128, sms, ghz);
+    for (int bits : {12, 10, 8, 6}) {
+        for (int packed : {1, 0}) {
+            for (int rep : {1, 2, 4, 8}) {
+                if (((1 << bits) >> packed) * rep > 4096) continue;
+                char name[64];
+                snprintf(name, sizeof name, "V8 %2d-bit keys %s x%d", bits, packed ? "packed16" : "word32  ", rep);
+                run(name, [&] { v8_bits<<<sms * 4, 512>>>(out, bits, packed, rep); }, sms * 4, 512, sms, ghz);
+            }
+        }
+    }
     return 0;
 }
