@@ -375,6 +375,19 @@ int skr_sim_edge_offsets(const void* d_c, int c_is_f64, int64_t m, int64_t n, in
 int skr_sim_edge_fill(const void* d_c, int c_is_f64, int64_t m, int64_t n, int64_t ld, int64_t row0, double cutoff,
                       int upper_only, const int64_t* d_offsets, int32_t* d_src, int32_t* d_dst, void* d_weight,
                       void* stream);
+/* The counting half fused into the GEMM ("emit the edge list from the GEMM epilogue"):
+ * skr_pearson_gemm_edges is skr_pearson_gemm for a float32 result whose epilogue also counts, per (row, column
+ * slice), the finished r values that are edges (same predicate as skr_sim_edge_offsets) and then scans the counts
+ * into d_offsets -- the offsets pass never reads the matrix; skr_sim_edge_fill follows as usual.  symmetric != 0
+ * needs upper_only != 0 (only the tiles on and above the diagonal are computed there).
+ * skr_sim_slice_width: columns per slice for an n-column matrix; skr_sim_offsets_scan: the scan alone, for counts
+ * already sitting in d_offsets[1 ..]. */
+int skr_pearson_gemm_edges(const uint16_t* d_a_hi, const uint16_t* d_a_lo, const float* d_a_scale, int64_t m,
+                           const uint16_t* d_b_hi, const uint16_t* d_b_lo, const float* d_b_scale, int64_t n, int64_t K,
+                           double alpha, float* d_c, int64_t ldc, int symmetric, int64_t row0, double cutoff,
+                           int upper_only, int64_t* d_offsets, void* stream);
+int64_t skr_sim_slice_width(int64_t n);
+int skr_sim_offsets_scan(int64_t* d_offsets, int64_t m, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Collectives over NVLink peer memory (one process per GPU; SURVEY section 8e: the Log2.post minimum

@@ -118,6 +118,10 @@ SIGNATURES = {
     "skr_sim_threshold": (_int, [_vp, _int, _i64, _i64, _i64, _i64, _dbl, _int, _vp]),
     "skr_sim_edge_offsets": (_int, [_vp, _int, _i64, _i64, _i64, _i64, _dbl, _int, _vp, _vp]),
     "skr_sim_edge_fill": (_int, [_vp, _int, _i64, _i64, _i64, _i64, _dbl, _int, _vp, _vp, _vp, _vp, _vp]),
+    "skr_pearson_gemm_edges": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _dbl, _vp, _i64, _int, _i64, _dbl, _int,
+                                      _vp, _vp]),
+    "skr_sim_slice_width": (_i64, [_i64]),
+    "skr_sim_offsets_scan": (_int, [_vp, _i64, _vp]),
     "skr_peer_alloc": (_int, [_sz, ctypes.POINTER(_vp), _vp]),
     "skr_peer_open": (_int, [_vp, ctypes.POINTER(_vp)]),
     "skr_peer_close": (_int, [_vp]),

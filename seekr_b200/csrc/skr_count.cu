@@ -647,9 +647,11 @@ struct BatchCfg {
     static constexpr int kG = kQuads >= kWorkers ? 1 : kWorkers / kQuads;
     static constexpr int kQc = kQ > 2 ? 2 : kQ;       // quads whose vector slices are in registers at a time
     static constexpr int kChunks = kQ / kQc;
-    static constexpr int kB = K >= 7 ? 5 : (K == 6 ? 8 : 32);  // records per batch
+    static constexpr int kB = K >= 8 ? 1 : (K == 7 ? 5 : (K == 6 ? 8 : 32));  // records per batch
+    // k = 8: one 128 KB histogram is all an SM holds: no slack for the size-aligned trick (the word address is an add)
+    static constexpr bool kAligned = K <= 7;
     // histograms start at a multiple of their size (count_chunk_full): one histogram of slack
-    static constexpr size_t kSmem = (size_t)(kB + 1) * kHistBytes;
+    static constexpr size_t kSmem = (size_t)(kB + (kAligned ? 1 : 0)) * kHistBytes;
     static_assert(kQuads % 32 == 0, "a warp works on one record at a time in the epilogue (table lookups are warp shuffles)");
     static_assert((kQuads >= kWorkers && kQuads % kWorkers == 0) || kWorkers % kQuads == 0, "whole quads per thread / whole groups per CTA");
     static_assert(kB % 32 == 0 || kB < 32, "the bookkeeping warp handles the records of a batch 32 at a time");
@@ -684,20 +686,20 @@ __device__ __forceinline__ unsigned long long lds_u64(uint32_t addr) {
 }
 
 // 16 windows without a masked base and without a ragged end: no predicates
-template <int K>
+template <int K, bool kAligned = true>
 __device__ __forceinline__ void count_chunk_full(uint32_t hist_addr, uint64_t x) {
     constexpr uint32_t kMask = (1u << (2 * K)) - 1;
     constexpr uint32_t kOffMask = (kMask >> 1) << 2;
     const uint64_t same = (x ^ (x << 2)) >> (64 - 2 * (16 + K - 2));
     if (same == 0) {  // homopolymer run: one add of 16 instead of 16 colliding adds
         const uint32_t kmer = (uint32_t)(x >> (64 - 2 * K)) & kMask;
-        red_add_shared_always(hist_addr | ((kmer >> 1) * 4), 16u << ((kmer & 1) * 16));
+        red_add_shared_always(hist_addr + ((kmer >> 1) * 4), 16u << ((kmer & 1) * 16));
         return;
     }
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
         const uint32_t t = (uint32_t)(x >> (64 - 2 * (j + K) - 1));
-        red_add_shared_always((t & kOffMask) | hist_addr, (t & 2u) ? 0x10000u : 1u);
+        red_add_shared_always(kAligned ? ((t & kOffMask) | hist_addr) : ((t & kOffMask) + hist_addr), (t & 2u) ? 0x10000u : 1u);
     }
 }
 
@@ -770,17 +772,17 @@ __device__ __noinline__ void count_phase(const uint32_t* __restrict__ codes, con
         const uint32_t h = hist_addr + (uint32_t)r * kHistBytes;
         const uint64_t m64 = ((uint64_t)m0 << 32) | m1;
         if (g < whole && (m64 >> (64 - (32 + K - 1))) == 0) {
-            count_chunk_full<K>(h, ((uint64_t)w0 << 32) | w1);
-            count_chunk_full<K>(h, ((uint64_t)w1 << 32) | w2);
+            count_chunk_full<K, BatchCfg<K>::kAligned>(h, ((uint64_t)w0 << 32) | w1);
+            count_chunk_full<K, BatchCfg<K>::kAligned>(h, ((uint64_t)w1 << 32) | w2);
         } else {
             // tail slot: nwin % 32 windows, 0 = nothing to do
             const long long left = (long long)lds_u64(mt_addr + oNwin + 8 * (uint32_t)r) - (long long)u * 32;
             if (left > 0)
-                count_chunk<K, true>(h, ((uint64_t)w0 << 32) | w1, (uint32_t)(m64 >> (64 - (16 + K - 1))),
-                                     left < 16 ? (int)left : 16);
+                count_chunk<K, BatchCfg<K>::kAligned>(h, ((uint64_t)w0 << 32) | w1, (uint32_t)(m64 >> (64 - (16 + K - 1))),
+                                                      left < 16 ? (int)left : 16);
             if (left > 16)
-                count_chunk<K, true>(h, ((uint64_t)w1 << 32) | w2, (uint32_t)((m64 << 16) >> (64 - (16 + K - 1))),
-                                     left < 32 ? (int)(left - 16) : 16);
+                count_chunk<K, BatchCfg<K>::kAligned>(h, ((uint64_t)w1 << 32) | w2, (uint32_t)((m64 << 16) >> (64 - (16 + K - 1))),
+                                                      left < 32 ? (int)(left - 16) : 16);
         }
         w0 = n0; w1 = n1; w2 = n2; m0 = q0; m1 = q1; u = un; r = rn; g = gn;
     }
@@ -815,7 +817,7 @@ __global__ void __launch_bounds__(BatchCfg<K>::kThreads, BatchCfg<K>::kCtasPerSm
     const int gi = kG > 1 ? tid / Cfg::kQuads : 0;    // epilogue group: records gi, gi + kG, ... of a batch
     const int qb = kG > 1 ? tid % Cfg::kQuads : tid;  // first bin quad of this thread
     const uint32_t raw_addr = skr::smem_u32(smem_b);
-    const uint32_t hist_addr = (raw_addr + Cfg::kHistBytes - 1) & ~(uint32_t)(Cfg::kHistBytes - 1);
+    const uint32_t hist_addr = Cfg::kAligned ? ((raw_addr + Cfg::kHistBytes - 1) & ~(uint32_t)(Cfg::kHistBytes - 1)) : raw_addr;
 
     float tmin = INFINITY;
     int tnan = 0;
@@ -1103,8 +1105,9 @@ int launch_batch(const CountParams& wp, int sms, cudaStream_t stream) {
 template <int K>
 bool batch_handles(const CountParams& wp, int vec_is_f64) {
     if (K <= 6) return true;
-    return !vec_is_f64 && wp.mean && wp.std_ && wp.rstd && !wp.colmin && !wp.no_store && !wp.colsum &&
-           !(wp.post_cell && wp.min_cell);
+    if (wp.colmin || wp.no_store || wp.colsum) return false;
+    if (!wp.mean && !wp.std_ && !wp.post_cell) return true;  // plain counts
+    return !vec_is_f64 && wp.mean && wp.std_ && wp.rstd && !(wp.post_cell && wp.min_cell);
 }
 
 template <int K, bool kVecF64>
@@ -1114,6 +1117,9 @@ int dispatch_batch(const CountParams& wp, int sms, cudaStream_t stream) {
             return skr::fail(SKR_ERR_ARG, "skr_count: internal dispatch error");
         } else {
             const bool mn7 = wp.min_cell != nullptr;
+            if (!wp.mean && !wp.std_ && !wp.post_cell)
+                return mn7 ? launch_batch<K, false, kBatchPlain, true>(wp, sms, stream)
+                           : launch_batch<K, false, kBatchPlain, false>(wp, sms, stream);
             if (wp.post_cell) return launch_batch<K, false, kBatchPost, false>(wp, sms, stream);
             return mn7 ? launch_batch<K, false, kBatchFast, true>(wp, sms, stream)
                        : launch_batch<K, false, kBatchFast, false>(wp, sms, stream);
@@ -1210,7 +1216,7 @@ int launch_count(CountParams p, cudaStream_t stream) {
     // the team / batch kernels take k <= 6 with float output (and k = 7 with fp32 vectors in the fast / post
     // flavours); they leave records that are too long for them on a list which the CTA kernel then drains
     constexpr bool kTeamK = K <= 6 && sizeof(OutT) == 4;
-    constexpr bool kBatchOnly = K == 7 && sizeof(OutT) == 4 && !kVecF64;
+    constexpr bool kBatchOnly = K >= 7 && sizeof(OutT) == 4 && !kVecF64;
     const bool use_list = kTeamK || (kBatchOnly && batch_handles<K>(p, kVecF64));
     if (use_list && p.m > 0xFFFFFFFFll) return skr::fail(SKR_ERR_ARG, "skr_count: more than 2^32 records");
     unsigned int* ctr = nullptr;

@@ -402,6 +402,24 @@ extern "C" int skr_sim_edge_offsets(const void* d_c, int c_is_f64, int64_t m, in
     return SKR_OK;
 }
 
+extern "C" int64_t skr_sim_slice_width(int64_t n) { return slice_width(n); }
+
+// offsets[1 ..] holds the per-(row, slice) counts (e.g. written by the Pearson GEMM's epilogue): the scan alone
+extern "C" int skr_sim_offsets_scan(int64_t* d_offsets, int64_t m, void* stream) {
+    if (!d_offsets) return skr::fail(SKR_ERR_ARG, "skr_sim_offsets_scan: null offsets");
+    if (m <= 0) return SKR_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    long long* counts = (long long*)d_offsets + 1;
+    long long* partial = nullptr;
+    SKR_CUDA_CHECK(cudaMallocAsync(&partial, sizeof(long long) * kScanCtas, s));
+    sim_chunk_sum_kernel<<<kScanCtas, kThreads, 0, s>>>(counts, (long long)m * kSlices, partial);
+    SKR_LAUNCH_CHECK();
+    sim_chunk_scan_kernel<<<kScanCtas, kThreads, 0, s>>>(counts, (long long)m * kSlices, partial, (long long*)d_offsets);
+    SKR_LAUNCH_CHECK();
+    SKR_CUDA_CHECK(cudaFreeAsync(partial, s));
+    return SKR_OK;
+}
+
 extern "C" int skr_sim_edge_fill(const void* d_c, int c_is_f64, int64_t m, int64_t n, int64_t ld, int64_t row0,
                                  double cutoff, int upper_only, const int64_t* d_offsets, int32_t* d_src,
                                  int32_t* d_dst, void* d_weight, void* stream) {

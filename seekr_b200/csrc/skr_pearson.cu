@@ -271,6 +271,15 @@ struct GemmParams {
     long long ldc;
     int c_is_f64;
     int symmetric;  // A == B, square tiles: only tiles with tn >= tm are computed, the rest is mirrored
+    // similarity-graph edge counts fused into the epilogue (kmer_leiden.py:91-104; skr_pearson_gemm_edges): the
+    // finished r values are compared with the threshold where they are produced, so the offsets pass of the edge
+    // extraction never reads the matrix.  counts[row * SKR_SIM_SLICES + column slice]; a 256-wide tile lies inside
+    // one slice (the slice width is a multiple of 256)
+    unsigned long long* edge_counts;
+    float edge_thr;          // edge iff r >= edge_thr (skr_graph.cu: edge_threshold), off the diagonal
+    int edge_upper;          // only columns right of the diagonal
+    long long edge_row0;     // whole-matrix index of row 0 of this block
+    long long edge_width;    // slice width in columns
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -557,6 +566,10 @@ pearson_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
             if (row < p.m) {
                 const float rs = p.alpha * __ldg(p.a_scale + row);
                 const long long colbase = (long long)tn * kBN + half * 128;
+                // fused edge count: the diagonal column and the first column that may hold an edge of this row
+                const long long gdiag = p.edge_row0 + row;
+                const long long jmin = p.edge_upper ? gdiag + 1 : 0;
+                int ecnt = 0;
 #pragma unroll
                 for (int c = 0; c < 128; c += 4) {
                     const long long col0 = colbase + c;
@@ -575,11 +588,24 @@ pearson_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                                 o.x += prev.x; o.y += prev.y; o.z += prev.z; o.w += prev.w;
                             }
                             *reinterpret_cast<float4*>(dst) = o;
+                            if (p.edge_counts) {
+                                if (col0 >= jmin && (gdiag < col0 || gdiag >= col0 + 4)) {
+                                    ecnt += (o.x >= p.edge_thr) + (o.y >= p.edge_thr) + (o.z >= p.edge_thr) + (o.w >= p.edge_thr);
+                                } else {
+                                    ecnt += (o.x >= p.edge_thr && col0 + 0 != gdiag && col0 + 0 >= jmin);
+                                    ecnt += (o.y >= p.edge_thr && col0 + 1 != gdiag && col0 + 1 >= jmin);
+                                    ecnt += (o.z >= p.edge_thr && col0 + 2 != gdiag && col0 + 2 >= jmin);
+                                    ecnt += (o.w >= p.edge_thr && col0 + 3 != gdiag && col0 + 3 >= jmin);
+                                }
+                            }
                         } else {
 #pragma unroll
                             for (int i = 0; i < 4; ++i)
-                                if (col0 + i < p.n)
-                                    dst[i] = sum[c + i] * rs * __ldg(p.b_scale + col0 + i) + (p.accumulate ? dst[i] : 0.0f);
+                                if (col0 + i < p.n) {
+                                    const float o = sum[c + i] * rs * __ldg(p.b_scale + col0 + i) + (p.accumulate ? dst[i] : 0.0f);
+                                    dst[i] = o;
+                                    if (p.edge_counts) ecnt += (o >= p.edge_thr && col0 + i != gdiag && col0 + i >= jmin);
+                                }
                         }
                     } else {
                         double* dst = reinterpret_cast<double*>(p.c) + row * p.ldc + col0;
@@ -589,6 +615,7 @@ pearson_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                                 dst[i] = (double)(sum[c + i] * rs * __ldg(p.b_scale + col0 + i)) + (p.accumulate ? dst[i] : 0.0);
                     }
                 }
+                if (ecnt) atomicAdd(p.edge_counts + row * SKR_SIM_SLICES + colbase / p.edge_width, (unsigned long long)ecnt);
             }
         }
     }
@@ -736,9 +763,53 @@ extern "C" int skr_pearson_prepare(const void* d_a, int a_is_f64, int64_t rows, 
     return SKR_OK;
 }
 
+struct EdgeArgs {
+    unsigned long long* counts = nullptr;
+    float thr = 0.0f;
+    int upper = 0;
+    long long row0 = 0, width = 1;
+};
+
+static int pearson_gemm_impl(const uint16_t* d_a_hi, const uint16_t* d_a_lo, const float* d_a_scale, int64_t m,
+                             const uint16_t* d_b_hi, const uint16_t* d_b_lo, const float* d_b_scale, int64_t n,
+                             int64_t K, double alpha, void* d_c, int c_is_f64, int64_t ldc, int symmetric,
+                             const EdgeArgs& edges, void* stream);
+
 extern "C" int skr_pearson_gemm(const uint16_t* d_a_hi, const uint16_t* d_a_lo, const float* d_a_scale, int64_t m,
                                 const uint16_t* d_b_hi, const uint16_t* d_b_lo, const float* d_b_scale, int64_t n,
                                 int64_t K, double alpha, void* d_c, int c_is_f64, int64_t ldc, int symmetric, void* stream) {
+    return pearson_gemm_impl(d_a_hi, d_a_lo, d_a_scale, m, d_b_hi, d_b_lo, d_b_scale, n, K, alpha, d_c, c_is_f64, ldc,
+                             symmetric, EdgeArgs{}, stream);
+}
+
+extern "C" int skr_pearson_gemm_edges(const uint16_t* d_a_hi, const uint16_t* d_a_lo, const float* d_a_scale, int64_t m,
+                                      const uint16_t* d_b_hi, const uint16_t* d_b_lo, const float* d_b_scale, int64_t n,
+                                      int64_t K, double alpha, float* d_c, int64_t ldc, int symmetric, int64_t row0,
+                                      double cutoff, int upper_only, int64_t* d_offsets, void* stream) {
+    if (!d_offsets) return skr::fail(SKR_ERR_ARG, "skr_pearson_gemm_edges: null offsets");
+    if (symmetric && !upper_only)
+        return skr::fail(SKR_ERR_ARG, "skr_pearson_gemm_edges: the symmetric GEMM computes the upper tiles only; count both "
+                                      "orientations with skr_sim_edge_offsets on the finished matrix");
+    cudaStream_t s = (cudaStream_t)stream;
+    SKR_CUDA_CHECK(cudaMemsetAsync(d_offsets, 0, sizeof(int64_t) * (size_t)((m > 0 ? m : 0) * SKR_SIM_SLICES + 1), s));
+    if (m <= 0 || n <= 0) return SKR_OK;
+    EdgeArgs e;
+    e.counts = reinterpret_cast<unsigned long long*>(d_offsets) + 1;  // scanned in place afterwards
+    const float cut = (float)cutoff;
+    e.thr = cut > 0.0f ? cut : 1.40129846432481707e-45f;  // !(x < cut) && x > 0 as one comparison (skr_graph.cu)
+    e.upper = upper_only;
+    e.row0 = row0;
+    e.width = skr_sim_slice_width(n);
+    int rc = pearson_gemm_impl(d_a_hi, d_a_lo, d_a_scale, m, d_b_hi, d_b_lo, d_b_scale, n, K, alpha, d_c, 0, ldc, symmetric, e,
+                               stream);
+    if (rc != SKR_OK) return rc;
+    return skr_sim_offsets_scan(d_offsets, m, stream);
+}
+
+static int pearson_gemm_impl(const uint16_t* d_a_hi, const uint16_t* d_a_lo, const float* d_a_scale, int64_t m,
+                             const uint16_t* d_b_hi, const uint16_t* d_b_lo, const float* d_b_scale, int64_t n,
+                             int64_t K, double alpha, void* d_c, int c_is_f64, int64_t ldc, int symmetric,
+                             const EdgeArgs& edges, void* stream) {
     if (m <= 0 || n <= 0) return SKR_OK;
     if (symmetric && (d_a_hi != d_b_hi || d_a_lo != d_b_lo || m != n))
         return skr::fail(SKR_ERR_ARG, "skr_pearson_gemm: symmetric mode needs identical operands");
@@ -797,6 +868,14 @@ extern "C" int skr_pearson_gemm(const uint16_t* d_a_hi, const uint16_t* d_a_lo, 
     p.ldc = ldc;
     p.c_is_f64 = c_is_f64;
     p.symmetric = symmetric;
+    if (kb_first + kb_count >= total_kb) {  // the finished values exist in the last K segment only
+        p.edge_counts = edges.counts;
+        p.edge_thr = edges.thr;
+        p.edge_upper = edges.upper;
+        p.edge_row0 = edges.row0;
+        p.edge_width = edges.width;
+    }
+    if (p.edge_width <= 0) p.edge_width = 1;
     cudaStream_t s = (cudaStream_t)stream;
     rc = cg == 2 ? launch_gemm<2>(ma_hi, ma_lo, mb_hi, mb_lo, p, s) : launch_gemm<1>(ma_hi, ma_lo, mb_hi, mb_lo, p, s);
     if (rc != SKR_OK) return rc;

@@ -46,14 +46,16 @@ def threshold_similarity(sim, pearsoncutoff=0, zero_diagonal=True, row0=0):
     return dev if on_device else device.to_host(dev, pinned=False)
 
 
-def similarity_edges(sim, pearsoncutoff=0, upper_only=False, return_offsets=False, with_sources=True, row0=0):
+def similarity_edges(sim, pearsoncutoff=0, upper_only=False, return_offsets=False, with_sources=True, row0=0,
+                     offsets=None):
     """Edges of the thresholded, zero-diagonal similarity matrix without forming it (kmer_leiden.py:91-104).
 
     Returns ``(rows, cols, weights)`` as host arrays (int32, int32, sim's dtype) in row-major order: the order of
     ``np.nonzero(adj > 0)`` and ``adj[adj > 0]``.  ``upper_only`` keeps j > i (one entry per undirected edge).
     ``return_offsets`` appends the CSR row offsets (int64, m + 1).  ``row0``: ``sim`` is a block of rows of the whole
     matrix starting at row row0 (a rank's shard, or one block of a result produced block by block); ``rows`` are
-    whole-matrix indices."""
+    whole-matrix indices.  ``offsets``: the (row, slice) offsets when they exist already (the Pearson GEMM counts the
+    edges in its epilogue, ``similarity_matrix_and_offsets``): the counting pass over ``sim`` is skipped."""
     torch = device.require_cuda()
     lib = _lib.load()
     dev, _ = _device_matrix(sim)
@@ -62,9 +64,10 @@ def similarity_edges(sim, pearsoncutoff=0, upper_only=False, return_offsets=Fals
     ld = dev.stride(0) if m else n
     stream = device.stream_ptr(None)
     slices = _lib.SIM_SLICES  # offsets per (row, column slice); every slices-th value is the CSR row offset
-    offsets = device.empty((m * slices + 1,), torch.int64)
-    _lib.check(lib.skr_sim_edge_offsets(device.ptr(dev), is64, m, n, ld, int(row0), float(pearsoncutoff), int(bool(upper_only)),
-                                        device.ptr(offsets), stream))
+    if offsets is None:
+        offsets = device.empty((m * slices + 1,), torch.int64)
+        _lib.check(lib.skr_sim_edge_offsets(device.ptr(dev), is64, m, n, ld, int(row0), float(pearsoncutoff),
+                                            int(bool(upper_only)), device.ptr(offsets), stream))
     total = int(offsets[m * slices].item())  # the one host round trip: sizes the edge arrays
     cols = device.empty((total,), torch.int32)
     rows = device.empty((total,), torch.int32) if with_sources else None
@@ -83,6 +86,24 @@ def similarity_edges(sim, pearsoncutoff=0, upper_only=False, return_offsets=Fals
 
 
 _SIM_MAX_BYTES = 96 << 30  # r matrices up to this size are formed whole on the device
+
+
+def similarity_matrix_and_offsets(pa, row0, nrows, pb, out, pearsoncutoff, upper_only, symmetric=False):
+    """Rows [row0, row0 + nrows) of pearson(a, b) into ``out`` with the edge counts of kmer_leiden.py:91-104 taken in
+    the GEMM's epilogue (skr_pearson_gemm_edges): returns the (row, slice) offsets ``similarity_edges`` would
+    otherwise obtain from a pass over the matrix."""
+    import ctypes
+
+    torch = device.require_cuda()
+    lib = _lib.load()
+    kp = pa.hi.shape[1]
+    offsets = device.empty((nrows * _lib.SIM_SLICES + 1,), torch.int64)
+    _lib.check(lib.skr_pearson_gemm_edges(
+        ctypes.c_void_p(pa.hi.data_ptr() + row0 * kp * 2), ctypes.c_void_p(pa.lo.data_ptr() + row0 * kp * 2),
+        ctypes.c_void_p(pa.scale.data_ptr() + row0 * 4), nrows, device.ptr(pb.hi), device.ptr(pb.lo), device.ptr(pb.scale),
+        pb.rows, pa.K, 1.0 / pa.K, device.ptr(out), out.stride(0), int(bool(symmetric)), int(row0), float(pearsoncutoff),
+        int(bool(upper_only)), device.ptr(offsets), device.stream_ptr(None)))
+    return offsets
 
 
 def leiden_inputs(inputfile, mean, std, k, pearsoncutoff=0, upper_only=True, dense=False, block_bytes=None):
@@ -115,8 +136,14 @@ def leiden_inputs(inputfile, mean, std, k, pearsoncutoff=0, upper_only=True, den
     budget = int(block_bytes) if block_bytes else min(_SIM_MAX_BYTES, torch.cuda.mem_get_info()[0] // 2)
     if n * n * 4 <= budget:
         # the whole r matrix fits: symmetric GEMM (upper tiles + mirror), one extraction
-        sim = skr_pearson.pearson_device(prepared, prepared)
-        rows, cols, weights, offsets = similarity_edges(sim, pearsoncutoff, upper_only=upper_only, return_offsets=True)
+        if upper_only:
+            # the edge counts come out of the GEMM's epilogue: the matrix is read once (to fill the edge arrays)
+            sim = device.empty((n, n), torch.float32)
+            pre = similarity_matrix_and_offsets(prepared, 0, n, prepared, sim, pearsoncutoff, True, symmetric=True)
+        else:
+            sim, pre = skr_pearson.pearson_device(prepared, prepared), None
+        rows, cols, weights, offsets = similarity_edges(sim, pearsoncutoff, upper_only=upper_only, return_offsets=True,
+                                                        offsets=pre)
         out = {"names": names, "rows": rows, "cols": cols, "weights": weights, "offsets": offsets}
         if dense:
             out["adjacency"] = device.to_host(threshold_similarity(sim, pearsoncutoff), pinned=False)
@@ -127,8 +154,9 @@ def leiden_inputs(inputfile, mean, std, k, pearsoncutoff=0, upper_only=True, den
     parts, row_offsets, dense_rows, total = [], [np.zeros(1, dtype=np.int64)], [], 0
     for row0 in range(0, n, block):
         nrows = min(block, n - row0)
-        skr_pearson.gemm_block(prepared, row0, nrows, prepared, buf, 1.0 / prepared.K)
-        r, c, w, off = similarity_edges(buf[:nrows], pearsoncutoff, upper_only=upper_only, return_offsets=True, row0=row0)
+        pre = similarity_matrix_and_offsets(prepared, row0, nrows, prepared, buf, pearsoncutoff, upper_only)
+        r, c, w, off = similarity_edges(buf[:nrows], pearsoncutoff, upper_only=upper_only, return_offsets=True, row0=row0,
+                                        offsets=pre)
         parts.append((r, c, w))
         row_offsets.append(off[1:] + total)
         total += int(off[-1])

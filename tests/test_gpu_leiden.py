@@ -222,3 +222,41 @@ def test_full_size_properties_on_a_symmetric_matrix():
             pos += int(mask.sum().item())
         assert pos == total
     assert totals[0] == 2 * totals[1] and totals[1] > 1000000
+
+
+@pytest.mark.parametrize("cutoff", [0.0, 0.05, 0.3])
+def test_gemm_epilogue_edge_counts_equal_the_matrix_pass(cutoff):
+    """skr_pearson_gemm_edges counts the edges where the r values are produced: its offsets must be those of
+    skr_sim_edge_offsets run over the finished matrix -- symmetric GEMM (upper tiles + mirror), row blocks with a
+    row offset (general GEMM, both orientations), ragged sizes, K cut into segments."""
+    import torch
+
+    from seekr_b200 import _lib, device
+    from seekr_b200 import kmer_leiden as kl
+    from seekr_b200 import pearson as skr_pearson
+
+    rng = np.random.default_rng(17)
+    lib = _lib.load()
+    for n, K in ((700, 300), (1030, 4096), (515, 9000)):
+        x = (rng.poisson(0.7, size=(n, K)) * rng.uniform(0.2, 3, size=(n, 1))).astype(np.float32)
+        x[:, 0] += 1e-3
+        prepared = skr_pearson.prepare(x, True)
+
+        def matrix_pass(sim, row0, upper):
+            m = sim.shape[0]
+            off = device.empty((m * _lib.SIM_SLICES + 1,), torch.int64)
+            _lib.check(lib.skr_sim_edge_offsets(device.ptr(sim), 0, m, n, sim.stride(0), row0, float(cutoff), int(upper),
+                                                device.ptr(off), device.stream_ptr(None)))
+            return off
+
+        # whole matrix, symmetric, upper half
+        sim = device.empty((n, n), torch.float32)
+        fused = kl.similarity_matrix_and_offsets(prepared, 0, n, prepared, sim, cutoff, True, symmetric=True)
+        assert torch.equal(fused, matrix_pass(sim, 0, True))
+        assert torch.equal(sim, skr_pearson.pearson_device(prepared, prepared))
+        # row blocks (every tile computed), both orientations
+        for row0, nrows in ((0, 256), (256, n - 256)):
+            buf = device.empty((nrows, n), torch.float32)
+            for upper in (True, False):
+                fused = kl.similarity_matrix_and_offsets(prepared, row0, nrows, prepared, buf, cutoff, upper)
+                assert torch.equal(fused, matrix_pass(buf, row0, upper)), (n, K, row0, upper)
