@@ -268,10 +268,26 @@ __device__ __forceinline__ void red_add_shared_always(uint32_t addr, uint32_t in
 
 // kAligned: hist_addr is a multiple of the histogram size, so base | offset replaces base + offset and the
 // word address is a single three-input logic operation on the shifted k-mer.
-template <int K, bool kAligned = false>
-__device__ __forceinline__ void count_chunk(uint32_t hist_addr, uint64_t x, uint32_t mb, int nv) {
+template <int K, bool kAligned = false, int KH = K>
+__device__ __forceinline__ void count_chunk(uint32_t hist_addr, uint64_t x, uint32_t mb, int nv, uint32_t pass = 0) {
     constexpr uint32_t kMask = (1u << (2 * K)) - 1;
     constexpr uint32_t kOffMask = (kMask >> 1) << 2;  // (kmer >> 1) * 4 out of t = kmer << 1
+    if constexpr (KH != K) {
+        // split histogram (see BatchCfg): every window through the predicated path, filtered by its leading base(s)
+        constexpr uint32_t kOffH = (((1u << (2 * KH)) - 1) >> 1) << 2;
+        uint32_t bad = mb;
+#pragma unroll
+        for (int i = 1; i < K; ++i) bad |= mb << i;
+        const uint32_t ok = ~(bad >> (K - 1)) & 0xFFFFu & ~(0xFFFFu >> nv);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const uint32_t t = (uint32_t)(x >> (64 - 2 * (j + K) - 1));
+            const uint32_t sel = ((t >> (2 * KH + 1)) & ((1u << (2 * (K - KH))) - 1)) == pass;
+            red_add_shared((kAligned ? ((t & kOffH) | hist_addr) : ((t & kOffH) + hist_addr)), (t & 2u) ? 0x10000u : 1u,
+                           (ok & (0x8000u >> j)) && sel);
+        }
+        return;
+    }
     if (mb == 0 && nv == 16) {
         // all 16 + K - 1 bases equal (homopolymer run): one add of 16 instead of 16 colliding adds
         const uint64_t same = (x ^ (x << 2)) >> (64 - 2 * (16 + K - 2));
@@ -622,18 +638,24 @@ __global__ void __launch_bounds__(WarpCfg<K>::kThreads, WarpCfg<K>::kMinCtas) co
 //   bookkeeping   warp 16 draws the next batch, reads its lengths / offsets, runs the kTab-entry binary64
 //                 value chains and the unit prefix while the workers are busy (double-buffered BatchMeta).
 // ---------------------------------------------------------------------------------------------
-template <int K>
+// kSplit (k = 8 with vectors): the 65 536 columns are produced in kPasses = 4 passes of 16 384 -- pass p counts the
+// windows whose first base is p into a k = 7 sized histogram and finishes columns [p * 16 384, (p + 1) * 16 384) --
+// so that five records share a batch and the vector slices are re-read once per batch instead of once per record
+// (a single 128 KB histogram per SM left the fused flavours L2-bound at 0.38-0.42 of the HBM roofline).
+template <int K, bool kSplit = false>
 struct BatchCfg {
-    static constexpr int kBins = 1 << (2 * K);
+    static constexpr int kHK = kSplit ? K - 1 : K;     // k of the histogram a CTA holds
+    static constexpr int kPasses = kSplit ? 4 : 1;
+    static constexpr int kBins = 1 << (2 * kHK);
     static constexpr int kWords = kBins / 2;
     static constexpr int kHistBytes = kWords * 4;
     // 512 threads, two CTAs per SM = 1024 threads = 64 registers each (with a 17th warp the limit was 56 and the
     // epilogue spilled).  Every thread owns bin quads in the epilogue; in the count phase warp 15 keeps the books
     // and the other 15 warps count.
     // k = 7: 32 KB per histogram, so one CTA of 1024 threads per SM with five records per batch
-    static constexpr int kWorkers = K >= 7 ? 1024 : 512;
+    static constexpr int kWorkers = kHK >= 7 ? 1024 : 512;
     static constexpr int kThreads = kWorkers;
-    static constexpr int kCtasPerSm = K >= 7 ? 1 : 2;
+    static constexpr int kCtasPerSm = kHK >= 7 ? 1 : 2;
     static constexpr int kCounters = kWorkers - 32;
     static constexpr int kQuads = kBins / 4;
     // k = 6: a thread owns kQ = 2 quads of EVERY record.  k = 4, 5: a histogram has fewer quads than the CTA has
@@ -647,9 +669,9 @@ struct BatchCfg {
     static constexpr int kG = kQuads >= kWorkers ? 1 : kWorkers / kQuads;
     static constexpr int kQc = kQ > 2 ? 2 : kQ;       // quads whose vector slices are in registers at a time
     static constexpr int kChunks = kQ / kQc;
-    static constexpr int kB = K >= 8 ? 1 : (K == 7 ? 5 : (K == 6 ? 8 : 32));  // records per batch
+    static constexpr int kB = kHK >= 8 ? 1 : (kHK == 7 ? 5 : (kHK == 6 ? 8 : 32));  // records per batch
     // k = 8: one 128 KB histogram is all an SM holds: no slack for the size-aligned trick (the word address is an add)
-    static constexpr bool kAligned = K <= 7;
+    static constexpr bool kAligned = kHK <= 7;
     // histograms start at a multiple of their size (count_chunk_full): one histogram of slack
     static constexpr size_t kSmem = (size_t)(kB + (kAligned ? 1 : 0)) * kHistBytes;
     static_assert(kQuads % 32 == 0, "a warp works on one record at a time in the epilogue (table lookups are warp shuffles)");
@@ -663,6 +685,7 @@ struct BatchMeta {
     alignas(128) float tab[kB][kTab];  // 128-byte rows: table address | 4*count
     long long rec0;                    // first record of the batch, < 0: no more work
     int nrec;
+    int pass;                          // kSplit: which quarter of the columns this batch produces
     uint32_t prefix[kB + 1];           // whole units (32 windows) before record r
     long long nwin[kB];
     unsigned long long b0[kB];         // first 64-base block
@@ -686,20 +709,28 @@ __device__ __forceinline__ unsigned long long lds_u64(uint32_t addr) {
 }
 
 // 16 windows without a masked base and without a ragged end: no predicates
-template <int K, bool kAligned = true>
-__device__ __forceinline__ void count_chunk_full(uint32_t hist_addr, uint64_t x) {
+template <int K, bool kAligned = true, int KH = K>
+__device__ __forceinline__ void count_chunk_full(uint32_t hist_addr, uint64_t x, uint32_t pass = 0) {
     constexpr uint32_t kMask = (1u << (2 * K)) - 1;
-    constexpr uint32_t kOffMask = (kMask >> 1) << 2;
+    constexpr uint32_t kOffMask = (((1u << (2 * KH)) - 1) >> 1) << 2;  // word offset of the histogram's 2 * KH key bits
     const uint64_t same = (x ^ (x << 2)) >> (64 - 2 * (16 + K - 2));
     if (same == 0) {  // homopolymer run: one add of 16 instead of 16 colliding adds
         const uint32_t kmer = (uint32_t)(x >> (64 - 2 * K)) & kMask;
-        red_add_shared_always(hist_addr + ((kmer >> 1) * 4), 16u << ((kmer & 1) * 16));
+        if (KH == K || (kmer >> (2 * KH)) == pass) {
+            const uint32_t key = kmer & ((1u << (2 * KH)) - 1);
+            red_add_shared_always(hist_addr + ((key >> 1) * 4), 16u << ((key & 1) * 16));
+        }
         return;
     }
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-        const uint32_t t = (uint32_t)(x >> (64 - 2 * (j + K) - 1));
-        red_add_shared_always(kAligned ? ((t & kOffMask) | hist_addr) : ((t & kOffMask) + hist_addr), (t & 2u) ? 0x10000u : 1u);
+        const uint32_t t = (uint32_t)(x >> (64 - 2 * (j + K) - 1));  // k-mer << 1
+        const uint32_t addr = kAligned ? ((t & kOffMask) | hist_addr) : ((t & kOffMask) + hist_addr);
+        if constexpr (KH == K) {
+            red_add_shared_always(addr, (t & 2u) ? 0x10000u : 1u);
+        } else {  // only the windows whose leading base(s) select this pass
+            red_add_shared(addr, (t & 2u) ? 0x10000u : 1u, ((t >> (2 * KH + 1)) & ((1u << (2 * (K - KH))) - 1)) == pass);
+        }
     }
 }
 
@@ -707,13 +738,13 @@ __device__ __forceinline__ void count_chunk_full(uint32_t hist_addr, uint64_t x)
 // current and of the next unit, the unit bookkeeping) are allocated apart from the epilogue's, which holds the
 // thread's slices of the mean / std / 1/std vectors; in one body the two sets together exceeded the 56 registers a
 // thread may have with 2 x 544 threads per SM, and the compiler spilled inside both hot loops.
-template <int K, int kB, int kW>
+template <int K, int kB, int kW, int KH, bool kAligned>
 __device__ __noinline__ void count_phase(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ mask,
-                                         uint32_t mt_addr, uint32_t hist_addr, int tid) {
+                                         uint32_t mt_addr, uint32_t hist_addr, int tid, uint32_t pass) {
     // mt_addr: shared-window address of the batch's BatchMeta (explicit ld.shared: a generic reference would make
     // every access a generic load in an out-of-line function)
     using Meta = BatchMeta<kB>;
-    constexpr uint32_t kHistBytes = (1u << (2 * K)) * 2;
+    constexpr uint32_t kHistBytes = (1u << (2 * KH)) * 2;
     constexpr uint32_t oPrefix = offsetof(Meta, prefix), oNwin = offsetof(Meta, nwin), oB0 = offsetof(Meta, b0);
     const uint32_t whole = lds_u32(mt_addr + oPrefix + 4 * kB);
     const uint32_t total = whole + kB;  // whole units first, then one tail slot per record
@@ -772,17 +803,17 @@ __device__ __noinline__ void count_phase(const uint32_t* __restrict__ codes, con
         const uint32_t h = hist_addr + (uint32_t)r * kHistBytes;
         const uint64_t m64 = ((uint64_t)m0 << 32) | m1;
         if (g < whole && (m64 >> (64 - (32 + K - 1))) == 0) {
-            count_chunk_full<K, BatchCfg<K>::kAligned>(h, ((uint64_t)w0 << 32) | w1);
-            count_chunk_full<K, BatchCfg<K>::kAligned>(h, ((uint64_t)w1 << 32) | w2);
+            count_chunk_full<K, kAligned, KH>(h, ((uint64_t)w0 << 32) | w1, pass);
+            count_chunk_full<K, kAligned, KH>(h, ((uint64_t)w1 << 32) | w2, pass);
         } else {
             // tail slot: nwin % 32 windows, 0 = nothing to do
             const long long left = (long long)lds_u64(mt_addr + oNwin + 8 * (uint32_t)r) - (long long)u * 32;
             if (left > 0)
-                count_chunk<K, BatchCfg<K>::kAligned>(h, ((uint64_t)w0 << 32) | w1, (uint32_t)(m64 >> (64 - (16 + K - 1))),
-                                                      left < 16 ? (int)left : 16);
+                count_chunk<K, kAligned, KH>(h, ((uint64_t)w0 << 32) | w1, (uint32_t)(m64 >> (64 - (16 + K - 1))),
+                                             left < 16 ? (int)left : 16, pass);
             if (left > 16)
-                count_chunk<K, BatchCfg<K>::kAligned>(h, ((uint64_t)w1 << 32) | w2, (uint32_t)((m64 << 16) >> (64 - (16 + K - 1))),
-                                                      left < 32 ? (int)(left - 16) : 16);
+                count_chunk<K, kAligned, KH>(h, ((uint64_t)w1 << 32) | w2, (uint32_t)((m64 << 16) >> (64 - (16 + K - 1))),
+                                             left < 32 ? (int)(left - 16) : 16, pass);
         }
         w0 = n0; w1 = n1; w2 = n2; m0 = q0; m1 = q1; u = un; r = rn; g = gn;
     }
@@ -796,9 +827,9 @@ __device__ __noinline__ void count_phase(const uint32_t* __restrict__ codes, con
 //   kBatchAny    everything decided at run time.
 enum { kBatchAny = 0, kBatchPlain = 1, kBatchFast = 2, kBatchPost = 3 };
 
-template <int K, bool kVecF64, int kMode, bool kMin, bool kColmin = false, bool kStats = false>
-__global__ void __launch_bounds__(BatchCfg<K>::kThreads, BatchCfg<K>::kCtasPerSm) count_batch_kernel(const CountParams p) {
-    using Cfg = BatchCfg<K>;
+template <int K, bool kVecF64, int kMode, bool kMin, bool kColmin = false, bool kStats = false, bool kSplit = false>
+__global__ void __launch_bounds__(BatchCfg<K, kSplit>::kThreads, BatchCfg<K, kSplit>::kCtasPerSm) count_batch_kernel(const CountParams p) {
+    using Cfg = BatchCfg<K, kSplit>;
     constexpr int kB = Cfg::kB, kW = Cfg::kWorkers, kQ = Cfg::kQ, kG = Cfg::kG, kQc = Cfg::kQc, kChunks = Cfg::kChunks;
     static_assert(kChunks == 1 || (!kColmin && !kStats && kMode != kBatchAny),
                   "k = 7 runs the plain, fast and post flavours here; the others stay with the CTA-per-record kernel");
@@ -828,9 +859,14 @@ __global__ void __launch_bounds__(BatchCfg<K>::kThreads, BatchCfg<K>::kCtasPerSm
     int zoff = -1;       // byte offset of that column's histogram word inside a record's histogram
     uint32_t zsh = 0;
     uint32_t zseen = 0;
+    int zpass = 0;  // kSplit: the pass whose columns hold the arg-min column
     if ((kMode == kBatchAny || kMode == kBatchPost) && p.spec) {
-        const int zc = p.spec->zero_col;
-        if (zc >= 0 && (kG > 1 ? (zc >> 2) == qb : ((zc >> 2) % kW) == tid)) { zoff = (zc >> 1) * 4; zsh = (uint32_t)(zc & 1) * 16u; }
+        int zc = p.spec->zero_col;
+        if (zc >= 0) {
+            zpass = zc / Cfg::kBins;
+            zc -= zpass * Cfg::kBins;  // column inside the pass
+            if (kG > 1 ? (zc >> 2) == qb : ((zc >> 2) % kW) == tid) { zoff = (zc >> 1) * 4; zsh = (uint32_t)(zc & 1) * 16u; }
+        }
     }
 
     // this thread's slices of the vectors (fp32 vectors only; binary64 vectors are read in the epilogue)
@@ -844,10 +880,10 @@ __global__ void __launch_bounds__(BatchCfg<K>::kThreads, BatchCfg<K>::kCtasPerSm
         for (int e = 0; e < 4; ++e) { cmin[j][e] = 0xFFFFFFFFu; sx[j][e] = 0.f; sq[j][e] = 0.f; }
     }
     // the thread's slices of the vectors for the quads of chunk `ch` (fp32 vectors)
-    auto load_vectors = [&](int ch) {
+    auto load_vectors = [&](int ch, int pass) {
 #pragma unroll
         for (int j = 0; j < kQc; ++j) {
-            const int q = qb + (ch * kQc + j) * kW;
+            const int q = pass * Cfg::kQuads + qb + (ch * kQc + j) * kW;
             if constexpr (kRegVec) {  // all three vectors are there (dispatch): unconditional, negated once
                 const float4 m4 = __ldg(reinterpret_cast<const float4*>(p.mean) + q);
                 const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.std_) + q);
@@ -862,7 +898,7 @@ __global__ void __launch_bounds__(BatchCfg<K>::kThreads, BatchCfg<K>::kCtasPerSm
         }
     };
     if (worker) {
-        if constexpr (!kVecF64 && kMode != kBatchPlain && kChunks == 1) load_vectors(0);  // once per kernel
+        if constexpr (!kVecF64 && kMode != kBatchPlain && kChunks == 1) load_vectors(0, 0);  // once per kernel
         uint4* h4 = reinterpret_cast<uint4*>(smem_b + (hist_addr - raw_addr) / 4);
         for (int i = tid; i < kB * Cfg::kWords / 4; i += kW) h4[i] = make_uint4(0, 0, 0, 0);
     }
@@ -873,6 +909,10 @@ __global__ void __launch_bounds__(BatchCfg<K>::kThreads, BatchCfg<K>::kCtasPerSm
         long long b = 0;
         if (lane == 0) b = (long long)atomicAdd(p.work_counter, 1u);
         b = __shfl_sync(0xFFFFFFFFu, b, 0);
+        // kSplit: work item = (pass, batch), passes outermost
+        const long long nbatches = (p.m + kB - 1) / kB;
+        const int pass = Cfg::kPasses > 1 ? (int)(b / nbatches) : 0;
+        if (Cfg::kPasses > 1) b = pass < Cfg::kPasses ? b - pass * nbatches : nbatches;
         const long long rec0 = b * kB;
         const int nrec = rec0 < p.m ? (int)min((long long)kB, p.m - rec0) : 0;
         uint32_t carry = 0;  // whole units of the records handled in earlier rounds
@@ -890,7 +930,7 @@ __global__ void __launch_bounds__(BatchCfg<K>::kThreads, BatchCfg<K>::kCtasPerSm
                     b0 = __ldg(p.blk_off + rec);
                     store = 1;
                     if (nwin > kLongWin) {
-                        p.long_list[atomicAdd(p.long_count, 1u)] = (uint32_t)rec;
+                        if (pass == 0) p.long_list[atomicAdd(p.long_count, 1u)] = (uint32_t)rec;  // listed once
                         store = 0;
                         nwin = 0;
                     }
@@ -925,6 +965,7 @@ __global__ void __launch_bounds__(BatchCfg<K>::kThreads, BatchCfg<K>::kCtasPerSm
             mt.prefix[0] = 0;
             mt.rec0 = nrec > 0 ? rec0 : -1;
             mt.nrec = nrec;
+            mt.pass = pass;
         }
     };
 
@@ -937,7 +978,7 @@ __global__ void __launch_bounds__(BatchCfg<K>::kThreads, BatchCfg<K>::kCtasPerSm
         if (!counter) {
             produce((it + 1) & 1);
         } else {
-            count_phase<K, kB, Cfg::kCounters>(p.codes, p.mask, skr::smem_u32(&mt), hist_addr, tid);
+            count_phase<K, kB, Cfg::kCounters, Cfg::kHK, Cfg::kAligned>(p.codes, p.mask, skr::smem_u32(&mt), hist_addr, tid, (uint32_t)mt.pass);
         }
         __syncthreads();
         if (worker) {
@@ -945,14 +986,17 @@ __global__ void __launch_bounds__(BatchCfg<K>::kThreads, BatchCfg<K>::kCtasPerSm
             const int nrec = mt.nrec;
 #pragma unroll 1
             for (int ch = 0; ch < kChunks; ++ch) {
-            if constexpr (!kVecF64 && kMode != kBatchPlain && kChunks > 1) load_vectors(ch);  // once per batch and chunk
+            if constexpr (!kVecF64 && kMode != kBatchPlain && kChunks > 1) load_vectors(ch, mt.pass);  // once per batch and chunk
             for (int r = gi; r < nrec; r += kG) {
                 if (!mt.store[r]) continue;
                 const uint32_t tab_addr = skr::smem_u32(&mt.tab[r][0]);
                 const float treg = lds_f32(tab_addr + (uint32_t)lane * 4);  // lane c holds the value of a bin seen c times
                 const uint32_t hrec = hist_addr + (uint32_t)r * Cfg::kHistBytes;
-                float* __restrict__ orow = reinterpret_cast<float*>(p.out) + (size_t)(mt.rec0 + r) * (size_t)p.ld_out;
-                if (ch == 0 && zoff >= 0 && ((lds_u32(hrec + (uint32_t)zoff) >> zsh) & 0xFFFFu) == 0) zseen = 1;
+                float* __restrict__ orow = reinterpret_cast<float*>(p.out) + (size_t)(mt.rec0 + r) * (size_t)p.ld_out +
+                                           (Cfg::kPasses > 1 ? (size_t)mt.pass * Cfg::kBins : 0);
+                if (ch == 0 && zoff >= 0 && (Cfg::kPasses == 1 || mt.pass == zpass) &&
+                    ((lds_u32(hrec + (uint32_t)zoff) >> zsh) & 0xFFFFu) == 0)
+                    zseen = 1;
 #pragma unroll
                 for (int j = 0; j < kQc; ++j) {
                     const int q = qb + (ch * kQc + j) * kW;
@@ -1086,16 +1130,16 @@ __global__ void __launch_bounds__(BatchCfg<K>::kThreads, BatchCfg<K>::kCtasPerSm
     }
 }
 
-template <int K, bool kVecF64, int kMode, bool kMin, bool kColmin = false, bool kStats = false>
+template <int K, bool kVecF64, int kMode, bool kMin, bool kColmin = false, bool kStats = false, bool kSplit = false>
 int launch_batch(const CountParams& wp, int sms, cudaStream_t stream) {
-    using B = BatchCfg<K>;
-    auto bkern = count_batch_kernel<K, kVecF64, kMode, kMin, kColmin, kStats>;
+    using B = BatchCfg<K, kSplit>;
+    auto bkern = count_batch_kernel<K, kVecF64, kMode, kMin, kColmin, kStats, kSplit>;
     SKR_CUDA_CHECK(cudaFuncSetAttribute(bkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B::kSmem));
     int bper_sm = 0;
     SKR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bper_sm, bkern, B::kThreads, B::kSmem));
     if (bper_sm < 1) return skr::fail(SKR_ERR_CUDA, "batch count kernel for k=%d does not fit on this device", K);
     long long bgrid = (long long)sms * bper_sm;
-    const long long bneed = (wp.m + B::kB - 1) / B::kB;
+    const long long bneed = (wp.m + B::kB - 1) / B::kB * B::kPasses;
     if (bgrid > bneed) bgrid = bneed;
     bkern<<<(unsigned)bgrid, B::kThreads, B::kSmem, stream>>>(wp);
     return SKR_OK;
@@ -1120,9 +1164,10 @@ int dispatch_batch(const CountParams& wp, int sms, cudaStream_t stream) {
             if (!wp.mean && !wp.std_ && !wp.post_cell)
                 return mn7 ? launch_batch<K, false, kBatchPlain, true>(wp, sms, stream)
                            : launch_batch<K, false, kBatchPlain, false>(wp, sms, stream);
-            if (wp.post_cell) return launch_batch<K, false, kBatchPost, false>(wp, sms, stream);
-            return mn7 ? launch_batch<K, false, kBatchFast, true>(wp, sms, stream)
-                       : launch_batch<K, false, kBatchFast, false>(wp, sms, stream);
+            constexpr bool kSp = K == 8;  // k = 8 with vectors: four column passes over a k = 7 sized histogram
+            if (wp.post_cell) return launch_batch<K, false, kBatchPost, false, false, false, kSp>(wp, sms, stream);
+            return mn7 ? launch_batch<K, false, kBatchFast, true, false, false, kSp>(wp, sms, stream)
+                       : launch_batch<K, false, kBatchFast, false, false, false, kSp>(wp, sms, stream);
         }
     } else {
     const bool plain = !wp.mean && !wp.std_ && !wp.post_cell && !wp.no_store;
