@@ -292,9 +292,30 @@ class Ctx:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
         return [float(v) for v in t.cpu()]
 
-    def timed(self, fn, reps, warm=1):
+    def align(self):
+        """A barrier ON THE DEVICE (single-warp kernel over NVLink peer memory, csrc/skr_peer.cu): enqueued right
+        before a start event, it lets the GPUs of all ranks leave within a microsecond of each other, and the host
+        enqueues the timed launches while it spins.  Without it a timed region that contains a collective measures
+        the jitter of the host barrier (tens of microseconds) on top of the step: the collective ends on every rank
+        when the LAST rank has arrived, the start event is per rank."""
+        if self.world == 1:
+            return
+        from seekr_b200 import parallel
+
+        if not hasattr(self, "_align"):
+            class _Cell:
+                pass
+
+            self._align_peer = parallel.PeerMinExchange()
+            self._align = _Cell()
+            self._align.min_cell = _Cell()
+            self._align.min_cell.t = self.torch.zeros(2, dtype=self.torch.int32, device=self.dev)
+            self._align.stream = None
+        self._align_peer.exchange(self._align)
+
+    def timed(self, fn, reps, warm=1, align=False):
         """Median over `reps` of fn()'s device time (events on the current stream, L2 flushed, barrier on both sides),
-        max over ranks."""
+        max over ranks.  align: device-side barrier right before the start event (see align())."""
         torch = self.torch
         ts = []
         for it in range(warm + reps):
@@ -302,6 +323,8 @@ class Ctx:
             torch.cuda.synchronize()
             self.barrier()
             a, b = self.ev(), self.ev()
+            if align:
+                self.align()
             a.record()
             fn()
             b.record()
@@ -336,8 +359,10 @@ def leg_strong_250k(cx, letters_all, offs_all, shard, dpk_shard):
     std_h = device.to_host(std_vec.t, pinned=False)
     mean_b, std_b = DeviceVector.from_host(mean_h, cols), DeviceVector.from_host(std_h, cols)
     reps = 5
-    t_a = cx.timed(lambda: eng_a.run(dpk_shard, True, True, out=out_a, reducer=reducer, vectors_only=True), reps)
-    t_b = cx.timed(lambda: eng_b.run(dpk_shard, mean_b, std_b, out=out_b, reducer=reducer), reps)
+    t_a = cx.timed(lambda: eng_a.run(dpk_shard, True, True, out=out_a, reducer=reducer, vectors_only=True), reps, align=True)
+    t_b = cx.timed(lambda: eng_b.run(dpk_shard, mean_b, std_b, out=out_b, reducer=reducer), reps, align=True)
+    t_a_host = cx.timed(lambda: eng_a.run(dpk_shard, True, True, out=out_a, reducer=reducer, vectors_only=True), reps)
+    t_b_host = cx.timed(lambda: eng_b.run(dpk_shard, mean_b, std_b, out=out_b, reducer=reducer), reps)
     held = bool(eng_b.spec.held()) if eng_b.spec is not None else None
     if reducer is not None:
         reducer.check()
@@ -346,7 +371,12 @@ def leg_strong_250k(cx, letters_all, offs_all, shard, dpk_shard):
            "value": m_all / (t_b * 1e-3), "unit": "transcripts/s",
            "norm_vectors_value": m_all / (t_a * 1e-3),
            "log2_post": "one pass, speculated shift %s" % ("held" if held else "FAILED: two-pass fallback ran"),
-           "exchanges_per_step": {"norm_vectors": 0 if cx.world == 1 else 1, "count_norm": 0 if cx.world == 1 else 1}}
+           "exchanges_per_step": {"norm_vectors": 0 if cx.world == 1 else 1, "count_norm": 0 if cx.world == 1 else 1},
+           "timing": "CUDA events per rank, max over ranks; at N > 1 a device-side barrier (peer-memory kernel) sits right "
+                     "before the start event, so the ranks' GPUs start together and the launches are already enqueued; "
+                     "host_barrier_only_ms = the same without it (adds the skew of the host barrier to a step that ends "
+                     "with a collective)",
+           "host_barrier_only_ms": {"norm_vectors": t_a_host, "count_norm": t_b_host}}
     state = {"out_b": out_b, "mean_h": mean_h, "std_h": std_h, "eng_b": eng_b, "mean_b": mean_b, "std_b": std_b}
     # the same job on ONE GPU, in this run (rank 0; the other ranks wait)
     single = None

@@ -419,6 +419,12 @@ int skr_min_exchange_skip(SkrMinCell* d_cell, void* const* d_peers, int world, i
  *                      flag) in ONE kernel: P2P stores of the partials into every peer, an epoch flag per rank, a
  *                      rank-ordered sum (all ranks get the same bits).  Peer buffers hold
  *                      skr_colstat_exchange_bytes(world, n_cap) bytes, zero-initialised (skr_peer_alloc). */
+/* skr_colsum_exchange    the ONE exchange of the accurate column statistics (d_colsum / d_colsq of skr_count_ex, laid out as
+ *                      [2][cols] doubles in d_acc) fused with skr_colstat_finish: same protocol and buffers as
+ *                      skr_colstat_exchange with n_cap >= 2 * cols; d_flags[2] is NOT cleared here. */
+int skr_colsum_exchange(const double* d_acc, void* const* d_peers, int world, int rank, uint64_t epoch, int64_t cols,
+                        int64_t n_cap, int64_t total_rows, float* d_mean, float* d_std, int* d_flags, int* d_err,
+                        void* stream);
 int64_t skr_colstat_exchange_bytes(int world, int64_t n_cap);
 int skr_colstat_exchange(const double* d_acc, void* const* d_peers, int world, int rank, uint64_t epoch, int64_t n,
                          int64_t n_cap, int64_t total_rows, int take_sqrt, float* d_out, int* d_flag, int* d_err,

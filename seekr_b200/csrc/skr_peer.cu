@@ -160,7 +160,101 @@ __global__ void __launch_bounds__(256) colstat_exchange_kernel(const double* __r
     }
 }
 
+// The ONE exchange of the accurate column statistics (skr_count_ex's d_colsum / d_colsq) fused with their finish:
+// acc = [2][cols] binary64 (sum, sum of squares).  Same protocol and buffer layout as colstat_exchange_kernel with
+// n = 2 * cols values; thread j finishes column j: mean = S1 / rows, std = sqrt(max(S2 / rows - mean^2, 0)).
+__global__ void __launch_bounds__(256) colsum_exchange_kernel(const double* __restrict__ acc, unsigned char* const* peers,
+                                                              int world, int rank, unsigned long long epoch, long long cols,
+                                                              long long n_cap, long long total_rows, float* __restrict__ mean,
+                                                              float* __restrict__ std_, int* flags, int* err,
+                                                              unsigned long long kSpinLimitNs) {
+    const unsigned long long parity = epoch & 1ull;
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t flags_off = (size_t)2 * world * n_cap * sizeof(double);
+    const size_t counter_off = flags_off + (size_t)2 * world * sizeof(unsigned long long);
+    if (j < cols) {
+        const double s1 = acc[j], s2 = acc[cols + j];
+        for (int t = 0; t < world; ++t) {
+            double* dst = reinterpret_cast<double*>(peers[t]) + (parity * world + rank) * n_cap;
+            asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(dst + j), "d"(s1) : "memory");
+            asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(dst + cols + j), "d"(s2) : "memory");
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ int s_bad;
+    if (threadIdx.x == 0) {
+        s_bad = 0;
+        unsigned int* counter = reinterpret_cast<unsigned int*>(peers[rank] + counter_off);
+        const unsigned int done = atomicAdd(counter, 1u);
+        if (done == gridDim.x - 1) {
+            *counter = 0u;
+            __threadfence_system();
+            for (int t = 0; t < world; ++t) {
+                unsigned long long* f = reinterpret_cast<unsigned long long*>(peers[t] + flags_off) + parity * world + rank;
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
+            }
+        }
+        const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(peers[rank] + flags_off) + parity * world;
+        const unsigned long long t0 = globaltimer_ns();
+        for (int t = 0; t < world; ++t) {
+            for (;;) {
+                unsigned long long f;
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(mine + t) : "memory");
+                if (f == epoch) break;
+                if (globaltimer_ns() - t0 > kSpinLimitNs) {
+                    atomicExch(err, 1);
+                    s_bad = 1;
+                    break;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (j >= cols || s_bad) return;
+    const double* slices = reinterpret_cast<const double*>(peers[rank]) + parity * world * n_cap;
+    double s1 = 0.0, s2 = 0.0;
+    for (int t = 0; t < world; ++t) {
+        double a, b;
+        asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(a) : "l"(slices + (size_t)t * n_cap + j) : "memory");
+        asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(b) : "l"(slices + (size_t)t * n_cap + cols + j) : "memory");
+        s1 += a;
+        s2 += b;
+    }
+    const double mu = s1 / (double)total_rows;
+    double var = s2 / (double)total_rows - mu * mu;
+    if (var < 0.0) var = 0.0;
+    const float mf = (float)mu, sf = (float)sqrt(var);
+    if (mean) mean[j] = mf;
+    if (std_) std_[j] = sf;
+    if (flags) {
+        int fm = 0, fs = 0;
+        if (!(mf - mf == 0.0f)) fm |= 1;
+        if (!(sf - sf == 0.0f)) fs |= 1;
+        if (!(sf > 0.0f)) fs |= 2;
+        if (fm) atomicOr(&flags[0], fm);
+        if (fs) atomicOr(&flags[1], fs);
+    }
+}
+
 }  // namespace
+
+extern "C" int skr_colsum_exchange(const double* d_acc, void* const* d_peers, int world, int rank, uint64_t epoch, int64_t cols,
+                                   int64_t n_cap, int64_t total_rows, float* d_mean, float* d_std, int* d_flags, int* d_err,
+                                   void* stream) {
+    if (cols <= 0) return SKR_OK;
+    if (!d_acc || !d_peers || !d_err || total_rows <= 0) return skr::fail(SKR_ERR_ARG, "skr_colsum_exchange: bad argument");
+    if (world < 1 || world > 64 || rank < 0 || rank >= world || 2 * cols > n_cap)
+        return skr::fail(SKR_ERR_ARG, "skr_colsum_exchange: bad world / rank / capacity");
+    if (epoch == 0) return skr::fail(SKR_ERR_ARG, "skr_colsum_exchange: epoch starts at 1");
+    const long long blocks = (cols + 255) / 256;
+    if (blocks > 148 * 4) return skr::fail(SKR_ERR_ARG, "skr_colsum_exchange: vector too long for a co-resident grid");
+    colsum_exchange_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_acc, (unsigned char* const*)d_peers, world, rank,
+                                                                               epoch, cols, n_cap, total_rows, d_mean, d_std,
+                                                                               d_flags, d_err, spin_limit_ns());
+    SKR_LAUNCH_CHECK();
+    return SKR_OK;
+}
 
 extern "C" int skr_peer_alloc(size_t bytes, void** d_out, unsigned char* handle64) {
     if (!d_out || !handle64 || bytes == 0) return skr::fail(SKR_ERR_ARG, "skr_peer_alloc: bad argument");

@@ -39,6 +39,9 @@ def alphabet_lut(alphabet="AGTC"):
     return lut
 
 
+_LOWER_TO_INVALID = bytes(0 if ord("a") <= b <= ord("z") else b for b in range(256))
+
+
 def default_pack_threads():
     """Host threads for the packer: all cores, divided among the ranks of a torchrun launch on this node."""
     cores = os.cpu_count() or 1
@@ -111,7 +114,10 @@ class PackedFasta:
         offs = np.zeros(len(seqs) + 1, dtype=np.int64)
         if len(seqs):
             np.cumsum([len(s) for s in seqs], out=offs[1:])
-        joined = "".join(seqs).encode("latin-1", "replace")
+        # The reference upper-cases what it reads from a FASTA file (fasta_reader.py:55,62) but takes hand-assigned
+        # ``seqs`` and the ``seq`` of occurrences(row, seq) as they are: a lower-case letter is then simply not in
+        # the k-mer map (kmer_counts.py:146-147).  The packer folds case, so lower-case letters are made invalid here.
+        joined = "".join(seqs).encode("latin-1", "replace").translate(_LOWER_TO_INVALID)
         letters = np.frombuffer(joined, dtype=np.uint8) if joined else np.zeros(1, dtype=np.uint8)
         out = ctypes.c_void_p()
         rc = lib.skr_pack_sequences(ctypes.c_void_p(letters.ctypes.data), ctypes.c_void_p(offs.ctypes.data),

@@ -366,6 +366,11 @@ class CountEngine:
         and ``min_allreduce(engine)``; None means all rows live on this device.
         """
         torch = self.torch
+        if self.stream is not None and torch.cuda.current_stream() != self.stream:
+            # torch-side work (allocations' stream ownership, dtype conversions, host reads, collectives) must sit
+            # on the engine's stream like the library's launches do
+            with torch.cuda.stream(self.stream):
+                return self.run(dpk, mean, std, out=out, reducer=reducer, vectors_only=vectors_only)
         m = dpk.m
         if out is None:
             out = device.empty((m, self.cols), torch.float32)
@@ -450,14 +455,17 @@ class CountEngine:
                 # reference's sequential fp32 order (that is the route below), closer to the exact value.
                 sums = device.zeros((2, self.cols), torch.float64)
                 self.count(dpk, out, colmin=colmin, colsums=(sums[0], sums[1]))
-                if reducer:
-                    reducer.sum_allreduce(sums)
                 total = reducer.total_rows(m, out.device) if reducer else m
                 mean_t = device.empty(self.cols, torch.float32) if mean is True else None
                 std_t = device.empty(self.cols, torch.float32) if std is True else None
-                _lib.check(self.lib.skr_colstat_finish(device.ptr(sums[0]), device.ptr(sums[1]), self.cols, total,
-                                                       device.ptr(mean_t), device.ptr(std_t), device.ptr(flags),
-                                                       device.stream_ptr(self.stream)))
+                # sharded: exchange + finish in one peer-memory kernel when the ranks share NVLink, else one NCCL
+                # all-reduce and the finish kernel
+                if not (reducer and reducer.sums_finish(self, sums, total, mean_t, std_t, flags)):
+                    if reducer:
+                        reducer.sum_allreduce(sums)
+                    _lib.check(self.lib.skr_colstat_finish(device.ptr(sums[0]), device.ptr(sums[1]), self.cols, total,
+                                                           device.ptr(mean_t), device.ptr(std_t), device.ptr(flags),
+                                                           device.stream_ptr(self.stream)))
                 if mean is True:
                     mean_vec = DeviceVector(mean_t, False, flag=flags[0:1])
                 if std is True:

@@ -183,6 +183,17 @@ class PeerColStatExchange(_PeerBuffer):
                                                  acc.numel(), self.cols, int(total_rows), int(take_sqrt), device.ptr(out),
                                                  device.ptr(flag), device.ptr(self.err), device.stream_ptr(engine.stream)))
 
+    def sums_finish(self, engine, sums, total_rows, mean_out, std_out, flags):
+        """sums: [2][cols] binary64 (column sums and sums of squares of this rank's rows) -> mean / std over all
+        ranks, exchange and finish in one kernel (skr_colsum_exchange); needs a buffer built for 2 * cols values."""
+        from . import _lib, device
+
+        self.epoch += 1
+        cols = sums.shape[1]
+        _lib.check(self.lib.skr_colsum_exchange(device.ptr(sums), device.ptr(self.table), self.world, self.rank, self.epoch,
+                                                cols, self.cols, int(total_rows), device.ptr(mean_out), device.ptr(std_out),
+                                                device.ptr(flags), device.ptr(self.err), device.stream_ptr(engine.stream)))
+
     def check(self):
         super().check("column-statistics exchange")
 
@@ -222,6 +233,18 @@ class _Base:
         """The ONE exchange of the accurate column statistics: 2 * 4^k binary64 column sums (kmer_counts.py:168,174
         couple all rows), one all-reduce over NVLink."""
         self.dist.all_reduce(sums, group=self.group)
+
+    def sums_finish(self, engine, sums, total_rows, mean_out, std_out, flags):
+        """Exchange + finish of the accurate column statistics in ONE kernel over NVLink peer memory
+        (skr_colsum_exchange); returns False when the peer path is not available (the caller then uses
+        sum_allreduce + skr_colstat_finish)."""
+        if not sums.is_cuda:
+            return False
+        peer = self._colstat_peer(2 * sums.shape[1]) if hasattr(self, "_colstat_peer") else None
+        if peer is None:
+            return False
+        peer.sums_finish(engine, sums, total_rows, mean_out, std_out, flags)
+        return True
 
     def flag_or(self, engine, spec):
         """OR of the "zero seen" flags of the speculative Log2.post route over the ranks: the (zero_col, zero_seen)

@@ -736,3 +736,16 @@ def test_full_size_log2_post_against_the_oracle():
     eng2.speculative = False
     dev2, _, _ = eng2.run(dpk, DeviceVector.from_host(mean, 4 ** k), DeviceVector.from_host(std, 4 ** k))
     assert torch.equal(dev, dev2)
+
+
+def test_hand_assigned_lower_case_is_not_upper_cased():
+    """The reference upper-cases FASTA input (fasta_reader.py:55,62) but not hand-assigned ``seqs`` or the ``seq`` of
+    occurrences(): a lower-case letter there is simply missing from the k-mer map (kmer_counts.py:146-147)."""
+    seq = "ACGTacgtACGTTTGACA"
+    counter = make(k=2, mean=False, std=False, log2=Log2.none)
+    row = counter.occurrences(np.zeros(16, dtype=np.float64), seq)
+    assert np.array_equal(row, po.occurrences(seq, 2))
+    assert row.sum() < po.occurrences(seq.upper(), 2).sum()
+    counter.seqs = [seq, seq.upper()]
+    counter.get_counts()
+    assert np.array_equal(counter.counts, c_oracle.raw_counts([seq, seq.upper()], 2))

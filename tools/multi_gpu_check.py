@@ -145,6 +145,80 @@ def main():
     if rank == 0:
         print("fused column-statistics exchange == NCCL path (1 ulp): %s; identical bits on all ranks: %s" % (close, same_bits))
         ok &= close and same_bits
+    # ---- round 2: one-pass routes on shards -------------------------------------------------------------------
+    from seekr_b200.fasta_reader import PackedFasta
+    from seekr_b200.kmer_counts import DeviceVector
+
+    k6 = 6
+    packed = PackedFasta.from_file(path, pinned=True)
+    begin, end = parallel.shard_ranges(packed.lengths, world)[rank]
+    eng6 = CountEngine(k6, "Log2.post")
+    dpk_all = eng6.upload(packed)
+    dpk = sharded.upload_slice(eng6, packed, begin, end)
+    # (1) accurate column statistics: sums inside the count kernel + exchange and finish in one peer-memory kernel,
+    #     against the same statistics of the whole set on one GPU and against the NCCL all-reduce route
+    one = CountEngine(k6, "Log2.post")
+    one.accurate_stats = True
+    _, m1, s1 = one.run(dpk_all, True, True, vectors_only=True)
+    got = {}
+    for name in ("peer", "nccl"):
+        if name == "nccl":
+            os.environ["SEEKR_B200_COLSTAT_EXCHANGE"] = "nccl"
+        red = parallel.AllReduceStats()
+        red.set_total_rows(packed.m)
+        e2 = CountEngine(k6, "Log2.post")
+        e2.accurate_stats = True
+        _, mv, sv = e2.run(dpk, True, True, reducer=red, vectors_only=True)
+        got[name] = (mv.t.cpu().numpy(), sv.t.cpu().numpy())
+        red.check()
+        os.environ.pop("SEEKR_B200_COLSTAT_EXCHANGE", None)
+    m1h, s1h = m1.t.cpu().numpy(), s1.t.cpu().numpy()
+    with np.errstate(all="ignore"):
+        dmax = max(float(np.nanmax(np.abs(got[n][0] - m1h) / np.maximum(np.abs(m1h), 1e-30))) for n in got)
+        smax = max(float(np.nanmax(np.abs(got[n][1] - s1h) / np.maximum(np.abs(s1h), 1e-30))) for n in got)
+    stats_ok = dmax < 2e-6 and smax < 2e-6
+    # (2) Log2.post with supplied vectors on shards: speculated shift, flags ORed after counting; equal to one GPU
+    mean_h, std_h = np.nan_to_num(m1h, nan=0.5), np.nan_to_num(s1h, nan=1.0)
+    std_h = np.where(std_h > 0, std_h, np.float32(1.0)).astype(np.float32)
+    mv, sv = DeviceVector.from_host(mean_h, 4 ** k6), DeviceVector.from_host(std_h, 4 ** k6)
+    ref_out, _, _ = CountEngine(k6, "Log2.post").run(dpk_all, mv, sv)
+    red = parallel.AllReduceStats()
+    e3 = CountEngine(k6, "Log2.post")
+    out, _, _ = e3.run(dpk, mv, sv, reducer=red)
+    held = e3.spec.held()
+    spec_ok = bool(torch.equal(out, ref_out[begin:end])) and held
+    # (3) the speculation fails on every rank (arg-min column never zero: every record starts with a poly-A run):
+    #     the two-pass route runs on all ranks, minimum exchanged, still equal to one GPU
+    rng = np.random.default_rng(5)
+    seqs = ["A" * (k6 + 3) + "".join(rng.choice(list("ACGT"), size=int(n))) for n in rng.integers(200, 900, size=400)]
+    pk2 = PackedFasta.from_sequences(seqs, pinned=True)
+    b2, e2_ = parallel.shard_ranges(pk2.lengths, world)[rank]
+    mean2 = np.full(4 ** k6, 0.25, dtype=np.float32)
+    mean2[0] = 500.0
+    std2 = np.full(4 ** k6, 0.5, dtype=np.float32)
+    mv2, sv2 = DeviceVector.from_host(mean2, 4 ** k6), DeviceVector.from_host(std2, 4 ** k6)
+    e4 = CountEngine(k6, "Log2.post")
+    all2 = e4.upload(pk2)
+    ref2, _, _ = CountEngine(k6, "Log2.post").run(all2, mv2, sv2)
+    red2 = parallel.AllReduceStats()
+    part2, _, _ = e4.run(sharded.upload_slice(e4, pk2, b2, e2_), mv2, sv2, reducer=red2)
+    red2.check()
+    fail_ok = bool(torch.equal(part2, ref2[b2:e2_])) and not e4.spec.held()
+    # (4) a rank that arrives seconds late at an exchange is waited for (the spin limit is 60 s, not 4 s)
+    if rank == world - 1:
+        import time
+        time.sleep(5.0)
+    red.min_allreduce(e3)
+    red.check()
+    flags = torch.tensor([int(stats_ok), int(spec_ok), int(fail_ok)], device="cuda")
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("accurate statistics on shards (peer kernel and NCCL route) vs one GPU: rel diff mean %.1e std %.1e: %s"
+              % (dmax, smax, bool(flags[0].item())))
+        print("one-pass Log2.post on shards == one GPU, speculation held: %s" % bool(flags[1].item()))
+        print("failing speculation on shards: two-pass route on every rank == one GPU: %s" % bool(flags[2].item()))
+        print("exchange with a rank 5 s late: completed")
+        ok &= bool(flags.min().item())
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)
     dist.barrier()
