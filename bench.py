@@ -705,6 +705,12 @@ def run_ours(args):
         tot += np.array(step(True))
     launches = int(lib.skr_launch_count(0))
     clocks = sampler.stop() if rank == 0 else None
+    if args.stop_after_steps:
+        if rank == 0:
+            emit({"note": "stopped after the timed steps (profiler run, no result)", "gpu_launches": launches})
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
     spec_held = bool(eng_cnt.spec.held()) if eng_cnt.spec is not None else None
     if reducer is not None:
         reducer.check()
@@ -963,6 +969,8 @@ def main():
     ap.add_argument("--strong-records", type=int, default=250000, help="records of the strong-scaling set (configs[2], [4])")
     ap.add_argument("--no-extras", action="store_true", help="skip strong_250k / parity / config5")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stop-after-steps", action="store_true",
+                    help="profiler runs (ncu launch list): exit after the timed steps, no JSON line of results")
     args = ap.parse_args()
     if args.warmup < 3:
         sys.stderr.write("bench.py: --warmup %d raised to 3 (timing rule: at least three untimed steps)\n" % args.warmup)

@@ -262,7 +262,8 @@ struct GemmParams {
     int num_kb;                // k-blocks of 64
     int chunk_kb;              // k-blocks accumulated in TMEM before promotion (see the header comment)
     int accumulate;            // add to what C already holds (K segments after the first)
-    int do_mirror;             // symmetric mode: fill the lower triangle after this launch (last K segment)
+    int do_mirror;             // last K segment: the values this launch stores are final
+    int mirror_epi;            // symmetric mode, final values: a tile above the diagonal also stores its transpose
     int tiles_m, tiles_n;
     float alpha;
     const float* a_scale;
@@ -570,6 +571,9 @@ pearson_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                 const long long gdiag = p.edge_row0 + row;
                 const long long jmin = p.edge_upper ? gdiag + 1 : 0;
                 int ecnt = 0;
+                // symmetric mode: the tile below the diagonal is this tile's transpose.  Lane = row, so the 32 lanes
+                // of a warp store one column of the tile as 128 consecutive bytes of the mirrored row.
+                const bool mir = p.mirror_epi && tn > tm;
 #pragma unroll
                 for (int c = 0; c < 128; c += 4) {
                     const long long col0 = colbase + c;
@@ -588,6 +592,13 @@ pearson_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                                 o.x += prev.x; o.y += prev.y; o.z += prev.z; o.w += prev.w;
                             }
                             *reinterpret_cast<float4*>(dst) = o;
+                            if (mir) {
+                                float* mt = reinterpret_cast<float*>(p.c) + col0 * p.ldc + row;
+                                mt[0] = o.x;
+                                mt[p.ldc] = o.y;
+                                mt[2 * p.ldc] = o.z;
+                                mt[3 * p.ldc] = o.w;
+                            }
                             if (p.edge_counts) {
                                 if (col0 >= jmin && (gdiag < col0 || gdiag >= col0 + 4)) {
                                     ecnt += (o.x >= p.edge_thr) + (o.y >= p.edge_thr) + (o.z >= p.edge_thr) + (o.w >= p.edge_thr);
@@ -604,6 +615,7 @@ pearson_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                                 if (col0 + i < p.n) {
                                     const float o = sum[c + i] * rs * __ldg(p.b_scale + col0 + i) + (p.accumulate ? dst[i] : 0.0f);
                                     dst[i] = o;
+                                    if (mir) reinterpret_cast<float*>(p.c)[(col0 + i) * p.ldc + row] = o;
                                     if (p.edge_counts) ecnt += (o >= p.edge_thr && col0 + i != gdiag && col0 + i >= jmin);
                                 }
                         }
@@ -611,8 +623,11 @@ pearson_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                         double* dst = reinterpret_cast<double*>(p.c) + row * p.ldc + col0;
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
-                            if (col0 + i < p.n)
-                                dst[i] = (double)(sum[c + i] * rs * __ldg(p.b_scale + col0 + i)) + (p.accumulate ? dst[i] : 0.0);
+                            if (col0 + i < p.n) {
+                                const double o = (double)(sum[c + i] * rs * __ldg(p.b_scale + col0 + i)) + (p.accumulate ? dst[i] : 0.0);
+                                dst[i] = o;
+                                if (mir) reinterpret_cast<double*>(p.c)[(col0 + i) * p.ldc + row] = o;
+                            }
                     }
                 }
                 if (ecnt) atomicAdd(p.edge_counts + row * SKR_SIM_SLICES + colbase / p.edge_width, (unsigned long long)ecnt);
@@ -630,60 +645,6 @@ pearson_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     }
 }
 
-
-// Symmetric mode: the GEMM wrote the 256 x 256 tiles on and above the diagonal; this fills every tile
-// below it with the transpose of its mirror image (32 x 32 blocks through shared memory, coalesced
-// reads and writes; ~2 passes over half the matrix at HBM speed).
-template <typename T, int MB>
-__global__ void __launch_bounds__(256) mirror_lower_kernel(T* __restrict__ c, long long n, long long ldc, int tiles) {
-    // MB x MB blocks ((256 / MB)^2 sub-blocks per 256 x 256 tile) through padded shared memory; 128-bit reads and
-    // writes when the block is interior.
-    extern __shared__ __align__(16) unsigned char mirror_smem[];
-    T(*tile)[MB + 1] = reinterpret_cast<T(*)[MB + 1]>(mirror_smem);
-    constexpr int SB = kBN / MB;  // sub-blocks per tile side
-    long long t = blockIdx.x;
-    int tm = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5) + 1;  // t = tm(tm-1)/2 + tn, tn < tm
-    while ((long long)tm * (tm - 1) / 2 > t) --tm;
-    while ((long long)(tm + 1) * tm / 2 <= t) ++tm;
-    const int tn = (int)(t - (long long)tm * (tm - 1) / 2);
-    if (tm >= tiles) return;
-    const int sb_r = blockIdx.y / SB, sb_c = blockIdx.y % SB;  // sub-block of the destination tile
-    const long long dr0 = (long long)tm * kBN + sb_r * MB, dc0 = (long long)tn * kBN + sb_c * MB;  // destination origin
-    constexpr int V = 16 / sizeof(T);       // elements per 128-bit access
-    constexpr int TX = MB / V;              // threads across an MB-wide row
-    constexpr int TY = 256 / TX;            // rows per sweep
-    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
-    const bool interior = dr0 + MB <= n && dc0 + MB <= n && (ldc % V) == 0;
-    // source block = C[dc0 .. dc0+MB-1][dr0 .. dr0+MB-1]
-    if (interior) {
-        for (int i = ty; i < MB; i += TY) {
-            const float4 v = *reinterpret_cast<const float4*>(c + (dc0 + i) * ldc + dr0 + tx * V);
-            const T* e = reinterpret_cast<const T*>(&v);
-#pragma unroll
-            for (int j = 0; j < V; ++j) tile[i][tx * V + j] = e[j];
-        }
-        __syncthreads();
-        for (int i = ty; i < MB; i += TY) {
-            float4 v;
-            T* e = reinterpret_cast<T*>(&v);
-#pragma unroll
-            for (int j = 0; j < V; ++j) e[j] = tile[tx * V + j][i];
-            *reinterpret_cast<float4*>(c + (dr0 + i) * ldc + dc0 + tx * V) = v;
-        }
-    } else {
-        for (int i = threadIdx.x / MB; i < MB; i += 256 / MB) {
-            const int j = threadIdx.x % MB;
-            const long long sr = dc0 + i, sc = dr0 + j;
-            if (sr < n && sc < n) tile[i][j] = c[sr * ldc + sc];
-        }
-        __syncthreads();
-        for (int i = threadIdx.x / MB; i < MB; i += 256 / MB) {
-            const int j = threadIdx.x % MB;
-            const long long r = dr0 + i, cc = dc0 + j;
-            if (r < n && cc < n) c[r * ldc + cc] = tile[j][i];
-        }
-    }
-}
 
 template <int kCG>
 int launch_gemm(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensorMap& mb_hi, const CUtensorMap& mb_lo,
@@ -714,23 +675,6 @@ int launch_gemm(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtens
     cfg.numAttrs = 1;
     SKR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, mb_hi, mb_lo, p));
     SKR_LAUNCH_CHECK();
-    if (p.symmetric && p.do_mirror && p.tiles_m > 1) {
-        const long long pairs = (long long)p.tiles_m * (p.tiles_m - 1) / 2;
-        if (p.c_is_f64) {
-            constexpr int MB = 64;
-            constexpr int smem = MB * (MB + 1) * (int)sizeof(double);
-            dim3 grid((unsigned)pairs, (kBN / MB) * (kBN / MB));
-            mirror_lower_kernel<double, MB><<<grid, 256, smem, stream>>>((double*)p.c, p.n, p.ldc, p.tiles_m);
-        } else {
-            constexpr int MB = 64;  // 128 x 128 blocks (512-byte segments, 66 KB of shared memory) measured slower: 2.9 vs 2.2 ms
-            constexpr int smem = MB * (MB + 1) * (int)sizeof(float);
-            auto kern = mirror_lower_kernel<float, MB>;
-            SKR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            dim3 grid((unsigned)pairs, (kBN / MB) * (kBN / MB));
-            kern<<<grid, 256, smem, stream>>>((float*)p.c, p.n, p.ldc, p.tiles_m);
-        }
-        SKR_LAUNCH_CHECK();
-    }
     return SKR_OK;
 }
 
@@ -868,6 +812,9 @@ static int pearson_gemm_impl(const uint16_t* d_a_hi, const uint16_t* d_a_lo, con
     p.ldc = ldc;
     p.c_is_f64 = c_is_f64;
     p.symmetric = symmetric;
+    // The separate mirror pass this replaces (read the upper tiles, transpose through shared memory, write) took
+    // 2.2 ms at 50k x 50k; from the epilogue the GEMM is 0.5 ms longer (profiles/r02_gemm_mirror.txt).
+    p.mirror_epi = symmetric && p.do_mirror;
     if (kb_first + kb_count >= total_kb) {  // the finished values exist in the last K segment only
         p.edge_counts = edges.counts;
         p.edge_thr = edges.thr;
