@@ -350,6 +350,22 @@ SKR_AVX2 const char* for_each_line_fast(const char* base, const char* from, cons
         const char* last_nl = nullptr;
         uint64_t nls = 0;
         uint32_t carry = 1;  // s is a line start: a '\n' right here is a blank line
+        while (p + 64 <= lim) {  // two vectors per step, no data-dependent branch but the exit
+            const __m256i v0 = _mm256_loadu_si256((const __m256i*)p);
+            const __m256i v1 = _mm256_loadu_si256((const __m256i*)(p + 32));
+            const uint64_t nlm = (uint64_t)(uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(v0, v_nl)) |
+                                 ((uint64_t)(uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(v1, v_nl)) << 32);
+            const __m256i s0 = _mm256_or_si256(_mm256_cmpeq_epi8(_mm256_min_epu8(v0, v_sp), v0), _mm256_cmpeq_epi8(v0, v_gt));
+            const __m256i s1 = _mm256_or_si256(_mm256_cmpeq_epi8(_mm256_min_epu8(v1, v_sp), v1), _mm256_cmpeq_epi8(v1, v_gt));
+            const uint64_t spm = ((uint64_t)(uint32_t)_mm256_movemask_epi8(s0) | ((uint64_t)(uint32_t)_mm256_movemask_epi8(s1) << 32)) & ~nlm;
+            const uint64_t blank = nlm & ((nlm << 1) | carry);
+            if (spm | blank) break;
+            nls += (uint64_t)__builtin_popcountll(nlm);
+            const char* cand = p + (63 - (int)_lzcnt_u64(nlm));  // p - 1 when the step holds no '\n': never selected
+            last_nl = nlm ? cand : last_nl;
+            carry = (uint32_t)(nlm >> 63);
+            p += 64;
+        }
         while (p + 32 <= lim) {
             const __m256i v = _mm256_loadu_si256((const __m256i*)p);
             const uint32_t nlm = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(v, v_nl));
