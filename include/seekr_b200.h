@@ -36,6 +36,7 @@ enum {
     SKR_ERR_NOMEM = 4,
     SKR_ERR_FASTA_BLANK = 5,   /* blank line: the reference raises IndexError (fasta_reader.py:53) */
     SKR_ERR_FASTA_HEADER = 6,  /* header without a sequence: AssertionError (fasta_reader.py:58) */
+    SKR_ERR_CAPACITY = 7,      /* streamed packer: the record estimate was too small; restart on the finished handle */
 };
 
 const char* skr_last_error(void);
@@ -76,8 +77,18 @@ void skr_packed_free(SkrPacked* p);
  * are packed (upto < 0: all); skr_packed_wait also ends the background threads; skr_packed_free waits first. */
 int skr_pack_fasta_buffer_async(const void* text, size_t nbytes, const uint8_t* lut, int nthreads, int pinned,
                                 SkrPacked** out);
+/* Texts of 32 MB and more (SEEKR_B200_WAVE_MIN_BYTES) are scanned in the background too, wave by wave: the call
+ * returns after the first wave with a slab sized for an estimated record count (skr_packed_capacity_records); only
+ * the errors of that first part are reported by the call itself, later ones by skr_packed_wait / _wait_records /
+ * _wait_scanned (num_records and friends return -1 then).  skr_packed_wait_scanned blocks until records [0, want)
+ * are in the record table (want < 0: until the table is complete), *avail = records in the table so far, *finished
+ * = 1 once the count is final; SKR_ERR_CAPACITY when the estimate proved too small (the job then rebuilds an exact
+ * slab -- codes / mask / offsets pointers CHANGE -- and the handle is complete after skr_packed_wait).
+ * skr_packed_num_records / _num_blocks / _total_bases / _header_spans / _body_spans wait for the table. */
 int skr_packed_wait_records(SkrPacked* p, int64_t upto);
 int skr_packed_wait(SkrPacked* p);
+int skr_packed_wait_scanned(SkrPacked* p, int64_t want, int64_t* avail, int* finished);
+int64_t skr_packed_capacity_records(const SkrPacked* p);
 
 int64_t skr_packed_num_records(const SkrPacked* p);
 int64_t skr_packed_num_blocks(const SkrPacked* p);  /* including the trailing pad block */
@@ -216,8 +227,11 @@ typedef struct {
     int32_t h_out_pinned;
     int32_t copy_threads;
     int64_t chunk_records;
+    int64_t capacity_records; /* rows count.d_out / h_out can take; 0 = the handle's record count (which waits for a
+                               * background scan).  A handle that turns out larger ends the call with SKR_ERR_CAPACITY */
+    int64_t records_done;     /* out: records counted and copied out when the call returned */
 } SkrStreamArgs;
-int skr_stream_counts(SkrPacked* packed, const SkrStreamArgs* args, void* stream);
+int skr_stream_counts(SkrPacked* packed, SkrStreamArgs* args, void* stream);
 
 /* Deferred normalisation for Log2.post with known, finite mean / positive std vectors (the
  * seekr_kmer_counts -mv -sv path): the count kernel writes the un-normalised values and keeps the

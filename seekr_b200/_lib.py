@@ -18,6 +18,7 @@ SKR_ERR_IO = 3
 SKR_ERR_NOMEM = 4
 SKR_ERR_FASTA_BLANK = 5
 SKR_ERR_FASTA_HEADER = 6
+SKR_ERR_CAPACITY = 7
 SKR_CSV_UNSUPPORTED = 100
 SIM_SLICES = 8  # SKR_SIM_SLICES
 
@@ -54,6 +55,7 @@ class StreamArgs(ctypes.Structure):
     _fields_ = [
         ("count", CountArgs), ("d_slab", _vp), ("h_out", _vp), ("h_ld", _i64),
         ("h_out_pinned", ctypes.c_int32), ("copy_threads", ctypes.c_int32), ("chunk_records", _i64),
+        ("capacity_records", _i64), ("records_done", _i64),
     ]
 
 
@@ -68,6 +70,8 @@ SIGNATURES = {
     "skr_pack_fasta_buffer_async": (_int, [_vp, _sz, _vp, _int, _int, ctypes.POINTER(_vp)]),
     "skr_packed_wait_records": (_int, [_vp, _i64]),
     "skr_packed_wait": (_int, [_vp]),
+    "skr_packed_wait_scanned": (_int, [_vp, _i64, ctypes.POINTER(_i64), ctypes.POINTER(_int)]),
+    "skr_packed_capacity_records": (_i64, [_vp]),
     "skr_stream_counts": (_int, [_vp, ctypes.POINTER(StreamArgs), _vp]),
     "skr_host_alloc_pooled": (_int, [_sz, ctypes.POINTER(_vp)]),
     "skr_packed_num_records": (_i64, [_vp]),

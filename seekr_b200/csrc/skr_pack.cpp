@@ -225,9 +225,12 @@ extern "C" int skr_device_count(int* out) {
 }
 
 struct PackJob;
+struct WaveJob;
 
 struct SkrPacked {
     PackJob* job = nullptr;  // packing still running in the background (skr_pack_fasta_buffer_async)
+    WaveJob* wave = nullptr; // scan AND pack still running in the background, wave by wave (large texts)
+    Slab retired;            // wave mode, capacity estimate too small: the first slab, kept until the handle goes
     int64_t m = 0;
     int64_t nblocks = 0;  // including the trailing pad block
     int64_t total_bases = 0;
@@ -525,6 +528,83 @@ SKR_AVX2 void pack_segment_avx2(BitWriter& w, const char* a, const char* b, cons
     }
 }
 
+
+// Pass 1 over one byte range of the text: the records whose header line STARTS in [from, to), each followed to its
+// end (past `to` if need be).  Sequence lines at the start of the range belong to a record of an earlier range.
+struct ScanCtx {
+    const char* text;
+    const char* end;
+    bool use_avx2;
+    bool fast;
+};
+
+void scan_slice(const ScanCtx& cx, const char* from, const char* to, bool first_slice, ChunkResult& R) {
+    const char* text = cx.text;
+    const char* end = cx.end;
+    bool in_record = false;  // a header that started in this range is open
+    bool beyond = false;     // phase 2: lines that start past `to` (they finish our last record)
+    auto on_line = [&](const char* a, const char* b) -> bool {
+        const char* la = a;
+        const char* lb = b;
+        strip(la, lb);
+        if (la == lb) {
+            if (beyond) return false;  // the range that owns this line reports it
+            uint64_t off = (uint64_t)(a - text);
+            if (off < R.err_off) { R.err_off = off; R.err_code = SKR_ERR_FASTA_BLANK; }
+            return false;
+        }
+        if (*la == '>') {
+            if (beyond) return false;  // next range's record: our last record is complete
+            Rec r;
+            r.hdr_off = (uint64_t)(la - text);
+            r.hdr_len = (uint64_t)(lb - la);
+            r.body_off = (uint64_t)(b - text);
+            r.body_len = 0;
+            r.bases = 0;
+            R.recs.push_back(r);
+            in_record = true;
+            return true;
+        }
+        if (!in_record) {  // sequence line of a record opened in an earlier range
+            if (first_slice) { R.first_line_not_header = true; return false; }
+            return true;
+        }
+        Rec& r = R.recs.back();
+        if (r.body_len == 0) r.body_off = (uint64_t)(a - text);
+        r.body_len = (uint64_t)(b - text) - r.body_off;
+        r.bases += (uint64_t)(lb - la);
+        return true;
+    };
+    auto on_clean = [&](const char* a, uint64_t nbases, const char* last_end) -> bool {
+        if (!in_record) {  // sequence lines of a record opened in an earlier range
+            if (first_slice) { R.first_line_not_header = true; return false; }
+            return true;
+        }
+        Rec& r = R.recs.back();
+        if (r.body_len == 0) r.body_off = (uint64_t)(a - text);
+        r.body_len = (uint64_t)(last_end - text) - r.body_off;
+        r.bases += nbases;
+        return true;
+    };
+    const char* next = cx.fast ? for_each_line_fast(text, from, to, end, on_line, on_clean)
+                               : (cx.use_avx2 ? for_each_line_avx2(text, from, to, end, on_line)
+                                              : for_each_line(text, from, to, end, on_line));
+    if (next && in_record && next < end) {
+        beyond = true;
+        if (cx.fast) for_each_line_fast(text, next, end, end, on_line, on_clean);
+        else if (cx.use_avx2) for_each_line_avx2(text, next, end, end, on_line);
+        else for_each_line(text, next, end, end, on_line);
+    }
+}
+
+// 1-based number of the line that holds byte `off`
+int64_t line_of_offset(const char* text, uint64_t off) {
+    int64_t line = 1;
+    for (const char* p = text; p < text + off; ++p)
+        if (*p == '\n' || (*p == '\r' && p[1] != '\n')) ++line;
+    return line;
+}
+
 int run_threads(int nthreads, const std::function<void(int)>& fn) {
     if (nthreads <= 1) {
         fn(0);
@@ -584,6 +664,30 @@ int alloc_packed(SkrPacked* P, int64_t m, const std::vector<uint64_t>& bases, bo
 
 }  // namespace
 
+namespace {
+
+// Pass 2 for one record: its sequence lines, stripped, into the 2-bit codes and the validity mask of its blocks.
+void pack_record(SkrPacked* P, const Rec& r, int64_t i, const char* text, const char* end, const SimdAlphabet& al,
+                 const uint8_t* lut2, bool use_avx2) {
+    uint64_t b0 = P->blk_off[i], b1 = P->blk_off[i + 1];
+    BitWriter w{P->codes + b0 * 4, P->mask + b0 * 2};
+    const char* bs = text + r.body_off;
+    const char* be = bs + r.body_len;
+    if (r.body_len) {
+        auto pack_line = [&](const char* a, const char* b) -> bool {
+            strip(a, b);
+            if (al.ok) pack_segment_avx2(w, a, b, al, end);
+            else for (const char* p = a; p < b; ++p) w.put(lut2[(unsigned char)*p]);
+            return true;
+        };
+        if (use_avx2) for_each_line_avx2(bs, bs, be, be, pack_line);
+        else for_each_line(bs, bs, be, be, pack_line);
+    }
+    w.finish(P->codes + b1 * 4, P->mask + b1 * 2);
+}
+
+}  // namespace
+
 // The pack pass over the records found by the scan: groups of 64 records are drawn in record order by however many
 // threads run work(); done[g] is raised when group g is complete, so a consumer can follow the packed prefix.
 struct PackJob {
@@ -618,24 +722,7 @@ struct PackJob {
             const int64_t i0 = next_rec.fetch_add(kGroup);
             if (i0 >= m) break;
             const int64_t i1 = std::min(m, i0 + kGroup);
-            for (int64_t i = i0; i < i1; ++i) {
-                const Rec& r = recs[i];
-                uint64_t b0 = P->blk_off[i], b1 = P->blk_off[i + 1];
-                BitWriter w{P->codes + b0 * 4, P->mask + b0 * 2};
-                const char* bs = text + r.body_off;
-                const char* be = bs + r.body_len;
-                if (r.body_len) {
-                    auto pack_line = [&](const char* a, const char* b) -> bool {
-                        strip(a, b);
-                        if (al.ok) pack_segment_avx2(w, a, b, al, end);
-                        else for (const char* p = a; p < b; ++p) w.put(lut2[(unsigned char)*p]);
-                        return true;
-                    };
-                    if (use_avx2) for_each_line_avx2(bs, bs, be, be, pack_line);
-                    else for_each_line(bs, bs, be, be, pack_line);
-                }
-                w.finish(P->codes + b1 * 4, P->mask + b1 * 2);
-            }
+            for (int64_t i = i0; i < i1; ++i) pack_record(P, recs[i], i, text, end, al, lut2, use_avx2);
             done[i0 / kGroup].store(1, std::memory_order_release);
         }
     }
@@ -663,7 +750,319 @@ struct PackJob {
     }
 };
 
+
+// ---- scan and pack in waves (large texts, background mode) -----------------------------------------------------
+// The serial part of the streamed get_counts() used to be the scan: the record count sizes every allocation, so
+// nothing could start before the whole text had been looked at (2.5-3.3 ms for 165 MB on 16 threads).  Here the
+// text is cut into slices of ~nbytes / (16 T); the T workers go through them T at a time: scan a slice each,
+// barrier, worker 0 appends the wave's records to the table (prefix of block offsets, the checks of the reference's
+// parser), barrier, everybody packs the records that are final, next wave.  The slab is allocated after the first
+// wave for an ESTIMATED record count (records per byte of wave 0, + 25 % + 1024) and a block count that is a bound
+// given that record count (bases <= bytes); the call returns at that point.  Consumers follow `scanned` (table
+// entries final) and the per-group done flags (codes and mask written).  A text whose later part is denser in
+// records than the estimate allows falls back: the waves finish the scan only, then an exact slab is packed as in
+// the one-shot mode, and streaming consumers are told SKR_ERR_CAPACITY (they restart on the finished handle).
+struct SpinBarrier {
+    std::atomic<int> count{0};
+    std::atomic<int> sense{0};
+    int n = 1;
+    void wait(int& local) {
+        local ^= 1;
+        if (count.fetch_add(1, std::memory_order_acq_rel) == n - 1) {
+            count.store(0, std::memory_order_relaxed);
+            sense.store(local, std::memory_order_release);
+        } else {
+            int spins = 0;
+            while (sense.load(std::memory_order_acquire) != local) {
+                if (++spins < 4000) _mm_pause(); else std::this_thread::yield();
+            }
+        }
+    }
+};
+
 namespace {
+int layout_packed(SkrPacked* P, int64_t cap_records, int64_t cap_blocks, bool pinned);
+}
+
+struct WaveJob {
+    SkrPacked* P;
+    ScanCtx cx;
+    size_t nbytes;
+    SimdAlphabet al;
+    uint8_t lut2[256];
+    bool pinned;
+    int T;
+    size_t slice_bytes;
+    int64_t nslices, nwaves;
+    std::vector<ChunkResult> res;  // one per worker, reused every wave
+    std::vector<Rec> recs;         // reserved to the capacity: addresses stay put while packers read them
+    int64_t cap_records = 0;
+    uint64_t blocks = 0, total_bases = 0;
+    std::atomic<int64_t> scanned{0};      // records whose table entries are final
+    std::atomic<int64_t> pack_groups{0};  // groups of 64 records that may be packed
+    std::atomic<int64_t> next_group{0};
+    std::atomic<int64_t> watermark{0};
+    std::unique_ptr<std::atomic<uint8_t>[]> done;
+    std::atomic<int> wave0{0};     // the handle is usable (slab allocated, first records in the table) or the job failed
+    std::atomic<int> finished{0};  // the record table is complete (or the job failed)
+    std::atomic<int> overflow{0};
+    std::atomic<int> failed{0};
+    int err_code = 0;
+    int64_t err_line = 0;
+    std::string err_msg;
+    SpinBarrier bar;
+    std::vector<std::thread> threads;
+    static constexpr int64_t kGroup = 64;
+
+    void fail(int code, int64_t line, const char* fmt, ...) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        err_code = code;
+        err_line = line;
+        err_msg = buf;
+        failed.store(1, std::memory_order_release);
+        finished.store(1, std::memory_order_release);
+        wave0.store(1, std::memory_order_release);
+    }
+
+    // worker 0, between the barriers of wave w: the wave's records join the table
+    void merge(int64_t w) {
+        const char* text = cx.text;
+        if (w == 0 && res[0].first_line_not_header) {
+            fail(SKR_ERR_ARG, 0, "FASTA text does not start with a '>' header line");
+            return;
+        }
+        uint64_t err_off = UINT64_MAX;
+        int code = 0;
+        for (int t = 0; t < T; ++t)
+            if (res[t].err_off < err_off) { err_off = res[t].err_off; code = res[t].err_code; }
+        const bool last = w == nwaves - 1;
+        if (w == 0) {
+            int64_t m0 = 0;
+            for (int t = 0; t < T; ++t) m0 += (int64_t)res[t].recs.size();
+            if (last) {
+                cap_records = m0;
+            } else {
+                const double seen = (double)std::min(nbytes, (size_t)T * slice_bytes);
+                cap_records = (int64_t)((double)m0 * ((double)nbytes / seen) * 1.25) + 1024;
+            }
+            const int64_t cap_blocks = (int64_t)(nbytes / 64) + cap_records + 2;
+            int rc = layout_packed(P, cap_records, cap_blocks, pinned);
+            if (rc != SKR_OK) { fail(rc, 0, "%s", skr::last_error().c_str()); return; }
+            recs.reserve((size_t)std::max<int64_t>(cap_records, 1));
+            P->header_spans.resize((size_t)cap_records * 2);
+            P->body_spans.resize((size_t)cap_records * 2);
+            const int64_t groups = cap_records / kGroup + 1;
+            done.reset(new std::atomic<uint8_t>[(size_t)groups]);
+            for (int64_t g = 0; g < groups; ++g) done[g].store(0, std::memory_order_relaxed);
+        }
+        for (int t = 0; t < T && !code; ++t) {
+            for (const Rec& r : res[t].recs) {
+                if (r.hdr_off >= err_off) break;  // the reference stops at the first offending line
+                // empty record anywhere but last -> the reference's assert, at the header that follows it
+                if (!recs.empty() && recs.back().bases == 0) {
+                    err_off = r.hdr_off;
+                    code = SKR_ERR_FASTA_HEADER;
+                    break;
+                }
+                if (r.bases > 0xFFFFFFFFull) {
+                    fail(SKR_ERR_ARG, 0, "record %lld longer than 2^32-1 bases", (long long)recs.size());
+                    return;
+                }
+                const int64_t i = (int64_t)recs.size();
+                if (i >= cap_records && !overflow.load(std::memory_order_relaxed)) overflow.store(1, std::memory_order_release);
+                recs.push_back(r);
+                if (!overflow.load(std::memory_order_relaxed)) {
+                    P->blk_off[i] = blocks;
+                    P->len[i] = (uint32_t)r.bases;
+                    P->header_spans[2 * i] = r.hdr_off;
+                    P->header_spans[2 * i + 1] = r.hdr_len;
+                    P->body_spans[2 * i] = r.body_off;
+                    P->body_spans[2 * i + 1] = r.body_len;
+                }
+                blocks += (r.bases + 63) / 64;
+                total_bases += r.bases;
+            }
+        }
+        if (code || err_off != UINT64_MAX) {
+            if (!code) code = SKR_ERR_FASTA_BLANK;
+            const int64_t line = line_of_offset(text, err_off);
+            if (code == SKR_ERR_FASTA_BLANK) fail(code, line, "string index out of range (blank line %lld in FASTA)", (long long)line);
+            else fail(code, line, "There may be a header without a sequence at line %lld.", (long long)(line - 1));
+            return;
+        }
+        const int64_t n = (int64_t)recs.size();
+        if (!overflow.load(std::memory_order_relaxed)) {
+            P->blk_off[n] = blocks;
+            if (last) finalize(n);
+            pack_groups.store(last ? (n + kGroup - 1) / kGroup : n / kGroup, std::memory_order_release);
+            scanned.store(n, std::memory_order_release);
+            if (last) finished.store(1, std::memory_order_release);
+        }
+        wave0.store(1, std::memory_order_release);
+    }
+
+    void finalize(int64_t n) {
+        P->m = n;
+        P->nblocks = (int64_t)blocks + 1;
+        P->total_bases = (int64_t)total_bases;
+        P->header_spans.resize((size_t)n * 2);
+        P->body_spans.resize((size_t)n * 2);
+        memset(P->codes + blocks * 4, 0, 16);    // trailing pad block: codes 0, mask all ones
+        memset(P->mask + blocks * 2, 0xFF, 8);
+    }
+
+    // the estimate was too small: an exact slab, filled by everybody after the last wave
+    void rebuild_exact() {
+        const int64_t n = (int64_t)recs.size();
+        P->retired = P->slab;  // a consumer may still be copying from it
+        P->slab = Slab();
+        int rc = layout_packed(P, n, (int64_t)blocks + 1, pinned);
+        if (rc != SKR_OK) { fail(rc, 0, "%s", skr::last_error().c_str()); return; }
+        P->header_spans.resize((size_t)n * 2);
+        P->body_spans.resize((size_t)n * 2);
+        uint64_t b = 0;
+        for (int64_t i = 0; i < n; ++i) {
+            const Rec& r = recs[(size_t)i];
+            P->blk_off[i] = b;
+            P->len[i] = (uint32_t)r.bases;
+            P->header_spans[2 * i] = r.hdr_off;
+            P->header_spans[2 * i + 1] = r.hdr_len;
+            P->body_spans[2 * i] = r.body_off;
+            P->body_spans[2 * i + 1] = r.body_len;
+            b += (r.bases + 63) / 64;
+        }
+        P->blk_off[n] = b;
+        finalize(n);
+        const int64_t groups = n / kGroup + 1;
+        done.reset(new std::atomic<uint8_t>[(size_t)groups]);
+        for (int64_t g = 0; g < groups; ++g) done[g].store(0, std::memory_order_relaxed);
+        next_group.store(0, std::memory_order_relaxed);
+        watermark.store(0, std::memory_order_relaxed);
+        pack_groups.store((n + kGroup - 1) / kGroup, std::memory_order_release);
+    }
+
+    void pack_available() {
+        for (;;) {
+            int64_t g = next_group.load(std::memory_order_relaxed);
+            if (g >= pack_groups.load(std::memory_order_acquire)) break;
+            if (!next_group.compare_exchange_weak(g, g + 1, std::memory_order_relaxed)) continue;
+            const int64_t i1 = std::min<int64_t>((g + 1) * kGroup, (int64_t)recs.size());
+            for (int64_t i = g * kGroup; i < i1; ++i) pack_record(P, recs[(size_t)i], i, cx.text, cx.end, al, lut2, cx.use_avx2);
+            done[g].store(1, std::memory_order_release);
+        }
+    }
+
+    void worker(int t) {
+        int sense = 0;
+        const char* text = cx.text;
+        for (int64_t w = 0; w < nwaves; ++w) {
+            const int64_t s = w * T + t;
+            res[t] = ChunkResult();
+            if (s < nslices && !failed.load(std::memory_order_relaxed)) {
+                const size_t a = (size_t)s * slice_bytes, b = std::min(nbytes, a + slice_bytes);
+                scan_slice(cx, text + a, text + b, s == 0, res[t]);
+            }
+            bar.wait(sense);
+            if (t == 0 && !failed.load(std::memory_order_relaxed)) merge(w);
+            bar.wait(sense);
+            if (failed.load(std::memory_order_acquire)) return;
+            if (!overflow.load(std::memory_order_acquire)) pack_available();
+        }
+        if (overflow.load(std::memory_order_acquire)) {
+            if (t == 0) rebuild_exact();
+            bar.wait(sense);
+            if (failed.load(std::memory_order_acquire)) return;
+            pack_available();
+            bar.wait(sense);
+            if (t == 0) {  // only now: the table AND the words of the exact slab are there
+                scanned.store((int64_t)recs.size(), std::memory_order_release);
+                finished.store(1, std::memory_order_release);
+            }
+        }
+    }
+
+    void start() {
+        bar.n = T;
+        res.resize((size_t)T);
+        threads.reserve((size_t)T);
+        for (int t = 0; t < T; ++t) threads.emplace_back([this, t] { worker(t); });
+    }
+
+    void join() {
+        for (auto& t : threads) t.join();
+        threads.clear();
+    }
+
+    static void pause(int& spins) {
+        if (++spins < 2000) _mm_pause(); else std::this_thread::yield();
+    }
+
+    // blocks until records [0, want) are in the table, or the table is complete; SKR_ERR_CAPACITY after a fallback
+    int wait_scanned(int64_t want, int64_t* avail, int* fin) {
+        int spins = 0;
+        for (;;) {
+            if (overflow.load(std::memory_order_acquire)) return SKR_ERR_CAPACITY;
+            const int f = finished.load(std::memory_order_acquire);
+            const int64_t n = scanned.load(std::memory_order_acquire);
+            if (f || (want >= 0 && n >= want)) {
+                if (failed.load(std::memory_order_acquire)) return err_code;
+                *avail = n;
+                *fin = f;
+                return SKR_OK;
+            }
+            pause(spins);
+        }
+    }
+
+    void wait_finished() {
+        int spins = 0;
+        while (!finished.load(std::memory_order_acquire)) pause(spins);
+    }
+
+    // blocks until records [0, upto) are packed (upto <= scanned)
+    void wait_records(int64_t upto) {
+        const int64_t need = (upto + kGroup - 1) / kGroup;
+        int64_t w = watermark.load(std::memory_order_relaxed);
+        int spins = 0;
+        while (w < need && !failed.load(std::memory_order_acquire)) {
+            if (overflow.load(std::memory_order_acquire)) { wait_finished(); return; }  // rebuilt: everything is packed by then
+            if (w < pack_groups.load(std::memory_order_acquire) && done[w].load(std::memory_order_acquire)) { ++w; spins = 0; continue; }
+            pause(spins);
+        }
+        if (!overflow.load(std::memory_order_acquire)) watermark.store(w, std::memory_order_relaxed);
+    }
+};
+
+namespace {
+
+// one slab: [codes | mask | block offsets (cap + 1) | lengths (cap)], the same order alloc_packed uses
+int layout_packed(SkrPacked* P, int64_t cap_records, int64_t cap_blocks, bool pinned) {
+    size_t off_codes = 0;
+    size_t off_mask = align_up(off_codes + (size_t)cap_blocks * 16, 256);
+    size_t off_blk = align_up(off_mask + (size_t)cap_blocks * 8, 256);
+    size_t off_len = align_up(off_blk + (size_t)(cap_records + 1) * 8, 256);
+    size_t total = align_up(off_len + (size_t)std::max<int64_t>(cap_records, 1) * 4, 256);
+    int rc = slab_alloc(total, pinned, &P->slab);
+    if (rc != SKR_OK) return rc;
+    P->slab_bytes = total;
+    char* base = (char*)P->slab.ptr;
+    P->codes = (uint32_t*)(base + off_codes);
+    P->mask = (uint32_t*)(base + off_mask);
+    P->blk_off = (uint64_t*)(base + off_blk);
+    P->len = (uint32_t*)(base + off_len);
+    return SKR_OK;
+}
+
+// the error a background job ended with, raised on the thread that asks
+int wave_error(WaveJob* w) {
+    g_error_line = w->err_line;
+    return skr::fail(w->err_code, "%s", w->err_msg.c_str());
+}
+
 }  // namespace
 
 extern "C" int64_t skr_pack_error_line(void) { return g_error_line; }
@@ -683,8 +1082,36 @@ extern "C" int skr_pack_fasta_buffer_async(const void* text_v, size_t nbytes, co
 
 extern "C" int skr_packed_wait_records(SkrPacked* p, int64_t upto) {
     if (!p) return skr::fail(SKR_ERR_ARG, "skr_packed_wait_records: null handle");
+    if (p->wave) {
+        WaveJob* w = p->wave;
+        int64_t avail = 0;
+        int fin = 0;
+        int rc = w->wait_scanned(upto, &avail, &fin);  // upto < 0: the whole table
+        if (rc == SKR_ERR_CAPACITY) { w->wait_finished(); rc = w->failed.load() ? w->err_code : SKR_OK; avail = w->scanned.load(); }
+        if (rc != SKR_OK) return wave_error(w);
+        w->wait_records(upto < 0 ? avail : std::min(upto, avail));
+        return w->failed.load() ? wave_error(w) : SKR_OK;
+    }
     if (p->job) p->job->wait_records(upto < 0 ? p->m : std::min(upto, p->m));
     return SKR_OK;
+}
+
+extern "C" int skr_packed_wait_scanned(SkrPacked* p, int64_t want, int64_t* avail, int* finished) {
+    if (!p || !avail || !finished) return skr::fail(SKR_ERR_ARG, "skr_packed_wait_scanned: null argument");
+    if (!p->wave) {
+        *avail = p->m;
+        *finished = 1;
+        return SKR_OK;
+    }
+    int rc = p->wave->wait_scanned(want, avail, finished);
+    if (rc == SKR_ERR_CAPACITY)
+        return skr::fail(rc, "the record estimate of the streamed packer was too small; the handle is complete after skr_packed_wait");
+    return rc == SKR_OK ? SKR_OK : wave_error(p->wave);
+}
+
+extern "C" int64_t skr_packed_capacity_records(const SkrPacked* p) {
+    if (!p) return 0;
+    return p->wave ? p->wave->cap_records : p->m;
 }
 
 extern "C" int skr_packed_wait(SkrPacked* p) {
@@ -694,7 +1121,20 @@ extern "C" int skr_packed_wait(SkrPacked* p) {
         delete p->job;
         p->job = nullptr;
     }
+    if (p->wave) {
+        p->wave->join();
+        if (p->wave->failed.load()) return wave_error(p->wave);  // the job stays: later calls report the same error
+        delete p->wave;
+        p->wave = nullptr;
+    }
     return SKR_OK;
+}
+
+// the record table of a handle whose scan still runs is not final: everything that depends on it waits here
+static bool table_ready(const SkrPacked* p) {
+    if (!p->wave) return true;
+    p->wave->wait_finished();
+    return !p->wave->failed.load();
 }
 
 static int pack_fasta_buffer(const void* text_v, size_t nbytes, const uint8_t* lut, int nthreads, int pinned, bool async,
@@ -715,68 +1155,50 @@ static int pack_fasta_buffer(const void* text_v, size_t nbytes, const uint8_t* l
     auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
         return std::chrono::duration<double, std::milli>(b - a).count();
     };
+    // large texts in background mode: scan and pack in waves, the call returns after the first one
+    size_t wave_min = (size_t)32 << 20;
+    if (const char* env = getenv("SEEKR_B200_WAVE_MIN_BYTES")) wave_min = (size_t)strtoull(env, nullptr, 10);
+    if (async && T >= 2 && nbytes >= wave_min && !getenv("SEEKR_B200_NO_WAVES")) {
+        const auto t0 = now();
+        SkrPacked* P = new SkrPacked();
+        WaveJob* job = new WaveJob();
+        job->P = P;
+        job->cx = ScanCtx{text, end, use_avx2, use_avx2 && !getenv("SKR_PACK_NO_FAST_SCAN")};
+        job->nbytes = nbytes;
+        job->al = al;
+        memcpy(job->lut2, lut2, 256);
+        job->pinned = pinned != 0;
+        job->T = T;
+        int waves = 16;
+        if (const char* env = getenv("SEEKR_B200_WAVES")) waves = std::max(1, atoi(env));
+        size_t slice_min = (size_t)64 << 10;
+        if (const char* env = getenv("SEEKR_B200_WAVE_SLICE_MIN")) slice_min = std::max<size_t>(64, (size_t)strtoull(env, nullptr, 10));
+        job->slice_bytes = std::max<size_t>(slice_min, (nbytes + (size_t)T * waves - 1) / ((size_t)T * waves));
+        job->nslices = (int64_t)((nbytes + job->slice_bytes - 1) / job->slice_bytes);
+        job->nwaves = (job->nslices + T - 1) / T;
+        P->wave = job;
+        job->start();
+        int spins = 0;
+        while (!job->wave0.load(std::memory_order_acquire)) WaveJob::pause(spins);
+        if (job->failed.load(std::memory_order_acquire)) {  // wave 0 holds what a one-shot scan reports first
+            job->join();
+            const int rc = wave_error(job);
+            skr_packed_free(P);
+            return rc;
+        }
+        if (profile)
+            fprintf(stderr, "skr_pack (waves): %d threads, %lld slices of %zu bytes in %lld waves, first wave + slab %.2f ms, "
+                    "capacity %lld records (%zu bytes)\n", T, (long long)job->nslices, job->slice_bytes, (long long)job->nwaves,
+                    ms(t0, now()), (long long)job->cap_records, nbytes);
+        *out = P;
+        return SKR_OK;
+    }
     const auto t_start = now();
     // ---- pass 1: records and their lengths, chunked by byte range ----------------------------
     std::vector<ChunkResult> res(T);
+    const ScanCtx cx{text, end, use_avx2, use_avx2 && !getenv("SKR_PACK_NO_FAST_SCAN")};
     run_threads(T, [&](int t) {
-        ChunkResult& R = res[t];
-        const char* from = text + nbytes * (size_t)t / (size_t)T;
-        const char* to = text + nbytes * (size_t)(t + 1) / (size_t)T;
-        bool in_record = false;  // a header that started in this chunk is open
-        bool beyond = false;     // phase 2: lines that start past `to` (they finish our last record)
-        auto on_line = [&](const char* a, const char* b) -> bool {
-            const char* la = a;
-            const char* lb = b;
-            strip(la, lb);
-            if (la == lb) {
-                if (beyond) return false;  // the chunk that owns this line reports it
-                uint64_t off = (uint64_t)(a - text);
-                if (off < R.err_off) { R.err_off = off; R.err_code = SKR_ERR_FASTA_BLANK; }
-                return false;
-            }
-            if (*la == '>') {
-                if (beyond) return false;  // next chunk's record: our last record is complete
-                Rec r;
-                r.hdr_off = (uint64_t)(la - text);
-                r.hdr_len = (uint64_t)(lb - la);
-                r.body_off = (uint64_t)(b - text);
-                r.body_len = 0;
-                r.bases = 0;
-                R.recs.push_back(r);
-                in_record = true;
-                return true;
-            }
-            if (!in_record) {  // sequence line of a record opened in an earlier chunk
-                if (t == 0) { R.first_line_not_header = true; return false; }
-                return true;
-            }
-            Rec& r = R.recs.back();
-            if (r.body_len == 0) r.body_off = (uint64_t)(a - text);
-            r.body_len = (uint64_t)(b - text) - r.body_off;
-            r.bases += (uint64_t)(lb - la);
-            return true;
-        };
-        auto on_clean = [&](const char* a, uint64_t nbases, const char* last_end) -> bool {
-            if (!in_record) {  // sequence lines of a record opened in an earlier chunk
-                if (t == 0) { R.first_line_not_header = true; return false; }
-                return true;
-            }
-            Rec& r = R.recs.back();
-            if (r.body_len == 0) r.body_off = (uint64_t)(a - text);
-            r.body_len = (uint64_t)(last_end - text) - r.body_off;
-            r.bases += nbases;
-            return true;
-        };
-        const bool fast = use_avx2 && !getenv("SKR_PACK_NO_FAST_SCAN");
-        const char* next = fast ? for_each_line_fast(text, from, to, end, on_line, on_clean)
-                                : (use_avx2 ? for_each_line_avx2(text, from, to, end, on_line)
-                                            : for_each_line(text, from, to, end, on_line));
-        if (next && in_record && next < end) {
-            beyond = true;
-            if (fast) for_each_line_fast(text, next, end, end, on_line, on_clean);
-            else if (use_avx2) for_each_line_avx2(text, next, end, end, on_line);
-            else for_each_line(text, next, end, end, on_line);
-        }
+        scan_slice(cx, text + nbytes * (size_t)t / (size_t)T, text + nbytes * (size_t)(t + 1) / (size_t)T, t == 0, res[t]);
     });
 
     // the earliest error wins: the reference stops at the first offending line
@@ -802,10 +1224,7 @@ static int pack_fasta_buffer(const void* text_v, size_t nbytes, const uint8_t* l
         }
     }
     if (err_code) {
-        int64_t line = 1;
-        for (const char* p = text; p < text + err_off; ++p) {
-            if (*p == '\n' || (*p == '\r' && p[1] != '\n')) ++line;
-        }
+        const int64_t line = line_of_offset(text, err_off);
         g_error_line = line;
         if (err_code == SKR_ERR_FASTA_BLANK)
             return skr::fail(err_code, "string index out of range (blank line %lld in FASTA)", (long long)line);
@@ -915,18 +1334,24 @@ extern "C" int skr_pack_sequences(const void* letters_v, const int64_t* offs, in
 extern "C" void skr_packed_free(SkrPacked* p) {
     if (!p) return;
     skr_packed_wait(p);  // background packing writes into the slab
+    if (p->wave) {       // a failed job is kept for its error message
+        delete p->wave;
+        p->wave = nullptr;
+    }
     slab_free(p->slab);
+    slab_free(p->retired);
     delete p;
 }
 
-extern "C" int64_t skr_packed_num_records(const SkrPacked* p) { return p->m; }
-extern "C" int64_t skr_packed_num_blocks(const SkrPacked* p) { return p->nblocks; }
-extern "C" int64_t skr_packed_total_bases(const SkrPacked* p) { return p->total_bases; }
+// -1 when a background scan ended with an error (skr_packed_wait reports it)
+extern "C" int64_t skr_packed_num_records(const SkrPacked* p) { return table_ready(p) ? p->m : -1; }
+extern "C" int64_t skr_packed_num_blocks(const SkrPacked* p) { return table_ready(p) ? p->nblocks : -1; }
+extern "C" int64_t skr_packed_total_bases(const SkrPacked* p) { return table_ready(p) ? p->total_bases : -1; }
 extern "C" const uint32_t* skr_packed_codes(const SkrPacked* p) { return p->codes; }
 extern "C" const uint32_t* skr_packed_mask(const SkrPacked* p) { return p->mask; }
 extern "C" const uint64_t* skr_packed_block_offsets(const SkrPacked* p) { return p->blk_off; }
 extern "C" const uint32_t* skr_packed_lengths(const SkrPacked* p) { return p->len; }
-extern "C" const uint64_t* skr_packed_header_spans(const SkrPacked* p) { return p->header_spans.data(); }
-extern "C" const uint64_t* skr_packed_body_spans(const SkrPacked* p) { return p->body_spans.data(); }
+extern "C" const uint64_t* skr_packed_header_spans(const SkrPacked* p) { return table_ready(p) ? p->header_spans.data() : nullptr; }
+extern "C" const uint64_t* skr_packed_body_spans(const SkrPacked* p) { return table_ready(p) ? p->body_spans.data() : nullptr; }
 extern "C" const void* skr_packed_slab(const SkrPacked* p) { return p->slab.ptr; }
 extern "C" size_t skr_packed_slab_bytes(const SkrPacked* p) { return p->slab_bytes; }

@@ -18,6 +18,7 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -56,10 +57,17 @@ double now_ms() {
 
 }  // namespace
 
-extern "C" int skr_stream_counts(SkrPacked* packed, const SkrStreamArgs* sa, void* stream_v) {
+extern "C" int skr_stream_counts(SkrPacked* packed, SkrStreamArgs* sa, void* stream_v) {
     if (!packed || !sa) return skr::fail(SKR_ERR_ARG, "skr_stream_counts: null argument");
-    const int64_t m = skr_packed_num_records(packed);
-    if (m == 0) return SKR_OK;
+    sa->records_done = 0;
+    // a handle whose scan still runs (large texts) has no record count yet: the chunks follow the scan
+    int64_t avail = 0;
+    int fin = 0;
+    int rc = skr_packed_wait_scanned(packed, 0, &avail, &fin);
+    if (rc != SKR_OK) return rc;
+    const int64_t capacity = sa->capacity_records > 0 ? sa->capacity_records : skr_packed_num_records(packed);
+    if (capacity < 0) return skr_packed_wait(packed);  // the scan failed: its error
+    if (fin && avail == 0) return SKR_OK;
     if (!sa->d_slab || !sa->count.d_out) return skr::fail(SKR_ERR_ARG, "skr_stream_counts: device slab and device matrix are required");
     if (sa->count.out_is_f64) return skr::fail(SKR_ERR_ARG, "skr_stream_counts: float32 matrices only");
     const int k = sa->count.k;
@@ -68,7 +76,7 @@ extern "C" int skr_stream_counts(SkrPacked* packed, const SkrStreamArgs* sa, voi
     if (sa->h_out && sa->h_ld < cols) return skr::fail(SKR_ERR_ARG, "skr_stream_counts: host pitch < 4^k");
     cudaStream_t s_k = (cudaStream_t)stream_v;
     StreamRes* res = nullptr;
-    int rc = get_streams(&res);
+    rc = get_streams(&res);
     if (rc != SKR_OK) return rc;
     const bool profile = getenv("SKR_STREAM_PROFILE") != nullptr;
     const double t_begin = now_ms();
@@ -82,31 +90,16 @@ extern "C" int skr_stream_counts(SkrPacked* packed, const SkrStreamArgs* sa, voi
     const uint32_t* h_len = skr_packed_lengths(packed);
     const size_t off_codes = (size_t)((const char*)h_codes - h_slab), off_mask = (size_t)((const char*)h_mask - h_slab);
     const size_t off_blk = (size_t)((const char*)h_blk - h_slab), off_len = (size_t)((const char*)h_len - h_slab);
-    const int64_t nblocks = skr_packed_num_blocks(packed);
 
     // chunks: a small first one so the pipeline fills quickly, then ~chunk_bytes of output each
     int64_t per = sa->chunk_records > 0 ? sa->chunk_records : std::max<int64_t>(256, ((int64_t)32 << 20) / (cols * 4));
     const bool ring = sa->h_out && !sa->h_out_pinned;
     if (ring) per = std::min<int64_t>(per, std::max<int64_t>(64, ((int64_t)8 << 20) / (cols * 4)));
-    std::vector<Chunk> chunks;
-    for (int64_t r = 0; r < m;) {
-        int64_t n = chunks.empty() ? std::max<int64_t>(64, per / 4) : per;
-        Chunk c;
-        c.r0 = r;
-        c.r1 = std::min(m, r + n);
-        chunks.push_back(c);
-        r = c.r1;
-    }
-    const int nchunks = (int)chunks.size();
+    const int64_t first = std::max<int64_t>(64, per / 4);
+    const int max_chunks = (int)(capacity / per + 3);
+    std::vector<Chunk> chunks((size_t)max_chunks);
+    std::atomic<int> nchunks{-1};  // known when the last chunk has been issued
 
-    // the record table first: it is complete before any code word is packed
-    SKR_CUDA_CHECK(cudaMemcpyAsync(d_slab + off_blk, h_blk, (size_t)(m + 1) * 8, cudaMemcpyHostToDevice, res->in));
-    SKR_CUDA_CHECK(cudaMemcpyAsync(d_slab + off_len, h_len, (size_t)m * 4, cudaMemcpyHostToDevice, res->in));
-    // trailing pad block (written by the allocator, not by the pack threads)
-    SKR_CUDA_CHECK(cudaMemcpyAsync(d_slab + off_codes + (size_t)(nblocks - 1) * 16, (const char*)h_codes + (size_t)(nblocks - 1) * 16, 16,
-                                   cudaMemcpyHostToDevice, res->in));
-    SKR_CUDA_CHECK(cudaMemcpyAsync(d_slab + off_mask + (size_t)(nblocks - 1) * 8, (const char*)h_mask + (size_t)(nblocks - 1) * 8, 8,
-                                   cudaMemcpyHostToDevice, res->in));
     // whatever the caller enqueued on its stream (vectors, the speculation cell) comes before the first kernel, and
     // the copy-in stream must not overwrite a slab an earlier launch on that stream still reads
     cudaEvent_t start_ev;
@@ -120,9 +113,7 @@ extern "C" int skr_stream_counts(SkrPacked* packed, const SkrStreamArgs* sa, voi
     size_t slot_bytes = 0;
     char* slots[kSlots] = {nullptr, nullptr, nullptr, nullptr};
     if (ring) {
-        int64_t max_rows = 0;
-        for (auto& c : chunks) max_rows = std::max(max_rows, c.r1 - c.r0);
-        slot_bytes = (size_t)max_rows * cols * 4;
+        slot_bytes = (size_t)std::max(per, first) * cols * 4;
         for (int i = 0; i < kSlots; ++i) {
             rc = skr_host_alloc(slot_bytes, (void**)&slots[i]);
             if (rc != SKR_OK) {
@@ -134,8 +125,8 @@ extern "C" int skr_stream_counts(SkrPacked* packed, const SkrStreamArgs* sa, voi
     }
     // copier threads for the ring: each drains whole chunks (event wait, then memcpy of its rows)
     std::atomic<int> copy_next{0}, copy_fail{0};
-    std::vector<std::atomic<int>> issued(nchunks), drained(nchunks);
-    for (int i = 0; i < nchunks; ++i) { issued[i].store(0); drained[i].store(0); }
+    std::vector<std::atomic<int>> issued((size_t)max_chunks), drained((size_t)max_chunks);
+    for (int i = 0; i < max_chunks; ++i) { issued[i].store(0); drained[i].store(0); }
     std::vector<std::thread> copiers;
     const int dev = res->dev;
     if (ring) {
@@ -145,9 +136,10 @@ extern "C" int skr_stream_counts(SkrPacked* packed, const SkrStreamArgs* sa, voi
                 cudaSetDevice(dev);
                 for (;;) {
                     const int i = copy_next.fetch_add(1);
-                    if (i >= nchunks) break;
-                    while (!issued[i].load(std::memory_order_acquire)) {
-                        if (copy_fail.load()) return;
+                    for (;;) {  // chunk i issued, or no chunk i
+                        const int n = nchunks.load(std::memory_order_acquire);
+                        if ((n >= 0 && i >= n) || copy_fail.load()) return;
+                        if (i < max_chunks && issued[i].load(std::memory_order_acquire)) break;
                         std::this_thread::yield();
                     }
                     const Chunk& c = chunks[i];
@@ -168,16 +160,36 @@ extern "C" int skr_stream_counts(SkrPacked* packed, const SkrStreamArgs* sa, voi
 
     int status = SKR_OK;
     double t_first_kernel = 0, t_last_issue = 0;
-    for (int i = 0; i < nchunks && status == SKR_OK; ++i) {
+    int64_t r = 0;
+    int i = 0;
+    for (; status == SKR_OK; ++i) {
+        // ---- the next chunk's records: in the table (scan), then packed
+        const int64_t want = r + (i == 0 ? first : per);
+        status = skr_packed_wait_scanned(packed, want, &avail, &fin);
+        if (status != SKR_OK) break;
+        const int64_t r1 = std::min(want, avail);
+        if (r1 == r) break;  // fin: nothing left
+        if (r1 > capacity || i >= max_chunks) {
+            status = skr::fail(SKR_ERR_CAPACITY, "skr_stream_counts: more records than the %lld the buffers were sized for", (long long)capacity);
+            break;
+        }
         Chunk& c = chunks[i];
+        c.r0 = r;
+        c.r1 = r1;
         cudaEventCreateWithFlags(&c.in_done, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&c.k_done, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&c.out_done, cudaEventDisableTiming);
-        // ---- wait for the packer, then copy the chunk's code and mask words in
-        skr_packed_wait_records(packed, c.r1);
+        status = skr_packed_wait_records(packed, c.r1);
+        if (status != SKR_OK) break;
+        // ---- its table entries and its code and mask words go in
         const uint64_t b0 = h_blk[c.r0], b1 = h_blk[c.r1];
-        cudaError_t e = cudaSuccess;
-        if (b1 > b0) {
+        uint32_t longest = 0;
+        for (int64_t q = c.r0; q < c.r1; ++q) longest = std::max(longest, h_len[q]);
+        cudaError_t e = cudaMemcpyAsync(d_slab + off_blk + (size_t)c.r0 * 8, h_blk + c.r0, (size_t)(c.r1 - c.r0 + 1) * 8,
+                                        cudaMemcpyHostToDevice, res->in);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(d_slab + off_len + (size_t)c.r0 * 4, h_len + c.r0, (size_t)(c.r1 - c.r0) * 4, cudaMemcpyHostToDevice, res->in);
+        if (b1 > b0 && e == cudaSuccess) {
             e = cudaMemcpyAsync(d_slab + off_codes + b0 * 16, (const char*)h_codes + b0 * 16, (size_t)(b1 - b0) * 16,
                                 cudaMemcpyHostToDevice, res->in);
             if (e == cudaSuccess)
@@ -194,6 +206,7 @@ extern "C" int skr_stream_counts(SkrPacked* packed, const SkrStreamArgs* sa, voi
         a.d_block_offsets = (const uint64_t*)(d_slab + off_blk) + c.r0;
         a.d_lengths = (const uint32_t*)(d_slab + off_len) + c.r0;
         a.m = c.r1 - c.r0;
+        a.max_length = (int64_t)longest;
         a.d_out = (char*)sa->count.d_out + (size_t)c.r0 * (size_t)sa->count.ld_out * 4;
         status = skr_count_ex(&a, s_k);
         if (status != SKR_OK) break;
@@ -222,27 +235,45 @@ extern "C" int skr_stream_counts(SkrPacked* packed, const SkrStreamArgs* sa, voi
         }
         if (e != cudaSuccess) { status = skr::fail(SKR_ERR_CUDA, "skr_stream_counts: %s", cudaGetErrorString(e)); break; }
         issued[i].store(1, std::memory_order_release);
+        r = c.r1;
     }
+    const int issued_chunks = i;  // chunk i (if the loop stopped inside it) was not issued
+    nchunks.store(issued_chunks, std::memory_order_release);
     t_last_issue = now_ms();
+    const std::string first_error = status != SKR_OK ? skr::last_error() : std::string();
     if (status != SKR_OK) copy_fail.store(1);
     for (auto& t : copiers) t.join();
     cudaError_t e1 = cudaStreamSynchronize(res->out);
     cudaError_t e2 = cudaStreamSynchronize(res->in);
+    if (status == SKR_OK) {
+        // the trailing pad block (written when the table was completed, not by the pack threads)
+        const int64_t nblocks = skr_packed_num_blocks(packed);
+        cudaMemcpyAsync(d_slab + off_codes + (size_t)(nblocks - 1) * 16, (const char*)h_codes + (size_t)(nblocks - 1) * 16, 16,
+                        cudaMemcpyHostToDevice, s_k);
+        cudaMemcpyAsync(d_slab + off_mask + (size_t)(nblocks - 1) * 8, (const char*)h_mask + (size_t)(nblocks - 1) * 8, 8,
+                        cudaMemcpyHostToDevice, s_k);
+    }
     // the caller's stream continues after the last chunk; nothing later on it may race with our copy-out reads
-    if (status == SKR_OK && !chunks.empty() && chunks.back().out_done && sa->h_out) cudaStreamWaitEvent(s_k, chunks.back().out_done, 0);
+    if (status == SKR_OK && issued_chunks > 0 && chunks[issued_chunks - 1].out_done && sa->h_out)
+        cudaStreamWaitEvent(s_k, chunks[issued_chunks - 1].out_done, 0);
     for (auto& c : chunks) {
         if (c.in_done) cudaEventDestroy(c.in_done);
         if (c.k_done) cudaEventDestroy(c.k_done);
         if (c.out_done) cudaEventDestroy(c.out_done);
     }
     cudaEventDestroy(start_ev);
-    for (int i = 0; i < kSlots; ++i) if (slots[i]) skr_host_free(slots[i]);
-    if (status == SKR_OK && (e1 != cudaSuccess || e2 != cudaSuccess))
-        status = skr::fail(SKR_ERR_CUDA, "skr_stream_counts: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
-    if (status == SKR_OK && copy_fail.load()) status = skr::fail(SKR_ERR_CUDA, "skr_stream_counts: copy-out failed");
+    for (int q = 0; q < kSlots; ++q) if (slots[q]) skr_host_free(slots[q]);
+    if (status != SKR_OK) {
+        skr::last_error() = first_error;
+        return status;
+    }
+    if (e1 != cudaSuccess || e2 != cudaSuccess)
+        return skr::fail(SKR_ERR_CUDA, "skr_stream_counts: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    if (copy_fail.load()) return skr::fail(SKR_ERR_CUDA, "skr_stream_counts: copy-out failed");
+    sa->records_done = r;
     if (profile)
         fprintf(stderr, "skr_stream: %d chunks (%s destination), first kernel issued at %.2f ms, last chunk issued at %.2f ms, done at %.2f ms\n",
-                nchunks, ring ? "pageable, pinned ring" : (sa->h_out ? "pinned" : "no host"), t_first_kernel - t_begin, t_last_issue - t_begin,
-                now_ms() - t_begin);
-    return status;
+                issued_chunks, ring ? "pageable, pinned ring" : (sa->h_out ? "pinned" : "no host"), t_first_kernel - t_begin,
+                t_last_issue - t_begin, now_ms() - t_begin);
+    return SKR_OK;
 }

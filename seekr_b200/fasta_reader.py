@@ -44,6 +44,12 @@ _LOWER_TO_INVALID = bytes(0 if ord("a") <= b <= ord("z") else b for b in range(2
 
 def default_pack_threads():
     """Host threads for the packer: all cores, divided among the ranks of a torchrun launch on this node."""
+    try:
+        forced = int(os.environ.get("SEEKR_B200_PACK_THREADS", "0"))
+    except ValueError:
+        forced = 0
+    if forced > 0:
+        return min(forced, 256)
     cores = os.cpu_count() or 1
     try:
         local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
@@ -55,12 +61,25 @@ def default_pack_threads():
 class PackedFasta:
     """Owner of one SkrPacked handle plus the source text it was parsed from."""
 
-    def __init__(self, handle, text=None):
+    # attributes that need the COMPLETE record table; for a handle whose scan still runs in the background (large
+    # texts, background=True) they are resolved on first use, which waits for the scan and raises what it found
+    _TABLE_ATTRS = frozenset(("m", "nblocks", "total_bases", "slab_ptr", "slab_bytes", "off_codes", "off_mask",
+                              "off_blk", "off_len", "max_length"))
+
+    def __init__(self, handle, text=None, scanning=False):
         self._lib = _lib.load()
         self._h = handle
         self._text = text  # bytes-like (mmap or bytes) or None for skr_pack_sequences input
-        lib = self._lib
-        self.m = int(lib.skr_packed_num_records(handle))
+        if not scanning:
+            self._resolve()
+
+    def _resolve(self):
+        lib, handle = self._lib, self._h
+        m = int(lib.skr_packed_num_records(handle))
+        if m < 0:  # the background scan found an error: raise it as the synchronous call would have
+            _lib.check(lib.skr_packed_wait(handle))
+            raise _lib.SeekrB200Error("background scan failed")
+        self.m = m
         self.nblocks = int(lib.skr_packed_num_blocks(handle))
         self.total_bases = int(lib.skr_packed_total_bases(handle))
         self.slab_ptr = lib.skr_packed_slab(handle)
@@ -72,6 +91,23 @@ class PackedFasta:
         self.off_len = (lib.skr_packed_lengths(handle) or 0) - base
         # the longest record (the record table is final even while a background packer still runs)
         self.max_length = int(self.lengths.max()) if self.m else 0
+
+    def __getattr__(self, name):
+        # reached only when the attribute is not set yet: a handle that is still being scanned
+        if name in PackedFasta._TABLE_ATTRS and self.__dict__.get("_h") is not None:
+            self._resolve()
+            return self.__dict__[name]
+        raise AttributeError(name)
+
+    @property
+    def scanning(self):
+        """True while the record count is not known yet (nothing has asked for it)."""
+        return "m" not in self.__dict__
+
+    def capacity(self):
+        """Records and slab bytes the handle is laid out for (>= the final figures while the scan runs)."""
+        lib = self._lib
+        return int(lib.skr_packed_capacity_records(self._h)), int(lib.skr_packed_slab_bytes(self._h))
 
     # -- construction ---------------------------------------------------------------------------
     @classmethod
@@ -102,7 +138,13 @@ class PackedFasta:
         pack = lib.skr_pack_fasta_buffer_async if background else lib.skr_pack_fasta_buffer
         rc = pack(addr, n, ctypes.c_void_p(lut.ctypes.data), nthreads, int(pinned), ctypes.byref(out))
         _lib.check(rc)
-        obj = cls(out, text)
+        # large texts come back while the scan is still running: the record table is resolved on first use
+        scanning = False
+        if background:
+            avail, fin = ctypes.c_int64(), ctypes.c_int()
+            rc = lib.skr_packed_wait_scanned(out, 0, ctypes.byref(avail), ctypes.byref(fin))
+            scanning = rc != _lib.SKR_OK or not fin.value
+        obj = cls(out, text, scanning=scanning)
         obj._pending = bool(background)
         return obj
 

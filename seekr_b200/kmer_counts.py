@@ -527,7 +527,9 @@ class CountEngine:
         mean=True / std=True, and Log2.post only with well-behaved supplied vectors (speculated shift).  Returns
         (device matrix, mean_vec, std_vec, host matrix or None), or None when the staged path must be used."""
         torch = self.torch
-        if mean is True or std is True or packed.m == 0 or packed.slab_ptr is None:
+        if mean is True or std is True:
+            return None
+        if not packed.scanning and (packed.m == 0 or packed.slab_ptr is None):
             return None
         mean_vec = mean if isinstance(mean, DeviceVector) else None
         std_vec = std if isinstance(std, DeviceVector) else None
@@ -537,10 +539,13 @@ class CountEngine:
         if mean_vec is not None and std_vec is not None and mean_vec.is_f64 != std_vec.is_f64:
             mean_vec, std_vec = mean_vec.as_f64(), std_vec.as_f64()
         vec_is_f64 = bool((mean_vec or std_vec).is_f64) if (mean_vec or std_vec) else False
-        m, cols = packed.m, self.cols
-        slab = torch.empty(max(packed.slab_bytes, 16), dtype=torch.uint8, device=device.current_device())
-        out = device.empty((m, cols), torch.float32)
-        host, pinned = (device.result_buffer((m, cols), np.float32) if want_host else (None, False))
+        # a text that is still being scanned (large files) has no record count yet: every buffer is sized for the
+        # packer's estimate and cut to the real count afterwards
+        cap, slab_bytes = packed.capacity()
+        cols = self.cols
+        slab = torch.empty(max(slab_bytes, 16), dtype=torch.uint8, device=device.current_device())
+        out = device.empty((cap, cols), torch.float32)
+        host, pinned = (device.result_buffer((cap, cols), np.float32) if want_host else (None, False))
         rstd = None
         if (std_vec is not None and not vec_is_f64 and std_vec.well_scaled and std_vec.positive
                 and (mean_vec is None or getattr(mean_vec, "bounded", False)) and self.fast_division):
@@ -548,7 +553,6 @@ class CountEngine:
         spec = self.spec_for(mean_vec, std_vec) if post else None
         sa = _lib.StreamArgs()
         a = sa.count
-        a.max_length = int(getattr(packed, "max_length", 0) or 0)
         a.k, a.log2_pre = self.k, 1 if self.log2 == "Log2.pre" else 0
         a.d_mean, a.d_std, a.d_rstd = device.ptr(mean_vec.t if mean_vec else None), device.ptr(std_vec.t if std_vec else None), device.ptr(rstd)
         a.vec_is_f64 = int(vec_is_f64)
@@ -563,9 +567,20 @@ class CountEngine:
         if host is not None:
             sa.h_out, sa.h_ld, sa.h_out_pinned = device.host_ptr(host), cols, int(pinned)
         sa.copy_threads = max(2, min(8, (os.cpu_count() or 4) // 2))
-        _lib.check(self.lib.skr_stream_counts(packed._h, ctypes.byref(sa), device.stream_ptr(self.stream)))
+        sa.capacity_records = cap
+        rc = self.lib.skr_stream_counts(packed._h, ctypes.byref(sa), device.stream_ptr(self.stream))
         device.sync(self.stream)
+        if rc == _lib.SKR_ERR_CAPACITY:
+            # the later part of the text holds more records per byte than its beginning promised: the packer has
+            # rebuilt an exact slab by the time wait() returns, and the staged route takes it from there
+            packed.wait()
+            return None
+        _lib.check(rc)
         packed.wait()
+        m = packed.m
+        if m != cap:
+            out = out[:m]
+            host = host[:m] if host is not None else None
         self._keep = (mean_vec, std_vec, rstd)
         self.std_applied = std_vec is not None
         dpk = DevicePacked(slab, packed)
@@ -676,7 +691,7 @@ class BasicCounter:
         self._map = None
 
         if self.seqs is not None:
-            if len(self.seqs) == 1 and self.std is True:
+            if self.std is True and len(self.seqs) == 1:  # (in this order: len() waits for a background scan)
                 err = (
                     "You cannot standardize a single sequence. "
                     "Please pass the path to an std. dev. array, "
@@ -822,21 +837,31 @@ class BasicCounter:
         torch = device.require_cuda()
         packed = self._get_packed()
         cols = self.alpha_len ** self.k
-        lengths = packed.lengths
-        if lengths.size and np.any(lengths.astype(np.int64) - self.k + 1 == 0):
-            raise ZeroDivisionError("division by zero")  # 1000 / (length - k + 1), kmer_counts.py:144
         if not 1 <= self.k <= 8:
             raise NotImplementedError("seekr_b200 counts k-mers for 1 <= k <= 8, got k=%r" % (self.k,))
+
+        def check_lengths():
+            lengths = packed.lengths
+            if lengths.size and np.any(lengths.astype(np.int64) - self.k + 1 == 0):
+                raise ZeroDivisionError("division by zero")  # 1000 / (length - k + 1), kmer_counts.py:144
+
+        # a large file may still be in the packer's scan: nothing here asks for the record table before the streamed
+        # path has had its chance to run alongside the scan (the checks that need the table come after it)
+        early = not (packed.scanning and self.silent)
+        if early:
+            check_lengths()
         bar = None if self.silent else my_tqdm()(total=packed.m, **({} if self.leave else
                                                                     {"desc": "Kmers", "leave": False}))
         engine = CountEngine(self.k, self.log2)
         mean = self.mean if isinstance(self.mean, bool) else DeviceVector.from_host(self.mean, cols)
         std = self.std if isinstance(self.std, bool) else DeviceVector.from_host(self.std, cols)
-        if packed.m == 0:
+        if early and packed.m == 0:
             self.counts = np.zeros([0, cols], dtype=np.float32)
             return
         device_only = getattr(self, "_device_only", False)
         streamed = engine.run_streamed(packed, mean, std, want_host=not device_only)
+        if not early:
+            check_lengths()
         if streamed is not None:
             out, mean_vec, std_vec, host = streamed
         else:

@@ -186,3 +186,83 @@ def test_fast_scan_lane_equals_line_by_line(threads, monkeypatch):
             else:
                 with pytest.raises(IndexError):
                     PackedFasta.from_buffer(text, nthreads=threads)
+
+
+def _force_waves(monkeypatch, slice_min=512):
+    monkeypatch.setenv("SEEKR_B200_WAVE_MIN_BYTES", "0")
+    monkeypatch.setenv("SEEKR_B200_WAVE_SLICE_MIN", str(slice_min))
+
+
+@pytest.mark.parametrize("threads", [2, 5, 16])
+def test_wave_packer_equals_one_shot(threads, monkeypatch):
+    """Large texts in background mode are scanned and packed wave by wave behind the caller (the record count is an
+    estimate until the last wave); forced onto small texts here, the finished handle must equal the one-shot one:
+    records that span several slices, CRLF, stress letters, no final newline, a single record."""
+    texts = [synth.fasta_bytes(400, seed=11, stress=True, lo=10, hi=3000),
+             synth.fasta_bytes(300, seed=12, wrap=60, lo=1, hi=200),
+             synth.fasta_bytes(40, seed=13, wrap=70, lo=20000, hi=60000),            # records longer than many slices
+             synth.fasta_bytes(200, seed=14, stress=True, wrap=33, lo=1, hi=900, newline=b"\r\n"),
+             synth.fasta_bytes(120, seed=15, wrap=60, lo=500, hi=900)[:-1],
+             b">only\n" + b"ACGT" * 5000 + b"\n"]
+    for text in texts:
+        monkeypatch.delenv("SEEKR_B200_WAVE_MIN_BYTES", raising=False)
+        one = _snapshot(PackedFasta.from_buffer(text, nthreads=threads))
+        _force_waves(monkeypatch)
+        for waves in ("16", "3"):
+            monkeypatch.setenv("SEEKR_B200_WAVES", waves)
+            packed = PackedFasta.from_buffer(text, nthreads=threads, background=True)
+            assert packed.scanning                      # nothing has asked for the record table yet
+            cap, _ = packed.capacity()
+            got = _snapshot(packed)
+            assert _same(one, got)
+            assert cap >= got[0] or cap < got[0]        # either sized well or rebuilt: equal both ways
+            assert packed.total_bases == int(one[1].astype(np.int64).sum())
+            assert packed.max_length == int(one[1].max())
+
+
+def test_wave_packer_rebuilds_when_the_estimate_is_too_small(monkeypatch):
+    """The slab is sized after the first wave from records per byte; a text that turns dense later (a few long
+    records, then thousands of tiny ones) overflows it: the job finishes the scan, packs an exact slab, and a
+    streaming consumer is told to restart (SKR_ERR_CAPACITY from skr_packed_wait_scanned)."""
+    import ctypes
+    from seekr_b200 import _lib
+    rng = np.random.default_rng(5)
+    long_part = b"".join(b">long%d\n" % i + bytes(rng.choice(list(b"ACGT"), size=40000).tolist()) + b"\n" for i in range(8))
+    short_part = b"".join(b">s%d\nACGTACGTAC\n" % i for i in range(6000))
+    text = long_part + short_part
+    one = _snapshot(PackedFasta.from_buffer(text, nthreads=4))
+    _force_waves(monkeypatch, 2048)
+    packed = PackedFasta.from_buffer(text, nthreads=4, background=True)
+    cap, _ = packed.capacity()
+    assert cap < one[0]
+    lib = _lib.load()
+    avail, fin = ctypes.c_int64(), ctypes.c_int()
+    rc = lib.skr_packed_wait_scanned(packed._h, -1, ctypes.byref(avail), ctypes.byref(fin))
+    assert rc == _lib.SKR_ERR_CAPACITY
+    assert _same(one, _snapshot(packed))
+    assert packed.sequence(8) == "ACGTACGTAC" and packed.header(6007) == ">s5999"
+
+
+@pytest.mark.parametrize("threads", [2, 7])
+def test_wave_packer_reports_errors_like_the_one_shot_scan(threads, tmp_path, monkeypatch):
+    """A format error in the first wave is raised by the call itself; one further down (the call has returned by
+    then) by the first thing that needs the record table -- the same exception type either way."""
+    _force_waves(monkeypatch)
+    good = synth.fasta_bytes(300, seed=21, wrap=60, lo=100, hi=600)
+    cases = {
+        "blank_late": (good + b">x\nACGT\n\nAC\n", IndexError),
+        "header_header_late": (good + b">x\nACGT\n>y\n>z\nAA\n", AssertionError),
+        "blank_first": (b">h1\nACGT\n\nAC\n" + good, IndexError),
+        "not_fasta": (b"ACGT\n" + good, ValueError),
+    }
+    for name, (text, exc) in cases.items():
+        with pytest.raises(exc):
+            PackedFasta.from_buffer(text, nthreads=threads)       # one-shot: at the call
+        with pytest.raises(exc):
+            packed = PackedFasta.from_buffer(text, nthreads=threads, background=True)
+            packed.m
+        with pytest.raises(exc):
+            PackedFasta.from_buffer(text, nthreads=threads, background=True).wait()
+    # an empty last record is allowed (fasta_reader.py:58 only asserts between records)
+    text = good + b">empty_last\n"
+    assert PackedFasta.from_buffer(text, nthreads=threads, background=True).m == PackedFasta.from_buffer(text, nthreads=threads).m
