@@ -791,6 +791,7 @@ struct WaveJob {
     SimdAlphabet al;
     uint8_t lut2[256];
     bool pinned;
+    int device = -1;  // the caller's CUDA device: worker 0 allocates the pinned slab, which must not wake device 0
     int T;
     size_t slice_bytes;
     int64_t nslices, nwaves;
@@ -959,6 +960,7 @@ struct WaveJob {
     void worker(int t) {
         int sense = 0;
         const char* text = cx.text;
+        if (t == 0 && pinned && device >= 0) cudaSetDevice(device);
         for (int64_t w = 0; w < nwaves; ++w) {
             const int64_t s = w * T + t;
             res[t] = ChunkResult();
@@ -1168,6 +1170,7 @@ static int pack_fasta_buffer(const void* text_v, size_t nbytes, const uint8_t* l
         job->al = al;
         memcpy(job->lut2, lut2, 256);
         job->pinned = pinned != 0;
+        if (job->pinned && cudaGetDevice(&job->device) != cudaSuccess) job->device = -1;
         job->T = T;
         int waves = 16;
         if (const char* env = getenv("SEEKR_B200_WAVES")) waves = std::max(1, atoi(env));

@@ -228,8 +228,12 @@ extern "C" int skr_stream_counts(SkrPacked* packed, SkrStreamArgs* sa, void* str
                 if (e == cudaSuccess)
                     e = cudaMemcpy2DAsync(slots[c.slot], row, src, (size_t)sa->count.ld_out * 4, row, rows, cudaMemcpyDeviceToHost, res->out);
             } else if (e == cudaSuccess) {
-                e = cudaMemcpy2DAsync((char*)sa->h_out + (size_t)c.r0 * (size_t)sa->h_ld * 4, (size_t)sa->h_ld * 4, src,
-                                      (size_t)sa->count.ld_out * 4, row, rows, cudaMemcpyDeviceToHost, res->out);
+                char* dst = (char*)sa->h_out + (size_t)c.r0 * (size_t)sa->h_ld * 4;
+                if (sa->h_ld == cols && sa->count.ld_out == cols)  // both sides dense: one linear copy
+                    e = cudaMemcpyAsync(dst, src, rows * row, cudaMemcpyDeviceToHost, res->out);
+                else
+                    e = cudaMemcpy2DAsync(dst, (size_t)sa->h_ld * 4, src, (size_t)sa->count.ld_out * 4, row, rows,
+                                          cudaMemcpyDeviceToHost, res->out);
             }
             if (e == cudaSuccess) e = cudaEventRecord(c.out_done, res->out);
         }

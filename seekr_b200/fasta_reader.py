@@ -128,6 +128,10 @@ class PackedFasta:
         lut = _lut if _lut is not None else alphabet_lut(alphabet)
         if nthreads <= 0 and len(text) > (1 << 22):
             nthreads = default_pack_threads()
+            if background and nthreads >= 8 and "SEEKR_B200_PACK_THREADS" not in os.environ:
+                # the packer runs beside the thread that drives the copy / count pipeline and the CUDA driver's own
+                # threads: two cores left to them finish earlier than all cores packing (profiles/r02_e2e_waves.txt)
+                nthreads -= 2
         n = len(text)
         if n:
             view = np.frombuffer(text, dtype=np.uint8)

@@ -695,6 +695,56 @@ def test_streamed_get_counts_equals_staged(mode, tmp_path):
     assert np.allclose(c.counts, exp0, rtol=0, atol=TOL)
 
 
+@pytest.mark.parametrize("mode", ["Log2.post", "Log2.none"])
+def test_streamed_get_counts_while_the_text_is_still_being_scanned(mode, tmp_path, monkeypatch):
+    """Large files are scanned wave by wave behind the streamed pipeline (forced onto a small file here): buffers
+    are sized for the packer's estimate and cut to the real count; a text that overflows the estimate restarts on
+    the rebuilt handle; a format error far down the file is raised by get_counts(); a record of k - 1 letters raises
+    the reference's ZeroDivisionError after the fact."""
+    k = 6
+    monkeypatch.setenv("SEEKR_B200_WAVE_MIN_BYTES", "0")
+    monkeypatch.setenv("SEEKR_B200_WAVE_SLICE_MIN", "4096")
+
+    def both(text, threads):
+        path = str(tmp_path / "w.fa")
+        with open(path, "wb") as handle:
+            handle.write(text)
+        monkeypatch.setenv("SEEKR_B200_NO_WAVES", "1")
+        ref = BasicCounter(path, k=k, mean=mean, std=std, log2=mode, silent=True)
+        ref.get_counts()
+        monkeypatch.delenv("SEEKR_B200_NO_WAVES")
+        monkeypatch.setenv("SEEKR_B200_PACK_THREADS", str(threads))
+        for pinned_result in (False, True):
+            device._cold_results = 0 if not pinned_result else 1
+            c = BasicCounter(path, k=k, mean=mean, std=std, log2=mode, silent=True)
+            c.get_counts()
+            assert c.counts.shape == ref.counts.shape and np.array_equal(c.counts, ref.counts)
+            assert np.array_equal(c.counts_device.cpu().numpy(), ref.counts)
+            assert len(c.seqs) == ref.counts.shape[0]
+        return path
+
+    rng = np.random.default_rng(3)
+    mean = (rng.random(4 ** k) * 0.3 + 0.1).astype(np.float32)
+    std = (rng.random(4 ** k) * 0.3 + 0.2).astype(np.float32)
+    both(synth.fasta_bytes(3000, seed=31, stress=True, lo=30, hi=4000), 5)
+    both(synth.fasta_bytes(3000, seed=32, wrap=60, lo=200, hi=900), 16)
+    # dense later than the first wave promises: the estimate overflows, the handle is rebuilt, the staged route runs
+    long_part = b"".join(b">long%d\n" % i + bytes(rng.choice(list(b"ACGT"), size=60000).tolist()) + b"\n" for i in range(8))
+    short_part = b"".join(b">s%d\nACGTACGTACGGT\n" % i for i in range(7000))
+    both(long_part + short_part, 4)
+    # errors that the call itself can no longer report
+    good = synth.fasta_bytes(2000, seed=33, wrap=60, lo=200, hi=900)
+    path = str(tmp_path / "bad.fa")
+    with open(path, "wb") as handle:
+        handle.write(good + b">x\nACGT\n\nAC\n")
+    with pytest.raises(IndexError):
+        BasicCounter(path, k=k, mean=mean, std=std, log2=mode, silent=True).get_counts()
+    with open(path, "wb") as handle:
+        handle.write(good + b">short\nACGTA\n" + good)
+    with pytest.raises(ZeroDivisionError):
+        BasicCounter(path, k=k, mean=mean, std=std, log2=mode, silent=True).get_counts()
+
+
 def test_full_size_log2_post_against_the_oracle():
     """BASELINE configs[1] size: 50 000 transcripts, k = 6, supplied vectors, Log2.post in one pass (speculated shift);
     a 5 000-row sample against the C restatement of the reference, the shift against the matrix's true minimum."""

@@ -211,11 +211,9 @@ def test_wave_packer_equals_one_shot(threads, monkeypatch):
         for waves in ("16", "3"):
             monkeypatch.setenv("SEEKR_B200_WAVES", waves)
             packed = PackedFasta.from_buffer(text, nthreads=threads, background=True)
-            assert packed.scanning                      # nothing has asked for the record table yet
-            cap, _ = packed.capacity()
+            # (packed.scanning is normally still True here; a text this small may already be through)
             got = _snapshot(packed)
             assert _same(one, got)
-            assert cap >= got[0] or cap < got[0]        # either sized well or rebuilt: equal both ways
             assert packed.total_bases == int(one[1].astype(np.int64).sum())
             assert packed.max_length == int(one[1].max())
 
