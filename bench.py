@@ -779,7 +779,8 @@ def run_ours(args):
         if it == 0:
             first_pass_s = t1 - t0
         counts_host = counter.counts
-        slab_bytes = counter._packed.slab_bytes
+        pk = counter._packed  # bytes the streamed path copies in: code + mask words of every block, the record table
+        slab_bytes = pk.nblocks * 24 + (pk.m + 1) * 8 + pk.m * 4
         sub = counts_host[:p_rows]
         r_host = skr_pearson.pearson(sub, sub)
         t2 = time.perf_counter()
