@@ -49,6 +49,7 @@ struct Chunk {
     int64_t r0 = 0, r1 = 0;
     cudaEvent_t in_done = nullptr, k_done = nullptr, out_done = nullptr;
     int slot = -1;
+    double t_issue = 0;  // host time the chunk's work was enqueued (profile)
 };
 
 double now_ms() {
@@ -103,7 +104,8 @@ extern "C" int skr_stream_counts(SkrPacked* packed, SkrStreamArgs* sa, void* str
     // whatever the caller enqueued on its stream (vectors, the speculation cell) comes before the first kernel, and
     // the copy-in stream must not overwrite a slab an earlier launch on that stream still reads
     cudaEvent_t start_ev;
-    SKR_CUDA_CHECK(cudaEventCreateWithFlags(&start_ev, cudaEventDisableTiming));
+    const unsigned ev_flags = profile ? cudaEventDefault : cudaEventDisableTiming;  // the profile prints a device timeline
+    SKR_CUDA_CHECK(cudaEventCreateWithFlags(&start_ev, ev_flags));
     SKR_CUDA_CHECK(cudaEventRecord(start_ev, s_k));
     SKR_CUDA_CHECK(cudaStreamWaitEvent(res->in, start_ev, 0));
     SKR_CUDA_CHECK(cudaStreamWaitEvent(res->out, start_ev, 0));
@@ -164,6 +166,9 @@ extern "C" int skr_stream_counts(SkrPacked* packed, SkrStreamArgs* sa, void* str
     int i = 0;
     for (; status == SKR_OK; ++i) {
         // ---- the next chunk's records: in the table (scan), then packed
+        // (chunks of 4 x `per` were tried for the pinned destination: fewer hand-overs, but 134 MB copies ran at
+        // 49.5 GB/s while the packer was still at work against 52.5 GB/s for 33 MB ones, and the last chunk's copy
+        // starts later: 15.8 against 15.2 ms, profiles/r02_e2e_timeline.txt)
         const int64_t want = r + (i == 0 ? first : per);
         status = skr_packed_wait_scanned(packed, want, &avail, &fin);
         if (status != SKR_OK) break;
@@ -176,9 +181,10 @@ extern "C" int skr_stream_counts(SkrPacked* packed, SkrStreamArgs* sa, void* str
         Chunk& c = chunks[i];
         c.r0 = r;
         c.r1 = r1;
-        cudaEventCreateWithFlags(&c.in_done, cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&c.k_done, cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&c.out_done, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&c.in_done, ev_flags);
+        cudaEventCreateWithFlags(&c.k_done, ev_flags);
+        cudaEventCreateWithFlags(&c.out_done, ev_flags);
+        c.t_issue = now_ms() - t_begin;
         status = skr_packed_wait_records(packed, c.r1);
         if (status != SKR_OK) break;
         // ---- its table entries and its code and mask words go in
@@ -260,6 +266,17 @@ extern "C" int skr_stream_counts(SkrPacked* packed, SkrStreamArgs* sa, void* str
     // the caller's stream continues after the last chunk; nothing later on it may race with our copy-out reads
     if (status == SKR_OK && issued_chunks > 0 && chunks[issued_chunks - 1].out_done && sa->h_out)
         cudaStreamWaitEvent(s_k, chunks[issued_chunks - 1].out_done, 0);
+    if (profile && status == SKR_OK && sa->h_out) {
+        fprintf(stderr, "skr_stream timeline (ms after the start event; host issue time in brackets):\n");
+        for (int q = 0; q < issued_chunks; ++q) {
+            float a = 0, b = 0, d = 0;
+            cudaEventElapsedTime(&a, start_ev, chunks[q].in_done);
+            cudaEventElapsedTime(&b, start_ev, chunks[q].k_done);
+            cudaEventElapsedTime(&d, start_ev, chunks[q].out_done);
+            fprintf(stderr, "  chunk %2d records %6lld-%6lld [%6.2f]  in %6.2f  counted %6.2f  out %6.2f\n", q, (long long)chunks[q].r0,
+                    (long long)chunks[q].r1, chunks[q].t_issue, a, b, d);
+        }
+    }
     for (auto& c : chunks) {
         if (c.in_done) cudaEventDestroy(c.in_done);
         if (c.k_done) cudaEventDestroy(c.k_done);
