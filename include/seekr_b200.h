@@ -153,6 +153,13 @@ typedef struct {
     uint32_t zero_seen; /* epoch of the last run in which a record with a zero count in column j* was seen */
 } SkrPostSpec;
 int skr_post_spec(const void* d_mean, const void* d_std, int vec_is_f64, int64_t cols, SkrPostSpec* d_spec, void* stream);
+/* ... and, when both vectors are given, the tail ((x - mean_j)/std_j + shift) + 1 of kmer_counts.py:169,175,208 as one
+ * multiply-add x * a_j + b_j: d_post_a[j] = RN(1/std_j); d_post_b[j] = the tail of a ZERO count in column j, evaluated
+ * with the reference's own fp32 operations, so empty bins keep the reference's bits and the matrix minimum is exactly
+ * log2(1) (16-byte aligned arrays of `cols` floats).  Every term is >= 0, nothing cancels: counted bins differ from the
+ * step-by-step tail by a few ulp before the log2.  skr_count_ex takes the arrays as d_post_a / d_post_b next to d_spec. */
+int skr_post_spec_affine(const void* d_mean, const void* d_std, int vec_is_f64, int64_t cols, SkrPostSpec* d_spec,
+                         float* d_post_a, float* d_post_b, void* stream);
 
 /* skr_count with every optional piece in one argument block (zero-initialise, then fill what is needed).
  * Beyond skr_count's arguments:
@@ -197,6 +204,8 @@ typedef struct {
     uint32_t spec_epoch;
     uint32_t reserved;
     SkrMinCell* d_min_reset;
+    const float* d_post_a; /* with d_spec: the Log2.post tail folded into log2(x * a_j + b_j) (skr_post_spec_affine) */
+    const float* d_post_b;
 } SkrCountArgs;
 int skr_count_ex(const SkrCountArgs* args, void* stream);
 int skr_colstat_finish(const double* d_colsum, const double* d_colsq, int64_t cols, int64_t total_rows, float* d_mean,

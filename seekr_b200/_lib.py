@@ -46,6 +46,7 @@ class CountArgs(ctypes.Structure):
         ("d_min", _vp), ("d_post", _vp), ("d_colmin", _vp), ("d_colsum", _vp), ("d_colsq", _vp),
         ("d_spec", _vp), ("d_skip", _vp), ("max_length", ctypes.c_uint32), ("skip_value", ctypes.c_uint32),
         ("spec_epoch", ctypes.c_uint32), ("reserved", ctypes.c_uint32), ("d_min_reset", _vp),
+        ("d_post_a", _vp), ("d_post_b", _vp),
     ]
 
 
@@ -90,6 +91,7 @@ SIGNATURES = {
     "skr_count": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _int, _vp, _vp, _int, _vp, _int, _i64, _vp, _vp, _vp, _vp]),
     "skr_count_ex": (_int, [ctypes.POINTER(CountArgs), _vp]),
     "skr_post_spec": (_int, [_vp, _vp, _int, _i64, _vp, _vp]),
+    "skr_post_spec_affine": (_int, [_vp, _vp, _int, _i64, _vp, _vp, _vp, _vp]),
     "skr_colstat_finish": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     "skr_post_log2_skip": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, ctypes.c_uint32, _vp]),
     "skr_colmin_reset": (_int, [_vp, _i64, _vp]),

@@ -62,6 +62,10 @@ struct CountParams {
     // speculative Log2.post (skr_post_spec): the shift in post_cell was derived from the vectors alone and is the
     // true matrix minimum iff some record has a zero count in column spec->zero_col; the kernel reports that
     SkrPostSpec* spec;
+    // ... and with it the whole tail folded into one multiply-add per value: a_j = 1/std_j, b_j = shift + 1 -
+    // mean_j/std_j (skr_post_spec_affine, binary64 then one rounding); out = log2(x * a_j + b_j)
+    const float* post_a;
+    const float* post_b;
     const uint32_t* skip_flag;    // the launch does nothing when *skip_flag == skip_value (device-side choice of the route)
     uint32_t skip_value;
     uint32_t spec_epoch;          // written to spec->zero_seen when a zero count is met in the arg-min column
@@ -825,7 +829,7 @@ __device__ __noinline__ void count_phase(const uint32_t* __restrict__ codes, con
 //   kBatchFast   fp32 mean, std and 1/std, no column minima / fused Log2.post,
 //   kBatchPost   kBatchFast + the Log2.post tail with a shift known before the launch (skr_post_spec),
 //   kBatchAny    everything decided at run time.
-enum { kBatchAny = 0, kBatchPlain = 1, kBatchFast = 2, kBatchPost = 3 };
+enum { kBatchAny = 0, kBatchPlain = 1, kBatchFast = 2, kBatchPost = 3, kBatchAffine = 4 };
 
 template <int K, bool kVecF64, int kMode, bool kMin, bool kColmin = false, bool kStats = false, bool kSplit = false>
 __global__ void __launch_bounds__(BatchCfg<K, kSplit>::kThreads, BatchCfg<K, kSplit>::kCtasPerSm) count_batch_kernel(const CountParams p) {
@@ -834,10 +838,12 @@ __global__ void __launch_bounds__(BatchCfg<K, kSplit>::kThreads, BatchCfg<K, kSp
     static_assert(kChunks == 1 || (!kColmin && !kStats && kMode != kBatchAny),
                   "k = 7 runs the plain, fast and post flavours here; the others stay with the CTA-per-record kernel");
     constexpr bool kRegVec = kMode == kBatchFast || kMode == kBatchPost;  // -mean, -std, 1/std in registers
+    constexpr bool kAffine = kMode == kBatchAffine;                       // a, b of the folded Log2.post tail in registers
     static_assert(!(kVecF64 && kMode != kBatchAny), "binary64 vectors take the generic epilogue");
     static_assert(!kColmin || kMode == kBatchPlain, "kColmin: column minima of the plain values (kBatchAny decides at run time)");
     static_assert(!kStats || kMode == kBatchPlain, "kStats: column sums of the plain values");
-    static_assert(!(kMin && kMode == kBatchPost), "the speculative Log2.post epilogue needs no running minimum");
+    static_assert(!(kMin && (kMode == kBatchPost || kAffine)), "the speculative Log2.post epilogue needs no running minimum");
+    static_assert(!(kAffine && (kVecF64 || kColmin || kStats)), "the folded tail: fp32 vectors, nothing else fused");
     if (p.skip_flag && *p.skip_flag == p.skip_value) return;
     if (p.min_reset && blockIdx.x == 0 && threadIdx.x == 0) { p.min_reset->min_ordered = skr::ordered_encode(INFINITY); p.min_reset->nan_seen = 0; }
     extern __shared__ __align__(16) uint32_t smem_b[];
@@ -860,7 +866,7 @@ __global__ void __launch_bounds__(BatchCfg<K, kSplit>::kThreads, BatchCfg<K, kSp
     uint32_t zsh = 0;
     uint32_t zseen = 0;
     int zpass = 0;  // kSplit: the pass whose columns hold the arg-min column
-    if ((kMode == kBatchAny || kMode == kBatchPost) && p.spec) {
+    if ((kMode == kBatchAny || kMode == kBatchPost || kAffine) && p.spec) {
         int zc = p.spec->zero_col;
         if (zc >= 0) {
             zpass = zc / Cfg::kBins;
@@ -875,7 +881,7 @@ __global__ void __launch_bounds__(BatchCfg<K, kSplit>::kThreads, BatchCfg<K, kSp
     float sx[kQc][4], sq[kQc][4];
 #pragma unroll
     for (int j = 0; j < kQc; ++j) {
-        if constexpr (!kRegVec) mv[j] = sv[j] = yv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if constexpr (!kRegVec && !kAffine) mv[j] = sv[j] = yv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int e = 0; e < 4; ++e) { cmin[j][e] = 0xFFFFFFFFu; sx[j][e] = 0.f; sq[j][e] = 0.f; }
     }
@@ -884,7 +890,10 @@ __global__ void __launch_bounds__(BatchCfg<K, kSplit>::kThreads, BatchCfg<K, kSp
 #pragma unroll
         for (int j = 0; j < kQc; ++j) {
             const int q = pass * Cfg::kQuads + qb + (ch * kQc + j) * kW;
-            if constexpr (kRegVec) {  // all three vectors are there (dispatch): unconditional, negated once
+            if constexpr (kAffine) {  // mv = a, sv = b
+                mv[j] = __ldg(reinterpret_cast<const float4*>(p.post_a) + q);
+                sv[j] = __ldg(reinterpret_cast<const float4*>(p.post_b) + q);
+            } else if constexpr (kRegVec) {  // all three vectors are there (dispatch): unconditional, negated once
                 const float4 m4 = __ldg(reinterpret_cast<const float4*>(p.mean) + q);
                 const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.std_) + q);
                 yv[j] = __ldg(reinterpret_cast<const float4*>(p.rstd) + q);
@@ -1023,7 +1032,15 @@ __global__ void __launch_bounds__(BatchCfg<K, kSplit>::kThreads, BatchCfg<K, kSp
                             sq[j][e] = __fmaf_rn(x[e], x[e], sq[j][e]);
                         }
                     }
-                    if constexpr (kRegVec) {
+                    if constexpr (kAffine) {
+                        // the whole tail in one FFMA2 per two columns, then the hardware log2
+                        const uint64_t z0 = skr::f2_fma(skr::f2_pack(x[0], x[1]), skr::f2_pack(mv[j].x, mv[j].y), skr::f2_pack(sv[j].x, sv[j].y));
+                        const uint64_t z1 = skr::f2_fma(skr::f2_pack(x[2], x[3]), skr::f2_pack(mv[j].z, mv[j].w), skr::f2_pack(sv[j].z, sv[j].w));
+                        skr::f2_unpack(z0, x[0], x[1]);
+                        skr::f2_unpack(z1, x[2], x[3]);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) x[e] = log2_post(x[e]);
+                    } else if constexpr (kRegVec) {
                         // mv / sv hold -mean / -std in these flavours (negated once, after the load); FADD2 / FMUL2 /
                         // FFMA2 do two columns per issue slot
                         uint64_t z0 = sub_div_by_rcp2(skr::f2_pack(x[0], x[1]), skr::f2_pack(mv[j].x, mv[j].y),
@@ -1165,6 +1182,7 @@ int dispatch_batch(const CountParams& wp, int sms, cudaStream_t stream) {
                 return mn7 ? launch_batch<K, false, kBatchPlain, true>(wp, sms, stream)
                            : launch_batch<K, false, kBatchPlain, false>(wp, sms, stream);
             constexpr bool kSp = K == 8;  // k = 8 with vectors: four column passes over a k = 7 sized histogram
+            if (wp.post_cell && wp.post_a) return launch_batch<K, false, kBatchAffine, false, false, false, kSp>(wp, sms, stream);
             if (wp.post_cell) return launch_batch<K, false, kBatchPost, false, false, false, kSp>(wp, sms, stream);
             return mn7 ? launch_batch<K, false, kBatchFast, true, false, false, kSp>(wp, sms, stream)
                        : launch_batch<K, false, kBatchFast, false, false, false, kSp>(wp, sms, stream);
@@ -1187,6 +1205,7 @@ int dispatch_batch(const CountParams& wp, int sms, cudaStream_t stream) {
                              : launch_batch<K, false, kBatchPlain, false>(wp, sms, stream);
         if (fast) return mn ? launch_batch<K, false, kBatchFast, true>(wp, sms, stream)
                             : launch_batch<K, false, kBatchFast, false>(wp, sms, stream);
+        if (post && wp.post_a) return launch_batch<K, false, kBatchAffine, false>(wp, sms, stream);
         if (post) return launch_batch<K, false, kBatchPost, false>(wp, sms, stream);
     }
     if (wp.colsum) return skr::fail(SKR_ERR_ARG, "skr_count: column sums go with plain counts (no vectors, no Log2.post)");
@@ -1598,6 +1617,8 @@ extern "C" int skr_count_ex(const SkrCountArgs* a, void* stream) {
         return skr::fail(SKR_ERR_ARG, "skr_count: column sums come in pairs and go with plain counts");
     if (a->d_colsum && (k < 4 || k > 6)) return skr::fail(SKR_ERR_ARG, "skr_count: in-kernel column sums are implemented for k = 4, 5, 6");
     if (a->d_spec && !a->d_post) return skr::fail(SKR_ERR_ARG, "skr_count: a speculation cell goes with a Log2.post shift");
+    if ((a->d_post_a == nullptr) != (a->d_post_b == nullptr) || (a->d_post_a && !a->d_post))
+        return skr::fail(SKR_ERR_ARG, "skr_count: the folded Log2.post tail needs both arrays and the shift they were built from");
     CountParams p{};
     p.codes = a->d_codes;
     p.mask = a->d_mask;
@@ -1615,6 +1636,8 @@ extern "C" int skr_count_ex(const SkrCountArgs* a, void* stream) {
     p.colmin = a->d_colmin;
     p.no_store = a->d_out == nullptr;
     p.spec = a->d_spec;
+    p.post_a = a->d_post_a;
+    p.post_b = a->d_post_b;
     p.skip_flag = a->d_skip;
     p.skip_value = a->skip_value ? a->skip_value : 1u;
     p.spec_epoch = a->spec_epoch ? a->spec_epoch : 1u;
@@ -1663,7 +1686,8 @@ extern "C" int skr_count(const uint32_t* d_codes, const uint32_t* d_mask, const 
 // Speculative Log2.post shift (see SkrPostSpec): min over the columns of the z-score of a ZERO count,
 // fl(fl(0 - mean_j) / std_j), and the first column that attains it.
 template <bool kVecF64>
-__global__ void __launch_bounds__(256) post_spec_kernel(const void* mean, const void* std_, long long cols, SkrPostSpec* spec) {
+__global__ void __launch_bounds__(256) post_spec_kernel(const void* mean, const void* std_, long long cols, SkrPostSpec* spec,
+                                                        float* post_a, float* post_b) {
     __shared__ float s_v[256];
     __shared__ long long s_j[256];
     float best = INFINITY;
@@ -1682,17 +1706,39 @@ __global__ void __launch_bounds__(256) post_spec_kernel(const void* mean, const 
         spec->shift.nan_seen = 0;
         spec->zero_col = (int32_t)bj;  // -1: nothing to speculate on (a NaN / +inf in every column): callers fall back
         spec->zero_seen = 0;
+        s_v[0] = bj >= 0 ? fabsf(best) : 0.0f;
     }
+    if (!post_a || !post_b || !mean || !std_) return;
+    // the tail ((x - mean) / std + shift) + 1 as x * a + b.  b_j is the reference's own value of a ZERO count in
+    // column j -- fl(fl(fl(fl(0 - mean_j) / std_j) + shift) + 1), the same fp32 operations -- so every empty bin
+    // (almost half of a 6-mer matrix) comes out with the reference's bits and the matrix minimum is exactly
+    // log2(1) = 0; a_j = RN(1 / std_j).  Every term of x * a + b is >= 0 (b_j >= 1), nothing cancels: a counted
+    // bin differs from the step-by-step tail by a few ulp before the log2.
+    __syncthreads();
+    const float shift = s_v[0];
+    for (long long j = threadIdx.x; j < cols; j += 256) {
+        const double sd = kVecF64 ? reinterpret_cast<const double*>(std_)[j] : (double)reinterpret_cast<const float*>(std_)[j];
+        const float z0 = ew_apply<OP_NORM, kVecF64>(0.0f, mean, std_, j, 0.0f);
+        post_a[j] = (float)(1.0 / sd);
+        post_b[j] = __fadd_rn(__fadd_rn(z0, shift), 1.0f);
+    }
+}
+
+extern "C" int skr_post_spec_affine(const void* d_mean, const void* d_std, int vec_is_f64, int64_t cols, SkrPostSpec* d_spec,
+                                    float* d_post_a, float* d_post_b, void* stream) {
+    if (!d_spec || cols <= 0 || (!d_mean && !d_std)) return skr::fail(SKR_ERR_ARG, "skr_post_spec: bad argument");
+    if ((d_post_a == nullptr) != (d_post_b == nullptr) || (d_post_a && (((uintptr_t)d_post_a | (uintptr_t)d_post_b) & 15)))
+        return skr::fail(SKR_ERR_ARG, "skr_post_spec_affine: a and b come together, 16-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (vec_is_f64) post_spec_kernel<true><<<1, 256, 0, s>>>(d_mean, d_std, cols, d_spec, d_post_a, d_post_b);
+    else post_spec_kernel<false><<<1, 256, 0, s>>>(d_mean, d_std, cols, d_spec, d_post_a, d_post_b);
+    SKR_LAUNCH_CHECK();
+    return SKR_OK;
 }
 
 extern "C" int skr_post_spec(const void* d_mean, const void* d_std, int vec_is_f64, int64_t cols, SkrPostSpec* d_spec,
                              void* stream) {
-    if (!d_spec || cols <= 0 || (!d_mean && !d_std)) return skr::fail(SKR_ERR_ARG, "skr_post_spec: bad argument");
-    cudaStream_t s = (cudaStream_t)stream;
-    if (vec_is_f64) post_spec_kernel<true><<<1, 256, 0, s>>>(d_mean, d_std, cols, d_spec);
-    else post_spec_kernel<false><<<1, 256, 0, s>>>(d_mean, d_std, cols, d_spec);
-    SKR_LAUNCH_CHECK();
-    return SKR_OK;
+    return skr_post_spec_affine(d_mean, d_std, vec_is_f64, cols, d_spec, nullptr, nullptr, stream);
 }
 
 // mean / std from the column sums the count kernel accumulated (accurate norm_vectors): binary64 throughout,

@@ -403,9 +403,9 @@ def test_deferred_normalisation_is_bit_identical_to_fused():
         std = (raw.std(axis=0) + 0.125).astype(np.float32)
         packed = PackedFasta.from_sequences(sub, pinned=True)
         outs = []
-        for deferred, speculative in ((True, False), (False, False), (False, True)):
+        for deferred, speculative, folded in ((True, False, False), (False, False, False), (False, True, False), (False, True, True)):
             eng = CountEngine(k, "Log2.post")
-            eng.deferred, eng.speculative = deferred, speculative
+            eng.deferred, eng.speculative, eng.folded_tail = deferred, speculative, folded
             dpk = eng.upload(packed)
             out, _, _ = eng.run(dpk, DeviceVector.from_host(mean, 4 ** k), DeviceVector.from_host(std, 4 ** k))
             outs.append(out.cpu().numpy())
@@ -415,6 +415,12 @@ def test_deferred_normalisation_is_bit_identical_to_fused():
         assert np.array_equal(outs[1], outs[2])
         exp, _, _ = c_oracle.normalise(raw, mean, std, "Log2.post")
         assert np.allclose(outs[0], exp, rtol=0, atol=TOL)
+        # the default: the tail folded into one multiply-add per value.  Empty bins keep the step-by-step bits (b_j is
+        # the reference's own value of a zero count), counted bins move by a few ulp before the log2
+        assert np.array_equal(outs[3][raw == 0], outs[2][raw == 0])
+        assert float(outs[3].min()) == 0.0
+        assert np.abs(outs[3].astype(np.float64) - outs[2].astype(np.float64)).max() < 2e-6
+        assert np.allclose(outs[3], exp, rtol=0, atol=TOL)
         # float64 vectors and mean-only / std-only variants
         for mv, sv in ((mean.astype(np.float64), std.astype(np.float64)), (mean, False), (False, std)):
             c = BasicCounter(k=k, mean=mv, std=sv, log2="Log2.post", silent=True)
@@ -611,7 +617,8 @@ def test_batch_kernel_matches_team_kernel(monkeypatch):
                 for vec_dtype, fast in ((None, True), (np.float32, True), (np.float32, False), (np.float64, True)):
                     eng = CountEngine(k, mode)
                     eng.fast_division = fast
-                    dpk = eng.upload(packed)
+                    eng.folded_tail = False   # bit-equality of the step-by-step flavours; the folded tail is the batch
+                    dpk = eng.upload(packed)  # kernel's alone (test_deferred_normalisation_is_bit_identical_to_fused)
                     mv = sv = None
                     if vec_dtype is not None:
                         mv = DeviceVector.from_host(mean.astype(vec_dtype), 4 ** k)
@@ -785,7 +792,13 @@ def test_full_size_log2_post_against_the_oracle():
     eng2 = CountEngine(k, "Log2.post")
     eng2.speculative = False
     dev2, _, _ = eng2.run(dpk, DeviceVector.from_host(mean, 4 ** k), DeviceVector.from_host(std, 4 ** k))
-    assert torch.equal(dev, dev2)
+    eng3 = CountEngine(k, "Log2.post")
+    eng3.folded_tail = False
+    dev3, _, _ = eng3.run(dpk, DeviceVector.from_host(mean, 4 ** k), DeviceVector.from_host(std, 4 ** k))
+    assert torch.equal(dev3, dev2)                   # one pass, step-by-step tail: the two-pass bits
+    fold = float((dev.double() - dev2.double()).abs().max())
+    assert fold < 2e-6, fold                         # folded tail (default): a few ulp before the log2
+    print("folded tail against the step-by-step tail at full size: max |diff| %.2e; against the oracle sample %.2e" % (fold, err))
 
 
 def test_hand_assigned_lower_case_is_not_upper_cased():

@@ -104,6 +104,12 @@ def main():
         spec.next_epoch()
         ms, mn = timeit(lambda: eng.count(dpk, out, mean, std, spec=spec), flush)
         report("count + speculative Log2.post", ms, mn, in_bytes + row_bytes)
+        eng.folded_tail = False
+        spec_u = PostSpec(eng, mean, std)
+        spec_u.next_epoch()
+        ms, mn = timeit(lambda: eng.count(dpk, out, mean, std, spec=spec_u), flush)
+        report("  (tail step by step, not folded)", ms, mn, in_bytes + row_bytes)
+        eng.folded_tail = True
         if k == 6:
             sums = torch.zeros((2, cols), dtype=torch.float64, device="cuda")
             ms, mn = timeit(lambda: eng.count(dpk, out, colsums=(sums[0], sums[1])), flush)
