@@ -951,6 +951,14 @@ __global__ void __launch_bounds__(BatchCfg<K, kSplit>::kThreads, BatchCfg<K, kSp
                 mt.inc[rr] = inc;
                 mt.store[rr] = store;
                 units = (uint32_t)(nwin >> 5);  // whole units; the ragged rest is the record's tail unit
+                if constexpr (kMode == kBatchAffine) {
+                    // folded Log2.post tail: the value of a bin seen c times is c * inc in fp32 (one rounding of the
+                    // product; 1.2e-7 from the chain below, far inside what the log2 behind it lets through), taken
+                    // from the counter with the 2^23 trick -- no table, no shuffles in the epilogue
+                    const float incf = __double2float_rn(inc);
+                    mt.tab[rr][0] = incf;
+                    mt.tab[rr][1] = -8388608.0f * incf;  // exact (a power of two)
+                } else {
                 double acc = 0.0;  // the literal chain of kmer_counts.py:144-150 for counts below kTab
                 mt.tab[rr][0] = p.log2_pre ? log2f(1.0f) : 0.0f;
 #pragma unroll 8
@@ -959,6 +967,7 @@ __global__ void __launch_bounds__(BatchCfg<K, kSplit>::kThreads, BatchCfg<K, kSp
                     float v = __double2float_rn(acc);
                     if (p.log2_pre) v = log2f(__fadd_rn(v, 1.0f));
                     mt.tab[rr][c] = v;
+                }
                 }
             }
             uint32_t incl = units;  // inclusive scan over the lanes of the round
@@ -999,7 +1008,9 @@ __global__ void __launch_bounds__(BatchCfg<K, kSplit>::kThreads, BatchCfg<K, kSp
             for (int r = gi; r < nrec; r += kG) {
                 if (!mt.store[r]) continue;
                 const uint32_t tab_addr = skr::smem_u32(&mt.tab[r][0]);
-                const float treg = lds_f32(tab_addr + (uint32_t)lane * 4);  // lane c holds the value of a bin seen c times
+                // lane c holds the value of a bin seen c times (kAffine: lanes 0 / 1 hold inc and -2^23 inc)
+                const float treg = lds_f32(tab_addr + (kAffine ? 0u : (uint32_t)lane * 4));
+                const float tneg = kAffine ? lds_f32(tab_addr + 4) : 0.0f;
                 const uint32_t hrec = hist_addr + (uint32_t)r * Cfg::kHistBytes;
                 float* __restrict__ orow = reinterpret_cast<float*>(p.out) + (size_t)(mt.rec0 + r) * (size_t)p.ld_out +
                                            (Cfg::kPasses > 1 ? (size_t)mt.pass * Cfg::kBins : 0);
@@ -1013,6 +1024,21 @@ __global__ void __launch_bounds__(BatchCfg<K, kSplit>::kThreads, BatchCfg<K, kSp
                     const uint2 v = lds_v2(a);
                     sts_zero_v2(a);
                     float x[4];
+                    if constexpr (kAffine) {
+                        // 0x4B000000 | c is the float 2^23 + c: (2^23 + c) * inc - 2^23 * inc = RN(c * inc) in one FFMA2
+                        // per two columns, then the folded tail in another, then the hardware log2
+                        const uint64_t inc2 = skr::f2_pack(treg, treg), neg2 = skr::f2_pack(tneg, tneg);
+                        const uint64_t m0 = skr::f2_pack(__uint_as_float(__byte_perm(v.x, 0x4B000000u, 0x7610)),
+                                                         __uint_as_float(__byte_perm(v.x, 0x4B000000u, 0x7632)));
+                        const uint64_t m1 = skr::f2_pack(__uint_as_float(__byte_perm(v.y, 0x4B000000u, 0x7610)),
+                                                         __uint_as_float(__byte_perm(v.y, 0x4B000000u, 0x7632)));
+                        const uint64_t z0 = skr::f2_fma(skr::f2_fma(m0, inc2, neg2), skr::f2_pack(mv[j].x, mv[j].y), skr::f2_pack(sv[j].x, sv[j].y));
+                        const uint64_t z1 = skr::f2_fma(skr::f2_fma(m1, inc2, neg2), skr::f2_pack(mv[j].z, mv[j].w), skr::f2_pack(sv[j].z, sv[j].w));
+                        skr::f2_unpack(z0, x[0], x[1]);
+                        skr::f2_unpack(z1, x[2], x[3]);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) x[e] = log2_post(x[e]);
+                    } else {
                     // indexed shuffles take the source lane modulo 32; counts of kTab and more are fixed up below
                     x[0] = __shfl_sync(0xFFFFFFFFu, treg, (int)v.x);
                     x[1] = __shfl_sync(0xFFFFFFFFu, treg, (int)(v.x >> 16));
@@ -1025,6 +1051,7 @@ __global__ void __launch_bounds__(BatchCfg<K, kSplit>::kThreads, BatchCfg<K, kSp
                         for (int e = 0; e < 4; ++e)
                             if (c4[e] >= kTab) x[e] = slow_bin_value(inc, c4[e], p.log2_pre);
                     }
+                    }
                     if constexpr (kStats) {  // column sums of the plain values (accurate norm_vectors)
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
@@ -1033,13 +1060,7 @@ __global__ void __launch_bounds__(BatchCfg<K, kSplit>::kThreads, BatchCfg<K, kSp
                         }
                     }
                     if constexpr (kAffine) {
-                        // the whole tail in one FFMA2 per two columns, then the hardware log2
-                        const uint64_t z0 = skr::f2_fma(skr::f2_pack(x[0], x[1]), skr::f2_pack(mv[j].x, mv[j].y), skr::f2_pack(sv[j].x, sv[j].y));
-                        const uint64_t z1 = skr::f2_fma(skr::f2_pack(x[2], x[3]), skr::f2_pack(mv[j].z, mv[j].w), skr::f2_pack(sv[j].z, sv[j].w));
-                        skr::f2_unpack(z0, x[0], x[1]);
-                        skr::f2_unpack(z1, x[2], x[3]);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) x[e] = log2_post(x[e]);
+                        // (done above)
                     } else if constexpr (kRegVec) {
                         // mv / sv hold -mean / -std in these flavours (negated once, after the load); FADD2 / FMUL2 /
                         // FFMA2 do two columns per issue slot
@@ -1182,7 +1203,7 @@ int dispatch_batch(const CountParams& wp, int sms, cudaStream_t stream) {
                 return mn7 ? launch_batch<K, false, kBatchPlain, true>(wp, sms, stream)
                            : launch_batch<K, false, kBatchPlain, false>(wp, sms, stream);
             constexpr bool kSp = K == 8;  // k = 8 with vectors: four column passes over a k = 7 sized histogram
-            if (wp.post_cell && wp.post_a) return launch_batch<K, false, kBatchAffine, false, false, false, kSp>(wp, sms, stream);
+            if (wp.post_cell && wp.post_a && !wp.log2_pre) return launch_batch<K, false, kBatchAffine, false, false, false, kSp>(wp, sms, stream);
             if (wp.post_cell) return launch_batch<K, false, kBatchPost, false, false, false, kSp>(wp, sms, stream);
             return mn7 ? launch_batch<K, false, kBatchFast, true, false, false, kSp>(wp, sms, stream)
                        : launch_batch<K, false, kBatchFast, false, false, false, kSp>(wp, sms, stream);
@@ -1205,7 +1226,7 @@ int dispatch_batch(const CountParams& wp, int sms, cudaStream_t stream) {
                              : launch_batch<K, false, kBatchPlain, false>(wp, sms, stream);
         if (fast) return mn ? launch_batch<K, false, kBatchFast, true>(wp, sms, stream)
                             : launch_batch<K, false, kBatchFast, false>(wp, sms, stream);
-        if (post && wp.post_a) return launch_batch<K, false, kBatchAffine, false>(wp, sms, stream);
+        if (post && wp.post_a && !wp.log2_pre) return launch_batch<K, false, kBatchAffine, false>(wp, sms, stream);
         if (post) return launch_batch<K, false, kBatchPost, false>(wp, sms, stream);
     }
     if (wp.colsum) return skr::fail(SKR_ERR_ARG, "skr_count: column sums go with plain counts (no vectors, no Log2.post)");
