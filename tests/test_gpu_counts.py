@@ -430,6 +430,29 @@ def test_deferred_normalisation_is_bit_identical_to_fused():
             assert np.allclose(c.counts, exp, rtol=0, atol=TOL)
 
 
+def test_folded_tail_coefficients():
+    """skr_post_spec_affine: a_j = RN(1/std_j); b_j = the reference's fp32 tail of an empty bin,
+    fl(fl(fl(fl(0 - mean_j) / std_j) + shift) + 1) with shift = |min_j fl(fl(0 - mean_j) / std_j)| -- numpy float32
+    arithmetic gives the same bits, so empty bins of the folded route carry log2 of the reference's own value."""
+    from seekr_b200.kmer_counts import PostSpec
+    rng = np.random.default_rng(17)
+    for k in (2, 6):
+        cols = 4 ** k
+        mean = (rng.random(cols) * 3 + 0.01).astype(np.float32)
+        std = (rng.random(cols) * 2 + 0.05).astype(np.float32)
+        eng = CountEngine(k, "Log2.post")
+        spec = PostSpec(eng, DeviceVector.from_host(mean, cols), DeviceVector.from_host(std, cols))
+        a, b = spec.ab.cpu().numpy()
+        z0 = ((np.float32(0) - mean) / std).astype(np.float32)
+        shift = np.abs(z0.min())
+        assert np.array_equal(a, (1.0 / std.astype(np.float64)).astype(np.float32))
+        assert np.array_equal(b, ((z0 + shift).astype(np.float32) + np.float32(1)).astype(np.float32))
+        assert b.min() == 1.0
+        # float64 vectors do not fold (the generic epilogue evaluates them in binary64)
+        spec64 = PostSpec(eng, DeviceVector.from_host(mean.astype(np.float64), cols), DeviceVector.from_host(std.astype(np.float64), cols))
+        assert spec64.ab is None
+
+
 def test_speculative_post_falls_back_when_the_speculation_fails():
     """The speculated shift is the z-score of a ZERO count in the arg-min column; when no record has a zero there
     the two-pass route behind it must redo the matrix (device-side choice) and give the reference's values."""
