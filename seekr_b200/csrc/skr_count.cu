@@ -1168,6 +1168,195 @@ __global__ void __launch_bounds__(BatchCfg<K, kSplit>::kThreads, BatchCfg<K, kSp
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// count_ws_kernel: the folded Log2.post flavour with the two phases of count_batch_kernel given to different warps.
+// In count_batch_kernel every warp counts, meets the others at a barrier, runs its share of the epilogue and meets
+// them again: a quarter of the warp time is spent at those two barriers (ncu, profiles/r02_ncu_count_details.txt).
+// Here warps 0-6 only count, warp 7 only keeps the books and warps 8-15 only run the epilogue; two histogram sets
+// of kB records circulate between them through mbarriers (meta ready -> counted -> empty), so the counters fill
+// one set while the epilogue drains the other and nobody waits for a phase change.  An epilogue thread owns four
+// bin quads of every record (1024 quads / 256 threads); that is affordable only because the folded tail needs two
+// vectors (a, b: 32 registers) instead of three.
+template <int K, int kB_ = 4, int kSets_ = 2>
+struct WsCfg {
+    static constexpr int kBins = 1 << (2 * K);
+    static constexpr int kHistBytes = kBins * 2;
+    static constexpr int kQuads = kBins / 4;
+    static constexpr int kB = kB_;    // records per histogram set
+    static constexpr int kSets = kSets_;
+    static constexpr int kThreads = 512;
+    static constexpr int kCountWarps = 7;
+    static constexpr int kCounters = kCountWarps * 32;
+    static constexpr int kEpi = 256;
+    static constexpr int kEpiWarps = kEpi / 32;
+    static constexpr int kQc = kQuads / kEpi;
+    static constexpr size_t kSmem = (size_t)(kSets * kB + 1) * kHistBytes;  // + one histogram of alignment slack
+    static_assert(kQuads % kEpi == 0 && kQc >= 1 && kQc <= 4, "whole quads per epilogue thread, vectors in registers");
+};
+
+template <int K, int kB_, int kSets_>
+__global__ void __launch_bounds__(WsCfg<K, kB_, kSets_>::kThreads, 2) count_ws_kernel(const CountParams p) {
+    using Cfg = WsCfg<K, kB_, kSets_>;
+    constexpr int kB = Cfg::kB;
+    constexpr int kSets = Cfg::kSets;
+    if (p.skip_flag && *p.skip_flag == p.skip_value) return;
+    if (p.min_reset && blockIdx.x == 0 && threadIdx.x == 0) { p.min_reset->min_ordered = skr::ordered_encode(INFINITY); p.min_reset->nan_seen = 0; }
+    extern __shared__ __align__(16) uint32_t smem_b[];
+    __shared__ BatchMeta<kB> s_meta[kSets];
+    __shared__ __align__(8) uint64_t s_full[kSets], s_counted[kSets], s_empty[kSets];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t raw_addr = skr::smem_u32(smem_b);
+    const uint32_t hist_addr = (raw_addr + Cfg::kHistBytes - 1) & ~(uint32_t)(Cfg::kHistBytes - 1);
+    {
+        uint4* h4 = reinterpret_cast<uint4*>(smem_b + (hist_addr - raw_addr) / 4);
+        for (int i = tid; i < Cfg::kSets * kB * Cfg::kHistBytes / 16; i += Cfg::kThreads) h4[i] = make_uint4(0, 0, 0, 0);
+    }
+    if (tid == 0) {
+        for (int s = 0; s < kSets; ++s) {
+            skr::mbar_init(&s_full[s], 1);
+            skr::mbar_init(&s_counted[s], Cfg::kCountWarps);
+            skr::mbar_init(&s_empty[s], Cfg::kEpiWarps);
+        }
+        skr::fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp < Cfg::kCountWarps) {
+        // ---- counters ----
+        for (int it = 0;; ++it) {
+            const int s = it % kSets;
+            skr::mbar_wait(&s_full[s], (uint32_t)(it / kSets) & 1u);
+            if (s_meta[s].rec0 < 0) break;
+            count_phase<K, kB, Cfg::kCounters, K, true>(p.codes, p.mask, skr::smem_u32(&s_meta[s]),
+                                                       hist_addr + (uint32_t)(s * kB) * Cfg::kHistBytes, tid, 0u);
+            __syncwarp();
+            if (lane == 0) skr::mbar_arrive(&s_counted[s]);
+        }
+    } else if (warp == Cfg::kCountWarps) {
+        // ---- bookkeeping ----
+        for (int it = 0;; ++it) {
+            const int s = it % kSets;
+            if (it >= kSets) skr::mbar_wait(&s_empty[s], (uint32_t)(it / kSets - 1) & 1u);  // the epilogue is done with this slot
+            BatchMeta<kB>& mt = s_meta[s];
+            long long b = 0;
+            if (lane == 0) b = (long long)atomicAdd(p.work_counter, 1u);
+            b = __shfl_sync(0xFFFFFFFFu, b, 0);
+            const long long rec0 = b * kB;
+            const int nrec = rec0 < p.m ? (int)min((long long)kB, p.m - rec0) : 0;
+            uint32_t units = 0;
+            if (lane < kB) {
+                long long nwin = 0;
+                unsigned long long b0 = 0;
+                int store = 0;
+                if (lane < nrec) {
+                    const long long rec = rec0 + lane;
+                    nwin = (long long)__ldg(p.len + rec) - K + 1;
+                    b0 = __ldg(p.blk_off + rec);
+                    store = 1;
+                    if (nwin > kLongWin) {
+                        p.long_list[atomicAdd(p.long_count, 1u)] = (uint32_t)rec;
+                        store = 0;
+                        nwin = 0;
+                    }
+                    if (nwin < 0) nwin = 0;
+                }
+                const double inc = nwin > 0 ? 1000.0 / (double)nwin : 0.0;
+                const float incf = __double2float_rn(inc);
+                mt.nwin[lane] = nwin;
+                mt.b0[lane] = b0;
+                mt.inc[lane] = inc;
+                mt.store[lane] = store;
+                mt.tab[lane][0] = incf;
+                mt.tab[lane][1] = -8388608.0f * incf;
+                units = (uint32_t)(nwin >> 5);
+            }
+            uint32_t incl = units;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            if (lane < kB) mt.prefix[lane + 1] = incl;
+            if (lane == 0) {
+                mt.prefix[0] = 0;
+                mt.rec0 = nrec > 0 ? rec0 : -1;
+                mt.nrec = nrec;
+                mt.pass = 0;
+            }
+            __syncwarp();
+            if (lane == 0) skr::mbar_arrive(&s_full[s]);
+            if (nrec == 0) break;
+        }
+    } else {
+        // ---- epilogue ----
+        const int et = tid - (Cfg::kThreads - Cfg::kEpi);
+        float4 av[Cfg::kQc], bv[Cfg::kQc];
+#pragma unroll
+        for (int j = 0; j < Cfg::kQc; ++j) {
+            av[j] = __ldg(reinterpret_cast<const float4*>(p.post_a) + et + j * Cfg::kEpi);
+            bv[j] = __ldg(reinterpret_cast<const float4*>(p.post_b) + et + j * Cfg::kEpi);
+        }
+        int zoff = -1;
+        uint32_t zsh = 0, zseen = 0;
+        if (p.spec) {
+            const int zc = p.spec->zero_col;
+            if (zc >= 0 && ((zc >> 2) % Cfg::kEpi) == et) { zoff = (zc >> 1) * 4; zsh = (uint32_t)(zc & 1) * 16u; }
+        }
+        for (int it = 0;; ++it) {
+            const int s = it % kSets;
+            const uint32_t ph = (uint32_t)(it / kSets) & 1u;
+            skr::mbar_wait(&s_full[s], ph);
+            const BatchMeta<kB>& mt = s_meta[s];
+            if (mt.rec0 < 0) break;
+            skr::mbar_wait(&s_counted[s], ph);
+            const int nrec = mt.nrec;
+            for (int r = 0; r < nrec; ++r) {
+                if (!mt.store[r]) continue;
+                const float incf = mt.tab[r][0], nincf = mt.tab[r][1];
+                const uint64_t inc2 = skr::f2_pack(incf, incf), neg2 = skr::f2_pack(nincf, nincf);
+                const uint32_t hrec = hist_addr + (uint32_t)(s * kB + r) * Cfg::kHistBytes;
+                float* __restrict__ orow = reinterpret_cast<float*>(p.out) + (size_t)(mt.rec0 + r) * (size_t)p.ld_out;
+                if (zoff >= 0 && ((lds_u32(hrec + (uint32_t)zoff) >> zsh) & 0xFFFFu) == 0) zseen = 1;
+#pragma unroll
+                for (int j = 0; j < Cfg::kQc; ++j) {
+                    const int q = et + j * Cfg::kEpi;
+                    const uint32_t a = hrec + (uint32_t)q * 8;
+                    const uint2 v = lds_v2(a);
+                    sts_zero_v2(a);
+                    const uint64_t m0 = skr::f2_pack(__uint_as_float(__byte_perm(v.x, 0x4B000000u, 0x7610)),
+                                                     __uint_as_float(__byte_perm(v.x, 0x4B000000u, 0x7632)));
+                    const uint64_t m1 = skr::f2_pack(__uint_as_float(__byte_perm(v.y, 0x4B000000u, 0x7610)),
+                                                     __uint_as_float(__byte_perm(v.y, 0x4B000000u, 0x7632)));
+                    const uint64_t z0 = skr::f2_fma(skr::f2_fma(m0, inc2, neg2), skr::f2_pack(av[j].x, av[j].y), skr::f2_pack(bv[j].x, bv[j].y));
+                    const uint64_t z1 = skr::f2_fma(skr::f2_fma(m1, inc2, neg2), skr::f2_pack(av[j].z, av[j].w), skr::f2_pack(bv[j].z, bv[j].w));
+                    float x[4];
+                    skr::f2_unpack(z0, x[0], x[1]);
+                    skr::f2_unpack(z1, x[2], x[3]);
+                    reinterpret_cast<float4*>(orow)[q] = make_float4(log2_post(x[0]), log2_post(x[1]), log2_post(x[2]), log2_post(x[3]));
+                }
+            }
+            __syncwarp();
+            if (lane == 0) skr::mbar_arrive(&s_empty[s]);
+        }
+        if (zseen) p.spec->zero_seen = p.spec_epoch;
+    }
+}
+
+template <int K, int kB_, int kSets_>
+int launch_ws(const CountParams& wp, int sms, cudaStream_t stream) {
+    using W = WsCfg<K, kB_, kSets_>;
+    auto kern = count_ws_kernel<K, kB_, kSets_>;
+    SKR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W::kSmem));
+    int per_sm = 0;
+    SKR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, W::kThreads, W::kSmem));
+    if (per_sm < 1) return skr::fail(SKR_ERR_CUDA, "count_ws_kernel for k=%d does not fit on this device", K);
+    long long grid = (long long)sms * per_sm;
+    const long long need = (wp.m + W::kB - 1) / W::kB;
+    if (grid > need) grid = need;
+    kern<<<(unsigned)grid, W::kThreads, W::kSmem, stream>>>(wp);
+    return SKR_OK;
+}
+
 template <int K, bool kVecF64, int kMode, bool kMin, bool kColmin = false, bool kStats = false, bool kSplit = false>
 int launch_batch(const CountParams& wp, int sms, cudaStream_t stream) {
     using B = BatchCfg<K, kSplit>;
@@ -1226,7 +1415,18 @@ int dispatch_batch(const CountParams& wp, int sms, cudaStream_t stream) {
                              : launch_batch<K, false, kBatchPlain, false>(wp, sms, stream);
         if (fast) return mn ? launch_batch<K, false, kBatchFast, true>(wp, sms, stream)
                             : launch_batch<K, false, kBatchFast, false>(wp, sms, stream);
-        if (post && wp.post_a && !wp.log2_pre) return launch_batch<K, false, kBatchAffine, false>(wp, sms, stream);
+        if (post && wp.post_a && !wp.log2_pre) {
+            if constexpr (K == 6) {
+                // three sets of four records measured best (S50k, alone): 0.178 ms against 0.195 (two sets of four),
+                // 0.184 (two of six), 0.180 (four of three), 0.193 (six of two) and 0.199 for count_batch_kernel
+                static const int ws = [] { const char* e = getenv("SEEKR_B200_COUNT_WS"); return e ? atoi(e) : 3; }();
+                if (ws == 1) return launch_ws<K, 4, 2>(wp, sms, stream);
+                if (ws == 2) return launch_ws<K, 6, 2>(wp, sms, stream);
+                if (ws == 3) return launch_ws<K, 4, 3>(wp, sms, stream);
+                if (ws == 4) return launch_ws<K, 3, 4>(wp, sms, stream);
+            }
+            return launch_batch<K, false, kBatchAffine, false>(wp, sms, stream);
+        }
         if (post) return launch_batch<K, false, kBatchPost, false>(wp, sms, stream);
     }
     if (wp.colsum) return skr::fail(SKR_ERR_ARG, "skr_count: column sums go with plain counts (no vectors, no Log2.post)");
