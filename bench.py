@@ -907,8 +907,9 @@ def run_ours(args):
                             "h2d_bytes_per_step": p_rows * cols * 4, "d2h_bytes_per_step": p_rows * p_rows * 4}},
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
                      "traffic": ncu_traffic("count_kernel", "skr_count.cu", m == 50000),
-                     "kernel": "count_batch_kernel<6, kBatchPost> (count + per-kb chain + -mean + /std + |min| shift + 1 + log2, "
-                               "one write of the row)", "kernel_ms": k_count,
+                     "kernel": "count_ws_kernel<6> (warp-specialised: count || bookkeeping || epilogue over three histogram sets; "
+                               "the tail (x - mean)/std + |min| + 1 folded into log2(c * inc * a + b), one write of the row)",
+                     "kernel_ms": k_count,
                      "algorithmic_bytes_per_launch": count_bytes, "peak_source": peaks["source"]},
         "cpu_baseline": cpu,
         "e2e": {"value": total_tr / e2e_count_s, "unit": "transcripts/s", "h2d_bytes_per_step": int(slab_bytes + 2 * cols * 4),

@@ -54,13 +54,15 @@ for n, us in sorted(agg.items(), key=lambda kv: -kv[1]):
     print("%10.1f us  %5.1f %%  %s" % (us, 100 * us / tot, n[:120]))
 if len(sys.argv) > 2:
     with open(sys.argv[2], "w") as out:
-        for key in ("count_batch_kernel", "pearson_gemm_kernel"):
-            cand = [(r["us"], start + i) for i, r in enumerate(step) if r["name"].startswith(key)]
+        for key in ("count", "pearson_gemm_kernel"):
+            names = ("count_ws_kernel", "count_batch_kernel") if key == "count" else (key,)
+            cand = [(r["us"], start + i) for i, r in enumerate(step) if r["name"].startswith(names)]
             if not cand:
                 continue
             # the count kernel bench.py's roofline is quoted on is phase B's: the last long one of the step (phase A's
             # plain count comes first and takes about as long)
             long_ones = [c for c in cand if c[0] > 0.5 * max(cand)[0]]
-            at = max(long_ones, key=lambda c: c[1])[1] if key == "count_batch_kernel" else max(cand)[1]
-            skip = sum(1 for r in rows[:at] if r["name"].startswith(key))
-            out.write("%s %d %.1f\n" % (key, skip, rows[at]["us"]))
+            at = max(long_ones, key=lambda c: c[1])[1] if key == "count" else max(cand)[1]
+            base = rows[at]["name"].split("<")[0]
+            skip = sum(1 for r in rows[:at] if r["name"].split("<")[0] == base)
+            out.write("%s %d %.1f\n" % (base, skip, rows[at]["us"]))

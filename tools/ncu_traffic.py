@@ -34,7 +34,7 @@ out = {"_comment": "dram__bytes_read.sum + dram__bytes_write.sum of ONE launch i
                    "tools/ncu_bench.sh); bench.py copies `bytes` into roofline.traffic only when source_sha matches "
                    "the .cu file it was built from"}
 for key, short, source, workload in (
-        ("count_kernel", "count", "skr_count.cu", "S50k, k=6, phase B of the bench step: count_batch_kernel, one-pass Log2.post (folded tail)"),
+        ("count_kernel", "count", "skr_count.cu", "S50k, k=6, phase B of the bench step: count_ws_kernel, one-pass Log2.post (folded tail)"),
         ("pearson_gemm_kernel", "gemm", "skr_pearson.cu", "50k x 50k x 4096, symmetric (tiles on and above the diagonal)")):
     path = os.path.join(ROOT, "gpurun_out", "%s_ncu_%s_raw.csv" % (tag, short))
     try:
