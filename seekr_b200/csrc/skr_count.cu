@@ -1194,7 +1194,7 @@ struct WsCfg {
     static_assert(kQuads % kEpi == 0 && kQc >= 1 && kQc <= 4, "whole quads per epilogue thread, vectors in registers");
 };
 
-template <int K, int kB_, int kSets_>
+template <int K, int kB_, int kSets_, bool kPlain = false>
 __global__ void __launch_bounds__(WsCfg<K, kB_, kSets_>::kThreads, 2) count_ws_kernel(const CountParams p) {
     using Cfg = WsCfg<K, kB_, kSets_>;
     constexpr int kB = Cfg::kB;
@@ -1261,13 +1261,25 @@ __global__ void __launch_bounds__(WsCfg<K, kB_, kSets_>::kThreads, 2) count_ws_k
                     if (nwin < 0) nwin = 0;
                 }
                 const double inc = nwin > 0 ? 1000.0 / (double)nwin : 0.0;
-                const float incf = __double2float_rn(inc);
                 mt.nwin[lane] = nwin;
                 mt.b0[lane] = b0;
                 mt.inc[lane] = inc;
                 mt.store[lane] = store;
-                mt.tab[lane][0] = incf;
-                mt.tab[lane][1] = -8388608.0f * incf;
+                if constexpr (kPlain) {
+                    double acc = 0.0;  // the literal chain of kmer_counts.py:144-150 for counts below kTab
+                    mt.tab[lane][0] = p.log2_pre ? log2f(1.0f) : 0.0f;
+#pragma unroll 8
+                    for (int c = 1; c < kTab; ++c) {
+                        acc = __dadd_rn(acc, inc);
+                        float v = __double2float_rn(acc);
+                        if (p.log2_pre) v = log2f(__fadd_rn(v, 1.0f));
+                        mt.tab[lane][c] = v;
+                    }
+                } else {
+                    const float incf = __double2float_rn(inc);
+                    mt.tab[lane][0] = incf;
+                    mt.tab[lane][1] = -8388608.0f * incf;
+                }
                 units = (uint32_t)(nwin >> 5);
             }
             uint32_t incl = units;
@@ -1291,14 +1303,16 @@ __global__ void __launch_bounds__(WsCfg<K, kB_, kSets_>::kThreads, 2) count_ws_k
         // ---- epilogue ----
         const int et = tid - (Cfg::kThreads - Cfg::kEpi);
         float4 av[Cfg::kQc], bv[Cfg::kQc];
+        if constexpr (!kPlain) {
 #pragma unroll
-        for (int j = 0; j < Cfg::kQc; ++j) {
-            av[j] = __ldg(reinterpret_cast<const float4*>(p.post_a) + et + j * Cfg::kEpi);
-            bv[j] = __ldg(reinterpret_cast<const float4*>(p.post_b) + et + j * Cfg::kEpi);
+            for (int j = 0; j < Cfg::kQc; ++j) {
+                av[j] = __ldg(reinterpret_cast<const float4*>(p.post_a) + et + j * Cfg::kEpi);
+                bv[j] = __ldg(reinterpret_cast<const float4*>(p.post_b) + et + j * Cfg::kEpi);
+            }
         }
         int zoff = -1;
         uint32_t zsh = 0, zseen = 0;
-        if (p.spec) {
+        if (!kPlain && p.spec) {
             const int zc = p.spec->zero_col;
             if (zc >= 0 && ((zc >> 2) % Cfg::kEpi) == et) { zoff = (zc >> 1) * 4; zsh = (uint32_t)(zc & 1) * 16u; }
         }
@@ -1312,7 +1326,8 @@ __global__ void __launch_bounds__(WsCfg<K, kB_, kSets_>::kThreads, 2) count_ws_k
             const int nrec = mt.nrec;
             for (int r = 0; r < nrec; ++r) {
                 if (!mt.store[r]) continue;
-                const float incf = mt.tab[r][0], nincf = mt.tab[r][1];
+                // plain: lane c holds the value of a bin seen c times; folded: lanes 0 / 1 of the row hold inc, -2^23 inc
+                const float incf = mt.tab[r][kPlain ? lane : 0], nincf = kPlain ? 0.0f : mt.tab[r][1];
                 const uint64_t inc2 = skr::f2_pack(incf, incf), neg2 = skr::f2_pack(nincf, nincf);
                 const uint32_t hrec = hist_addr + (uint32_t)(s * kB + r) * Cfg::kHistBytes;
                 float* __restrict__ orow = reinterpret_cast<float*>(p.out) + (size_t)(mt.rec0 + r) * (size_t)p.ld_out;
@@ -1323,16 +1338,32 @@ __global__ void __launch_bounds__(WsCfg<K, kB_, kSets_>::kThreads, 2) count_ws_k
                     const uint32_t a = hrec + (uint32_t)q * 8;
                     const uint2 v = lds_v2(a);
                     sts_zero_v2(a);
+                    float x[4];
+                    if constexpr (kPlain) {
+                        // indexed shuffles take the source lane modulo 32; counts of kTab and more are fixed up below
+                        x[0] = __shfl_sync(0xFFFFFFFFu, incf, (int)v.x);
+                        x[1] = __shfl_sync(0xFFFFFFFFu, incf, (int)(v.x >> 16));
+                        x[2] = __shfl_sync(0xFFFFFFFFu, incf, (int)v.y);
+                        x[3] = __shfl_sync(0xFFFFFFFFu, incf, (int)(v.y >> 16));
+                        if (((v.x | v.y) & ~(uint32_t)((kTab - 1) * 0x10001u)) != 0) {
+                            const uint32_t c4[4] = {v.x & 0xFFFFu, v.x >> 16, v.y & 0xFFFFu, v.y >> 16};
+                            const double inc = mt.inc[r];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (c4[e] >= kTab) x[e] = slow_bin_value(inc, c4[e], p.log2_pre);
+                        }
+                        reinterpret_cast<float4*>(orow)[q] = make_float4(x[0], x[1], x[2], x[3]);
+                    } else {
                     const uint64_t m0 = skr::f2_pack(__uint_as_float(__byte_perm(v.x, 0x4B000000u, 0x7610)),
                                                      __uint_as_float(__byte_perm(v.x, 0x4B000000u, 0x7632)));
                     const uint64_t m1 = skr::f2_pack(__uint_as_float(__byte_perm(v.y, 0x4B000000u, 0x7610)),
                                                      __uint_as_float(__byte_perm(v.y, 0x4B000000u, 0x7632)));
                     const uint64_t z0 = skr::f2_fma(skr::f2_fma(m0, inc2, neg2), skr::f2_pack(av[j].x, av[j].y), skr::f2_pack(bv[j].x, bv[j].y));
                     const uint64_t z1 = skr::f2_fma(skr::f2_fma(m1, inc2, neg2), skr::f2_pack(av[j].z, av[j].w), skr::f2_pack(bv[j].z, bv[j].w));
-                    float x[4];
                     skr::f2_unpack(z0, x[0], x[1]);
                     skr::f2_unpack(z1, x[2], x[3]);
                     reinterpret_cast<float4*>(orow)[q] = make_float4(log2_post(x[0]), log2_post(x[1]), log2_post(x[2]), log2_post(x[3]));
+                    }
                 }
             }
             __syncwarp();
@@ -1342,10 +1373,10 @@ __global__ void __launch_bounds__(WsCfg<K, kB_, kSets_>::kThreads, 2) count_ws_k
     }
 }
 
-template <int K, int kB_, int kSets_>
+template <int K, int kB_, int kSets_, bool kPlain = false>
 int launch_ws(const CountParams& wp, int sms, cudaStream_t stream) {
     using W = WsCfg<K, kB_, kSets_>;
-    auto kern = count_ws_kernel<K, kB_, kSets_>;
+    auto kern = count_ws_kernel<K, kB_, kSets_, kPlain>;
     SKR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W::kSmem));
     int per_sm = 0;
     SKR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, W::kThreads, W::kSmem));
@@ -1411,6 +1442,12 @@ int dispatch_batch(const CountParams& wp, int sms, cudaStream_t stream) {
         }
         if (plain && wp.colmin) return mn ? launch_batch<K, false, kBatchPlain, true, true>(wp, sms, stream)
                                           : launch_batch<K, false, kBatchPlain, false, true>(wp, sms, stream);
+        if (plain && !mn) {
+            if constexpr (K == 6) {  // raw counts: the warp-specialised kernel (the table lookups need no vector registers)
+                static const int ws = [] { const char* e = getenv("SEEKR_B200_COUNT_WS"); return e ? atoi(e) : 3; }();
+                if (ws) return launch_ws<K, 4, 3, true>(wp, sms, stream);
+            }
+        }
         if (plain) return mn ? launch_batch<K, false, kBatchPlain, true>(wp, sms, stream)
                              : launch_batch<K, false, kBatchPlain, false>(wp, sms, stream);
         if (fast) return mn ? launch_batch<K, false, kBatchFast, true>(wp, sms, stream)
