@@ -1176,7 +1176,9 @@ __global__ void __launch_bounds__(BatchCfg<K, kSplit>::kThreads, BatchCfg<K, kSp
 // of kB records circulate between them through mbarriers (meta ready -> counted -> empty), so the counters fill
 // one set while the epilogue drains the other and nobody waits for a phase change.  An epilogue thread owns four
 // bin quads of every record (1024 quads / 256 threads); that is affordable only because the folded tail needs two
-// vectors (a, b: 32 registers) instead of three.
+// vectors (a, b: 32 registers) instead of three.  Raw counts (kPlain: table lookups, no vectors) run here too; the
+// flavour with per-thread column sums was tried and is slower than in count_batch_kernel (0.266 against 0.223 ms:
+// 32 more registers spill and the eight epilogue warps become the bottleneck).
 template <int K, int kB_ = 4, int kSets_ = 2>
 struct WsCfg {
     static constexpr int kBins = 1 << (2 * K);
