@@ -1446,8 +1446,8 @@ int dispatch_batch(const CountParams& wp, int sms, cudaStream_t stream) {
                                           : launch_batch<K, false, kBatchPlain, false, true>(wp, sms, stream);
         if (plain && !mn) {
             if constexpr (K == 6) {  // raw counts: the warp-specialised kernel (the table lookups need no vector registers)
-                static const int ws = [] { const char* e = getenv("SEEKR_B200_COUNT_WS"); return e ? atoi(e) : 3; }();
-                if (ws) return launch_ws<K, 4, 3, true>(wp, sms, stream);
+                const char* e = getenv("SEEKR_B200_COUNT_WS");  // read per launch: tests switch it
+                if (!e || atoi(e) != 0) return launch_ws<K, 4, 3, true>(wp, sms, stream);
             }
         }
         if (plain) return mn ? launch_batch<K, false, kBatchPlain, true>(wp, sms, stream)
@@ -1458,7 +1458,8 @@ int dispatch_batch(const CountParams& wp, int sms, cudaStream_t stream) {
             if constexpr (K == 6) {
                 // three sets of four records measured best (S50k, alone): 0.178 ms against 0.195 (two sets of four),
                 // 0.184 (two of six), 0.180 (four of three), 0.193 (six of two) and 0.199 for count_batch_kernel
-                static const int ws = [] { const char* e = getenv("SEEKR_B200_COUNT_WS"); return e ? atoi(e) : 3; }();
+                const char* e = getenv("SEEKR_B200_COUNT_WS");  // read per launch: tests switch it
+                const int ws = e ? atoi(e) : 3;
                 if (ws == 1) return launch_ws<K, 4, 2>(wp, sms, stream);
                 if (ws == 2) return launch_ws<K, 6, 2>(wp, sms, stream);
                 if (ws == 3) return launch_ws<K, 4, 3>(wp, sms, stream);

@@ -430,6 +430,36 @@ def test_deferred_normalisation_is_bit_identical_to_fused():
             assert np.allclose(c.counts, exp, rtol=0, atol=TOL)
 
 
+def test_warp_specialised_kernel_equals_the_batch_kernel(monkeypatch):
+    """k = 6 raw counts and the folded one-pass Log2.post run count_ws_kernel (counter / bookkeeping / epilogue warps
+    over circulating histogram sets); SEEKR_B200_COUNT_WS=0 sends them through count_batch_kernel.  Same arithmetic,
+    so the bits must agree -- on record counts around the set size, records shorter than k, N runs, lower case, a
+    70 kb record (the long-record list), and with every set shape."""
+    k = 6
+    rng = np.random.default_rng(23)
+    mean = (rng.random(4 ** k) * 0.6 + 0.05).astype(np.float32)
+    std = (rng.random(4 ** k) * 0.5 + 0.2).astype(np.float32)
+    for m in (1, 3, 4, 5, 8, 9, 13, 203):
+        seqs = synth.seq_strings(max(m, 8), seed=300 + m, stress=True, lo=30, hi=4000)[:m]
+        seqs = [s for s in seqs if len(s) != k - 1]
+        if m == 203:
+            seqs[7] = "ACGTTGCA" * 9000          # 72 000 bases: drained by the long-record kernel
+            seqs[11] = "A" * 40000                # one bin counted 39 995 times
+        packed = PackedFasta.from_sequences(seqs, pinned=True)
+        res = {}
+        for ws in ("0", "3", "1", "2", "4"):
+            monkeypatch.setenv("SEEKR_B200_COUNT_WS", ws)
+            eng = CountEngine(k, "Log2.post")
+            dpk = eng.upload(packed)
+            raw, _, _ = CountEngine(k, "Log2.none").run(dpk, False, False)
+            post, _, _ = eng.run(dpk, DeviceVector.from_host(mean, 4 ** k), DeviceVector.from_host(std, 4 ** k))
+            res[ws] = (raw.cpu().numpy().copy(), post.cpu().numpy().copy())
+        for ws in ("3", "1", "2", "4"):
+            assert np.array_equal(res[ws][0], res["0"][0]), (m, ws)
+            assert np.array_equal(res[ws][1], res["0"][1], equal_nan=True), (m, ws)
+        assert np.array_equal(res["3"][0], c_oracle.raw_counts(seqs, k))
+
+
 def test_folded_tail_coefficients():
     """skr_post_spec_affine: a_j = RN(1/std_j); b_j = the reference's fp32 tail of an empty bin,
     fl(fl(fl(fl(0 - mean_j) / std_j) + shift) + 1) with shift = |min_j fl(fl(0 - mean_j) / std_j)| -- numpy float32
