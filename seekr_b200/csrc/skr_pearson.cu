@@ -375,6 +375,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// the same load without the wait: several can be in flight, tmem_wait_ld() covers all of them
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // Tile order: groups of kGroupM tile-rows sweep the tile-columns, so the CTAs running at the same time
 // share a handful of A and B slabs in L2.  Symmetric mode keeps the order but skips tiles below the diagonal.
 __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int symmetric, int& tm, int& tn) {
@@ -552,15 +567,27 @@ pearson_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                 skr::mbar_wait(&tmem_full_bar[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kBN + half * 128);
+                // The drain paces the MMA pipe (the accumulator buffer of chunk i is the one chunk i + 2 needs): two
+                // loads in flight per wait instead of one, and the buffer is handed back as soon as the last load has
+                // landed in registers, before the additions (4 round trips + 128 adds -> 2 round trips before the
+                // arrive).
+                uint32_t v0[32], v1[32];
+                tmem_ld32_nowait(taddr, v0);
+                tmem_ld32_nowait(taddr + 32u, v1);
+                tmem_wait_ld();
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t v[32];
-                    tmem_ld32(taddr + (uint32_t)(c * 32), v);
+                for (int i = 0; i < 32; ++i) sum[i] = __fadd_rn(sum[i], __uint_as_float(v0[i]));
+                tmem_ld32_nowait(taddr + 64u, v0);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) sum[c * 32 + i] = __fadd_rn(sum[c * 32 + i], __uint_as_float(v[i]));
-                }
+                for (int i = 0; i < 32; ++i) sum[32 + i] = __fadd_rn(sum[32 + i], __uint_as_float(v1[i]));
+                tmem_ld32_nowait(taddr + 96u, v1);
+                tmem_wait_ld();
                 tc_fence_before();
                 mbar_arrive_cluster(&tmem_empty_bar[acc], 0);  // the leader's MMA warp owns this barrier
+#pragma unroll
+                for (int i = 0; i < 32; ++i) sum[64 + i] = __fadd_rn(sum[64 + i], __uint_as_float(v0[i]));
+#pragma unroll
+                for (int i = 0; i < 32; ++i) sum[96 + i] = __fadd_rn(sum[96 + i], __uint_as_float(v1[i]));
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
             const long long row = (long long)(tm * kCG + (int)cta_rank) * kBM + quarter * 32 + lane;
