@@ -12,6 +12,8 @@
 // destination is written directly when it is pinned; a pageable destination is reached through a small ring of
 // pinned slots that host threads drain with memcpy (no allocation of result-sized pinned memory on a cold start).
 #include <cuda_runtime.h>
+#include <sys/mman.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
@@ -43,6 +45,21 @@ int get_streams(StreamRes** out) {
     }
     *out = &g_res;
     return SKR_OK;
+}
+
+#ifndef MADV_POPULATE_WRITE
+#define MADV_POPULATE_WRITE 23
+#endif
+
+// A pageable destination that has never been touched costs one page fault per 4 KB inside the copier's memcpy
+// (1.6 s for the 4.1 GB result of 250 000 transcripts); asking the kernel for the whole range of a chunk in one call
+// maps the pages without the per-page trap.  Best effort: older kernels return EINVAL and the memcpy faults as before.
+void prefault_for_write(char* begin, char* end, char* lo, char* hi) {
+    static const uintptr_t page = (uintptr_t)sysconf(_SC_PAGESIZE);
+    uintptr_t a = (uintptr_t)begin & ~(page - 1), b = ((uintptr_t)end + page - 1) & ~(page - 1);
+    if (a < (uintptr_t)lo) a = ((uintptr_t)lo + page - 1) & ~(page - 1);
+    if (b > (uintptr_t)hi) b = (uintptr_t)hi & ~(page - 1);
+    if (b > a) (void)madvise((void*)a, (size_t)(b - a), MADV_POPULATE_WRITE);
 }
 
 struct Chunk {
@@ -145,10 +162,13 @@ extern "C" int skr_stream_counts(SkrPacked* packed, SkrStreamArgs* sa, void* str
                         std::this_thread::yield();
                     }
                     const Chunk& c = chunks[i];
-                    if (cudaEventSynchronize(c.out_done) != cudaSuccess) { copy_fail.store(1); drained[i].store(1); return; }
                     const size_t row = (size_t)cols * 4;
-                    const char* src = slots[c.slot];
                     char* dst = (char*)sa->h_out + (size_t)c.r0 * (size_t)sa->h_ld * 4;
+                    // map the chunk's pages while its rows are still on their way
+                    prefault_for_write(dst, dst + (size_t)(c.r1 - c.r0) * (size_t)sa->h_ld * 4, (char*)sa->h_out,
+                                       (char*)sa->h_out + (size_t)capacity * (size_t)sa->h_ld * 4);
+                    if (cudaEventSynchronize(c.out_done) != cudaSuccess) { copy_fail.store(1); drained[i].store(1); return; }
+                    const char* src = slots[c.slot];
                     if ((size_t)sa->h_ld == (size_t)cols) {
                         memcpy(dst, src, (size_t)(c.r1 - c.r0) * row);
                     } else {
