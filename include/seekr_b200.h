@@ -437,6 +437,17 @@ int skr_min_exchange(SkrMinCell* d_cell, void* const* d_peers, int world, int ra
  * is 60 s, or SEEKR_B200_PEER_TIMEOUT_S. */
 int skr_min_exchange_skip(SkrMinCell* d_cell, void* const* d_peers, int world, int rank, uint64_t epoch,
                           const uint32_t* d_skip, uint32_t skip_value, uint32_t flag_value, int* d_err, void* stream);
+/* skr_flag_or_exchange   OR of one flag per rank (set = *d_flag == flag_value; the OR comes back as flag_value / 0) that
+ *                      does not wait in the common case: a rank whose own flag is set stores its word into every peer and
+ *                      returns -- the OR is already known to it; only a rank whose flag is clear waits for the others.
+ *                      Every word also carries the outcomes of the writer's previous 31 epochs, so that a straggler that
+ *                      finds a peer's slot overwritten by a later epoch still learns what its own epoch turned out to
+ *                      be; d_state (one zero-initialised word per rank, kept by the caller) holds that history.  The
+ *                      peer buffers are those of the minimum exchange, skr_min_exchange_bytes(world) bytes each; the
+ *                      epochs of this exchange count on their own, from 1. */
+int64_t skr_min_exchange_bytes(int world);
+int skr_flag_or_exchange(uint32_t* d_flag, uint32_t flag_value, void* const* d_peers, int world, int rank, uint64_t epoch,
+                         uint32_t* d_state, int* d_err, void* stream);
 /* skr_colstat_exchange   all-reduce(sum) of the n binary64 column partials of skr_col_partial_f64 over the ranks,
  *                      fused with skr_col_finish_f64 (divide by the total row count, optional sqrt, fp32, quality
  *                      flag) in ONE kernel: P2P stores of the partials into every peer, an epoch flag per rank, a

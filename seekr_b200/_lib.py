@@ -134,6 +134,8 @@ SIGNATURES = {
     "skr_peer_free": (_int, [_vp]),
     "skr_min_exchange": (_int, [_vp, _vp, _int, _int, ctypes.c_uint64, _vp, _vp]),
     "skr_min_exchange_skip": (_int, [_vp, _vp, _int, _int, ctypes.c_uint64, _vp, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp]),
+    "skr_min_exchange_bytes": (_i64, [_int]),
+    "skr_flag_or_exchange": (_int, [_vp, ctypes.c_uint32, _vp, _int, _int, ctypes.c_uint64, _vp, _vp, _vp]),
     "skr_colsum_exchange": (_int, [_vp, _vp, _int, _int, ctypes.c_uint64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "skr_colstat_exchange_bytes": (_i64, [_int, _i64]),
     "skr_colstat_exchange": (_int, [_vp, _vp, _int, _int, ctypes.c_uint64, _i64, _i64, _i64, _int, _vp, _vp, _vp, _vp]),

@@ -86,6 +86,52 @@ __global__ void min_exchange_kernel(SkrMinCell* cell, unsigned long long* const*
     }
 }
 
+// OR of one flag per rank WITHOUT waiting in the common case (the speculative Log2.post route: "some record had a
+// zero count in the arg-min column").  A rank whose own flag is set knows the OR already and returns after storing its
+// word into every peer; only a rank whose flag is clear waits for the others.  Because ranks no longer wait for each
+// other every epoch, a waiting rank can find a peer's slot already overwritten by a LATER epoch; every word therefore
+// carries, beside the writer's own flag for its epoch, the OUTCOMES (global ORs) of the writer's previous 31 epochs --
+// a rank only moves on once it knows the outcome of its epoch (own flag set, or learnt by waiting), so a peer that is
+// d epochs ahead can tell a straggler what epoch - d turned out to be.  word = epoch << 32 | outcomes(epoch-31 ..
+// epoch-1) << 1 | own flag; slots [world] after the two parities of the minimum exchange; `state` = this rank's
+// outcome history.  A straggler more than 31 epochs behind sets *err (callers raise).
+__global__ void flag_or_kernel(uint32_t* flag, uint32_t flag_value, unsigned long long* const* peers, int world, int rank,
+                               unsigned long long epoch, uint32_t* state, int* err, unsigned long long kSpinLimitNs) {
+    const int lane = threadIdx.x;
+    const uint32_t mine = *flag == flag_value ? 1u : 0u;
+    const uint32_t hist = *state & 0x7FFFFFFFu;  // bit d - 1 = outcome of epoch - d
+    const unsigned long long word = (epoch << 32) | ((unsigned long long)hist << 1) | mine;
+    const size_t base = (size_t)2 * world;  // behind the minimum exchange's [2][world] words
+    if (lane < world && lane != rank) st_sys_u64(peers[lane] + base + rank, word);
+    uint32_t outcome = mine;
+    if (!mine) {  // nobody here saw it: ask the others
+        uint32_t bit = 0;
+        if (lane < world && lane != rank) {
+            const unsigned long long* slot = peers[rank] + base + lane;
+            const unsigned long long t0 = globaltimer_ns();
+            for (;;) {
+                const unsigned long long w = ld_sys_u64(slot);
+                const unsigned long long we = w >> 32;
+                if (we >= epoch) {
+                    const unsigned long long d = we - epoch;
+                    if (d > 31) atomicExch(err, 1);  // too far ahead to tell
+                    else bit = (uint32_t)(w >> d) & 1u;  // d = 0: its own flag; d > 0: the outcome it recorded for our epoch
+                    break;
+                }
+                if (globaltimer_ns() - t0 > kSpinLimitNs) {
+                    atomicExch(err, 1);
+                    break;
+                }
+            }
+        }
+        outcome = __any_sync(0xFFFFFFFFu, bit) ? 1u : 0u;
+    }
+    if (lane == 0) {
+        if (!mine) *flag = outcome ? flag_value : 0u;
+        *state = ((hist << 1) | outcome) & 0x7FFFFFFFu;
+    }
+}
+
 // All-reduce(sum) of n binary64 column partials fused with the finishing step of the column statistics
 // (skr_col_finish_f64: / total rows, optional sqrt, one rounding to fp32, quality flag).  Exchange buffer of a rank:
 // [2 parities][world][n_cap] doubles, then [2][world] 64-bit flags, then one 32-bit CTA counter.  Every CTA stores
@@ -305,6 +351,21 @@ extern "C" int skr_min_exchange_skip(SkrMinCell* d_cell, void* const* d_peers, i
     if (epoch == 0 || epoch >= (1ull << 31)) return skr::fail(SKR_ERR_ARG, "skr_min_exchange: epoch must be 1 .. 2^31 - 1");
     min_exchange_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_cell, (unsigned long long* const*)d_peers, world, rank, epoch, d_err,
                                                             spin_limit_ns(), d_skip, skip_value ? skip_value : 1u, flag_value);
+    SKR_LAUNCH_CHECK();
+    return SKR_OK;
+}
+
+extern "C" int64_t skr_min_exchange_bytes(int world) { return (int64_t)3 * world * 8; }
+
+extern "C" int skr_flag_or_exchange(uint32_t* d_flag, uint32_t flag_value, void* const* d_peers, int world, int rank,
+                                    uint64_t epoch, uint32_t* d_state, int* d_err, void* stream) {
+    if (!d_flag || !d_peers || !d_state || !d_err) return skr::fail(SKR_ERR_ARG, "skr_flag_or_exchange: null argument");
+    if (world < 1 || world > 32 || rank < 0 || rank >= world)
+        return skr::fail(SKR_ERR_ARG, "skr_flag_or_exchange: world must be 1..32 and 0 <= rank < world");
+    if (epoch == 0 || epoch >= (1ull << 32) || flag_value == 0)
+        return skr::fail(SKR_ERR_ARG, "skr_flag_or_exchange: epoch must be 1 .. 2^32 - 1 and flag_value non-zero");
+    flag_or_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_flag, flag_value, (unsigned long long* const*)d_peers, world, rank, epoch,
+                                                       d_state, d_err, spin_limit_ns());
     SKR_LAUNCH_CHECK();
     return SKR_OK;
 }

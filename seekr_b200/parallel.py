@@ -143,7 +143,13 @@ class PeerMinExchange(_PeerBuffer):
 
         if dist.get_world_size(group) > 32:
             raise ValueError("peer exchange handles up to 32 ranks")
-        super().__init__(2 * dist.get_world_size(group) * 8, group)
+        from . import _lib, device
+
+        import torch
+
+        super().__init__(int(_lib.load().skr_min_exchange_bytes(dist.get_world_size(group))), group)
+        self.flag_epoch = 0                               # the flag exchange counts its epochs on its own
+        self.flag_state = device.zeros(1, torch.int32)    # outcomes of this rank's last 31 flag exchanges
 
     def exchange(self, engine, cell=None, skip=None, flag_value=0):
         """cell: int32 pair on the device seen as a SkrMinCell (default: the engine's minimum cell); skip: a PostSpec,
@@ -157,6 +163,16 @@ class PeerMinExchange(_PeerBuffer):
                                                   device.ptr(skip.flag if skip is not None else None),
                                                   skip.epoch if skip is not None else 0, int(flag_value),
                                                   device.ptr(self.err), device.stream_ptr(engine.stream)))
+
+    def flag_or(self, engine, flag, flag_value):
+        """OR over the ranks of "flag == flag_value" (device uint32 word, written back as flag_value / 0) without
+        waiting when this rank's own flag is set (skr_flag_or_exchange)."""
+        from . import _lib, device
+
+        self.flag_epoch += 1
+        _lib.check(self.lib.skr_flag_or_exchange(device.ptr(flag), int(flag_value), device.ptr(self.table), self.world, self.rank,
+                                                 self.flag_epoch, device.ptr(self.flag_state), device.ptr(self.err),
+                                                 device.stream_ptr(engine.stream)))
 
     def check(self):
         super().check("minimum exchange")
@@ -249,7 +265,25 @@ class _Base:
     def flag_or(self, engine, spec):
         """OR of the "zero seen" flags of the speculative Log2.post route over the ranks: the (zero_col, zero_seen)
         pair is exchanged as a minimum cell (MIN of the identical column index, OR of the flag)."""
+        import os
+
+        if spec.cell.is_cuda and os.environ.get("SEEKR_B200_MIN_EXCHANGE", "peer") != "nccl" and self._get_peer() is not None \
+                and os.environ.get("SEEKR_B200_FLAG_OR", "nowait") != "wait":
+            self._peer.flag_or(engine, spec.flag, spec.epoch)
+            return
         self.min_allreduce(engine, cell=spec.cell, flag_value=spec.epoch)
+
+    def _get_peer(self):
+        """The peer-memory exchange object of this group, or None when CUDA IPC between the ranks is unavailable."""
+        if getattr(self, "_peer", None) is None and not getattr(self, "_peer_failed", False):
+            try:
+                self._peer = _peer_cached("min", self.group, 0, lambda: PeerMinExchange(self.group))
+            except Exception as exc:  # no IPC / no peer access: still a GPU collective, just not ours
+                import warnings
+
+                warnings.warn("peer-memory minimum exchange unavailable (%s); using the NCCL all-reduce" % (exc,))
+                self._peer_failed = True
+        return getattr(self, "_peer", None)
 
     def min_allreduce(self, engine, cell=None, skip=None, flag_value=0):
         """Combine the per-rank Log2.post cells (uint32 pair on the device) across ranks.  On CUDA this is one
@@ -263,15 +297,7 @@ class _Base:
 
         cell = engine.min_cell.t if cell is None else cell  # int32 storage of two uint32
         if cell.is_cuda and os.environ.get("SEEKR_B200_MIN_EXCHANGE", "peer") != "nccl":
-            if getattr(self, "_peer", None) is None and not getattr(self, "_peer_failed", False):
-                try:
-                    self._peer = _peer_cached("min", self.group, 0, lambda: PeerMinExchange(self.group))
-                except Exception as exc:  # no IPC / no peer access: still a GPU collective, just not ours
-                    import warnings
-
-                    warnings.warn("peer-memory minimum exchange unavailable (%s); using the NCCL all-reduce" % (exc,))
-                    self._peer_failed = True
-            if getattr(self, "_peer", None) is not None:
+            if self._get_peer() is not None:
                 self._peer.exchange(engine, cell=cell, skip=skip, flag_value=flag_value)
                 return
         as64 = cell.to(torch.int64) & 0xFFFFFFFF

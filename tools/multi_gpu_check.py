@@ -210,7 +210,41 @@ def main():
         time.sleep(5.0)
     red.min_allreduce(e3)
     red.check()
-    flags = torch.tensor([int(stats_ok), int(spec_ok), int(fail_ok)], device="cuda")
+    # (5) the flag OR that does not wait (skr_flag_or_exchange): truth table, and a rank that is several epochs
+    #     behind peers which never waited for it (their flags were set) and must read the outcomes from their history
+    import time
+
+    peer = red._get_peer()
+    nowait_ok = peer is not None
+    if peer is not None:
+        class _Eng:  # the exchange only needs a stream
+            stream = None
+
+        def flag_or(value, epoch_value):
+            cell = torch.tensor([epoch_value if value else 0], dtype=torch.int32, device="cuda")
+            peer.flag_or(_Eng, cell, epoch_value)
+            torch.cuda.synchronize()
+            return int(cell.item()) == epoch_value
+
+        # every rank set / only rank 0 set / only the last rank set / nobody
+        got_tt = [flag_or(True, 11), flag_or(rank == 0, 12), flag_or(rank == world - 1, 13), flag_or(False, 14)]
+        nowait_ok &= got_tt == [True, True, True, False]
+        dist.barrier()
+        # rank 0 .. world-2 run seven epochs without waiting; the last rank sleeps, then asks with its flag clear
+        if rank == world - 1:
+            time.sleep(2.0)
+        t0 = time.perf_counter()
+        outcomes = [flag_or(rank != world - 1 and (e % 3 != 1), 20 + e) for e in range(7)]
+        dt = time.perf_counter() - t0
+        # epochs with e % 3 == 1: nobody set -> everybody must have waited for the sleeper and got False
+        expect = [e % 3 != 1 for e in range(7)]
+        nowait_ok &= outcomes == expect
+        peer.check()
+        dist.barrier()
+        if rank == 0:
+            print("flag OR without waiting: truth table %s, straggler sequence %s (rank 0 spent %.2f s: it waits only in "
+                  "the epochs nobody set)" % (got_tt, outcomes, dt))
+    flags = torch.tensor([int(stats_ok), int(spec_ok), int(fail_ok), int(nowait_ok)], device="cuda")
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
     if rank == 0:
         print("accurate statistics on shards (peer kernel and NCCL route) vs one GPU: rel diff mean %.1e std %.1e: %s"
@@ -218,6 +252,7 @@ def main():
         print("one-pass Log2.post on shards == one GPU, speculation held: %s" % bool(flags[1].item()))
         print("failing speculation on shards: two-pass route on every rank == one GPU: %s" % bool(flags[2].item()))
         print("exchange with a rank 5 s late: completed")
+        print("flag OR without waiting (truth table, straggler reading the outcome history): %s" % bool(flags[3].item()))
         ok &= bool(flags.min().item())
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)
