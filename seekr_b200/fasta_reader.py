@@ -130,8 +130,10 @@ class PackedFasta:
             nthreads = default_pack_threads()
             if background and nthreads >= 8 and "SEEKR_B200_PACK_THREADS" not in os.environ:
                 # the packer runs beside the thread that drives the copy / count pipeline and the CUDA driver's own
-                # threads: two cores left to them finish earlier than all cores packing (profiles/r02_e2e_waves.txt)
-                nthreads -= 2
+                # threads: with 16 cores, two left to them finish earlier than all cores packing (17.4 against 18.8 ms,
+                # profiles/r02_e2e_waves.txt); with 8 cores per rank one is the better trade (22.4 ms with 7 or 8
+                # threads against 25.4 with 6: the pipeline is pack-bound there)
+                nthreads -= 2 if nthreads >= 12 else 1
         n = len(text)
         if n:
             view = np.frombuffer(text, dtype=np.uint8)
