@@ -110,7 +110,10 @@ extern "C" int skr_stream_counts(SkrPacked* packed, SkrStreamArgs* sa, void* str
     const size_t off_blk = (size_t)((const char*)h_blk - h_slab), off_len = (size_t)((const char*)h_len - h_slab);
 
     // chunks: a small first one so the pipeline fills quickly, then ~chunk_bytes of output each
-    int64_t per = sa->chunk_records > 0 ? sa->chunk_records : std::max<int64_t>(256, ((int64_t)32 << 20) / (cols * 4));
+    int64_t chunk_mb = 32;
+    // experiment knob; 16 ... 96 MB all end within the run-to-run noise of the 32 MB default (17.5 - 19 ms at S50k)
+    if (const char* env = getenv("SEEKR_B200_STREAM_CHUNK_MB")) chunk_mb = std::max(1, atoi(env));
+    int64_t per = sa->chunk_records > 0 ? sa->chunk_records : std::max<int64_t>(256, (chunk_mb << 20) / (cols * 4));
     const bool ring = sa->h_out && !sa->h_out_pinned;
     if (ring) per = std::min<int64_t>(per, std::max<int64_t>(64, ((int64_t)8 << 20) / (cols * 4)));
     const int64_t first = std::max<int64_t>(64, per / 4);
